@@ -113,6 +113,8 @@ def test_tracker_twin_matches_cv2_twin():
         res = tr.result()
         assert np.array_equal(res["ids"], g[f"f{i}_ids"]), f"frame {i}"          # bit-exact IDs
         assert np.array_equal(res["track_cnt"], g[f"f{i}_track_cnt"]), f"frame {i}"
+        if len(res["ids"]) == 0:
+            continue
         assert np.abs(res["cur_pts"] - g[f"f{i}_cur_pts"]).max() <= 1e-3        # px (LK float-lane noise)
         assert np.abs(res["un_pts"] - g[f"f{i}_un_pts"]).max() <= 1e-5
         assert np.abs(res["velocity"] - g[f"f{i}_velocity"]).max() <= 1e-3
