@@ -243,7 +243,7 @@ void orc_lk(const uint8_t* prev, const uint8_t* next, int rows, int cols, int st
     for (auto& L : P) scharr_deriv(L);
     const float half = (win - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (1 << 20);
-    const float epsilon = (float)(eps * eps);  // OpenCV squares criteria.epsilon
+    const double epsilon = eps * eps;  // OpenCV squares criteria.epsilon (stays double)
     std::vector<int16_t> Iw((size_t)win * win), dIw((size_t)win * win * 2);
     for (int i = 0; i < n; i++) status[i] = 1;
     for (int level = nlev; level >= 0; level--) {

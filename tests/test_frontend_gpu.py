@@ -1,0 +1,134 @@
+"""GPU parity tests of the front end: CUDA path (through the C ABI) vs the CPU oracle on the same inputs."""
+import numpy as np
+import pytest
+
+import orc
+from harness import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def FT():
+    from vins_mono_b200 import FeatureTracker
+    return FeatureTracker
+
+
+def _in_border(p, rows, cols):
+    x, y = np.rint(p[:, 0]).astype(int), np.rint(p[:, 1]).astype(int)
+    return (1 <= x) & (x < cols - 1) & (1 <= y) & (y < rows - 1)
+
+
+@pytest.mark.parametrize("shape", [(480, 752), (123, 157), (240, 376)])
+def test_clahe_and_pyramid_bit_exact(FT, shape):
+    rows, cols = shape
+    img = synth.value_noise_image(rows, cols, 21)
+    t = FT(**synth.tracker_config_dict(rows=rows, cols=cols))
+    t.readImage(img, 0.0, False)
+    ref = orc.clahe(img)
+    lvl = 0
+    while True:
+        got = t.debug_level(lvl)
+        assert np.array_equal(got, ref), f"level {lvl}"
+        nxt = orc.pyrdown(ref)
+        if lvl == 3 or nxt.shape[0] <= 21 or nxt.shape[1] <= 21:
+            break
+        ref, lvl = nxt, lvl + 1
+
+
+@pytest.mark.parametrize("shape,seed", [((480, 752), 1), ((480, 752), 2), ((123, 157), 3)])
+def test_gftt_bit_exact(FT, shape, seed):
+    rows, cols = shape
+    img = orc.clahe(synth.value_noise_image(rows, cols, seed))
+    rng = np.random.default_rng(seed)
+    mask = np.full((rows, cols), 255, np.uint8)
+    for _ in range(25):
+        orc.circle(mask, rng.integers(-10, cols + 10), rng.integers(-10, rows + 10), 30)
+    t = FT(**synth.tracker_config_dict(rows=rows, cols=cols, max_cnt=300))
+    for m, maxc in [(mask, 150), (None, 300), (mask, 7)]:
+        ref, ncand_ref = orc.gftt(img, maxc, 0.01, 30, m)
+        got, ncand, eig = t.debug_gftt(img, m, maxc, want_eig=True)
+        assert np.array_equal(eig.view(np.int32), orc.min_eig(img).view(np.int32))   # f32 bit patterns
+        assert ncand == ncand_ref
+        assert np.array_equal(got, ref)                                                # list and order
+
+
+def test_gftt_empty_and_flat(FT):
+    rows, cols = 240, 376
+    t = FT(**synth.tracker_config_dict(rows=rows, cols=cols))
+    flat = np.full((rows, cols), 128, np.uint8)
+    got, ncand, _ = t.debug_gftt(flat, None, 50)
+    assert len(got) == 0 and ncand == 0
+    img = synth.value_noise_image(rows, cols, 4)
+    got, ncand, _ = t.debug_gftt(img, np.zeros((rows, cols), np.uint8), 50)      # everything masked
+    ref, _ = orc.gftt(img, 50, 0.01, 30, np.zeros((rows, cols), np.uint8))
+    assert len(got) == len(ref) == 0
+
+
+@pytest.mark.parametrize("shift", [(3.3, -2.2), (12.5, 7.0), (-25.0, 14.0), (0.4, 0.3)])
+def test_lk_bit_exact(FT, shift):
+    rows, cols = 480, 752
+    big = synth.value_noise_image(rows + 80, cols + 80, 9)
+    a = big[40:40 + rows, 40:40 + cols]
+    # integer part by slicing, fractional part by a bilinear blend
+    ix, iy = int(np.floor(shift[0])), int(np.floor(shift[1]))
+    fx, fy = shift[0] - ix, shift[1] - iy
+    def crop(dx, dy):
+        return big[40 - dy:40 - dy + rows, 40 - dx:40 - dx + cols].astype(np.float32)
+    b = ((1 - fx) * (1 - fy) * crop(ix, iy) + fx * (1 - fy) * crop(ix + 1, iy) + (1 - fx) * fy * crop(ix, iy + 1)
+         + fx * fy * crop(ix + 1, iy + 1))
+    b = np.clip(np.rint(b), 0, 255).astype(np.uint8)
+    pts, _ = orc.gftt(a, 150, 0.01, 30)
+    extra = np.float32([[1.5, 2.5], [750.2, 478.9], [3.0, 400.0], [700.5, 2.2], [0, 0], [751, 479], [375.5, 0.5]])
+    pts = np.vstack([pts, extra]).astype(np.float32)
+    t = FT(**synth.tracker_config_dict(rows=rows, cols=cols, max_cnt=200))
+    got, st = t.debug_lk(a, b, pts)
+    ref, rst = orc.lk(a, b, pts)
+    rst = rst & _in_border(ref, rows, cols).astype(np.uint8)     # the CUDA kernel fuses readImage's inBorder cull
+    assert np.array_equal(st, rst)
+    assert np.array_equal(got.view(np.int32), ref.view(np.int32))  # f32 bit patterns, tracked or not
+    assert rst.sum() > 100
+
+
+def test_tracker_sequence_matches_oracle(FT):
+    """Whole readImage path, 30 frames of a rendered sequence: ids, track counts, pixel coordinates,
+    undistorted coordinates and velocities must be identical (bit patterns) to the CPU oracle."""
+    seq = synth.Sequence(seed=3, duration=2.0)
+    ts, imgs = seq.images(30)
+    cfg = synth.tracker_config_dict()
+    gpu, cpu = FT(**cfg), orc.OracleTracker(cfg)
+    n_pub = 0
+    for i in range(len(ts)):
+        rg, _ = gpu.node_image(imgs[i], float(ts[i]))
+        rc, _ = cpu.node_image(imgs[i], float(ts[i]))
+        assert rg == rc
+        if not rc:
+            continue
+        a, b = gpu.result(), cpu.result()
+        for k in ("ids", "track_cnt"):
+            assert np.array_equal(a[k], b[k]), f"frame {i} {k}"
+        for k in ("cur_pts", "un_pts", "velocity"):
+            assert np.array_equal(a[k].view(np.int32), b[k].view(np.int32)), f"frame {i} {k}"
+        n_pub += rc == 2
+    assert n_pub >= 10 and len(a["ids"]) > 100 and a["ids"].max() > 160
+
+
+def test_full_size_properties(FT):
+    """BASELINE-size run: properties that need no oracle — ids unique and monotone in age, min distance
+    respected between surviving tracks at publish frames, published points all have track_cnt > 1."""
+    seq = synth.Sequence(seed=5, duration=3.0)
+    ts, imgs = seq.images(40)
+    t = FT(**synth.tracker_config_dict())
+    for i in range(len(ts)):
+        r, _ = t.node_image(imgs[i], float(ts[i]))
+        if r == 0:
+            continue
+        res = t.result()
+        assert len(set(res["ids"].tolist())) == len(res["ids"]) <= 150
+        assert (res["track_cnt"] >= 1).all()
+        if r == 2:
+            msg = t.feature_message()
+            assert len(msg) == int((res["track_cnt"] > 1).sum())
+            p = np.rint(res["cur_pts"]).astype(int)
+            d = np.abs(p[:, None, :] - p[None, :, :]).max(-1) + np.eye(len(p), dtype=int) * 1000
+            assert d.min() >= 15  # discs of radius 30 keep rounded points apart (Chebyshev >= 21 on the raster)
