@@ -158,3 +158,116 @@ class OracleTracker:
         s = np.zeros(5, np.int32)
         lib().orc_tracker_stats(self.h, P(s, i32p))
         return dict(lk_in=int(s[0]), lk_ok=int(s[1]), ransac_in=int(s[2]), ransac_ok=int(s[3]), new=int(s[4]))
+
+
+# ------------------------------------------------------------------------------------------------
+# back end
+class BeConfig(C.Structure):
+    _fields_ = [("window_size", C.c_int), ("num_iterations", C.c_int), ("estimate_extrinsic", C.c_int),
+                ("estimate_td", C.c_int), ("focal_length", C.c_double), ("min_parallax", C.c_double),
+                ("acc_n", C.c_double), ("gyr_n", C.c_double), ("acc_w", C.c_double), ("gyr_w", C.c_double),
+                ("g_norm", C.c_double), ("init_depth", C.c_double), ("td", C.c_double), ("tr", C.c_double),
+                ("row", C.c_double), ("tic", C.c_double * 3), ("ric", C.c_double * 9)]
+
+
+def be_config(window_size=10, num_iterations=8, estimate_extrinsic=0, estimate_td=0, td=0.0, tr=0.0, row=480.0,
+              tic=None, ric=None):
+    from harness import synth
+    c = BeConfig(window_size=window_size, num_iterations=num_iterations, estimate_extrinsic=estimate_extrinsic,
+                 estimate_td=estimate_td, focal_length=460.0, min_parallax=10.0 / 460.0, acc_n=synth.ACC_N,
+                 gyr_n=synth.GYR_N, acc_w=synth.ACC_W, gyr_w=synth.GYR_W, g_norm=synth.G_NORM, init_depth=5.0, td=td,
+                 tr=tr, row=row)
+    c.tic[:] = list(synth.TIC if tic is None else tic)
+    c.ric[:] = list(np.asarray(synth.RIC if ric is None else ric).ravel())
+    return c
+
+
+def _d(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+def preintegrate(cfg, ba, bg, dt, acc, gyr, want_sqrt_info=True):
+    dt, acc, gyr = _d(dt), _d(acc), _d(gyr)
+    out, jac, cov, si = np.zeros(11), np.zeros((15, 15)), np.zeros((15, 15)), np.zeros((15, 15))
+    lib().orc_preintegrate(C.byref(cfg), P(_d(ba), f64p), P(_d(bg), f64p), len(dt), P(dt, f64p), P(acc, f64p), P(gyr, f64p),
+                           P(out, f64p), P(jac, f64p), P(cov, f64p), P(si, f64p) if want_sqrt_info else None)
+    return dict(sum_dt=out[0], delta_p=out[1:4], delta_q=out[4:8], delta_v=out[8:11], jacobian=jac, covariance=cov,
+                sqrt_info=si)
+
+
+def imu_factor(cfg, ba, bg, dt, acc, gyr, params32):
+    dt, acc, gyr, p = _d(dt), _d(acc), _d(gyr), _d(params32)
+    res, raw = np.zeros(15), np.zeros(15)
+    J = [np.zeros((15, 7)), np.zeros((15, 9)), np.zeros((15, 7)), np.zeros((15, 9))]
+    lib().orc_imu_factor(C.byref(cfg), P(_d(ba), f64p), P(_d(bg), f64p), len(dt), P(dt, f64p), P(acc, f64p), P(gyr, f64p),
+                         P(p, f64p), P(res, f64p), P(raw, f64p), *[P(j, f64p) for j in J])
+    return res, raw, J
+
+
+def projection_factor(params23, data, use_td=False, focal_length=460.0, TR=0.0, ROW=480.0):
+    p, d = _d(params23), _d(data)
+    res = np.zeros(2)
+    J = [np.zeros((2, 7)), np.zeros((2, 7)), np.zeros((2, 7)), np.zeros((2, 1)), np.zeros((2, 1))]
+    lib().orc_projection_factor(int(use_td), C.c_double(focal_length), C.c_double(TR), C.c_double(ROW), P(p, f64p), P(d, f64p),
+                                P(res, f64p), *[P(j, f64p) for j in J])
+    return res, J
+
+
+def pose_plus(x, delta):
+    out = np.zeros(7)
+    lib().orc_pose_plus(P(_d(x), f64p), P(_d(delta), f64p), P(out, f64p))
+    return out
+
+
+def sym_eigen(A):
+    A = _d(A)
+    n = A.shape[0]
+    w, V = np.zeros(n), np.zeros((n, n))
+    lib().orc_sym_eigen(n, P(A, f64p), P(w, f64p), P(V, f64p))
+    return w, V
+
+
+class OracleEstimator:
+    """Estimator twin (oracle/be_estimator.cpp)."""
+
+    def __init__(self, cfg):
+        lib().orc_est_create.restype = C.c_void_p
+        self.cfg = cfg
+        self.W = cfg.window_size
+        self.h = C.c_void_p(lib().orc_est_create(C.byref(cfg)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_est_destroy(self.h)
+            self.h = None
+
+    def set_seed(self, rows, ba, bg):
+        rows = _d(rows)
+        lib().orc_est_set_seed(self.h, len(rows), P(rows, f64p), P(_d(ba), f64p), P(_d(bg), f64p))
+
+    def processIMU(self, dt, acc, gyr):
+        lib().orc_est_process_imu(self.h, C.c_double(dt), P(_d(acc), f64p), P(_d(gyr), f64p))
+
+    def processImage(self, ids, xyz_uv_vel, stamp):
+        ids = np.ascontiguousarray(ids, np.int32)
+        d = _d(xyz_uv_vel)
+        lib().orc_est_process_image(self.h, len(ids), P(ids, i32p), P(d, f64p), C.c_double(stamp))
+
+    def info(self):
+        o, c = np.zeros(10, np.int32), np.zeros(2)
+        lib().orc_est_info(self.h, P(o, i32p), P(c, f64p))
+        keys = ["solver_flag", "frame_count", "marginalization_flag", "n_solves", "n_reboots", "landmarks", "visual",
+                "iterations", "successful_steps", "termination"]
+        d = {k: int(v) for k, v in zip(keys, o)}
+        d["initial_cost"], d["final_cost"] = float(c[0]), float(c[1])
+        return d
+
+    def states(self):
+        out, td = np.zeros((self.W + 1, 16)), C.c_double(0)
+        lib().orc_est_states(self.h, P(out, f64p), C.byref(td))
+        return out, td.value
+
+    def prior(self, cap=256):
+        A, b = np.zeros((cap, cap)), np.zeros(cap)
+        n = lib().orc_est_prior(self.h, cap, P(A, f64p), P(b, f64p))
+        return A.ravel()[: n * n].reshape(n, n).copy(), b[:n].copy()
