@@ -234,3 +234,56 @@ def value_noise_image(rows, cols, seed):
     img = (img - img.min()) / (img.max() - img.min())
     img = 30 + 195 * img + rng.normal(0, 2, (rows, cols))
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def track_messages(seq: Sequence, n_pub: int, n_points: int = 2500, max_feats: int = 150, pub_hz: float = 10.0, pixel_sigma: float = 0.3,
+                   start_id: int = 0):
+    """Feature messages (stamp, ids, xyz_uv_vel[n,7]) made directly from the scene geometry (no images), in the
+    spirit of the reference's data_generator (data_generator/src/data_generator.cpp:11-59): random landmarks on
+    the room walls, projected through the EuRoC pinhole+radtan model, at most `max_feats` per frame with stable
+    ids, pixel noise sigma `pixel_sigma`.  Back-end tests/benchmarks use this to avoid rendering."""
+    rng = np.random.default_rng(5000 + seq.seed)
+    lo, hi = seq.room_lo, seq.room_hi
+    pts = []
+    for _ in range(n_points):
+        ax = int(rng.integers(0, 3))
+        p = rng.uniform(lo, hi)
+        p[ax] = lo[ax] if rng.random() < 0.5 else hi[ax]
+        pts.append(p)
+    pts = np.array(pts)
+
+    def project(t):
+        p, R, *_ = seq.pose(t)
+        Pc = ((pts - (p + R @ TIC)) @ (R @ RIC))  # rows: R_wc^T (X - o)
+        z = Pc[:, 2]
+        x, y = Pc[:, 0] / z, Pc[:, 1] / z
+        r2 = x * x + y * y
+        rad = K1 * r2 + K2 * r2 * r2
+        xd = x + x * rad + 2 * P1 * x * y + P2 * (r2 + 2 * x * x)
+        yd = y + y * rad + 2 * P2 * x * y + P1 * (r2 + 2 * y * y)
+        u, v = FX * xd + CX, FY * yd + CY
+        vis = (z > 0.3) & (u > 5) & (u < COLS - 5) & (v > 5) & (v < ROWS - 5) & (r2 < 1.2)
+        return np.c_[x, y], np.c_[u, v], vis
+
+    active = []
+    msgs = []
+    noise = {}
+    for k in range(n_pub):
+        t = seq.t0 + (k + 2) / pub_hz
+        un, uv, vis = project(t)
+        un_prev, _, _ = project(t - 0.05)
+        active = [i for i in active if vis[i]]
+        if len(active) < max_feats:
+            cand = [i for i in np.nonzero(vis)[0] if i not in active]
+            rng.shuffle(cand)
+            active += cand[: max_feats - len(active)]
+        ids = np.array(sorted(active), np.int32)
+        d = np.zeros((len(ids), 7))
+        for r, i in enumerate(ids):
+            e = rng.normal(0, pixel_sigma, 2)
+            d[r, 0:2] = un[i] + e / 460.0
+            d[r, 2] = 1.0
+            d[r, 3:5] = uv[i] + e
+            d[r, 5:7] = (un[i] - un_prev[i]) / 0.05
+        msgs.append((float(t), ids + start_id, d))
+    return msgs

@@ -743,3 +743,26 @@ void orc_sym_eigen(int n, const double* A, double* w, double* V) {
 }
 
 }  // extern "C"
+
+// kept blocks of the last prior, (type, index after addr_shift, offset, local size) each; returns the block count
+extern "C" int orc_est_prior_blocks(void* h, int* out4) {
+    Estimator* e = (Estimator*)h;
+    if (!e->last_marginalization_info) return 0;
+    const MarginalizationInfo* mi = e->last_marginalization_info.get();
+    const int nb = (int)mi->keep_block_size.size();
+    for (int k = 0; k < nb; k++) {
+        double* addr = e->last_marginalization_parameter_blocks[k];
+        int type = -1, index = 0;
+        for (int i = 0; i <= e->W; i++) {
+            if (addr == e->para_Pose[i].data()) type = 0, index = i;
+            if (addr == e->para_SpeedBias[i].data()) type = 1, index = i;
+        }
+        if (addr == e->para_Ex_Pose.data()) type = 2;
+        if (addr == e->para_Td.data()) type = 3;
+        out4[4 * k] = type;
+        out4[4 * k + 1] = index;
+        out4[4 * k + 2] = mi->keep_block_idx[k] - mi->m;
+        out4[4 * k + 3] = MarginalizationInfo::localSize(mi->keep_block_size[k]);
+    }
+    return nb;
+}

@@ -268,6 +268,9 @@ class OracleEstimator:
         return out, td.value
 
     def prior(self, cap=256):
-        A, b = np.zeros((cap, cap)), np.zeros(cap)
+        """(A', b', blocks) of the last marginalisation; blocks = [(type, index, offset, size)]."""
+        A, b = np.zeros(cap * cap), np.zeros(cap)
         n = lib().orc_est_prior(self.h, cap, P(A, f64p), P(b, f64p))
-        return A.ravel()[: n * n].reshape(n, n).copy(), b[:n].copy()
+        blk = np.zeros(4 * 64, np.int32)
+        nb = lib().orc_est_prior_blocks(self.h, P(blk, i32p))
+        return A[: n * n].reshape(n, n).copy(), b[:n].copy(), [tuple(int(v) for v in blk[4 * k:4 * k + 4]) for k in range(nb)]

@@ -1,0 +1,1263 @@
+// Sliding-window BA kernels for sm_100a, float64.
+//
+//   preint_push_kernel    IntegrationBase::propagate / midPointIntegration     integration_base.h:54-158
+//   sqrt_info_kernel      LLT(covariance^-1).matrixL().transpose()            imu_factor.h:64
+//   ba_linearize_kernel   factor Evaluate() + Cauchy corrector + J^T J / J^T r accumulation; one warp per
+//                         landmark (lanes = its observations), one warp per IMU factor, one CTA for the prior;
+//                         the last CTA to finish runs the trust-region accept/reject logic
+//   ba_schur_kernel       landmark elimination S = Hpp - Hpl^T (Hll + mu E)^-1 Hpl as a dense tiled SYRK
+//                         (deterministic summation order), plus the reduced gradient
+//   ba_step_kernel        Jacobi scaling, dogleg (Cauchy point, regularised Gauss-Newton via in-shared-memory
+//                         Cholesky), model cost change, candidate point x (+) delta
+//   marg_build_kernel / marg_solve_kernel   MarginalizationInfo::preMarginalize + marginalize
+//                         (marginalization_factor.cpp:110-297) producing the new prior in information form
+// The solve replaces ceres::Solve(DENSE_SCHUR, DOGLEG) at estimator.cpp:803-818; no wall-clock cap.
+// Everything here is small dense float64 algebra: latency bound for one sequence, HBM bound in batches;
+// B200's FP64 pipe is far from saturated, so no tensor-core path is used.
+#include "ba_kernels.h"
+
+#include <cfloat>
+
+#include "ba_device.cuh"
+
+namespace vb {
+
+// ------------------------------------------------------------------------------------------------
+// IMU pre-integration: appends n samples (dt, acc[3], gyr[3]) to one slot.  Single CTA of 256 threads;
+// the 15x15 products run in parallel, the 3x3 geometry of each step on thread 0.
+__global__ void __launch_bounds__(256) preint_push_kernel(PreInt* __restrict__ slot, int n, const double* __restrict__ samples,
+                                                          double acc_n, double gyr_n, double acc_w, double gyr_w) {
+    __shared__ double F[225], V[270], J[225], P[225], T[225], nz[18];
+    __shared__ double st[20];  // dp dq dv acc0 gyr0
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 225; i += 256) {
+        J[i] = slot->jac[i];
+        P[i] = slot->cov[i];
+    }
+    if (tid < 18) nz[tid] = tid < 3 ? acc_n * acc_n : tid < 6 ? gyr_n * gyr_n : tid < 9 ? acc_n * acc_n : tid < 12 ? gyr_n * gyr_n : tid < 15 ? acc_w * acc_w : gyr_w * gyr_w;
+    if (tid == 0) {
+        for (int i = 0; i < 3; i++) { st[i] = slot->dp[i]; st[7 + i] = slot->dv[i]; st[10 + i] = slot->acc0[i]; st[13 + i] = slot->gyr0[i]; }
+        for (int i = 0; i < 4; i++) st[3 + i] = slot->dq[i];
+        st[16] = slot->sum_dt;
+    }
+    __syncthreads();
+    const V3d ba = mk(slot->ba[0], slot->ba[1], slot->ba[2]), bg = mk(slot->bg[0], slot->bg[1], slot->bg[2]);
+    for (int k = 0; k < n; k++) {
+        for (int i = tid; i < 225; i += 256) F[i] = 0.0;
+        for (int i = tid; i < 270; i += 256) V[i] = 0.0;
+        __syncthreads();
+        if (tid == 0) {
+            const double dt = samples[7 * k];
+            const V3d a1 = mk(samples[7 * k + 1], samples[7 * k + 2], samples[7 * k + 3]);
+            const V3d g1 = mk(samples[7 * k + 4], samples[7 * k + 5], samples[7 * k + 6]);
+            const V3d a0 = mk(st[10], st[11], st[12]), g0 = mk(st[13], st[14], st[15]);
+            const V3d dp = mk(st[0], st[1], st[2]), dv = mk(st[7], st[8], st[9]);
+            const Q4 dq = Q4{st[3], st[4], st[5], st[6]};
+            const V3d un_acc_0 = qrot(dq, a0 - ba);
+            const V3d un_gyr = 0.5 * (g0 + g1) - bg;
+            const Q4 rq = qmul(dq, Q4{1, un_gyr.x * dt / 2, un_gyr.y * dt / 2, un_gyr.z * dt / 2});
+            const V3d un_acc_1 = qrot(rq, a1 - ba);
+            const V3d un_acc = 0.5 * (un_acc_0 + un_acc_1);
+            const V3d rdp = dp + dv * dt + 0.5 * un_acc * dt * dt;
+            const V3d rdv = dv + un_acc * dt;
+            const M3d Rwx = skew(un_gyr), Ra0 = skew(a0 - ba), Ra1 = skew(a1 - ba);
+            const M3d Rq = qR(dq), Rr = qR(rq), I = mident();
+            const M3d ImW = msub(I, mscale(Rwx, dt));
+            auto putF = [&](int r0, int c0, const M3d& b) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) F[(r0 + i) * 15 + c0 + j] = b.m[3 * i + j]; };
+            auto putV = [&](int r0, int c0, const M3d& b) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) V[(r0 + i) * 18 + c0 + j] = b.m[3 * i + j]; };
+            const M3d RqA0 = mmul(Rq, Ra0), RrA1 = mmul(Rr, Ra1), RrA1W = mmul(RrA1, ImW);
+            putF(0, 0, I);
+            putF(0, 3, madd(mscale(RqA0, -0.25 * dt * dt), mscale(RrA1W, -0.25 * dt * dt)));
+            putF(0, 6, mscale(I, dt));
+            putF(0, 9, mscale(madd(Rq, Rr), -0.25 * dt * dt));
+            putF(0, 12, mscale(RrA1, -0.25 * dt * dt * -dt));
+            putF(3, 3, ImW);
+            putF(3, 12, mscale(I, -1.0 * dt));
+            putF(6, 3, madd(mscale(RqA0, -0.5 * dt), mscale(RrA1W, -0.5 * dt)));
+            putF(6, 6, I);
+            putF(6, 9, mscale(madd(Rq, Rr), -0.5 * dt));
+            putF(6, 12, mscale(RrA1, -0.5 * dt * -dt));
+            putF(9, 9, I);
+            putF(12, 12, I);
+            const M3d v03 = mscale(RrA1, 0.25 * -1.0 * dt * dt * 0.5 * dt), v63 = mscale(RrA1, 0.5 * -1.0 * dt * 0.5 * dt);
+            putV(0, 0, mscale(Rq, 0.25 * dt * dt));
+            putV(0, 3, v03);
+            putV(0, 6, mscale(Rr, 0.25 * dt * dt));
+            putV(0, 9, v03);
+            putV(3, 3, mscale(I, 0.5 * dt));
+            putV(3, 9, mscale(I, 0.5 * dt));
+            putV(6, 0, mscale(Rq, 0.5 * dt));
+            putV(6, 3, v63);
+            putV(6, 6, mscale(Rr, 0.5 * dt));
+            putV(6, 9, v63);
+            putV(9, 12, mscale(I, dt));
+            putV(12, 15, mscale(I, dt));
+            const Q4 nq = qnormalized(rq);
+            st[0] = rdp.x; st[1] = rdp.y; st[2] = rdp.z;
+            st[3] = nq.w; st[4] = nq.x; st[5] = nq.y; st[6] = nq.z;
+            st[7] = rdv.x; st[8] = rdv.y; st[9] = rdv.z;
+            st[10] = a1.x; st[11] = a1.y; st[12] = a1.z;
+            st[13] = g1.x; st[14] = g1.y; st[15] = g1.z;
+            st[16] += dt;
+        }
+        __syncthreads();
+        if (tid < 225) {  // T = F * J ; then J = T
+            const int i = tid / 15, j = tid % 15;
+            double s = 0;
+            for (int q = 0; q < 15; q++) s += F[i * 15 + q] * J[q * 15 + j];
+            T[tid] = s;
+        }
+        __syncthreads();
+        if (tid < 225) J[tid] = T[tid];
+        __syncthreads();
+        if (tid < 225) {  // T = F * P
+            const int i = tid / 15, j = tid % 15;
+            double s = 0;
+            for (int q = 0; q < 15; q++) s += F[i * 15 + q] * P[q * 15 + j];
+            T[tid] = s;
+        }
+        __syncthreads();
+        if (tid < 225) {  // P = T * F^T + V N V^T
+            const int i = tid / 15, j = tid % 15;
+            double s = 0;
+            for (int q = 0; q < 15; q++) s += T[i * 15 + q] * F[j * 15 + q];
+            double v = 0;
+            for (int q = 0; q < 18; q++) v += V[i * 18 + q] * nz[q] * V[j * 18 + q];
+            P[tid] = s + v;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < 225; i += 256) {
+        slot->jac[i] = J[i];
+        slot->cov[i] = P[i];
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 3; i++) { slot->dp[i] = st[i]; slot->dv[i] = st[7 + i]; slot->acc0[i] = st[10 + i]; slot->gyr0[i] = st[13 + i]; }
+        for (int i = 0; i < 4; i++) slot->dq[i] = st[3 + i];
+        slot->sum_dt = st[16];
+    }
+}
+
+// sqrt_info = chol_lower(cov^-1)^T for each listed slot (one warp each; Gauss-Jordan with partial pivoting).
+__global__ void __launch_bounds__(32) sqrt_info_kernel(PreInt* __restrict__ slots, const int* __restrict__ which, int count) {
+    __shared__ double A[15][31];
+    __shared__ double Lm[15][15];
+    const int lane = threadIdx.x;
+    if ((int)blockIdx.x >= count) return;
+    PreInt* s = slots + which[blockIdx.x];
+    for (int i = lane; i < 225; i += 32) {
+        A[i / 15][i % 15] = s->cov[i];
+        A[i / 15][15 + i % 15] = (i / 15 == i % 15) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+    for (int k = 0; k < 15; k++) {
+        int piv = k;
+        double best = fabs(A[k][k]);
+        for (int i = k + 1; i < 15; i++)
+            if (fabs(A[i][k]) > best) best = fabs(A[i][k]), piv = i;
+        if (piv != k && lane < 30) {
+            const double t = A[k][lane];
+            A[k][lane] = A[piv][lane];
+            A[piv][lane] = t;
+        }
+        __syncwarp();
+        const double pv = A[k][k];
+        __syncwarp();
+        if (lane < 30) A[k][lane] /= pv;
+        __syncwarp();
+        for (int i = 0; i < 15; i++) {
+            if (i == k) continue;
+            const double f = A[i][k];
+            __syncwarp();
+            if (lane < 30) A[i][lane] -= f * A[k][lane];
+            __syncwarp();
+        }
+    }
+    // A[:,15:30] = cov^-1 ; lower Cholesky
+    for (int j = 0; j < 15; j++) {
+        double sdiag = A[j][15 + j];
+        for (int k = 0; k < j; k++) sdiag -= Lm[j][k] * Lm[j][k];
+        const double ljj = sqrt(sdiag);
+        __syncwarp();
+        if (lane == 0) Lm[j][j] = ljj;
+        if (lane > j && lane < 15) {
+            double t = 0.5 * (A[lane][15 + j] + A[j][15 + lane]);
+            for (int k = 0; k < j; k++) t -= Lm[lane][k] * Lm[j][k];
+            Lm[lane][j] = t / ljj;
+        }
+        if (lane < j) Lm[lane][j] = 0.0;
+        __syncwarp();
+    }
+    for (int i = lane; i < 225; i += 32) s->sqrt_info[i] = Lm[i % 15][i / 15];  // transpose
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ba_zero_kernel(BaProblem p, int initial) {
+    const SolverState* st = p.st;
+    if (!initial && (st->done || !st->cand_valid)) return;
+    const int b = initial ? st->cur : 1 - st->cur;
+    const BaAccum a = p.acc[b];
+    const int D = p.dims.D, L = p.dims.L;
+    const size_t n1 = (size_t)D * D, n2 = (size_t)L * D;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + D + 2 * (size_t)L + 1; i += stride) {
+        if (i < n1) a.Hpp[i] = 0.0;
+        else if (i < n1 + n2) a.Hpl[i - n1] = 0.0;
+        else if (i < n1 + n2 + D) a.gp[i - n1 - n2] = 0.0;
+        else if (i < n1 + n2 + D + L) a.Hll[i - n1 - n2 - D] = 0.0;
+        else if (i < n1 + n2 + D + 2 * (size_t)L) a.gl[i - n1 - n2 - D - L] = 0.0;
+        else a.cost[0] = 0.0;
+    }
+}
+
+namespace {
+
+// Trust-region bookkeeping after a point has been evaluated (Ceres TrustRegionMinimizer: iteration zero,
+// ParameterToleranceReached, FunctionToleranceReached, IsStepSuccessful, Handle(Un)SuccessfulStep and
+// DoglegStrategy::StepAccepted / StepRejected).
+__device__ void decide(const BaProblem& p, int initial) {
+    SolverState* st = p.st;
+    if (initial) {
+        const double c = *(volatile double*)p.acc[st->cur].cost;
+        st->x_cost = c;
+        st->initial_cost = c;
+        return;
+    }
+    const double cand = *(volatile double*)p.acc[1 - st->cur].cost;
+    st->cand_cost = cand;
+    if (st->step_norm <= 1e-8 * (st->x_norm + 1e-8)) {
+        st->done = 2;
+        return;
+    }
+    const double cost_change = st->x_cost - cand;
+    if (fabs(cost_change) <= 1e-6 * st->x_cost) {
+        st->done = 3;
+        return;
+    }
+    const double rho = cost_change / st->model_cost_change;
+    if (rho > 1e-3) {
+        st->cur = 1 - st->cur;
+        st->x_cost = cand;
+        st->successful++;
+        if (rho < 0.25) st->radius *= 0.5;
+        if (rho > 0.75) st->radius = fmax(st->radius, 3.0 * st->dogleg_step_norm);
+        st->mu = fmax(1e-8, 2.0 * st->mu / 10.0);
+        st->reuse = 0;
+    } else {
+        st->radius *= 0.5;
+        st->reuse = 1;
+    }
+    if (st->iteration >= st->max_iterations) st->done = 1;
+}
+
+__device__ __forceinline__ void lin_visual(const BaProblem& p, const BaStates& x, const BaAccum& a, int l, int lane) {
+    const BaDims& d = p.dims;
+    const int D = d.D;
+    const int s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0;
+    const int fi = p.lm_anchor[l];
+    const bool has = lane < nobs;
+    VisualEval e;
+    int fj = fi;
+    if (has) {
+        const int o = s0 + lane;
+        fj = p.ob_frame[o];
+        eval_visual(d, x.pose + 7 * fi, x.pose + 7 * fj, x.ex, x.lam[l], d.est_td ? x.td[0] : 0.0, p.lm_pts[2 * l], p.lm_pts[2 * l + 1],
+                    p.ob_pts[2 * o], p.ob_pts[2 * o + 1], p.lm_vel[2 * l], p.lm_vel[2 * l + 1], p.ob_vel[2 * o], p.ob_vel[2 * o + 1],
+                    p.lm_td[l], p.ob_td[o], p.lm_row[l], p.ob_row[o], true, true, e);
+    } else {
+        e.r[0] = e.r[1] = 0;
+        e.half_rho = 0;
+#pragma unroll
+        for (int k = 0; k < 20; k++) e.J[0][k] = e.J[1][k] = 0;
+    }
+    const int ci = 6 * fi, cj = 6 * fj;
+    double v = warp_sum_d(e.half_rho);
+    if (lane == 0) atomicAdd(a.cost, v);
+    v = warp_sum_d(e.J[0][18] * e.J[0][18] + e.J[1][18] * e.J[1][18]);
+    if (lane == 0) a.Hll[l] = v;
+    v = warp_sum_d(e.J[0][18] * e.r[0] + e.J[1][18] * e.r[1]);
+    if (lane == 0) a.gl[l] = v;
+    auto dotJ = [&](int aa, int bb) { return e.J[0][aa] * e.J[0][bb] + e.J[1][aa] * e.J[1][bb]; };
+    auto dotr = [&](int aa) { return e.J[0][aa] * e.r[0] + e.J[1][aa] * e.r[1]; };
+    // anchor pose block (shared by all observations of the landmark): warp-reduce, one lane commits
+#pragma unroll
+    for (int aa = 0; aa < 6; aa++) {
+#pragma unroll
+        for (int bb = aa; bb < 6; bb++) {
+            v = warp_sum_d(dotJ(aa, bb));
+            if (lane == 0) atomicAdd(&a.Hpp[(size_t)(ci + aa) * D + ci + bb], v);
+        }
+        v = warp_sum_d(dotr(aa));
+        if (lane == 0) atomicAdd(&a.gp[ci + aa], v);
+        v = warp_sum_d(dotJ(aa, 18));
+        if (lane == 0) a.Hpl[(size_t)l * D + ci + aa] = v;
+    }
+    if (has) {  // blocks involving this observation's own frame j
+#pragma unroll
+        for (int aa = 0; aa < 6; aa++) {
+#pragma unroll
+            for (int bb = 0; bb < 6; bb++) atomicAdd(&a.Hpp[(size_t)(ci + aa) * D + cj + bb], dotJ(aa, 6 + bb));
+#pragma unroll
+            for (int bb = aa; bb < 6; bb++) atomicAdd(&a.Hpp[(size_t)(cj + aa) * D + cj + bb], dotJ(6 + aa, 6 + bb));
+            atomicAdd(&a.gp[cj + aa], dotr(6 + aa));
+            a.Hpl[(size_t)l * D + cj + aa] = dotJ(6 + aa, 18);
+        }
+    }
+    if (d.col_ex >= 0) {
+        const int ce = d.col_ex;
+#pragma unroll
+        for (int aa = 0; aa < 6; aa++) {
+#pragma unroll
+            for (int bb = 0; bb < 6; bb++) {
+                v = warp_sum_d(dotJ(aa, 12 + bb));
+                if (lane == 0) atomicAdd(&a.Hpp[(size_t)(ci + aa) * D + ce + bb], v);
+                if (has) atomicAdd(&a.Hpp[(size_t)(cj + aa) * D + ce + bb], dotJ(6 + aa, 12 + bb));
+            }
+#pragma unroll
+            for (int bb = aa; bb < 6; bb++) {
+                v = warp_sum_d(dotJ(12 + aa, 12 + bb));
+                if (lane == 0) atomicAdd(&a.Hpp[(size_t)(ce + aa) * D + ce + bb], v);
+            }
+            v = warp_sum_d(dotr(12 + aa));
+            if (lane == 0) atomicAdd(&a.gp[ce + aa], v);
+            v = warp_sum_d(dotJ(12 + aa, 18));
+            if (lane == 0) a.Hpl[(size_t)l * D + ce + aa] = v;
+        }
+    }
+    if (d.col_td >= 0) {
+        const int ct = d.col_td;
+#pragma unroll
+        for (int aa = 0; aa < 6; aa++) {
+            v = warp_sum_d(dotJ(aa, 19));
+            if (lane == 0) atomicAdd(&a.Hpp[(size_t)(ci + aa) * D + ct], v);
+            if (has) atomicAdd(&a.Hpp[(size_t)(cj + aa) * D + ct], dotJ(6 + aa, 19));
+            if (d.col_ex >= 0) {
+                v = warp_sum_d(dotJ(12 + aa, 19));
+                if (lane == 0) atomicAdd(&a.Hpp[(size_t)(d.col_ex + aa) * D + ct], v);
+            }
+        }
+        v = warp_sum_d(dotJ(19, 19));
+        if (lane == 0) atomicAdd(&a.Hpp[(size_t)ct * D + ct], v);
+        v = warp_sum_d(dotr(19));
+        if (lane == 0) atomicAdd(&a.gp[ct], v);
+        v = warp_sum_d(dotJ(19, 18));
+        if (lane == 0) a.Hpl[(size_t)l * D + ct] = v;
+    }
+}
+
+__device__ __forceinline__ int imu_col(const BaDims& d, int k, int aa) {
+    if (aa < 6) return 6 * k + aa;
+    if (aa < 15) return d.col_sb + 9 * k + (aa - 6);
+    if (aa < 21) return 6 * (k + 1) + (aa - 15);
+    return d.col_sb + 9 * (k + 1) + (aa - 21);
+}
+
+// Whitened IMU residual and Jacobian of factor k in shared memory (Jw 15x30, rw 15).  Returns false if skipped.
+__device__ __forceinline__ bool imu_whitened(const BaProblem& p, const BaStates& x, int k, int lane, double* Jraw, double* Jw,
+                                             double* rr, double* rw) {
+    const int slot = p.imu_slot[k];
+    if (slot < 0) return false;
+    const PreInt& pre = p.preint[slot];
+    for (int i = lane; i < 450; i += 32) Jraw[i] = 0.0;
+    __syncwarp();
+    if (lane == 0) eval_imu_raw(p.dims, pre, x.pose + 7 * k, x.sb + 9 * k, x.pose + 7 * (k + 1), x.sb + 9 * (k + 1), rr, Jraw);
+    __syncwarp();
+    for (int idx = lane; idx < 450; idx += 32) {
+        const int i = idx / 30, c = idx % 30;
+        double s = 0;
+        for (int q = 0; q < 15; q++) s += pre.sqrt_info[i * 15 + q] * Jraw[q * 30 + c];
+        Jw[idx] = s;
+    }
+    if (lane < 15) {
+        double s = 0;
+        for (int q = 0; q < 15; q++) s += pre.sqrt_info[lane * 15 + q] * rr[q];
+        rw[lane] = s;
+    }
+    __syncwarp();
+    return true;
+}
+
+__device__ __forceinline__ void lin_imu(const BaProblem& p, const BaStates& x, const BaAccum& a, int k, int lane, double* Jraw,
+                                        double* Jw, double* rr, double* rw) {
+    if (!imu_whitened(p, x, k, lane, Jraw, Jw, rr, rw)) return;
+    const BaDims& d = p.dims;
+    const int D = d.D;
+    if (lane == 0) {
+        double c = 0;
+        for (int q = 0; q < 15; q++) c += rw[q] * rw[q];
+        atomicAdd(a.cost, 0.5 * c);
+    }
+    for (int idx = lane; idx < 900; idx += 32) {
+        const int aa = idx / 30, bb = idx % 30;
+        const int ga = imu_col(d, k, aa), gb = imu_col(d, k, bb);
+        if (ga > gb) continue;
+        double s = 0;
+        for (int q = 0; q < 15; q++) s += Jw[q * 30 + aa] * Jw[q * 30 + bb];
+        if (s != 0.0) atomicAdd(&a.Hpp[(size_t)ga * D + gb], s);
+    }
+    if (lane < 30) {
+        double s = 0;
+        for (int q = 0; q < 15; q++) s += Jw[q * 30 + lane] * rw[q];
+        atomicAdd(&a.gp[imu_col(d, k, lane)], s);
+    }
+}
+
+#define PRIOR_MAX_N 160
+
+// dx of the prior's kept blocks (MarginalizationFactor::Evaluate, marginalization_factor.cpp:343-364)
+__device__ __forceinline__ void prior_dx(const BaProblem& p, const BaStates& x, double* dx, int tid, int nthreads) {
+    const BaPrior& pr = p.prior;
+    for (int b = tid; b < pr.nblocks; b += nthreads) {
+        const int type = pr.type[b], idx = pr.index[b], off = pr.off[b];
+        const double* x0 = pr.x0 + 9 * b;
+        if (type == 0 || type == 2) {
+            const double* xv = type == 0 ? x.pose + 7 * idx : x.ex;
+            for (int q = 0; q < 3; q++) dx[off + q] = xv[q] - x0[q];
+            const Q4 dq = qmul(qinv(q_from_param(x0)), q_from_param(xv));
+            const double sg = (dq.w >= 0) ? 2.0 : -2.0;
+            dx[off + 3] = sg * dq.x;
+            dx[off + 4] = sg * dq.y;
+            dx[off + 5] = sg * dq.z;
+        } else if (type == 1) {
+            for (int q = 0; q < 9; q++) dx[off + q] = x.sb[9 * idx + q] - x0[q];
+        } else {
+            dx[off] = x.td[0] - x0[0];
+        }
+    }
+}
+
+__device__ __forceinline__ void prior_cols(const BaProblem& p, int* col, int tid, int nthreads) {
+    const BaPrior& pr = p.prior;
+    const BaDims& d = p.dims;
+    for (int b = tid; b < pr.nblocks; b += nthreads) {
+        const int type = pr.type[b], idx = pr.index[b], off = pr.off[b];
+        if (type == 0) for (int q = 0; q < 6; q++) col[off + q] = 6 * idx + q;
+        else if (type == 1) for (int q = 0; q < 9; q++) col[off + q] = d.col_sb + 9 * idx + q;
+        else if (type == 2) for (int q = 0; q < 6; q++) col[off + q] = d.col_ex >= 0 ? d.col_ex + q : -1;
+        else col[off] = d.col_td;
+    }
+}
+
+__device__ void lin_prior(const BaProblem& p, const BaStates& x, const BaAccum& a) {
+    __shared__ double dx[PRIOR_MAX_N], gpr[PRIOR_MAX_N];
+    __shared__ int col[PRIOR_MAX_N];
+    __shared__ double red[4];
+    const BaPrior& pr = p.prior;
+    const int n = pr.n, tid = threadIdx.x, nt = blockDim.x, D = p.dims.D;
+    if (n <= 0) return;
+    prior_dx(p, x, dx, tid, nt);
+    prior_cols(p, col, tid, nt);
+    __syncthreads();
+    double part = 0;
+    for (int aa = tid; aa < n; aa += nt) {
+        double s = pr.g0[aa];
+        for (int bb = 0; bb < n; bb++) s += pr.A[(size_t)aa * n + bb] * dx[bb];
+        gpr[aa] = s;
+        part += dx[aa] * (pr.g0[aa] + s);
+    }
+    part = warp_sum_d(part);
+    if ((tid & 31) == 0) red[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+        double c = pr.c0[0];
+        for (int w = 0; w < nt / 32; w++) c += red[w];
+        atomicAdd(a.cost, 0.5 * c);
+    }
+    for (int idx = tid; idx < n * n; idx += nt) {
+        const int aa = idx / n, bb = idx % n;
+        const int ga = col[aa], gb = col[bb];
+        if (ga < 0 || gb < 0 || ga > gb || (ga == gb && aa != bb)) continue;
+        const double v = pr.A[idx];
+        if (v != 0.0) atomicAdd(&a.Hpp[(size_t)ga * D + gb], v);
+    }
+    for (int aa = tid; aa < n; aa += nt)
+        if (col[aa] >= 0) atomicAdd(&a.gp[col[aa]], gpr[aa]);
+}
+
+}  // namespace
+
+#define LIN_WARPS 4
+__global__ void __launch_bounds__(32 * LIN_WARPS) ba_linearize_kernel(BaProblem p, int initial) {
+    __shared__ double sJraw[LIN_WARPS][450], sJw[LIN_WARPS][450], srr[LIN_WARPS][15], srw[LIN_WARPS][15];
+    SolverState* st = p.st;
+    if (!initial && (st->done || !st->cand_valid)) return;
+    const int b = initial ? st->cur : 1 - st->cur;
+    const BaStates x = p.x[b];
+    const BaAccum a = p.acc[b];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nb_vis = (p.dims.L + LIN_WARPS - 1) / LIN_WARPS, nb_imu = (p.dims.W + LIN_WARPS - 1) / LIN_WARPS;
+    const int blk = blockIdx.x;
+    if (blk < nb_vis) {
+        const int l = blk * LIN_WARPS + wid;
+        if (l < p.dims.L) lin_visual(p, x, a, l, lane);
+    } else if (blk < nb_vis + nb_imu) {
+        const int k = (blk - nb_vis) * LIN_WARPS + wid;
+        if (k < p.dims.W) lin_imu(p, x, a, k, lane, sJraw[wid], sJw[wid], srr[wid], srw[wid]);
+    } else {
+        lin_prior(p, x, a);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(&st->lin_ticket, 1u);
+        if (t == gridDim.x - 1) {
+            st->lin_ticket = 0;
+            __threadfence();
+            decide(p, initial);
+        }
+    }
+}
+
+int ba_linearize_grid(const BaDims& d) { return (d.L + LIN_WARPS - 1) / LIN_WARPS + (d.W + LIN_WARPS - 1) / LIN_WARPS + 1; }
+
+// ------------------------------------------------------------------------------------------------
+// Landmark elimination as a dense, deterministic tiled product:
+//   S = sym(Hpp) - sum_l w_l w_l^T / (Hll_l + mu E_l),   gred = gp - sum_l w_l gl_l / (Hll_l + mu E_l)
+// E_l = clamp(Hll_l s_l^2, 1e-6, 1e32) / s_l^2 is the dogleg/LM diagonal expressed in unscaled variables.
+#define ST 16
+__device__ __forceinline__ double lm_inv_lambda(const BaProblem& p, const BaAccum& a, int l, double mu, int first) {
+    const double h = a.Hll[l];
+    const double s = first ? 1.0 / (1.0 + sqrt(h)) : p.scale[p.dims.D + l];
+    const double d2 = fmin(fmax(h * s * s, 1e-6), 1e32);
+    return 1.0 / (h + mu * d2 / (s * s));
+}
+
+__global__ void __launch_bounds__(ST* ST) ba_schur_kernel(BaProblem p) {
+    const SolverState* st = p.st;
+    if (st->done || st->reuse) return;
+    if (blockIdx.y > blockIdx.x) return;  // upper tiles only
+    __shared__ double As[ST][ST + 1], Bs[ST][ST + 1], inv[ST], gls[ST];
+    const BaAccum a = p.acc[st->cur];
+    const int D = p.dims.D, L = p.dims.L;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int r0 = blockIdx.y * ST, c0 = blockIdx.x * ST;
+    const double mu = st->mu;
+    const int first = st->first;
+    double acc = 0, gacc = 0;
+    for (int l0 = 0; l0 < L; l0 += ST) {
+        const int l = l0 + ty;
+        As[ty][tx] = (l < L && r0 + tx < D) ? a.Hpl[(size_t)l * D + r0 + tx] : 0.0;
+        Bs[ty][tx] = (l < L && c0 + tx < D) ? a.Hpl[(size_t)l * D + c0 + tx] : 0.0;
+        if (tx == 0) {
+            inv[ty] = l < L ? lm_inv_lambda(p, a, l, mu, first) : 0.0;
+            gls[ty] = l < L ? a.gl[l] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < ST; q++) {
+            acc += As[q][ty] * inv[q] * Bs[q][tx];
+            if (blockIdx.x == blockIdx.y && ty == 0) gacc += Bs[q][tx] * inv[q] * gls[q];
+        }
+        __syncthreads();
+    }
+    const int r = r0 + ty, c = c0 + tx;
+    if (r < D && c < D) {
+        const double h = r <= c ? a.Hpp[(size_t)r * D + c] : a.Hpp[(size_t)c * D + r];
+        p.Hfull[(size_t)r * D + c] = h;
+        p.S[(size_t)r * D + c] = h - acc;
+        if (blockIdx.x != blockIdx.y) {
+            p.Hfull[(size_t)c * D + r] = h;
+            p.S[(size_t)c * D + r] = h - acc;
+        }
+    }
+    if (blockIdx.x == blockIdx.y && ty == 0 && c < D) p.gred[c] = a.gp[c] - gacc;
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum_d(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0;
+    for (unsigned w = 0; w < blockDim.x / 32; w++) s += red[w];
+    return s;
+}
+
+// q = v^T H v over all parameters (H = [[Hfull, Hpl^T], [Hpl, diag(Hll)]]), also returns v^T g if g given
+__device__ double quad_form(const BaProblem& p, const BaAccum& a, const double* v, double* tmp, double* red) {
+    const int D = p.dims.D, L = p.dims.L;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x / 32;
+    double part = 0;
+    for (int r = wid; r < D; r += nw) {
+        double s = 0;
+        for (int c = lane; c < D; c += 32) s += p.Hfull[(size_t)r * D + c] * v[c];
+        s = warp_sum_d(s);
+        if (lane == 0) part += v[r] * s;
+    }
+    for (int l = wid; l < L; l += nw) {
+        double s = 0;
+        for (int c = lane; c < D; c += 32) s += a.Hpl[(size_t)l * D + c] * v[c];
+        s = warp_sum_d(s);
+        if (lane == 0) part += v[D + l] * (2.0 * s + a.Hll[l] * v[D + l]);
+    }
+    (void)tmp;
+    return block_sum(part, red);
+}
+
+// In-place lower Cholesky of the n x n matrix stored packed (row-major lower triangle) in `Lp`.
+__device__ bool cholesky_packed(double* Lp, int n, int* flag) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    auto at = [&](int i, int j) -> double& { return Lp[(size_t)i * (i + 1) / 2 + j]; };
+    if (threadIdx.x == 0) *flag = 1;
+    __syncthreads();
+    for (int k = 0; k < n; k++) {
+        if (threadIdx.x == 0) {
+            const double pv = at(k, k);
+            if (!(pv > 0.0) || !isfinite(pv)) *flag = 0;
+            else at(k, k) = sqrt(pv);
+        }
+        __syncthreads();
+        if (!*flag) return false;
+        const double dkk = at(k, k);
+        for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) at(i, k) /= dkk;
+        __syncthreads();
+        for (int i = k + 1 + ty; i < n; i += 32) {
+            const double lik = at(i, k);
+            for (int j = k + 1 + tx; j <= i; j += 32) at(i, j) -= lik * at(j, k);
+        }
+        __syncthreads();
+    }
+    return true;
+}
+
+// Solves L L^T y = b with the packed factor, single warp (warp 0), y in/out in `y` (global or shared).
+__device__ void chol_solve_packed(const double* Lp, int n, double* y) {
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    auto at = [&](int i, int j) { return Lp[(size_t)i * (i + 1) / 2 + j]; };
+    for (int k = 0; k < n; k++) {  // forward
+        double yk = 0;
+        if (lane == (k & 31)) {
+            yk = y[k] / at(k, k);
+            y[k] = yk;
+        }
+        yk = __shfl_sync(0xffffffffu, yk, k & 31);
+        for (int i = k + 1 + ((lane - (k + 1)) & 31); i < n; i += 32) y[i] -= at(i, k) * yk;
+        __syncwarp();
+    }
+    for (int k = n - 1; k >= 0; k--) {  // backward
+        double yk = 0;
+        if (lane == (k & 31)) {
+            yk = y[k] / at(k, k);
+            y[k] = yk;
+        }
+        yk = __shfl_sync(0xffffffffu, yk, k & 31);
+        for (int i = lane; i < k; i += 32) y[i] -= at(k, i) * yk;
+        __syncwarp();
+    }
+}
+
+// Slow path: recompute S for a new mu inside the single step CTA (only after a failed factorisation).
+__device__ void reduce_single_cta(const BaProblem& p, const BaAccum& a, double mu, int first) {
+    const int D = p.dims.D, L = p.dims.L;
+    for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+        const int r = idx / D, c = idx % D;
+        if (r > c) continue;
+        double acc = 0;
+        for (int l = 0; l < L; l++) {
+            const double wr = a.Hpl[(size_t)l * D + r];
+            if (wr == 0.0) continue;
+            acc += wr * lm_inv_lambda(p, a, l, mu, first) * a.Hpl[(size_t)l * D + c];
+        }
+        const double h = p.Hfull[idx];
+        p.S[idx] = h - acc;
+        p.S[(size_t)c * D + r] = h - acc;
+    }
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        double acc = 0;
+        for (int l = 0; l < L; l++) acc += a.Hpl[(size_t)l * D + c] * lm_inv_lambda(p, a, l, mu, first) * a.gl[l];
+        p.gred[c] = a.gp[c] - acc;
+    }
+    __syncthreads();
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(1024) ba_step_kernel(BaProblem p, int use_smem_chol) {
+    extern __shared__ double chol_smem[];
+    __shared__ double red[32];
+    __shared__ int flag;
+    SolverState* st = p.st;
+    if (st->done) return;
+    if (st->iteration >= st->max_iterations) {
+        if (threadIdx.x == 0) st->done = 1;
+        return;
+    }
+    const BaDims& d = p.dims;
+    const int D = d.D, L = d.L, N = D + L;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int cur = st->cur;
+    const BaAccum a = p.acc[cur];
+    double* u = p.work;            // N
+    double* y = p.work + N;        // N
+    double* delta = p.work + 2 * N;  // N
+    double* Lp = use_smem_chol ? chol_smem : p.work + 4 * (size_t)N;  // packed factor
+    const int first = st->first;
+    double mu = st->mu;
+    bool linear_ok = true;
+    if (!st->reuse) {
+        double gg_part = 0;
+        for (int j = tid; j < N; j += nt) {
+            const double hjj = j < D ? p.Hfull[(size_t)j * D + j] : a.Hll[j - D];
+            const double gj = j < D ? a.gp[j] : a.gl[j - D];
+            if (first) p.scale[j] = 1.0 / (1.0 + sqrt(hjj));
+            const double s = p.scale[j];
+            const double d2 = fmin(fmax(hjj * s * s, 1e-6), 1e32);
+            const double dg = sqrt(d2);
+            p.diag[j] = dg;
+            const double g = gj * s / dg;
+            p.grad[j] = g;
+            u[j] = g / dg * s;
+            gg_part += g * g;
+        }
+        const double gg = block_sum(gg_part, red);
+        const double uHu = quad_form(p, a, u, nullptr, red);
+        const double alpha = gg / uHu;
+        // regularised Gauss-Newton step: (S + mu E_p) y_p = gred
+        linear_ok = false;
+        while (mu < 1.0) {
+            for (int idx = tid; idx < D * (D + 1) / 2; idx += nt) {
+                // idx -> (i, j) of the packed lower triangle
+                int i = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+                while ((size_t)i * (i + 1) / 2 > (size_t)idx) i--;
+                while ((size_t)(i + 1) * (i + 2) / 2 <= (size_t)idx) i++;
+                const int j = idx - i * (i + 1) / 2;
+                double v = p.S[(size_t)i * D + j];
+                if (i == j) {
+                    const double s = p.scale[i];
+                    v += mu * (p.diag[i] * p.diag[i]) / (s * s);
+                }
+                Lp[idx] = v;
+            }
+            __syncthreads();
+            if (cholesky_packed(Lp, D, &flag)) {
+                linear_ok = true;
+                break;
+            }
+            mu *= 10.0;
+            if (tid == 0) st->retries++;
+            __syncthreads();
+            if (mu < 1.0) reduce_single_cta(p, a, mu, first);
+        }
+        if (linear_ok) {
+            for (int j = tid; j < D; j += nt) y[j] = p.gred[j];
+            __syncthreads();
+            chol_solve_packed(Lp, D, y);
+            __syncthreads();
+            const int lane = tid & 31, wid = tid >> 5, nw = nt / 32;
+            for (int l = wid; l < L; l += nw) {
+                double s = 0;
+                for (int c = lane; c < D; c += 32) s += a.Hpl[(size_t)l * D + c] * y[c];
+                s = warp_sum_d(s);
+                if (lane == 0) y[D + l] = (a.gl[l] - s) * lm_inv_lambda(p, a, l, mu, first);
+            }
+            __syncthreads();
+            for (int j = tid; j < N; j += nt) p.gn[j] = -p.diag[j] * y[j] / p.scale[j];
+        }
+        if (tid == 0) {
+            st->alpha = alpha;
+            st->mu = mu;
+            st->reuse = 1;
+            st->first = 0;
+        }
+        __syncthreads();
+    }
+    // ---- traditional dogleg (DoglegStrategy::ComputeTraditionalDoglegStep)
+    bool valid = false;
+    double mcc = 0, dogleg_norm = 0;
+    if (linear_ok) {
+        double p1 = 0, p2 = 0, p3 = 0;
+        for (int j = tid; j < N; j += nt) {
+            p1 += p.grad[j] * p.grad[j];
+            p2 += p.gn[j] * p.gn[j];
+            p3 += p.grad[j] * p.gn[j];
+        }
+        const double gg = block_sum(p1, red), nn = block_sum(p2, red), gdn = block_sum(p3, red);
+        const double gradient_norm = sqrt(gg), gn_norm = sqrt(nn);
+        const double radius = st->radius, alpha = st->alpha;
+        double ca = 0, cb = 0;  // step = ca * gradient + cb * gauss_newton
+        if (gn_norm <= radius) {
+            cb = 1.0;
+            dogleg_norm = gn_norm;
+        } else if (gradient_norm * alpha >= radius) {
+            ca = -(radius / gradient_norm);
+            dogleg_norm = radius;
+        } else {
+            const double b_dot_a = -alpha * gdn;
+            const double a_sq = (alpha * gradient_norm) * (alpha * gradient_norm);
+            const double bma = a_sq - 2 * b_dot_a + gn_norm * gn_norm;
+            const double c = b_dot_a - a_sq;
+            const double dd = sqrt(c * c + bma * (radius * radius - a_sq));
+            const double beta = (c <= 0) ? (dd - c) / bma : (radius * radius - a_sq) / (dd + c);
+            ca = -alpha * (1.0 - beta);
+            cb = beta;
+            dogleg_norm = -1.0;  // computed below
+        }
+        double pn = 0, pg = 0;
+        for (int j = tid; j < N; j += nt) {
+            const double sd = ca * p.grad[j] + cb * p.gn[j];
+            pn += sd * sd;
+            const double dl = sd / p.diag[j] * p.scale[j];  // undo trust-region diagonal and Jacobi scaling
+            delta[j] = dl;
+            pg += dl * (j < D ? a.gp[j] : a.gl[j - D]);
+        }
+        const double sn = block_sum(pn, red), dg = block_sum(pg, red);
+        if (dogleg_norm < 0) dogleg_norm = sqrt(sn);
+        const double dHd = quad_form(p, a, delta, nullptr, red);
+        mcc = -(dg + 0.5 * dHd);
+        valid = mcc > 0.0;
+    }
+    if (!valid) {  // HandleInvalidStep + DoglegStrategy::StepIsInvalid
+        if (tid == 0) {
+            st->iteration++;
+            st->cand_valid = 0;
+            st->invalid_streak++;
+            if (st->invalid_streak >= 5) st->done = 4;
+            st->mu = st->mu * 10.0;
+            st->reuse = 0;
+            if (st->iteration >= st->max_iterations && !st->done) st->done = 1;
+        }
+        return;
+    }
+    // ---- candidate point and the norms the tolerance tests need
+    const BaStates xc = p.x[cur], xn = p.x[1 - cur];
+    double xs = 0, ss = 0;
+    const int F = d.W + 1;
+    for (int f = tid; f < F; f += nt) {
+        double out[7];
+        pose_plus(xc.pose + 7 * f, delta + 6 * f, out);
+        for (int q = 0; q < 7; q++) {
+            const double o = xc.pose[7 * f + q];
+            xn.pose[7 * f + q] = out[q];
+            xs += o * o;
+            ss += (o - out[q]) * (o - out[q]);
+        }
+    }
+    for (int i = tid; i < 9 * F; i += nt) {
+        const double o = xc.sb[i], nv = o + delta[d.col_sb + i];
+        xn.sb[i] = nv;
+        xs += o * o;
+        ss += (o - nv) * (o - nv);
+    }
+    if (tid == 0) {
+        if (d.col_ex >= 0) {
+            double out[7];
+            pose_plus(xc.ex, delta + d.col_ex, out);
+            for (int q = 0; q < 7; q++) {
+                const double o = xc.ex[q];
+                xn.ex[q] = out[q];
+                xs += o * o;
+                ss += (o - out[q]) * (o - out[q]);
+            }
+        } else
+            for (int q = 0; q < 7; q++) xn.ex[q] = xc.ex[q];
+        if (d.col_td >= 0) {
+            const double o = xc.td[0], nv = o + delta[d.col_td];
+            xn.td[0] = nv;
+            xs += o * o;
+            ss += (o - nv) * (o - nv);
+        } else
+            xn.td[0] = xc.td[0];
+    }
+    for (int l = tid; l < L; l += nt) {
+        const double o = xc.lam[l], nv = o + delta[D + l];
+        xn.lam[l] = nv;
+        xs += o * o;
+        ss += (o - nv) * (o - nv);
+    }
+    const double x_norm2 = block_sum(xs, red), step_norm2 = block_sum(ss, red);
+    if (tid == 0) {
+        st->iteration++;
+        st->cand_valid = 1;
+        st->invalid_streak = 0;
+        st->model_cost_change = mcc;
+        st->dogleg_step_norm = dogleg_norm;
+        st->x_norm = sqrt(x_norm2);
+        st->step_norm = sqrt(step_norm2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Marginalisation.  Column layout of the dense system: [m_dense | m_landmarks (diagonal block) | kept n].
+namespace {
+
+struct LocalCols {
+    int c[30];
+};
+
+__device__ __forceinline__ void marg_scatter(double* Am, double* bm, int P, const double* J, int ld, int nrows, const double* r,
+                                             const int* gc, int ncols, int lane, int nlanes) {
+    for (int idx = lane; idx < ncols * ncols; idx += nlanes) {
+        const int aa = idx / ncols, bb = idx % ncols;
+        const int ga = gc[aa], gb = gc[bb];
+        if (ga < 0 || gb < 0 || ga > gb || (ga == gb && aa > bb)) continue;
+        double s = 0;
+        for (int q = 0; q < nrows; q++) s += J[q * ld + aa] * J[q * ld + bb];
+        if (ga == gb && aa != bb) s *= 2.0;  // two local columns mapping to one global column never happens; kept for safety
+        if (s != 0.0) atomicAdd(&Am[(size_t)ga * P + gb], s);
+    }
+    for (int aa = lane; aa < ncols; aa += nlanes) {
+        if (gc[aa] < 0) continue;
+        double s = 0;
+        for (int q = 0; q < nrows; q++) s += J[q * ld + aa] * r[q];
+        atomicAdd(&bm[gc[aa]], s);
+    }
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(128) marg_build_kernel(BaProblem p, MargPlan mp) {
+    __shared__ double sJraw[4][450], sJw[4][450], srr[4][15], srw[4][15];
+    __shared__ double dx[PRIOR_MAX_N], gpr[PRIOR_MAX_N];
+    __shared__ int pcol[PRIOR_MAX_N];
+    const BaStates x = p.x[0];
+    const BaDims& d = p.dims;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int P = mp.P;
+    const int nb_vis = (mp.n_lm + 3) / 4;
+    const int blk = blockIdx.x;
+    if (blk < nb_vis) {
+        const int li = blk * 4 + wid;
+        if (li >= mp.n_lm) return;
+        const int l = mp.lms[li];
+        const int s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0, fi = p.lm_anchor[l];
+        // one observation at a time per lane group would waste lanes; instead every lane evaluates one
+        // observation and commits its own 2 x 20 block with atomics
+        if (lane < nobs) {
+            const int o = s0 + lane, fj = p.ob_frame[o];
+            VisualEval e;
+            eval_visual(d, x.pose + 7 * fi, x.pose + 7 * fj, x.ex, x.lam[l], d.est_td ? x.td[0] : 0.0, p.lm_pts[2 * l], p.lm_pts[2 * l + 1],
+                        p.ob_pts[2 * o], p.ob_pts[2 * o + 1], p.lm_vel[2 * l], p.lm_vel[2 * l + 1], p.ob_vel[2 * o], p.ob_vel[2 * o + 1],
+                        p.lm_td[l], p.ob_td[o], p.lm_row[l], p.ob_row[o], true, true, e);
+            int gc[20];
+            for (int q = 0; q < 6; q++) {
+                gc[q] = mp.col_pose[fi] + q;
+                gc[6 + q] = mp.col_pose[fj] + q;
+                gc[12 + q] = mp.col_ex + q;
+            }
+            gc[18] = mp.col_lm[li];
+            gc[19] = d.est_td ? mp.col_td : -1;
+            marg_scatter(mp.Am, mp.bm, P, &e.J[0][0], 20, 2, e.r, gc, 20, 0, 1);
+        }
+    } else if (blk == nb_vis) {
+        if (wid == 0 && mp.use_imu) {
+            if (imu_whitened(p, x, 0, lane, sJraw[0], sJw[0], srr[0], srw[0])) {
+                __shared__ int gci[30];
+                if (lane < 30) {
+                    int c;
+                    if (lane < 6) c = mp.col_pose[0] + lane;
+                    else if (lane < 15) c = mp.col_sb[0] + lane - 6;
+                    else if (lane < 21) c = mp.col_pose[1] + lane - 15;
+                    else c = mp.col_sb[1] + lane - 21;
+                    gci[lane] = c;
+                }
+                __syncwarp();
+                marg_scatter(mp.Am, mp.bm, P, sJw[0], 30, 15, srw[0], gci, 30, lane, 32);
+            }
+        }
+    } else {
+        // previous prior: J^T J = A, J^T r = g0 + A dx, columns through the kept-block -> marg column map
+        const BaPrior& pr = p.prior;
+        const int n = pr.n, tid = threadIdx.x, nt = blockDim.x;
+        if (n <= 0) return;
+        prior_dx(p, x, dx, tid, nt);
+        for (int b = tid; b < pr.nblocks; b += nt) {
+            const int type = pr.type[b], idx = pr.index[b], off = pr.off[b];
+            const int base = type == 0 ? mp.col_pose[idx] : type == 1 ? mp.col_sb[idx] : type == 2 ? mp.col_ex : mp.col_td;
+            const int sz = type == 0 || type == 2 ? 6 : type == 1 ? 9 : 1;
+            for (int q = 0; q < sz; q++) pcol[off + q] = base + q;
+        }
+        __syncthreads();
+        for (int aa = tid; aa < n; aa += nt) {
+            double s = pr.g0[aa];
+            for (int bb = 0; bb < n; bb++) s += pr.A[(size_t)aa * n + bb] * dx[bb];
+            gpr[aa] = s;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < n * n; idx += nt) {
+            const int aa = idx / n, bb = idx % n;
+            const int ga = pcol[aa], gb = pcol[bb];
+            if (ga > gb || (ga == gb && aa != bb)) continue;
+            const double v = pr.A[idx];
+            if (v != 0.0) atomicAdd(&mp.Am[(size_t)ga * P + gb], v);
+        }
+        for (int aa = tid; aa < n; aa += nt) atomicAdd(&mp.bm[pcol[aa]], gpr[aa]);
+    }
+}
+
+namespace {
+
+// Cyclic Jacobi with round-robin parallel ordering on an n x n symmetric matrix in shared memory.
+// A is overwritten (eigenvalues on the diagonal), V receives the eigenvectors (columns).
+__device__ void jacobi_eigen(double* A, double* V, int n, double* cs, int* pq, double* red) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int ne = n + (n & 1), half = ne / 2;
+    for (int i = tid; i < n * n; i += nt) V[i] = (i / n == i % n) ? 1.0 : 0.0;
+    __syncthreads();
+    for (int sweep = 0; sweep < 40; sweep++) {
+        double off = 0, dg = 0;
+        for (int i = tid; i < n * n; i += nt) {
+            const int r = i / n, c = i % n;
+            const double v = A[i];
+            if (r == c) dg += v * v;
+            else if (r < c) off += v * v;
+        }
+        off = block_sum(off, red);
+        dg = block_sum(dg, red);
+        if (off <= 1e-30 * dg || off == 0.0) break;
+        for (int round = 0; round < ne - 1; round++) {
+            if (tid < half) {
+                int a, b;
+                if (tid == 0) {
+                    a = ne - 1;
+                    b = round;
+                } else {
+                    a = (round + tid) % (ne - 1);
+                    b = (round - tid + (ne - 1)) % (ne - 1);
+                }
+                int pp = min(a, b), qq = max(a, b);
+                double c = 1.0, s = 0.0;
+                if (qq < n) {
+                    const double apq = A[pp * n + qq];
+                    const double app = A[pp * n + pp], aqq = A[qq * n + qq];
+                    if (apq != 0.0 && fabs(apq) > 1e-300 + 1e-18 * sqrt(fabs(app * aqq))) {
+                        const double theta = (aqq - app) / (2 * apq);
+                        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+                        c = 1 / sqrt(t * t + 1);
+                        s = t * c;
+                    }
+                } else {
+                    pp = -1;
+                }
+                pq[2 * tid] = pp;
+                pq[2 * tid + 1] = qq;
+                cs[2 * tid] = c;
+                cs[2 * tid + 1] = s;
+            }
+            __syncthreads();
+            for (int w = tid; w < half * n; w += nt) {  // columns: A <- A J, V <- V J
+                const int k = w / n, i = w % n;
+                const int pp = pq[2 * k], qq = pq[2 * k + 1];
+                if (pp < 0) continue;
+                const double c = cs[2 * k], s = cs[2 * k + 1];
+                if (s == 0.0) continue;
+                const double aip = A[i * n + pp], aiq = A[i * n + qq];
+                A[i * n + pp] = c * aip - s * aiq;
+                A[i * n + qq] = s * aip + c * aiq;
+                const double vip = V[i * n + pp], viq = V[i * n + qq];
+                V[i * n + pp] = c * vip - s * viq;
+                V[i * n + qq] = s * vip + c * viq;
+            }
+            __syncthreads();
+            for (int w = tid; w < half * n; w += nt) {  // rows: A <- J^T A
+                const int k = w / n, j = w % n;
+                const int pp = pq[2 * k], qq = pq[2 * k + 1];
+                if (pp < 0) continue;
+                const double c = cs[2 * k], s = cs[2 * k + 1];
+                if (s == 0.0) continue;
+                const double apj = A[pp * n + j], aqj = A[qq * n + j];
+                A[pp * n + j] = c * apj - s * aqj;
+                A[qq * n + j] = s * apj + c * aqj;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace
+
+// Single CTA.  Dynamic shared memory: Wk (q x q), Ev (max(md, n)^2), Vv (same), bw (q), misc.
+__global__ void __launch_bounds__(1024) marg_solve_kernel(MargPlan mp, double eps) {
+    extern __shared__ double sm[];
+    __shared__ double red[32];
+    __shared__ double cs[2 * 96];
+    __shared__ int pq[2 * 96];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int md = mp.m_dense, nl = mp.n_lm, n = mp.n, P = mp.P;
+    const int q = md + n;
+    const int ne = max(md, n);
+    double* Wk = sm;                 // q*q
+    double* Ev = Wk + q * q;         // ne*ne
+    double* Vv = Ev + ne * ne;       // ne*ne
+    double* bw = Vv + ne * ne;       // q
+    double* tv = bw + q;             // ne
+    auto symA = [&](int a, int b) { return a <= b ? mp.Am[(size_t)a * P + b] : mp.Am[(size_t)b * P + a]; };
+    auto full = [&](int a) { return a < md ? a : a + nl; };  // index in Am of reduced index a
+    // 1. eliminate the landmark columns (exactly diagonal block): rank-1 downdates
+    for (int idx = tid; idx < q * q; idx += nt) {
+        const int aa = idx / q, bb = idx % q;
+        if (aa > bb) continue;
+        const int fa = full(aa), fb = full(bb);
+        double acc = symA(fa, fb);
+        for (int c = 0; c < nl; c++) {
+            const int fc = md + c;
+            const double dc = mp.Am[(size_t)fc * P + fc];
+            if (dc > eps) acc -= symA(fa, fc) * symA(fb, fc) / dc;
+        }
+        Wk[aa * q + bb] = acc;
+        Wk[bb * q + aa] = acc;
+    }
+    for (int aa = tid; aa < q; aa += nt) {
+        const int fa = full(aa);
+        double acc = mp.bm[fa];
+        for (int c = 0; c < nl; c++) {
+            const int fc = md + c;
+            const double dc = mp.Am[(size_t)fc * P + fc];
+            if (dc > eps) acc -= symA(fa, fc) * mp.bm[fc] / dc;
+        }
+        bw[aa] = acc;
+    }
+    __syncthreads();
+    // 2. pseudo-inverse of the dense marginalised block T (md x md) by eigen-decomposition
+    for (int idx = tid; idx < md * md; idx += nt) Ev[idx] = Wk[(idx / md) * q + idx % md];
+    __syncthreads();
+    jacobi_eigen(Ev, Vv, md, cs, pq, red);
+    __syncthreads();
+    // Tinv = V diag(1/w > eps) V^T  (stored back into Ev's off-diagonal-free copy: use tv for 1/w)
+    for (int k = tid; k < md; k += nt) {
+        const double w = Ev[k * md + k];
+        tv[k] = w > eps ? 1.0 / w : 0.0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < md * md; idx += nt) {
+        const int i = idx / md, j = idx % md;
+        double s = 0;
+        for (int k = 0; k < md; k++) s += Vv[i * md + k] * tv[k] * Vv[j * md + k];
+        Ev[idx] = s;  // diagonal eigenvalues no longer needed
+    }
+    __syncthreads();
+    // 3. A' = Wrr - Wrm Tinv Wmr ; b' = br - Wrm Tinv bm.  X = Wrm Tinv (n x md) kept in Vv
+    for (int idx = tid; idx < n * md; idx += nt) {
+        const int i = idx / md, j = idx % md;
+        double s = 0;
+        for (int k = 0; k < md; k++) s += Wk[(md + i) * q + k] * Ev[k * md + j];
+        Vv[idx] = s;
+    }
+    __syncthreads();
+    double* Ap = mp.Aout;  // n x n (global, becomes the prior's A after thresholding)
+    for (int idx = tid; idx < n * n; idx += nt) {
+        const int i = idx / n, j = idx % n;
+        double s = Wk[(md + i) * q + md + j];
+        for (int k = 0; k < md; k++) s -= Vv[i * md + k] * Wk[k * q + md + j];
+        Ap[idx] = s;
+    }
+    for (int i = tid; i < n; i += nt) {
+        double s = bw[md + i];
+        for (int k = 0; k < md; k++) s -= Vv[i * md + k] * bw[k];
+        mp.gout[i] = s;
+    }
+    __syncthreads();
+    // keep the un-thresholded A', b' for parity tests
+    if (mp.Araw)
+        for (int idx = tid; idx < n * n; idx += nt) mp.Araw[idx] = 0.5 * (Ap[idx] + Ap[(idx % n) * n + idx / n]);
+    if (mp.graw)
+        for (int i = tid; i < n; i += nt) mp.graw[i] = mp.gout[i];
+    // 4. eigen-decomposition of A' with the eps floor: A+ = V S+ V^T, g0 = V 1+ V^T b', c0 = b'^T V S+^-1 V^T b'
+    for (int idx = tid; idx < n * n; idx += nt) Ev[idx] = 0.5 * (Ap[idx] + Ap[(idx % n) * n + idx / n]);
+    __syncthreads();
+    jacobi_eigen(Ev, Vv, n, cs, pq, red);
+    __syncthreads();
+    for (int k = tid; k < n; k += nt) {
+        double s = 0;
+        for (int i = 0; i < n; i++) s += Vv[i * n + k] * mp.gout[i];
+        tv[k] = s;  // V_k^T b'
+    }
+    __syncthreads();
+    double cpart = 0;
+    for (int k = tid; k < n; k += nt) {
+        const double w = Ev[k * n + k];
+        if (w > eps) cpart += tv[k] * tv[k] / w;
+    }
+    const double c0 = block_sum(cpart, red);
+    for (int idx = tid; idx < n * n; idx += nt) {
+        const int i = idx / n, j = idx % n;
+        double s = 0;
+        for (int k = 0; k < n; k++) {
+            const double w = Ev[k * n + k];
+            if (w > eps) s += Vv[i * n + k] * w * Vv[j * n + k];
+        }
+        Ap[idx] = s;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        double s = 0;
+        for (int k = 0; k < n; k++)
+            if (Ev[k * n + k] > eps) s += Vv[i * n + k] * tv[k];
+        bw[i] = s;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) mp.gout[i] = bw[i];
+    if (tid == 0) mp.cout[0] = c0;
+}
+
+size_t marg_solve_smem_bytes(int m_dense, int n) {
+    const int q = m_dense + n, ne = m_dense > n ? m_dense : n;
+    return sizeof(double) * ((size_t)q * q + 2 * (size_t)ne * ne + q + ne);
+}
+
+}  // namespace vb
+
+// ------------------------------------------------------------------------------------------------
+// launch wrappers
+namespace vb {
+
+size_t ba_work_doubles(int D, int L) { return 4 * (size_t)(D + L) + (size_t)D * (D + 1) / 2; }
+
+void launch_preint_push(PreInt* slot, int n, const double* d_samples, double acc_n, double gyr_n, double acc_w, double gyr_w,
+                        cudaStream_t s) {
+    if (n <= 0) return;
+    preint_push_kernel<<<1, 256, 0, s>>>(slot, n, d_samples, acc_n, gyr_n, acc_w, gyr_w);
+}
+
+void launch_sqrt_info(PreInt* slots, const int* d_which, int count, cudaStream_t s) {
+    if (count <= 0) return;
+    sqrt_info_kernel<<<count, 32, 0, s>>>(slots, d_which, count);
+}
+
+void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int* launches) {
+    const BaDims& d = p.dims;
+    const int lin_grid = ba_linearize_grid(d);
+    const int zero_grid = 64;
+    const int tiles = (d.D + ST - 1) / ST;
+    const size_t chol_bytes = sizeof(double) * (size_t)d.D * (d.D + 1) / 2;
+    static int smem_limit = -1;
+    if (smem_limit < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncSetAttribute(ba_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit - 1024);
+    }
+    const int use_smem = chol_bytes + 1024 <= (size_t)smem_limit ? 1 : 0;
+    int n = 0;
+    ba_zero_kernel<<<zero_grid, 256, 0, s>>>(p, 1);
+    ba_linearize_kernel<<<lin_grid, 32 * LIN_WARPS, 0, s>>>(p, 1);
+    n += 2;
+    for (int it = 0; it < max_iterations; it++) {
+        ba_schur_kernel<<<dim3(tiles, tiles), dim3(ST, ST), 0, s>>>(p);
+        ba_step_kernel<<<1, 1024, use_smem ? chol_bytes : 0, s>>>(p, use_smem);
+        ba_zero_kernel<<<zero_grid, 256, 0, s>>>(p, 0);
+        ba_linearize_kernel<<<lin_grid, 32 * LIN_WARPS, 0, s>>>(p, 0);
+        n += 4;
+    }
+    if (launches) *launches += n;
+}
+
+void launch_marginalize(const BaProblem& p, const MargPlan& mp, cudaStream_t s, int* launches) {
+    cudaMemsetAsync(mp.Am, 0, sizeof(double) * (size_t)mp.P * mp.P, s);
+    cudaMemsetAsync(mp.bm, 0, sizeof(double) * (size_t)mp.P, s);
+    const int grid = (mp.n_lm + 3) / 4 + 2;
+    marg_build_kernel<<<grid, 128, 0, s>>>(p, mp);
+    const size_t smem = marg_solve_smem_bytes(mp.m_dense, mp.n);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(marg_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    marg_solve_kernel<<<1, 1024, smem, s>>>(mp, 1e-8);
+    if (launches) *launches += 2;
+}
+
+}  // namespace vb

@@ -1,0 +1,35 @@
+// Launch interface of the BA kernels (ba_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ba_types.h"
+
+namespace vb {
+
+constexpr int BA_MAX_FRAMES = 32;
+
+struct MargPlan {  // dense marginalisation system layout: [m_dense | n_lm landmark columns | n kept]
+    int P, m_dense, n_lm, n;
+    const int* lms;     // device: indices (into the problem's landmark table) of the marginalised landmarks
+    const int* col_lm;  // device: their columns
+    int col_pose[BA_MAX_FRAMES], col_sb[BA_MAX_FRAMES];  // -1 when the block does not take part
+    int col_ex, col_td;
+    int use_imu;        // include IMU factor (frames 0,1)
+    double* Am;         // P x P (upper triangle accumulated)
+    double* bm;         // P
+    double* Aout;       // n x n   new prior A  (after the eps floor)
+    double* gout;       // n       new prior g0
+    double* cout;       // 1       new prior c0
+    double* Araw;       // n x n   Schur complement before the eps floor (tests), may be null
+    double* graw;       // n
+};
+
+void launch_preint_push(PreInt* slot, int n, const double* d_samples, double acc_n, double gyr_n, double acc_w, double gyr_w,
+                        cudaStream_t s);
+void launch_sqrt_info(PreInt* slots, const int* d_which, int count, cudaStream_t s);
+// full trust-region solve: linearise x[st->cur], then max_iterations x {schur, step, zero, linearise+decide}
+void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int* launches);
+void launch_marginalize(const BaProblem& p, const MargPlan& mp, cudaStream_t s, int* launches);
+size_t ba_work_doubles(int D, int L);
+
+}  // namespace vb

@@ -1,0 +1,123 @@
+"""ctypes mirror of include/vinsb200/estimator.h; method names follow the reference's Estimator
+(vins_estimator/src/estimator.h:25-139)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .tracker import load_library
+
+
+class EstimatorConfig(C.Structure):
+    _fields_ = [("window_size", C.c_int), ("max_features", C.c_int), ("num_iterations", C.c_int),
+                ("estimate_extrinsic", C.c_int), ("estimate_td", C.c_int), ("focal_length", C.c_double),
+                ("keyframe_parallax", C.c_double), ("acc_n", C.c_double), ("gyr_n", C.c_double), ("acc_w", C.c_double),
+                ("gyr_w", C.c_double), ("g_norm", C.c_double), ("init_depth", C.c_double), ("td", C.c_double),
+                ("tr", C.c_double), ("row", C.c_double), ("tic", C.c_double * 3), ("ric", C.c_double * 9),
+                ("device", C.c_int)]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _d(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+_bound = False
+
+
+def _bind(lib):
+    global _bound
+    if _bound:
+        return
+    lib.ve_last_error.restype = C.c_char_p
+    lib.ve_last_error.argtypes = [C.c_void_p]
+    lib.ve_create.argtypes = [C.POINTER(EstimatorConfig), C.POINTER(C.c_void_p)]
+    lib.ve_destroy.argtypes = [C.c_void_p]
+    lib.ve_clear_state.argtypes = [C.c_void_p]
+    lib.ve_set_seed.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ve_process_imu.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    lib.ve_process_image.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double]
+    lib.ve_get_states.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+    lib.ve_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ve_get_prior.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
+    lib.ve_last_timing.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    _bound = True
+
+
+class Estimator:
+    """Drop-in for the reference Estimator: processIMU / processImage, then read Ps, Rs, Vs, Bas, Bgs."""
+
+    def __init__(self, window_size=10, max_features=1000, num_iterations=8, estimate_extrinsic=0, estimate_td=0,
+                 focal_length=460.0, keyframe_parallax=10.0, acc_n=0.08, gyr_n=0.004, acc_w=0.00004, gyr_w=2.0e-6,
+                 g_norm=9.81007, init_depth=5.0, td=0.0, tr=0.0, row=480.0, tic=(0, 0, 0), ric=np.eye(3), device=0):
+        self.lib = load_library()
+        _bind(self.lib)
+        cfg = EstimatorConfig(window_size=window_size, max_features=max_features, num_iterations=num_iterations,
+                              estimate_extrinsic=estimate_extrinsic, estimate_td=estimate_td, focal_length=focal_length,
+                              keyframe_parallax=keyframe_parallax, acc_n=acc_n, gyr_n=gyr_n, acc_w=acc_w, gyr_w=gyr_w,
+                              g_norm=g_norm, init_depth=init_depth, td=td, tr=tr, row=row, device=device)
+        cfg.tic[:] = list(np.asarray(tic, float))
+        cfg.ric[:] = list(np.asarray(ric, float).ravel())
+        self.cfg, self.W = cfg, window_size
+        h = C.c_void_p()
+        rc = self.lib.ve_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"ve_create failed with status {rc} (-2 = no CUDA device; this library has no CPU path)")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ve_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc < 0:
+            raise RuntimeError(f"vinsb200 error {rc}: {self.lib.ve_last_error(self.h).decode()}")
+        return rc
+
+    def clearState(self):
+        self._check(self.lib.ve_clear_state(self.h))
+
+    def set_seed(self, rows, ba, bg):
+        rows, ba, bg = _d(rows), _d(ba), _d(bg)
+        self._check(self.lib.ve_set_seed(self.h, len(rows), _p(rows), _p(ba), _p(bg)))
+
+    def processIMU(self, dt, linear_acceleration, angular_velocity):
+        a, g = _d(linear_acceleration), _d(angular_velocity)
+        self._check(self.lib.ve_process_imu(self.h, float(dt), _p(a), _p(g)))
+
+    def processImage(self, ids, xyz_uv_vel, stamp):
+        ids = np.ascontiguousarray(ids, np.int32)
+        d = _d(xyz_uv_vel)
+        self._check(self.lib.ve_process_image(self.h, len(ids), _p(ids), _p(d), float(stamp)))
+
+    def states(self):
+        out, td = np.zeros((self.W + 1, 16)), C.c_double(0)
+        self._check(self.lib.ve_get_states(self.h, _p(out), C.byref(td)))
+        return out, td.value
+
+    def info(self):
+        o, c = np.zeros(10, np.int32), np.zeros(2)
+        self._check(self.lib.ve_info(self.h, _p(o), _p(c)))
+        keys = ["solver_flag", "frame_count", "marginalization_flag", "n_solves", "n_reboots", "landmarks", "visual",
+                "iterations", "successful_steps", "termination"]
+        d = {k: int(v) for k, v in zip(keys, o)}
+        d["initial_cost"], d["final_cost"] = float(c[0]), float(c[1])
+        return d
+
+    def prior(self, cap=256):
+        A, b = np.zeros(cap * cap), np.zeros(cap)
+        nb, blk = C.c_int(0), np.zeros(4 * 64, np.int32)
+        n = self._check(self.lib.ve_get_prior(self.h, cap, _p(A), _p(b), C.byref(nb), _p(blk)))
+        return A[: n * n].reshape(n, n).copy(), b[:n].copy(), [tuple(int(v) for v in blk[4 * k:4 * k + 4]) for k in range(nb.value)]
+
+    def timing(self):
+        ms, k = np.zeros(4, np.float32), C.c_int(0)
+        self.lib.ve_last_timing(self.h, _p(ms), C.byref(k))
+        return dict(preint_ms=float(ms[0]), solve_ms=float(ms[1]), marg_ms=float(ms[2]), total_ms=float(ms[3]), launches=k.value)
