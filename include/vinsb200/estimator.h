@@ -74,6 +74,10 @@ int ve_get_prior(const ve_estimator* e, int cap, double* A, double* b, int* nblo
  * [3] total; launches = kernels launched. */
 int ve_last_timing(const ve_estimator* e, float* ms4, int* launches);
 
+/* Solver internals of the last solve (profiling/tests): out[0] linear-solver retries, [1] mu, [2] radius,
+ * [3..12] per-phase cycle counters of the step kernel summed over the iterations. */
+int ve_solver_debug(const ve_estimator* e, double* out13);
+
 #ifdef __cplusplus
 }
 #endif

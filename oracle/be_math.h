@@ -234,19 +234,23 @@ inline void sym_eigen(const Mat& A, std::vector<double>& w, Mat& V) {
     const int n = A.r;
     Mat a = A;
     V = Mat::Identity(n);
+    // Stop when a whole sweep finds every off-diagonal entry negligible against its own diagonal pair
+    // (|a_pq| <= 1e-15 sqrt|a_pp a_qq|): the relative criterion of Jacobi methods, which also resolves the small
+    // eigenvalues of the badly scaled information matrices (entries from 1e-3 to 1e14) this is used on.
+    // Entries below 1e-16 of the largest diagonal are round-off of the rotations among the large rows (absolute
+    // accuracy eps*|A| is also all Eigen's tridiagonal-QR SelfAdjointEigenSolver delivers).
+    double amax = 0;
+    for (int i = 0; i < n; i++) amax = std::max(amax, std::fabs(a(i, i)));
+    const double floor_abs = 1e-16 * amax;
     for (int sweep = 0; sweep < 60; sweep++) {
-        double off = 0, diag = 0;
-        for (int i = 0; i < n; i++) {
-            diag += a(i, i) * a(i, i);
-            for (int j = i + 1; j < n; j++) off += a(i, j) * a(i, j);
-        }
-        if (off <= 1e-30 * diag || off == 0) break;
+        bool rotated = false;
         for (int p = 0; p < n - 1; p++)
             for (int q = p + 1; q < n; q++) {
                 const double apq = a(p, q);
                 if (apq == 0) continue;
                 const double app = a(p, p), aqq = a(q, q);
-                if (std::fabs(apq) <= 1e-300 + 1e-18 * std::sqrt(std::fabs(app * aqq))) { a(p, q) = a(q, p) = 0; continue; }
+                if (std::fabs(apq) <= std::max(floor_abs, 1e-15 * std::sqrt(std::fabs(app * aqq)))) continue;
+                rotated = true;
                 const double theta = (aqq - app) / (2 * apq);
                 const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
                 const double c = 1 / std::sqrt(t * t + 1), s = t * c;
@@ -266,6 +270,7 @@ inline void sym_eigen(const Mat& A, std::vector<double>& w, Mat& V) {
                     V(k, q) = s * vkp + c * vkq;
                 }
             }
+        if (!rotated) break;
     }
     std::vector<int> idx(n);
     for (int i = 0; i < n; i++) idx[i] = i;

@@ -16,6 +16,7 @@
 // B200's FP64 pipe is far from saturated, so no tensor-core path is used.
 #include "ba_kernels.h"
 
+#include <algorithm>
 #include <cfloat>
 
 #include "ba_device.cuh"
@@ -555,6 +556,7 @@ __global__ void __launch_bounds__(ST* ST) ba_schur_kernel(BaProblem p) {
         const double h = r <= c ? a.Hpp[(size_t)r * D + c] : a.Hpp[(size_t)c * D + r];
         p.Hfull[(size_t)r * D + c] = h;
         p.S[(size_t)r * D + c] = h - acc;
+        if (r <= c) p.Spk[(size_t)c * (c + 1) / 2 + r] = h - acc;
         if (blockIdx.x != blockIdx.y) {
             p.Hfull[(size_t)c * D + r] = h;
             p.S[(size_t)c * D + r] = h - acc;
@@ -597,55 +599,130 @@ __device__ double quad_form(const BaProblem& p, const BaAccum& a, const double* 
     return block_sum(part, red);
 }
 
-// In-place lower Cholesky of the n x n matrix stored packed (row-major lower triangle) in `Lp`.
-__device__ bool cholesky_packed(double* Lp, int n, int* flag) {
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    auto at = [&](int i, int j) -> double& { return Lp[(size_t)i * (i + 1) / 2 + j]; };
-    if (threadIdx.x == 0) *flag = 1;
+// In-place lower Cholesky of the n x n matrix stored packed (row-major lower triangle) in `Lp`; rdiag receives
+// 1 / L_kk.  Right-looking, blocked by 8 columns: the 8x8 diagonal block is factorised by warp 0 in registers
+// (one row per lane, pivots and multipliers exchanged with shuffles), the panel below by one thread per row
+// (forward substitution against the diagonal block, reciprocal pivots), the trailing matrix with 4x4 register
+// tiles (0.5 shared-memory loads per FMA).  3 barriers per block column.
+#define CHOL_NB 8
+__device__ bool cholesky_packed(double* Lp, int n, double* rdiag, int* flag) {
+    __shared__ double dblk[CHOL_NB][CHOL_NB + 1];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) *flag = 1;
     __syncthreads();
-    for (int k = 0; k < n; k++) {
-        if (threadIdx.x == 0) {
-            const double pv = at(k, k);
-            if (!(pv > 0.0) || !isfinite(pv)) *flag = 0;
-            else at(k, k) = sqrt(pv);
+    for (int kb = 0; kb < n; kb += CHOL_NB) {
+        const int w = min(CHOL_NB, n - kb), ke = kb + w;
+        if (tid < 32) {
+            const int r = tid;  // row inside the block; rows >= w behave like identity rows
+            double a[CHOL_NB];
+            const size_t rb = (size_t)(kb + r) * (kb + r + 1) / 2 + kb;
+#pragma unroll
+            for (int c = 0; c < CHOL_NB; c++) a[c] = (r < w && c <= r) ? Lp[rb + c] : (c == r ? 1.0 : 0.0);
+            bool ok = true;
+#pragma unroll
+            for (int c = 0; c < CHOL_NB; c++) {
+                const double piv = __shfl_sync(0xffffffffu, a[c], c);
+                if (!(piv > 0.0) || !isfinite(piv)) ok = false;
+                const double dcc = sqrt(piv), rc = 1.0 / dcc;
+                if (r == c) a[c] = dcc;
+                else if (r > c) a[c] *= rc;
+#pragma unroll
+                for (int k = c + 1; k < CHOL_NB; k++) {
+                    const double lkc = __shfl_sync(0xffffffffu, a[c], k);
+                    if (r >= k) a[k] -= a[c] * lkc;
+                }
+                if (r == c && c < w) rdiag[kb + c] = rc;
+            }
+            if (r < w) {
+#pragma unroll
+                for (int c = 0; c < CHOL_NB; c++)
+                    if (c <= r) {
+                        Lp[rb + c] = a[c];
+                        dblk[r][c] = a[c];
+                    }
+            }
+            if (!ok && tid == 0) *flag = 0;
         }
         __syncthreads();
         if (!*flag) return false;
-        const double dkk = at(k, k);
-        for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) at(i, k) /= dkk;
+        for (int i = ke + tid; i < n; i += nt) {
+            double x[CHOL_NB];
+            const size_t ib = (size_t)i * (i + 1) / 2 + kb;
+#pragma unroll
+            for (int c = 0; c < CHOL_NB; c++) {
+                if (c < w) {
+                    double v = Lp[ib + c];
+#pragma unroll
+                    for (int t = 0; t < c; t++) v -= x[t] * dblk[c][t];
+                    x[c] = v * rdiag[kb + c];
+                    Lp[ib + c] = x[c];
+                } else
+                    x[c] = 0.0;
+            }
+        }
         __syncthreads();
-        for (int i = k + 1 + ty; i < n; i += 32) {
-            const double lik = at(i, k);
-            for (int j = k + 1 + tx; j <= i; j += 32) at(i, j) -= lik * at(j, k);
+        const int m = n - ke, nt4 = (m + 3) / 4, ntiles = nt4 * (nt4 + 1) / 2;
+        for (int t = tid; t < ntiles; t += nt) {
+            int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+            while (ti * (ti + 1) / 2 > t) ti--;
+            while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+            const int tj = t - ti * (ti + 1) / 2;
+            const int i0 = ke + 4 * ti, j0 = ke + 4 * tj;
+            size_t ibase[4], jbase[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int ii = min(i0 + r, n - 1), jj = min(j0 + r, n - 1);
+                ibase[r] = (size_t)ii * (ii + 1) / 2;
+                jbase[r] = (size_t)jj * (jj + 1) / 2;
+            }
+            double acc[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc[r][q] = 0.0;
+#pragma unroll
+            for (int c = 0; c < CHOL_NB; c++) {
+                if (c < w) {
+                    double li[4], lj[4];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        li[r] = Lp[ibase[r] + kb + c];
+                        lj[r] = Lp[jbase[r] + kb + c];
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+#pragma unroll
+                        for (int q = 0; q < 4; q++) acc[r][q] += li[r] * lj[q];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (i0 + r < n && j0 + q <= i0 + r) Lp[ibase[r] + j0 + q] -= acc[r][q];
         }
         __syncthreads();
     }
     return true;
 }
 
-// Solves L L^T y = b with the packed factor, single warp (warp 0), y in/out in `y` (global or shared).
-__device__ void chol_solve_packed(const double* Lp, int n, double* y) {
+// Solves L L^T y = b with the packed factor, single warp (warp 0); y (in/out) must be in shared memory.
+__device__ void chol_solve_packed(const double* Lp, const double* rdiag, int n, double* y) {
     if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
-    auto at = [&](int i, int j) { return Lp[(size_t)i * (i + 1) / 2 + j]; };
-    for (int k = 0; k < n; k++) {  // forward
-        double yk = 0;
-        if (lane == (k & 31)) {
-            yk = y[k] / at(k, k);
-            y[k] = yk;
-        }
-        yk = __shfl_sync(0xffffffffu, yk, k & 31);
-        for (int i = k + 1 + ((lane - (k + 1)) & 31); i < n; i += 32) y[i] -= at(i, k) * yk;
+    for (int k = 0; k < n; k++) {  // forward: L z = b
+        const double yk = y[k] * rdiag[k];
+        __syncwarp();
+        if (lane == 0) y[k] = yk;
+        for (int i = k + 1 + lane; i < n; i += 32) y[i] -= Lp[(size_t)i * (i + 1) / 2 + k] * yk;
         __syncwarp();
     }
-    for (int k = n - 1; k >= 0; k--) {  // backward
-        double yk = 0;
-        if (lane == (k & 31)) {
-            yk = y[k] / at(k, k);
-            y[k] = yk;
-        }
-        yk = __shfl_sync(0xffffffffu, yk, k & 31);
-        for (int i = lane; i < k; i += 32) y[i] -= at(k, i) * yk;
+    for (int k = n - 1; k >= 0; k--) {  // backward: L^T y = z
+        const double yk = y[k] * rdiag[k];
+        __syncwarp();
+        if (lane == 0) y[k] = yk;
+        const size_t kb = (size_t)k * (k + 1) / 2;
+        for (int i = lane; i < k; i += 32) y[i] -= Lp[kb + i] * yk;
         __syncwarp();
     }
 }
@@ -665,6 +742,7 @@ __device__ void reduce_single_cta(const BaProblem& p, const BaAccum& a, double m
         const double h = p.Hfull[idx];
         p.S[idx] = h - acc;
         p.S[(size_t)c * D + r] = h - acc;
+        p.Spk[(size_t)c * (c + 1) / 2 + r] = h - acc;
     }
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
         double acc = 0;
@@ -676,9 +754,11 @@ __device__ void reduce_single_cta(const BaProblem& p, const BaAccum& a, double m
 
 }  // namespace
 
-__global__ void __launch_bounds__(1024) ba_step_kernel(BaProblem p, int use_smem_chol) {
+#define STEP_MAXD 352
+__global__ void __launch_bounds__(512) ba_step_kernel(BaProblem p, int use_smem_chol) {
     extern __shared__ double chol_smem[];
     __shared__ double red[32];
+    __shared__ double rdiag[STEP_MAXD], ysm[STEP_MAXD];
     __shared__ int flag;
     SolverState* st = p.st;
     if (st->done) return;
@@ -689,17 +769,19 @@ __global__ void __launch_bounds__(1024) ba_step_kernel(BaProblem p, int use_smem
     const BaDims& d = p.dims;
     const int D = d.D, L = d.L, N = D + L;
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     const int cur = st->cur;
     const BaAccum a = p.acc[cur];
-    double* u = p.work;            // N
-    double* y = p.work + N;        // N
-    double* delta = p.work + 2 * N;  // N
+    double* u = p.work;              // N  Cauchy direction (unscaled variables)
+    double* y = p.work + N;          // N  Gauss-Newton solution
+    double* delta = p.work + 2 * N;  // N  step in the original variables
     double* Lp = use_smem_chol ? chol_smem : p.work + 4 * (size_t)N;  // packed factor
     const int first = st->first;
     double mu = st->mu;
     bool linear_ok = true;
+    long long c0 = clock64();
+#define STAMP(k) do { if (tid == 0) { const long long c1_ = clock64(); st->clk[k] += c1_ - c0; c0 = c1_; } } while (0)
     if (!st->reuse) {
-        double gg_part = 0;
         for (int j = tid; j < N; j += nt) {
             const double hjj = j < D ? p.Hfull[(size_t)j * D + j] : a.Hll[j - D];
             const double gj = j < D ? a.gp[j] : a.gl[j - D];
@@ -708,32 +790,25 @@ __global__ void __launch_bounds__(1024) ba_step_kernel(BaProblem p, int use_smem
             const double d2 = fmin(fmax(hjj * s * s, 1e-6), 1e32);
             const double dg = sqrt(d2);
             p.diag[j] = dg;
-            const double g = gj * s / dg;
-            p.grad[j] = g;
-            u[j] = g / dg * s;
-            gg_part += g * g;
+            p.grad[j] = gj * s / dg;
         }
-        const double gg = block_sum(gg_part, red);
-        const double uHu = quad_form(p, a, u, nullptr, red);
-        const double alpha = gg / uHu;
-        // regularised Gauss-Newton step: (S + mu E_p) y_p = gred
+        __syncthreads();
+        STAMP(0);
+        // regularised Gauss-Newton step: (S + mu E_p) y_p = gred, E = diag^2 / scale^2
         linear_ok = false;
+        const int npk = D * (D + 1) / 2;
         while (mu < 1.0) {
-            for (int idx = tid; idx < D * (D + 1) / 2; idx += nt) {
-                // idx -> (i, j) of the packed lower triangle
-                int i = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
-                while ((size_t)i * (i + 1) / 2 > (size_t)idx) i--;
-                while ((size_t)(i + 1) * (i + 2) / 2 <= (size_t)idx) i++;
-                const int j = idx - i * (i + 1) / 2;
-                double v = p.S[(size_t)i * D + j];
-                if (i == j) {
-                    const double s = p.scale[i];
-                    v += mu * (p.diag[i] * p.diag[i]) / (s * s);
-                }
-                Lp[idx] = v;
+            for (int idx = tid; idx < npk; idx += nt) Lp[idx] = p.Spk[idx];
+            __syncthreads();
+            for (int i = tid; i < D; i += nt) {
+                const double s_ = p.scale[i];
+                Lp[(size_t)i * (i + 1) / 2 + i] += mu * (p.diag[i] * p.diag[i]) / (s_ * s_);
             }
             __syncthreads();
-            if (cholesky_packed(Lp, D, &flag)) {
+            STAMP(2);
+            const bool ok_ = cholesky_packed(Lp, D, rdiag, &flag);
+            STAMP(3);
+            if (ok_) {
                 linear_ok = true;
                 break;
             }
@@ -743,25 +818,27 @@ __global__ void __launch_bounds__(1024) ba_step_kernel(BaProblem p, int use_smem
             if (mu < 1.0) reduce_single_cta(p, a, mu, first);
         }
         if (linear_ok) {
-            for (int j = tid; j < D; j += nt) y[j] = p.gred[j];
+            for (int j = tid; j < D; j += nt) ysm[j] = p.gred[j];
             __syncthreads();
-            chol_solve_packed(Lp, D, y);
+            chol_solve_packed(Lp, rdiag, D, ysm);
             __syncthreads();
-            const int lane = tid & 31, wid = tid >> 5, nw = nt / 32;
+            STAMP(4);
+            for (int j = tid; j < D; j += nt) y[j] = ysm[j];
             for (int l = wid; l < L; l += nw) {
                 double s = 0;
-                for (int c = lane; c < D; c += 32) s += a.Hpl[(size_t)l * D + c] * y[c];
+                for (int c = lane; c < D; c += 32) s += a.Hpl[(size_t)l * D + c] * ysm[c];
                 s = warp_sum_d(s);
                 if (lane == 0) y[D + l] = (a.gl[l] - s) * lm_inv_lambda(p, a, l, mu, first);
             }
             __syncthreads();
             for (int j = tid; j < N; j += nt) p.gn[j] = -p.diag[j] * y[j] / p.scale[j];
+            STAMP(5);
         }
         if (tid == 0) {
-            st->alpha = alpha;
             st->mu = mu;
             st->reuse = 1;
             st->first = 0;
+            st->alpha_valid = 0;
         }
         __syncthreads();
     }
@@ -777,38 +854,64 @@ __global__ void __launch_bounds__(1024) ba_step_kernel(BaProblem p, int use_smem
         }
         const double gg = block_sum(p1, red), nn = block_sum(p2, red), gdn = block_sum(p3, red);
         const double gradient_norm = sqrt(gg), gn_norm = sqrt(nn);
-        const double radius = st->radius, alpha = st->alpha;
-        double ca = 0, cb = 0;  // step = ca * gradient + cb * gauss_newton
+        const double radius = st->radius;
+        double ca = 0, cb = 0;  // step = ca * gradient + cb * gauss_newton  (trust-region-scaled space)
         if (gn_norm <= radius) {
             cb = 1.0;
             dogleg_norm = gn_norm;
-        } else if (gradient_norm * alpha >= radius) {
-            ca = -(radius / gradient_norm);
-            dogleg_norm = radius;
         } else {
-            const double b_dot_a = -alpha * gdn;
-            const double a_sq = (alpha * gradient_norm) * (alpha * gradient_norm);
-            const double bma = a_sq - 2 * b_dot_a + gn_norm * gn_norm;
-            const double c = b_dot_a - a_sq;
-            const double dd = sqrt(c * c + bma * (radius * radius - a_sq));
-            const double beta = (c <= 0) ? (dd - c) / bma : (radius * radius - a_sq) / (dd + c);
-            ca = -alpha * (1.0 - beta);
-            cb = beta;
-            dogleg_norm = -1.0;  // computed below
+            // The Cauchy step length alpha = |g|^2 / |J D^-1 g|^2 needs one product with the full Hessian; it is
+            // only evaluated when the Gauss-Newton step leaves the trust region (never at the default radius 1e4
+            // unless steps were rejected).
+            if (!st->alpha_valid) {
+                for (int j = tid; j < N; j += nt) u[j] = p.grad[j] / p.diag[j] * p.scale[j];
+                __syncthreads();
+                const double uHu = quad_form(p, a, u, nullptr, red);
+                if (tid == 0) {
+                    st->alpha = gg / uHu;
+                    st->alpha_valid = 1;
+                }
+                __syncthreads();
+            }
+            const double alpha = st->alpha;
+            if (gradient_norm * alpha >= radius) {
+                ca = -(radius / gradient_norm);
+                dogleg_norm = radius;
+            } else {
+                const double b_dot_a = -alpha * gdn;
+                const double a_sq = (alpha * gradient_norm) * (alpha * gradient_norm);
+                const double bma = a_sq - 2 * b_dot_a + gn_norm * gn_norm;
+                const double c = b_dot_a - a_sq;
+                const double dd = sqrt(c * c + bma * (radius * radius - a_sq));
+                const double beta = (c <= 0) ? (dd - c) / bma : (radius * radius - a_sq) / (dd + c);
+                ca = -alpha * (1.0 - beta);
+                cb = beta;
+                dogleg_norm = -1.0;  // computed below
+            }
         }
-        double pn = 0, pg = 0;
+        double pn = 0, pg = 0, pe = 0;
         for (int j = tid; j < N; j += nt) {
             const double sd = ca * p.grad[j] + cb * p.gn[j];
             pn += sd * sd;
-            const double dl = sd / p.diag[j] * p.scale[j];  // undo trust-region diagonal and Jacobi scaling
+            const double s_ = p.scale[j];
+            const double dl = sd / p.diag[j] * s_;  // undo trust-region diagonal and Jacobi scaling
             delta[j] = dl;
             pg += dl * (j < D ? a.gp[j] : a.gl[j - D]);
+            pe += dl * dl * (p.diag[j] * p.diag[j]) / (s_ * s_);
         }
-        const double sn = block_sum(pn, red), dg = block_sum(pg, red);
+        const double sn = block_sum(pn, red), dg = block_sum(pg, red), dEd = block_sum(pe, red);
         if (dogleg_norm < 0) dogleg_norm = sqrt(sn);
-        const double dHd = quad_form(p, a, delta, nullptr, red);
+        double dHd;
+        if (ca == 0.0 && cb == 1.0) {
+            // full Gauss-Newton step: (H + mu E) delta = -g  =>  delta^T H delta = -delta^T g - mu delta^T E delta
+            dHd = -dg - st->mu * dEd;
+        } else {
+            __syncthreads();
+            dHd = quad_form(p, a, delta, nullptr, red);
+        }
         mcc = -(dg + 0.5 * dHd);
         valid = mcc > 0.0;
+        STAMP(6);
     }
     if (!valid) {  // HandleInvalidStep + DoglegStrategy::StepIsInvalid
         if (tid == 0) {
@@ -823,6 +926,7 @@ __global__ void __launch_bounds__(1024) ba_step_kernel(BaProblem p, int use_smem
         return;
     }
     // ---- candidate point and the norms the tolerance tests need
+    __syncthreads();
     const BaStates xc = p.x[cur], xn = p.x[1 - cur];
     double xs = 0, ss = 0;
     const int F = d.W + 1;
@@ -869,6 +973,7 @@ __global__ void __launch_bounds__(1024) ba_step_kernel(BaProblem p, int use_smem
         ss += (o - nv) * (o - nv);
     }
     const double x_norm2 = block_sum(xs, red), step_norm2 = block_sum(ss, red);
+    STAMP(7);
     if (tid == 0) {
         st->iteration++;
         st->cand_valid = 1;
@@ -990,47 +1095,45 @@ __global__ void __launch_bounds__(128) marg_build_kernel(BaProblem p, MargPlan m
 
 namespace {
 
-// Cyclic Jacobi with round-robin parallel ordering on an n x n symmetric matrix in shared memory.
-// A is overwritten (eigenvalues on the diagonal), V receives the eigenvectors (columns).
-__device__ void jacobi_eigen(double* A, double* V, int n, double* cs, int* pq, double* red) {
+// Cyclic Jacobi with round-robin parallel ordering on a symmetric matrix in shared memory.
+// A is ld x ld with ld even and >= n, rows/columns >= n zero (a zero row never rotates).  On exit the
+// eigenvalues are on the diagonal and V (ld x ld) holds the eigenvectors in its columns.  Each round applies
+// ld/2 disjoint rotations: one phase computes (c, s) per pair, one phase updates every 2x2 block
+// G_k^T A_(k,k') G_k' and V G_k, i.e. two barriers per round.  Sweeps stop when no pair needed a rotation under
+// |a_pq| > 1e-15 sqrt|a_pp a_qq| (relative criterion, resolves the small eigenvalues of badly scaled matrices).
+__device__ void jacobi_eigen(double* A, double* V, int ld, double* cs, int* pq, int* flags) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int ne = n + (n & 1), half = ne / 2;
-    for (int i = tid; i < n * n; i += nt) V[i] = (i / n == i % n) ? 1.0 : 0.0;
+    const int half = ld / 2;
+    for (int i = tid; i < ld * ld; i += nt) V[i] = (i / ld == i % ld) ? 1.0 : 0.0;
+    if (tid < 2) flags[tid] = 0;
+    double amax = 0;  // largest |diagonal|: entries below 1e-16 of it are round-off of the large rotations
+    for (int i = 0; i < ld; i++) amax = fmax(amax, fabs(A[i * ld + i]));
+    const double floor_abs = 1e-16 * amax;
     __syncthreads();
     for (int sweep = 0; sweep < 40; sweep++) {
-        double off = 0, dg = 0;
-        for (int i = tid; i < n * n; i += nt) {
-            const int r = i / n, c = i % n;
-            const double v = A[i];
-            if (r == c) dg += v * v;
-            else if (r < c) off += v * v;
-        }
-        off = block_sum(off, red);
-        dg = block_sum(dg, red);
-        if (off <= 1e-30 * dg || off == 0.0) break;
-        for (int round = 0; round < ne - 1; round++) {
+        int* flag = &flags[sweep & 1];
+        for (int round = 0; round < ld - 1; round++) {
             if (tid < half) {
                 int a, b;
                 if (tid == 0) {
-                    a = ne - 1;
+                    a = ld - 1;
                     b = round;
                 } else {
-                    a = (round + tid) % (ne - 1);
-                    b = (round - tid + (ne - 1)) % (ne - 1);
+                    a = (round + tid) % (ld - 1);
+                    b = (round - tid + (ld - 1)) % (ld - 1);
                 }
-                int pp = min(a, b), qq = max(a, b);
+                const int pp = min(a, b), qq = max(a, b);
                 double c = 1.0, s = 0.0;
-                if (qq < n) {
-                    const double apq = A[pp * n + qq];
-                    const double app = A[pp * n + pp], aqq = A[qq * n + qq];
-                    if (apq != 0.0 && fabs(apq) > 1e-300 + 1e-18 * sqrt(fabs(app * aqq))) {
+                const double apq = A[pp * ld + qq];
+                if (apq != 0.0) {
+                    const double app = A[pp * ld + pp], aqq = A[qq * ld + qq];
+                    if (fabs(apq) > fmax(floor_abs, 1e-15 * sqrt(fabs(app * aqq)))) {
                         const double theta = (aqq - app) / (2 * apq);
                         const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
                         c = 1 / sqrt(t * t + 1);
                         s = t * c;
+                        *flag = 1;
                     }
-                } else {
-                    pp = -1;
                 }
                 pq[2 * tid] = pp;
                 pq[2 * tid + 1] = qq;
@@ -1038,52 +1141,56 @@ __device__ void jacobi_eigen(double* A, double* V, int n, double* cs, int* pq, d
                 cs[2 * tid + 1] = s;
             }
             __syncthreads();
-            for (int w = tid; w < half * n; w += nt) {  // columns: A <- A J, V <- V J
-                const int k = w / n, i = w % n;
-                const int pp = pq[2 * k], qq = pq[2 * k + 1];
-                if (pp < 0) continue;
-                const double c = cs[2 * k], s = cs[2 * k + 1];
-                if (s == 0.0) continue;
-                const double aip = A[i * n + pp], aiq = A[i * n + qq];
-                A[i * n + pp] = c * aip - s * aiq;
-                A[i * n + qq] = s * aip + c * aiq;
-                const double vip = V[i * n + pp], viq = V[i * n + qq];
-                V[i * n + pp] = c * vip - s * viq;
-                V[i * n + qq] = s * vip + c * viq;
+            for (int w = tid; w < half * half; w += nt) {
+                const int k = w / half, k2 = w - k * half;
+                const double c1 = cs[2 * k], s1 = cs[2 * k + 1], c2 = cs[2 * k2], s2 = cs[2 * k2 + 1];
+                if (s1 == 0.0 && s2 == 0.0) continue;
+                const int p0 = pq[2 * k], q0 = pq[2 * k + 1], p2 = pq[2 * k2], q2 = pq[2 * k2 + 1];
+                const double a00 = A[p0 * ld + p2], a01 = A[p0 * ld + q2], a10 = A[q0 * ld + p2], a11 = A[q0 * ld + q2];
+                const double t00 = c2 * a00 - s2 * a01, t01 = s2 * a00 + c2 * a01;
+                const double t10 = c2 * a10 - s2 * a11, t11 = s2 * a10 + c2 * a11;
+                A[p0 * ld + p2] = c1 * t00 - s1 * t10;
+                A[q0 * ld + p2] = s1 * t00 + c1 * t10;
+                A[p0 * ld + q2] = c1 * t01 - s1 * t11;
+                A[q0 * ld + q2] = s1 * t01 + c1 * t11;
             }
-            __syncthreads();
-            for (int w = tid; w < half * n; w += nt) {  // rows: A <- J^T A
-                const int k = w / n, j = w % n;
+            for (int w = tid; w < half * ld; w += nt) {
+                const int k = w / ld, i = w - k * ld;
+                const double c = cs[2 * k], s_ = cs[2 * k + 1];
+                if (s_ == 0.0) continue;
                 const int pp = pq[2 * k], qq = pq[2 * k + 1];
-                if (pp < 0) continue;
-                const double c = cs[2 * k], s = cs[2 * k + 1];
-                if (s == 0.0) continue;
-                const double apj = A[pp * n + j], aqj = A[qq * n + j];
-                A[pp * n + j] = c * apj - s * aqj;
-                A[qq * n + j] = s * apj + c * aqj;
+                const double vip = V[i * ld + pp], viq = V[i * ld + qq];
+                V[i * ld + pp] = c * vip - s_ * viq;
+                V[i * ld + qq] = s_ * vip + c * viq;
             }
             __syncthreads();
         }
+        const int any = *flag;
+        if (tid == 0) flags[(sweep + 1) & 1] = 0;
+        __syncthreads();
+        if (!any) break;
     }
 }
 
 }  // namespace
 
-// Single CTA.  Dynamic shared memory: Wk (q x q), Ev (max(md, n)^2), Vv (same), bw (q), misc.
-__global__ void __launch_bounds__(1024) marg_solve_kernel(MargPlan mp, double eps) {
+// Single CTA.  Dynamic shared memory: Wk (q x q), Ev and Vv (ldx x ldx, ldx = even(max(md, n))), bw (q), tv (ldx).
+__global__ void __launch_bounds__(512) marg_solve_kernel(MargPlan mp, double eps) {
     extern __shared__ double sm[];
     __shared__ double red[32];
     __shared__ double cs[2 * 96];
     __shared__ int pq[2 * 96];
+    __shared__ int jflags[2];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int md = mp.m_dense, nl = mp.n_lm, n = mp.n, P = mp.P;
     const int q = md + n;
-    const int ne = max(md, n);
-    double* Wk = sm;                 // q*q
-    double* Ev = Wk + q * q;         // ne*ne
-    double* Vv = Ev + ne * ne;       // ne*ne
-    double* bw = Vv + ne * ne;       // q
-    double* tv = bw + q;             // ne
+    const int ldm = md + (md & 1), ldn = n + (n & 1), ldx = max(ldm, ldn);
+    const int esz = max(ldx * ldx, n * (ldm + md));
+    double* Wk = sm;                  // q*q
+    double* Ev = Wk + q * q;          // esz
+    double* Vv = Ev + esz;            // ldx*ldx
+    double* bw = Vv + ldx * ldx;      // q
+    double* tv = bw + q;              // ldx
     auto symA = [&](int a, int b) { return a <= b ? mp.Am[(size_t)a * P + b] : mp.Am[(size_t)b * P + a]; };
     auto full = [&](int a) { return a < md ? a : a + nl; };  // index in Am of reduced index a
     // 1. eliminate the landmark columns (exactly diagonal block): rank-1 downdates
@@ -1094,8 +1201,10 @@ __global__ void __launch_bounds__(1024) marg_solve_kernel(MargPlan mp, double ep
         double acc = symA(fa, fb);
         for (int c = 0; c < nl; c++) {
             const int fc = md + c;
+            const double wa = symA(fa, fc);
+            if (wa == 0.0) continue;
             const double dc = mp.Am[(size_t)fc * P + fc];
-            if (dc > eps) acc -= symA(fa, fc) * symA(fb, fc) / dc;
+            if (dc > eps) acc -= wa * symA(fb, fc) / dc;
         }
         Wk[aa * q + bb] = acc;
         Wk[bb * q + aa] = acc;
@@ -1112,80 +1221,83 @@ __global__ void __launch_bounds__(1024) marg_solve_kernel(MargPlan mp, double ep
     }
     __syncthreads();
     // 2. pseudo-inverse of the dense marginalised block T (md x md) by eigen-decomposition
-    for (int idx = tid; idx < md * md; idx += nt) Ev[idx] = Wk[(idx / md) * q + idx % md];
-    __syncthreads();
-    jacobi_eigen(Ev, Vv, md, cs, pq, red);
-    __syncthreads();
-    // Tinv = V diag(1/w > eps) V^T  (stored back into Ev's off-diagonal-free copy: use tv for 1/w)
-    for (int k = tid; k < md; k += nt) {
-        const double w = Ev[k * md + k];
-        tv[k] = w > eps ? 1.0 / w : 0.0;
+    for (int idx = tid; idx < ldm * ldm; idx += nt) {
+        const int i = idx / ldm, j = idx % ldm;
+        Ev[idx] = (i < md && j < md) ? Wk[i * q + j] : 0.0;
     }
     __syncthreads();
-    for (int idx = tid; idx < md * md; idx += nt) {
-        const int i = idx / md, j = idx % md;
+    jacobi_eigen(Ev, Vv, ldm, cs, pq, jflags);
+    for (int k = tid; k < ldm; k += nt) {
+        const double w = Ev[k * ldm + k];
+        tv[k] = (k < md && w > eps) ? 1.0 / w : 0.0;
+    }
+    __syncthreads();
+    // 3. X = Wrm Tinv (n x md) computed directly from the eigen-factors: X = (Wrm V) diag(tv) V^T
+    //    Y = Wrm V  -> stored in Ev as n x ldm (Ev is free: eigenvalues already consumed into tv)
+    for (int idx = tid; idx < n * ldm; idx += nt) {
+        const int i = idx / ldm, k = idx % ldm;
         double s = 0;
-        for (int k = 0; k < md; k++) s += Vv[i * md + k] * tv[k] * Vv[j * md + k];
-        Ev[idx] = s;  // diagonal eigenvalues no longer needed
+        for (int j = 0; j < md; j++) s += Wk[(md + i) * q + j] * Vv[j * ldm + k];
+        Ev[idx] = s * tv[k];
     }
     __syncthreads();
-    // 3. A' = Wrr - Wrm Tinv Wmr ; b' = br - Wrm Tinv bm.  X = Wrm Tinv (n x md) kept in Vv
+    double* X = Ev + (size_t)n * ldm;  // n x md (Ev holds max(ldx^2, n (ldm + md)) doubles)
     for (int idx = tid; idx < n * md; idx += nt) {
         const int i = idx / md, j = idx % md;
         double s = 0;
-        for (int k = 0; k < md; k++) s += Wk[(md + i) * q + k] * Ev[k * md + j];
-        Vv[idx] = s;
+        for (int k = 0; k < ldm; k++) s += Ev[i * ldm + k] * Vv[j * ldm + k];
+        X[idx] = s;
     }
     __syncthreads();
     double* Ap = mp.Aout;  // n x n (global, becomes the prior's A after thresholding)
     for (int idx = tid; idx < n * n; idx += nt) {
         const int i = idx / n, j = idx % n;
         double s = Wk[(md + i) * q + md + j];
-        for (int k = 0; k < md; k++) s -= Vv[i * md + k] * Wk[k * q + md + j];
+        for (int k = 0; k < md; k++) s -= X[i * md + k] * Wk[k * q + md + j];
         Ap[idx] = s;
     }
     for (int i = tid; i < n; i += nt) {
         double s = bw[md + i];
-        for (int k = 0; k < md; k++) s -= Vv[i * md + k] * bw[k];
+        for (int k = 0; k < md; k++) s -= X[i * md + k] * bw[k];
         mp.gout[i] = s;
     }
     __syncthreads();
-    // keep the un-thresholded A', b' for parity tests
     if (mp.Araw)
         for (int idx = tid; idx < n * n; idx += nt) mp.Araw[idx] = 0.5 * (Ap[idx] + Ap[(idx % n) * n + idx / n]);
     if (mp.graw)
         for (int i = tid; i < n; i += nt) mp.graw[i] = mp.gout[i];
     // 4. eigen-decomposition of A' with the eps floor: A+ = V S+ V^T, g0 = V 1+ V^T b', c0 = b'^T V S+^-1 V^T b'
-    for (int idx = tid; idx < n * n; idx += nt) Ev[idx] = 0.5 * (Ap[idx] + Ap[(idx % n) * n + idx / n]);
+    for (int idx = tid; idx < ldn * ldn; idx += nt) {
+        const int i = idx / ldn, j = idx % ldn;
+        Ev[idx] = (i < n && j < n) ? 0.5 * (Ap[i * n + j] + Ap[j * n + i]) : 0.0;
+    }
     __syncthreads();
-    jacobi_eigen(Ev, Vv, n, cs, pq, red);
-    __syncthreads();
-    for (int k = tid; k < n; k += nt) {
+    jacobi_eigen(Ev, Vv, ldn, cs, pq, jflags);
+    for (int k = tid; k < ldn; k += nt) {
         double s = 0;
-        for (int i = 0; i < n; i++) s += Vv[i * n + k] * mp.gout[i];
+        for (int i = 0; i < n; i++) s += Vv[i * ldn + k] * mp.gout[i];
         tv[k] = s;  // V_k^T b'
     }
     __syncthreads();
     double cpart = 0;
-    for (int k = tid; k < n; k += nt) {
-        const double w = Ev[k * n + k];
+    for (int k = tid; k < ldn; k += nt) {
+        const double w = Ev[k * ldn + k];
         if (w > eps) cpart += tv[k] * tv[k] / w;
     }
     const double c0 = block_sum(cpart, red);
     for (int idx = tid; idx < n * n; idx += nt) {
         const int i = idx / n, j = idx % n;
         double s = 0;
-        for (int k = 0; k < n; k++) {
-            const double w = Ev[k * n + k];
-            if (w > eps) s += Vv[i * n + k] * w * Vv[j * n + k];
+        for (int k = 0; k < ldn; k++) {
+            const double w = Ev[k * ldn + k];
+            if (w > eps) s += Vv[i * ldn + k] * w * Vv[j * ldn + k];
         }
         Ap[idx] = s;
     }
-    __syncthreads();
     for (int i = tid; i < n; i += nt) {
         double s = 0;
-        for (int k = 0; k < n; k++)
-            if (Ev[k * n + k] > eps) s += Vv[i * n + k] * tv[k];
+        for (int k = 0; k < ldn; k++)
+            if (Ev[k * ldn + k] > eps) s += Vv[i * ldn + k] * tv[k];
         bw[i] = s;
     }
     __syncthreads();
@@ -1194,8 +1306,10 @@ __global__ void __launch_bounds__(1024) marg_solve_kernel(MargPlan mp, double ep
 }
 
 size_t marg_solve_smem_bytes(int m_dense, int n) {
-    const int q = m_dense + n, ne = m_dense > n ? m_dense : n;
-    return sizeof(double) * ((size_t)q * q + 2 * (size_t)ne * ne + q + ne);
+    const int q = m_dense + n;
+    const int ldm = m_dense + (m_dense & 1), ldn = n + (n & 1), ldx = ldm > ldn ? ldm : ldn;
+    const size_t esz = std::max((size_t)ldx * ldx, (size_t)n * (ldm + m_dense));
+    return sizeof(double) * ((size_t)q * q + esz + (size_t)ldx * ldx + q + ldx);
 }
 
 }  // namespace vb
@@ -1223,21 +1337,27 @@ void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int
     const int zero_grid = 64;
     const int tiles = (d.D + ST - 1) / ST;
     const size_t chol_bytes = sizeof(double) * (size_t)d.D * (d.D + 1) / 2;
-    static int smem_limit = -1;
+    static int smem_limit = -1, smem_static = 0, smem_configured = 0;
     if (smem_limit < 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        cudaFuncSetAttribute(ba_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit - 1024);
+        cudaFuncAttributes fa{};
+        cudaFuncGetAttributes(&fa, ba_step_kernel);
+        smem_static = (int)fa.sharedSizeBytes;
     }
-    const int use_smem = chol_bytes + 1024 <= (size_t)smem_limit ? 1 : 0;
+    const int use_smem = chol_bytes + (size_t)smem_static + 256 <= (size_t)smem_limit ? 1 : 0;
+    if (use_smem && (int)chol_bytes > smem_configured) {
+        cudaFuncSetAttribute(ba_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_bytes);
+        smem_configured = (int)chol_bytes;
+    }
     int n = 0;
     ba_zero_kernel<<<zero_grid, 256, 0, s>>>(p, 1);
     ba_linearize_kernel<<<lin_grid, 32 * LIN_WARPS, 0, s>>>(p, 1);
     n += 2;
     for (int it = 0; it < max_iterations; it++) {
         ba_schur_kernel<<<dim3(tiles, tiles), dim3(ST, ST), 0, s>>>(p);
-        ba_step_kernel<<<1, 1024, use_smem ? chol_bytes : 0, s>>>(p, use_smem);
+        ba_step_kernel<<<1, 512, use_smem ? chol_bytes : 0, s>>>(p, use_smem);
         ba_zero_kernel<<<zero_grid, 256, 0, s>>>(p, 0);
         ba_linearize_kernel<<<lin_grid, 32 * LIN_WARPS, 0, s>>>(p, 0);
         n += 4;
@@ -1256,7 +1376,7 @@ void launch_marginalize(const BaProblem& p, const MargPlan& mp, cudaStream_t s, 
         cudaFuncSetAttribute(marg_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    marg_solve_kernel<<<1, 1024, smem, s>>>(mp, 1e-8);
+    marg_solve_kernel<<<1, 512, smem, s>>>(mp, 1e-8);
     if (launches) *launches += 2;
 }
 

@@ -69,10 +69,12 @@ struct SolverState {  // trust-region / dogleg state, lives in device memory
     int done;        // 0 running; 1 iteration cap; 2 parameter tol; 3 function tol; 4 failure
     int cur;         // which of the two state/accumulation buffers holds the current point
     int reuse, cand_valid, first, successful, retries, invalid_streak;
+    int alpha_valid, pad2;
     unsigned lin_ticket;
     int pad;
     double radius, mu, x_cost, cand_cost, model_cost_change, dogleg_step_norm, alpha, x_norm, step_norm;
     double initial_cost;
+    long long clk[10];  // per-phase cycle counters of the last ba_step_kernel (profiling aid)
 };
 
 struct BaProblem {
@@ -97,6 +99,7 @@ struct BaProblem {
     BaPrior prior;
     // solver workspace
     double* S;       // D x D Schur complement (full symmetric)
+    double* Spk;     // the same, packed row-major lower triangle (what the Cholesky consumes)
     double* Hfull;   // D x D symmetrised Hpp
     double* gred;    // D
     double* scale;   // D + L Jacobi scaling

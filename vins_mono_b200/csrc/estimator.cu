@@ -114,7 +114,7 @@ struct ve_estimator {
     DeviceBuf<double> d_acc[2];      // Hpp | gp | Hpl | Hll | gl | cost
     DeviceBuf<int> d_ints;           // lm_anchor | lm_start | ob_frame | imu_slot
     DeviceBuf<double> d_obs;         // lm_pts | lm_vel | lm_td | lm_row | ob_pts | ob_vel | ob_td | ob_row
-    DeviceBuf<double> d_S, d_Hfull, d_gred, d_vec, d_work;
+    DeviceBuf<double> d_S, d_Spk, d_Hfull, d_gred, d_vec, d_work;
     DeviceBuf<vb::SolverState> d_st;
     DeviceBuf<double> d_prior[2];    // A | g0 | c0 | x0
     DeviceBuf<int> d_prior_i[2];     // type | index | off
@@ -627,6 +627,7 @@ int build_problem(ve_estimator* e, vb::BaProblem& p, bool upload_tables) {
     p.preint = e->d_preint.p;
     p.prior = prior_view(e);
     p.S = e->d_S.p;
+    p.Spk = e->d_Spk.p;
     p.Hfull = e->d_Hfull.p;
     p.gred = e->d_gred.p;
     const size_t N = (size_t)e->D + e->Lmax;
@@ -733,6 +734,7 @@ int marginalize(ve_estimator* e, vb::BaProblem& p) {
     mp.cout = mp.gout + e->nmax;
     // NOTE: Aout is written with leading dimension n (dense n x n at the front of the buffer)
     vb::launch_marginalize(p, mp, e->stream, &e->last_launches);
+    VE_CUDA(cudaGetLastError());
     // new prior: linearisation point = current parameter values of the kept blocks, identities shifted
     // (addr_shift, estimator.cpp:913-925 / :969-990)
     double* x0 = e->h_prior;
@@ -789,6 +791,7 @@ int optimization(ve_estimator* e) {
     st.mu = 1e-8;
     VE_CUDA(cudaMemcpyAsync(e->d_st.p, &st, sizeof(st), cudaMemcpyHostToDevice, e->stream));
     vb::launch_ba_solve(p, e->cfg.num_iterations, e->stream, &e->last_launches);
+    VE_CUDA(cudaGetLastError());
     VE_CUDA(cudaMemcpyAsync(&st, e->d_st.p, sizeof(st), cudaMemcpyDeviceToHost, e->stream));
     const size_t ns = states_doubles(e);
     double* h2 = e->h_states + ns;  // second half of the staging area holds both device buffers
@@ -938,6 +941,7 @@ int ve_create(const ve_config* cfg, ve_estimator** out) {
     VE_TRY(e->d_ints.alloc((size_t)2 * e->Lmax + 1 + e->Mmax + W));
     VE_TRY(e->d_obs.alloc(6 * (size_t)e->Lmax + 6 * (size_t)e->Mmax));
     VE_TRY(e->d_S.alloc((size_t)e->D * e->D));
+    VE_TRY(e->d_Spk.alloc((size_t)e->D * (e->D + 1) / 2));
     VE_TRY(e->d_Hfull.alloc((size_t)e->D * e->D));
     VE_TRY(e->d_gred.alloc(e->D));
     VE_TRY(e->d_vec.alloc(4 * ((size_t)e->D + e->Lmax)));
@@ -966,7 +970,7 @@ void ve_destroy(ve_estimator* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     e->d_preint.release(); e->d_samples.release(); e->d_which.release();
     for (int b = 0; b < 2; b++) { e->d_states[b].release(); e->d_acc[b].release(); e->d_prior[b].release(); e->d_prior_i[b].release(); }
-    e->d_ints.release(); e->d_obs.release(); e->d_S.release(); e->d_Hfull.release(); e->d_gred.release(); e->d_vec.release();
+    e->d_ints.release(); e->d_obs.release(); e->d_S.release(); e->d_Spk.release(); e->d_Hfull.release(); e->d_gred.release(); e->d_vec.release();
     e->d_work.release(); e->d_st.release(); e->d_marg.release(); e->d_marg_i.release();
     cudaFreeHost(e->h_states); cudaFreeHost(e->h_obs); cudaFreeHost(e->h_ints); cudaFreeHost(e->h_samples); cudaFreeHost(e->h_preint);
     cudaFreeHost(e->h_st); cudaFreeHost(e->h_prior); cudaFreeHost(e->h_prior_i); cudaFreeHost(e->h_marg_i); cudaFreeHost(e->h_marg_out);
@@ -1093,6 +1097,15 @@ int ve_get_prior(const ve_estimator* e, int cap, double* A, double* b, int* nblo
             blocks4[4 * k + 3] = e->prior_blocks[k].size;
         }
     return n;
+}
+
+int ve_solver_debug(const ve_estimator* e, double* out13) {
+    if (!e || !out13) return VE_ERR_INVALID;
+    out13[0] = e->last_state.retries;
+    out13[1] = e->last_state.mu;
+    out13[2] = e->last_state.radius;
+    for (int k = 0; k < 10; k++) out13[3 + k] = (double)e->last_state.clk[k];
+    return VE_OK;
 }
 
 int ve_last_timing(const ve_estimator* e, float* ms4, int* launches) {

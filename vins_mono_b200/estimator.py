@@ -45,6 +45,7 @@ def _bind(lib):
     lib.ve_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ve_get_prior.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
     lib.ve_last_timing.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    lib.ve_solver_debug.argtypes = [C.c_void_p, C.c_void_p]
     _bound = True
 
 
@@ -116,6 +117,11 @@ class Estimator:
         nb, blk = C.c_int(0), np.zeros(4 * 64, np.int32)
         n = self._check(self.lib.ve_get_prior(self.h, cap, _p(A), _p(b), C.byref(nb), _p(blk)))
         return A[: n * n].reshape(n, n).copy(), b[:n].copy(), [tuple(int(v) for v in blk[4 * k:4 * k + 4]) for k in range(nb.value)]
+
+    def solver_debug(self):
+        out = np.zeros(13)
+        self.lib.ve_solver_debug(self.h, _p(out))
+        return dict(retries=int(out[0]), mu=out[1], radius=out[2], clk=out[3:].astype(np.int64).tolist())
 
     def timing(self):
         ms, k = np.zeros(4, np.float32), C.c_int(0)
