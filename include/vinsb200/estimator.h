@@ -74,6 +74,15 @@ int ve_get_prior(const ve_estimator* e, int cap, double* A, double* b, int* nblo
  * [3] total; launches = kernels launched. */
 int ve_last_timing(const ve_estimator* e, float* ms4, int* launches);
 
+/* n consecutive ve_process_imu calls (same semantics; saves per-call overhead in scripting hosts). */
+int ve_process_imu_batch(ve_estimator* e, int n, const double* dt, const double* acc, const double* gyr);
+/* Kernel profiling (serialises the pipeline; not for timed runs): accumulated device ms and launch counts per kernel:
+ * 0 ba_linearize, 1 ba_schur, 2 ba_step, 3 ba_zero, 4 marg_build, 5 marg_solve, 6 preint_push, 7 sqrt_info. */
+int ve_set_profile(ve_estimator* e, int on);
+int ve_kernel_times(const ve_estimator* e, double* ms8, int* count8);
+/* Host<->device bytes moved by the last ve_process_image. */
+int ve_last_traffic(const ve_estimator* e, double* h2d_bytes, double* d2h_bytes);
+
 /* Solver internals of the last solve (profiling/tests): out[0] linear-solver retries, [1] mu, [2] radius,
  * [3..12] per-phase cycle counters of the step kernel summed over the iterations. */
 int ve_solver_debug(const ve_estimator* e, double* out13);

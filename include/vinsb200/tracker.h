@@ -75,6 +75,8 @@ int vt_get(const vt_tracker* t, int* ids, int* track_cnt, float* cur_pts, float*
  * 2 (tracked and a feature message is due) or < 0 on error; *restart is set to 1 when the
  * discontinuity rule fired (the node publishes /feature_tracker/restart). */
 int vt_node_image(vt_tracker* t, const uint8_t* img, size_t row_stride, double stamp, int* restart);
+/* Same with the frame already resident in device memory. */
+int vt_node_image_device(vt_tracker* t, const uint8_t* d_img, size_t row_stride, double stamp, int* restart);
 /* Feature message of the last vt_node_image that returned 2: per point x_un, y_un (z = 1),
  * channel values id*NUM_OF_CAM+cam (NUM_OF_CAM = 1), u, v, velocity_x, velocity_y.  Returns the point count. */
 int vt_node_pack(const vt_tracker* t, int capacity, float* xy_un, float* id_of_point, float* u_of_point,
@@ -82,6 +84,13 @@ int vt_node_pack(const vt_tracker* t, int capacity, float* xy_un, float* id_of_p
 
 /* Device time (ms, CUDA events on the handle's stream) and launch count of the last read_image. */
 int vt_last_timing(const vt_tracker* t, float* device_ms, int* kernel_launches);
+
+/* Kernel profiling (serialises the pipeline; not for timed runs): accumulated device ms / launch counts per group:
+ * 0 clahe (lut + apply), 1 pyrdown x3, 2 lk_track, 3 mask_discs, 4 min_eig, 5 candidates + sort + select. */
+int vt_set_profile(vt_tracker* t, int on);
+int vt_kernel_times(const vt_tracker* t, double* ms6, int* count6);
+/* Host<->device bytes moved by the last vt_read_image. */
+int vt_last_traffic(const vt_tracker* t, double* h2d_bytes, double* d2h_bytes);
 
 /* Test/benchmark access to single stages on device-resident data (all arrays are host pointers). */
 int vt_debug_equalized(vt_tracker* t, int level, uint8_t* out, int* rows, int* cols);

@@ -237,11 +237,11 @@ inline void sym_eigen(const Mat& A, std::vector<double>& w, Mat& V) {
     // Stop when a whole sweep finds every off-diagonal entry negligible against its own diagonal pair
     // (|a_pq| <= 1e-15 sqrt|a_pp a_qq|): the relative criterion of Jacobi methods, which also resolves the small
     // eigenvalues of the badly scaled information matrices (entries from 1e-3 to 1e14) this is used on.
-    // Entries below 1e-16 of the largest diagonal are round-off of the rotations among the large rows (absolute
+    // Entries below 1e-14 (~50 eps) of the largest diagonal are round-off of the rotations among the large rows (absolute
     // accuracy eps*|A| is also all Eigen's tridiagonal-QR SelfAdjointEigenSolver delivers).
     double amax = 0;
     for (int i = 0; i < n; i++) amax = std::max(amax, std::fabs(a(i, i)));
-    const double floor_abs = 1e-16 * amax;
+    const double floor_abs = 1e-14 * amax;
     for (int sweep = 0; sweep < 60; sweep++) {
         bool rotated = false;
         for (int p = 0; p < n - 1; p++)

@@ -706,24 +706,51 @@ __device__ bool cholesky_packed(double* Lp, int n, double* rdiag, int* flag) {
     return true;
 }
 
-// Solves L L^T y = b with the packed factor, single warp (warp 0); y (in/out) must be in shared memory.
+// Solves L L^T y = b with the packed factor; y (in/out) in shared memory, all threads of the CTA take part.
+// Blocked by 8: the 8x8 triangular block is solved by one thread, the remaining rows are updated with 8 columns
+// at once by one thread per row -> 2 barriers per block instead of 2 per unknown.
 __device__ void chol_solve_packed(const double* Lp, const double* rdiag, int n, double* y) {
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
-    for (int k = 0; k < n; k++) {  // forward: L z = b
-        const double yk = y[k] * rdiag[k];
-        __syncwarp();
-        if (lane == 0) y[k] = yk;
-        for (int i = k + 1 + lane; i < n; i += 32) y[i] -= Lp[(size_t)i * (i + 1) / 2 + k] * yk;
-        __syncwarp();
+    const int tid = threadIdx.x, nt = blockDim.x;
+    auto L = [&](int i, int j) { return Lp[(size_t)i * (i + 1) / 2 + j]; };
+    for (int kb = 0; kb < n; kb += CHOL_NB) {  // forward: L z = b
+        const int w = min(CHOL_NB, n - kb), ke = kb + w;
+        if (tid == 0) {
+            for (int c = 0; c < w; c++) {
+                double v = y[kb + c];
+                for (int t = 0; t < c; t++) v -= L(kb + c, kb + t) * y[kb + t];
+                y[kb + c] = v * rdiag[kb + c];
+            }
+        }
+        __syncthreads();
+        for (int i = ke + tid; i < n; i += nt) {
+            const size_t ib = (size_t)i * (i + 1) / 2 + kb;
+            double v = y[i];
+#pragma unroll
+            for (int c = 0; c < CHOL_NB; c++)
+                if (c < w) v -= Lp[ib + c] * y[kb + c];
+            y[i] = v;
+        }
+        __syncthreads();
     }
-    for (int k = n - 1; k >= 0; k--) {  // backward: L^T y = z
-        const double yk = y[k] * rdiag[k];
-        __syncwarp();
-        if (lane == 0) y[k] = yk;
-        const size_t kb = (size_t)k * (k + 1) / 2;
-        for (int i = lane; i < k; i += 32) y[i] -= Lp[kb + i] * yk;
-        __syncwarp();
+    const int last = ((n - 1) / CHOL_NB) * CHOL_NB;
+    for (int kb = last; kb >= 0; kb -= CHOL_NB) {  // backward: L^T y = z
+        const int w = min(CHOL_NB, n - kb);
+        if (tid == 0) {
+            for (int c = w - 1; c >= 0; c--) {
+                double v = y[kb + c];
+                for (int t = c + 1; t < w; t++) v -= L(kb + t, kb + c) * y[kb + t];
+                y[kb + c] = v * rdiag[kb + c];
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < kb; i += nt) {
+            double v = y[i];
+#pragma unroll
+            for (int c = 0; c < CHOL_NB; c++)
+                if (c < w) v -= L(kb + c, i) * y[kb + c];
+            y[i] = v;
+        }
+        __syncthreads();
     }
 }
 
@@ -1106,9 +1133,9 @@ __device__ void jacobi_eigen(double* A, double* V, int ld, double* cs, int* pq, 
     const int half = ld / 2;
     for (int i = tid; i < ld * ld; i += nt) V[i] = (i / ld == i % ld) ? 1.0 : 0.0;
     if (tid < 2) flags[tid] = 0;
-    double amax = 0;  // largest |diagonal|: entries below 1e-16 of it are round-off of the large rotations
+    double amax = 0;  // largest |diagonal|: entries below 1e-14 (~50 eps) of it are round-off of the large rotations
     for (int i = 0; i < ld; i++) amax = fmax(amax, fabs(A[i * ld + i]));
-    const double floor_abs = 1e-16 * amax;
+    const double floor_abs = 1e-14 * amax;
     __syncthreads();
     for (int sweep = 0; sweep < 40; sweep++) {
         int* flag = &flags[sweep & 1];
@@ -1331,7 +1358,9 @@ void launch_sqrt_info(PreInt* slots, const int* d_which, int count, cudaStream_t
     sqrt_info_kernel<<<count, 32, 0, s>>>(slots, d_which, count);
 }
 
-void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int* launches) {
+void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int* launches, KernelProfile* prof) {
+    KernelProfile none;
+    if (!prof) prof = &none;
     const BaDims& d = p.dims;
     const int lin_grid = ba_linearize_grid(d);
     const int zero_grid = 64;
@@ -1352,31 +1381,49 @@ void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int
         smem_configured = (int)chol_bytes;
     }
     int n = 0;
+    prof->begin(s);
     ba_zero_kernel<<<zero_grid, 256, 0, s>>>(p, 1);
+    prof->end(3, s);
+    prof->begin(s);
     ba_linearize_kernel<<<lin_grid, 32 * LIN_WARPS, 0, s>>>(p, 1);
+    prof->end(0, s);
     n += 2;
     for (int it = 0; it < max_iterations; it++) {
+        prof->begin(s);
         ba_schur_kernel<<<dim3(tiles, tiles), dim3(ST, ST), 0, s>>>(p);
+        prof->end(1, s);
+        prof->begin(s);
         ba_step_kernel<<<1, 512, use_smem ? chol_bytes : 0, s>>>(p, use_smem);
+        prof->end(2, s);
+        prof->begin(s);
         ba_zero_kernel<<<zero_grid, 256, 0, s>>>(p, 0);
+        prof->end(3, s);
+        prof->begin(s);
         ba_linearize_kernel<<<lin_grid, 32 * LIN_WARPS, 0, s>>>(p, 0);
+        prof->end(0, s);
         n += 4;
     }
     if (launches) *launches += n;
 }
 
-void launch_marginalize(const BaProblem& p, const MargPlan& mp, cudaStream_t s, int* launches) {
+void launch_marginalize(const BaProblem& p, const MargPlan& mp, cudaStream_t s, int* launches, KernelProfile* prof) {
+    KernelProfile none;
+    if (!prof) prof = &none;
     cudaMemsetAsync(mp.Am, 0, sizeof(double) * (size_t)mp.P * mp.P, s);
     cudaMemsetAsync(mp.bm, 0, sizeof(double) * (size_t)mp.P, s);
     const int grid = (mp.n_lm + 3) / 4 + 2;
+    prof->begin(s);
     marg_build_kernel<<<grid, 128, 0, s>>>(p, mp);
+    prof->end(4, s);
     const size_t smem = marg_solve_smem_bytes(mp.m_dense, mp.n);
     static size_t configured = 0;
     if (smem > configured) {
         cudaFuncSetAttribute(marg_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
+    prof->begin(s);
     marg_solve_kernel<<<1, 512, smem, s>>>(mp, 1e-8);
+    prof->end(5, s);
     if (launches) *launches += 2;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "ba_types.h"
+#include "kprof.h"
 
 namespace vb {
 
@@ -28,8 +29,9 @@ void launch_preint_push(PreInt* slot, int n, const double* d_samples, double acc
                         cudaStream_t s);
 void launch_sqrt_info(PreInt* slots, const int* d_which, int count, cudaStream_t s);
 // full trust-region solve: linearise x[st->cur], then max_iterations x {schur, step, zero, linearise+decide}
-void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int* launches);
-void launch_marginalize(const BaProblem& p, const MargPlan& mp, cudaStream_t s, int* launches);
+// profile slots: 0 linearize, 1 schur, 2 step, 3 zero, 4 marg_build, 5 marg_solve, 6 preint, 7 sqrt_info
+void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int* launches, KernelProfile* prof = nullptr);
+void launch_marginalize(const BaProblem& p, const MargPlan& mp, cudaStream_t s, int* launches, KernelProfile* prof = nullptr);
 size_t ba_work_doubles(int D, int L);
 
 }  // namespace vb

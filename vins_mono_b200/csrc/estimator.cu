@@ -105,6 +105,8 @@ struct ve_estimator {
     vb::SolverState last_state{};
     float last_ms[4] = {0, 0, 0, 0};
     int last_launches = 0;
+    vb::KernelProfile prof;
+    size_t h2d_bytes = 0, d2h_bytes = 0;  // of the last process_image
     // ---- device memory
     int Lmax = 0, Mmax = 0, D = 0, nmax = 0;
     DeviceBuf<vb::PreInt> d_preint;
@@ -202,8 +204,11 @@ int flush_frame(ve_estimator* e, int frame) {
         s[1] = a.x; s[2] = a.y; s[3] = a.z; s[4] = w.x; s[5] = w.y; s[6] = w.z;
     }
     VE_CUDA(cudaMemcpyAsync(e->d_samples.p, e->h_samples, sizeof(double) * 7 * cnt, cudaMemcpyHostToDevice, e->stream));
+    e->prof.begin(e->stream);
     vb::launch_preint_push(e->d_preint.p + e->slot_of[frame], (int)cnt, e->d_samples.p, e->cfg.acc_n, e->cfg.gyr_n, e->cfg.acc_w,
                            e->cfg.gyr_w, e->stream);
+    e->prof.end(6, e->stream);
+    e->h2d_bytes += sizeof(double) * 7 * cnt;
     e->last_launches++;
     VE_CUDA(cudaStreamSynchronize(e->stream));  // staging buffers are reused by the next flush
     e->flushed[frame] = n;
@@ -222,7 +227,9 @@ int refresh_sqrt_info(ve_estimator* e) {
     }
     if (!cnt) return VE_OK;
     VE_CUDA(cudaMemcpyAsync(e->d_which.p, e->h_marg_i, sizeof(int) * cnt, cudaMemcpyHostToDevice, e->stream));
+    e->prof.begin(e->stream);
     vb::launch_sqrt_info(e->d_preint.p, e->d_which.p, cnt, e->stream);
+    e->prof.end(7, e->stream);
     e->last_launches++;
     VE_CUDA(cudaStreamSynchronize(e->stream));
     return VE_OK;
@@ -584,6 +591,7 @@ int build_problem(ve_estimator* e, vb::BaProblem& p, bool upload_tables) {
         const size_t nobs = 6 * (size_t)e->Lmax + 6 * (size_t)e->Mmax;
         VE_CUDA(cudaMemcpyAsync(e->d_ints.p, e->h_ints, sizeof(int) * nints, cudaMemcpyHostToDevice, e->stream));
         VE_CUDA(cudaMemcpyAsync(e->d_obs.p, e->h_obs, sizeof(double) * nobs, cudaMemcpyHostToDevice, e->stream));
+        e->h2d_bytes += sizeof(int) * nints + sizeof(double) * nobs;
     }
     vb::BaDims& d = p.dims;
     d.W = W;
@@ -645,6 +653,7 @@ int build_problem(ve_estimator* e, vb::BaProblem& p, bool upload_tables) {
 int upload_states(ve_estimator* e, int* n_lam) {
     pack_states(e, e->h_states, n_lam);
     VE_CUDA(cudaMemcpyAsync(e->d_states[0].p, e->h_states, sizeof(double) * states_doubles(e), cudaMemcpyHostToDevice, e->stream));
+    e->h2d_bytes += sizeof(double) * states_doubles(e);
     return VE_OK;
 }
 
@@ -733,7 +742,7 @@ int marginalize(ve_estimator* e, vb::BaProblem& p) {
     mp.gout = mp.Aout + (size_t)e->nmax * e->nmax;
     mp.cout = mp.gout + e->nmax;
     // NOTE: Aout is written with leading dimension n (dense n x n at the front of the buffer)
-    vb::launch_marginalize(p, mp, e->stream, &e->last_launches);
+    vb::launch_marginalize(p, mp, e->stream, &e->last_launches, &e->prof);
     VE_CUDA(cudaGetLastError());
     // new prior: linearisation point = current parameter values of the kept blocks, identities shifted
     // (addr_shift, estimator.cpp:913-925 / :969-990)
@@ -790,13 +799,14 @@ int optimization(ve_estimator* e) {
     st.radius = 1e4;
     st.mu = 1e-8;
     VE_CUDA(cudaMemcpyAsync(e->d_st.p, &st, sizeof(st), cudaMemcpyHostToDevice, e->stream));
-    vb::launch_ba_solve(p, e->cfg.num_iterations, e->stream, &e->last_launches);
+    vb::launch_ba_solve(p, e->cfg.num_iterations, e->stream, &e->last_launches, &e->prof);
     VE_CUDA(cudaGetLastError());
     VE_CUDA(cudaMemcpyAsync(&st, e->d_st.p, sizeof(st), cudaMemcpyDeviceToHost, e->stream));
     const size_t ns = states_doubles(e);
     double* h2 = e->h_states + ns;  // second half of the staging area holds both device buffers
     VE_CUDA(cudaMemcpyAsync(h2, e->d_states[0].p, sizeof(double) * ns, cudaMemcpyDeviceToHost, e->stream));
     VE_CUDA(cudaMemcpyAsync(h2 + ns, e->d_states[1].p, sizeof(double) * ns, cudaMemcpyDeviceToHost, e->stream));
+    e->d2h_bytes += 2 * sizeof(double) * ns + sizeof(st);
     VE_CUDA(cudaEventRecord(e->ev[2], e->stream));
     VE_CUDA(cudaStreamSynchronize(e->stream));
     e->last_state = st;
@@ -1016,6 +1026,7 @@ int ve_process_image(ve_estimator* e, int n, const int* ids, const double* xyz_u
     if (!e || n < 0 || (n && (!ids || !xyz_uv_vel))) return VE_ERR_INVALID;
     VE_CUDA(cudaSetDevice(e->cfg.device));
     e->last_launches = 0;
+    e->h2d_bytes = e->d2h_bytes = 0;
     e->last_ms[0] = e->last_ms[1] = e->last_ms[2] = e->last_ms[3] = 0;
     std::vector<int> order(n);
     for (int i = 0; i < n; i++) order[i] = i;
@@ -1097,6 +1108,38 @@ int ve_get_prior(const ve_estimator* e, int cap, double* A, double* b, int* nblo
             blocks4[4 * k + 3] = e->prior_blocks[k].size;
         }
     return n;
+}
+
+int ve_process_imu_batch(ve_estimator* e, int n, const double* dt, const double* acc, const double* gyr) {
+    if (!e || n < 0 || (n && (!dt || !acc || !gyr))) return VE_ERR_INVALID;
+    VE_CUDA(cudaSetDevice(e->cfg.device));
+    for (int i = 0; i < n; i++) {
+        const int rc = process_imu(e, dt[i], Vec3(acc[3 * i], acc[3 * i + 1], acc[3 * i + 2]), Vec3(gyr[3 * i], gyr[3 * i + 1], gyr[3 * i + 2]));
+        if (rc) return rc;
+    }
+    return VE_OK;
+}
+
+int ve_set_profile(ve_estimator* e, int on) {
+    if (!e) return VE_ERR_INVALID;
+    e->prof.enable(on != 0);
+    return VE_OK;
+}
+
+int ve_kernel_times(const ve_estimator* e, double* ms8, int* count8) {
+    if (!e) return VE_ERR_INVALID;
+    for (int k = 0; k < 8; k++) {
+        if (ms8) ms8[k] = e->prof.ms[k];
+        if (count8) count8[k] = e->prof.count[k];
+    }
+    return VE_OK;
+}
+
+int ve_last_traffic(const ve_estimator* e, double* h2d_bytes, double* d2h_bytes) {
+    if (!e) return VE_ERR_INVALID;
+    if (h2d_bytes) *h2d_bytes = (double)e->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = (double)e->d2h_bytes;
+    return VE_OK;
 }
 
 int ve_solver_debug(const ve_estimator* e, double* out13) {

@@ -19,6 +19,7 @@
 
 #include "fe_kernels.h"
 #include "fm_ransac.h"
+#include "kprof.h"
 #include "vinsb200/tracker.h"
 
 namespace {
@@ -83,6 +84,9 @@ struct vt_tracker {
     // diagnostics
     float last_ms = 0;
     int last_launches = 0;
+    vb::KernelProfile prof;  // 0 clahe_lut+apply, 1 pyrdown x3, 2 lk, 3 mask, 4 min_eig, 5 candidates+sort+select
+    size_t h2d_bytes = 0, d2h_bytes = 0;
+    double host_ms_ransac = 0, host_ms_mask = 0;
 };
 
 namespace {
@@ -274,17 +278,21 @@ int build_forw_pyramid(vt_tracker* t) {
     const int rows = t->cfg.rows, cols = t->cfg.cols;
     uint8_t* l0 = const_cast<uint8_t*>(f.view.img[0]);
     if (t->cfg.equalize) {
+        t->prof.begin(t->stream);
         vb::launch_clahe(t->d_raw, rows, cols, t->raw_pitch, t->d_lut, l0, f.view.pitch[0], t->stream);
+        t->prof.end(0, t->stream, 2);
         t->last_launches += 2;
     } else {
         VT_CUDA(cudaMemcpy2DAsync(l0, f.view.pitch[0], t->d_raw, t->raw_pitch, cols, rows, cudaMemcpyDeviceToDevice,
                                   t->stream));
     }
+    t->prof.begin(t->stream);
     for (int l = 1; l <= f.view.nlev; l++) {
         vb::launch_pyrdown(f.view.img[l - 1], f.view.rows[l - 1], f.view.cols[l - 1], f.view.pitch[l - 1],
                            const_cast<uint8_t*>(f.view.img[l]), f.view.pitch[l], t->stream);
         t->last_launches++;
     }
+    t->prof.end(1, t->stream, f.view.nlev);
     return VT_OK;
 }
 
@@ -293,11 +301,16 @@ int detect_new(vt_tracker* t, const uint8_t* d_img, int pitch, const uint8_t* d_
     const int rows = t->cfg.rows, cols = t->cfg.cols;
     VT_CUDA(cudaMemsetAsync(t->d_count, 0, 2 * sizeof(int), t->stream));
     VT_CUDA(cudaMemsetAsync(t->d_max, 0, sizeof(unsigned), t->stream));
+    t->prof.begin(t->stream);
     vb::launch_min_eig(d_img, rows, cols, pitch, d_mask, cols, t->d_eig, cols, t->d_max, t->stream);
+    t->prof.end(4, t->stream);
+    t->prof.begin(t->stream);
     vb::launch_gftt_tail(t->d_eig, rows, cols, cols, d_mask, cols, t->d_max, 0.01, t->d_keys, t->key_capacity,
                          t->d_count, max_corners, (float)t->cfg.min_dist, t->d_cell_cnt, t->d_cell_pts, t->d_pts_out,
                          t->d_count + 1, t->stream);
+    t->prof.end(5, t->stream, 3);
     t->last_launches += 4;
+    t->d2h_bytes += 2 * sizeof(int) + (size_t)max_corners * 2 * sizeof(float);
     VT_CUDA(cudaMemcpyAsync(t->h_counts, t->d_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, t->stream));
     VT_CUDA(cudaMemcpyAsync(h_out, t->d_pts_out, (size_t)max_corners * 2 * sizeof(float), cudaMemcpyDeviceToHost,
                             t->stream));
@@ -326,8 +339,12 @@ int read_image_impl(vt_tracker* t, double cur_time, bool pub) {
         const int n = (int)t->cur_pts.size();
         std::memcpy(t->h_pts, t->cur_pts.data(), (size_t)n * sizeof(Pt));
         VT_CUDA(cudaMemcpyAsync(t->d_pts_in, t->h_pts, (size_t)n * sizeof(Pt), cudaMemcpyHostToDevice, t->stream));
+        t->prof.begin(t->stream);
         vb::launch_lk(curp.view, forwp.view, t->d_pts_in, n, t->d_pts_out, t->d_status, t->stream);
+        t->prof.end(2, t->stream);
         t->last_launches++;
+        t->h2d_bytes += (size_t)n * sizeof(Pt);
+        t->d2h_bytes += (size_t)n * (sizeof(Pt) + 1);
         VT_CUDA(cudaMemcpyAsync(t->h_pts, t->d_pts_out, (size_t)n * sizeof(Pt), cudaMemcpyDeviceToHost, t->stream));
         VT_CUDA(cudaMemcpyAsync(t->h_status, t->d_status, n, cudaMemcpyDeviceToHost, t->stream));
         VT_CUDA(cudaStreamSynchronize(t->stream));
@@ -354,9 +371,12 @@ int read_image_impl(vt_tracker* t, double cur_time, bool pub) {
             if (kept > 0) {
                 VT_CUDA(cudaMemcpyAsync(t->d_centres, t->h_centres, (size_t)kept * 2 * sizeof(int),
                                         cudaMemcpyHostToDevice, t->stream));
+                t->prof.begin(t->stream);
                 vb::launch_mask_discs(t->d_mask, rows, cols, cols, t->d_centres, kept, t->cfg.min_dist, t->d_halfw,
                                       t->stream);
+                t->prof.end(3, t->stream);
                 t->last_launches++;
+                t->h2d_bytes += (size_t)kept * 2 * sizeof(int);
             }
             int n_new = 0;
             rc = detect_new(t, forwp.view.img[0], forwp.view.pitch[0], t->d_mask, n_max_cnt, t->h_pts, &n_new, nullptr);
@@ -394,6 +414,8 @@ int read_image_common(vt_tracker* t, const uint8_t* img, size_t stride, double c
     if (!t || !img || stride < (size_t)t->cfg.cols) return VT_ERR_INVALID;
     VT_CUDA(cudaSetDevice(t->cfg.device));
     t->last_launches = 0;
+    t->h2d_bytes = on_device ? 0 : (size_t)t->cfg.rows * t->cfg.cols;
+    t->d2h_bytes = 0;
     VT_CUDA(cudaEventRecord(t->ev0, t->stream));
     int rc = upload_frame(t, img, stride, on_device);
     if (rc) return rc;
@@ -532,7 +554,7 @@ int vt_get(const vt_tracker* t, int* ids, int* track_cnt, float* cur_pts, float*
     return (int)n;
 }
 
-int vt_node_image(vt_tracker* t, const uint8_t* img, size_t row_stride, double stamp, int* restart) {
+static int node_image_common(vt_tracker* t, const uint8_t* img, size_t row_stride, double stamp, int* restart, bool on_device) {
     if (!t) return VT_ERR_INVALID;
     if (restart) *restart = 0;
     if (t->first_image_flag) {
@@ -558,7 +580,7 @@ int vt_node_image(vt_tracker* t, const uint8_t* img, size_t row_stride, double s
         }
     } else
         pub = false;
-    const int rc = vt_read_image(t, img, row_stride, stamp, pub);
+    const int rc = read_image_common(t, img, row_stride, stamp, pub, on_device);
     if (rc) return rc;
     if (pub) {
         t->pub_count++;
@@ -569,6 +591,14 @@ int vt_node_image(vt_tracker* t, const uint8_t* img, size_t row_stride, double s
         return 2;
     }
     return 1;
+}
+
+int vt_node_image(vt_tracker* t, const uint8_t* img, size_t row_stride, double stamp, int* restart) {
+    return node_image_common(t, img, row_stride, stamp, restart, false);
+}
+
+int vt_node_image_device(vt_tracker* t, const uint8_t* d_img, size_t row_stride, double stamp, int* restart) {
+    return node_image_common(t, d_img, row_stride, stamp, restart, true);
 }
 
 int vt_node_pack(const vt_tracker* t, int capacity, float* xy_un, float* id_of_point, float* u_of_point,
@@ -594,6 +624,28 @@ int vt_last_timing(const vt_tracker* t, float* device_ms, int* kernel_launches) 
     if (!t) return VT_ERR_INVALID;
     if (device_ms) *device_ms = t->last_ms;
     if (kernel_launches) *kernel_launches = t->last_launches;
+    return VT_OK;
+}
+
+int vt_set_profile(vt_tracker* t, int on) {
+    if (!t) return VT_ERR_INVALID;
+    t->prof.enable(on != 0);
+    return VT_OK;
+}
+
+int vt_kernel_times(const vt_tracker* t, double* ms6, int* count6) {
+    if (!t) return VT_ERR_INVALID;
+    for (int k = 0; k < 6; k++) {
+        if (ms6) ms6[k] = t->prof.ms[k];
+        if (count6) count6[k] = t->prof.count[k];
+    }
+    return VT_OK;
+}
+
+int vt_last_traffic(const vt_tracker* t, double* h2d_bytes, double* d2h_bytes) {
+    if (!t) return VT_ERR_INVALID;
+    if (h2d_bytes) *h2d_bytes = (double)t->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = (double)t->d2h_bytes;
     return VT_OK;
 }
 

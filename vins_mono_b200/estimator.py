@@ -46,6 +46,10 @@ def _bind(lib):
     lib.ve_get_prior.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
     lib.ve_last_timing.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
     lib.ve_solver_debug.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ve_process_imu_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ve_set_profile.argtypes = [C.c_void_p, C.c_int]
+    lib.ve_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ve_last_traffic.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _bound = True
 
 
@@ -117,6 +121,25 @@ class Estimator:
         nb, blk = C.c_int(0), np.zeros(4 * 64, np.int32)
         n = self._check(self.lib.ve_get_prior(self.h, cap, _p(A), _p(b), C.byref(nb), _p(blk)))
         return A[: n * n].reshape(n, n).copy(), b[:n].copy(), [tuple(int(v) for v in blk[4 * k:4 * k + 4]) for k in range(nb.value)]
+
+    KERNELS = ["ba_linearize", "ba_schur", "ba_step", "ba_zero", "marg_build", "marg_solve", "preint_push", "sqrt_info"]
+
+    def processIMU_batch(self, dt, acc, gyr):
+        dt, acc, gyr = _d(dt), _d(acc), _d(gyr)
+        self._check(self.lib.ve_process_imu_batch(self.h, len(dt), _p(dt), _p(acc), _p(gyr)))
+
+    def set_profile(self, on):
+        self.lib.ve_set_profile(self.h, int(on))
+
+    def kernel_times(self):
+        ms, cnt = np.zeros(8), np.zeros(8, np.int32)
+        self.lib.ve_kernel_times(self.h, _p(ms), _p(cnt))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNELS)}
+
+    def traffic(self):
+        a, b = C.c_double(0), C.c_double(0)
+        self.lib.ve_last_traffic(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def solver_debug(self):
         out = np.zeros(13)

@@ -36,8 +36,12 @@ def load_library():
         lib.vt_count.argtypes = [C.c_void_p]
         lib.vt_get.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         lib.vt_node_image.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.POINTER(C.c_int)]
+        lib.vt_node_image_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.POINTER(C.c_int)]
         lib.vt_node_pack.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
         lib.vt_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        lib.vt_set_profile.argtypes = [C.c_void_p, C.c_int]
+        lib.vt_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.vt_last_traffic.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         lib.vt_debug_equalized.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.vt_debug_gftt.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
                                       C.POINTER(C.c_int), C.c_void_p]
@@ -102,6 +106,10 @@ class FeatureTracker:
         r = self._check(self.lib.vt_node_image(self.h, _ptr(img), img.strides[0], float(stamp), C.byref(restart)))
         return r, restart.value
 
+    def node_image_device(self, dptr, stride, stamp):
+        restart = C.c_int(0)
+        return self._check(self.lib.vt_node_image_device(self.h, C.c_void_p(dptr), stride, float(stamp), C.byref(restart)))
+
     def result(self):
         n = self.lib.vt_count(self.h)
         ids, tc = np.zeros(n, np.int32), np.zeros(n, np.int32)
@@ -118,6 +126,21 @@ class FeatureTracker:
         n = self._check(self.lib.vt_node_pack(self.h, cap, _ptr(xy), *[_ptr(c) for c in ch]))
         return {int(ch[0][i]): (float(xy[i, 0]), float(xy[i, 1]), 1.0, float(ch[1][i]), float(ch[2][i]),
                                 float(ch[3][i]), float(ch[4][i])) for i in range(n)}
+
+    KERNEL_GROUPS = ["clahe", "pyrdown", "lk_track", "mask_discs", "min_eig", "gftt_tail"]
+
+    def set_profile(self, on):
+        self.lib.vt_set_profile(self.h, int(on))
+
+    def kernel_times(self):
+        ms, cnt = np.zeros(6), np.zeros(6, np.int32)
+        self.lib.vt_kernel_times(self.h, _ptr(ms), _ptr(cnt))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_GROUPS)}
+
+    def traffic(self):
+        a, b = C.c_double(0), C.c_double(0)
+        self.lib.vt_last_traffic(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def timing(self):
         ms, k = C.c_float(0), C.c_int(0)
