@@ -234,26 +234,22 @@ inline void sym_eigen(const Mat& A, std::vector<double>& w, Mat& V) {
     const int n = A.r;
     Mat a = A;
     V = Mat::Identity(n);
-    // Stop when a whole sweep finds every off-diagonal entry negligible against its own diagonal pair
-    // (|a_pq| <= 1e-15 sqrt|a_pp a_qq|): the relative criterion of Jacobi methods, which also resolves the small
-    // eigenvalues of the badly scaled information matrices (entries from 1e-3 to 1e14) this is used on.
-    // Entries below 1e-14 (~50 eps) of the largest diagonal are round-off of the rotations among the large rows (absolute
-    // accuracy eps*|A| is also all Eigen's tridiagonal-QR SelfAdjointEigenSolver delivers).
-    double amax = 0;
-    for (int i = 0; i < n; i++) amax = std::max(amax, std::fabs(a(i, i)));
-    const double floor_abs = 1e-14 * amax;
+    // A pair (p, q) is rotated when |a_pq| > 1e-15 sqrt|a_pp a_qq| (relative criterion of Jacobi methods: it
+    // resolves the small eigenvalues of the badly scaled information matrices, entries 1e-3 .. 1e14, this is used
+    // on).  Sweeps stop when every rotation of a sweep was the identity in floating point (c == 1): the matrix
+    // is then a fixed point of the iteration.
     for (int sweep = 0; sweep < 60; sweep++) {
-        bool rotated = false;
+        bool changed = false;
         for (int p = 0; p < n - 1; p++)
             for (int q = p + 1; q < n; q++) {
                 const double apq = a(p, q);
                 if (apq == 0) continue;
                 const double app = a(p, p), aqq = a(q, q);
-                if (std::fabs(apq) <= std::max(floor_abs, 1e-15 * std::sqrt(std::fabs(app * aqq)))) continue;
-                rotated = true;
+                if (std::fabs(apq) <= 1e-300 + 1e-15 * std::sqrt(std::fabs(app * aqq))) continue;
                 const double theta = (aqq - app) / (2 * apq);
                 const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
                 const double c = 1 / std::sqrt(t * t + 1), s = t * c;
+                if (c != 1.0) changed = true;
                 for (int k = 0; k < n; k++) {
                     const double akp = a(k, p), akq = a(k, q);
                     a(k, p) = c * akp - s * akq;
@@ -270,7 +266,7 @@ inline void sym_eigen(const Mat& A, std::vector<double>& w, Mat& V) {
                     V(k, q) = s * vkp + c * vkq;
                 }
             }
-        if (!rotated) break;
+        if (!changed) break;
     }
     std::vector<int> idx(n);
     for (int i = 0; i < n; i++) idx[i] = i;

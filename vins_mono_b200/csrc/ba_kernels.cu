@@ -605,7 +605,7 @@ __device__ double quad_form(const BaProblem& p, const BaAccum& a, const double* 
 // (forward substitution against the diagonal block, reciprocal pivots), the trailing matrix with 4x4 register
 // tiles (0.5 shared-memory loads per FMA).  3 barriers per block column.
 #define CHOL_NB 8
-__device__ bool cholesky_packed(double* Lp, int n, double* rdiag, int* flag) {
+__device__ bool cholesky_packed(double* Lp, int n, double* rdiag, double* linv, int* flag) {
     __shared__ double dblk[CHOL_NB][CHOL_NB + 1];
     const int tid = threadIdx.x, nt = blockDim.x;
     if (tid == 0) *flag = 1;
@@ -642,6 +642,26 @@ __device__ bool cholesky_packed(double* Lp, int n, double* rdiag, int* flag) {
                     }
             }
             if (!ok && tid == 0) *flag = 0;
+            // inverse of the diagonal block (lower triangular), one column per lane: the triangular solves then
+            // need only an 8x8 product per block instead of a dependent substitution chain
+            __syncwarp();
+            if (r < CHOL_NB) {
+                const int c = r;
+                double x[CHOL_NB];
+#pragma unroll
+                for (int rr = 0; rr < CHOL_NB; rr++) {
+                    double v = 0.0;
+                    if (rr >= c && rr < w && c < w) {
+                        v = (rr == c) ? 1.0 : 0.0;
+#pragma unroll
+                        for (int k = 0; k < CHOL_NB; k++)
+                            if (k >= c && k < rr) v -= dblk[rr][k] * x[k];
+                        v *= rdiag[kb + rr];
+                    }
+                    x[rr] = v;
+                    linv[(kb / CHOL_NB) * 64 + rr * CHOL_NB + c] = v;
+                }
+            }
         }
         __syncthreads();
         if (!*flag) return false;
@@ -707,19 +727,19 @@ __device__ bool cholesky_packed(double* Lp, int n, double* rdiag, int* flag) {
 }
 
 // Solves L L^T y = b with the packed factor; y (in/out) in shared memory, all threads of the CTA take part.
-// Blocked by 8: the 8x8 triangular block is solved by one thread, the remaining rows are updated with 8 columns
-// at once by one thread per row -> 2 barriers per block instead of 2 per unknown.
-__device__ void chol_solve_packed(const double* Lp, const double* rdiag, int n, double* y) {
+// Blocked by 8: the 8x8 triangular block is applied through its precomputed inverse (8 lanes, independent dot
+// products), the remaining rows are updated with 8 columns at once by one thread per row.
+__device__ void chol_solve_packed(const double* Lp, const double* linv, int n, double* y) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    auto L = [&](int i, int j) { return Lp[(size_t)i * (i + 1) / 2 + j]; };
     for (int kb = 0; kb < n; kb += CHOL_NB) {  // forward: L z = b
         const int w = min(CHOL_NB, n - kb), ke = kb + w;
-        if (tid == 0) {
-            for (int c = 0; c < w; c++) {
-                double v = y[kb + c];
-                for (int t = 0; t < c; t++) v -= L(kb + c, kb + t) * y[kb + t];
-                y[kb + c] = v * rdiag[kb + c];
-            }
+        if (tid < 32) {
+            double v = 0.0;
+            const double* Li = linv + (kb / CHOL_NB) * 64;
+            if (tid < w)
+                for (int c = 0; c <= tid; c++) v += Li[tid * CHOL_NB + c] * y[kb + c];
+            __syncwarp();
+            if (tid < w) y[kb + tid] = v;
         }
         __syncthreads();
         for (int i = ke + tid; i < n; i += nt) {
@@ -735,19 +755,20 @@ __device__ void chol_solve_packed(const double* Lp, const double* rdiag, int n, 
     const int last = ((n - 1) / CHOL_NB) * CHOL_NB;
     for (int kb = last; kb >= 0; kb -= CHOL_NB) {  // backward: L^T y = z
         const int w = min(CHOL_NB, n - kb);
-        if (tid == 0) {
-            for (int c = w - 1; c >= 0; c--) {
-                double v = y[kb + c];
-                for (int t = c + 1; t < w; t++) v -= L(kb + t, kb + c) * y[kb + t];
-                y[kb + c] = v * rdiag[kb + c];
-            }
+        if (tid < 32) {
+            double v = 0.0;
+            const double* Li = linv + (kb / CHOL_NB) * 64;
+            if (tid < w)
+                for (int r = tid; r < w; r++) v += Li[r * CHOL_NB + tid] * y[kb + r];
+            __syncwarp();
+            if (tid < w) y[kb + tid] = v;
         }
         __syncthreads();
         for (int i = tid; i < kb; i += nt) {
             double v = y[i];
 #pragma unroll
             for (int c = 0; c < CHOL_NB; c++)
-                if (c < w) v -= L(kb + c, i) * y[kb + c];
+                if (c < w) v -= Lp[(size_t)(kb + c) * (kb + c + 1) / 2 + i] * y[kb + c];
             y[i] = v;
         }
         __syncthreads();
@@ -785,7 +806,7 @@ __device__ void reduce_single_cta(const BaProblem& p, const BaAccum& a, double m
 __global__ void __launch_bounds__(512) ba_step_kernel(BaProblem p, int use_smem_chol) {
     extern __shared__ double chol_smem[];
     __shared__ double red[32];
-    __shared__ double rdiag[STEP_MAXD], ysm[STEP_MAXD];
+    __shared__ double rdiag[STEP_MAXD], ysm[STEP_MAXD], linv[(STEP_MAXD / CHOL_NB) * 64];
     __shared__ int flag;
     SolverState* st = p.st;
     if (st->done) return;
@@ -833,7 +854,7 @@ __global__ void __launch_bounds__(512) ba_step_kernel(BaProblem p, int use_smem_
             }
             __syncthreads();
             STAMP(2);
-            const bool ok_ = cholesky_packed(Lp, D, rdiag, &flag);
+            const bool ok_ = cholesky_packed(Lp, D, rdiag, linv, &flag);
             STAMP(3);
             if (ok_) {
                 linear_ok = true;
@@ -847,7 +868,7 @@ __global__ void __launch_bounds__(512) ba_step_kernel(BaProblem p, int use_smem_
         if (linear_ok) {
             for (int j = tid; j < D; j += nt) ysm[j] = p.gred[j];
             __syncthreads();
-            chol_solve_packed(Lp, rdiag, D, ysm);
+            chol_solve_packed(Lp, linv, D, ysm);
             __syncthreads();
             STAMP(4);
             for (int j = tid; j < D; j += nt) y[j] = ysm[j];
@@ -1126,18 +1147,18 @@ namespace {
 // A is ld x ld with ld even and >= n, rows/columns >= n zero (a zero row never rotates).  On exit the
 // eigenvalues are on the diagonal and V (ld x ld) holds the eigenvectors in its columns.  Each round applies
 // ld/2 disjoint rotations: one phase computes (c, s) per pair, one phase updates every 2x2 block
-// G_k^T A_(k,k') G_k' and V G_k, i.e. two barriers per round.  Sweeps stop when no pair needed a rotation under
-// |a_pq| > 1e-15 sqrt|a_pp a_qq| (relative criterion, resolves the small eigenvalues of badly scaled matrices).
-__device__ void jacobi_eigen(double* A, double* V, int ld, double* cs, int* pq, int* flags) {
+// G_k^T A_(k,k') G_k' and V G_k, i.e. two barriers per round.  A pair is rotated when
+// |a_pq| > 1e-15 sqrt|a_pp a_qq| (relative criterion: resolves the small eigenvalues of these badly scaled
+// matrices); sweeps stop when every rotation of a sweep was the identity in floating point (c == 1).
+__device__ int jacobi_eigen(double* A, double* V, int ld, double* cs, int* pq, int* flags) {
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     const int half = ld / 2;
-    for (int i = tid; i < ld * ld; i += nt) V[i] = (i / ld == i % ld) ? 1.0 : 0.0;
+    for (int i = wid; i < ld; i += nw)
+        for (int j = lane; j < ld; j += 32) V[i * ld + j] = (i == j) ? 1.0 : 0.0;
     if (tid < 2) flags[tid] = 0;
-    double amax = 0;  // largest |diagonal|: entries below 1e-14 (~50 eps) of it are round-off of the large rotations
-    for (int i = 0; i < ld; i++) amax = fmax(amax, fabs(A[i * ld + i]));
-    const double floor_abs = 1e-14 * amax;
     __syncthreads();
-    for (int sweep = 0; sweep < 40; sweep++) {
+    for (int sweep = 0; sweep < 60; sweep++) {
         int* flag = &flags[sweep & 1];
         for (int round = 0; round < ld - 1; round++) {
             if (tid < half) {
@@ -1146,20 +1167,22 @@ __device__ void jacobi_eigen(double* A, double* V, int ld, double* cs, int* pq, 
                     a = ld - 1;
                     b = round;
                 } else {
-                    a = (round + tid) % (ld - 1);
-                    b = (round - tid + (ld - 1)) % (ld - 1);
+                    a = round + tid;
+                    if (a >= ld - 1) a -= ld - 1;
+                    b = round - tid;
+                    if (b < 0) b += ld - 1;
                 }
                 const int pp = min(a, b), qq = max(a, b);
                 double c = 1.0, s = 0.0;
                 const double apq = A[pp * ld + qq];
                 if (apq != 0.0) {
                     const double app = A[pp * ld + pp], aqq = A[qq * ld + qq];
-                    if (fabs(apq) > fmax(floor_abs, 1e-15 * sqrt(fabs(app * aqq)))) {
+                    if (fabs(apq) > 1e-300 + 1e-15 * sqrt(fabs(app * aqq))) {
                         const double theta = (aqq - app) / (2 * apq);
                         const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
-                        c = 1 / sqrt(t * t + 1);
+                        c = rsqrt(t * t + 1);
                         s = t * c;
-                        *flag = 1;
+                        if (c != 1.0) *flag = 1;
                     }
                 }
                 pq[2 * tid] = pp;
@@ -1168,41 +1191,50 @@ __device__ void jacobi_eigen(double* A, double* V, int ld, double* cs, int* pq, 
                 cs[2 * tid + 1] = s;
             }
             __syncthreads();
-            for (int w = tid; w < half * half; w += nt) {
-                const int k = w / half, k2 = w - k * half;
-                const double c1 = cs[2 * k], s1 = cs[2 * k + 1], c2 = cs[2 * k2], s2 = cs[2 * k2 + 1];
-                if (s1 == 0.0 && s2 == 0.0) continue;
-                const int p0 = pq[2 * k], q0 = pq[2 * k + 1], p2 = pq[2 * k2], q2 = pq[2 * k2 + 1];
-                const double a00 = A[p0 * ld + p2], a01 = A[p0 * ld + q2], a10 = A[q0 * ld + p2], a11 = A[q0 * ld + q2];
-                const double t00 = c2 * a00 - s2 * a01, t01 = s2 * a00 + c2 * a01;
-                const double t10 = c2 * a10 - s2 * a11, t11 = s2 * a10 + c2 * a11;
-                A[p0 * ld + p2] = c1 * t00 - s1 * t10;
-                A[q0 * ld + p2] = s1 * t00 + c1 * t10;
-                A[p0 * ld + q2] = c1 * t01 - s1 * t11;
-                A[q0 * ld + q2] = s1 * t01 + c1 * t11;
-            }
-            for (int w = tid; w < half * ld; w += nt) {
-                const int k = w / ld, i = w - k * ld;
-                const double c = cs[2 * k], s_ = cs[2 * k + 1];
-                if (s_ == 0.0) continue;
-                const int pp = pq[2 * k], qq = pq[2 * k + 1];
-                const double vip = V[i * ld + pp], viq = V[i * ld + qq];
-                V[i * ld + pp] = c * vip - s_ * viq;
-                V[i * ld + qq] = s_ * vip + c * viq;
+            // warp tasks: (pair k, 32-wide chunk of pairs k2) for the A blocks, (pair k, 32 rows) for V
+            const int chA = (half + 31) >> 5, chV = (ld + 31) >> 5;
+            const int nA = half * chA, nV = half * chV;
+            for (int task = wid; task < nA + nV; task += nw) {
+                if (task < nA) {
+                    const int k = task / chA, k2 = (task - k * chA) * 32 + lane;
+                    if (k2 >= half) continue;
+                    const double c1 = cs[2 * k], s1 = cs[2 * k + 1];
+                    const double c2 = cs[2 * k2], s2 = cs[2 * k2 + 1];
+                    if (s1 == 0.0 && s2 == 0.0) continue;
+                    const int p0 = pq[2 * k], q0 = pq[2 * k + 1];
+                    const int p2 = pq[2 * k2], q2 = pq[2 * k2 + 1];
+                    const double a00 = A[p0 * ld + p2], a01 = A[p0 * ld + q2], a10 = A[q0 * ld + p2], a11 = A[q0 * ld + q2];
+                    const double t00 = c2 * a00 - s2 * a01, t01 = s2 * a00 + c2 * a01;
+                    const double t10 = c2 * a10 - s2 * a11, t11 = s2 * a10 + c2 * a11;
+                    A[p0 * ld + p2] = c1 * t00 - s1 * t10;
+                    A[q0 * ld + p2] = s1 * t00 + c1 * t10;
+                    A[p0 * ld + q2] = c1 * t01 - s1 * t11;
+                    A[q0 * ld + q2] = s1 * t01 + c1 * t11;
+                } else {
+                    const int tv_ = task - nA;
+                    const int k = tv_ / chV, i = (tv_ - k * chV) * 32 + lane;
+                    const double c1 = cs[2 * k], s1 = cs[2 * k + 1];
+                    if (i >= ld || s1 == 0.0) continue;
+                    const int p0 = pq[2 * k], q0 = pq[2 * k + 1];
+                    const double vip = V[i * ld + p0], viq = V[i * ld + q0];
+                    V[i * ld + p0] = c1 * vip - s1 * viq;
+                    V[i * ld + q0] = s1 * vip + c1 * viq;
+                }
             }
             __syncthreads();
         }
         const int any = *flag;
         if (tid == 0) flags[(sweep + 1) & 1] = 0;
         __syncthreads();
-        if (!any) break;
+        if (!any) return sweep + 1;
     }
+    return 60;
 }
 
 }  // namespace
 
 // Single CTA.  Dynamic shared memory: Wk (q x q), Ev and Vv (ldx x ldx, ldx = even(max(md, n))), bw (q), tv (ldx).
-__global__ void __launch_bounds__(512) marg_solve_kernel(MargPlan mp, double eps) {
+__global__ void __launch_bounds__(1024) marg_solve_kernel(MargPlan mp, double eps) {
     extern __shared__ double sm[];
     __shared__ double red[32];
     __shared__ double cs[2 * 96];
@@ -1212,7 +1244,7 @@ __global__ void __launch_bounds__(512) marg_solve_kernel(MargPlan mp, double eps
     const int md = mp.m_dense, nl = mp.n_lm, n = mp.n, P = mp.P;
     const int q = md + n;
     const int ldm = md + (md & 1), ldn = n + (n & 1), ldx = max(ldm, ldn);
-    const int esz = max(ldx * ldx, n * (ldm + md));
+    const int esz = max(max(ldx * ldx, n * (ldm + md)), 16 * q);
     double* Wk = sm;                  // q*q
     double* Ev = Wk + q * q;          // esz
     double* Vv = Ev + esz;            // ldx*ldx
@@ -1220,31 +1252,52 @@ __global__ void __launch_bounds__(512) marg_solve_kernel(MargPlan mp, double eps
     double* tv = bw + q;              // ldx
     auto symA = [&](int a, int b) { return a <= b ? mp.Am[(size_t)a * P + b] : mp.Am[(size_t)b * P + a]; };
     auto full = [&](int a) { return a < md ? a : a + nl; };  // index in Am of reduced index a
-    // 1. eliminate the landmark columns (exactly diagonal block): rank-1 downdates
+    long long mclk[6] = {0, 0, 0, 0, 0, 0};
+    long long mc0 = clock64();
+#define MSTAMP(k) do { const long long c1_ = clock64(); mclk[k] = c1_ - mc0; mc0 = c1_; } while (0)
+    // 1. eliminate the landmark columns (exactly diagonal block): rank-1 downdates, landmark rows staged through
+    //    shared memory 32 at a time (Ev is free until step 2: 32 * q <= ldx^2 is checked on the host side)
     for (int idx = tid; idx < q * q; idx += nt) {
-        const int aa = idx / q, bb = idx % q;
-        if (aa > bb) continue;
-        const int fa = full(aa), fb = full(bb);
-        double acc = symA(fa, fb);
-        for (int c = 0; c < nl; c++) {
-            const int fc = md + c;
-            const double wa = symA(fa, fc);
-            if (wa == 0.0) continue;
-            const double dc = mp.Am[(size_t)fc * P + fc];
-            if (dc > eps) acc -= wa * symA(fb, fc) / dc;
-        }
-        Wk[aa * q + bb] = acc;
-        Wk[bb * q + aa] = acc;
+        const int aa = idx / q, bb = idx - aa * q;
+        if (aa <= bb) Wk[idx] = symA(full(aa), full(bb));
     }
-    for (int aa = tid; aa < q; aa += nt) {
-        const int fa = full(aa);
-        double acc = mp.bm[fa];
-        for (int c = 0; c < nl; c++) {
-            const int fc = md + c;
-            const double dc = mp.Am[(size_t)fc * P + fc];
-            if (dc > eps) acc -= symA(fa, fc) * mp.bm[fc] / dc;
+    for (int aa = tid; aa < q; aa += nt) bw[aa] = mp.bm[full(aa)];
+    __syncthreads();
+    double* Wl = Ev;        // chunk x q landmark rows
+    double* invd = tv;      // chunk: 1 / d_c (0 when d_c <= eps), then b_c / d_c in invd + 32
+    for (int c0 = 0; c0 < nl; c0 += 16) {
+        const int cn = min(16, nl - c0);
+        for (int idx = tid; idx < cn * q; idx += nt) {
+            const int c = idx / q, aa = idx - c * q;
+            Wl[idx] = symA(full(aa), md + c0 + c);
         }
-        bw[aa] = acc;
+        if (tid < cn) {
+            const int fc = md + c0 + tid;
+            const double dc = mp.Am[(size_t)fc * P + fc];
+            invd[tid] = dc > eps ? 1.0 / dc : 0.0;
+            invd[16 + tid] = mp.bm[fc];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < q * q; idx += nt) {
+            const int aa = idx / q, bb = idx - aa * q;
+            if (aa > bb) continue;
+            double acc = 0;
+            for (int c = 0; c < cn; c++) {
+                const double wa = Wl[c * q + aa];
+                if (wa != 0.0) acc += wa * invd[c] * Wl[c * q + bb];
+            }
+            Wk[idx] -= acc;
+        }
+        for (int aa = tid; aa < q; aa += nt) {
+            double acc = 0;
+            for (int c = 0; c < cn; c++) acc += Wl[c * q + aa] * invd[c] * invd[16 + c];
+            bw[aa] -= acc;
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < q * q; idx += nt) {
+        const int aa = idx / q, bb = idx - aa * q;
+        if (aa > bb) Wk[idx] = Wk[bb * q + aa];
     }
     __syncthreads();
     // 2. pseudo-inverse of the dense marginalised block T (md x md) by eigen-decomposition
@@ -1253,7 +1306,9 @@ __global__ void __launch_bounds__(512) marg_solve_kernel(MargPlan mp, double eps
         Ev[idx] = (i < md && j < md) ? Wk[i * q + j] : 0.0;
     }
     __syncthreads();
-    jacobi_eigen(Ev, Vv, ldm, cs, pq, jflags);
+    MSTAMP(0);
+    const int sweeps_m = jacobi_eigen(Ev, Vv, ldm, cs, pq, jflags);
+    MSTAMP(1);
     for (int k = tid; k < ldm; k += nt) {
         const double w = Ev[k * ldm + k];
         tv[k] = (k < md && w > eps) ? 1.0 / w : 0.0;
@@ -1299,7 +1354,9 @@ __global__ void __launch_bounds__(512) marg_solve_kernel(MargPlan mp, double eps
         Ev[idx] = (i < n && j < n) ? 0.5 * (Ap[i * n + j] + Ap[j * n + i]) : 0.0;
     }
     __syncthreads();
-    jacobi_eigen(Ev, Vv, ldn, cs, pq, jflags);
+    MSTAMP(2);
+    const int sweeps_n = jacobi_eigen(Ev, Vv, ldn, cs, pq, jflags);
+    MSTAMP(3);
     for (int k = tid; k < ldn; k += nt) {
         double s = 0;
         for (int i = 0; i < n; i++) s += Vv[i * ldn + k] * mp.gout[i];
@@ -1329,14 +1386,22 @@ __global__ void __launch_bounds__(512) marg_solve_kernel(MargPlan mp, double eps
     }
     __syncthreads();
     for (int i = tid; i < n; i += nt) mp.gout[i] = bw[i];
-    if (tid == 0) mp.cout[0] = c0;
+    if (tid == 0) {
+        mp.cout[0] = c0;
+        if (mp.graw) {  // diagnostics behind the n used entries
+            mp.graw[n] = sweeps_m;
+            mp.graw[n + 1] = sweeps_n;
+            MSTAMP(4);
+            for (int k = 0; k < 5; k++) mp.graw[n + 2 + k] = (double)mclk[k];
+        }
+    }
 }
 
 size_t marg_solve_smem_bytes(int m_dense, int n) {
     const int q = m_dense + n;
     const int ldm = m_dense + (m_dense & 1), ldn = n + (n & 1), ldx = ldm > ldn ? ldm : ldn;
-    const size_t esz = std::max((size_t)ldx * ldx, (size_t)n * (ldm + m_dense));
-    return sizeof(double) * ((size_t)q * q + esz + (size_t)ldx * ldx + q + ldx);
+    const size_t esz = std::max(std::max((size_t)ldx * ldx, (size_t)n * (ldm + m_dense)), (size_t)16 * q);
+    return sizeof(double) * ((size_t)q * q + esz + (size_t)ldx * ldx + q + std::max(ldx, 32));
 }
 
 }  // namespace vb
@@ -1422,7 +1487,7 @@ void launch_marginalize(const BaProblem& p, const MargPlan& mp, cudaStream_t s, 
         configured = smem;
     }
     prof->begin(s);
-    marg_solve_kernel<<<1, 512, smem, s>>>(mp, 1e-8);
+    marg_solve_kernel<<<1, 1024, smem, s>>>(mp, 1e-8);
     prof->end(5, s);
     if (launches) *launches += 2;
 }

@@ -134,6 +134,7 @@ struct ve_estimator {
     int* h_marg_i = nullptr;
     double* h_marg_out = nullptr;
     std::vector<double> prior_raw_A, prior_raw_b;  // last Schur complement before the eps floor
+    double marg_sweeps[7] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -778,6 +779,8 @@ int marginalize(ve_estimator* e, vb::BaProblem& p) {
     VE_CUDA(cudaStreamSynchronize(e->stream));
     e->prior_raw_A.assign(e->h_marg_out, e->h_marg_out + (size_t)mp.n * mp.n);
     e->prior_raw_b.assign(e->h_marg_out + (size_t)e->nmax * e->nmax, e->h_marg_out + (size_t)e->nmax * e->nmax + mp.n);
+    if (mp.n + 7 <= e->nmax)
+        for (int k = 0; k < 7; k++) e->marg_sweeps[k] = e->h_marg_out[(size_t)e->nmax * e->nmax + mp.n + k];
     return VE_OK;
 }
 
@@ -1142,12 +1145,15 @@ int ve_last_traffic(const ve_estimator* e, double* h2d_bytes, double* d2h_bytes)
     return VE_OK;
 }
 
-int ve_solver_debug(const ve_estimator* e, double* out13) {
+int ve_solver_debug(const ve_estimator* e, double* out13) {  // 18 doubles
     if (!e || !out13) return VE_ERR_INVALID;
     out13[0] = e->last_state.retries;
     out13[1] = e->last_state.mu;
     out13[2] = e->last_state.radius;
-    for (int k = 0; k < 10; k++) out13[3 + k] = (double)e->last_state.clk[k];
+    for (int k = 0; k < 8; k++) out13[3 + k] = (double)e->last_state.clk[k];
+    out13[11] = e->marg_sweeps[0];
+    out13[12] = e->marg_sweeps[1];
+    for (int k = 0; k < 5; k++) out13[13 + k] = e->marg_sweeps[2 + k];
     return VE_OK;
 }
 

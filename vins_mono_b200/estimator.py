@@ -142,7 +142,7 @@ class Estimator:
         return a.value, b.value
 
     def solver_debug(self):
-        out = np.zeros(13)
+        out = np.zeros(18)
         self.lib.ve_solver_debug(self.h, _p(out))
         return dict(retries=int(out[0]), mu=out[1], radius=out[2], clk=out[3:].astype(np.int64).tolist())
 
