@@ -102,8 +102,9 @@ def make_gpu_pair(device):
     return trk, est
 
 
-def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images, profile=False, flush=None):
-    """One pass over the sequence.  Returns per-step device-event ms (timed steps only) and bookkeeping."""
+def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images, profile=False, flush=None, sync_cb=None):
+    """One pass over the sequence.  The K timed steps form ONE region bracketed by device synchronisation and a pair of
+    CUDA events (ms per step = region / K); sync_cb, if given, is the cross-rank barrier placed inside the bracket."""
     import torch
     trk, est = make_gpu_pair(device)
     if profile:
@@ -118,23 +119,28 @@ def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images
         d_imgs = torch.from_numpy(imgs).to(f"cuda:{device}")
         base = d_imgs.data_ptr()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    times, launches, h2d, d2h, traj_t, traj_p = [], 0, 0.0, 0.0, [], []
+    launches, h2d, d2h, traj_t, traj_p = 0, 0.0, 0.0, [], []
     pubs, i, first_msg = 0, 0, True
     n_img = len(ts)
+    n_timed, started = 0, False
 
     def one_image(k):
         if host_images:
             return trk.node_image(imgs[k], float(ts[k]))[0]
-        # img_callback gating is host logic; replicate vt_node_image with the device-resident frame
         return trk.node_image_device(base + k * frame_bytes, imgs.shape[2], float(ts[k]))
 
     while pubs < n_pub and i < n_img:
         timed = pubs >= n_init + warmup
-        if timed:
+        if timed and not started:
+            # start of the timed region: drain the device, evict L2 once (every timed step reads images that were
+            # uploaded long ago and never touched since, i.e. cold in L2; the rest of a step's data is produced inside it)
             if flush is not None:
-                flush.fill_(1.0)  # evict L2 between timed steps (untimed)
+                flush.fill_(1.0)
             torch.cuda.synchronize(device)
+            if sync_cb:
+                sync_cb()
             ev0.record()
+            started = True
         step_launch, step_h2d, step_d2h = 0, 0.0, 0.0
         r = 0
         while r != 2 and i < n_img:  # images until one publishes
@@ -154,14 +160,12 @@ def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images
         else:
             feeder.feed(est, stamp)
             est.processImage(ids, d, stamp)
-            step_launch += est.timing()["launches"]
+            step_launch += est.launch_count()
             a, b = est.traffic()
             step_h2d += a
             step_d2h += b
         if timed:
-            ev1.record()
-            ev1.synchronize()
-            times.append(ev0.elapsed_time(ev1))
+            n_timed += 1
             launches += step_launch
             h2d += step_h2d
             d2h += step_d2h
@@ -170,6 +174,10 @@ def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images
             traj_t.append(stamp)
             traj_p.append(st[-1, 0:3].copy())
         pubs += 1
+    torch.cuda.synchronize(device)  # includes the last frame's (asynchronous) marginalisation
+    ev1.record()
+    ev1.synchronize()
+    times = [ev0.elapsed_time(ev1) / max(n_timed, 1)] * n_timed if started else []
     out = dict(times=times, launches=launches, h2d=h2d, d2h=d2h, traj_t=traj_t, traj_p=traj_p, info=est.info())
     if profile:
         out["trk_k"], out["est_k"] = trk.kernel_times(), est.kernel_times()
@@ -279,11 +287,12 @@ def main():
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
-    res_dev = run_ours_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, a.steps, local, host_images=False, flush=flush)
+    rank_barrier = (lambda: dist.barrier()) if world > 1 else None
+    res_dev = run_ours_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, a.steps, local, host_images=False, flush=flush, sync_cb=rank_barrier)
     barrier()
     clk = clocks.stop()
     barrier()
-    res_e2e = run_ours_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, a.steps, local, host_images=True, flush=flush)
+    res_e2e = run_ours_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, a.steps, local, host_images=True, flush=flush, sync_cb=rank_barrier)
     barrier()
 
     def agg(res):
@@ -352,8 +361,9 @@ def main():
         "ms_per_step": 1e3 * t_dev / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "configs[1]: single 752x480 synthetic sequence per GPU, 10-keyframe window, 150 features, 200 Hz IMU, "
-                               "fp64 Jacobians", "sequences_per_gpu": 1, "l2_flush_between_steps": True,
-                   "timing": "CUDA events around each step (sync both sides), summed; max over ranks"},
+                               "fp64 Jacobians", "sequences_per_gpu": 1,
+                   "l2": "L2 flushed (256 MB write) at the start of the timed region; every step reads two images that were never touched since upload",
+                   "timing": "one CUDA-event pair around the K steps, device synchronised (and ranks barriered) on both sides; max over ranks"},
         "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": 1e3 * t_e2e / k,
                 "h2d_bytes_per_step": res_e2e["h2d"] / k, "d2h_bytes_per_step": res_e2e["d2h"] / k},
         "gpu_launches": int(launches.item()),

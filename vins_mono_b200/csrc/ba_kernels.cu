@@ -139,6 +139,32 @@ __global__ void __launch_bounds__(256) preint_push_kernel(PreInt* __restrict__ s
     }
 }
 
+// new IntegrationBase{acc_0, gyr_0, ba, bg}: identity Jacobian, zero covariance (integration_base.h:13-28)
+struct PreIntInit {
+    double acc0[3], gyr0[3], ba[3], bg[3];
+};
+__global__ void __launch_bounds__(256) preint_init_kernel(PreInt* __restrict__ slot, PreIntInit v) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 225; i += 256) {
+        slot->jac[i] = (i / 15 == i % 15) ? 1.0 : 0.0;
+        slot->cov[i] = 0.0;
+        slot->sqrt_info[i] = 0.0;
+    }
+    if (tid == 0) {
+        slot->sum_dt = 0.0;
+        slot->dq[0] = 1.0;
+        for (int i = 0; i < 3; i++) {
+            slot->dp[i] = 0.0;
+            slot->dv[i] = 0.0;
+            slot->dq[1 + i] = 0.0;
+            slot->ba[i] = v.ba[i];
+            slot->bg[i] = v.bg[i];
+            slot->acc0[i] = v.acc0[i];
+            slot->gyr0[i] = v.gyr0[i];
+        }
+    }
+}
+
 // sqrt_info = chol_lower(cov^-1)^T for each listed slot (one warp each; Gauss-Jordan with partial pivoting).
 __global__ void __launch_bounds__(32) sqrt_info_kernel(PreInt* __restrict__ slots, const int* __restrict__ which, int count) {
     __shared__ double A[15][31];
@@ -1416,6 +1442,17 @@ void launch_preint_push(PreInt* slot, int n, const double* d_samples, double acc
                         cudaStream_t s) {
     if (n <= 0) return;
     preint_push_kernel<<<1, 256, 0, s>>>(slot, n, d_samples, acc_n, gyr_n, acc_w, gyr_w);
+}
+
+void launch_preint_init(PreInt* slot, const double* acc0, const double* gyr0, const double* ba, const double* bg, cudaStream_t s) {
+    PreIntInit v;
+    for (int i = 0; i < 3; i++) {
+        v.acc0[i] = acc0[i];
+        v.gyr0[i] = gyr0[i];
+        v.ba[i] = ba[i];
+        v.bg[i] = bg[i];
+    }
+    preint_init_kernel<<<1, 256, 0, s>>>(slot, v);
 }
 
 void launch_sqrt_info(PreInt* slots, const int* d_which, int count, cudaStream_t s) {

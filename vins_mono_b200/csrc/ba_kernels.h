@@ -27,6 +27,7 @@ struct MargPlan {  // dense marginalisation system layout: [m_dense | n_lm landm
 
 void launch_preint_push(PreInt* slot, int n, const double* d_samples, double acc_n, double gyr_n, double acc_w, double gyr_w,
                         cudaStream_t s);
+void launch_preint_init(PreInt* slot, const double* acc0, const double* gyr0, const double* ba, const double* bg, cudaStream_t s);
 void launch_sqrt_info(PreInt* slots, const int* d_which, int count, cudaStream_t s);
 // full trust-region solve: linearise x[st->cur], then max_iterations x {schur, step, zero, linearise+decide}
 // profile slots: 0 linearize, 1 schur, 2 step, 3 zero, 4 marg_build, 5 marg_solve, 6 preint, 7 sqrt_info

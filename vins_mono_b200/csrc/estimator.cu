@@ -135,6 +135,9 @@ struct ve_estimator {
     double* h_marg_out = nullptr;
     std::vector<double> prior_raw_A, prior_raw_b;  // last Schur complement before the eps floor
     double marg_sweeps[7] = {0, 0, 0, 0, 0, 0, 0};
+    int sample_seg = 0;
+    bool marg_pending = false;  // marginalisation kernels enqueued, results not yet read back
+    int marg_n = 0;
 };
 
 namespace {
@@ -169,17 +172,10 @@ bool usable(const ve_estimator* e, FeaturePerId& it) {  // the filter repeated a
 
 // ---- pre-integration slots ---------------------------------------------------------------------
 int init_slot(ve_estimator* e, int frame, const Vec3& a0, const Vec3& g0, const Vec3& ba, const Vec3& bg) {
-    vb::PreInt& s = *e->h_preint;
-    std::memset(&s, 0, sizeof(s));
-    s.dq[0] = 1.0;
-    for (int i = 0; i < 15; i++) s.jac[16 * i] = 1.0;
-    s.ba[0] = ba.x; s.ba[1] = ba.y; s.ba[2] = ba.z;
-    s.bg[0] = bg.x; s.bg[1] = bg.y; s.bg[2] = bg.z;
-    s.acc0[0] = a0.x; s.acc0[1] = a0.y; s.acc0[2] = a0.z;
-    s.gyr0[0] = g0.x; s.gyr0[1] = g0.y; s.gyr0[2] = g0.z;
+    const double A0[3] = {a0.x, a0.y, a0.z}, G0[3] = {g0.x, g0.y, g0.z}, BA[3] = {ba.x, ba.y, ba.z}, BG[3] = {bg.x, bg.y, bg.z};
     const int slot = e->slot_of[frame];
-    VE_CUDA(cudaMemcpyAsync(e->d_preint.p + slot, &s, sizeof(s), cudaMemcpyHostToDevice, e->stream));
-    VE_CUDA(cudaStreamSynchronize(e->stream));  // h_preint is reused
+    vb::launch_preint_init(e->d_preint.p + slot, A0, G0, BA, BG, e->stream);  // values travel as kernel arguments
+    e->last_launches++;
     e->slot_valid[frame] = true;
     e->flushed[frame] = 0;
     e->sum_dt[frame] = 0;
@@ -194,24 +190,29 @@ int flush_frame(ve_estimator* e, int frame) {
     const size_t n = e->dt_buf[frame].size();
     if (!e->slot_valid[frame] || e->flushed[frame] >= n) return VE_OK;
     const size_t k0 = e->flushed[frame], cnt = n - k0;
-    if (cnt > 4096) {
+    if (cnt > 512) {
         e->err = "too many IMU samples in one interval";
         return VE_ERR_CAPACITY;
     }
+    // ring of 8 staging segments: no host wait here; a segment is reused 8 flushes later, by which time at least one
+    // per-frame synchronisation (the solve's state read-back) has drained the stream
+    const int seg = e->sample_seg;
+    e->sample_seg = (e->sample_seg + 1) & 7;
+    double* hs = e->h_samples + (size_t)seg * 7 * 512;
+    double* ds = e->d_samples.p + (size_t)seg * 7 * 512;
     for (size_t k = 0; k < cnt; k++) {
-        double* s = e->h_samples + 7 * k;
+        double* s = hs + 7 * k;
         s[0] = e->dt_buf[frame][k0 + k];
         const Vec3 &a = e->acc_buf[frame][k0 + k], &w = e->gyr_buf[frame][k0 + k];
         s[1] = a.x; s[2] = a.y; s[3] = a.z; s[4] = w.x; s[5] = w.y; s[6] = w.z;
     }
-    VE_CUDA(cudaMemcpyAsync(e->d_samples.p, e->h_samples, sizeof(double) * 7 * cnt, cudaMemcpyHostToDevice, e->stream));
+    VE_CUDA(cudaMemcpyAsync(ds, hs, sizeof(double) * 7 * cnt, cudaMemcpyHostToDevice, e->stream));
     e->prof.begin(e->stream);
-    vb::launch_preint_push(e->d_preint.p + e->slot_of[frame], (int)cnt, e->d_samples.p, e->cfg.acc_n, e->cfg.gyr_n, e->cfg.acc_w,
+    vb::launch_preint_push(e->d_preint.p + e->slot_of[frame], (int)cnt, ds, e->cfg.acc_n, e->cfg.gyr_n, e->cfg.acc_w,
                            e->cfg.gyr_w, e->stream);
     e->prof.end(6, e->stream);
     e->h2d_bytes += sizeof(double) * 7 * cnt;
     e->last_launches++;
-    VE_CUDA(cudaStreamSynchronize(e->stream));  // staging buffers are reused by the next flush
     e->flushed[frame] = n;
     e->sqrt_dirty[e->slot_of[frame]] = true;
     return VE_OK;
@@ -776,16 +777,30 @@ int marginalize(ve_estimator* e, vb::BaProblem& p) {
     e->has_prior = true;
     rc = upload_prior_meta(e, nb);
     if (rc) return rc;
-    VE_CUDA(cudaStreamSynchronize(e->stream));
-    e->prior_raw_A.assign(e->h_marg_out, e->h_marg_out + (size_t)mp.n * mp.n);
-    e->prior_raw_b.assign(e->h_marg_out + (size_t)e->nmax * e->nmax, e->h_marg_out + (size_t)e->nmax * e->nmax + mp.n);
-    if (mp.n + 7 <= e->nmax)
-        for (int k = 0; k < 7; k++) e->marg_sweeps[k] = e->h_marg_out[(size_t)e->nmax * e->nmax + mp.n + k];
+    // No host wait: the new prior is consumed by the next solve on the same (in-order) stream, so the marginalisation
+    // overlaps whatever the caller does next (the reference's tracker node runs in another process anyway).
+    e->marg_pending = true;
+    e->marg_n = mp.n;
+    return VE_OK;
+}
+
+// Waits for a pending marginalisation and collects its diagnostics (Schur complement before the eps floor).
+int finish_marg(ve_estimator* e) {
+    if (!e->marg_pending) return VE_OK;
+    VE_CUDA(cudaEventSynchronize(e->ev[3]));
+    e->marg_pending = false;
+    const int n = e->marg_n;
+    e->prior_raw_A.assign(e->h_marg_out, e->h_marg_out + (size_t)n * n);
+    e->prior_raw_b.assign(e->h_marg_out + (size_t)e->nmax * e->nmax, e->h_marg_out + (size_t)e->nmax * e->nmax + n);
+    if (n + 7 <= e->nmax)
+        for (int k = 0; k < 7; k++) e->marg_sweeps[k] = e->h_marg_out[(size_t)e->nmax * e->nmax + n + k];
+    cudaEventElapsedTime(&e->last_ms[2], e->ev[2], e->ev[3]);
     return VE_OK;
 }
 
 int optimization(ve_estimator* e) {
     int rc;
+    if ((rc = finish_marg(e))) return rc;  // staging buffers and the event pair are about to be reused
     VE_CUDA(cudaEventRecord(e->ev[0], e->stream));
     for (int f = 0; f <= e->W; f++)
         if ((rc = flush_frame(e, f))) return rc;
@@ -815,14 +830,13 @@ int optimization(ve_estimator* e) {
     e->last_state = st;
     e->n_solves++;
     unpack_states(e, h2 + (size_t)st.cur * ns);
+    cudaEventElapsedTime(&e->last_ms[0], e->ev[0], e->ev[1]);
+    cudaEventElapsedTime(&e->last_ms[1], e->ev[1], e->ev[2]);
+    cudaEventElapsedTime(&e->last_ms[3], e->ev[0], e->ev[2]);
     rc = marginalize(e, p);
     if (rc) return rc;
     VE_CUDA(cudaEventRecord(e->ev[3], e->stream));
-    VE_CUDA(cudaEventSynchronize(e->ev[3]));
-    cudaEventElapsedTime(&e->last_ms[0], e->ev[0], e->ev[1]);
-    cudaEventElapsedTime(&e->last_ms[1], e->ev[1], e->ev[2]);
-    cudaEventElapsedTime(&e->last_ms[2], e->ev[2], e->ev[3]);
-    cudaEventElapsedTime(&e->last_ms[3], e->ev[0], e->ev[3]);
+    if (e->prof.on && (rc = finish_marg(e))) return rc;  // profiling runs are serialised anyway
     return VE_OK;
 }
 
@@ -942,7 +956,7 @@ int ve_create(const ve_config* cfg, ve_estimator** out) {
     VE_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     for (auto& ev : e->ev) VE_TRY(cudaEventCreate(&ev));
     VE_TRY(e->d_preint.alloc(F));
-    VE_TRY(e->d_samples.alloc(7 * 4096));
+    VE_TRY(e->d_samples.alloc(8 * 7 * 512));
     VE_TRY(e->d_which.alloc(F));
     const size_t Pm = (size_t)e->nmax + 15 + e->Lmax;
     for (int b = 0; b < 2; b++) {
@@ -965,7 +979,7 @@ int ve_create(const ve_config* cfg, ve_estimator** out) {
     VE_TRY(cudaHostAlloc(&e->h_states, sizeof(double) * 3 * states_doubles(e), cudaHostAllocDefault));
     VE_TRY(cudaHostAlloc(&e->h_obs, sizeof(double) * (6 * (size_t)e->Lmax + 6 * (size_t)e->Mmax), cudaHostAllocDefault));
     VE_TRY(cudaHostAlloc(&e->h_ints, sizeof(int) * ((size_t)2 * e->Lmax + 1 + e->Mmax + W), cudaHostAllocDefault));
-    VE_TRY(cudaHostAlloc(&e->h_samples, sizeof(double) * 7 * 4096, cudaHostAllocDefault));
+    VE_TRY(cudaHostAlloc(&e->h_samples, sizeof(double) * 8 * 7 * 512, cudaHostAllocDefault));
     VE_TRY(cudaHostAlloc(&e->h_preint, sizeof(vb::PreInt), cudaHostAllocDefault));
     VE_TRY(cudaHostAlloc(&e->h_st, sizeof(vb::SolverState), cudaHostAllocDefault));
     VE_TRY(cudaHostAlloc(&e->h_prior, sizeof(double) * 9 * 64, cudaHostAllocDefault));
@@ -1086,7 +1100,7 @@ int ve_info(const ve_estimator* e, int* o, double* costs2) {
     if (!e || !o) return VE_ERR_INVALID;
     o[0] = e->solver_flag; o[1] = e->frame_count; o[2] = e->marginalization_flag; o[3] = e->n_solves; o[4] = e->n_reboots;
     o[5] = e->last_landmarks; o[6] = e->last_visual; o[7] = e->last_state.iteration; o[8] = e->last_state.successful;
-    // same coding as the oracle: 0 iteration cap, 1 parameter tol, 2 function tol, 4 failure
+    // termination coding: 0 iteration cap, 1 parameter tol, 2 function tol, 4 failure
     o[9] = e->last_state.done == 2 ? 1 : e->last_state.done == 3 ? 2 : e->last_state.done == 4 ? 4 : 0;
     if (costs2) {
         costs2[0] = e->last_state.initial_cost;
@@ -1095,9 +1109,11 @@ int ve_info(const ve_estimator* e, int* o, double* costs2) {
     return VE_OK;
 }
 
-int ve_get_prior(const ve_estimator* e, int cap, double* A, double* b, int* nblocks, int* blocks4) {
-    if (!e) return VE_ERR_INVALID;
+int ve_get_prior(const ve_estimator* ce, int cap, double* A, double* b, int* nblocks, int* blocks4) {
+    if (!ce) return VE_ERR_INVALID;
+    ve_estimator* e = const_cast<ve_estimator*>(ce);
     if (!e->has_prior) return 0;
+    if (finish_marg(e)) return VE_ERR_CUDA;
     const int n = e->prior_n;
     if (n > cap) return -n;
     std::memcpy(A, e->prior_raw_A.data(), sizeof(double) * (size_t)n * n);
@@ -1145,8 +1161,10 @@ int ve_last_traffic(const ve_estimator* e, double* h2d_bytes, double* d2h_bytes)
     return VE_OK;
 }
 
-int ve_solver_debug(const ve_estimator* e, double* out13) {  // 18 doubles
-    if (!e || !out13) return VE_ERR_INVALID;
+int ve_solver_debug(const ve_estimator* ce, double* out13) {  // 18 doubles
+    if (!ce || !out13) return VE_ERR_INVALID;
+    ve_estimator* e = const_cast<ve_estimator*>(ce);
+    if (finish_marg(e)) return VE_ERR_CUDA;
     out13[0] = e->last_state.retries;
     out13[1] = e->last_state.mu;
     out13[2] = e->last_state.radius;
@@ -1157,8 +1175,10 @@ int ve_solver_debug(const ve_estimator* e, double* out13) {  // 18 doubles
     return VE_OK;
 }
 
-int ve_last_timing(const ve_estimator* e, float* ms4, int* launches) {
-    if (!e) return VE_ERR_INVALID;
+int ve_last_timing(const ve_estimator* ce, float* ms4, int* launches) {
+    if (!ce) return VE_ERR_INVALID;
+    ve_estimator* e = const_cast<ve_estimator*>(ce);
+    if (ms4 && finish_marg(e)) return VE_ERR_CUDA;
     if (ms4) std::memcpy(ms4, e->last_ms, sizeof(e->last_ms));
     if (launches) *launches = e->last_launches;
     return VE_OK;

@@ -2,7 +2,7 @@
 //
 // Every kernel reproduces the integer / IEEE-f32 arithmetic of the OpenCV routine the reference calls
 // (feature_tracker/src/feature_tracker.cpp:87-93 CLAHE, :113 calcOpticalFlowPyrLK, :66 circle,
-// :149 goodFeaturesToTrack) operation by operation, so results are bit-identical to the CPU oracle:
+// :149 goodFeaturesToTrack) operation by operation, so results are bit-identical to a plain CPU evaluation:
 // no FMA contraction where OpenCV's baseline build has none (explicit __fmul_rn/__fadd_rn), integer
 // window sums accumulated exactly.  All of this is HBM/L2-bound byte and integer work; nothing here is
 // GEMM shaped, so no tensor cores.

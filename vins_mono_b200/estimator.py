@@ -146,6 +146,12 @@ class Estimator:
         self.lib.ve_solver_debug(self.h, _p(out))
         return dict(retries=int(out[0]), mu=out[1], radius=out[2], clk=out[3:].astype(np.int64).tolist())
 
+    def launch_count(self):
+        """Kernel launches of the last processImage (does not wait for a pending marginalisation)."""
+        k = C.c_int(0)
+        self.lib.ve_last_timing(self.h, None, C.byref(k))
+        return k.value
+
     def timing(self):
         ms, k = np.zeros(4, np.float32), C.c_int(0)
         self.lib.ve_last_timing(self.h, _p(ms), C.byref(k))
