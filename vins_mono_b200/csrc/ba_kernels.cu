@@ -1171,7 +1171,8 @@ namespace {
 
 // Cyclic Jacobi with round-robin parallel ordering on a symmetric matrix in shared memory.
 // A is ld x ld with ld even and >= n, rows/columns >= n zero (a zero row never rotates).  On exit the
-// eigenvalues are on the diagonal and V (ld x ld) holds the eigenvectors in its columns.  Each round applies
+// eigenvalues are on the diagonal and V (ld x ld) holds the eigenvectors in its ROWS (V[k*ld + i] = component i of
+// eigenvector k: the rotation then touches two contiguous rows, free of shared-memory bank conflicts).  Each round applies
 // ld/2 disjoint rotations: one phase computes (c, s) per pair, one phase updates every 2x2 block
 // G_k^T A_(k,k') G_k' and V G_k, i.e. two barriers per round.  A pair is rotated when
 // |a_pq| > 1e-15 sqrt|a_pp a_qq| (relative criterion: resolves the small eigenvalues of these badly scaled
@@ -1242,9 +1243,9 @@ __device__ int jacobi_eigen(double* A, double* V, int ld, double* cs, int* pq, i
                     const double c1 = cs[2 * k], s1 = cs[2 * k + 1];
                     if (i >= ld || s1 == 0.0) continue;
                     const int p0 = pq[2 * k], q0 = pq[2 * k + 1];
-                    const double vip = V[i * ld + p0], viq = V[i * ld + q0];
-                    V[i * ld + p0] = c1 * vip - s1 * viq;
-                    V[i * ld + q0] = s1 * vip + c1 * viq;
+                    const double vip = V[p0 * ld + i], viq = V[q0 * ld + i];
+                    V[p0 * ld + i] = c1 * vip - s1 * viq;
+                    V[q0 * ld + i] = s1 * vip + c1 * viq;
                 }
             }
             __syncthreads();
@@ -1345,7 +1346,7 @@ __global__ void __launch_bounds__(1024) marg_solve_kernel(MargPlan mp, double ep
     for (int idx = tid; idx < n * ldm; idx += nt) {
         const int i = idx / ldm, k = idx % ldm;
         double s = 0;
-        for (int j = 0; j < md; j++) s += Wk[(md + i) * q + j] * Vv[j * ldm + k];
+        for (int j = 0; j < md; j++) s += Wk[(md + i) * q + j] * Vv[k * ldm + j];
         Ev[idx] = s * tv[k];
     }
     __syncthreads();
@@ -1353,7 +1354,7 @@ __global__ void __launch_bounds__(1024) marg_solve_kernel(MargPlan mp, double ep
     for (int idx = tid; idx < n * md; idx += nt) {
         const int i = idx / md, j = idx % md;
         double s = 0;
-        for (int k = 0; k < ldm; k++) s += Ev[i * ldm + k] * Vv[j * ldm + k];
+        for (int k = 0; k < ldm; k++) s += Ev[i * ldm + k] * Vv[k * ldm + j];
         X[idx] = s;
     }
     __syncthreads();
@@ -1385,7 +1386,7 @@ __global__ void __launch_bounds__(1024) marg_solve_kernel(MargPlan mp, double ep
     MSTAMP(3);
     for (int k = tid; k < ldn; k += nt) {
         double s = 0;
-        for (int i = 0; i < n; i++) s += Vv[i * ldn + k] * mp.gout[i];
+        for (int i = 0; i < n; i++) s += Vv[k * ldn + i] * mp.gout[i];
         tv[k] = s;  // V_k^T b'
     }
     __syncthreads();
@@ -1400,14 +1401,14 @@ __global__ void __launch_bounds__(1024) marg_solve_kernel(MargPlan mp, double ep
         double s = 0;
         for (int k = 0; k < ldn; k++) {
             const double w = Ev[k * ldn + k];
-            if (w > eps) s += Vv[i * ldn + k] * w * Vv[j * ldn + k];
+            if (w > eps) s += Vv[k * ldn + i] * w * Vv[k * ldn + j];
         }
         Ap[idx] = s;
     }
     for (int i = tid; i < n; i += nt) {
         double s = 0;
         for (int k = 0; k < ldn; k++)
-            if (Ev[k * ldn + k] > eps) s += Vv[i * ldn + k] * tv[k];
+            if (Ev[k * ldn + k] > eps) s += Vv[k * ldn + i] * tv[k];
         bw[i] = s;
     }
     __syncthreads();

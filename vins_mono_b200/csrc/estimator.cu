@@ -135,7 +135,7 @@ struct ve_estimator {
     double* h_marg_out = nullptr;
     std::vector<double> prior_raw_A, prior_raw_b;  // last Schur complement before the eps floor
     double marg_sweeps[7] = {0, 0, 0, 0, 0, 0, 0};
-    int sample_seg = 0;
+    int sample_seg = 0, flushes_in_flight = 0;
     bool marg_pending = false;  // marginalisation kernels enqueued, results not yet read back
     int marg_n = 0;
 };
@@ -196,6 +196,10 @@ int flush_frame(ve_estimator* e, int frame) {
     }
     // ring of 8 staging segments: no host wait here; a segment is reused 8 flushes later, by which time at least one
     // per-frame synchronisation (the solve's state read-back) has drained the stream
+    if (++e->flushes_in_flight > 8) {  // every staging segment may still be waiting for its copy
+        VE_CUDA(cudaStreamSynchronize(e->stream));
+        e->flushes_in_flight = 1;
+    }
     const int seg = e->sample_seg;
     e->sample_seg = (e->sample_seg + 1) & 7;
     double* hs = e->h_samples + (size_t)seg * 7 * 512;
@@ -827,6 +831,7 @@ int optimization(ve_estimator* e) {
     e->d2h_bytes += 2 * sizeof(double) * ns + sizeof(st);
     VE_CUDA(cudaEventRecord(e->ev[2], e->stream));
     VE_CUDA(cudaStreamSynchronize(e->stream));
+    e->flushes_in_flight = 0;
     e->last_state = st;
     e->n_solves++;
     unpack_states(e, h2 + (size_t)st.cur * ns);

@@ -159,8 +159,10 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(const uint8_t* __restrict_
 // 24x24 previous-image neighbourhood in shared memory, derives the Scharr gradient there (zero outside
 // the image, reflect-101 inside), builds the 21x21 int16 patch + gradient patch, then iterates on the
 // next image re-staging a 22x22 tile per iteration.  Reductions are warp shuffles on 64-bit integers.
+#define LK_RS 40                 // next-image search region cached per level: 22x22 window + 9 px margin each side
 struct LkSmem {
-    uint8_t tile[24 * 24];       // previous-level neighbourhood / next-level 22x22 tile
+    uint8_t tile[24 * 24];       // previous-level neighbourhood
+    uint8_t region[LK_RS * LK_RS];  // next-level search region (reflect-101 padded coordinates)
     int16_t deriv[22 * 22 * 2];  // Scharr dx,dy at the 22x22 bilinear source positions
     int16_t iwin[441];
     int16_t dwin[441 * 2];
@@ -276,6 +278,8 @@ __global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(PyramidView pre
         nx = __fsub_rn(nx, half);
         ny = __fsub_rn(ny, half);
         float pdx = 0.f, pdy = 0.f;
+        int ry0 = 0, rx0 = 0;
+        bool have_region = false;
         for (int j = 0; j < max_iter; j++) {
             const int inx = (int)floorf(nx), iny = (int)floorf(ny);
             if (inx < -W || inx >= cols || iny < -W || iny >= rows) {
@@ -288,17 +292,25 @@ __global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(PyramidView pre
             iw01 = __float2int_rn(__fmul_rn(__fmul_rn(a, __fsub_rn(1.f, b)), 16384.f));
             iw10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), b), 16384.f));
             iw11 = 16384 - iw00 - iw01 - iw10;
-            __syncwarp();
-            for (int i = lane; i < 22 * 22; i += 32) {
-                const int ty = i / 22, tx = i - ty * 22;
-                sm.tile[i] = J[(size_t)reflect101(iny + ty, rows) * pitch + reflect101(inx + tx, cols)];
+            // the 22x22 tile the window needs: served from the cached region, which is (re)loaded around the
+            // current position only when the window walks out of it
+            if (!have_region || inx < rx0 || inx + 22 > rx0 + LK_RS || iny < ry0 || iny + 22 > ry0 + LK_RS) {
+                ry0 = iny - (LK_RS - 22) / 2;
+                rx0 = inx - (LK_RS - 22) / 2;
+                __syncwarp();
+                for (int i = lane; i < LK_RS * LK_RS; i += 32) {
+                    const int ty = i / LK_RS, tx = i - ty * LK_RS;
+                    sm.region[i] = J[(size_t)reflect101(ry0 + ty, rows) * pitch + reflect101(rx0 + tx, cols)];
+                }
+                __syncwarp();
+                have_region = true;
             }
-            __syncwarp();
+            const uint8_t* rbase = &sm.region[(iny - ry0) * LK_RS + (inx - rx0)];
             long long b1 = 0, b2 = 0;
             for (int i = lane; i < 441; i += 32) {
                 const int y = i / 21, x = i - y * 21;
-                const uint8_t* t = &sm.tile[y * 22 + x];
-                const int diff = ((t[0] * iw00 + t[1] * iw01 + t[22] * iw10 + t[23] * iw11 + (1 << 8)) >> 9) - sm.iwin[i];
+                const uint8_t* t = rbase + y * LK_RS + x;
+                const int diff = ((t[0] * iw00 + t[1] * iw01 + t[LK_RS] * iw10 + t[LK_RS + 1] * iw11 + (1 << 8)) >> 9) - sm.iwin[i];
                 b1 += (long long)(diff * sm.dwin[2 * i]);
                 b2 += (long long)(diff * sm.dwin[2 * i + 1]);
             }
