@@ -84,8 +84,8 @@ int ve_kernel_times(const ve_estimator* e, double* ms8, int* count8);
 int ve_last_traffic(const ve_estimator* e, double* h2d_bytes, double* d2h_bytes);
 
 /* Solver internals of the last solve (profiling/tests): out[0] linear-solver retries, [1] mu, [2] radius,
- * [3..10] per-phase cycle counters of the step kernel summed over the iterations, [11..12] Jacobi sweeps of the two
- * eigen-decompositions of the last marginalisation, [13..17] its phase cycle counters. */
+ * [3..10] per-phase cycle counters of the step kernel summed over the iterations, [11..12] cycles of the
+ * tridiagonalisation / QL phases of the last marginalisation's prior eigen-decomposition, [13..17] its phase cycle counters. */
 int ve_solver_debug(const ve_estimator* e, double* out18);
 
 #ifdef __cplusplus

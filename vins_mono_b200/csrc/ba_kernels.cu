@@ -20,6 +20,7 @@
 #include <cfloat>
 
 #include "ba_device.cuh"
+#include "sym_eig.h"
 
 namespace vb {
 
@@ -626,129 +627,198 @@ __device__ double quad_form(const BaProblem& p, const BaAccum& a, const double* 
 }
 
 // In-place lower Cholesky of the n x n matrix stored packed (row-major lower triangle) in `Lp`; rdiag receives
-// 1 / L_kk.  Right-looking, blocked by 8 columns: the 8x8 diagonal block is factorised by warp 0 in registers
-// (one row per lane, pivots and multipliers exchanged with shuffles), the panel below by one thread per row
-// (forward substitution against the diagonal block, reciprocal pivots), the trailing matrix with 4x4 register
-// tiles (0.5 shared-memory loads per FMA).  3 barriers per block column.
+// 1 / L_kk, linv the inverses of the 8x8 diagonal blocks (for the triangular solves).  Right-looking, blocked by 8
+// columns, with one block of look-ahead: the trailing update is split into the next block column (all warps, "part A")
+// and the rest ("part B"); warp 0 factorises the next 8x8 diagonal block in registers (one row per lane, pivots and
+// multipliers exchanged with shuffles) WHILE the other warps run part B, which takes the serial diagonal chain
+// (8 dependent rsqrt + shuffle rounds) off the critical path.  The panel below a diagonal block is solved by one
+// thread per row, trailing tiles are 4x4 register tiles (0.5 shared-memory loads per FMA).  3 barriers per block column.
 #define CHOL_NB 8
-__device__ bool cholesky_packed(double* Lp, int n, double* rdiag, double* linv, int* flag) {
-    __shared__ double dblk[CHOL_NB][CHOL_NB + 1];
+#define CHOL_PS 360  // panel copy stride: STEP_MAXD + 8 rows of slack for partial tiles
+#ifdef CHOL_PROF  // harness/micro/chol_bench.cu: per-phase cycle counters kept in shared memory by thread 0
+__shared__ long long chol_clk[8];
+#define CP_BEGIN() long long cp0_ = clock64()
+#define CP(k) do { if (threadIdx.x == 0) { const long long c1_ = clock64(); chol_clk[k] += c1_ - cp0_; cp0_ = c1_; } } while (0)
+#else
+#define CP_BEGIN() do {} while (0)
+#define CP(k) do {} while (0)
+#endif
+// One full warp factorises the diagonal block starting at kb (w columns) and publishes it in dblk and rdiag.
+// When upd != 0 the pending rank-8 update from the previous panel (held column-major in Pc) is applied first: the 64
+// entries of the block are spread over the lanes (a length-8 dot product each) and staged in shared memory.  Every
+// lane then factorises the WHOLE 8x8 block redundantly in registers: no shuffles, so the dependent chain per column
+// is rsqrt -> scale -> one FMA (one row per lane with shuffled pivots/multipliers measured 2.6k cycles per block for
+// the chain alone, this form 1.1k; harness/micro/chol_bench.cu).  Rows >= w behave like identity rows.
+__device__ __forceinline__ void chol_diag_block(double* Lp, const double* Pc, int kb, int w, double* rdiag,
+                                                double (*dblk)[CHOL_NB + 1], int* flag, int upd, double* stage) {
+    const int lane = threadIdx.x & 31;
+    CP_BEGIN();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int e = lane + 32 * h, rr = e >> 3, c = e & 7;
+        double v = (rr == c) ? 1.0 : 0.0;
+        if (rr < w && c <= rr) {
+            v = Lp[(kb + rr) * (kb + rr + 1) / 2 + kb + c];
+            if (upd) {
+                double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+                for (int t = 0; t < CHOL_NB; t += 2) {
+                    acc0 += Pc[t * CHOL_PS + kb + rr] * Pc[t * CHOL_PS + kb + c];
+                    acc1 += Pc[(t + 1) * CHOL_PS + kb + rr] * Pc[(t + 1) * CHOL_PS + kb + c];
+                }
+                v -= acc0 + acc1;
+            }
+        }
+        stage[e] = v;
+    }
+    __syncwarp();
+    double a[CHOL_NB][CHOL_NB];
+#pragma unroll
+    for (int rr = 0; rr < CHOL_NB; rr++)
+#pragma unroll
+        for (int c = 0; c <= rr; c++) a[rr][c] = stage[rr * CHOL_NB + c];
+    CP(0);
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < CHOL_NB; c++) {
+        const double piv = a[c][c];
+        if (!(piv > 0.0) || !isfinite(piv)) ok = false;
+        const double rc = rsqrt(piv);
+        a[c][c] = piv * rc;
+#pragma unroll
+        for (int rr = c + 1; rr < CHOL_NB; rr++) a[rr][c] *= rc;
+        // column c is final: every lane holds the same values and stores them to the same addresses (the stores fill
+        // the latency bubbles of the chain and free the registers early)
+        if (c < w) {
+            rdiag[kb + c] = rc;
+#pragma unroll
+            for (int rr = c; rr < CHOL_NB; rr++)
+                if (rr < w) {
+                    Lp[(kb + rr) * (kb + rr + 1) / 2 + kb + c] = a[rr][c];
+                    dblk[rr][c] = a[rr][c];
+                }
+        }
+#pragma unroll
+        for (int k = c + 1; k < CHOL_NB; k++)
+#pragma unroll
+            for (int rr = k; rr < CHOL_NB; rr++) a[rr][k] -= a[rr][c] * a[k][c];
+    }
+    CP(1);
+    if (!ok && lane == 0) *flag = 0;
+    CP(2);
+}
+
+// Trailing update of one 8 (rows) x 4 (columns) register tile from the current panel.  The panel is read from its
+// column-major copy Pc: a thread's 8 (4) consecutive rows of one panel column are 64 (32) contiguous bytes, so the
+// loads are 128-bit, conflict-free across a warp (consecutive lanes = consecutive column tiles) and the row operand is
+// a broadcast.  0.375 loads per FMA; the packed matrix is only touched for the final read-modify-write.
+__device__ __forceinline__ void chol_tile84(double* Lp, const double* Pc, int n, int ke, int ti8, int tj4) {
+    const int i0 = ke + 8 * ti8, j0 = ke + 4 * tj4;
+    double acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[r][q] = 0.0;
+#pragma unroll
+    for (int c = 0; c < CHOL_NB; c++) {
+        const double2* pi = reinterpret_cast<const double2*>(Pc + c * CHOL_PS + i0);
+        const double2* pj = reinterpret_cast<const double2*>(Pc + c * CHOL_PS + j0);
+        const double2 i01 = pi[0], i23 = pi[1], i45 = pi[2], i67 = pi[3];
+        const double2 j01 = pj[0], j23 = pj[1];
+        const double li[8] = {i01.x, i01.y, i23.x, i23.y, i45.x, i45.y, i67.x, i67.y};
+        const double lj[4] = {j01.x, j01.y, j23.x, j23.y};
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[r][q] += li[r] * lj[q];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int i = i0 + r;
+        if (i < n) {
+            const int ib = i * (i + 1) / 2;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (j0 + q <= i) Lp[ib + j0 + q] -= acc[r][q];
+        }
+    }
+}
+
+// Pc: CHOL_NB * CHOL_PS doubles of 16-byte aligned shared memory (current panel, column-major, rows >= n zero).
+__device__ bool cholesky_packed(double* Lp, double* Pc, int n, double* rdiag, double* linv, int* flag) {
+    __shared__ double dblk[CHOL_NB][CHOL_NB + 1], stage[CHOL_NB * CHOL_NB];
     const int tid = threadIdx.x, nt = blockDim.x;
     if (tid == 0) *flag = 1;
+    for (int c = 0; c < CHOL_NB; c++)
+        for (int i = n + tid; i < CHOL_PS; i += nt) Pc[c * CHOL_PS + i] = 0.0;
     __syncthreads();
+    if (tid < 32) chol_diag_block(Lp, Pc, 0, min(CHOL_NB, n), rdiag, dblk, flag, 0, stage);
+    __syncthreads();
+    CP_BEGIN();
     for (int kb = 0; kb < n; kb += CHOL_NB) {
-        const int w = min(CHOL_NB, n - kb), ke = kb + w;
-        if (tid < 32) {
-            const int r = tid;  // row inside the block; rows >= w behave like identity rows
-            double a[CHOL_NB];
-            const size_t rb = (size_t)(kb + r) * (kb + r + 1) / 2 + kb;
-#pragma unroll
-            for (int c = 0; c < CHOL_NB; c++) a[c] = (r < w && c <= r) ? Lp[rb + c] : (c == r ? 1.0 : 0.0);
-            bool ok = true;
-#pragma unroll
-            for (int c = 0; c < CHOL_NB; c++) {
-                const double piv = __shfl_sync(0xffffffffu, a[c], c);
-                if (!(piv > 0.0) || !isfinite(piv)) ok = false;
-                const double dcc = sqrt(piv), rc = 1.0 / dcc;
-                if (r == c) a[c] = dcc;
-                else if (r > c) a[c] *= rc;
-#pragma unroll
-                for (int k = c + 1; k < CHOL_NB; k++) {
-                    const double lkc = __shfl_sync(0xffffffffu, a[c], k);
-                    if (r >= k) a[k] -= a[c] * lkc;
-                }
-                if (r == c && c < w) rdiag[kb + c] = rc;
-            }
-            if (r < w) {
-#pragma unroll
-                for (int c = 0; c < CHOL_NB; c++)
-                    if (c <= r) {
-                        Lp[rb + c] = a[c];
-                        dblk[r][c] = a[c];
-                    }
-            }
-            if (!ok && tid == 0) *flag = 0;
-            // inverse of the diagonal block (lower triangular), one column per lane: the triangular solves then
-            // need only an 8x8 product per block instead of a dependent substitution chain
-            __syncwarp();
-            if (r < CHOL_NB) {
-                const int c = r;
-                double x[CHOL_NB];
-#pragma unroll
-                for (int rr = 0; rr < CHOL_NB; rr++) {
-                    double v = 0.0;
-                    if (rr >= c && rr < w && c < w) {
-                        v = (rr == c) ? 1.0 : 0.0;
-#pragma unroll
-                        for (int k = 0; k < CHOL_NB; k++)
-                            if (k >= c && k < rr) v -= dblk[rr][k] * x[k];
-                        v *= rdiag[kb + rr];
-                    }
-                    x[rr] = v;
-                    linv[(kb / CHOL_NB) * 64 + rr * CHOL_NB + c] = v;
-                }
-            }
-        }
-        __syncthreads();
+        const int ke = kb + CHOL_NB;  // a block with a panel below it is always full
         if (!*flag) return false;
+        if (ke >= n) break;
+        CP(3);
+        // panel: rows below the diagonal block, forward substitution against it
         for (int i = ke + tid; i < n; i += nt) {
             double x[CHOL_NB];
-            const size_t ib = (size_t)i * (i + 1) / 2 + kb;
+            const int ib = i * (i + 1) / 2 + kb;
 #pragma unroll
             for (int c = 0; c < CHOL_NB; c++) {
-                if (c < w) {
-                    double v = Lp[ib + c];
+                double v = Lp[ib + c];
 #pragma unroll
-                    for (int t = 0; t < c; t++) v -= x[t] * dblk[c][t];
-                    x[c] = v * rdiag[kb + c];
-                    Lp[ib + c] = x[c];
-                } else
-                    x[c] = 0.0;
+                for (int t = 0; t < c; t++) v -= x[t] * dblk[c][t];
+                x[c] = v * rdiag[kb + c];
+                Lp[ib + c] = x[c];
+                Pc[c * CHOL_PS + i] = x[c];
             }
         }
+        CP(4);
         __syncthreads();
-        const int m = n - ke, nt4 = (m + 3) / 4, ntiles = nt4 * (nt4 + 1) / 2;
-        for (int t = tid; t < ntiles; t += nt) {
-            int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-            while (ti * (ti + 1) / 2 > t) ti--;
-            while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
-            const int tj = t - ti * (ti + 1) / 2;
-            const int i0 = ke + 4 * ti, j0 = ke + 4 * tj;
-            size_t ibase[4], jbase[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const int ii = min(i0 + r, n - 1), jj = min(j0 + r, n - 1);
-                ibase[r] = (size_t)ii * (ii + 1) / 2;
-                jbase[r] = (size_t)jj * (jj + 1) / 2;
+        CP(5);
+        // warp 0: next diagonal block (update + factorisation); the others: every other trailing tile.  Tile row
+        // ti8 holds the column tiles tj4 = 0 .. 2 ti8 + 1 (t = ti8 (ti8 + 1) + tj4); t = 0, 1 are the diagonal block.
+        if (tid < 32) {
+            chol_diag_block(Lp, Pc, ke, min(CHOL_NB, n - ke), rdiag, dblk, flag, 1, stage);
+        } else {
+            const int m = n - ke, nr8 = (m + 7) / 8, ntiles = nr8 * (nr8 + 1);
+            for (int t = 2 + tid - 32; t < ntiles; t += nt - 32) {
+                int ti8 = (int)((sqrtf(4.f * (float)t + 1.f) - 1.f) * 0.5f);
+                while (ti8 * (ti8 + 1) > t) ti8--;
+                while ((ti8 + 1) * (ti8 + 2) <= t) ti8++;
+                chol_tile84(Lp, Pc, n, ke, ti8, t - ti8 * (ti8 + 1));
             }
-            double acc[4][4];
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-#pragma unroll
-                for (int q = 0; q < 4; q++) acc[r][q] = 0.0;
-#pragma unroll
-            for (int c = 0; c < CHOL_NB; c++) {
-                if (c < w) {
-                    double li[4], lj[4];
-#pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        li[r] = Lp[ibase[r] + kb + c];
-                        lj[r] = Lp[jbase[r] + kb + c];
-                    }
-#pragma unroll
-                    for (int r = 0; r < 4; r++)
-#pragma unroll
-                        for (int q = 0; q < 4; q++) acc[r][q] += li[r] * lj[q];
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (i0 + r < n && j0 + q <= i0 + r) Lp[ibase[r] + j0 + q] -= acc[r][q];
         }
+        CP(6);
         __syncthreads();
+        CP(7);
     }
+    // inverses of the diagonal blocks (lower triangular), one block per warp, one column per lane: the triangular
+    // solves then need an 8x8 product per block instead of a dependent substitution chain
+    const int wid = tid >> 5, nw = nt >> 5, lane = tid & 31;
+    for (int blk = wid; blk * CHOL_NB < n; blk += nw) {
+        const int kb = blk * CHOL_NB, w = min(CHOL_NB, n - kb);
+        if (lane < CHOL_NB) {
+            const int c = lane;
+            double x[CHOL_NB];
+#pragma unroll
+            for (int rr = 0; rr < CHOL_NB; rr++) {
+                double v = 0.0;
+                if (rr >= c && rr < w && c < w) {
+                    v = (rr == c) ? 1.0 : 0.0;
+                    const size_t rb = (size_t)(kb + rr) * (kb + rr + 1) / 2 + kb;
+#pragma unroll
+                    for (int k = 0; k < CHOL_NB; k++)
+                        if (k >= c && k < rr) v -= Lp[rb + k] * x[k];
+                    v *= rdiag[kb + rr];
+                }
+                x[rr] = v;
+                linv[blk * 64 + rr * CHOL_NB + c] = v;
+            }
+        }
+    }
+    __syncthreads();
     return true;
 }
 
@@ -830,7 +900,7 @@ __device__ void reduce_single_cta(const BaProblem& p, const BaAccum& a, double m
 
 #define STEP_MAXD 352
 __global__ void __launch_bounds__(512) ba_step_kernel(BaProblem p, int use_smem_chol) {
-    extern __shared__ double chol_smem[];
+    extern __shared__ __align__(16) double chol_smem[];  // panel copy (CHOL_NB * CHOL_PS), then the packed factor
     __shared__ double red[32];
     __shared__ double rdiag[STEP_MAXD], ysm[STEP_MAXD], linv[(STEP_MAXD / CHOL_NB) * 64];
     __shared__ int flag;
@@ -849,7 +919,7 @@ __global__ void __launch_bounds__(512) ba_step_kernel(BaProblem p, int use_smem_
     double* u = p.work;              // N  Cauchy direction (unscaled variables)
     double* y = p.work + N;          // N  Gauss-Newton solution
     double* delta = p.work + 2 * N;  // N  step in the original variables
-    double* Lp = use_smem_chol ? chol_smem : p.work + 4 * (size_t)N;  // packed factor
+    double* Lp = use_smem_chol ? chol_smem + CHOL_NB * CHOL_PS : p.work + 4 * (size_t)N;  // packed factor
     const int first = st->first;
     double mu = st->mu;
     bool linear_ok = true;
@@ -880,7 +950,7 @@ __global__ void __launch_bounds__(512) ba_step_kernel(BaProblem p, int use_smem_
             }
             __syncthreads();
             STAMP(2);
-            const bool ok_ = cholesky_packed(Lp, D, rdiag, linv, &flag);
+            const bool ok_ = cholesky_packed(Lp, chol_smem, D, rdiag, linv, &flag);
             STAMP(3);
             if (ok_) {
                 linear_ok = true;
@@ -1167,115 +1237,24 @@ __global__ void __launch_bounds__(128) marg_build_kernel(BaProblem p, MargPlan m
     }
 }
 
-namespace {
+constexpr int MARG_THREADS = 512;
 
-// Cyclic Jacobi with round-robin parallel ordering on a symmetric matrix in shared memory.
-// A is ld x ld with ld even and >= n, rows/columns >= n zero (a zero row never rotates).  On exit the
-// eigenvalues are on the diagonal and V (ld x ld) holds the eigenvectors in its ROWS (V[k*ld + i] = component i of
-// eigenvector k: the rotation then touches two contiguous rows, free of shared-memory bank conflicts).  Each round applies
-// ld/2 disjoint rotations: one phase computes (c, s) per pair, one phase updates every 2x2 block
-// G_k^T A_(k,k') G_k' and V G_k, i.e. two barriers per round.  A pair is rotated when
-// |a_pq| > 1e-15 sqrt|a_pp a_qq| (relative criterion: resolves the small eigenvalues of these badly scaled
-// matrices); sweeps stop when every rotation of a sweep was the identity in floating point (c == 1).
-__device__ int jacobi_eigen(double* A, double* V, int ld, double* cs, int* pq, int* flags) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-    const int half = ld / 2;
-    for (int i = wid; i < ld; i += nw)
-        for (int j = lane; j < ld; j += 32) V[i * ld + j] = (i == j) ? 1.0 : 0.0;
-    if (tid < 2) flags[tid] = 0;
-    __syncthreads();
-    for (int sweep = 0; sweep < 60; sweep++) {
-        int* flag = &flags[sweep & 1];
-        for (int round = 0; round < ld - 1; round++) {
-            if (tid < half) {
-                int a, b;
-                if (tid == 0) {
-                    a = ld - 1;
-                    b = round;
-                } else {
-                    a = round + tid;
-                    if (a >= ld - 1) a -= ld - 1;
-                    b = round - tid;
-                    if (b < 0) b += ld - 1;
-                }
-                const int pp = min(a, b), qq = max(a, b);
-                double c = 1.0, s = 0.0;
-                const double apq = A[pp * ld + qq];
-                if (apq != 0.0) {
-                    const double app = A[pp * ld + pp], aqq = A[qq * ld + qq];
-                    if (fabs(apq) > 1e-300 + 1e-15 * sqrt(fabs(app * aqq))) {
-                        const double theta = (aqq - app) / (2 * apq);
-                        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
-                        c = rsqrt(t * t + 1);
-                        s = t * c;
-                        if (c != 1.0) *flag = 1;
-                    }
-                }
-                pq[2 * tid] = pp;
-                pq[2 * tid + 1] = qq;
-                cs[2 * tid] = c;
-                cs[2 * tid + 1] = s;
-            }
-            __syncthreads();
-            // warp tasks: (pair k, 32-wide chunk of pairs k2) for the A blocks, (pair k, 32 rows) for V
-            const int chA = (half + 31) >> 5, chV = (ld + 31) >> 5;
-            const int nA = half * chA, nV = half * chV;
-            for (int task = wid; task < nA + nV; task += nw) {
-                if (task < nA) {
-                    const int k = task / chA, k2 = (task - k * chA) * 32 + lane;
-                    if (k2 >= half) continue;
-                    const double c1 = cs[2 * k], s1 = cs[2 * k + 1];
-                    const double c2 = cs[2 * k2], s2 = cs[2 * k2 + 1];
-                    if (s1 == 0.0 && s2 == 0.0) continue;
-                    const int p0 = pq[2 * k], q0 = pq[2 * k + 1];
-                    const int p2 = pq[2 * k2], q2 = pq[2 * k2 + 1];
-                    const double a00 = A[p0 * ld + p2], a01 = A[p0 * ld + q2], a10 = A[q0 * ld + p2], a11 = A[q0 * ld + q2];
-                    const double t00 = c2 * a00 - s2 * a01, t01 = s2 * a00 + c2 * a01;
-                    const double t10 = c2 * a10 - s2 * a11, t11 = s2 * a10 + c2 * a11;
-                    A[p0 * ld + p2] = c1 * t00 - s1 * t10;
-                    A[q0 * ld + p2] = s1 * t00 + c1 * t10;
-                    A[p0 * ld + q2] = c1 * t01 - s1 * t11;
-                    A[q0 * ld + q2] = s1 * t01 + c1 * t11;
-                } else {
-                    const int tv_ = task - nA;
-                    const int k = tv_ / chV, i = (tv_ - k * chV) * 32 + lane;
-                    const double c1 = cs[2 * k], s1 = cs[2 * k + 1];
-                    if (i >= ld || s1 == 0.0) continue;
-                    const int p0 = pq[2 * k], q0 = pq[2 * k + 1];
-                    const double vip = V[p0 * ld + i], viq = V[q0 * ld + i];
-                    V[p0 * ld + i] = c1 * vip - s1 * viq;
-                    V[q0 * ld + i] = s1 * vip + c1 * viq;
-                }
-            }
-            __syncthreads();
-        }
-        const int any = *flag;
-        if (tid == 0) flags[(sweep + 1) & 1] = 0;
-        __syncthreads();
-        if (!any) return sweep + 1;
-    }
-    return 60;
-}
-
-}  // namespace
-
-// Single CTA.  Dynamic shared memory: Wk (q x q), Ev and Vv (ldx x ldx, ldx = even(max(md, n))), bw (q), tv (ldx).
-__global__ void __launch_bounds__(1024) marg_solve_kernel(MargPlan mp, double eps) {
+// Single CTA.  Dynamic shared memory: Wk (q x q), Ev (scratch), Vv ((ldx+1)^2: matrix in / eigenvectors out), bw (q), tv.
+// Both eigen-decompositions (the dense marginalised block T and the new prior A') use the tridiagonal-QL solver of
+// sym_eig.h: eigenvector k is the COLUMN k of Vv (odd leading dimension: conflict-free row walks).
+__global__ void __launch_bounds__(MARG_THREADS) marg_solve_kernel(MargPlan mp, double eps) {
     extern __shared__ double sm[];
     __shared__ double red[32];
-    __shared__ double cs[2 * 96];
-    __shared__ int pq[2 * 96];
-    __shared__ int jflags[2];
+    __shared__ double dval[96], ework[96], cs[2 * 96], scal[16];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int md = mp.m_dense, nl = mp.n_lm, n = mp.n, P = mp.P;
     const int q = md + n;
     const int ldm = md + (md & 1), ldn = n + (n & 1), ldx = max(ldm, ldn);
-    const int esz = max(max(ldx * ldx, n * (ldm + md)), 16 * q);
+    const int esz = max(max((ldx + 1) * (ldx + 1), n * (ldm + md)), 16 * q);
     double* Wk = sm;                  // q*q
     double* Ev = Wk + q * q;          // esz
-    double* Vv = Ev + esz;            // ldx*ldx
-    double* bw = Vv + ldx * ldx;      // q
+    double* Vv = Ev + esz;            // (ldx+1)^2
+    double* bw = Vv + (ldx + 1) * (ldx + 1);  // q
     double* tv = bw + q;              // ldx
     auto symA = [&](int a, int b) { return a <= b ? mp.Am[(size_t)a * P + b] : mp.Am[(size_t)b * P + a]; };
     auto full = [&](int a) { return a < md ? a : a + nl; };  // index in Am of reduced index a
@@ -1328,33 +1307,31 @@ __global__ void __launch_bounds__(1024) marg_solve_kernel(MargPlan mp, double ep
     }
     __syncthreads();
     // 2. pseudo-inverse of the dense marginalised block T (md x md) by eigen-decomposition
-    for (int idx = tid; idx < ldm * ldm; idx += nt) {
-        const int i = idx / ldm, j = idx % ldm;
-        Ev[idx] = (i < md && j < md) ? Wk[i * q + j] : 0.0;
+    const int ldvm = md | 1, ldvn = n | 1;
+    for (int idx = tid; idx < md * md; idx += nt) {
+        const int i = idx / md, j = idx - i * md;
+        Vv[i * ldvm + j] = Wk[i * q + j];
     }
     __syncthreads();
     MSTAMP(0);
-    const int sweeps_m = jacobi_eigen(Ev, Vv, ldm, cs, pq, jflags);
+    sym_eig(CtaCtx(), Vv, md, ldvm, dval, ework, cs, scal);
     MSTAMP(1);
-    for (int k = tid; k < ldm; k += nt) {
-        const double w = Ev[k * ldm + k];
-        tv[k] = (k < md && w > eps) ? 1.0 / w : 0.0;
-    }
+    for (int k = tid; k < md; k += nt) tv[k] = dval[k] > eps ? 1.0 / dval[k] : 0.0;
     __syncthreads();
     // 3. X = Wrm Tinv (n x md) computed directly from the eigen-factors: X = (Wrm V) diag(tv) V^T
-    //    Y = Wrm V  -> stored in Ev as n x ldm (Ev is free: eigenvalues already consumed into tv)
-    for (int idx = tid; idx < n * ldm; idx += nt) {
-        const int i = idx / ldm, k = idx % ldm;
+    //    Y = Wrm V diag(tv) -> Ev as n x md
+    for (int idx = tid; idx < n * md; idx += nt) {
+        const int i = idx / md, k = idx - i * md;
         double s = 0;
-        for (int j = 0; j < md; j++) s += Wk[(md + i) * q + j] * Vv[k * ldm + j];
+        for (int j = 0; j < md; j++) s += Wk[(md + i) * q + j] * Vv[j * ldvm + k];
         Ev[idx] = s * tv[k];
     }
     __syncthreads();
-    double* X = Ev + (size_t)n * ldm;  // n x md (Ev holds max(ldx^2, n (ldm + md)) doubles)
+    double* X = Ev + (size_t)n * md;  // n x md
     for (int idx = tid; idx < n * md; idx += nt) {
-        const int i = idx / md, j = idx % md;
+        const int i = idx / md, j = idx - i * md;
         double s = 0;
-        for (int k = 0; k < ldm; k++) s += Ev[i * ldm + k] * Vv[k * ldm + j];
+        for (int k = 0; k < md; k++) s += Ev[i * md + k] * Vv[j * ldvm + k];
         X[idx] = s;
     }
     __syncthreads();
@@ -1376,39 +1353,44 @@ __global__ void __launch_bounds__(1024) marg_solve_kernel(MargPlan mp, double ep
     if (mp.graw)
         for (int i = tid; i < n; i += nt) mp.graw[i] = mp.gout[i];
     // 4. eigen-decomposition of A' with the eps floor: A+ = V S+ V^T, g0 = V 1+ V^T b', c0 = b'^T V S+^-1 V^T b'
-    for (int idx = tid; idx < ldn * ldn; idx += nt) {
-        const int i = idx / ldn, j = idx % ldn;
-        Ev[idx] = (i < n && j < n) ? 0.5 * (Ap[i * n + j] + Ap[j * n + i]) : 0.0;
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += nt) {
+        const int i = idx / n, j = idx - i * n;
+        Vv[i * ldvn + j] = 0.5 * (Ap[i * n + j] + Ap[j * n + i]);
     }
     __syncthreads();
     MSTAMP(2);
-    const int sweeps_n = jacobi_eigen(Ev, Vv, ldn, cs, pq, jflags);
+    sym_eig(CtaCtx(), Vv, n, ldvn, dval, ework, cs, scal);
     MSTAMP(3);
-    for (int k = tid; k < ldn; k += nt) {
+    for (int k = tid; k < n; k += nt) {
         double s = 0;
-        for (int i = 0; i < n; i++) s += Vv[k * ldn + i] * mp.gout[i];
+        for (int i = 0; i < n; i++) s += Vv[i * ldvn + k] * mp.gout[i];
         tv[k] = s;  // V_k^T b'
     }
     __syncthreads();
     double cpart = 0;
-    for (int k = tid; k < ldn; k += nt) {
-        const double w = Ev[k * ldn + k];
+    for (int k = tid; k < n; k += nt) {
+        const double w = dval[k];
         if (w > eps) cpart += tv[k] * tv[k] / w;
     }
     const double c0 = block_sum(cpart, red);
+    // scale the kept eigenvectors once (Ev <- V diag(w+)), then A+ = Ev V^T
     for (int idx = tid; idx < n * n; idx += nt) {
-        const int i = idx / n, j = idx % n;
+        const int i = idx / n, k = idx - i * n;
+        const double w = dval[k];
+        Ev[i * ldvn + k] = w > eps ? Vv[i * ldvn + k] * w : 0.0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += nt) {
+        const int i = idx / n, j = idx - i * n;
         double s = 0;
-        for (int k = 0; k < ldn; k++) {
-            const double w = Ev[k * ldn + k];
-            if (w > eps) s += Vv[k * ldn + i] * w * Vv[k * ldn + j];
-        }
+        for (int k = 0; k < n; k++) s += Ev[i * ldvn + k] * Vv[j * ldvn + k];
         Ap[idx] = s;
     }
     for (int i = tid; i < n; i += nt) {
         double s = 0;
-        for (int k = 0; k < ldn; k++)
-            if (Ev[k * ldn + k] > eps) s += Vv[k * ldn + i] * tv[k];
+        for (int k = 0; k < n; k++)
+            if (dval[k] > eps) s += Vv[i * ldvn + k] * tv[k];
         bw[i] = s;
     }
     __syncthreads();
@@ -1416,8 +1398,8 @@ __global__ void __launch_bounds__(1024) marg_solve_kernel(MargPlan mp, double ep
     if (tid == 0) {
         mp.cout[0] = c0;
         if (mp.graw) {  // diagnostics behind the n used entries
-            mp.graw[n] = sweeps_m;
-            mp.graw[n + 1] = sweeps_n;
+            mp.graw[n] = scal[4];      // A' decomposition: tridiagonalisation cycles
+            mp.graw[n + 1] = scal[5];  // QL cycles
             MSTAMP(4);
             for (int k = 0; k < 5; k++) mp.graw[n + 2 + k] = (double)mclk[k];
         }
@@ -1427,8 +1409,8 @@ __global__ void __launch_bounds__(1024) marg_solve_kernel(MargPlan mp, double ep
 size_t marg_solve_smem_bytes(int m_dense, int n) {
     const int q = m_dense + n;
     const int ldm = m_dense + (m_dense & 1), ldn = n + (n & 1), ldx = ldm > ldn ? ldm : ldn;
-    const size_t esz = std::max(std::max((size_t)ldx * ldx, (size_t)n * (ldm + m_dense)), (size_t)16 * q);
-    return sizeof(double) * ((size_t)q * q + esz + (size_t)ldx * ldx + q + std::max(ldx, 32));
+    const size_t esz = std::max(std::max((size_t)(ldx + 1) * (ldx + 1), (size_t)n * (ldm + m_dense)), (size_t)16 * q);
+    return sizeof(double) * ((size_t)q * q + esz + (size_t)(ldx + 1) * (ldx + 1) + q + std::max(ldx, 32));
 }
 
 }  // namespace vb
@@ -1468,7 +1450,8 @@ void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int
     const int lin_grid = ba_linearize_grid(d);
     const int zero_grid = 64;
     const int tiles = (d.D + ST - 1) / ST;
-    const size_t chol_bytes = sizeof(double) * (size_t)d.D * (d.D + 1) / 2;
+    const size_t panel_bytes = sizeof(double) * CHOL_NB * CHOL_PS;
+    const size_t chol_bytes = sizeof(double) * (size_t)d.D * (d.D + 1) / 2 + panel_bytes;
     static int smem_limit = -1, smem_static = 0, smem_configured = 0;
     if (smem_limit < 0) {
         int dev = 0;
@@ -1479,9 +1462,10 @@ void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int
         smem_static = (int)fa.sharedSizeBytes;
     }
     const int use_smem = chol_bytes + (size_t)smem_static + 256 <= (size_t)smem_limit ? 1 : 0;
-    if (use_smem && (int)chol_bytes > smem_configured) {
-        cudaFuncSetAttribute(ba_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_bytes);
-        smem_configured = (int)chol_bytes;
+    const size_t step_dyn = use_smem ? chol_bytes : panel_bytes;
+    if ((int)step_dyn > smem_configured) {
+        cudaFuncSetAttribute(ba_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dyn);
+        smem_configured = (int)step_dyn;
     }
     int n = 0;
     prof->begin(s);
@@ -1496,7 +1480,7 @@ void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int
         ba_schur_kernel<<<dim3(tiles, tiles), dim3(ST, ST), 0, s>>>(p);
         prof->end(1, s);
         prof->begin(s);
-        ba_step_kernel<<<1, 512, use_smem ? chol_bytes : 0, s>>>(p, use_smem);
+        ba_step_kernel<<<1, 512, step_dyn, s>>>(p, use_smem);
         prof->end(2, s);
         prof->begin(s);
         ba_zero_kernel<<<zero_grid, 256, 0, s>>>(p, 0);
@@ -1525,7 +1509,7 @@ void launch_marginalize(const BaProblem& p, const MargPlan& mp, cudaStream_t s, 
         configured = smem;
     }
     prof->begin(s);
-    marg_solve_kernel<<<1, 1024, smem, s>>>(mp, 1e-8);
+    marg_solve_kernel<<<1, MARG_THREADS, smem, s>>>(mp, 1e-8);
     prof->end(5, s);
     if (launches) *launches += 2;
 }

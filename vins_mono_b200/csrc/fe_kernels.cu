@@ -154,15 +154,21 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(const uint8_t* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pyramidal Lucas-Kanade, one warp per point, all levels inside one launch.
-// Mirrors OpenCV's LKTrackerInvoker with exact (int64) window sums.  Per level the warp stages the
+// Pyramidal Lucas-Kanade, one 128-thread CTA per point, all levels inside one launch.
+// Mirrors OpenCV's LKTrackerInvoker with exact (int64) window sums.  Per level the CTA stages the
 // 24x24 previous-image neighbourhood in shared memory, derives the Scharr gradient there (zero outside
-// the image, reflect-101 inside), builds the 21x21 int16 patch + gradient patch, then iterates on the
-// next image re-staging a 22x22 tile per iteration.  Reductions are warp shuffles on 64-bit integers.
+// the image, reflect-101 inside), builds the 21x21 int16 patch + gradient patch, then iterates on a cached
+// 40x40 region of the next image.  The 441-pixel window is spread over 4 warps (the track count of a frame, 150,
+// matches the SM count, so a point per CTA puts one warp on each scheduler of an SM; a warp per point left three
+// of the four schedulers idle and the kernel bound by one warp's issue latency).  Reductions are warp shuffles
+// on 64-bit integers + a 4-entry shared-memory exchange; every thread then evaluates the same scalar update,
+// so control flow stays CTA-uniform.
+#define LK_WARPS 4
 #define LK_RS 40                 // next-image search region cached per level: 22x22 window + 9 px margin each side
 struct LkSmem {
     uint8_t tile[24 * 24];       // previous-level neighbourhood
     uint8_t region[LK_RS * LK_RS];  // next-level search region (reflect-101 padded coordinates)
+    long long red[2][LK_WARPS][3];  // cross-warp exchange, double buffered (one barrier per reduction)
     int16_t deriv[22 * 22 * 2];  // Scharr dx,dy at the 22x22 bilinear source positions
     int16_t iwin[441];
     int16_t dwin[441 * 2];
@@ -174,19 +180,19 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
     return v;
 }
 
-#define LK_WARPS 4
-
 __global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(PyramidView prev, PyramidView next,
                                                                  const float* __restrict__ prev_pts, int n,
                                                                  int max_iter, double eps2, float min_eig_thr,
                                                                  int img_rows, int img_cols,
                                                                  float* __restrict__ next_pts,
                                                                  uint8_t* __restrict__ status) {
-    __shared__ LkSmem sm_all[LK_WARPS];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int p = blockIdx.x * LK_WARPS + wid;
+    __shared__ LkSmem sm;
+    constexpr int NT = 32 * LK_WARPS;
+    const int lane = threadIdx.x;  // index within the CTA that owns point p
+    const int wl = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int p = blockIdx.x;
     if (p >= n) return;
-    LkSmem& sm = sm_all[wid];
+    int rpar = 0;
     const int W = 21;
     const float half = 10.f;
     const float FLT_SCALE = 1.f / (1 << 20);
@@ -222,14 +228,14 @@ __global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(PyramidView pre
         int iw10 = __float2int_rn(__fmul_rn(__fmul_rn(__fsub_rn(1.f, a), b), 16384.f));
         int iw11 = 16384 - iw00 - iw01 - iw10;
         // stage the 24x24 neighbourhood, origin (ipy-1, ipx-1), reflect-101 padding
-        __syncwarp();
-        for (int i = lane; i < 24 * 24; i += 32) {
+        __syncthreads();
+        for (int i = lane; i < 24 * 24; i += NT) {
             const int ty = i / 24, tx = i - ty * 24;
             sm.tile[i] = I[(size_t)reflect101(ipy - 1 + ty, rows) * pitch + reflect101(ipx - 1 + tx, cols)];
         }
-        __syncwarp();
+        __syncthreads();
         // Scharr gradient at the 22x22 positions (calcSharrDeriv); zero outside the image
-        for (int i = lane; i < 22 * 22; i += 32) {
+        for (int i = lane; i < 22 * 22; i += NT) {
             const int dyi = i / 22, dxi = i - dyi * 22;
             const int gy = ipy + dyi, gx = ipx + dxi;
             int ddx = 0, ddy = 0;
@@ -244,9 +250,9 @@ __global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(PyramidView pre
             sm.deriv[2 * i] = (int16_t)ddx;
             sm.deriv[2 * i + 1] = (int16_t)ddy;
         }
-        __syncwarp();
+        __syncthreads();
         long long a11 = 0, a12 = 0, a22 = 0;
-        for (int i = lane; i < 441; i += 32) {
+        for (int i = lane; i < 441; i += NT) {
             const int y = i / 21, x = i - y * 21;
             const uint8_t* t = &sm.tile[(y + 1) * 24 + (x + 1)];
             const int ival = (t[0] * iw00 + t[1] * iw01 + t[24] * iw10 + t[25] * iw11 + (1 << 8)) >> 9;
@@ -263,6 +269,20 @@ __global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(PyramidView pre
         a11 = warp_sum_ll(a11);
         a12 = warp_sum_ll(a12);
         a22 = warp_sum_ll(a22);
+        if (wl == 0) {
+            sm.red[rpar][wid][0] = a11;
+            sm.red[rpar][wid][1] = a12;
+            sm.red[rpar][wid][2] = a22;
+        }
+        __syncthreads();
+        a11 = a12 = a22 = 0;
+#pragma unroll
+        for (int w = 0; w < LK_WARPS; w++) {
+            a11 += sm.red[rpar][w][0];
+            a12 += sm.red[rpar][w][1];
+            a22 += sm.red[rpar][w][2];
+        }
+        rpar ^= 1;
         const float A11 = __fmul_rn(__ll2float_rn(a11), FLT_SCALE);
         const float A12 = __fmul_rn(__ll2float_rn(a12), FLT_SCALE);
         const float A22 = __fmul_rn(__ll2float_rn(a22), FLT_SCALE);
@@ -297,17 +317,17 @@ __global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(PyramidView pre
             if (!have_region || inx < rx0 || inx + 22 > rx0 + LK_RS || iny < ry0 || iny + 22 > ry0 + LK_RS) {
                 ry0 = iny - (LK_RS - 22) / 2;
                 rx0 = inx - (LK_RS - 22) / 2;
-                __syncwarp();
-                for (int i = lane; i < LK_RS * LK_RS; i += 32) {
+                __syncthreads();
+                for (int i = lane; i < LK_RS * LK_RS; i += NT) {
                     const int ty = i / LK_RS, tx = i - ty * LK_RS;
                     sm.region[i] = J[(size_t)reflect101(ry0 + ty, rows) * pitch + reflect101(rx0 + tx, cols)];
                 }
-                __syncwarp();
+                __syncthreads();
                 have_region = true;
             }
             const uint8_t* rbase = &sm.region[(iny - ry0) * LK_RS + (inx - rx0)];
             long long b1 = 0, b2 = 0;
-            for (int i = lane; i < 441; i += 32) {
+            for (int i = lane; i < 441; i += NT) {
                 const int y = i / 21, x = i - y * 21;
                 const uint8_t* t = rbase + y * LK_RS + x;
                 const int diff = ((t[0] * iw00 + t[1] * iw01 + t[LK_RS] * iw10 + t[LK_RS + 1] * iw11 + (1 << 8)) >> 9) - sm.iwin[i];
@@ -316,6 +336,18 @@ __global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(PyramidView pre
             }
             b1 = warp_sum_ll(b1);
             b2 = warp_sum_ll(b2);
+            if (wl == 0) {
+                sm.red[rpar][wid][0] = b1;
+                sm.red[rpar][wid][1] = b2;
+            }
+            __syncthreads();
+            b1 = b2 = 0;
+#pragma unroll
+            for (int w = 0; w < LK_WARPS; w++) {
+                b1 += sm.red[rpar][w][0];
+                b2 += sm.red[rpar][w][1];
+            }
+            rpar ^= 1;
             const float fb1 = __fmul_rn(__ll2float_rn(b1), FLT_SCALE), fb2 = __fmul_rn(__ll2float_rn(b2), FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb2), __fmul_rn(A22, fb1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb1), __fmul_rn(A11, fb2)), D);
@@ -616,7 +648,7 @@ void launch_lk(const PyramidView& prev, const PyramidView& next, const float* pr
                uint8_t* status, cudaStream_t s) {
     if (n <= 0) return;
     const double eps = 0.01;
-    lk_track_kernel<<<(n + LK_WARPS - 1) / LK_WARPS, 32 * LK_WARPS, 0, s>>>(prev, next, prev_pts, n, 30, eps * eps, 1e-4f,
+    lk_track_kernel<<<n, 32 * LK_WARPS, 0, s>>>(prev, next, prev_pts, n, 30, eps * eps, 1e-4f,
                                                                           prev.rows[0], prev.cols[0], next_pts, status);
 }
 
