@@ -29,6 +29,8 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 from harness import synth, pipeline  # noqa: E402
 
 METRIC = "frames/sec (tracker+BA) at 752x480, 10-KF window, 150 feats; ATE vs ref"
+WORKLOAD = ("configs[1]: single 752x480 synthetic sequence per GPU, 10-keyframe window, 150 features, 200 Hz IMU, "
+            "fp64 Jacobians")
 INIT_PUBS = 12           # published frames consumed before the window is full and seeded (estimator goes NON_LINEAR)
 ALGO_BYTES_IMAGE = 1_319_760   # compulsory front-end traffic per input image
 ALGO_BYTES_SOLVE = 233_000     # back-end inputs+outputs per solve at C1
@@ -102,9 +104,47 @@ def make_gpu_pair(device):
     return trk, est
 
 
+class TwoStage:
+    """Runs a tracker stage (producer thread) and an estimator stage (caller's thread) the way the reference runs its two
+    nodes: concurrently, coupled by a bounded queue of feature messages.  The producer stops after `n_before` messages
+    until `go()` is called, so that a timed region contains exactly the frames produced after it (pipeline fill and
+    drain fall inside the region)."""
+
+    def __init__(self, produce, n_before, n_total, depth=2):
+        import queue
+        self.q, self.gate, self.err = queue.Queue(maxsize=depth), threading.Event(), None
+        self.produce, self.n_before, self.n_total = produce, n_before, n_total
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        try:
+            for k in range(self.n_total):
+                if k == self.n_before:
+                    self.gate.wait()
+                msg = self.produce()
+                self.q.put(msg)
+                if msg is None:
+                    return
+            self.q.put(None)
+        except BaseException as e:  # surfaced by get()
+            self.err = e
+            self.q.put(None)
+
+    def go(self):
+        self.gate.set()
+
+    def get(self):
+        msg = self.q.get()
+        if self.err:
+            raise self.err
+        return msg
+
+
 def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images, profile=False, flush=None, sync_cb=None):
     """One pass over the sequence.  The K timed steps form ONE region bracketed by device synchronisation and a pair of
-    CUDA events (ms per step = region / K); sync_cb, if given, is the cross-rank barrier placed inside the bracket."""
+    CUDA events (ms per step = region / K); sync_cb, if given, is the cross-rank barrier placed inside the bracket.
+    Tracker and estimator handles are driven from two host threads (TwoStage); with profile=True they run serially."""
     import torch
     trk, est = make_gpu_pair(device)
     if profile:
@@ -120,20 +160,46 @@ def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images
         base = d_imgs.data_ptr()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches, h2d, d2h, traj_t, traj_p = 0, 0.0, 0.0, [], []
-    pubs, i, first_msg = 0, 0, True
     n_img = len(ts)
-    n_timed, started = 0, False
+    cursor = [0]
 
     def one_image(k):
         if host_images:
             return trk.node_image(imgs[k], float(ts[k]))[0]
         return trk.node_image_device(base + k * frame_bytes, imgs.shape[2], float(ts[k]))
 
-    while pubs < n_pub and i < n_img:
+    def produce():
+        """Images until one publishes -> (stamp, ids, observations, launches, h2d, d2h) or None at end of data."""
+        torch.cuda.set_device(device)
+        n_l, n_h, n_d, r = 0, 0.0, 0.0, 0
+        while r != 2 and cursor[0] < n_img:
+            r = one_image(cursor[0])
+            cursor[0] += 1
+            if r:
+                n_l += trk.timing()[1]
+                a, b = trk.traffic()
+                n_h += a
+                n_d += b
+        if r != 2:
+            return None
+        ids, d = pipeline.oracle_feature_message(trk.result())
+        return float(ts[cursor[0] - 1]), ids, d, n_l, n_h, n_d
+
+    class Serial:
+        def go(self):
+            pass
+
+        def get(self):
+            return produce()
+
+    stage = Serial() if profile else TwoStage(produce, n_init + warmup, n_pub)
+    pubs, first_msg, n_timed, started = 0, True, 0, False
+    while pubs < n_pub:
         timed = pubs >= n_init + warmup
         if timed and not started:
-            # start of the timed region: drain the device, evict L2 once (every timed step reads images that were
-            # uploaded long ago and never touched since, i.e. cold in L2; the rest of a step's data is produced inside it)
+            # start of the timed region: both stages idle, device drained, L2 evicted once (every timed step reads images
+            # that were uploaded long ago and never touched since, i.e. cold in L2; the rest of a step's data is
+            # produced inside it)
             if flush is not None:
                 flush.fill_(1.0)
             torch.cuda.synchronize(device)
@@ -141,20 +207,11 @@ def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images
                 sync_cb()
             ev0.record()
             started = True
-        step_launch, step_h2d, step_d2h = 0, 0.0, 0.0
-        r = 0
-        while r != 2 and i < n_img:  # images until one publishes
-            r = one_image(i)
-            i += 1
-            if r:
-                step_launch += trk.timing()[1]
-                a, b = trk.traffic()
-                step_h2d += a
-                step_d2h += b
-        if r != 2:
+            stage.go()
+        msg = stage.get()
+        if msg is None:
             break
-        stamp = float(ts[i - 1])
-        ids, d = pipeline.oracle_feature_message(trk.result())
+        stamp, ids, d, step_launch, step_h2d, step_d2h = msg
         if first_msg:  # estimator_node.cpp:167-172 drops the first feature message
             first_msg = False
         else:
@@ -177,6 +234,7 @@ def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images
     torch.cuda.synchronize(device)  # includes the last frame's (asynchronous) marginalisation
     ev1.record()
     ev1.synchronize()
+    stage.go()
     times = [ev0.elapsed_time(ev1) / max(n_timed, 1)] * n_timed if started else []
     out = dict(times=times, launches=launches, h2d=h2d, d2h=d2h, traj_t=traj_t, traj_p=traj_p, info=est.info())
     if profile:
@@ -187,40 +245,53 @@ def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images
 
 
 def run_reference_pass(seq, ts, imgs, imu, n_init, warmup, steps):
-    """The CPU port of the reference path (oracle tracker + estimator twins), single thread like the reference nodes'
-    hot loops (tracker node single-threaded; Ceres num_threads = 1)."""
+    """The CPU port of the reference path (oracle tracker + estimator twins) on two host threads, tracker and estimator
+    coupled by a queue like the reference's two nodes (each hot loop single-threaded: the tracker node is, and Ceres
+    runs with num_threads = 1)."""
     import orc
     trk = orc.OracleTracker(synth.tracker_config_dict())
     est = orc.OracleEstimator(orc.be_config())
     feeder = pipeline.ImuFeeder(*imu)
     est.set_seed(pipeline.gt_seed_rows(seq, ts), seq.ba, seq.bg)
     n_pub = n_init + warmup + steps
-    times, traj_t, traj_p = [], [], []
-    pubs, i, first_msg = 0, 0, True
-    while pubs < n_pub and i < len(ts):
-        timed = pubs >= n_init + warmup
-        t0 = time.perf_counter()
+    traj_t, traj_p = [], []
+    cursor = [0]
+
+    def produce():
         r = 0
-        while r != 2 and i < len(ts):
-            r, _ = trk.node_image(imgs[i], float(ts[i]))
-            i += 1
+        while r != 2 and cursor[0] < len(ts):
+            r, _ = trk.node_image(imgs[cursor[0]], float(ts[cursor[0]]))
+            cursor[0] += 1
         if r != 2:
-            break
-        stamp = float(ts[i - 1])
+            return None
         ids, d = pipeline.oracle_feature_message(trk.result())
+        return float(ts[cursor[0] - 1]), ids, d
+
+    stage = TwoStage(produce, n_init + warmup, n_pub)
+    pubs, first_msg, n_timed, t0 = 0, True, 0, None
+    while pubs < n_pub:
+        if pubs == n_init + warmup:
+            t0 = time.perf_counter()
+            stage.go()
+        msg = stage.get()
+        if msg is None:
+            break
+        stamp, ids, d = msg
         if first_msg:
             first_msg = False
         else:
             feeder.feed(est, stamp)
             est.processImage(ids, d, stamp)
-        if timed:
-            times.append((time.perf_counter() - t0) * 1e3)
+        if t0 is not None:
+            n_timed += 1
         if est.info()["solver_flag"] == 1:
             st, _ = est.states()
             traj_t.append(stamp)
             traj_p.append(st[-1, 0:3].copy())
         pubs += 1
-    return dict(times=times, traj_t=traj_t, traj_p=traj_p)
+    total_ms = (time.perf_counter() - t0) * 1e3 if t0 is not None else 0.0
+    stage.go()
+    return dict(times=[total_ms / max(n_timed, 1)] * n_timed, traj_t=traj_t, traj_p=traj_p)
 
 
 def cpu_model():
@@ -257,8 +328,9 @@ def main():
             "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": len(r["times"]),
             "warmup": warmup, "ms_per_step": 1e3 * total_s / len(r["times"]), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[0]: single 752x480 synthetic sequence, 10-keyframe window, 150 features, 200 Hz IMU, CPU, 1 stream"},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port", "sample": sample, "cpu": cpu_model(),
+            "config": {"workload": WORKLOAD, "sequences_per_gpu": 1,
+                       "arm": "configs[0]: the same sequence on the host CPU, 1 stream (tracker thread + estimator thread)"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 2, "kind": "port", "sample": sample, "cpu": cpu_model(),
                              "note": "CPU restatement of the reference path (oracle/), not Ceres/OpenCV; no wall-clock solver cap"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "ate_rmse_m": pipeline.ate_rmse(seq, r["traj_t"], r["traj_p"]) if len(r["traj_t"]) > 3 else None,
@@ -266,13 +338,14 @@ def main():
         return
 
     import torch
+    from vins_mono_b200 import shard
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the vinsb200 library has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    seq, ts, imgs, imu = sequence_inputs(rank, n_pub)
+    seq, ts, imgs, imu = sequence_inputs(shard.sequences_of_rank(rank, world, 1)[0], n_pub)
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=f"cuda:{local}")  # 256 MB > 126 MB L2
 
     # untimed shake-out pass (first CUDA context / module load, pinned allocations)
@@ -296,12 +369,8 @@ def main():
     barrier()
 
     def agg(res):
-        tot = torch.tensor([sum(res["times"]) / 1e3, float(len(res["times"]))], dtype=torch.float64, device=f"cuda:{local}")
-        mx, cnt = tot[0:1].clone(), tot[1:2].clone()
-        if world > 1:
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        return float(cnt.item()) / float(mx.item()), float(mx.item())
+        rate, sec, _ = shard.aggregate_rate(sum(res["times"]), len(res["times"]), device=f"cuda:{local}")
+        return rate, sec
 
     fps_dev, t_dev = agg(res_dev)
     fps_e2e, t_e2e = agg(res_e2e)
@@ -336,23 +405,32 @@ def main():
         algo = ALGO_BYTES_SOLVE / max(per_frame[dominant], 1e-9)
     avg_s = kt[dominant]["avg_us"] * 1e-6
     achieved = algo / avg_s / 1e9
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(dominant, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": algo, "avg_launch_us": kt[dominant]["avg_us"],
                 "note": "single-sequence step: every kernel is latency/launch bound, not HBM bound (see DESIGN.md)",
                 "kernels": kt}
 
     # ---- CPU baseline on this box's host cores (bounded sample of the same workload)
     cpu_b = None
-    ate_ref = None
+    ate_ref = ate_same = None
     if not a.no_cpu_baseline and world == 1:
-        ns = min(a.steps, 30)
-        rr = run_reference_pass(seq, ts, imgs, imu, INIT_PUBS, 2, ns)
+        ns = min(a.steps, 60)
+        rr = run_reference_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, ns)
         tot = sum(rr["times"]) / 1e3
-        cpu_b = {"value": len(rr["times"]) / tot, "unit": "frames/s", "cores": 1, "kind": "port", "cpu": cpu_model(),
-                 "sample": f"{len(rr['times'])} published frames of the same sequence (oracle tracker + estimator twins, {tot:.1f} s)"}
+        cpu_b = {"value": len(rr["times"]) / tot, "unit": "frames/s", "cores": 2, "kind": "port", "cpu": cpu_model(),
+                 "sample": f"{len(rr['times'])} published frames of the same sequence after the same {INIT_PUBS} init + {warmup} "
+                           f"warm-up frames (oracle tracker + estimator twins on two threads, {tot:.1f} s)"}
         if len(rr["traj_t"]) > 3:
             ate_ref = pipeline.ate_rmse(seq, rr["traj_t"], rr["traj_p"])
+            # the same frames of our trajectory, so that the two ATE figures are comparable
+            nn = len(rr["traj_t"])
+            ate_same = pipeline.ate_rmse(seq, res_dev["traj_t"][:nn], res_dev["traj_p"][:nn])
     ate = pipeline.ate_rmse(seq, res_dev["traj_t"], res_dev["traj_p"]) if len(res_dev["traj_t"]) > 3 else None
 
     k = len(res_dev["times"])
@@ -360,15 +438,17 @@ def main():
         "impl": "b200", "metric": METRIC, "value": fps_dev, "unit": "frames/s", "n_gpus": world, "steps": k, "warmup": warmup,
         "ms_per_step": 1e3 * t_dev / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "configs[1]: single 752x480 synthetic sequence per GPU, 10-keyframe window, 150 features, 200 Hz IMU, "
-                               "fp64 Jacobians", "sequences_per_gpu": 1,
+        "config": {"workload": WORKLOAD, "sequences_per_gpu": 1,
+                   "pipelining": "tracker and estimator handles driven from two host threads coupled by a depth-2 queue (the "
+                                 "reference's two nodes); the timed region starts with both idle and ends with both drained",
                    "l2": "L2 flushed (256 MB write) at the start of the timed region; every step reads two images that were never touched since upload",
                    "timing": "one CUDA-event pair around the K steps, device synchronised (and ranks barriered) on both sides; max over ranks"},
         "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": 1e3 * t_e2e / k,
                 "h2d_bytes_per_step": res_e2e["h2d"] / k, "d2h_bytes_per_step": res_e2e["d2h"] / k},
         "gpu_launches": int(launches.item()),
         "roofline": roofline, "cpu_baseline": cpu_b, "clocks": clk,
-        "ate_rmse_m": ate, "ate_rmse_m_cpu_port": ate_ref,
+        "ate_rmse_m": ate, "ate_rmse_m_same_frames": ate_same, "ate_rmse_m_cpu_port": ate_ref,
+        "ate_rel_diff": (abs(ate_same - ate_ref) / ate_ref) if ate_ref else None,
         "solver": res_dev["info"],
     }))
     if world > 1:

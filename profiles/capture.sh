@@ -1,0 +1,19 @@
+#!/bin/bash
+# Evidence capture for one round (run on the GPU box through gpurun):  bash profiles/capture.sh r1
+# Writes into gpurun_out/ (scratch); profiles/summarize.py turns the reports into the committed CSV/JSON summaries.
+# Numbers printed by processes running under ncu are never bench values.
+R=${1:-r1}
+mkdir -p gpurun_out
+NCU="ncu --clock-control none"
+# 1. launch list (per-launch durations) of the bench command itself
+$NCU --metrics gpu__time_duration.sum -c 12000 --csv --log-file gpurun_out/${R}_bench_launches.csv \
+    python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_bench_under_ncu.log 2>&1
+# 2. --set full captures of single launches in steady state (window full, marginalisation running)
+FULL="$NCU --set full --import-source on -f"
+$FULL -k regex:marg_solve -s 4 -c 1 -o gpurun_out/${R}_marg_solve python harness/debug_backend.py 16 > gpurun_out/${R}_ncu_marg.log 2>&1
+$FULL -k regex:ba_step -s 60 -c 1 -o gpurun_out/${R}_ba_step python harness/debug_backend.py 16 > gpurun_out/${R}_ncu_step.log 2>&1
+$FULL -k "regex:ba_linearize|ba_schur|marg_build|preint_push" -s 200 -c 6 -o gpurun_out/${R}_ba_small python harness/debug_backend.py 16 > gpurun_out/${R}_ncu_small.log 2>&1
+$FULL -k regex:lk_track -s 12 -c 1 -o gpurun_out/${R}_lk_track python harness/run_tracker.py --frames 24 > gpurun_out/${R}_ncu_lk.log 2>&1
+$FULL -k "regex:clahe|pyrdown|min_eig|gftt|sort_keys|mask_discs" -s 60 -c 9 -o gpurun_out/${R}_fe_small python harness/run_tracker.py --frames 24 > gpurun_out/${R}_ncu_fe.log 2>&1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_event_reasons.active --format=csv > gpurun_out/${R}_clocks.csv
+ls -la gpurun_out/
