@@ -1,0 +1,67 @@
+// Phase timing of the single-CTA symmetric eigen-solver (vins_mono_b200/csrc/sym_eig.h) on a real marginalisation
+// prior (harness/micro/prior75.bin: the 75x75 Schur complement A' of a steady-state frame, dumped from the CPU twin).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o harness/micro/eig_bench harness/micro/eig_bench.cu
+#define SE_PROF 1
+#include "../../vins_mono_b200/csrc/sym_eig.h"
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cmath>
+using namespace vb;
+
+__global__ void __launch_bounds__(512) eig_bench_kernel(const double* A, int n, int reps, double* evals, double* evecs, long long* clk) {
+    extern __shared__ double V[];
+    __shared__ double d[96], e[96], cs[4 * 96], scal[16];
+    const int ld = n | 1;
+    if (threadIdx.x < 16) se_clk[threadIdx.x] = 0;
+    long long tot = 0;
+    for (int r = 0; r < reps; r++) {
+        for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) V[(idx / n) * ld + idx % n] = A[idx];
+        __syncthreads();
+        const long long t0 = clock64();
+        sym_eig(CtaCtx(), V, n, ld, d, e, cs, scal);
+        tot += clock64() - t0;
+        __syncthreads();
+    }
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) evecs[idx] = V[(idx / n) * ld + idx % n];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) evals[i] = d[i];
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 16; k++) clk[k] = se_clk[k] / reps;
+        clk[16] = tot / reps;
+        clk[17] = (long long)scal[4];
+        clk[18] = (long long)scal[5];
+    }
+}
+
+int main(int argc, char** argv) {
+    const int n = 75, reps = 5;
+    std::vector<double> A(n * n);
+    FILE* f = fopen(argc > 1 ? argv[1] : "harness/micro/prior75.bin", "rb");
+    if (!f || fread(A.data(), 8, n * n, f) != (size_t)n * n) { printf("cannot read prior\n"); return 1; }
+    fclose(f);
+    double *dA, *dw, *dV; long long* dclk;
+    cudaMalloc(&dA, n * n * 8); cudaMalloc(&dw, n * 8); cudaMalloc(&dV, n * n * 8); cudaMalloc(&dclk, 32 * 8);
+    cudaMemcpy(dA, A.data(), n * n * 8, cudaMemcpyHostToDevice);
+    const int smem = n * (n | 1) * 8 + 64;
+    cudaFuncSetAttribute(eig_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int threads : {512, 256, 128}) {
+        eig_bench_kernel<<<1, threads, smem>>>(dA, n, reps, dw, dV, dclk);
+        cudaDeviceSynchronize();
+        std::vector<double> w(n), V(n * n); long long clk[32];
+        cudaMemcpy(w.data(), dw, n * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(V.data(), dV, n * n * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(clk, dclk, 32 * 8, cudaMemcpyDeviceToHost);
+        double res = 0, amax = 0, orth = 0;
+        for (int i = 0; i < n; i++) for (int k = 0; k < n; k++) {
+            double s = 0, o = 0;
+            for (int j = 0; j < n; j++) { s += A[i * n + j] * V[j * n + k]; o += V[j * n + i] * V[j * n + k]; }
+            res = fmax(res, fabs(s - V[i * n + k] * w[k])); amax = fmax(amax, fabs(A[i * n + k])); orth = fmax(orth, fabs(o - (i == k)));
+        }
+        printf("threads %d: %s  |AV-VW|/|A| = %.2e  |VtV-I| = %.2e   total %lld cycles (tridiag %lld, QL %lld)\n", threads,
+               cudaGetErrorString(cudaGetLastError()), res / amax, orth, clk[16], clk[17], clk[18]);
+        const char* names[] = {"tred2 scalar (scale, h)", "tred2 matvec", "tred2 scalar (e/h, f)", "tred2 rank-2 update", "tred2 row copy",
+                               "accum d = V/h", "accum dots", "accum update+zero", "QL search/bookkeeping", "QL wait for consumers", "QL sweep recurrence"};
+        for (int k = 0; k < 11; k++) printf("    %-28s %9lld\n", names[k], clk[k]);
+    }
+    return 0;
+}

@@ -11,8 +11,8 @@ $NCU --metrics gpu__time_duration.sum -c 12000 --csv --log-file gpurun_out/${R}_
 # 2. --set full captures of single launches in steady state (window full, marginalisation running)
 FULL="$NCU --set full --import-source on -f"
 $FULL -k regex:marg_solve -s 4 -c 1 -o gpurun_out/${R}_marg_solve python harness/debug_backend.py 16 > gpurun_out/${R}_ncu_marg.log 2>&1
-$FULL -k regex:ba_step -s 60 -c 1 -o gpurun_out/${R}_ba_step python harness/debug_backend.py 16 > gpurun_out/${R}_ncu_step.log 2>&1
-$FULL -k "regex:ba_linearize|ba_schur|marg_build|preint_push" -s 200 -c 6 -o gpurun_out/${R}_ba_small python harness/debug_backend.py 16 > gpurun_out/${R}_ncu_small.log 2>&1
+$FULL -k regex:ba_step -s 20 -c 1 -o gpurun_out/${R}_ba_step python harness/debug_backend.py 16 > gpurun_out/${R}_ncu_step.log 2>&1
+$FULL -k "regex:ba_linearize|ba_schur|marg_build|preint_push" -s 40 -c 8 -o gpurun_out/${R}_ba_small python harness/debug_backend.py 16 > gpurun_out/${R}_ncu_small.log 2>&1
 $FULL -k regex:lk_track -s 12 -c 1 -o gpurun_out/${R}_lk_track python harness/run_tracker.py --frames 24 > gpurun_out/${R}_ncu_lk.log 2>&1
 $FULL -k "regex:clahe|pyrdown|min_eig|gftt|sort_keys|mask_discs" -s 60 -c 9 -o gpurun_out/${R}_fe_small python harness/run_tracker.py --frames 24 > gpurun_out/${R}_ncu_fe.log 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_event_reasons.active --format=csv > gpurun_out/${R}_clocks.csv

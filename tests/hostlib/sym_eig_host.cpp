@@ -4,7 +4,7 @@
 #include <vector>
 extern "C" void host_sym_eig(const double* A, int n, double* evals, double* evecs) {
     const int ld = n | 1;
-    std::vector<double> V(static_cast<size_t>(n) * ld), e(n), cs(2 * n), scal(16);
+    std::vector<double> V(static_cast<size_t>(n) * ld), e(n), cs(4 * n), scal(16);
     for (int i = 0; i < n; i++)
         for (int j = 0; j < n; j++) V[i * ld + j] = A[i * n + j];
     vb::sym_eig(vb::HostCtx(), V.data(), n, ld, evals, e.data(), cs.data(), scal.data());

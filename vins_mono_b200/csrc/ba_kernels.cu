@@ -1243,16 +1243,16 @@ constexpr int MARG_THREADS = 512;
 // Both eigen-decompositions (the dense marginalised block T and the new prior A') use the tridiagonal-QL solver of
 // sym_eig.h: eigenvector k is the COLUMN k of Vv (odd leading dimension: conflict-free row walks).
 __global__ void __launch_bounds__(MARG_THREADS) marg_solve_kernel(MargPlan mp, double eps) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
-    __shared__ double dval[96], ework[96], cs[2 * 96], scal[16];
+    __shared__ double dval[96], ework[96], cs[4 * 96], scal[16];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int md = mp.m_dense, nl = mp.n_lm, n = mp.n, P = mp.P;
     const int q = md + n;
     const int ldm = md + (md & 1), ldn = n + (n & 1), ldx = max(ldm, ldn);
-    const int esz = max(max((ldx + 1) * (ldx + 1), n * (ldm + md)), 16 * q);
+    const int esz = max(max((ldx + 1) * (ldx + 1), n * (ldm + md)), 32 * ((q + 3) & ~3));
     double* Wk = sm;                  // q*q
-    double* Ev = Wk + q * q;          // esz
+    double* Ev = Wk + ((q * q + 1) & ~1);  // esz (16-byte aligned: 128-bit loads of the staged landmark rows)
     double* Vv = Ev + esz;            // (ldx+1)^2
     double* bw = Vv + (ldx + 1) * (ldx + 1);  // q
     double* tv = bw + q;              // ldx
@@ -1261,49 +1261,91 @@ __global__ void __launch_bounds__(MARG_THREADS) marg_solve_kernel(MargPlan mp, d
     long long mclk[6] = {0, 0, 0, 0, 0, 0};
     long long mc0 = clock64();
 #define MSTAMP(k) do { const long long c1_ = clock64(); mclk[k] = c1_ - mc0; mc0 = c1_; } while (0)
-    // 1. eliminate the landmark columns (exactly diagonal block): rank-1 downdates, landmark rows staged through
-    //    shared memory 32 at a time (Ev is free until step 2: 32 * q <= ldx^2 is checked on the host side)
-    for (int idx = tid; idx < q * q; idx += nt) {
-        const int aa = idx / q, bb = idx - aa * q;
-        if (aa <= bb) Wk[idx] = symA(full(aa), full(bb));
-    }
-    for (int aa = tid; aa < q; aa += nt) bw[aa] = mp.bm[full(aa)];
-    __syncthreads();
-    double* Wl = Ev;        // chunk x q landmark rows
-    double* invd = tv;      // chunk: 1 / d_c (0 when d_c <= eps), then b_c / d_c in invd + 32
-    for (int c0 = 0; c0 < nl; c0 += 16) {
-        const int cn = min(16, nl - c0);
-        for (int idx = tid; idx < cn * q; idx += nt) {
-            const int c = idx / q, aa = idx - c * q;
-            Wl[idx] = symA(full(aa), md + c0 + c);
-        }
-        if (tid < cn) {
-            const int fc = md + c0 + tid;
-            const double dc = mp.Am[(size_t)fc * P + fc];
-            invd[tid] = dc > eps ? 1.0 / dc : 0.0;
-            invd[16 + tid] = mp.bm[fc];
-        }
-        __syncthreads();
-        for (int idx = tid; idx < q * q; idx += nt) {
-            const int aa = idx / q, bb = idx - aa * q;
-            if (aa > bb) continue;
-            double acc = 0;
-            for (int c = 0; c < cn; c++) {
-                const double wa = Wl[c * q + aa];
-                if (wa != 0.0) acc += wa * invd[c] * Wl[c * q + bb];
+    // 1. eliminate the landmark columns (exactly diagonal block): W -= sum_c w_c w_c^T / d_c over the landmarks c.
+    //    Register-tiled: a thread owns one 4x4 tile of the upper triangle of W (q = 90 -> 276 tiles) and accumulates
+    //    over ALL landmarks in registers; the landmark rows are staged 16 at a time in shared memory (raw and scaled by
+    //    1/d_c, row stride qp = q rounded up to 4 so that a tile operand is two 128-bit loads).  Landmark rows are sparse
+    //    (only the observing frames' pose blocks): a tile skips a landmark whose scaled operand is zero.
+    const int qp = (q + 3) & ~3, nt4 = qp >> 2, ntile = nt4 * (nt4 + 1) / 2;
+    constexpr int MCH = 16;
+    double* Wl = Ev;             // MCH x qp raw rows
+    double* Ws = Ev + MCH * qp;  // MCH x qp rows scaled by 1 / d_c (0 when d_c <= eps)
+    double* invd = tv;           // MCH: 1 / d_c, then b_c in invd + MCH
+    const int tile_threads = nt - q;  // the last q threads accumulate the right-hand side (first round only)
+    for (int t0 = 0; t0 < ntile; t0 += tile_threads) {  // one round at the shipped sizes; more for larger windows
+        const int tile = t0 + tid;
+        const bool has_tile = tid < tile_threads && tile < ntile;
+        const bool has_rhs = t0 == 0 && tid >= tile_threads;
+        int ta = 0, tb = 0;
+        if (has_tile) {  // tile index -> (ta <= tb): row ta holds tiles tb = ta .. nt4-1
+            int rem = tile;
+            while (rem >= nt4 - ta) {
+                rem -= nt4 - ta;
+                ta++;
             }
-            Wk[idx] -= acc;
+            tb = ta + rem;
         }
-        for (int aa = tid; aa < q; aa += nt) {
-            double acc = 0;
-            for (int c = 0; c < cn; c++) acc += Wl[c * q + aa] * invd[c] * invd[16 + c];
-            bw[aa] -= acc;
+        double acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[r][c] = 0.0;
+        double bacc = 0.0;  // sum_c w_c[aa] b_c / d_c
+        for (int c0 = 0; c0 < nl; c0 += MCH) {
+            const int cn = min(MCH, nl - c0);
+            if (tid < cn) {
+                const int fc = md + c0 + tid;
+                const double dc = mp.Am[(size_t)fc * P + fc];
+                invd[tid] = dc > eps ? 1.0 / dc : 0.0;
+                invd[MCH + tid] = mp.bm[fc];
+            }
+            __syncthreads();
+            for (int idx = tid; idx < MCH * qp; idx += nt) {
+                const int c = idx / qp, aa = idx - c * qp;
+                double v = 0.0;
+                if (c < cn && aa < q) {
+                    const int fc = md + c0 + c;
+                    v = aa < md ? mp.Am[(size_t)aa * P + fc] : mp.Am[(size_t)fc * P + aa + nl];
+                }
+                Wl[idx] = v;
+                Ws[idx] = c < cn ? v * invd[c] : 0.0;
+            }
+            __syncthreads();
+            if (has_tile) {
+                for (int c = 0; c < cn; c++) {
+                    const double2* pa = reinterpret_cast<const double2*>(Ws + c * qp + 4 * ta);
+                    const double2 a01 = pa[0], a23 = pa[1];
+                    if (a01.x == 0.0 && a01.y == 0.0 && a23.x == 0.0 && a23.y == 0.0) continue;
+                    const double2* pb = reinterpret_cast<const double2*>(Wl + c * qp + 4 * tb);
+                    const double2 b01 = pb[0], b23 = pb[1];
+                    const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+#pragma unroll
+                        for (int cc = 0; cc < 4; cc++) acc[r][cc] += av[r] * bv[cc];
+                }
+            } else if (has_rhs) {
+                const int aa = tid - tile_threads;
+                for (int c = 0; c < cn; c++) bacc += Ws[c * qp + aa] * invd[MCH + c];
+            }
+            __syncthreads();
         }
-        __syncthreads();
-    }
-    for (int idx = tid; idx < q * q; idx += nt) {
-        const int aa = idx / q, bb = idx - aa * q;
-        if (aa > bb) Wk[idx] = Wk[bb * q + aa];
+        if (has_tile) {
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int cc = 0; cc < 4; cc++) {
+                    const int aa = 4 * ta + r, bb = 4 * tb + cc;
+                    if (aa <= bb && bb < q) {
+                        const double v = symA(full(aa), full(bb)) - acc[r][cc];
+                        Wk[aa * q + bb] = v;
+                        Wk[bb * q + aa] = v;
+                    }
+                }
+        } else if (has_rhs) {
+            const int aa = tid - tile_threads;
+            bw[aa] = mp.bm[full(aa)] - bacc;
+        }
     }
     __syncthreads();
     // 2. pseudo-inverse of the dense marginalised block T (md x md) by eigen-decomposition
@@ -1409,8 +1451,8 @@ __global__ void __launch_bounds__(MARG_THREADS) marg_solve_kernel(MargPlan mp, d
 size_t marg_solve_smem_bytes(int m_dense, int n) {
     const int q = m_dense + n;
     const int ldm = m_dense + (m_dense & 1), ldn = n + (n & 1), ldx = ldm > ldn ? ldm : ldn;
-    const size_t esz = std::max(std::max((size_t)(ldx + 1) * (ldx + 1), (size_t)n * (ldm + m_dense)), (size_t)16 * q);
-    return sizeof(double) * ((size_t)q * q + esz + (size_t)(ldx + 1) * (ldx + 1) + q + std::max(ldx, 32));
+    const size_t esz = std::max(std::max((size_t)(ldx + 1) * (ldx + 1), (size_t)n * (ldm + m_dense)), (size_t)32 * ((q + 3) & ~3));
+    return sizeof(double) * ((size_t)q * q + 1 + esz + (size_t)(ldx + 1) * (ldx + 1) + q + std::max(ldx, 32));
 }
 
 }  // namespace vb
