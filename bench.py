@@ -23,6 +23,10 @@ import time
 
 import numpy as np
 
+# Concurrent sequences use two CUDA streams each; the default of 8 hardware work queues would alias them onto each other
+# (false serialisation).  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
@@ -141,7 +145,31 @@ class TwoStage:
         return msg
 
 
-def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images, profile=False, flush=None, sync_cb=None):
+class SoloGate:
+    """Brackets the timed region of ONE sequence: device drained, L2 evicted, optional cross-rank barrier, CUDA events."""
+
+    def __init__(self, device, flush=None, sync_cb=None):
+        import torch
+        self.torch, self.device, self.flush, self.sync_cb = torch, device, flush, sync_cb
+        self.ev0, self.ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def begin(self):
+        if self.flush is not None:
+            self.flush.fill_(1.0)
+        self.torch.cuda.synchronize(self.device)
+        if self.sync_cb:
+            self.sync_cb()
+        self.ev0.record()
+
+    def end(self):
+        self.torch.cuda.synchronize(self.device)  # includes the last frame's (asynchronous) marginalisation
+        self.ev1.record()
+        self.ev1.synchronize()
+        return self.ev0.elapsed_time(self.ev1)
+
+
+def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images, profile=False, flush=None, sync_cb=None,
+                  gate=None, d_imgs=None):
     """One pass over the sequence.  The K timed steps form ONE region bracketed by device synchronisation and a pair of
     CUDA events (ms per step = region / K); sync_cb, if given, is the cross-rank barrier placed inside the bracket.
     Tracker and estimator handles are driven from two host threads (TwoStage); with profile=True they run serially."""
@@ -153,12 +181,13 @@ def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images
     feeder = BatchedImu(*imu)
     n_pub = n_init + warmup + steps
     est.set_seed(pipeline.gt_seed_rows(seq, ts), seq.ba, seq.bg)
-    d_imgs = None
     frame_bytes = imgs.shape[1] * imgs.shape[2]
     if not host_images:
-        d_imgs = torch.from_numpy(imgs).to(f"cuda:{device}")
+        if d_imgs is None:
+            d_imgs = torch.from_numpy(imgs).to(f"cuda:{device}")
         base = d_imgs.data_ptr()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if gate is None:
+        gate = SoloGate(device, flush, sync_cb)
     launches, h2d, d2h, traj_t, traj_p = 0, 0.0, 0.0, [], []
     n_img = len(ts)
     cursor = [0]
@@ -200,12 +229,7 @@ def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images
             # start of the timed region: both stages idle, device drained, L2 evicted once (every timed step reads images
             # that were uploaded long ago and never touched since, i.e. cold in L2; the rest of a step's data is
             # produced inside it)
-            if flush is not None:
-                flush.fill_(1.0)
-            torch.cuda.synchronize(device)
-            if sync_cb:
-                sync_cb()
-            ev0.record()
+            gate.begin()
             started = True
             stage.go()
         msg = stage.get()
@@ -231,17 +255,55 @@ def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images
             traj_t.append(stamp)
             traj_p.append(st[-1, 0:3].copy())
         pubs += 1
-    torch.cuda.synchronize(device)  # includes the last frame's (asynchronous) marginalisation
-    ev1.record()
-    ev1.synchronize()
+    region_ms = gate.end() if started else 0.0
     stage.go()
-    times = [ev0.elapsed_time(ev1) / max(n_timed, 1)] * n_timed if started else []
+    times = [region_ms / max(n_timed, 1)] * n_timed if started else []
     out = dict(times=times, launches=launches, h2d=h2d, d2h=d2h, traj_t=traj_t, traj_p=traj_p, info=est.info())
     if profile:
         out["trk_k"], out["est_k"] = trk.kernel_times(), est.kernel_times()
     trk.close()
     est.close()
     return out
+
+
+def run_replay_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, n_seq, host_images=False, flush=None, sync_cb=None):
+    """n_seq replicas of the sequence driven by the native replay driver (include/vinsb200/replay.h: the reference's two
+    node loops in C++, one thread pair per sequence), all concurrently on one GPU.  The timed region is ONE vr_advance
+    call of `steps` published frames per sequence, bracketed like the single-sequence pass.  n_seq = 1 is the plain
+    single-sequence pipeline without any Python in the loop."""
+    import torch
+    from vins_mono_b200 import ReplaySession
+    t_imu, acc, gyr = imu
+    pairs = [make_gpu_pair(device) for _ in range(n_seq)]
+    seed = pipeline.gt_seed_rows(seq, ts)
+    for _, est in pairs:
+        est.set_seed(seed, seq.ba, seq.bg)
+    d_imgs = None
+    if host_images:
+        images = dict(images=imgs)
+    else:
+        d_imgs = torch.from_numpy(np.array(imgs, copy=True)).to(f"cuda:{device}")
+        images = dict(images=d_imgs.data_ptr(), shape=imgs.shape)
+    seqs = [dict(stamps=ts, imu_t=t_imu, acc=acc, gyr=gyr, **images) for _ in range(n_seq)]
+    ses = ReplaySession([p[0] for p in pairs], [p[1] for p in pairs], seqs)
+    gate = SoloGate(device, flush, sync_cb)
+    ses.advance(n_init + warmup)
+    before = [ses.stats(k) for k in range(n_seq)]
+    gate.begin()
+    frames = ses.advance(steps)
+    region_ms = gate.end()
+    after = [ses.stats(k) for k in range(n_seq)]
+    trajs = [ses.trajectory(k) for k in range(n_seq)]
+    infos = [p[1].info() for p in pairs]
+    ses.close()
+    for trk, est in pairs:
+        trk.close()
+        est.close()
+    del d_imgs
+    return dict(frames=frames, region_ms=region_ms, fps=frames / (region_ms / 1e3) if region_ms else 0.0,
+                launches=sum(a["launches"] - b["launches"] for a, b in zip(after, before)),
+                h2d=sum(a["h2d"] - b["h2d"] for a, b in zip(after, before)), d2h=sum(a["d2h"] - b["d2h"] for a, b in zip(after, before)),
+                trajs=trajs, infos=infos, final_cost=[i["final_cost"] for i in infos])
 
 
 def run_reference_pass(seq, ts, imgs, imu, n_init, warmup, steps):
@@ -311,6 +373,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=16,
+                    help="supplementary pass: this many concurrent replicas of the sequence per GPU (0 = skip)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
@@ -416,6 +480,21 @@ def main():
                 "note": "single-sequence step: every kernel is latency/launch bound, not HBM bound (see DESIGN.md)",
                 "kernels": kt}
 
+    # ---- supplementary: concurrent sequences on the same GPU (BASELINE.json configs[2] direction; not the headline)
+    batch = None
+    if a.batch > 1 and world == 1:
+        rb = run_replay_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, min(a.steps, 30), local, a.batch, flush=flush)
+        spread = max(abs(c - rb["final_cost"][0]) for c in rb["final_cost"]) / max(1.0, abs(rb["final_cost"][0]))
+        r1 = run_replay_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, min(a.steps, 30), local, 1, flush=flush)
+        batch = {"sequences_per_gpu": a.batch, "value": rb["fps"], "unit": "frames/s", "frames": rb["frames"],
+                 "ms_region": rb["region_ms"], "gpu_launches": rb["launches"], "replica_final_cost_rel_spread": spread,
+                 "single_sequence_same_driver": {"value": r1["fps"], "unit": "frames/s", "frames": r1["frames"]},
+                 "spread_note": "replicas see identical inputs; they differ only through the order of the fp64 atomic adds "
+                                "of the Hessian assembly (not bit-reproducible run to run, same as a single sequence)",
+                 "note": "replicas of sequence 0 (device-resident frames) driven by the native replay driver "
+                         "(vinsb200/replay.h: one tracker thread + one estimator thread per sequence); aggregate frames/s "
+                         "over one shared timed region"}
+
     # ---- CPU baseline on this box's host cores (bounded sample of the same workload)
     cpu_b = None
     ate_ref = ate_same = None
@@ -446,7 +525,7 @@ def main():
         "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": 1e3 * t_e2e / k,
                 "h2d_bytes_per_step": res_e2e["h2d"] / k, "d2h_bytes_per_step": res_e2e["d2h"] / k},
         "gpu_launches": int(launches.item()),
-        "roofline": roofline, "cpu_baseline": cpu_b, "clocks": clk,
+        "roofline": roofline, "cpu_baseline": cpu_b, "clocks": clk, "batch": batch,
         "ate_rmse_m": ate, "ate_rmse_m_same_frames": ate_same, "ate_rmse_m_cpu_port": ate_ref,
         "ate_rel_diff": (abs(ate_same - ate_ref) / ate_ref) if ate_ref else None,
         "solver": res_dev["info"],

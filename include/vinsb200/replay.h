@@ -1,0 +1,63 @@
+/* vinsb200 replay driver — C ABI of the two node loops around the hot path, for offline sequences.
+ *
+ * Restates, for data already in memory instead of ROS topics:
+ *   feature_tracker_node.cpp:28-165  img_callback: every image goes through vt_node_image (first-frame / discontinuity /
+ *                                    frequency gating, readImage, updateID), a feature message is produced when it
+ *                                    publishes (track_cnt > 1 points; x, y, z = 1 and the id/u/v/velocity channels
+ *                                    travel as float32 exactly like sensor_msgs/PointCloud)
+ *   estimator_node.cpp:98-136        getMeasurements: the IMU samples up to the image stamp plus the first one after it
+ *   estimator_node.cpp:167-172       feature_callback drops the very first feature message
+ *   estimator_node.cpp:225-265       process(): per-sample dt, linear interpolation of the sample that straddles the stamp
+ *   estimator_node.cpp:275-316       image map construction and Estimator::processImage
+ * The reference runs the two loops in two processes; here every sequence gets one tracker thread and one estimator
+ * thread coupled by a bounded queue (depth 2), and any number of sequences run concurrently on one GPU (each handle
+ * owns its CUDA stream).  No ROS, no CPU fallback: the handles are the CUDA ones of tracker.h / estimator.h.
+ */
+#ifndef VINSB200_REPLAY_H
+#define VINSB200_REPLAY_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "vinsb200/estimator.h"
+#include "vinsb200/tracker.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vr_sequence {
+    const uint8_t* images;  /* n_images frames, frame k at images + k * frame_stride (host or device memory) */
+    size_t row_stride, frame_stride;
+    int n_images;
+    int images_on_device;   /* 0: host pointers (each frame is copied to the GPU inside the call), 1: device pointers */
+    const double* stamps;   /* n_images image time stamps (s) */
+    int n_imu;
+    const double* imu_t;    /* n_imu sample stamps (s), ascending */
+    const double* acc;      /* n_imu x 3 linear_acceleration */
+    const double* gyr;      /* n_imu x 3 angular_velocity */
+} vr_sequence;
+
+typedef struct vr_session vr_session;
+
+/* The session borrows the handles and the sequence memory: they must outlive it.  Seed / configure the estimators
+ * before the first vr_advance. */
+int vr_open(int n_seq, vt_tracker* const* trackers, ve_estimator* const* estimators, const vr_sequence* seqs, vr_session** out);
+void vr_close(vr_session* s);
+const char* vr_last_error(const vr_session* s);
+
+/* Runs every sequence forward by up to n_pub published frames (fewer when its images run out), all sequences
+ * concurrently, and returns when every queue has drained (device work may still be in flight on the handles' streams).
+ * Returns the number of published frames consumed over all sequences, or < 0 (a vt_status / ve_status value). */
+int vr_advance(vr_session* s, int n_pub);
+
+/* Per sequence counters since vr_open: published frames consumed, kernels launched, host<->device bytes. */
+int vr_stats(const vr_session* s, int seq, int* frames, long long* launches, double* h2d_bytes, double* d2h_bytes);
+/* Position of the newest window frame after every processImage in the NON_LINEAR state: copies up to cap entries,
+ * returns the number available. */
+int vr_trajectory(const vr_session* s, int seq, int cap, double* stamps, double* positions3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

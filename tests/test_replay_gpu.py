@@ -1,0 +1,55 @@
+"""The native replay driver (include/vinsb200/replay.h) against the Python-driven node loops: same handles, same data,
+so the feature messages are identical and the estimator states agree up to the order of the fp64 atomic adds."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+pytestmark = pytest.mark.gpu
+
+
+def test_replay_matches_python_loop_and_replicas_agree():
+    from harness import synth, pipeline
+    from vins_mono_b200 import FeatureTracker, Estimator, ReplaySession
+    n_pub = 18
+    n_img = 2 * (n_pub + 1) + 2
+    seq = synth.Sequence(seed=3, duration=n_img / 20.0 + 0.5)
+    ts, imgs = pipeline.cached_images(seq, n_img)
+    imgs = np.ascontiguousarray(imgs)
+    t_imu, acc, gyr = seq.imu()
+    seed = pipeline.gt_seed_rows(seq, ts)
+
+    def pair():
+        t = FeatureTracker(**synth.tracker_config_dict())
+        e = Estimator(tic=synth.TIC, ric=synth.RIC)
+        e.set_seed(seed, seq.ba, seq.bg)
+        return t, e
+
+    # reference: the Python loop of harness.pipeline (feature_messages + ImuFeeder + processImage)
+    trk, est = pair()
+    ref = pipeline.run_vio(seq, trk, est, n_img, messages=list(pipeline.feature_messages(trk, ts, imgs))[:n_pub])
+    ref_states, _ = est.states()
+    trk.close()
+    est.close()
+
+    pairs = [pair() for _ in range(3)]
+    ses = ReplaySession([p[0] for p in pairs], [p[1] for p in pairs],
+                        [dict(images=imgs, stamps=ts, imu_t=t_imu, acc=acc, gyr=gyr) for _ in pairs])
+    assert ses.advance(7) == 3 * 7          # two calls: the session keeps its cursors / IMU position
+    assert ses.advance(n_pub - 7) == 3 * (n_pub - 7)
+    for k, (t, e) in enumerate(pairs):
+        st = ses.stats(k)
+        assert st["frames"] == n_pub and st["launches"] > 0 and st["h2d"] > n_pub * 2 * 752 * 480 * 0.9
+        tt, pp = ses.trajectory(k)
+        assert len(tt) == len(ref["t"]) and np.array_equal(tt, np.asarray(ref["t"]))
+        assert np.abs(pp - np.asarray(ref["P"])).max() < 1e-6
+        states, _ = e.states()
+        assert np.abs(states - ref_states).max() < 1e-6
+    ses.close()
+    for t, e in pairs:
+        t.close()
+        e.close()

@@ -6,3 +6,4 @@ loading fails loudly when the library is missing, creating a tracker fails when 
 """
 from .tracker import FeatureTracker, TrackerConfig, load_library, LIB_PATH  # noqa: F401
 from .estimator import Estimator, EstimatorConfig  # noqa: F401
+from .replay import ReplaySession  # noqa: F401

@@ -17,6 +17,7 @@
 #include "ba_kernels.h"
 
 #include <algorithm>
+#include <mutex>
 #include <cfloat>
 
 #include "ba_device.cuh"
@@ -1494,6 +1495,8 @@ void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int
     const int tiles = (d.D + ST - 1) / ST;
     const size_t panel_bytes = sizeof(double) * CHOL_NB * CHOL_PS;
     const size_t chol_bytes = sizeof(double) * (size_t)d.D * (d.D + 1) / 2 + panel_bytes;
+    static std::mutex cfg_mutex;  // handles on different host threads share the per-function attributes
+    std::unique_lock<std::mutex> cfg_lock(cfg_mutex);
     static int smem_limit = -1, smem_static = 0, smem_configured = 0;
     if (smem_limit < 0) {
         int dev = 0;
@@ -1509,6 +1512,7 @@ void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int
         cudaFuncSetAttribute(ba_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dyn);
         smem_configured = (int)step_dyn;
     }
+    cfg_lock.unlock();
     int n = 0;
     prof->begin(s);
     ba_zero_kernel<<<zero_grid, 256, 0, s>>>(p, 1);
@@ -1545,10 +1549,14 @@ void launch_marginalize(const BaProblem& p, const MargPlan& mp, cudaStream_t s, 
     marg_build_kernel<<<grid, 128, 0, s>>>(p, mp);
     prof->end(4, s);
     const size_t smem = marg_solve_smem_bytes(mp.m_dense, mp.n);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(marg_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
+    {
+        static std::mutex cfg_mutex;
+        static size_t configured = 0;
+        std::lock_guard<std::mutex> lock(cfg_mutex);
+        if (smem > configured) {
+            cudaFuncSetAttribute(marg_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = smem;
+        }
     }
     prof->begin(s);
     marg_solve_kernel<<<1, MARG_THREADS, smem, s>>>(mp, 1e-8);

@@ -8,6 +8,8 @@
 // GEMM shaped, so no tensor cores.
 #include "fe_kernels.h"
 
+#include <mutex>
+
 #include <cfloat>
 #include <cstdint>
 
@@ -673,11 +675,12 @@ void launch_gftt_tail(const float* eig, int rows, int cols, int epitch, const ui
     dim3 block(32, 8), grid((cols + 31) / 32, (rows + 7) / 8);
     gftt_candidates_kernel<<<grid, block, 0, s>>>(eig, rows, cols, epitch, mask, mpitch, max_sortable, quality, keys,
                                                   capacity, count);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(sort_keys_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SORT_SMEM_KEYS * (int)sizeof(unsigned long long));
-        attr_set = true;
+    {
+        static std::once_flag attr_once;  // trackers on different host threads share the function attribute
+        std::call_once(attr_once, [] {
+            cudaFuncSetAttribute(sort_keys_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 SORT_SMEM_KEYS * (int)sizeof(unsigned long long));
+        });
     }
     sort_keys_desc_kernel<<<1, 1024, SORT_SMEM_KEYS * sizeof(unsigned long long), s>>>(keys, count, capacity);
     const int cell = (int)lrint((double)min_dist);

@@ -1,0 +1,287 @@
+// Offline replay driver: the tracker node loop and the estimator node loop of the reference around the CUDA handles,
+// one thread pair per sequence, any number of sequences concurrently.  See include/vinsb200/replay.h for the mapping
+// to feature_tracker_node.cpp / estimator_node.cpp.  Pure host code on top of the two C ABIs.
+#include "vinsb200/replay.h"
+
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct FeatureMsg {
+    double stamp = 0;
+    std::vector<int> ids;
+    std::vector<double> obs;  // n x 7: x y z u v vx vy
+    long long launches = 0;
+    double h2d = 0, d2h = 0;
+    bool end = false;  // producer is done for this vr_advance call
+};
+
+struct Channel {  // bounded queue between the two loops of one sequence
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<FeatureMsg> q;
+    size_t depth = 2;
+    void put(FeatureMsg&& v) {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return q.size() < depth; });
+        q.push_back(std::move(v));
+        cv.notify_all();
+    }
+    FeatureMsg get() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return !q.empty(); });
+        FeatureMsg v = std::move(q.front());
+        q.pop_front();
+        cv.notify_all();
+        return v;
+    }
+};
+
+struct SeqState {
+    vt_tracker* trk = nullptr;
+    ve_estimator* est = nullptr;
+    vr_sequence in{};
+    int cursor = 0;           // next image
+    bool first_msg = true;    // estimator_node.cpp:167-172
+    int imu_k = 0;            // next IMU sample
+    double current_time = -1; // estimator_node.cpp:221
+    double last_acc[3] = {0, 0, 0}, last_gyr[3] = {0, 0, 0};
+    int frames = 0;
+    long long launches = 0;
+    double h2d = 0, d2h = 0;
+    std::vector<double> traj_t, traj_p;
+    Channel ch;
+    // scratch
+    std::vector<float> f_xy, f_id, f_u, f_v, f_vx, f_vy;
+    std::vector<double> dt, acc, gyr, states;
+};
+
+}  // namespace
+
+struct vr_session {
+    std::vector<SeqState> seqs;
+    std::string error;
+    std::mutex err_m;
+    std::atomic<int> status{0};
+    void fail(int code, const std::string& what) {
+        std::lock_guard<std::mutex> lk(err_m);
+        if (status.load() == 0) {
+            status.store(code);
+            error = what;
+        }
+    }
+};
+
+namespace {
+
+// images until one publishes (or the data / the quota ends)
+void tracker_loop(vr_session* s, SeqState* q, int n_pub) {
+    for (int produced = 0; produced < n_pub && s->status.load() == 0;) {
+        FeatureMsg msg;
+        int r = 0;
+        while (r != 2 && q->cursor < q->in.n_images) {
+            const uint8_t* img = q->in.images + (size_t)q->cursor * q->in.frame_stride;
+            const double stamp = q->in.stamps[q->cursor];
+            int restart = 0;
+            r = q->in.images_on_device ? vt_node_image_device(q->trk, img, q->in.row_stride, stamp, &restart)
+                                       : vt_node_image(q->trk, img, q->in.row_stride, stamp, &restart);
+            q->cursor++;
+            if (r < 0) {
+                s->fail(r, std::string("tracker: ") + vt_last_error(q->trk));
+                break;
+            }
+            if (r > 0) {
+                int l = 0;
+                double a = 0, b = 0;
+                vt_last_timing(q->trk, nullptr, &l);
+                vt_last_traffic(q->trk, &a, &b);
+                msg.launches += l;
+                msg.h2d += a;
+                msg.d2h += b;
+            }
+        }
+        if (r != 2) break;
+        const int cap = vt_count(q->trk);
+        q->f_xy.resize(2 * (size_t)cap + 2);
+        q->f_id.resize(cap + 1);
+        q->f_u.resize(cap + 1);
+        q->f_v.resize(cap + 1);
+        q->f_vx.resize(cap + 1);
+        q->f_vy.resize(cap + 1);
+        const int n = vt_node_pack(q->trk, cap, q->f_xy.data(), q->f_id.data(), q->f_u.data(), q->f_v.data(), q->f_vx.data(),
+                                   q->f_vy.data());
+        if (n < 0) {
+            s->fail(n, "tracker: vt_node_pack");
+            break;
+        }
+        msg.stamp = q->in.stamps[q->cursor - 1];
+        msg.ids.resize(n);
+        msg.obs.resize(7 * (size_t)n);
+        for (int k = 0; k < n; k++) {  // estimator_node.cpp:283-302: v = id_of_point + 0.5, feature_id = v / NUM_OF_CAM
+            msg.ids[k] = (int)(q->f_id[k] + 0.5f);
+            double* o = &msg.obs[7 * (size_t)k];
+            o[0] = q->f_xy[2 * k];
+            o[1] = q->f_xy[2 * k + 1];
+            o[2] = 1.0;
+            o[3] = q->f_u[k];
+            o[4] = q->f_v[k];
+            o[5] = q->f_vx[k];
+            o[6] = q->f_vy[k];
+        }
+        q->ch.put(std::move(msg));
+        produced++;
+    }
+    FeatureMsg fin;
+    fin.end = true;
+    q->ch.put(std::move(fin));
+}
+
+void imu_one(SeqState* q, int k, double img_t) {
+    const double t = q->in.imu_t[k];
+    const double* a = q->in.acc + 3 * (size_t)k;
+    const double* g = q->in.gyr + 3 * (size_t)k;
+    if (t <= img_t) {
+        if (q->current_time < 0) q->current_time = t;
+        const double dt = t - q->current_time;
+        q->current_time = t;
+        for (int c = 0; c < 3; c++) {
+            q->last_acc[c] = a[c];
+            q->last_gyr[c] = g[c];
+        }
+        q->dt.push_back(dt);
+    } else {
+        const double dt_1 = img_t - q->current_time, dt_2 = t - img_t;
+        q->current_time = img_t;
+        const double w1 = dt_2 / (dt_1 + dt_2), w2 = dt_1 / (dt_1 + dt_2);
+        for (int c = 0; c < 3; c++) {
+            q->last_acc[c] = w1 * q->last_acc[c] + w2 * a[c];
+            q->last_gyr[c] = w1 * q->last_gyr[c] + w2 * g[c];
+        }
+        q->dt.push_back(dt_1);
+    }
+    for (int c = 0; c < 3; c++) {
+        q->acc.push_back(q->last_acc[c]);
+        q->gyr.push_back(q->last_gyr[c]);
+    }
+}
+
+void estimator_loop(vr_session* s, SeqState* q) {
+    for (;;) {
+        FeatureMsg msg = q->ch.get();
+        if (msg.end) break;
+        if (s->status.load() != 0) continue;  // keep draining so that the producer can finish
+        long long launches = msg.launches;
+        double h2d = msg.h2d, d2h = msg.d2h;
+        if (q->first_msg) {
+            q->first_msg = false;
+        } else {
+            q->dt.clear();
+            q->acc.clear();
+            q->gyr.clear();
+            while (q->imu_k < q->in.n_imu && q->in.imu_t[q->imu_k] < msg.stamp) {
+                imu_one(q, q->imu_k, msg.stamp);
+                q->imu_k++;
+            }
+            if (q->imu_k < q->in.n_imu) imu_one(q, q->imu_k, msg.stamp);  // used, but stays in the buffer
+            int rc = q->dt.empty() ? 0 : ve_process_imu_batch(q->est, (int)q->dt.size(), q->dt.data(), q->acc.data(), q->gyr.data());
+            if (rc == 0) rc = ve_process_image(q->est, (int)msg.ids.size(), msg.ids.data(), msg.obs.data(), msg.stamp);
+            if (rc < 0) {
+                s->fail(rc, std::string("estimator: ") + ve_last_error(q->est));
+                continue;
+            }
+            int l = 0;
+            double a = 0, b = 0;
+            ve_last_timing(q->est, nullptr, &l);
+            ve_last_traffic(q->est, &a, &b);
+            launches += l;
+            h2d += a;
+            d2h += b;
+        }
+        q->frames++;
+        q->launches += launches;
+        q->h2d += h2d;
+        q->d2h += d2h;
+        int info[10];
+        double costs[2];
+        if (ve_info(q->est, info, costs) == 0 && info[0] == 1) {
+            ve_get_states(q->est, q->states.data(), nullptr);
+            const double* newest = &q->states[16 * (size_t)info[1]];  // frame_count == WINDOW_SIZE: the newest frame
+            q->traj_t.push_back(msg.stamp);
+            q->traj_p.insert(q->traj_p.end(), newest, newest + 3);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int vr_open(int n_seq, vt_tracker* const* trackers, ve_estimator* const* estimators, const vr_sequence* seqs, vr_session** out) {
+    if (n_seq <= 0 || !trackers || !estimators || !seqs || !out) return -1;
+    auto* s = new vr_session;
+    s->seqs = std::vector<SeqState>(n_seq);
+    for (int k = 0; k < n_seq; k++) {
+        SeqState& q = s->seqs[k];
+        if (!trackers[k] || !estimators[k] || !seqs[k].images || !seqs[k].stamps || (seqs[k].n_imu > 0 && !seqs[k].imu_t)) {
+            delete s;
+            return -1;
+        }
+        q.trk = trackers[k];
+        q.est = estimators[k];
+        q.in = seqs[k];
+        q.states.assign(16 * 65, 0.0);  // window_size + 1 <= 65 rows
+    }
+    *out = s;
+    return 0;
+}
+
+void vr_close(vr_session* s) { delete s; }
+
+const char* vr_last_error(const vr_session* s) { return s ? s->error.c_str() : "null session"; }
+
+int vr_advance(vr_session* s, int n_pub) {
+    if (!s || n_pub < 0) return -1;
+    if (s->status.load() != 0) return s->status.load();
+    std::vector<int> before(s->seqs.size());
+    std::vector<std::thread> threads;
+    for (size_t k = 0; k < s->seqs.size(); k++) {
+        before[k] = s->seqs[k].frames;
+        threads.emplace_back(tracker_loop, s, &s->seqs[k], n_pub);
+        threads.emplace_back(estimator_loop, s, &s->seqs[k]);
+    }
+    for (auto& t : threads) t.join();
+    if (s->status.load() != 0) return s->status.load();
+    int total = 0;
+    for (size_t k = 0; k < s->seqs.size(); k++) total += s->seqs[k].frames - before[k];
+    return total;
+}
+
+int vr_stats(const vr_session* s, int seq, int* frames, long long* launches, double* h2d_bytes, double* d2h_bytes) {
+    if (!s || seq < 0 || seq >= (int)s->seqs.size()) return -1;
+    const SeqState& q = s->seqs[seq];
+    if (frames) *frames = q.frames;
+    if (launches) *launches = q.launches;
+    if (h2d_bytes) *h2d_bytes = q.h2d;
+    if (d2h_bytes) *d2h_bytes = q.d2h;
+    return 0;
+}
+
+int vr_trajectory(const vr_session* s, int seq, int cap, double* stamps, double* positions3) {
+    if (!s || seq < 0 || seq >= (int)s->seqs.size()) return -1;
+    const SeqState& q = s->seqs[seq];
+    const int n = (int)q.traj_t.size();
+    for (int k = 0; k < n && k < cap; k++) {
+        if (stamps) stamps[k] = q.traj_t[k];
+        if (positions3)
+            for (int c = 0; c < 3; c++) positions3[3 * k + c] = q.traj_p[3 * (size_t)k + c];
+    }
+    return n;
+}
+
+}  // extern "C"
