@@ -16,7 +16,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -70,35 +69,57 @@ class _Recorder:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons polled through NVML (every ~2 ms) while a pass runs; the reported figures use the
+    samples that fall inside the timed region (SoloGate marks its begin / end)."""
 
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop_flag, self.thread = index, [], threading.Event(), None
+        self.t_begin = self.t_end = None
+        self.max_mhz = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES-agnostic lookup is not needed: one process per GPU with LOCAL_RANK == device index
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # no NVML: report nothing rather than fail the bench
+            return
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        def poll():
+            while not self.stop_flag.is_set():
+                try:
+                    mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    why = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.rows.append((time.perf_counter(), float(mhz), int(why)))
+                except Exception:
+                    pass
+                time.sleep(0.002)
+
+        self.thread = threading.Thread(target=poll, daemon=True)
+        self.thread.start()
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(1.0)
+        rows = self.rows
+        if self.t_begin is not None and self.t_end is not None:
+            inside = [r for r in rows if self.t_begin <= r[0] <= self.t_end]
+            rows = inside or rows
+        sm = [r[1] for r in rows]
+        reasons = sorted({name for r in rows for bit, name in self.REASONS.items() if r[2] & bit})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "source": "NVML, polled every 2 ms inside the timed region"}
 
 
 def make_gpu_pair(device):
@@ -148,9 +169,9 @@ class TwoStage:
 class SoloGate:
     """Brackets the timed region of ONE sequence: device drained, L2 evicted, optional cross-rank barrier, CUDA events."""
 
-    def __init__(self, device, flush=None, sync_cb=None):
+    def __init__(self, device, flush=None, sync_cb=None, clocks=None):
         import torch
-        self.torch, self.device, self.flush, self.sync_cb = torch, device, flush, sync_cb
+        self.torch, self.device, self.flush, self.sync_cb, self.clocks = torch, device, flush, sync_cb, clocks
         self.ev0, self.ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def begin(self):
@@ -159,17 +180,21 @@ class SoloGate:
         self.torch.cuda.synchronize(self.device)
         if self.sync_cb:
             self.sync_cb()
+        if self.clocks:
+            self.clocks.mark_begin()
         self.ev0.record()
 
     def end(self):
         self.torch.cuda.synchronize(self.device)  # includes the last frame's (asynchronous) marginalisation
         self.ev1.record()
         self.ev1.synchronize()
+        if self.clocks:
+            self.clocks.mark_end()
         return self.ev0.elapsed_time(self.ev1)
 
 
 def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images, profile=False, flush=None, sync_cb=None,
-                  gate=None, d_imgs=None):
+                  gate=None, d_imgs=None, clocks=None):
     """One pass over the sequence.  The K timed steps form ONE region bracketed by device synchronisation and a pair of
     CUDA events (ms per step = region / K); sync_cb, if given, is the cross-rank barrier placed inside the bracket.
     Tracker and estimator handles are driven from two host threads (TwoStage); with profile=True they run serially."""
@@ -187,7 +212,7 @@ def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images
             d_imgs = torch.from_numpy(imgs).to(f"cuda:{device}")
         base = d_imgs.data_ptr()
     if gate is None:
-        gate = SoloGate(device, flush, sync_cb)
+        gate = SoloGate(device, flush, sync_cb, clocks)
     launches, h2d, d2h, traj_t, traj_p = 0, 0.0, 0.0, [], []
     n_img = len(ts)
     cursor = [0]
@@ -408,6 +433,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keeps NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     seq, ts, imgs, imu = sequence_inputs(shard.sequences_of_rank(rank, world, 1)[0], n_pub)
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=f"cuda:{local}")  # 256 MB > 126 MB L2
@@ -425,7 +452,8 @@ def main():
     barrier()
     clocks.start()
     rank_barrier = (lambda: dist.barrier()) if world > 1 else None
-    res_dev = run_ours_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, a.steps, local, host_images=False, flush=flush, sync_cb=rank_barrier)
+    res_dev = run_ours_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, a.steps, local, host_images=False, flush=flush, sync_cb=rank_barrier,
+                            clocks=clocks)
     barrier()
     clk = clocks.stop()
     barrier()

@@ -22,7 +22,7 @@ def quat_angle(a, b):
     return 2 * np.arccos(np.clip(d, -1, 1))
 
 
-def run_both(seq, msgs, cfg_kw=None, gpu_kw=None, check_prior=True):
+def run_both(seq, msgs, cfg_kw=None, gpu_kw=None, check_prior=True, cost_rel=1e-3):
     cfg_kw, gpu_kw = cfg_kw or {}, gpu_kw or {}
     cpu, gpu = orc.OracleEstimator(orc.be_config(**cfg_kw)), make_gpu(**gpu_kw)
     t_imu, acc, gyr = seq.imu()
@@ -54,7 +54,7 @@ def run_both(seq, msgs, cfg_kw=None, gpu_kw=None, check_prior=True):
         # directions; the smallest retained lambda_k are round-off (the prior is rank deficient in the 4 gauge
         # directions and the reference keeps whatever lands above eps = 1e-8), so only cost *decreases* are comparable.
         da, db_ = ia["initial_cost"] - ia["final_cost"], ib["initial_cost"] - ib["final_cost"]
-        assert abs(da - db_) <= 2e-2 + 1e-3 * abs(da), (stamp, da, db_, ia, ib)
+        assert abs(da - db_) <= 2e-2 + cost_rel * abs(da), (stamp, da, db_, ia, ib)
         if check_prior:
             Aa, ba_, blka = cpu.prior()
             Ab, bb_, blkb = gpu.prior()
@@ -108,3 +108,43 @@ def test_estimator_trajectory_error():
     ate_g, ate_c = pipeline.ate_rmse(seq, res["t"], res["P"]), pipeline.ate_rmse(seq, ref["t"], ref["P"])
     print("ATE rmse gpu", ate_g, "cpu oracle", ate_c)
     assert ate_g < 0.05 and abs(ate_g - ate_c) <= 0.01 * max(ate_c, 1e-3) + 1e-6    # within 1 % of the CPU path
+
+
+def test_estimator_margin_second_new_path():
+    """30 Hz feature messages: the parallax test (feature_manager.cpp:46-79) rejects most frames as keyframes, so
+    optimization() takes the MARGIN_SECOND_NEW branch (estimator.cpp:929-1002: prior-only marginalisation of the
+    second-newest pose, slideWindowNew with merged pre-integration) interleaved with MARGIN_OLD."""
+    seq = synth.Sequence(seed=14, duration=4.0)
+    msgs = synth.track_messages(seq, 60, pub_hz=30.0)
+    flags = []
+    worst, n_nl, cpu, gpu = run_both(seq, msgs)
+    print("worst deviations (mixed marginalisation)", worst, "frames", n_nl)
+    assert n_nl >= 40
+    for k, tol in TOL.items():
+        assert worst[k] <= tol, (k, worst)
+
+
+def test_estimator_feature_dropouts_and_capacity():
+    """Frames with no or very few features in the middle of a sequence (tracking loss: every landmark of the window
+    loses its newest observation, estimator.cpp:120-150 still optimises with IMU + prior), and the landmark capacity
+    bound (NUM_OF_F, estimator.h:111) turned into an error instead of an overflow."""
+    seq = synth.Sequence(seed=15, duration=5.0)
+    msgs = synth.track_messages(seq, 36)
+    for k in (20, 21):                                   # two consecutive frames without a single feature
+        msgs[k] = (msgs[k][0], np.zeros(0, np.int32), np.zeros((0, 7)))
+    s, ids, d = msgs[27]
+    msgs[27] = (s, ids[:5].copy(), d[:5].copy())         # five features only
+    # after the outage the window is re-linearised far from its optimum (costs in the thousands, every step at the trust
+    # region boundary): summation-order noise is amplified more than in steady state, hence the wider cost tolerance
+    worst, n_nl, cpu, gpu = run_both(seq, msgs, check_prior=False, cost_rel=2e-2)
+    print("worst deviations (dropouts)", worst, "frames", n_nl)
+    for k, tol in TOL.items():
+        assert worst[k] <= 10 * tol, (k, worst)
+    small = make_gpu(max_features=40)
+    small.set_seed(pipeline.gt_seed_rows(seq, [m[0] for m in msgs]), seq.ba, seq.bg)
+    fb = pipeline.ImuFeeder(*seq.imu())
+    clean = synth.track_messages(seq, 14)
+    with pytest.raises(RuntimeError):
+        for stamp, ids, d in clean:
+            fb.feed(small, stamp)
+            small.processImage(ids, d, stamp)

@@ -132,3 +132,60 @@ def test_full_size_properties(FT):
             p = np.rint(res["cur_pts"]).astype(int)
             d = np.abs(p[:, None, :] - p[None, :, :]).max(-1) + np.eye(len(p), dtype=int) * 1000
             assert d.min() >= 15  # discs of radius 30 keep rounded points apart (Chebyshev >= 21 on the raster)
+
+
+def _same_result(gpu, cpu, tag):
+    a, b = gpu.result(), cpu.result()
+    for k in ("ids", "track_cnt"):
+        assert np.array_equal(a[k], b[k]), f"{tag} {k}"
+    for k in ("cur_pts", "un_pts", "velocity"):
+        assert np.array_equal(a[k].view(np.int32), b[k].view(np.int32)), f"{tag} {k}"
+    return a
+
+
+def test_tracker_edge_cases_match_oracle(FT):
+    """The gating and bookkeeping branches of img_callback / readImage the plain sequence never takes
+    (feature_tracker_node.cpp:36-62, feature_tracker.cpp:106-128, 169-173): frames without any corner, every track lost
+    at once (ids keep counting), fewer than 8 tracked points (rejectWithF skipped), a time jump (restart published,
+    tracker state dropped), a backwards stamp, and recovery afterwards.  Everything bit-identical to the CPU oracle."""
+    cfg = synth.tracker_config_dict()
+    gpu, cpu = FT(**cfg), orc.OracleTracker(cfg)
+    rows, cols = cfg["rows"], cfg["cols"]
+    tex = synth.value_noise_image(rows, cols, seed=21)
+    tex2 = synth.value_noise_image(rows, cols, seed=22)
+    flat = np.full((rows, cols), 128, np.uint8)
+    sparse = np.full((rows, cols), 90, np.uint8)           # five isolated blobs: < 8 trackable points
+    for cy, cx in ((100, 120), (200, 500), (350, 300), (420, 650), (60, 700)):
+        sparse[cy - 6:cy + 6, cx - 6:cx + 6] = 220
+    shift = lambda im, dx: np.ascontiguousarray(np.roll(im, dx, axis=1))
+    frames = []
+    t = 10.0
+    def add(img, dt=0.05):
+        nonlocal t
+        t += dt
+        frames.append((img, t))
+    for k in range(6):
+        add(shift(tex, 2 * k))                              # normal tracking
+    for k in range(3):
+        add(flat)                                           # nothing to track, nothing to detect
+    for k in range(4):
+        add(shift(tex2, 3 * k))                             # all-new features after a total loss
+    for k in range(5):
+        add(shift(sparse, k))                               # < 8 points: the F-matrix test is skipped
+    add(shift(tex, 0), dt=1.5)                              # stamp jumps by > 1 s: restart
+    for k in range(1, 4):
+        add(shift(tex, 2 * k))
+    add(shift(tex, 8), dt=-0.2)                             # stamp goes backwards: restart as well
+    for k in range(5, 9):
+        add(shift(tex, 2 * k))
+    seen_restart, max_id = 0, -1
+    for i, (img, stamp) in enumerate(frames):
+        rg, sg = gpu.node_image(img, stamp)
+        rc, sc = cpu.node_image(img, stamp)
+        assert (rg, sg) == (rc, sc), f"frame {i}"
+        seen_restart += int(sc)
+        if rc:
+            a = _same_result(gpu, cpu, f"frame {i}")
+            if len(a["ids"]):
+                max_id = max(max_id, int(a["ids"].max()))
+    assert seen_restart == 2 and max_id > 150

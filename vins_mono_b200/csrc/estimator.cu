@@ -932,6 +932,9 @@ int ve_create(const ve_config* cfg, ve_estimator** out) {
     if (cfg->window_size < 3 || cfg->window_size + 1 > vb::BA_MAX_FRAMES || cfg->window_size + 1 > vb::BA_MAX_OBS_PER_LM ||
         cfg->max_features < 8 || cfg->num_iterations < 1 || cfg->estimate_extrinsic > 1)
         return VE_ERR_INVALID;
+    // the marginalisation kernel keeps the prior (6 W + 9 + 6 + 1 parameters) and its eigen-solver work arrays in the
+    // shared memory of one CTA: up to 96 parameters, i.e. WINDOW_SIZE <= 13 (the reference ships 10)
+    if (6 * cfg->window_size + 16 > 96) return VE_ERR_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) return VE_ERR_NO_DEVICE;
     ve_estimator* e = new ve_estimator();
