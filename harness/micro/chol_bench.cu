@@ -18,18 +18,24 @@ __global__ void __launch_bounds__(512) chol_bench_kernel(const double* Ain, int 
     long long total = 0, tsolve = 0;
     for (int r = 0; r < reps; r++) {
         for (int i = threadIdx.x; i < np; i += blockDim.x) Lp[i] = Ain[i];
+        for (int i = threadIdx.x; i <= n; i += blockDim.x) Lp[np + i] = i < n ? 1.0 + i : 0.0;
         for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = 1.0 + i;
         __syncthreads();
         const long long t0 = clock64();
-        cholesky_packed(Lp, Pc, n, rdiag, linv, &flag);
+        cholesky_packed(Lp, Pc, n, rdiag, linv, &flag, n + 1);
         const long long t1 = clock64();
-        if (mode) chol_solve_packed(Lp, linv, n, y);
+        if (mode) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = Lp[np + i];
+            __syncthreads();
+            chol_solve_packed(Lp, linv, n, y, false);
+        }
         __syncthreads();
         const long long t2 = clock64();
         total += t1 - t0;
         tsolve += t2 - t1;
     }
     for (int i = threadIdx.x; i < np; i += blockDim.x) Lout[i] = Lp[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) Lout[np + i] = y[i];
     if (threadIdx.x == 0) {
         for (int k = 0; k < 8; k++) clk[k] = chol_clk[k] / reps;
         clk[8] = total / reps;
@@ -58,19 +64,25 @@ int main(int argc, char** argv) {
         for (int i = j; i < n; i++) L[i * n + j] /= d;
     }
     double *dA, *dL; long long* dclk;
-    cudaMalloc(&dA, np * 8); cudaMalloc(&dL, np * 8); cudaMalloc(&dclk, 16 * 8);
+    cudaMalloc(&dA, np * 8); cudaMalloc(&dL, (np + n) * 8); cudaMalloc(&dclk, 16 * 8);
     cudaMemcpy(dA, Ap.data(), np * 8, cudaMemcpyHostToDevice);
-    const int dynb = (np + CHOL_NB * CHOL_PS) * 8;
+    const int dynb = (np + n + 1 + CHOL_NB * CHOL_PS) * 8;
     cudaFuncSetAttribute(chol_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dynb);
     chol_bench_kernel<<<1, 512, dynb>>>(dA, n, reps, dL, dclk, 1);
     cudaDeviceSynchronize();
     printf("launch: %s\n", cudaGetErrorString(cudaGetLastError()));
-    std::vector<double> Lg(np); long long clk[16];
-    cudaMemcpy(Lg.data(), dL, np * 8, cudaMemcpyDeviceToHost);
+    std::vector<double> Lg(np + n); long long clk[16];
+    cudaMemcpy(Lg.data(), dL, (np + n) * 8, cudaMemcpyDeviceToHost);
     cudaMemcpy(clk, dclk, 16 * 8, cudaMemcpyDeviceToHost);
     double err = 0;
     for (int i = 0; i < n; i++) for (int j = 0; j <= i; j++) err = fmax(err, fabs(Lg[i * (i + 1) / 2 + j] - L[i * n + j]));
-    printf("n=%d ok=%lld max|L-Lref|=%.3e\n", n, clk[10], err);
+    // reference solution of A y = b, b_i = 1 + i
+    std::vector<double> yr(n);
+    for (int i = 0; i < n; i++) { double v = 1.0 + i; for (int k = 0; k < i; k++) v -= L[i * n + k] * yr[k]; yr[i] = v / L[i * n + i]; }
+    for (int i = n - 1; i >= 0; i--) { double v = yr[i]; for (int k = i + 1; k < n; k++) v -= L[k * n + i] * yr[k]; yr[i] = v / L[i * n + i]; }
+    double yerr = 0, ymax = 0;
+    for (int i = 0; i < n; i++) { yerr = fmax(yerr, fabs(Lg[np + i] - yr[i])); ymax = fmax(ymax, fabs(yr[i])); }
+    printf("n=%d ok=%lld max|L-Lref|=%.3e  max|y-yref|/|y|=%.3e\n", n, clk[10], err, yerr / ymax);
     const char* names[] = {"diag: load+update", "diag: factor chain", "diag: store", "loop top", "panel", "sync after panel", "warp0 diag total/others tiles", "sync after trailing"};
     for (int k = 0; k < 8; k++) printf("  %-34s %9lld cycles\n", names[k], clk[k]);
     printf("  cholesky total %lld, solve total %lld cycles\n", clk[8], clk[9]);

@@ -9,7 +9,10 @@ from harness import synth, pipeline
 
 pytestmark = pytest.mark.gpu
 
-TOL = dict(p=1e-4, q=1e-4, v=1e-4, ba=1e-4, bg=1e-5)   # m, rad, m/s, m/s^2, rad/s  (SURVEY §8d proposal: 1e-3 .. 1e-4)
+# m, rad, m/s, m/s^2, rad/s.  SURVEY §8d proposes 1e-3 (1e-4 for bg) "tighten after measuring": measured over repeated
+# runs (the fp64 atomics make every run different) the worst window-state deviation is 1e-5 .. 5e-5 in steady state, so
+# the gate is 3e-4 (3e-5 for bg), never above the survey's figure even where a test multiplies it.
+TOL = dict(p=3e-4, q=3e-4, v=3e-4, ba=3e-4, bg=3e-5)
 
 
 def make_gpu(**kw):
@@ -94,7 +97,7 @@ def test_estimator_td_and_extrinsic_blocks():
     worst, n_nl, cpu, gpu = run_both(seq, msgs, cfg_kw=dict(tr=0.0, **kw), gpu_kw=dict(tr=0.0, **kw))
     print("worst deviations (td + extrinsic)", worst, "frames", n_nl)
     for k, tol in TOL.items():
-        assert worst[k] <= 10 * tol, (k, worst)
+        assert worst[k] <= 2 * tol, (k, worst)
     assert abs(cpu.states()[1] - gpu.states()[1]) < 1e-5
 
 
@@ -139,7 +142,7 @@ def test_estimator_feature_dropouts_and_capacity():
     worst, n_nl, cpu, gpu = run_both(seq, msgs, check_prior=False, cost_rel=2e-2)
     print("worst deviations (dropouts)", worst, "frames", n_nl)
     for k, tol in TOL.items():
-        assert worst[k] <= 10 * tol, (k, worst)
+        assert worst[k] <= 3 * tol, (k, worst)
     small = make_gpu(max_features=40)
     small.set_seed(pipeline.gt_seed_rows(seq, [m[0] for m in msgs]), seq.ba, seq.bg)
     fb = pipeline.ImuFeeder(*seq.imu())

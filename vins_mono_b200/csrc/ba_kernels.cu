@@ -553,8 +553,27 @@ __device__ __forceinline__ double lm_inv_lambda(const BaProblem& p, const BaAccu
 
 __global__ void __launch_bounds__(ST* ST) ba_schur_kernel(BaProblem p) {
     const SolverState* st = p.st;
-    if (st->done || st->reuse) return;
-    if (blockIdx.y > blockIdx.x) return;  // upper tiles only
+    if (st->done) return;
+    if (blockIdx.y > blockIdx.x) {
+        // The product needs the upper tiles only; the CTAs of the lower triangle clear the accumulators the next
+        // linearisation (of the candidate point) adds into, which saves a launch per iteration.
+        const BaAccum z = p.acc[1 - st->cur];
+        const int D = p.dims.D, L = p.dims.L;
+        const int nlow = gridDim.x * (gridDim.x - 1) / 2;
+        const int lin = blockIdx.y * (blockIdx.y - 1) / 2 + blockIdx.x;  // 0 .. nlow-1
+        const size_t n1 = (size_t)D * D, n2 = (size_t)L * D, total = n1 + n2 + D + 2 * (size_t)L + 1;
+        const size_t stride = (size_t)nlow * ST * ST;
+        for (size_t i = (size_t)lin * ST * ST + threadIdx.y * ST + threadIdx.x; i < total; i += stride) {
+            if (i < n1) z.Hpp[i] = 0.0;
+            else if (i < n1 + n2) z.Hpl[i - n1] = 0.0;
+            else if (i < n1 + n2 + D) z.gp[i - n1 - n2] = 0.0;
+            else if (i < n1 + n2 + D + L) z.Hll[i - n1 - n2 - D] = 0.0;
+            else if (i < n1 + n2 + D + 2 * (size_t)L) z.gl[i - n1 - n2 - D - L] = 0.0;
+            else z.cost[0] = 0.0;
+        }
+        return;
+    }
+    if (st->reuse) return;
     __shared__ double As[ST][ST + 1], Bs[ST][ST + 1], inv[ST], gls[ST];
     const BaAccum a = p.acc[st->cur];
     const int D = p.dims.D, L = p.dims.L;
@@ -651,7 +670,7 @@ __shared__ long long chol_clk[8];
 // is rsqrt -> scale -> one FMA (one row per lane with shuffled pivots/multipliers measured 2.6k cycles per block for
 // the chain alone, this form 1.1k; harness/micro/chol_bench.cu).  Rows >= w behave like identity rows.
 __device__ __forceinline__ void chol_diag_block(double* Lp, const double* Pc, int kb, int w, double* rdiag,
-                                                double (*dblk)[CHOL_NB + 1], int* flag, int upd, double* stage) {
+                                                double (*dblk)[CHOL_NB + 1], int* flag, int upd, double* stage, int nrows) {
     const int lane = threadIdx.x & 31;
     CP_BEGIN();
 #pragma unroll
@@ -669,6 +688,12 @@ __device__ __forceinline__ void chol_diag_block(double* Lp, const double* Pc, in
                 }
                 v -= acc0 + acc1;
             }
+        } else if (upd && rr >= w && kb + rr < nrows && c < w) {
+            // a row below a partial last block (the appended right-hand-side row): it only receives the update
+            double acc0 = 0.0;
+#pragma unroll
+            for (int t = 0; t < CHOL_NB; t++) acc0 += Pc[t * CHOL_PS + kb + rr] * Pc[t * CHOL_PS + kb + c];
+            Lp[(kb + rr) * (kb + rr + 1) / 2 + kb + c] -= acc0;
         }
         stage[e] = v;
     }
@@ -746,49 +771,56 @@ __device__ __forceinline__ void chol_tile84(double* Lp, const double* Pc, int n,
 }
 
 // Pc: CHOL_NB * CHOL_PS doubles of 16-byte aligned shared memory (current panel, column-major, rows >= n zero).
-__device__ bool cholesky_packed(double* Lp, double* Pc, int n, double* rdiag, double* linv, int* flag) {
+// nrows >= n: rows n .. nrows-1 of the packed array are carried along without being factorised (row n = a right-hand
+// side b turns into L^-1 b, i.e. the forward substitution comes for free with the trailing updates).
+__device__ bool cholesky_packed(double* Lp, double* Pc, int n, double* rdiag, double* linv, int* flag, int nrows) {
     __shared__ double dblk[CHOL_NB][CHOL_NB + 1], stage[CHOL_NB * CHOL_NB];
     const int tid = threadIdx.x, nt = blockDim.x;
     if (tid == 0) *flag = 1;
     for (int c = 0; c < CHOL_NB; c++)
-        for (int i = n + tid; i < CHOL_PS; i += nt) Pc[c * CHOL_PS + i] = 0.0;
+        for (int i = nrows + tid; i < CHOL_PS; i += nt) Pc[c * CHOL_PS + i] = 0.0;
     __syncthreads();
-    if (tid < 32) chol_diag_block(Lp, Pc, 0, min(CHOL_NB, n), rdiag, dblk, flag, 0, stage);
+    if (tid < 32) chol_diag_block(Lp, Pc, 0, min(CHOL_NB, n), rdiag, dblk, flag, 0, stage, nrows);
     __syncthreads();
     CP_BEGIN();
     for (int kb = 0; kb < n; kb += CHOL_NB) {
-        const int ke = kb + CHOL_NB;  // a block with a panel below it is always full
+        const int w = min(CHOL_NB, n - kb), ke = kb + w;  // only the last block can be partial
         if (!*flag) return false;
-        if (ke >= n) break;
+        if (ke >= nrows) break;
         CP(3);
         // panel: rows below the diagonal block, forward substitution against it
-        for (int i = ke + tid; i < n; i += nt) {
+        for (int i = ke + tid; i < nrows; i += nt) {
             double x[CHOL_NB];
             const int ib = i * (i + 1) / 2 + kb;
 #pragma unroll
             for (int c = 0; c < CHOL_NB; c++) {
-                double v = Lp[ib + c];
+                double v = 0.0;
+                if (c < w) {
+                    v = Lp[ib + c];
 #pragma unroll
-                for (int t = 0; t < c; t++) v -= x[t] * dblk[c][t];
-                x[c] = v * rdiag[kb + c];
-                Lp[ib + c] = x[c];
-                Pc[c * CHOL_PS + i] = x[c];
+                    for (int t = 0; t < c; t++) v -= x[t] * dblk[c][t];
+                    v *= rdiag[kb + c];
+                    Lp[ib + c] = v;
+                }
+                x[c] = v;
+                Pc[c * CHOL_PS + i] = v;
             }
         }
         CP(4);
         __syncthreads();
         CP(5);
+        if (ke >= n) break;  // nothing left to factorise (the carried rows are complete)
         // warp 0: next diagonal block (update + factorisation); the others: every other trailing tile.  Tile row
         // ti8 holds the column tiles tj4 = 0 .. 2 ti8 + 1 (t = ti8 (ti8 + 1) + tj4); t = 0, 1 are the diagonal block.
         if (tid < 32) {
-            chol_diag_block(Lp, Pc, ke, min(CHOL_NB, n - ke), rdiag, dblk, flag, 1, stage);
+            chol_diag_block(Lp, Pc, ke, min(CHOL_NB, n - ke), rdiag, dblk, flag, 1, stage, nrows);
         } else {
-            const int m = n - ke, nr8 = (m + 7) / 8, ntiles = nr8 * (nr8 + 1);
+            const int m = nrows - ke, nr8 = (m + 7) / 8, ntiles = nr8 * (nr8 + 1);
             for (int t = 2 + tid - 32; t < ntiles; t += nt - 32) {
                 int ti8 = (int)((sqrtf(4.f * (float)t + 1.f) - 1.f) * 0.5f);
                 while (ti8 * (ti8 + 1) > t) ti8--;
                 while ((ti8 + 1) * (ti8 + 2) <= t) ti8++;
-                chol_tile84(Lp, Pc, n, ke, ti8, t - ti8 * (ti8 + 1));
+                chol_tile84(Lp, Pc, nrows, ke, ti8, t - ti8 * (ti8 + 1));
             }
         }
         CP(6);
@@ -826,9 +858,9 @@ __device__ bool cholesky_packed(double* Lp, double* Pc, int n, double* rdiag, do
 // Solves L L^T y = b with the packed factor; y (in/out) in shared memory, all threads of the CTA take part.
 // Blocked by 8: the 8x8 triangular block is applied through its precomputed inverse (8 lanes, independent dot
 // products), the remaining rows are updated with 8 columns at once by one thread per row.
-__device__ void chol_solve_packed(const double* Lp, const double* linv, int n, double* y) {
+__device__ void chol_solve_packed(const double* Lp, const double* linv, int n, double* y, bool forward = true) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int kb = 0; kb < n; kb += CHOL_NB) {  // forward: L z = b
+    for (int kb = 0; forward && kb < n; kb += CHOL_NB) {  // forward: L z = b
         const int w = min(CHOL_NB, n - kb), ke = kb + w;
         if (tid < 32) {
             double v = 0.0;
@@ -944,6 +976,7 @@ __global__ void __launch_bounds__(512) ba_step_kernel(BaProblem p, int use_smem_
         const int npk = D * (D + 1) / 2;
         while (mu < 1.0) {
             for (int idx = tid; idx < npk; idx += nt) Lp[idx] = p.Spk[idx];
+            for (int j = tid; j <= D; j += nt) Lp[npk + j] = j < D ? p.gred[j] : 0.0;  // row D: the right-hand side
             __syncthreads();
             for (int i = tid; i < D; i += nt) {
                 const double s_ = p.scale[i];
@@ -951,7 +984,7 @@ __global__ void __launch_bounds__(512) ba_step_kernel(BaProblem p, int use_smem_
             }
             __syncthreads();
             STAMP(2);
-            const bool ok_ = cholesky_packed(Lp, chol_smem, D, rdiag, linv, &flag);
+            const bool ok_ = cholesky_packed(Lp, chol_smem, D, rdiag, linv, &flag, D + 1);
             STAMP(3);
             if (ok_) {
                 linear_ok = true;
@@ -963,9 +996,9 @@ __global__ void __launch_bounds__(512) ba_step_kernel(BaProblem p, int use_smem_
             if (mu < 1.0) reduce_single_cta(p, a, mu, first);
         }
         if (linear_ok) {
-            for (int j = tid; j < D; j += nt) ysm[j] = p.gred[j];
+            for (int j = tid; j < D; j += nt) ysm[j] = Lp[npk + j];  // L^-1 gred, carried through the factorisation
             __syncthreads();
-            chol_solve_packed(Lp, linv, D, ysm);
+            chol_solve_packed(Lp, linv, D, ysm, false);
             __syncthreads();
             STAMP(4);
             for (int j = tid; j < D; j += nt) y[j] = ysm[j];
@@ -1462,7 +1495,7 @@ size_t marg_solve_smem_bytes(int m_dense, int n) {
 // launch wrappers
 namespace vb {
 
-size_t ba_work_doubles(int D, int L) { return 4 * (size_t)(D + L) + (size_t)D * (D + 1) / 2; }
+size_t ba_work_doubles(int D, int L) { return 4 * (size_t)(D + L) + (size_t)(D + 1) * (D + 2) / 2; }
 
 void launch_preint_push(PreInt* slot, int n, const double* d_samples, double acc_n, double gyr_n, double acc_w, double gyr_w,
                         cudaStream_t s) {
@@ -1494,7 +1527,7 @@ void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int
     const int zero_grid = 64;
     const int tiles = (d.D + ST - 1) / ST;
     const size_t panel_bytes = sizeof(double) * CHOL_NB * CHOL_PS;
-    const size_t chol_bytes = sizeof(double) * (size_t)d.D * (d.D + 1) / 2 + panel_bytes;
+    const size_t chol_bytes = sizeof(double) * (size_t)(d.D + 1) * (d.D + 2) / 2 + panel_bytes;
     static std::mutex cfg_mutex;  // handles on different host threads share the per-function attributes
     std::unique_lock<std::mutex> cfg_lock(cfg_mutex);
     static int smem_limit = -1, smem_static = 0, smem_configured = 0;
@@ -1528,13 +1561,16 @@ void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int
         prof->begin(s);
         ba_step_kernel<<<1, 512, step_dyn, s>>>(p, use_smem);
         prof->end(2, s);
-        prof->begin(s);
-        ba_zero_kernel<<<zero_grid, 256, 0, s>>>(p, 0);
-        prof->end(3, s);
+        if (tiles < 2) {  // no lower-triangle CTA to do the clearing (never at the supported window sizes)
+            prof->begin(s);
+            ba_zero_kernel<<<zero_grid, 256, 0, s>>>(p, 0);
+            prof->end(3, s);
+            n += 1;
+        }
         prof->begin(s);
         ba_linearize_kernel<<<lin_grid, 32 * LIN_WARPS, 0, s>>>(p, 0);
         prof->end(0, s);
-        n += 4;
+        n += 3;
     }
     if (launches) *launches += n;
 }
