@@ -59,9 +59,9 @@ int main(int argc, char** argv) {
         }
         printf("threads %d: %s  |AV-VW|/|A| = %.2e  |VtV-I| = %.2e   total %lld cycles (tridiag %lld, QL %lld)\n", threads,
                cudaGetErrorString(cudaGetLastError()), res / amax, orth, clk[16], clk[17], clk[18]);
-        const char* names[] = {"tred2 scalar (scale, h)", "tred2 matvec", "tred2 scalar (e/h, f)", "tred2 rank-2 update", "tred2 row copy",
-                               "accum d = V/h", "accum dots", "accum update+zero", "QL search/bookkeeping", "QL wait for consumers", "QL sweep recurrence"};
-        for (int k = 0; k < 11; k++) printf("    %-28s %9lld\n", names[k], clk[k]);
+        const char* names[] = {"tred2 A: matvec || |u|^2, scalars", "tred2 B: fix, scale, p -= f/2h u", "tred2 C: rank-2 update, next u", "(unused)", "(unused)",
+                               "(unused)", "accum dots", "accum update + zero column", "QL search/bookkeeping", "QL wait for consumers", "QL sweep recurrence"};
+        for (int k = 0; k < 11; k++) printf("    %-34s %9lld\n", names[k], clk[k]);
     }
     return 0;
 }

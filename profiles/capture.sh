@@ -15,5 +15,7 @@ $FULL -k regex:ba_step -s 20 -c 1 -o gpurun_out/${R}_ba_step python harness/debu
 $FULL -k "regex:ba_linearize|ba_schur|marg_build|preint_push" -s 40 -c 8 -o gpurun_out/${R}_ba_small python harness/debug_backend.py 16 > gpurun_out/${R}_ncu_small.log 2>&1
 $FULL -k regex:lk_track -s 12 -c 1 -o gpurun_out/${R}_lk_track python harness/run_tracker.py --frames 24 > gpurun_out/${R}_ncu_lk.log 2>&1
 $FULL -k "regex:clahe|pyrdown|min_eig|gftt|sort_keys|mask_discs" -s 60 -c 9 -o gpurun_out/${R}_fe_small python harness/run_tracker.py --frames 24 > gpurun_out/${R}_ncu_fe.log 2>&1
+# 3. microbenchmarks that sized the single-CTA solvers (cycle counters, not wall clock)
+for b in lat chol_bench eig_bench; do [ -x harness/micro/$b ] && harness/micro/$b > gpurun_out/${R}_micro_$b.txt 2>&1; done
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_event_reasons.active --format=csv > gpurun_out/${R}_clocks.csv
 ls -la gpurun_out/

@@ -137,7 +137,7 @@ if __name__ == "__main__":
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r1"
     launches(rnd)
     full_captures(rnd)
-    for f in (f"{rnd}_clocks.csv",):
+    for f in (f"{rnd}_clocks.csv", f"{rnd}_micro_lat.txt", f"{rnd}_micro_chol_bench.txt", f"{rnd}_micro_eig_bench.txt"):
         src = os.path.join(SCRATCH, f)
         if os.path.exists(src):
             open(os.path.join(OUT, f), "w").write(open(src).read())

@@ -406,25 +406,35 @@ __device__ __forceinline__ bool imu_whitened(const BaProblem& p, const BaStates&
     return true;
 }
 
-__device__ __forceinline__ void lin_imu(const BaProblem& p, const BaStates& x, const BaAccum& a, int k, int lane, double* Jraw,
-                                        double* Jw, double* rr, double* rw) {
-    if (!imu_whitened(p, x, k, lane, Jraw, Jw, rr, rw)) return;
+// One CTA per IMU factor: warp 0 evaluates and whitens the 15x30 Jacobian (shared memory), then every warp of the
+// CTA adds its share of the 30x30 product into the Hessian (the product was 29 serial passes for a single warp and,
+// with the prior, the critical path of the kernel).
+__device__ __forceinline__ void lin_imu(const BaProblem& p, const BaStates& x, const BaAccum& a, int k, double* Jraw, double* Jw,
+                                        double* rr, double* rw, int* valid) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    if (tid < 32) {
+        const bool ok = imu_whitened(p, x, k, lane, Jraw, Jw, rr, rw);
+        if (lane == 0) *valid = ok ? 1 : 0;
+    }
+    __syncthreads();
+    if (!*valid) return;
     const BaDims& d = p.dims;
     const int D = d.D;
-    if (lane == 0) {
+    if (tid == 0) {
         double c = 0;
         for (int q = 0; q < 15; q++) c += rw[q] * rw[q];
         atomicAdd(a.cost, 0.5 * c);
     }
-    for (int idx = lane; idx < 900; idx += 32) {
-        const int aa = idx / 30, bb = idx % 30;
+    for (int idx = tid; idx < 900; idx += nt) {
+        const int aa = idx / 30, bb = idx - aa * 30;
         const int ga = imu_col(d, k, aa), gb = imu_col(d, k, bb);
         if (ga > gb) continue;
         double s = 0;
+#pragma unroll
         for (int q = 0; q < 15; q++) s += Jw[q * 30 + aa] * Jw[q * 30 + bb];
         if (s != 0.0) atomicAdd(&a.Hpp[(size_t)ga * D + gb], s);
     }
-    if (lane < 30) {
+    if (tid >= nt - 32 && lane < 30) {  // the last warp: gradient
         double s = 0;
         for (int q = 0; q < 15; q++) s += Jw[q * 30 + lane] * rw[q];
         atomicAdd(&a.gp[imu_col(d, k, lane)], s);
@@ -478,11 +488,15 @@ __device__ void lin_prior(const BaProblem& p, const BaStates& x, const BaAccum& 
     prior_cols(p, col, tid, nt);
     __syncthreads();
     double part = 0;
-    for (int aa = tid; aa < n; aa += nt) {
-        double s = pr.g0[aa];
-        for (int bb = 0; bb < n; bb++) s += pr.A[(size_t)aa * n + bb] * dx[bb];
-        gpr[aa] = s;
-        part += dx[aa] * (pr.g0[aa] + s);
+    for (int aa = tid >> 5; aa < n; aa += nt >> 5) {  // a warp per row of A: coalesced reads, shuffle reduction
+        double s = 0;
+        for (int bb = tid & 31; bb < n; bb += 32) s += pr.A[(size_t)aa * n + bb] * dx[bb];
+        s = warp_sum_d(s);
+        if ((tid & 31) == 0) {
+            s += pr.g0[aa];
+            gpr[aa] = s;
+            part += dx[aa] * (pr.g0[aa] + s);
+        }
     }
     part = warp_sum_d(part);
     if ((tid & 31) == 0) red[tid >> 5] = part;
@@ -507,21 +521,21 @@ __device__ void lin_prior(const BaProblem& p, const BaStates& x, const BaAccum& 
 
 #define LIN_WARPS 4
 __global__ void __launch_bounds__(32 * LIN_WARPS) ba_linearize_kernel(BaProblem p, int initial) {
-    __shared__ double sJraw[LIN_WARPS][450], sJw[LIN_WARPS][450], srr[LIN_WARPS][15], srw[LIN_WARPS][15];
+    __shared__ double sJraw[450], sJw[450], srr[15], srw[15];
+    __shared__ int imu_valid;
     SolverState* st = p.st;
     if (!initial && (st->done || !st->cand_valid)) return;
     const int b = initial ? st->cur : 1 - st->cur;
     const BaStates x = p.x[b];
     const BaAccum a = p.acc[b];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int nb_vis = (p.dims.L + LIN_WARPS - 1) / LIN_WARPS, nb_imu = (p.dims.W + LIN_WARPS - 1) / LIN_WARPS;
+    const int nb_vis = (p.dims.L + LIN_WARPS - 1) / LIN_WARPS, nb_imu = p.dims.W;
     const int blk = blockIdx.x;
-    if (blk < nb_vis) {
-        const int l = blk * LIN_WARPS + wid;
+    if (blk < nb_imu) {  // the long CTAs first
+        lin_imu(p, x, a, blk, sJraw, sJw, srr, srw, &imu_valid);
+    } else if (blk < nb_imu + nb_vis) {
+        const int l = (blk - nb_imu) * LIN_WARPS + wid;
         if (l < p.dims.L) lin_visual(p, x, a, l, lane);
-    } else if (blk < nb_vis + nb_imu) {
-        const int k = (blk - nb_vis) * LIN_WARPS + wid;
-        if (k < p.dims.W) lin_imu(p, x, a, k, lane, sJraw[wid], sJw[wid], srr[wid], srw[wid]);
     } else {
         lin_prior(p, x, a);
     }
@@ -537,7 +551,7 @@ __global__ void __launch_bounds__(32 * LIN_WARPS) ba_linearize_kernel(BaProblem 
     }
 }
 
-int ba_linearize_grid(const BaDims& d) { return (d.L + LIN_WARPS - 1) / LIN_WARPS + (d.W + LIN_WARPS - 1) / LIN_WARPS + 1; }
+int ba_linearize_grid(const BaDims& d) { return (d.L + LIN_WARPS - 1) / LIN_WARPS + d.W + 1; }
 
 // ------------------------------------------------------------------------------------------------
 // Landmark elimination as a dense, deterministic tiled product:
@@ -582,15 +596,30 @@ __global__ void __launch_bounds__(ST* ST) ba_schur_kernel(BaProblem p) {
     const double mu = st->mu;
     const int first = st->first;
     double acc = 0, gacc = 0;
-    for (int l0 = 0; l0 < L; l0 += ST) {
+    // software pipelined: the global loads of chunk k+1 are in flight while chunk k is multiplied out of shared memory
+    // (a chunk is only 16 landmark rows; unpipelined, every chunk paid a full L2 round trip behind a barrier)
+    auto fetch = [&](int l0, double& va, double& vb, double& vi, double& vg) {
         const int l = l0 + ty;
-        As[ty][tx] = (l < L && r0 + tx < D) ? a.Hpl[(size_t)l * D + r0 + tx] : 0.0;
-        Bs[ty][tx] = (l < L && c0 + tx < D) ? a.Hpl[(size_t)l * D + c0 + tx] : 0.0;
+        va = (l < L && r0 + tx < D) ? a.Hpl[(size_t)l * D + r0 + tx] : 0.0;
+        vb = (l < L && c0 + tx < D) ? a.Hpl[(size_t)l * D + c0 + tx] : 0.0;
+        vi = 0.0;
+        vg = 0.0;
+        if (tx == 0 && l < L) {
+            vi = lm_inv_lambda(p, a, l, mu, first);
+            vg = a.gl[l];
+        }
+    };
+    double va, vb, vi, vg;
+    fetch(0, va, vb, vi, vg);
+    for (int l0 = 0; l0 < L; l0 += ST) {
+        As[ty][tx] = va;
+        Bs[ty][tx] = vb;
         if (tx == 0) {
-            inv[ty] = l < L ? lm_inv_lambda(p, a, l, mu, first) : 0.0;
-            gls[ty] = l < L ? a.gl[l] : 0.0;
+            inv[ty] = vi;
+            gls[ty] = vg;
         }
         __syncthreads();
+        if (l0 + ST < L) fetch(l0 + ST, va, vb, vi, vg);
 #pragma unroll
         for (int q = 0; q < ST; q++) {
             acc += As[q][ty] * inv[q] * Bs[q][tx];
