@@ -398,6 +398,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=200,
+                    help="published frames of the CPU-baseline sample inside the b200 arm (~10 s of CPU work)")
     ap.add_argument("--batch", type=int, default=16,
                     help="supplementary pass: this many concurrent replicas of the sequence per GPU (0 = skip)")
     a = ap.parse_args()
@@ -426,8 +428,11 @@ def main():
         }))
         return
 
-    import torch
     from vins_mono_b200 import shard
+    # frames are rendered (fork pool) before this process touches CUDA; the CPU-baseline sample needs a longer sequence
+    cpu_frames = max(a.steps, a.cpu_frames) if (not a.no_cpu_baseline and world == 1) else a.steps
+    seq, ts, imgs, imu = sequence_inputs(shard.sequences_of_rank(rank, world, 1)[0], INIT_PUBS + warmup + cpu_frames)
+    import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the vinsb200 library has no CPU path")
     torch.cuda.set_device(local)
@@ -436,7 +441,6 @@ def main():
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keeps NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    seq, ts, imgs, imu = sequence_inputs(shard.sequences_of_rank(rank, world, 1)[0], n_pub)
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=f"cuda:{local}")  # 256 MB > 126 MB L2
 
     # untimed shake-out pass (first CUDA context / module load, pinned allocations)
@@ -527,16 +531,14 @@ def main():
     cpu_b = None
     ate_ref = ate_same = None
     if not a.no_cpu_baseline and world == 1:
-        ns = min(a.steps, 60)
-        rr = run_reference_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, ns)
+        rr = run_reference_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, cpu_frames)
         tot = sum(rr["times"]) / 1e3
         cpu_b = {"value": len(rr["times"]) / tot, "unit": "frames/s", "cores": 2, "kind": "port", "cpu": cpu_model(),
                  "sample": f"{len(rr['times'])} published frames of the same sequence after the same {INIT_PUBS} init + {warmup} "
                            f"warm-up frames (oracle tracker + estimator twins on two threads, {tot:.1f} s)"}
-        if len(rr["traj_t"]) > 3:
-            ate_ref = pipeline.ate_rmse(seq, rr["traj_t"], rr["traj_p"])
-            # the same frames of our trajectory, so that the two ATE figures are comparable
-            nn = len(rr["traj_t"])
+        nn = min(len(rr["traj_t"]), len(res_dev["traj_t"]))
+        if nn > 3:  # the same frames of both trajectories, so that the two ATE figures are comparable
+            ate_ref = pipeline.ate_rmse(seq, rr["traj_t"][:nn], rr["traj_p"][:nn])
             ate_same = pipeline.ate_rmse(seq, res_dev["traj_t"][:nn], res_dev["traj_p"][:nn])
     ate = pipeline.ate_rmse(seq, res_dev["traj_t"], res_dev["traj_p"]) if len(res_dev["traj_t"]) > 3 else None
 

@@ -12,6 +12,8 @@ IMU model (the one Estimator::processIMU inverts, vins_estimator/src/estimator.c
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 G_NORM = 9.81007
@@ -206,11 +208,32 @@ class Sequence:
             out = out + rng.normal(0, self.pixel_noise, out.shape).astype(np.float32)
         return np.clip(np.rint(out), 0, 255).astype(np.uint8).reshape(self.rows, self.cols)
 
-    def images(self, n=None, start=0):
+    def images(self, n=None, start=0, workers=None):
+        """Frames start .. start+n-1.  Long runs are rendered by a fork pool (textures and rays are built first and
+        shared copy-on-write); call before any CUDA context exists in the process."""
         ts = self.image_times()
         if n is None:
             n = len(ts) - start
-        return ts[start:start + n], np.stack([self.render(ts[i], i) for i in range(start, start + n)])
+        idx = list(range(start, start + n))
+        if workers is None:
+            workers = min(32, os.cpu_count() or 1) if n >= 24 else 1
+        if workers <= 1:
+            return ts[start:start + n], np.stack([self.render(ts[i], i) for i in idx])
+        import multiprocessing as mp
+        self._textures()
+        self._pixel_rays()
+        global _RENDER_SEQ
+        _RENDER_SEQ = self
+        with mp.get_context("fork").Pool(workers) as pool:
+            frames = pool.map(_render_one, idx, chunksize=max(1, n // (4 * workers)))
+        return ts[start:start + n], np.stack(frames)
+
+
+_RENDER_SEQ = None
+
+
+def _render_one(i):
+    return _RENDER_SEQ.render(_RENDER_SEQ.image_times()[i], i)
 
 
 def tracker_config_dict(rows=ROWS, cols=COLS, max_cnt=150, min_dist=30, freq=10, equalize=1):

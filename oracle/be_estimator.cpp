@@ -733,6 +733,14 @@ void orc_projection_factor(int use_td, double focal_length, double TR, double RO
 }
 void orc_pose_plus(const double* x, const double* delta, double* out) { pose_plus(x, delta, out); }
 // sym_eigen / cholesky known answers
+void orc_sym_eigen_ql(int n, const double* A, double* w, double* V) {
+    Mat a(n, n), v;
+    std::memcpy(a.d.data(), A, (size_t)n * n * sizeof(double));
+    std::vector<double> ww;
+    sym_eigen_ql(a, ww, v);
+    std::memcpy(w, ww.data(), n * sizeof(double));
+    std::memcpy(V, v.d.data(), (size_t)n * n * sizeof(double));
+}
 void orc_sym_eigen(int n, const double* A, double* w, double* V) {
     Mat a(n, n), v;
     std::memcpy(a.d.data(), A, (size_t)n * n * sizeof(double));

@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  Small dense linear algebra used by the back-end restatement
 // (stands in for the Eigen calls of the reference; Eigen is not available offline).
 #pragma once
+#include "../vins_mono_b200/csrc/sym_eig.h"
 #include <algorithm>
 #include <cassert>
 #include <cmath>
@@ -278,6 +279,30 @@ inline void sym_eigen(const Mat& A, std::vector<double>& w, Mat& V) {
         for (int i = 0; i < n; i++) Vs(i, k) = V(i, idx[k]);
     }
     V = Vs;
+}
+
+// Cross-check of the solver above: the tridiagonal-QL template that the CUDA marginalisation kernel instantiates
+// (vins_mono_b200/csrc/sym_eig.h; tred2 + tql2, the algorithm family of Eigen's SelfAdjointEigenSolver which the
+// reference calls at marginalization_factor.cpp:268, :283), run on one host thread.  The oracle itself keeps the
+// Jacobi solver: it is independent of the product code and resolves small eigenvalues of these graded matrices to
+// relative accuracy, whereas QL/QR (the reference included) delivers them to eps*|A| only — which of the round-off
+// eigenvalues of the rank-deficient prior pass the reference's 1e-8 floor is therefore implementation noise, and it
+// bounds the achievable state parity at ~1e-5.
+inline void sym_eigen_ql(const Mat& A, std::vector<double>& w, Mat& V) {
+    const int n = A.r, ld = n | 1;
+    std::vector<double> v((size_t)n * ld, 0.0), d(n), e(n), cs(4 * (size_t)n), scal(16);
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) v[(size_t)i * ld + j] = 0.5 * (A(i, j) + A(j, i));
+    vb::sym_eig(vb::HostCtx(), v.data(), n, ld, d.data(), e.data(), cs.data(), scal.data());
+    std::vector<int> idx(n);
+    for (int i = 0; i < n; i++) idx[i] = i;
+    std::sort(idx.begin(), idx.end(), [&](int i, int j) { return d[i] < d[j]; });
+    w.resize(n);
+    V = Mat(n, n);
+    for (int k = 0; k < n; k++) {
+        w[k] = d[idx[k]];
+        for (int i = 0; i < n; i++) V(i, k) = v[(size_t)i * ld + idx[k]];
+    }
 }
 
 // Right singular vector of the smallest singular value of A (rows x 4): one-sided Jacobi on the columns

@@ -219,6 +219,14 @@ def pose_plus(x, delta):
     return out
 
 
+def sym_eigen_ql(A):
+    A = np.ascontiguousarray(A, np.float64)
+    n = A.shape[0]
+    w, V = np.zeros(n), np.zeros((n, n))
+    lib().orc_sym_eigen_ql(n, P(A, f64p), P(w, f64p), P(V, f64p))
+    return w, V
+
+
 def sym_eigen(A):
     A = _d(A)
     n = A.shape[0]

@@ -186,7 +186,8 @@ def test_small_dense_kernels():
     rng = np.random.default_rng(0)
     B = rng.normal(size=(40, 40))
     A = B @ B.T + np.diag(10.0 ** rng.uniform(-6, 6, 40))
-    w, V = orc.sym_eigen(A)
-    assert np.allclose(w, np.linalg.eigvalsh(A), rtol=1e-10, atol=1e-9)
-    assert np.allclose(V @ np.diag(w) @ V.T, A, rtol=1e-10, atol=1e-8)
-    assert np.allclose(V.T @ V, np.eye(40), atol=1e-12)
+    for solver in (orc.sym_eigen, orc.sym_eigen_ql):   # cyclic Jacobi (the oracle) and tridiagonal QL (the kernel's template)
+        w, V = solver(A)
+        assert np.allclose(w, np.linalg.eigvalsh(A), rtol=1e-10, atol=1e-9 * np.abs(A).max())
+        assert np.allclose(V @ np.diag(w) @ V.T, A, rtol=1e-10, atol=1e-9 * np.abs(A).max())
+        assert np.allclose(V.T @ V, np.eye(40), atol=1e-12)
