@@ -127,9 +127,10 @@ def lift_projective(cfg_dict, px):
 class OracleTracker:
     """FeatureTracker twin (oracle/fe_tracker.cpp)."""
 
-    def __init__(self, cfg_dict):
+    def __init__(self, cfg_dict, fisheye_mask=None):
         self.cfg = make_config(cfg_dict)
-        self.h = C.c_void_p(lib().orc_tracker_create(C.byref(self.cfg), None))
+        self._mask = np.ascontiguousarray(fisheye_mask, np.uint8) if fisheye_mask is not None else None
+        self.h = C.c_void_p(lib().orc_tracker_create(C.byref(self.cfg), P(self._mask, u8p) if self._mask is not None else None))
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -189,3 +189,44 @@ def test_tracker_edge_cases_match_oracle(FT):
             if len(a["ids"]):
                 max_id = max(max_id, int(a["ids"].max()))
     assert seen_restart == 2 and max_id > 150
+
+
+@pytest.mark.parametrize("variant", ["fisheye_mask", "no_equalize", "small_dense", "qvga_rate20"])
+def test_tracker_config_variants_match_oracle(FT, variant):
+    """Configurations beyond the EuRoC default (euroc_config.yaml:45-51 / parameters.cpp:37-74): FISHEYE with a circular
+    mask as the initial setMask image (feature_tracker.cpp:38-41), EQUALIZE off (:87-95), other MAX_CNT / MIN_DIST, other
+    image sizes and FREQ.  20 frames each, bit-identical to the CPU oracle."""
+    rows, cols = 480, 752
+    kw, mask = {}, None
+    if variant == "fisheye_mask":
+        yy, xx = np.mgrid[0:rows, 0:cols]
+        mask = np.where((yy - rows / 2) ** 2 + (xx - cols / 2) ** 2 < 210 ** 2, 255, 0).astype(np.uint8)
+        kw = dict(fisheye=1)
+    elif variant == "no_equalize":
+        kw = dict(equalize=0)
+    elif variant == "small_dense":
+        kw = dict(max_cnt=300, min_dist=12)
+    elif variant == "qvga_rate20":
+        rows, cols = 240, 320
+        kw = dict(max_cnt=80, min_dist=15, freq=20)
+    cfg = synth.tracker_config_dict(rows=rows, cols=cols, **{k: v for k, v in kw.items() if k in ("max_cnt", "min_dist", "freq", "equalize")})
+    cfg.update({k: v for k, v in kw.items() if k == "fisheye"})
+    gpu = FT(fisheye_mask=mask, **cfg) if mask is not None else FT(**cfg)
+    cpu = orc.OracleTracker(cfg, fisheye_mask=mask)
+    tex = synth.value_noise_image(rows + 40, cols + 60, seed=31)
+    n_pub, n_feat = 0, 0
+    for k in range(20):
+        dx, dy = int(round(18 * np.sin(0.3 * k))) + 20, int(round(9 * np.cos(0.25 * k))) + 15
+        img = np.ascontiguousarray(tex[dy:dy + rows, dx:dx + cols])
+        rg, sg = gpu.node_image(img, 5.0 + 0.05 * k)
+        rc, sc = cpu.node_image(img, 5.0 + 0.05 * k)
+        assert (rg, sg) == (rc, sc), f"{variant} frame {k}"
+        if rc:
+            a = _same_result(gpu, cpu, f"{variant} frame {k}")
+            n_feat = max(n_feat, len(a["ids"]))
+            if mask is not None and len(a["ids"]):
+                p = np.rint(a["cur_pts"]).astype(int)
+                new = a["track_cnt"] == 1
+                assert (mask[p[new, 1], p[new, 0]] == 255).all()      # detections only inside the fisheye mask
+        n_pub += rc == 2
+    assert n_pub >= 5 and n_feat >= 40
