@@ -6,8 +6,10 @@ from harness import synth, pipeline
 from vins_mono_b200 import Estimator
 
 seq = synth.Sequence(seed=11, duration=6.0)
-msgs = synth.track_messages(seq, int(sys.argv[1]) if len(sys.argv) > 1 else 20)
-kw = {}
+NMSG = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+kw = dict(window_size=20, estimate_td=1, tr=0.033) if len(sys.argv) > 2 and sys.argv[2] == 'w20' else {}
+max_feats = 300 if kw else 150
+msgs = synth.track_messages(seq, NMSG, max_feats=max_feats)
 cpu, gpu = orc.OracleEstimator(orc.be_config(**kw)), Estimator(tic=synth.TIC, ric=synth.RIC, **kw)
 t_imu, acc, gyr = seq.imu()
 fa, fb = pipeline.ImuFeeder(t_imu, acc, gyr), pipeline.ImuFeeder(t_imu, acc, gyr)

@@ -33,7 +33,7 @@ extern "C" {
 typedef enum ve_status { VE_OK = 0, VE_ERR_INVALID = -1, VE_ERR_NO_DEVICE = -2, VE_ERR_CUDA = -3, VE_ERR_CAPACITY = -4 } ve_status;
 
 typedef struct ve_config {
-    int window_size;         /* WINDOW_SIZE (parameters.h:12), runtime here; 3..13 (ve_create rejects larger windows) */
+    int window_size;         /* WINDOW_SIZE (parameters.h:12), runtime here; 3..22 (ve_create rejects larger windows) */
     int max_features;        /* NUM_OF_F (parameters.h:13): landmark capacity, bound-checked */
     int num_iterations;      /* max_num_iterations (euroc_config.yaml:55) */
     int estimate_extrinsic;  /* 0 or 1 (2 = online calibration is not part of this path) */

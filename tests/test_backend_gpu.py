@@ -89,13 +89,15 @@ def test_estimator_matches_oracle_on_synthetic_tracks():
     assert worst["prior"] <= 1e-5
 
 
-def test_estimator_td_and_extrinsic_blocks():
-    """ProjectionTdFactor path (estimate_td) together with a free extrinsic (estimate_extrinsic = 1)."""
+@pytest.mark.parametrize("tr", [0.0, 0.033])
+def test_estimator_td_and_extrinsic_blocks(tr):
+    """ProjectionTdFactor path (estimate_td) together with a free extrinsic (estimate_extrinsic = 1); tr > 0 adds the
+    rolling-shutter row term TR / ROW * row of projection_td_factor.cpp:34-46 (rolling_shutter_tr of the YAML)."""
     seq = synth.Sequence(seed=12, duration=5.0)
     msgs = synth.track_messages(seq, 35)
     kw = dict(estimate_td=1, estimate_extrinsic=1)
-    worst, n_nl, cpu, gpu = run_both(seq, msgs, cfg_kw=dict(tr=0.0, **kw), gpu_kw=dict(tr=0.0, **kw))
-    print("worst deviations (td + extrinsic)", worst, "frames", n_nl)
+    worst, n_nl, cpu, gpu = run_both(seq, msgs, cfg_kw=dict(tr=tr, **kw), gpu_kw=dict(tr=tr, **kw))
+    print("worst deviations (td + extrinsic, tr = %g)" % tr, worst, "frames", n_nl)
     for k, tol in TOL.items():
         assert worst[k] <= 2 * tol, (k, worst)
     assert abs(cpu.states()[1] - gpu.states()[1]) < 1e-5
@@ -151,3 +153,18 @@ def test_estimator_feature_dropouts_and_capacity():
         for stamp, ids, d in clean:
             fb.feed(small, stamp)
             small.processImage(ids, d, stamp)
+
+
+def test_estimator_window20_300_features_rolling_shutter():
+    """BASELINE.json configs[3]: 20-keyframe window, 300 features, ProjectionTdFactor with rolling shutter.  The reduced
+    camera system (322 columns) and the prior (136 parameters) no longer fit one CTA's shared memory: the step kernel
+    factorises in global memory and the marginalisation keeps its reduced system there."""
+    seq = synth.Sequence(seed=16, duration=5.0)
+    msgs = synth.track_messages(seq, 30, max_feats=300)
+    kw = dict(window_size=20, estimate_td=1, tr=0.033)
+    worst, n_nl, cpu, gpu = run_both(seq, msgs, cfg_kw=kw, gpu_kw=kw)
+    print("worst deviations (W = 20, 300 features, td + rolling shutter)", worst, "frames", n_nl)
+    assert n_nl >= 8
+    for k, tol in TOL.items():
+        assert worst[k] <= 2 * tol, (k, worst)
+    assert abs(cpu.states()[1] - gpu.states()[1]) < 1e-5

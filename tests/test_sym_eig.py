@@ -30,7 +30,7 @@ def run(lib, A):
     return w, V
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 6, 15, 75, 76])
+@pytest.mark.parametrize("n", [1, 2, 3, 6, 15, 75, 76, 136])
 def test_random_symmetric(lib, n):
     rng = np.random.default_rng(n)
     B = rng.standard_normal((n, n))

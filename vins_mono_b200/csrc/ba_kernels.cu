@@ -1301,6 +1301,14 @@ __global__ void __launch_bounds__(128) marg_build_kernel(BaProblem p, MargPlan m
 }
 
 constexpr int MARG_THREADS = 512;
+constexpr int MARG_MAXN = 160;  // kept prior parameters (6 W + 9 + 6 + 1) supported by the work arrays: WINDOW_SIZE <= 22
+
+// doubles of the scratch area Ev: staged landmark rows (2 x 16 x qp) or the n x md products Y and X
+__host__ __device__ inline int marg_scratch_doubles(int md, int n) {
+    const int q = md + n, qp = (q + 3) & ~3, ldm = md + (md & 1);
+    const int a = 32 * qp, b = n * (ldm + md);
+    return ((a > b ? a : b) + 1) & ~1;
+}
 
 // Single CTA.  Dynamic shared memory: Wk (q x q), Ev (scratch), Vv ((ldx+1)^2: matrix in / eigenvectors out), bw (q), tv.
 // Both eigen-decompositions (the dense marginalised block T and the new prior A') use the tridiagonal-QL solver of
@@ -1308,14 +1316,15 @@ constexpr int MARG_THREADS = 512;
 __global__ void __launch_bounds__(MARG_THREADS) marg_solve_kernel(MargPlan mp, double eps) {
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
-    __shared__ double dval[96], ework[96], cs[4 * 96], scal[16];
+    __shared__ double dval[MARG_MAXN], ework[MARG_MAXN], cs[4 * MARG_MAXN], scal[16];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int md = mp.m_dense, nl = mp.n_lm, n = mp.n, P = mp.P;
     const int q = md + n;
     const int ldm = md + (md & 1), ldn = n + (n & 1), ldx = max(ldm, ldn);
-    const int esz = max(max((ldx + 1) * (ldx + 1), n * (ldm + md)), 32 * ((q + 3) & ~3));
-    double* Wk = sm;                  // q*q
-    double* Ev = Wk + ((q * q + 1) & ~1);  // esz (16-byte aligned: 128-bit loads of the staged landmark rows)
+    const int esz = marg_scratch_doubles(md, n);
+    // the reduced system W (q x q) lives in shared memory when it fits (the shipped window), else in global memory
+    double* Wk = mp.w_in_global ? mp.Wglobal : sm;
+    double* Ev = mp.w_in_global ? sm : sm + ((q * q + 1) & ~1);  // esz, 16-byte aligned (128-bit loads of the staged rows)
     double* Vv = Ev + esz;            // (ldx+1)^2
     double* bw = Vv + (ldx + 1) * (ldx + 1);  // q
     double* tv = bw + q;              // ldx
@@ -1479,17 +1488,13 @@ __global__ void __launch_bounds__(MARG_THREADS) marg_solve_kernel(MargPlan mp, d
         if (w > eps) cpart += tv[k] * tv[k] / w;
     }
     const double c0 = block_sum(cpart, red);
-    // scale the kept eigenvectors once (Ev <- V diag(w+)), then A+ = Ev V^T
-    for (int idx = tid; idx < n * n; idx += nt) {
-        const int i = idx / n, k = idx - i * n;
-        const double w = dval[k];
-        Ev[i * ldvn + k] = w > eps ? Vv[i * ldvn + k] * w : 0.0;
-    }
+    // A+ = V diag(w+) V^T with the floored eigenvalues w+ (ework is free after the decomposition)
+    for (int k = tid; k < n; k += nt) ework[k] = dval[k] > eps ? dval[k] : 0.0;
     __syncthreads();
     for (int idx = tid; idx < n * n; idx += nt) {
         const int i = idx / n, j = idx - i * n;
         double s = 0;
-        for (int k = 0; k < n; k++) s += Ev[i * ldvn + k] * Vv[j * ldvn + k];
+        for (int k = 0; k < n; k++) s += Vv[i * ldvn + k] * ework[k] * Vv[j * ldvn + k];
         Ap[idx] = s;
     }
     for (int i = tid; i < n; i += nt) {
@@ -1511,11 +1516,11 @@ __global__ void __launch_bounds__(MARG_THREADS) marg_solve_kernel(MargPlan mp, d
     }
 }
 
-size_t marg_solve_smem_bytes(int m_dense, int n) {
+size_t marg_solve_smem_bytes(int m_dense, int n, bool w_in_global) {
     const int q = m_dense + n;
     const int ldm = m_dense + (m_dense & 1), ldn = n + (n & 1), ldx = ldm > ldn ? ldm : ldn;
-    const size_t esz = std::max(std::max((size_t)(ldx + 1) * (ldx + 1), (size_t)n * (ldm + m_dense)), (size_t)32 * ((q + 3) & ~3));
-    return sizeof(double) * ((size_t)q * q + 1 + esz + (size_t)(ldx + 1) * (ldx + 1) + q + std::max(ldx, 32));
+    const size_t esz = (size_t)marg_scratch_doubles(m_dense, n);
+    return sizeof(double) * ((w_in_global ? 0 : (size_t)q * q + 1) + esz + (size_t)(ldx + 1) * (ldx + 1) + q + std::max(ldx, 32));
 }
 
 }  // namespace vb
@@ -1604,16 +1609,31 @@ void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int
     if (launches) *launches += n;
 }
 
-void launch_marginalize(const BaProblem& p, const MargPlan& mp, cudaStream_t s, int* launches, KernelProfile* prof) {
+void launch_marginalize(const BaProblem& p, const MargPlan& mp_in, cudaStream_t s, int* launches, KernelProfile* prof) {
     KernelProfile none;
     if (!prof) prof = &none;
+    MargPlan mp = mp_in;
+    {
+        static int smem_limit = -1, smem_static = 0;
+        static std::mutex m;
+        std::lock_guard<std::mutex> lock(m);
+        if (smem_limit < 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            cudaFuncAttributes fa{};
+            cudaFuncGetAttributes(&fa, marg_solve_kernel);
+            smem_static = (int)fa.sharedSizeBytes;
+        }
+        mp.w_in_global = marg_solve_smem_bytes(mp.m_dense, mp.n, false) + (size_t)smem_static + 256 > (size_t)smem_limit ? 1 : 0;
+    }
     cudaMemsetAsync(mp.Am, 0, sizeof(double) * (size_t)mp.P * mp.P, s);
     cudaMemsetAsync(mp.bm, 0, sizeof(double) * (size_t)mp.P, s);
     const int grid = (mp.n_lm + 3) / 4 + 2;
     prof->begin(s);
     marg_build_kernel<<<grid, 128, 0, s>>>(p, mp);
     prof->end(4, s);
-    const size_t smem = marg_solve_smem_bytes(mp.m_dense, mp.n);
+    const size_t smem = marg_solve_smem_bytes(mp.m_dense, mp.n, mp.w_in_global != 0);
     {
         static std::mutex cfg_mutex;
         static size_t configured = 0;

@@ -23,6 +23,8 @@ struct MargPlan {  // dense marginalisation system layout: [m_dense | n_lm landm
     double* cout;       // 1       new prior c0
     double* Araw;       // n x n   Schur complement before the eps floor (tests), may be null
     double* graw;       // n
+    double* Wglobal;    // q x q scratch (q = m_dense + n) used when the reduced system does not fit shared memory
+    int w_in_global;    // set by launch_marginalize
 };
 
 void launch_preint_push(PreInt* slot, int n, const double* d_samples, double acc_n, double gyr_n, double acc_w, double gyr_w,

@@ -743,6 +743,8 @@ int marginalize(ve_estimator* e, vb::BaProblem& p) {
     mp.bm = mp.Am + Pm * Pm;
     mp.Araw = mp.bm + Pm;
     mp.graw = mp.Araw + (size_t)e->nmax * e->nmax;
+    mp.Wglobal = mp.graw + e->nmax;  // (nmax + 15)^2 doubles
+    mp.w_in_global = 0;
     const int nb = e->prior_buf ^ 1;
     mp.Aout = e->d_prior[nb].p;
     mp.gout = mp.Aout + (size_t)e->nmax * e->nmax;
@@ -932,9 +934,10 @@ int ve_create(const ve_config* cfg, ve_estimator** out) {
     if (cfg->window_size < 3 || cfg->window_size + 1 > vb::BA_MAX_FRAMES || cfg->window_size + 1 > vb::BA_MAX_OBS_PER_LM ||
         cfg->max_features < 8 || cfg->num_iterations < 1 || cfg->estimate_extrinsic > 1)
         return VE_ERR_INVALID;
-    // the marginalisation kernel keeps the prior (6 W + 9 + 6 + 1 parameters) and its eigen-solver work arrays in the
-    // shared memory of one CTA: up to 96 parameters, i.e. WINDOW_SIZE <= 13 (the reference ships 10)
-    if (6 * cfg->window_size + 16 > 96) return VE_ERR_INVALID;
+    // work arrays of the single-CTA solvers: prior of 6 W + 9 + 6 + 1 <= 160 parameters, reduced system of
+    // 15 (W + 1) + 7 <= 352 columns, i.e. WINDOW_SIZE <= 22 (the reference ships 10; above 13 the reduced systems
+    // move from shared to global memory)
+    if (6 * cfg->window_size + 16 > 160 || 15 * (cfg->window_size + 1) + 7 > 352) return VE_ERR_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) return VE_ERR_NO_DEVICE;
     ve_estimator* e = new ve_estimator();
@@ -982,7 +985,7 @@ int ve_create(const ve_config* cfg, ve_estimator** out) {
     VE_TRY(e->d_vec.alloc(4 * ((size_t)e->D + e->Lmax)));
     VE_TRY(e->d_work.alloc(vb::ba_work_doubles(e->D, e->Lmax)));
     VE_TRY(e->d_st.alloc(1));
-    VE_TRY(e->d_marg.alloc(Pm * Pm + Pm + (size_t)e->nmax * e->nmax + e->nmax));
+    VE_TRY(e->d_marg.alloc(Pm * Pm + Pm + (size_t)e->nmax * e->nmax + e->nmax + ((size_t)e->nmax + 15) * (e->nmax + 15)));
     VE_TRY(e->d_marg_i.alloc(2 * (size_t)e->Lmax));
     VE_TRY(cudaHostAlloc(&e->h_states, sizeof(double) * 3 * states_doubles(e), cudaHostAllocDefault));
     VE_TRY(cudaHostAlloc(&e->h_obs, sizeof(double) * (6 * (size_t)e->Lmax + 6 * (size_t)e->Mmax), cudaHostAllocDefault));

@@ -19,6 +19,8 @@
 
 namespace vb {
 
+constexpr int SE_PER_LANE = 5;  // columns per lane in the warp-wide phases of the device context: n <= 160
+
 #if defined(SE_PROF) && defined(__CUDACC__)  // harness/micro/eig_bench.cu: per-phase cycle counters (thread 0)
 __shared__ long long se_clk[16];
 __host__ __device__ inline long long se_now() {
@@ -197,7 +199,8 @@ __device__ __forceinline__ void se_bar_arrive(int id, int count) { asm volatile(
 // rotation sequences sweep by sweep into a double-buffered coefficient array; warps 1..3 (one thread per row) consume
 // them.  Hand-over through named barriers: full[b] = 1 + b (producer arrives, consumers wait), empty[b] = 3 + b
 // (consumers arrive, producer waits before reusing buffer b).  d and e are touched by the producer only, V by the
-// consumers only.  cs holds 4n doubles, scal[9..12] the (l, m) of the sweep in each buffer.  n <= 96.
+// consumers only.  cs holds 4n doubles, scal[9..12] the (l, m) of the sweep in each buffer.  n <= 192 (two rows per
+// consumer thread).
 __device__ inline void ql_pipelined(double* V, int n, int ld, double* d, double* e, double* cs, double* scal) {
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     constexpr int PART = 128;  // producer warp + three consumer warps
@@ -271,9 +274,9 @@ __device__ inline void ql_pipelined(double* V, int n, int ld, double* d, double*
             const int l = (int)meta[2 * b];
             if (l < 0) break;
             const int m = (int)meta[2 * b + 1];
-            if (k < n) {
+            for (int kr = k; kr < n; kr += 96) {
                 const double* c2 = cs + b * 2 * n;
-                double* row = V + k * ld;
+                double* row = V + kr * ld;
                 double vi1 = row[m];
                 for (int i = m - 1; i >= l; i--) {
                     const double c = c2[2 * i], s = c2[2 * i + 1];
@@ -356,10 +359,13 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
             double part = 0.0;
             if (ctx.aux_size() == 1) {
                 for (int k = 0; k < i; k++) part += u[k] * u[k];
-            } else {  // n <= 3 * 32: the three loads are issued together
-                const int k0 = ctx.aux_lane(), k1 = k0 + 32, k2 = k0 + 64;
-                const double a0 = k0 < i ? u[k0] : 0.0, a1 = k1 < i ? u[k1] : 0.0, a2 = k2 < i ? u[k2] : 0.0;
-                part = a0 * a0 + a1 * a1 + a2 * a2;
+            } else {  // n <= SE_PER_LANE * 32: the loads are issued together
+#pragma unroll
+                for (int t = 0; t < SE_PER_LANE; t++) {
+                    const int k = ctx.aux_lane() + 32 * t;
+                    const double a = k < i ? u[k] : 0.0;
+                    part += a * a;
+                }
             }
             const double hsum = ctx.aux_sum(part);
             if (ctx.aux_lane() == 0) {
@@ -414,17 +420,19 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
                     u[j] = uj;
                     VV(j, i) = uj;
                 }
-            } else {  // one warp, n <= 3 * 32: three elements per lane held in registers, loads issued together
-                double uj[3], ej[3];
+            } else {  // one warp, n <= SE_PER_LANE * 32: the lane's elements stay in registers, loads issued together
+                double uj[SE_PER_LANE], ej[SE_PER_LANE];
+                double part = 0.0;
 #pragma unroll
-                for (int t = 0; t < 3; t++) {
+                for (int t = 0; t < SE_PER_LANE; t++) {
                     const int j = tid + 32 * t;
                     uj[t] = j < i ? ((j == i - 1) ? ulast : u[j]) : 0.0;
                     ej[t] = j < i ? (e[j] + VV(i - 1, j) * du) * rh : 0.0;
+                    part += ej[t] * uj[t];
                 }
-                const double hh = ctx.lead_sum(ej[0] * uj[0] + ej[1] * uj[1] + ej[2] * uj[2]) * 0.5 * rh;
+                const double hh = ctx.lead_sum(part) * 0.5 * rh;
 #pragma unroll
-                for (int t = 0; t < 3; t++) {
+                for (int t = 0; t < SE_PER_LANE; t++) {
                     const int j = tid + 32 * t;
                     if (j < i) {
                         e[j] = ej[t] - hh * uj[t];
@@ -438,10 +446,10 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
         SE_STAMP(1);
         // ---- C
         {
-            // each lane keeps its columns' u and e in registers for the whole phase (n <= 3 * 32 on the device)
-            double uj[3], ej[3];
+            // each lane keeps its columns' u and e in registers for the whole phase (n <= SE_PER_LANE * 32 on the device)
+            double uj[SE_PER_LANE], ej[SE_PER_LANE];
 #pragma unroll
-            for (int t = 0; t < 3; t++) {
+            for (int t = 0; t < SE_PER_LANE; t++) {
                 const int j = lane + t * ws;
                 uj[t] = j < i ? u[j] : 0.0;
                 ej[t] = j < i ? e[j] : 0.0;
@@ -456,7 +464,7 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
                     }
                 } else {
 #pragma unroll
-                    for (int t = 0; t < 3; t++) {
+                    for (int t = 0; t < SE_PER_LANE; t++) {
                         const int j = lane + t * ws;
                         if (j <= k) {
                             const double v = VV(k, j) - (uj[t] * ek + ej[t] * uk);
@@ -503,9 +511,9 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
             ctx.sync();
             SE_STAMP(6);
         }
-        double ej2[3];
+        double ej2[SE_PER_LANE];
 #pragma unroll
-        for (int t = 0; t < 3; t++) {
+        for (int t = 0; t < SE_PER_LANE; t++) {
             const int j = lane + t * ws;
             ej2[t] = (active && j <= i) ? e[j] : 0.0;
         }
@@ -516,7 +524,7 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
                     for (int j = 0; j <= i; j++) VV(k, j) -= e[j] * c;
                 } else {
 #pragma unroll
-                    for (int t = 0; t < 3; t++) {
+                    for (int t = 0; t < SE_PER_LANE; t++) {
                         const int j = lane + t * ws;
                         if (j <= i) VV(k, j) -= ej2[t] * c;
                     }
