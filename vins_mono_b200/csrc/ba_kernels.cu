@@ -3,7 +3,7 @@
 //   preint_push_kernel    IntegrationBase::propagate / midPointIntegration     integration_base.h:54-158
 //   sqrt_info_kernel      LLT(covariance^-1).matrixL().transpose()            imu_factor.h:64
 //   ba_linearize_kernel   factor Evaluate() + Cauchy corrector + J^T J / J^T r accumulation; one warp per
-//                         landmark (lanes = its observations), one warp per IMU factor, one CTA for the prior;
+//                         landmark (lanes = its observations), one CTA per IMU factor, one CTA for the prior;
 //                         the last CTA to finish runs the trust-region accept/reject logic
 //   ba_schur_kernel       landmark elimination S = Hpp - Hpl^T (Hll + mu E)^-1 Hpl as a dense tiled SYRK
 //                         (deterministic summation order), plus the reduced gradient
@@ -742,16 +742,15 @@ __device__ __forceinline__ void chol_diag_block(double* Lp, const double* Pc, in
         a[c][c] = piv * rc;
 #pragma unroll
         for (int rr = c + 1; rr < CHOL_NB; rr++) a[rr][c] *= rc;
-        // column c is final: every lane holds the same values and stores them to the same addresses (the stores fill
-        // the latency bubbles of the chain and free the registers early)
+        // column c is final: every lane holds the same values and stores them to the same addresses of the small block
+        // buffer (the stores fill the latency bubbles of the chain and free the registers early).  The copy into the
+        // packed matrix is left to idle threads of the next panel phase: stores to the big array queue behind the tile
+        // warps' traffic and cost this chain 30 k cycles per factorisation when issued here.
         if (c < w) {
             rdiag[kb + c] = rc;
 #pragma unroll
             for (int rr = c; rr < CHOL_NB; rr++)
-                if (rr < w) {
-                    Lp[(kb + rr) * (kb + rr + 1) / 2 + kb + c] = a[rr][c];
-                    dblk[rr][c] = a[rr][c];
-                }
+                if (rr < w) dblk[rr][c] = a[rr][c];
         }
 #pragma unroll
         for (int k = c + 1; k < CHOL_NB; k++)
@@ -815,6 +814,10 @@ __device__ bool cholesky_packed(double* Lp, double* Pc, int n, double* rdiag, do
     for (int kb = 0; kb < n; kb += CHOL_NB) {
         const int w = min(CHOL_NB, n - kb), ke = kb + w;  // only the last block can be partial
         if (!*flag) return false;
+        if (tid >= nt - 64) {  // factorised diagonal block -> packed matrix (threads that have no panel row)
+            const int e = tid - (nt - 64), rr = e >> 3, c = e & 7;
+            if (rr < w && c <= rr) Lp[(kb + rr) * (kb + rr + 1) / 2 + kb + c] = dblk[rr][c];
+        }
         if (ke >= nrows) break;
         CP(3);
         // panel: rows below the diagonal block, forward substitution against it
@@ -1304,10 +1307,14 @@ constexpr int MARG_THREADS = 512;
 constexpr int MARG_MAXN = 160;  // kept prior parameters (6 W + 9 + 6 + 1) supported by the work arrays: WINDOW_SIZE <= 22
 
 // doubles of the scratch area Ev: staged landmark rows (2 x 16 x qp) or the n x md products Y and X
-__host__ __device__ inline int marg_scratch_doubles(int md, int n) {
+// (+ a copy of the scaled eigenvectors, n x (n|1), when the reduced system lives in shared memory, i.e. small windows)
+__host__ __device__ inline int marg_scratch_doubles(int md, int n, bool w_in_global) {
     const int q = md + n, qp = (q + 3) & ~3, ldm = md + (md & 1);
-    const int a = 32 * qp, b = n * (ldm + md);
-    return ((a > b ? a : b) + 1) & ~1;
+    int a = 32 * qp;
+    const int b = n * (ldm + md), c = w_in_global ? 0 : n * (n | 1);
+    a = a > b ? a : b;
+    a = a > c ? a : c;
+    return (a + 1) & ~1;
 }
 
 // Single CTA.  Dynamic shared memory: Wk (q x q), Ev (scratch), Vv ((ldx+1)^2: matrix in / eigenvectors out), bw (q), tv.
@@ -1321,7 +1328,7 @@ __global__ void __launch_bounds__(MARG_THREADS) marg_solve_kernel(MargPlan mp, d
     const int md = mp.m_dense, nl = mp.n_lm, n = mp.n, P = mp.P;
     const int q = md + n;
     const int ldm = md + (md & 1), ldn = n + (n & 1), ldx = max(ldm, ldn);
-    const int esz = marg_scratch_doubles(md, n);
+    const int esz = marg_scratch_doubles(md, n, mp.w_in_global != 0);
     // the reduced system W (q x q) lives in shared memory when it fits (the shipped window), else in global memory
     double* Wk = mp.w_in_global ? mp.Wglobal : sm;
     double* Ev = mp.w_in_global ? sm : sm + ((q * q + 1) & ~1);  // esz, 16-byte aligned (128-bit loads of the staged rows)
@@ -1428,7 +1435,7 @@ __global__ void __launch_bounds__(MARG_THREADS) marg_solve_kernel(MargPlan mp, d
     }
     __syncthreads();
     MSTAMP(0);
-    sym_eig(CtaCtx(), Vv, md, ldvm, dval, ework, cs, scal);
+    sym_eig<CtaCtx, 3>(CtaCtx(), Vv, md, ldvm, dval, ework, cs, scal);  // md <= 15
     MSTAMP(1);
     for (int k = tid; k < md; k += nt) tv[k] = dval[k] > eps ? 1.0 / dval[k] : 0.0;
     __syncthreads();
@@ -1474,7 +1481,10 @@ __global__ void __launch_bounds__(MARG_THREADS) marg_solve_kernel(MargPlan mp, d
     }
     __syncthreads();
     MSTAMP(2);
-    sym_eig(CtaCtx(), Vv, n, ldvn, dval, ework, cs, scal);
+    if (n <= 96)
+        sym_eig<CtaCtx, 3>(CtaCtx(), Vv, n, ldvn, dval, ework, cs, scal);
+    else
+        sym_eig<CtaCtx, SE_PER_LANE_MAX>(CtaCtx(), Vv, n, ldvn, dval, ework, cs, scal);
     MSTAMP(3);
     for (int k = tid; k < n; k += nt) {
         double s = 0;
@@ -1491,11 +1501,25 @@ __global__ void __launch_bounds__(MARG_THREADS) marg_solve_kernel(MargPlan mp, d
     // A+ = V diag(w+) V^T with the floored eigenvalues w+ (ework is free after the decomposition)
     for (int k = tid; k < n; k += nt) ework[k] = dval[k] > eps ? dval[k] : 0.0;
     __syncthreads();
-    for (int idx = tid; idx < n * n; idx += nt) {
-        const int i = idx / n, j = idx - i * n;
-        double s = 0;
-        for (int k = 0; k < n; k++) s += Vv[i * ldvn + k] * ework[k] * Vv[j * ldvn + k];
-        Ap[idx] = s;
+    if (!mp.w_in_global) {  // room for a scaled copy of V: one multiply less in the n^3 product
+        for (int idx = tid; idx < n * n; idx += nt) {
+            const int i = idx / n, k = idx - i * n;
+            Ev[i * ldvn + k] = Vv[i * ldvn + k] * ework[k];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < n * n; idx += nt) {
+            const int i = idx / n, j = idx - i * n;
+            double s = 0;
+            for (int k = 0; k < n; k++) s += Ev[i * ldvn + k] * Vv[j * ldvn + k];
+            Ap[idx] = s;
+        }
+    } else {
+        for (int idx = tid; idx < n * n; idx += nt) {
+            const int i = idx / n, j = idx - i * n;
+            double s = 0;
+            for (int k = 0; k < n; k++) s += Vv[i * ldvn + k] * ework[k] * Vv[j * ldvn + k];
+            Ap[idx] = s;
+        }
     }
     for (int i = tid; i < n; i += nt) {
         double s = 0;
@@ -1519,7 +1543,7 @@ __global__ void __launch_bounds__(MARG_THREADS) marg_solve_kernel(MargPlan mp, d
 size_t marg_solve_smem_bytes(int m_dense, int n, bool w_in_global) {
     const int q = m_dense + n;
     const int ldm = m_dense + (m_dense & 1), ldn = n + (n & 1), ldx = ldm > ldn ? ldm : ldn;
-    const size_t esz = (size_t)marg_scratch_doubles(m_dense, n);
+    const size_t esz = (size_t)marg_scratch_doubles(m_dense, n, w_in_global);
     return sizeof(double) * ((w_in_global ? 0 : (size_t)q * q + 1) + esz + (size_t)(ldx + 1) * (ldx + 1) + q + std::max(ldx, 32));
 }
 

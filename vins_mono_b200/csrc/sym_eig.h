@@ -19,7 +19,7 @@
 
 namespace vb {
 
-constexpr int SE_PER_LANE = 5;  // columns per lane in the warp-wide phases of the device context: n <= 160
+constexpr int SE_PER_LANE_MAX = 5;  // columns per lane in the warp-wide phases of the device context: n <= 160
 
 #if defined(SE_PROF) && defined(__CUDACC__)  // harness/micro/eig_bench.cu: per-phase cycle counters (thread 0)
 __shared__ long long se_clk[16];
@@ -201,6 +201,7 @@ __device__ __forceinline__ void se_bar_arrive(int id, int count) { asm volatile(
 // (consumers arrive, producer waits before reusing buffer b).  d and e are touched by the producer only, V by the
 // consumers only.  cs holds 4n doubles, scal[9..12] the (l, m) of the sweep in each buffer.  n <= 192 (two rows per
 // consumer thread).
+template <bool TWO_ROWS>
 __device__ inline void ql_pipelined(double* V, int n, int ld, double* d, double* e, double* cs, double* scal) {
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     constexpr int PART = 128;  // producer warp + three consumer warps
@@ -274,7 +275,7 @@ __device__ inline void ql_pipelined(double* V, int n, int ld, double* d, double*
             const int l = (int)meta[2 * b];
             if (l < 0) break;
             const int m = (int)meta[2 * b + 1];
-            for (int kr = k; kr < n; kr += 96) {
+            for (int kr = k; kr < n && kr < (TWO_ROWS ? 192 : 96); kr += 96) {
                 const double* c2 = cs + b * 2 * n;
                 double* row = V + kr * ld;
                 double vi1 = row[m];
@@ -295,7 +296,9 @@ __device__ inline void ql_pipelined(double* V, int n, int ld, double* d, double*
 }
 #endif
 
-template <class Ctx>
+// SE_PER_LANE: columns per lane of the warp-wide phases on the device (n <= 32 * SE_PER_LANE); callers pick the smallest
+// instantiation that covers their n (the unrolled per-lane loops cost instructions even when predicated off).
+template <class Ctx, int SE_PER_LANE = 3>
 SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, double* cs, double* scal) {
     const int tid = ctx.tid(), nt = ctx.nt();
     const int LD = ctx.lead(), G = ctx.grp();
@@ -330,6 +333,7 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
     ctx.sync();
     SE_T0();
     for (int i = n - 1; i > 0; i--) {
+        const int npi = (i + 32) / 32;  // per-lane columns in use at this step (j <= i)
         // ---- A
         for (int j0 = 0; j0 < i; j0 += ng) {
             const int j = j0 + gi;
@@ -362,9 +366,11 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
             } else {  // n <= SE_PER_LANE * 32: the loads are issued together
 #pragma unroll
                 for (int t = 0; t < SE_PER_LANE; t++) {
-                    const int k = ctx.aux_lane() + 32 * t;
-                    const double a = k < i ? u[k] : 0.0;
-                    part += a * a;
+                    if (t < npi) {
+                        const int k = ctx.aux_lane() + 32 * t;
+                        const double a = k < i ? u[k] : 0.0;
+                        part += a * a;
+                    }
                 }
             }
             const double hsum = ctx.aux_sum(part);
@@ -425,16 +431,19 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
                 double part = 0.0;
 #pragma unroll
                 for (int t = 0; t < SE_PER_LANE; t++) {
-                    const int j = tid + 32 * t;
-                    uj[t] = j < i ? ((j == i - 1) ? ulast : u[j]) : 0.0;
-                    ej[t] = j < i ? (e[j] + VV(i - 1, j) * du) * rh : 0.0;
-                    part += ej[t] * uj[t];
+                    uj[t] = ej[t] = 0.0;
+                    if (t < npi) {
+                        const int j = tid + 32 * t;
+                        uj[t] = j < i ? ((j == i - 1) ? ulast : u[j]) : 0.0;
+                        ej[t] = j < i ? (e[j] + VV(i - 1, j) * du) * rh : 0.0;
+                        part += ej[t] * uj[t];
+                    }
                 }
                 const double hh = ctx.lead_sum(part) * 0.5 * rh;
 #pragma unroll
                 for (int t = 0; t < SE_PER_LANE; t++) {
                     const int j = tid + 32 * t;
-                    if (j < i) {
+                    if (t < npi && j < i) {
                         e[j] = ej[t] - hh * uj[t];
                         u[j] = uj[t];
                         VV(j, i) = uj[t];
@@ -451,8 +460,8 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
 #pragma unroll
             for (int t = 0; t < SE_PER_LANE; t++) {
                 const int j = lane + t * ws;
-                uj[t] = j < i ? u[j] : 0.0;
-                ej[t] = j < i ? e[j] : 0.0;
+                uj[t] = (t < npi && j < i) ? u[j] : 0.0;
+                ej[t] = (t < npi && j < i) ? e[j] : 0.0;
             }
             for (int k = wid; k < i; k += nw) {
                 const double ek = e[k], uk = u[k];
@@ -466,7 +475,7 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
 #pragma unroll
                     for (int t = 0; t < SE_PER_LANE; t++) {
                         const int j = lane + t * ws;
-                        if (j <= k) {
+                        if (t < npi && j <= k) {
                             const double v = VV(k, j) - (uj[t] * ek + ej[t] * uk);
                             VV(k, j) = v;
                             if (k == i - 1) un[j] = v;  // row i-1 is the next u
@@ -490,6 +499,7 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
     }
     ctx.sync();
     for (int i = 0; i < n - 1; i++) {
+        const int npi = (i + 32) / 32;
         const bool active = hv[i + 1] != 0.0;
         if (active) {
             const double rh = rhv[i + 1];
@@ -515,7 +525,7 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
 #pragma unroll
         for (int t = 0; t < SE_PER_LANE; t++) {
             const int j = lane + t * ws;
-            ej2[t] = (active && j <= i) ? e[j] : 0.0;
+            ej2[t] = (t < npi && active && j <= i) ? e[j] : 0.0;
         }
         for (int k = wid; k <= i; k += nw) {
             if (active) {
@@ -526,7 +536,7 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
 #pragma unroll
                     for (int t = 0; t < SE_PER_LANE; t++) {
                         const int j = lane + t * ws;
-                        if (j <= i) VV(k, j) -= ej2[t] * c;
+                        if (t < npi && j <= i) VV(k, j) -= ej2[t] * c;
                     }
                 }
             }
@@ -560,7 +570,7 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
     const double eps = 2.220446049250313e-16;
 #if defined(__CUDA_ARCH__)
     if constexpr (Ctx::kPipelinedQL) {
-        ql_pipelined(V, n, ld, d, e, cs, scal);
+        ql_pipelined<(SE_PER_LANE > 3)>(V, n, ld, d, e, cs, scal);
         if (tid == 0) {
             scal[4] = (double)(clk1 - clk0);
             scal[5] = (double)(clock64() - clk1);
