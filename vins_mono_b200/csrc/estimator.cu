@@ -67,7 +67,7 @@ struct ve_estimator {
     std::string err;
     int W = 10;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[5] = {};
+    cudaEvent_t ev[8] = {};  // 0-2 solve phases, 3 marginalisation done, 5 marginalisation start, 6 state upload of marginalize()
     // ---- Estimator state (estimator.h:65-115)
     int solver_flag = 0;           // INITIAL = 0, NON_LINEAR = 1
     int marginalization_flag = 0;  // MARGIN_OLD = 0, MARGIN_SECOND_NEW = 1
@@ -132,12 +132,14 @@ struct ve_estimator {
     double* h_prior = nullptr;
     int* h_prior_i = nullptr;
     int* h_marg_i = nullptr;
+    int* h_which = nullptr;          // pinned staging of refresh_sqrt_info (h_marg_i may still be in flight)
     double* h_marg_out = nullptr;
     std::vector<double> prior_raw_A, prior_raw_b;  // last Schur complement before the eps floor
     double marg_sweeps[7] = {0, 0, 0, 0, 0, 0, 0};
     int sample_seg = 0, flushes_in_flight = 0;
     bool marg_pending = false;  // marginalisation kernels enqueued, results not yet read back
     int marg_n = 0;
+    bool states_upload_pending = false;
 };
 
 namespace {
@@ -227,17 +229,17 @@ int refresh_sqrt_info(ve_estimator* e) {
     for (int f = 1; f <= e->W; f++) {
         const int s = e->slot_of[f];
         if (e->slot_valid[f] && e->sqrt_dirty[s] && e->dt_buf[f].size() > 0) {
-            e->h_marg_i[cnt++] = s;
+            e->h_which[cnt++] = s;
             e->sqrt_dirty[s] = false;
         }
     }
     if (!cnt) return VE_OK;
-    VE_CUDA(cudaMemcpyAsync(e->d_which.p, e->h_marg_i, sizeof(int) * cnt, cudaMemcpyHostToDevice, e->stream));
+    // no host wait: h_which is rewritten only after the next solve's read-back has drained the stream
+    VE_CUDA(cudaMemcpyAsync(e->d_which.p, e->h_which, sizeof(int) * cnt, cudaMemcpyHostToDevice, e->stream));
     e->prof.begin(e->stream);
     vb::launch_sqrt_info(e->d_preint.p, e->d_which.p, cnt, e->stream);
     e->prof.end(7, e->stream);
     e->last_launches++;
-    VE_CUDA(cudaStreamSynchronize(e->stream));
     return VE_OK;
 }
 
@@ -375,6 +377,10 @@ void set_parameter(ve_estimator* e) {
 }
 
 void clear_state(ve_estimator* e) {
+    if (e->stream) cudaStreamSynchronize(e->stream);  // nothing of the old state may still be in flight
+    e->marg_pending = false;
+    e->states_upload_pending = false;
+    e->flushes_in_flight = 0;
     for (int i = 0; i <= e->W; i++) {
         e->Rs[i] = Mat3();
         e->Ps[i] = e->Vs[i] = e->Bas[i] = e->Bgs[i] = Vec3();
@@ -657,11 +663,17 @@ int build_problem(ve_estimator* e, vb::BaProblem& p, bool upload_tables) {
 }
 
 int upload_states(ve_estimator* e, int* n_lam) {
+    if (e->states_upload_pending) {  // marginalize() of the previous frame staged its linearisation point here
+        VE_CUDA(cudaEventSynchronize(e->ev[6]));
+        e->states_upload_pending = false;
+    }
     pack_states(e, e->h_states, n_lam);
     VE_CUDA(cudaMemcpyAsync(e->d_states[0].p, e->h_states, sizeof(double) * states_doubles(e), cudaMemcpyHostToDevice, e->stream));
     e->h2d_bytes += sizeof(double) * states_doubles(e);
     return VE_OK;
 }
+
+int finish_marg(ve_estimator* e);
 
 // The marginalisation branches of Estimator::optimization (estimator.cpp:826-999)
 int marginalize(ve_estimator* e, vb::BaProblem& p) {
@@ -673,10 +685,17 @@ int marginalize(ve_estimator* e, vb::BaProblem& p) {
         return false;
     };
     if (!old && !(e->has_prior && prior_has(0, W - 1))) return VE_OK;
+    // the previous marginalisation's diagnostics are collected before its staging area is reused (the stream has just
+    // been drained by the solve's read-back: no wait)
+    int rc = finish_marg(e);
+    if (rc) return rc;
     // vector2double() after double2vector(): the linearisation point is the re-anchored state
     int n_lam = 0;
-    int rc = upload_states(e, &n_lam);
+    rc = upload_states(e, &n_lam);
     if (rc) return rc;
+    VE_CUDA(cudaEventRecord(e->ev[6], e->stream));
+    e->states_upload_pending = true;
+    VE_CUDA(cudaEventRecord(e->ev[5], e->stream));
     // which parameter blocks take part
     std::vector<bool> t_pose(F, false), t_sb(F, false);
     bool t_ex = false, t_td = false;
@@ -800,13 +819,15 @@ int finish_marg(ve_estimator* e) {
     e->prior_raw_b.assign(e->h_marg_out + (size_t)e->nmax * e->nmax, e->h_marg_out + (size_t)e->nmax * e->nmax + n);
     if (n + 7 <= e->nmax)
         for (int k = 0; k < 7; k++) e->marg_sweeps[k] = e->h_marg_out[(size_t)e->nmax * e->nmax + n + k];
-    cudaEventElapsedTime(&e->last_ms[2], e->ev[2], e->ev[3]);
+    cudaEventElapsedTime(&e->last_ms[2], e->ev[5], e->ev[3]);
     return VE_OK;
 }
 
 int optimization(ve_estimator* e) {
     int rc;
-    if ((rc = finish_marg(e))) return rc;  // staging buffers and the event pair are about to be reused
+    // No wait for the previous frame's marginalisation here: everything below is enqueued behind it on the same stream
+    // while it is still running, so the host side of a frame (bookkeeping, problem tables, uploads, 26 launches) is
+    // hidden instead of sitting between two kernels.
     VE_CUDA(cudaEventRecord(e->ev[0], e->stream));
     for (int f = 0; f <= e->W; f++)
         if ((rc = flush_frame(e, f))) return rc;
@@ -996,6 +1017,7 @@ int ve_create(const ve_config* cfg, ve_estimator** out) {
     VE_TRY(cudaHostAlloc(&e->h_prior, sizeof(double) * 9 * 64, cudaHostAllocDefault));
     VE_TRY(cudaHostAlloc(&e->h_prior_i, sizeof(int) * 192, cudaHostAllocDefault));
     VE_TRY(cudaHostAlloc(&e->h_marg_i, sizeof(int) * std::max<size_t>(2 * (size_t)e->Lmax, 64), cudaHostAllocDefault));
+    VE_TRY(cudaHostAlloc(&e->h_which, sizeof(int) * 64, cudaHostAllocDefault));
     VE_TRY(cudaHostAlloc(&e->h_marg_out, sizeof(double) * ((size_t)e->nmax * e->nmax + e->nmax), cudaHostAllocDefault));
 #undef VE_TRY
     *out = e;
@@ -1011,7 +1033,7 @@ void ve_destroy(ve_estimator* e) {
     e->d_ints.release(); e->d_obs.release(); e->d_S.release(); e->d_Spk.release(); e->d_Hfull.release(); e->d_gred.release(); e->d_vec.release();
     e->d_work.release(); e->d_st.release(); e->d_marg.release(); e->d_marg_i.release();
     cudaFreeHost(e->h_states); cudaFreeHost(e->h_obs); cudaFreeHost(e->h_ints); cudaFreeHost(e->h_samples); cudaFreeHost(e->h_preint);
-    cudaFreeHost(e->h_st); cudaFreeHost(e->h_prior); cudaFreeHost(e->h_prior_i); cudaFreeHost(e->h_marg_i); cudaFreeHost(e->h_marg_out);
+    cudaFreeHost(e->h_st); cudaFreeHost(e->h_prior); cudaFreeHost(e->h_prior_i); cudaFreeHost(e->h_marg_i); cudaFreeHost(e->h_which); cudaFreeHost(e->h_marg_out);
     for (auto& ev : e->ev)
         if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
