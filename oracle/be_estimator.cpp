@@ -251,6 +251,10 @@ class Estimator {
     CauchyLoss loss{1.0};
     SolveSummary last_summary;
     int n_solves = 0, n_reboots = 0, last_landmarks = 0, last_visual = 0;
+    // test hook: called with (columns, residuals) right before Solve of solve number probe_solve (-1: every solve)
+    void (*probe_cb)(int, int) = nullptr;
+    int probe_solve = -1;
+    Problem* probe_problem = nullptr;
     double sqrt_info_scale;
 
     explicit Estimator(const BeConfig& c) : cfg(c), W(c.window_size) {
@@ -458,6 +462,11 @@ class Estimator {
         }
         last_landmarks = feature_index + 1;
         last_visual = f_m_cnt;
+        if (probe_cb && (probe_solve < 0 || probe_solve == n_solves)) {  // tests: hand the problem to an independent optimiser
+            probe_problem = &problem;
+            probe_cb(ProbeColumns(problem), ProbeResiduals(problem));
+            probe_problem = nullptr;
+        }
         last_summary = Solve(problem, cfg.num_iterations);
         n_solves++;
         double2vector();
@@ -732,6 +741,19 @@ void orc_projection_factor(int use_td, double focal_length, double TR, double RO
     }
 }
 void orc_pose_plus(const double* x, const double* delta, double* out) { pose_plus(x, delta, out); }
+// solver cross-check hooks (be_solver.h: ProbeEvaluate)
+void orc_est_set_probe(void* h, void (*cb)(int, int), int solve_index) {
+    Estimator* e = static_cast<Estimator*>(h);
+    e->probe_cb = cb;
+    e->probe_solve = solve_index;
+}
+int orc_est_probe_residuals(void* h, const double* delta, double* out) {
+    Estimator* e = static_cast<Estimator*>(h);
+    if (!e->probe_problem) return -1;
+    ProbeEvaluate(*e->probe_problem, delta, out);
+    return 0;
+}
+void orc_est_set_iterations(void* h, int n) { static_cast<Estimator*>(h)->cfg.num_iterations = n; }
 // sym_eigen / cholesky known answers
 void orc_sym_eigen_ql(int n, const double* A, double* w, double* V) {
     Mat a(n, n), v;

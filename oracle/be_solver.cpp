@@ -328,6 +328,41 @@ double dot(const std::vector<double>& a, const std::vector<double>& b) {
 
 }  // namespace
 
+int ProbeColumns(Problem& problem) { return reduce_program(problem).ncols; }
+
+int ProbeResiduals(Problem& problem) {
+    int n = 0;
+    for (auto& r : problem.residuals) n += r.cf->num_residuals;
+    return n;
+}
+
+void ProbeEvaluate(Problem& problem, const double* delta, double* out) {
+    Program g = reduce_program(problem);
+    const int nb = (int)problem.blocks.size();
+    std::vector<std::vector<double>> x(nb), xn;
+    for (int b = 0; b < nb; b++) x[b].assign(problem.blocks[b].ptr, problem.blocks[b].ptr + problem.blocks[b].size);
+    plus(g, x, std::vector<double>(delta, delta + g.ncols), xn);
+    std::vector<const double*> params;
+    int off = 0;
+    for (auto& rb : problem.residuals) {
+        const int nr = rb.cf->num_residuals;
+        params.resize(rb.blocks.size());
+        for (size_t i = 0; i < rb.blocks.size(); i++) params[i] = xn[rb.blocks[i]].data();
+        rb.cf->Evaluate(params.data(), out + off, nullptr);
+        if (rb.loss) {
+            double sq = 0;
+            for (int k = 0; k < nr; k++) sq += out[off + k] * out[off + k];
+            if (sq > 0) {
+                double rho[3];
+                rb.loss->Evaluate(sq, rho);
+                const double sc = std::sqrt(rho[0] / sq);
+                for (int k = 0; k < nr; k++) out[off + k] *= sc;
+            }
+        }
+        off += nr;
+    }
+}
+
 SolveSummary Solve(Problem& problem, int max_num_iterations) {
     SolveSummary sum;
     Program g = reduce_program(problem);

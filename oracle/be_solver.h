@@ -48,4 +48,12 @@ class Problem {
 
 SolveSummary Solve(Problem& problem, int max_num_iterations);
 
+// Cross-check hooks (tests/test_oracle_solver_minimum.py): the robustified residual vector of the whole problem,
+// sqrt(rho(|r_i|^2)) r_i / |r_i| per residual block (so that its squared norm is twice the Ceres cost), at the current
+// parameter values (+) delta, delta in the local coordinates of the non-constant blocks (poses 6, others their size).
+// An independent optimiser (scipy) minimises it and must land on the minimum Solve converges to.
+int ProbeColumns(Problem& problem);
+int ProbeResiduals(Problem& problem);
+void ProbeEvaluate(Problem& problem, const double* delta, double* out);
+
 }  // namespace orc

@@ -250,6 +250,27 @@ class OracleEstimator:
             lib().orc_est_destroy(self.h)
             self.h = None
 
+    # ---- solver cross-check hooks (oracle/be_solver.h ProbeEvaluate)
+    PROBE_CB = C.CFUNCTYPE(None, C.c_int, C.c_int)
+
+    def set_probe(self, fn, solve_index=-1):
+        """fn(n_columns, n_residuals, evaluate) is called right before Solve of the given solve (inside processImage);
+        evaluate(delta) returns the robustified residual vector at x (+) delta."""
+        def cb(ncols, nres):
+            def evaluate(delta):
+                delta = np.ascontiguousarray(delta, np.float64)
+                out = np.zeros(nres)
+                rc = lib().orc_est_probe_residuals(self.h, P(delta, f64p), P(out, f64p))
+                assert rc == 0
+                return out
+            fn(ncols, nres, evaluate)
+        self._probe = self.PROBE_CB(cb) if fn else self.PROBE_CB()
+        lib().orc_est_set_probe.argtypes = [C.c_void_p, self.PROBE_CB, C.c_int]
+        lib().orc_est_set_probe(self.h, self._probe, solve_index)
+
+    def set_iterations(self, n):
+        lib().orc_est_set_iterations(self.h, int(n))
+
     def set_seed(self, rows, ba, bg):
         rows = _d(rows)
         lib().orc_est_set_seed(self.h, len(rows), P(rows, f64p), P(_d(ba), f64p), P(_d(bg), f64p))
