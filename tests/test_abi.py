@@ -65,3 +65,14 @@ def test_host_shims_compile_and_link(lib, tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert "no device" in out.stdout or "tracked" in out.stdout
+
+
+def test_offline_replay_example_builds(lib, tmp_path):
+    """examples/offline_replay.cpp: a ROS-free C++ client of the three headers (tracker, estimator, replay)."""
+    from vins_mono_b200 import LIB_PATH
+    exe = tmp_path / "offline_replay"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "offline_replay.cpp"), "-L", os.path.dirname(LIB_PATH), "-lvinsb200",
+                           f"-Wl,-rpath,{os.path.dirname(LIB_PATH)}", "-lpthread", "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 2 and "usage" in out.stderr
