@@ -98,6 +98,16 @@ int vt_debug_gftt(vt_tracker* t, const uint8_t* img, size_t row_stride, const ui
                   float* corners, int* n_candidates, float* eig_out);
 int vt_debug_lk(vt_tracker* t, const uint8_t* prev, const uint8_t* next, size_t row_stride, const float* pts, int n,
                 float* next_pts, uint8_t* status);
+/* The host side of rejectWithF (feature_tracker.cpp:191: cv::findFundamentalMat(un_cur, un_forw, FM_RANSAC, F_THRESHOLD,
+ * 0.99, status)) on n correspondences of (x, y) floats; needs no handle and no device.  Returns 1 when a model was
+ * found (status = inlier mask), 0 otherwise (status all zero). */
+int vt_debug_fundamental_ransac(const float* pts1, const float* pts2, int n, double threshold, double confidence, uint8_t* status);
+/* PinholeCamera::liftProjective (PinholeCamera.cc:450-510) as undistortedPoints() applies it: n pixel pairs -> n normalised
+ * (x, y) pairs; intrinsics8 = fx fy cx cy k1 k2 p1 p2.  Host only. */
+int vt_debug_lift_projective(const double* intrinsics8, const double* px, int n, double* out_xy);
+/* Half widths per row offset |dy| = 0..radius of the filled cv::circle that setMask() draws (feature_tracker.cpp:66): the
+ * table the mask kernel rasterises discs from.  out has radius + 1 entries.  Host only. */
+int vt_debug_disc_half_widths(int radius, int* out);
 
 #ifdef __cplusplus
 }

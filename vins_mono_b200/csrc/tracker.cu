@@ -620,6 +620,26 @@ int vt_node_pack(const vt_tracker* t, int capacity, float* xy_un, float* id_of_p
     return k;
 }
 
+int vt_debug_fundamental_ransac(const float* pts1, const float* pts2, int n, double threshold, double confidence, uint8_t* status) {
+    if (!pts1 || !pts2 || !status || n < 0) return VT_ERR_INVALID;
+    return vb::fundamental_ransac_mask(pts1, pts2, n, threshold, confidence, status) ? 1 : 0;
+}
+
+int vt_debug_lift_projective(const double* intrinsics8, const double* px, int n, double* out_xy) {
+    if (!intrinsics8 || !px || !out_xy || n < 0) return VT_ERR_INVALID;
+    vt_config c{};
+    for (int i = 0; i < 8; i++) c.intrinsics[i] = intrinsics8[i];
+    for (int k = 0; k < n; k++) lift_projective(c, px[2 * k], px[2 * k + 1], out_xy[2 * k], out_xy[2 * k + 1]);
+    return VT_OK;
+}
+
+int vt_debug_disc_half_widths(int radius, int* out) {
+    if (radius < 0 || !out) return VT_ERR_INVALID;
+    const std::vector<int> hw = disc_half_widths(radius);
+    for (int d = 0; d <= radius; d++) out[d] = hw[d];
+    return VT_OK;
+}
+
 int vt_last_timing(const vt_tracker* t, float* device_ms, int* kernel_launches) {
     if (!t) return VT_ERR_INVALID;
     if (device_ms) *device_ms = t->last_ms;
