@@ -1,6 +1,7 @@
-"""The product's host-side front-end pieces checked on a box without a GPU: the F-matrix RANSAC
-a box without a GPU: bit-identical inlier masks to cv2.findFundamentalMat on the stored golden problems
-(tests/golden/frontend_ops.npz, generated by tests/golden/make_frontend_golden.py) and the degenerate inputs."""
+"""The product's host-side front-end pieces (vins_mono_b200/csrc/{fm_ransac.cpp,tracker.cu}) checked on a box without
+a GPU through handle-free debug entries: the F-matrix RANSAC of rejectWithF (inlier masks bit-identical to
+cv2.findFundamentalMat on the golden problems of tests/golden/frontend_ops.npz, plus degenerate inputs), the disc table of
+setMask (reproduces cv2's filled circles) and PinholeCamera::liftProjective."""
 import ctypes as C
 import os
 
