@@ -57,6 +57,13 @@ int vr_stats(const vr_session* s, int seq, int* frames, long long* launches, dou
  * returns the number available. */
 int vr_trajectory(const vr_session* s, int seq, int cap, double* stamps, double* positions3);
 
+/* Test access to the IMU side of the estimator loop (needs no device): for each of n_stamps image stamps, in order, the
+ * (dt, acc, gyr) samples that would be handed to ve_process_imu before that image — getMeasurements' selection, the
+ * per-sample dt and the interpolated sample at the stamp (estimator_node.cpp:98-136, 225-265).  counts[k] samples for
+ * stamp k, concatenated in dt / acc_out / gyr_out (capacity cap samples).  Returns the total or < 0. */
+int vr_debug_imu_batches(int n_imu, const double* imu_t, const double* acc, const double* gyr, int n_stamps, const double* stamps,
+                         int cap, int* counts, double* dt, double* acc_out, double* gyr_out);
+
 #ifdef __cplusplus
 }
 #endif

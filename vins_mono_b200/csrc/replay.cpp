@@ -171,6 +171,18 @@ void imu_one(SeqState* q, int k, double img_t) {
     }
 }
 
+// getMeasurements + the dt / interpolation rules of process() for one image stamp: fills q->dt / acc / gyr
+void collect_imu(SeqState* q, double stamp) {
+    q->dt.clear();
+    q->acc.clear();
+    q->gyr.clear();
+    while (q->imu_k < q->in.n_imu && q->in.imu_t[q->imu_k] < stamp) {
+        imu_one(q, q->imu_k, stamp);
+        q->imu_k++;
+    }
+    if (q->imu_k < q->in.n_imu) imu_one(q, q->imu_k, stamp);  // used, but stays in the buffer
+}
+
 void estimator_loop(vr_session* s, SeqState* q) {
     for (;;) {
         FeatureMsg msg = q->ch.get();
@@ -181,14 +193,7 @@ void estimator_loop(vr_session* s, SeqState* q) {
         if (q->first_msg) {
             q->first_msg = false;
         } else {
-            q->dt.clear();
-            q->acc.clear();
-            q->gyr.clear();
-            while (q->imu_k < q->in.n_imu && q->in.imu_t[q->imu_k] < msg.stamp) {
-                imu_one(q, q->imu_k, msg.stamp);
-                q->imu_k++;
-            }
-            if (q->imu_k < q->in.n_imu) imu_one(q, q->imu_k, msg.stamp);  // used, but stays in the buffer
+            collect_imu(q, msg.stamp);
             int rc = q->dt.empty() ? 0 : ve_process_imu_batch(q->est, (int)q->dt.size(), q->dt.data(), q->acc.data(), q->gyr.data());
             if (rc == 0) rc = ve_process_image(q->est, (int)msg.ids.size(), msg.ids.data(), msg.obs.data(), msg.stamp);
             if (rc < 0) {
@@ -259,6 +264,30 @@ int vr_advance(vr_session* s, int n_pub) {
     if (s->status.load() != 0) return s->status.load();
     int total = 0;
     for (size_t k = 0; k < s->seqs.size(); k++) total += s->seqs[k].frames - before[k];
+    return total;
+}
+
+int vr_debug_imu_batches(int n_imu, const double* imu_t, const double* acc, const double* gyr, int n_stamps, const double* stamps,
+                         int cap, int* counts, double* dt, double* acc_out, double* gyr_out) {
+    if (n_imu < 0 || n_stamps < 0 || !imu_t || !acc || !gyr || !stamps || !counts) return -1;
+    SeqState q;
+    q.in.n_imu = n_imu;
+    q.in.imu_t = imu_t;
+    q.in.acc = acc;
+    q.in.gyr = gyr;
+    int total = 0;
+    for (int k = 0; k < n_stamps; k++) {
+        collect_imu(&q, stamps[k]);
+        counts[k] = (int)q.dt.size();
+        for (size_t i = 0; i < q.dt.size(); i++, total++) {
+            if (total >= cap) return -2;
+            if (dt) dt[total] = q.dt[i];
+            for (int c = 0; c < 3; c++) {
+                if (acc_out) acc_out[3 * total + c] = q.acc[3 * i + c];
+                if (gyr_out) gyr_out[3 * total + c] = q.gyr[3 * i + c];
+            }
+        }
+    }
     return total;
 }
 
