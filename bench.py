@@ -338,6 +338,7 @@ def run_reference_pass(seq, ts, imgs, imu, n_init, warmup, steps):
     import orc
     trk = orc.OracleTracker(synth.tracker_config_dict())
     est = orc.OracleEstimator(orc.be_config())
+    est.set_fast_eigen(True)  # tridiagonal QL (the reference's Eigen solver class) instead of the parity tests' Jacobi
     feeder = pipeline.ImuFeeder(*imu)
     est.set_seed(pipeline.gt_seed_rows(seq, ts), seq.ba, seq.bg)
     n_pub = n_init + warmup + steps

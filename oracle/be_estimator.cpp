@@ -14,6 +14,7 @@
 // ESTIMATE_EXTRINSIC == 2.  The solver is be_solver.cpp (no wall-clock cap).
 #include <cstdio>
 #include <array>
+#include <chrono>
 #include <list>
 #include <map>
 
@@ -252,6 +253,8 @@ class Estimator {
     SolveSummary last_summary;
     int n_solves = 0, n_reboots = 0, last_landmarks = 0, last_visual = 0;
     // test hook: called with (columns, residuals) right before Solve of solve number probe_solve (-1: every solve)
+    bool fast_eigen = false;  // see MarginalizationInfo::eigen_ql
+    double prof_solve_s = 0, prof_marg_s = 0;  // accumulated wall time of Solve() and of the marginalisation (profiling)
     void (*probe_cb)(int, int) = nullptr;
     int probe_solve = -1;
     Problem* probe_problem = nullptr;
@@ -467,11 +470,14 @@ class Estimator {
             probe_cb(ProbeColumns(problem), ProbeResiduals(problem));
             probe_problem = nullptr;
         }
+        const auto t_solve0 = std::chrono::steady_clock::now();
         last_summary = Solve(problem, cfg.num_iterations);
+        prof_solve_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_solve0).count();
         n_solves++;
         double2vector();
         if (marginalization_flag == MARGIN_OLD) {
             auto mi = std::unique_ptr<MarginalizationInfo>(new MarginalizationInfo());
+            mi->eigen_ql = fast_eigen;
             vector2double();
             if (last_marginalization_info) {
                 std::vector<int> drop_set;
@@ -505,8 +511,10 @@ class Estimator {
                     }
                 }
             }
+            const auto t_m0 = std::chrono::steady_clock::now();
             mi->preMarginalize();
             mi->marginalize();
+            prof_marg_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_m0).count();
             std::map<double*, double*> addr_shift;
             for (int i = 1; i <= W; i++) {
                 addr_shift[para_Pose[i].data()] = para_Pose[i - 1].data();
@@ -521,6 +529,8 @@ class Estimator {
             if (last_marginalization_info &&
                 std::count(last_marginalization_parameter_blocks.begin(), last_marginalization_parameter_blocks.end(), para_Pose[W - 1].data())) {
                 auto mi = std::unique_ptr<MarginalizationInfo>(new MarginalizationInfo());
+                mi->eigen_ql = fast_eigen;
+            mi->eigen_ql = fast_eigen;
                 vector2double();
                 std::vector<int> drop_set;
                 for (int i = 0; i < (int)last_marginalization_parameter_blocks.size(); i++)
@@ -528,8 +538,10 @@ class Estimator {
                 mi->addResidualBlockInfo(std::make_shared<ResidualBlockInfo>(
                     std::make_shared<MarginalizationFactor>(last_marginalization_info.get()), nullptr,
                     last_marginalization_parameter_blocks, drop_set));
+                const auto t_m0 = std::chrono::steady_clock::now();
                 mi->preMarginalize();
                 mi->marginalize();
+                prof_marg_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_m0).count();
                 std::map<double*, double*> addr_shift;
                 for (int i = 0; i <= W; i++) {
                     if (i == W - 1) continue;
@@ -753,6 +765,12 @@ int orc_est_probe_residuals(void* h, const double* delta, double* out) {
     ProbeEvaluate(*e->probe_problem, delta, out);
     return 0;
 }
+void orc_est_profile(void* h, double* out2) {
+    Estimator* e = static_cast<Estimator*>(h);
+    out2[0] = e->prof_solve_s;
+    out2[1] = e->prof_marg_s;
+}
+void orc_est_set_fast_eigen(void* h, int on) { static_cast<Estimator*>(h)->fast_eigen = on != 0; }
 void orc_est_set_iterations(void* h, int n) { static_cast<Estimator*>(h)->cfg.num_iterations = n; }
 // sym_eigen / cholesky known answers
 void orc_sym_eigen_ql(int n, const double* A, double* w, double* V) {

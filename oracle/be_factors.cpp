@@ -459,7 +459,8 @@ void MarginalizationInfo::marginalize() {
     Mat V;
     Mat Amm_inv(m, m);
     if (m > 0) {
-        sym_eigen(Amm, w, V);
+        if (eigen_ql) sym_eigen_ql(Amm, w, V);
+        else sym_eigen(Amm, w, V);
         for (int i = 0; i < m; i++)
             for (int j = 0; j < m; j++) {
                 double s = 0;
@@ -480,7 +481,8 @@ void MarginalizationInfo::marginalize() {
     b_debug = bp;
     std::vector<double> S;
     Mat V2;
-    sym_eigen(Ap, S, V2);
+    if (eigen_ql) sym_eigen_ql(Ap, S, V2);
+    else sym_eigen(Ap, S, V2);
     linearized_jacobians = Mat(n, n);
     linearized_residuals.assign(n, 0.0);
     for (int k = 0; k < n; k++) {

@@ -271,6 +271,15 @@ class OracleEstimator:
     def set_iterations(self, n):
         lib().orc_est_set_iterations(self.h, int(n))
 
+    def set_fast_eigen(self, on=True):
+        """Tridiagonal QL instead of cyclic Jacobi in the marginalisation (the timed CPU baseline uses it)."""
+        lib().orc_est_set_fast_eigen(self.h, int(bool(on)))
+
+    def profile(self):
+        out = (C.c_double * 2)()
+        lib().orc_est_profile(self.h, out)
+        return dict(solve_s=out[0], marg_s=out[1])
+
     def set_seed(self, rows, ba, bg):
         rows = _d(rows)
         lib().orc_est_set_seed(self.h, len(rows), P(rows, f64p), P(_d(ba), f64p), P(_d(bg), f64p))
