@@ -49,6 +49,7 @@ typedef struct ve_config {
 } ve_config;
 
 typedef struct ve_estimator ve_estimator;
+typedef struct ve_batch ve_batch;
 
 int ve_create(const ve_config* cfg, ve_estimator** out);
 void ve_destroy(ve_estimator* e);
@@ -82,6 +83,54 @@ int ve_set_profile(ve_estimator* e, int on);
 int ve_kernel_times(const ve_estimator* e, double* ms8, int* count8);
 /* Host<->device bytes moved by the last ve_process_image. */
 int ve_last_traffic(const ve_estimator* e, double* h2d_bytes, double* d2h_bytes);
+
+/* tic (3) and ric (9, row-major) as currently estimated (estimator.h:75-76); either may be NULL. */
+int ve_get_extrinsic(const ve_estimator* e, double* tic3, double* ric9);
+
+/* ---- Batched sequences (SURVEY.md 8b "Threading", BASELINE configs[2] / [4]) --------------------------------------
+ * n independent estimators with one configuration that advance frame by frame TOGETHER: one host-to-device copy, one
+ * kernel launch per solver stage (the member index is a grid dimension) and one device-to-host copy per frame for the
+ * whole batch, the host bookkeeping of the members on a thread pool.  Within a member the serial chain of the reference
+ * (last_marginalization_info feeding the next optimisation, estimator.cpp:929-930) is kept: frame k+1 of a member is
+ * enqueued behind its own frame k.  A stand-alone handle from ve_create is a batch of one running the same code.
+ *
+ *   ve_batch_member            borrowed handle of member k for the per-sequence calls: ve_set_seed, ve_process_imu(_batch),
+ *                              ve_clear_state, ve_get_states, ve_info, ve_get_prior, ve_last_traffic (NOT ve_process_image /
+ *                              ve_destroy: members are driven and destroyed through the batch)
+ *   ve_batch_process_image     Estimator::processImage for every member k with active[k] != 0 (NULL = all): n[k] points,
+ *                              ids[k], xyz_uv_vel[k], stamps[k] as in ve_process_image.  status (may be NULL) receives each
+ *                              member's ve_status; the return value is the first non-zero one.
+ *   ve_batch_last_timing       device ms of the last batch frame: [0] pre-integration, [1] solve, [2] marginalisation, [3] total
+ */
+int ve_batch_create(const ve_config* cfg, int n, ve_batch** out);
+void ve_batch_destroy(ve_batch* b);
+int ve_batch_size(const ve_batch* b);
+ve_estimator* ve_batch_member(ve_batch* b, int k);
+const char* ve_batch_last_error(const ve_batch* b);
+int ve_batch_process_image(ve_batch* b, const int* active, const int* n, const int* const* ids, const double* const* xyz_uv_vel,
+                           const double* stamps, int* status);
+int ve_batch_last_timing(const ve_batch* b, float* ms4, int* launches);
+int ve_batch_set_profile(ve_batch* b, int on);
+int ve_batch_kernel_times(const ve_batch* b, double* ms8, int* count8);
+/* Waits until everything the batch has enqueued (including the last marginalisation) has finished. */
+int ve_batch_sync(ve_batch* b);
+
+/* ---- Single-factor test entries (parity tests; projection_factor.cpp:176-224 has the reference's own check()) -------
+ * The device functions of the solve evaluated on caller-supplied parameter blocks, Jacobians in the 6-dof tangent
+ * parameterisation (the reference's 7th column is identically zero).
+ *   ve_debug_projection_factor  params23 = pose_i 7 (p, qx qy qz qw) | pose_j 7 | ex_pose 7 | inverse depth | td;
+ *                               data12 = pts_i xy, pts_j xy, velocity_i xy, velocity_j xy, td_i, td_j, row_i, row_j;
+ *                               out43 = residual 2 | J row 0 (20: pose_i 6, pose_j 6, ex 6, depth, td) | J row 1 | rho/2.
+ *                               use_td selects ProjectionTdFactor; robust applies CauchyLoss(1) + the corrector.
+ *   ve_debug_imu_factor         integrates n samples (sample 0 = acc_0 / gyr_0 of the IntegrationBase, dt[0] unused) with
+ *                               noise4 = acc_n, gyr_n, acc_w, gyr_w and linearised biases ba, bg on the device;
+ *                               out_preint (686) = sum_dt | delta_p 3 | delta_q wxyz | delta_v 3 | jacobian 225 | covariance 225 |
+ *                               sqrt_info 225; with params32 = pose_i 7 | speedbias_i 9 | pose_j 7 | speedbias_j 9,
+ *                               out_factor (465) = whitened residual 15 | whitened Jacobian 15 x 30 (pose_i 6, sb_i 9, pose_j 6, sb_j 9). */
+int ve_debug_projection_factor(const double* params23, const double* data12, int use_td, double focal_length, double tr, double row,
+                               int robust, double* out43);
+int ve_debug_imu_factor(const double* noise4, double g_norm, const double* ba, const double* bg, int n, const double* dt,
+                        const double* acc, const double* gyr, const double* params32, double* out_preint, double* out_factor);
 
 /* Solver internals of the last solve (profiling/tests): out[0] linear-solver retries, [1] mu, [2] radius,
  * [3..10] per-phase cycle counters of the step kernel summed over the iterations, [11..12] cycles of the

@@ -5,5 +5,5 @@ ctypes mirror of the reference's host classes for tests and benchmarks.  There i
 loading fails loudly when the library is missing, creating a tracker fails when no CUDA device exists.
 """
 from .tracker import FeatureTracker, TrackerConfig, load_library, LIB_PATH  # noqa: F401
-from .estimator import Estimator, EstimatorConfig  # noqa: F401
+from .estimator import Estimator, EstimatorBatch, EstimatorConfig, debug_projection_factor, debug_imu_factor  # noqa: F401
 from .replay import ReplaySession  # noqa: F401

@@ -301,6 +301,51 @@ __device__ inline void eval_imu_raw(const BaDims& d, const PreInt& pre, const do
     put(12, 27, I3);
 }
 
+// Utility::R2ypr / ypr2R (utility.h:70-112, degrees) and Eigen's rotation-matrix -> quaternion conversion, used by the
+// device-side double2vector / vector2double.
+__device__ inline V3d R2ypr_dev(const M3d& R) {
+    const V3d n = mk(R.m[0], R.m[3], R.m[6]), o = mk(R.m[1], R.m[4], R.m[7]), a = mk(R.m[2], R.m[5], R.m[8]);
+    const double y = atan2(n.y, n.x);
+    const double p = atan2(-n.z, n.x * cos(y) + n.y * sin(y));
+    const double r = atan2(a.x * sin(y) - a.y * cos(y), -o.x * sin(y) + o.y * cos(y));
+    return mk(y, p, r) * (1.0 / 3.14159265358979323846 * 180.0);
+}
+__device__ inline M3d ypr2R_dev(V3d ypr) {
+    const double y = ypr.x / 180.0 * 3.14159265358979323846, p = ypr.y / 180.0 * 3.14159265358979323846,
+                 r = ypr.z / 180.0 * 3.14159265358979323846;
+    M3d Rz = mident(), Ry = mident(), Rx = mident();
+    Rz.m[0] = cos(y); Rz.m[1] = -sin(y); Rz.m[3] = sin(y); Rz.m[4] = cos(y);
+    Ry.m[0] = cos(p); Ry.m[2] = sin(p); Ry.m[6] = -sin(p); Ry.m[8] = cos(p);
+    Rx.m[4] = cos(r); Rx.m[5] = -sin(r); Rx.m[7] = sin(r); Rx.m[8] = cos(r);
+    return mmul(mmul(Rz, Ry), Rx);
+}
+__device__ inline Q4 q_from_R(const M3d& m) {
+    Q4 q;
+    double t = m.m[0] + m.m[4] + m.m[8];
+    if (t > 0) {
+        t = sqrt(t + 1.0);
+        q.w = 0.5 * t;
+        t = 0.5 / t;
+        q.x = (m.m[7] - m.m[5]) * t;
+        q.y = (m.m[2] - m.m[6]) * t;
+        q.z = (m.m[3] - m.m[1]) * t;
+    } else {
+        int i = 0;
+        if (m.m[4] > m.m[0]) i = 1;
+        if (m.m[8] > m.m[4 * i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrt(m.m[4 * i] - m.m[4 * j] - m.m[4 * k] + 1.0);
+        double c[3];
+        c[i] = 0.5 * t;
+        t = 0.5 / t;
+        q.w = (m.m[3 * k + j] - m.m[3 * j + k]) * t;
+        c[j] = (m.m[3 * j + i] + m.m[3 * i + j]) * t;
+        c[k] = (m.m[3 * k + i] + m.m[3 * i + k]) * t;
+        q.x = c[0]; q.y = c[1]; q.z = c[2];
+    }
+    return q;
+}
+
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

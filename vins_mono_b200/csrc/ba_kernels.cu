@@ -28,11 +28,15 @@ namespace vb {
 // ------------------------------------------------------------------------------------------------
 // IMU pre-integration: appends n samples (dt, acc[3], gyr[3]) to one slot.  Single CTA of 256 threads;
 // the 15x15 products run in parallel, the 3x3 geometry of each step on thread 0.
-__global__ void __launch_bounds__(256) preint_push_kernel(PreInt* __restrict__ slot, int n, const double* __restrict__ samples,
-                                                          double acc_n, double gyr_n, double acc_w, double gyr_w) {
-    __shared__ double F[225], V[270], J[225], P[225], T[225], nz[18];
-    __shared__ double st[20];  // dp dq dv acc0 gyr0
+struct PreintSmem {
+    double F[225], V[270], J[225], P[225], T[225], nz[18];
+    double st[20];  // dp dq dv acc0 gyr0
+};
+__device__ void preint_push_dev(PreInt* __restrict__ slot, int n, const double* __restrict__ samples, double acc_n, double gyr_n,
+                                double acc_w, double gyr_w, PreintSmem& sm) {
+    double *F = sm.F, *V = sm.V, *J = sm.J, *P = sm.P, *T = sm.T, *nz = sm.nz, *st = sm.st;
     const int tid = threadIdx.x;
+    __syncthreads();  // the previous job of this CTA is done with the shared arrays
     for (int i = tid; i < 225; i += 256) {
         J[i] = slot->jac[i];
         P[i] = slot->cov[i];
@@ -139,14 +143,14 @@ __global__ void __launch_bounds__(256) preint_push_kernel(PreInt* __restrict__ s
         for (int i = 0; i < 4; i++) slot->dq[i] = st[3 + i];
         slot->sum_dt = st[16];
     }
+    __threadfence_block();
+    __syncthreads();  // the slot is complete in global memory before the next job (or the sqrt_info refresh) reads it
 }
 
 // new IntegrationBase{acc_0, gyr_0, ba, bg}: identity Jacobian, zero covariance (integration_base.h:13-28)
-struct PreIntInit {
-    double acc0[3], gyr0[3], ba[3], bg[3];
-};
-__global__ void __launch_bounds__(256) preint_init_kernel(PreInt* __restrict__ slot, PreIntInit v) {
+__device__ void preint_init_dev(PreInt* __restrict__ slot, const PreintJob& v) {
     const int tid = threadIdx.x;
+    __syncthreads();
     for (int i = tid; i < 225; i += 256) {
         slot->jac[i] = (i / 15 == i % 15) ? 1.0 : 0.0;
         slot->cov[i] = 0.0;
@@ -165,15 +169,14 @@ __global__ void __launch_bounds__(256) preint_init_kernel(PreInt* __restrict__ s
             slot->gyr0[i] = v.gyr0[i];
         }
     }
+    __threadfence_block();
+    __syncthreads();
 }
 
 // sqrt_info = chol_lower(cov^-1)^T for each listed slot (one warp each; Gauss-Jordan with partial pivoting).
-__global__ void __launch_bounds__(32) sqrt_info_kernel(PreInt* __restrict__ slots, const int* __restrict__ which, int count) {
-    __shared__ double A[15][31];
-    __shared__ double Lm[15][15];
+// Runs on the first warp of the CTA.
+__device__ void sqrt_info_dev(PreInt* __restrict__ s, double (*A)[31], double (*Lm)[15]) {
     const int lane = threadIdx.x;
-    if ((int)blockIdx.x >= count) return;
-    PreInt* s = slots + which[blockIdx.x];
     for (int i = lane; i < 225; i += 32) {
         A[i / 15][i % 15] = s->cov[i];
         A[i / 15][15 + i % 15] = (i / 15 == i % 15) ? 1.0 : 0.0;
@@ -220,8 +223,48 @@ __global__ void __launch_bounds__(32) sqrt_info_kernel(PreInt* __restrict__ slot
     for (int i = lane; i < 225; i += 32) s->sqrt_info[i] = Lm[i % 15][i / 15];  // transpose
 }
 
+// One CTA per (pre-integration slot, member): executes the member's jobs for that slot in list order (new
+// IntegrationBase, push_back of the samples that arrived since the last solve: processIMU / slideWindow /
+// repropagate, estimator.cpp:84-118, 1070-1081), then refreshes the cached sqrt_info if the slot takes part in
+// this frame's problem.
+__global__ void __launch_bounds__(256) preint_jobs_kernel(BaSeq* __restrict__ seqs) {
+    __shared__ PreintSmem sm;
+    __shared__ double sqA[15][31], sqL[15][15];
+    const BaSeq& q = seqs[blockIdx.y];
+    const int slot = blockIdx.x;
+    const int nj = q.n_jobs;
+    PreInt* pre = q.p.preint + slot;
+    for (int j = 0; j < nj; j++) {
+        const PreintJob& job = q.jobs[j];
+        if (job.slot != slot) continue;  // CTA-uniform
+        if (job.type == 0)
+            preint_init_dev(pre, job);
+        else if (job.n > 0)
+            preint_push_dev(pre, job.n, q.samples + 7 * (size_t)job.sample_off, q.noise[0], q.noise[1], q.noise[2], q.noise[3], sm);
+    }
+    if ((q.sqrt_mask >> slot) & 1u) {
+        __syncthreads();
+        if (threadIdx.x < 32) sqrt_info_dev(pre, sqA, sqL);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ba_zero_kernel(BaProblem p, int initial) {
+// Copies a member's descriptor part into shared memory (kernel parameters used to carry it; with a batch it lives
+// in device memory and every field would otherwise be a dependent global load).
+template <class T>
+__device__ __forceinline__ void load_desc(T* dst, const T* src) {
+    static_assert(sizeof(T) % 8 == 0, "descriptor structs are multiples of 8 bytes");
+    const int nth = blockDim.x * blockDim.y * blockDim.z;
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    for (int i = tid; i < (int)(sizeof(T) / 8); i += nth)
+        reinterpret_cast<unsigned long long*>(dst)[i] = reinterpret_cast<const unsigned long long*>(src)[i];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) ba_zero_kernel(const BaSeq* __restrict__ seqs, int initial) {
+    const BaSeq& q = seqs[blockIdx.y];
+    if (!q.active) return;
+    const BaProblem& p = q.p;
     const SolverState* st = p.st;
     if (!initial && (st->done || !st->cand_valid)) return;
     const int b = initial ? st->cur : 1 - st->cur;
@@ -520,11 +563,21 @@ __device__ void lin_prior(const BaProblem& p, const BaStates& x, const BaAccum& 
 }  // namespace
 
 #define LIN_WARPS 4
-__global__ void __launch_bounds__(32 * LIN_WARPS) ba_linearize_kernel(BaProblem p, int initial) {
+__host__ __device__ inline int ba_linearize_grid(const BaDims& d) { return (d.L + LIN_WARPS - 1) / LIN_WARPS + d.W + 1; }
+__global__ void __launch_bounds__(32 * LIN_WARPS) ba_linearize_kernel(const BaSeq* __restrict__ seqs, int initial) {
     __shared__ double sJraw[450], sJw[450], srr[15], srw[15];
     __shared__ int imu_valid;
+    __shared__ BaProblem sp;
+    const BaSeq& q = seqs[blockIdx.y];
+    if (!q.active) return;
+    {
+        const SolverState* st0 = &q.st;
+        if (!initial && (st0->done || !st0->cand_valid)) return;
+    }
+    load_desc(&sp, &q.p);
+    const BaProblem& p = sp;
     SolverState* st = p.st;
-    if (!initial && (st->done || !st->cand_valid)) return;
+    if ((int)blockIdx.x >= ba_linearize_grid(p.dims)) return;  // the grid is sized for the largest member of the batch
     const int b = initial ? st->cur : 1 - st->cur;
     const BaStates x = p.x[b];
     const BaAccum a = p.acc[b];
@@ -543,7 +596,7 @@ __global__ void __launch_bounds__(32 * LIN_WARPS) ba_linearize_kernel(BaProblem 
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned t = atomicAdd(&st->lin_ticket, 1u);
-        if (t == gridDim.x - 1) {
+        if (t == (unsigned)ba_linearize_grid(p.dims) - 1u) {
             st->lin_ticket = 0;
             __threadfence();
             decide(p, initial);
@@ -551,7 +604,6 @@ __global__ void __launch_bounds__(32 * LIN_WARPS) ba_linearize_kernel(BaProblem 
     }
 }
 
-int ba_linearize_grid(const BaDims& d) { return (d.L + LIN_WARPS - 1) / LIN_WARPS + d.W + 1; }
 
 // ------------------------------------------------------------------------------------------------
 // Landmark elimination as a dense, deterministic tiled product:
@@ -565,9 +617,13 @@ __device__ __forceinline__ double lm_inv_lambda(const BaProblem& p, const BaAccu
     return 1.0 / (h + mu * d2 / (s * s));
 }
 
-__global__ void __launch_bounds__(ST* ST) ba_schur_kernel(BaProblem p) {
+__global__ void __launch_bounds__(ST* ST) ba_schur_kernel(const BaSeq* __restrict__ seqs) {
+    __shared__ BaProblem sp;
+    const BaSeq& q = seqs[blockIdx.z];
+    if (!q.active || q.st.done) return;
+    load_desc(&sp, &q.p);
+    const BaProblem& p = sp;
     const SolverState* st = p.st;
-    if (st->done) return;
     if (blockIdx.y > blockIdx.x) {
         // The product needs the upper tiles only; the CTAs of the lower triangle clear the accumulators the next
         // linearisation (of the candidate point) adds into, which saves a launch per iteration.
@@ -993,13 +1049,17 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 
 #define STEP_MAXD 352
-__global__ void __launch_bounds__(512) ba_step_kernel(BaProblem p, int use_smem_chol) {
+__global__ void __launch_bounds__(512) ba_step_kernel(const BaSeq* __restrict__ seqs, int use_smem_chol) {
     extern __shared__ __align__(16) double chol_smem[];  // panel copy (CHOL_NB * CHOL_PS), then the packed factor
     __shared__ double red[32];
     __shared__ double rdiag[STEP_MAXD], ysm[STEP_MAXD], linv[(STEP_MAXD / CHOL_NB) * 64];
     __shared__ int flag;
+    __shared__ BaProblem sp;
+    const BaSeq& q = seqs[blockIdx.x];
+    if (!q.active || q.st.done) return;
+    load_desc(&sp, &q.p);
+    const BaProblem& p = sp;
     SolverState* st = p.st;
-    if (st->done) return;
     if (st->iteration >= st->max_iterations) {
         if (threadIdx.x == 0) st->done = 1;
         return;
@@ -1281,10 +1341,32 @@ __device__ __forceinline__ void marg_scatter(double* Am, double* bm, int P, cons
 
 }  // namespace
 
-__global__ void __launch_bounds__(128) marg_build_kernel(BaProblem p, MargPlan mp) {
-    __shared__ double sJraw[4][450], sJw[4][450], srr[4][15], srw[4][15];
+// Clears the members' marginalisation systems (Am P x P, bm P).
+__global__ void __launch_bounds__(256) marg_zero_kernel(const BaSeq* __restrict__ seqs) {
+    const BaSeq& q = seqs[blockIdx.y];
+    if (!q.active || !q.do_marg) return;
+    const size_t P = (size_t)q.mp.P, total = P * P + P;
+    double* Am = q.mp.Am;
+    double* bm = q.mp.bm;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        if (i < P * P) Am[i] = 0.0;
+        else bm[i - P * P] = 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(128) marg_build_kernel(const BaSeq* __restrict__ seqs) {
+    __shared__ double sJraw[1][450], sJw[1][450], srr[1][15], srw[1][15];
     __shared__ double dx[PRIOR_MAX_N], gpr[PRIOR_MAX_N];
     __shared__ int pcol[PRIOR_MAX_N];
+    __shared__ BaProblem sp;
+    __shared__ MargPlan smp;
+    const BaSeq& q = seqs[blockIdx.y];
+    if (!q.active || !q.do_marg) return;
+    if ((int)blockIdx.x >= (q.mp.n_lm + 3) / 4 + 2) return;
+    load_desc(&sp, &q.p);
+    load_desc(&smp, &q.mp);
+    const BaProblem& p = sp;
+    const MargPlan& mp = smp;
     const BaStates x = p.x[0];
     const BaDims& d = p.dims;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1377,10 +1459,17 @@ __host__ __device__ inline int marg_scratch_doubles(int md, int n, bool w_in_glo
 // Single CTA.  Dynamic shared memory: Wk (q x q), Ev (scratch), Vv ((ldx+1)^2: matrix in / eigenvectors out), bw (q), tv.
 // Both eigen-decompositions (the dense marginalised block T and the new prior A') use the tridiagonal-QL solver of
 // sym_eig.h: eigenvector k is the COLUMN k of Vv (odd leading dimension: conflict-free row walks).
-__global__ void __launch_bounds__(MARG_THREADS) marg_solve_kernel(MargPlan mp, double eps) {
+__global__ void __launch_bounds__(MARG_THREADS) marg_solve_kernel(const BaSeq* __restrict__ seqs, double eps) {
     extern __shared__ __align__(16) double sm[];
     __shared__ double red[32];
     __shared__ double dval[MARG_MAXN], ework[MARG_MAXN], cs[4 * MARG_MAXN], scal[16];
+    __shared__ MargPlan smp;
+    {
+        const BaSeq& q = seqs[blockIdx.x];
+        if (!q.active || !q.do_marg) return;
+        load_desc(&smp, &q.mp);
+    }
+    const MargPlan& mp = smp;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int md = mp.m_dense, nl = mp.n_lm, n = mp.n, P = mp.P;
     const int q = md + n;
@@ -1604,6 +1693,141 @@ size_t marg_solve_smem_bytes(int m_dense, int n, bool w_in_global) {
     return sizeof(double) * ((w_in_global ? 0 : (size_t)q * q + 1) + esz + (size_t)(ldx + 1) * (ldx + 1) + q + std::max(ldx, 32));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Estimator::double2vector (estimator.cpp:530-619) followed by vector2double (:486-528) on the device, one CTA per
+// member: the solved window is re-anchored to the yaw and position of frame 0 before the solve (the 4 unobservable
+// degrees of freedom), written to the member's output block for the host (Ps, Rs, Vs, Bas, Bgs, tic, ric, td, depths)
+// and packed again into x[0], the linearisation point of this frame's marginalisation; the new prior's x0 is taken from it.
+__global__ void __launch_bounds__(128) ba_finish_kernel(BaSeq* __restrict__ seqs) {
+    __shared__ double sin_[BA_MAX_FRAMES * 16 + 8];
+    __shared__ double rot[9];
+    BaSeq& q = seqs[blockIdx.x];
+    if (!q.active) return;
+    const BaProblem& p = q.p;
+    const FinishPlan& fp = q.fin;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int F = p.dims.W + 1, L = p.dims.L;
+    const int cur = q.st.cur;
+    const BaStates xs = p.x[cur], xd = p.x[0];
+    for (int i = tid; i < 7 * F; i += nt) sin_[i] = xs.pose[i];
+    for (int i = tid; i < 9 * F; i += nt) sin_[7 * F + i] = xs.sb[i];
+    for (int i = tid; i < 7; i += nt) sin_[16 * F + i] = xs.ex[i];
+    if (tid == 0) sin_[16 * F + 7] = xs.td[0];
+    __syncthreads();
+    if (tid == 0) {
+        const M3d R00 = qR(q_from_param(sin_));
+        const V3d o0 = mk(fp.origin_ypr[0], fp.origin_ypr[1], fp.origin_ypr[2]);
+        const V3d o00 = R2ypr_dev(R00);
+        const double y_diff = o0.x - o00.x;
+        M3d rd = ypr2R_dev(mk(y_diff, 0.0, 0.0));
+        if (fabs(fabs(o0.y) - 90) < 1.0 || fabs(fabs(o00.y) - 90) < 1.0) {
+            M3d R0;
+            for (int k = 0; k < 9; k++) R0.m[k] = fp.Rs0[k];
+            rd = mmul(R0, mT(R00));
+        }
+        for (int k = 0; k < 9; k++) rot[k] = rd.m[k];
+    }
+    __syncthreads();
+    double* out = fp.out;
+    {  // header: the final trust-region state
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&q.st);
+        for (int i = tid; i < (int)(sizeof(SolverState) / 8); i += nt) reinterpret_cast<unsigned long long*>(out)[i] = src[i];
+    }
+    double* of = out + BA_OUT_ST_DOUBLES;
+    M3d rd;
+    for (int k = 0; k < 9; k++) rd.m[k] = rot[k];
+    for (int f = tid; f < F; f += nt) {
+        const double* pp = sin_ + 7 * f;
+        const double* sbp = sin_ + 7 * F + 9 * f;
+        const M3d R = mmul(rd, qR(qnormalized(q_from_param(pp))));
+        const V3d P = mv(rd, mk(pp[0] - sin_[0], pp[1] - sin_[1], pp[2] - sin_[2])) + mk(fp.origin_P0[0], fp.origin_P0[1], fp.origin_P0[2]);
+        const V3d V = mv(rd, mk(sbp[0], sbp[1], sbp[2]));
+        double* o = of + 21 * f;
+        o[0] = P.x; o[1] = P.y; o[2] = P.z;
+        for (int k = 0; k < 9; k++) o[3 + k] = R.m[k];
+        o[12] = V.x; o[13] = V.y; o[14] = V.z;
+        for (int k = 0; k < 6; k++) o[15 + k] = sbp[3 + k];
+        // vector2double
+        const Q4 qq = q_from_R(R);
+        double* dp = xd.pose + 7 * f;
+        dp[0] = P.x; dp[1] = P.y; dp[2] = P.z; dp[3] = qq.x; dp[4] = qq.y; dp[5] = qq.z; dp[6] = qq.w;
+        double* ds = xd.sb + 9 * f;
+        ds[0] = V.x; ds[1] = V.y; ds[2] = V.z;
+        for (int k = 0; k < 6; k++) ds[3 + k] = sbp[3 + k];
+    }
+    if (tid == nt - 1) {
+        const double* xe = sin_ + 16 * F;
+        const M3d ric = qR(q_from_param(xe));
+        double* o = of + 21 * F;
+        o[0] = xe[0]; o[1] = xe[1]; o[2] = xe[2];
+        for (int k = 0; k < 9; k++) o[3 + k] = ric.m[k];
+        o[12] = xe[7];
+        const Q4 qq = q_from_R(ric);
+        xd.ex[0] = xe[0]; xd.ex[1] = xe[1]; xd.ex[2] = xe[2];
+        xd.ex[3] = qq.x; xd.ex[4] = qq.y; xd.ex[5] = qq.z; xd.ex[6] = qq.w;
+        xd.td[0] = xe[7];
+    }
+    double* od = of + 21 * F + 13;
+    for (int l = tid; l < L; l += nt) {  // FeatureManager::setDepth, then getDepthVector
+        const double dep = 1.0 / xs.lam[l];
+        od[l] = dep;
+        xd.lam[l] = 1. / dep;
+    }
+    __syncthreads();
+    // linearisation point of the new prior: the packed values of the kept blocks (marginalization_factor.cpp:299-319)
+    if (q.do_marg)
+        for (int b = tid; b < fp.n_kept; b += nt) {
+            const int type = fp.kept_type[b], idx = fp.kept_index[b];
+            double* dst = fp.x0_out + 9 * b;
+            const double* src = type == 0 ? xd.pose + 7 * idx : type == 1 ? xd.sb + 9 * idx : type == 2 ? xd.ex : xd.td;
+            const int n = type == 0 || type == 2 ? 7 : type == 1 ? 9 : 1;
+            for (int k = 0; k < 9; k++) dst[k] = k < n ? src[k] : 0.0;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Single-factor evaluation for the parity tests (ve_debug_*): the device functions the solve uses, one thread.
+__global__ void debug_visual_kernel(BaDims d, const double* __restrict__ prm, const double* __restrict__ dat, int robust,
+                                    double* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    VisualEval e;
+    // prm: pose_i 7 | pose_j 7 | ex 7 | inv_dep | td     dat: pts_i 2, pts_j 2, vel_i 2, vel_j 2, td_i, td_j, row_i, row_j
+    eval_visual(d, prm, prm + 7, prm + 14, prm[21], prm[22], dat[0], dat[1], dat[2], dat[3], dat[4], dat[5], dat[6], dat[7], dat[8],
+                dat[9], dat[10], dat[11], true, robust != 0, e);
+    out[0] = e.r[0];
+    out[1] = e.r[1];
+    for (int k = 0; k < 20; k++) {
+        out[2 + k] = e.J[0][k];
+        out[22 + k] = e.J[1][k];
+    }
+    out[42] = e.half_rho;
+}
+
+__global__ void __launch_bounds__(32) debug_imu_kernel(BaDims d, const PreInt* __restrict__ pre, const double* __restrict__ prm,
+                                                       double* __restrict__ out) {
+    __shared__ double Jraw[450], Jw[450], rr[15], rw[15];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 450; i += 32) Jraw[i] = 0.0;
+    __syncwarp();
+    // prm: pose_i 7 | sb_i 9 | pose_j 7 | sb_j 9
+    if (lane == 0) eval_imu_raw(d, *pre, prm, prm + 7, prm + 16, prm + 23, rr, Jraw);
+    __syncwarp();
+    for (int idx = lane; idx < 450; idx += 32) {
+        const int i = idx / 30, c = idx % 30;
+        double s = 0;
+        for (int k = 0; k < 15; k++) s += pre->sqrt_info[i * 15 + k] * Jraw[k * 30 + c];
+        Jw[idx] = s;
+    }
+    if (lane < 15) {
+        double s = 0;
+        for (int k = 0; k < 15; k++) s += pre->sqrt_info[lane * 15 + k] * rr[k];
+        rw[lane] = s;
+    }
+    __syncwarp();
+    for (int i = lane; i < 15; i += 32) out[i] = rw[i];
+    for (int i = lane; i < 450; i += 32) out[15 + i] = Jw[i];
+}
+
 }  // namespace vb
 
 // ------------------------------------------------------------------------------------------------
@@ -1612,122 +1836,139 @@ namespace vb {
 
 size_t ba_work_doubles(int D, int L) { return 4 * (size_t)(D + L) + (size_t)(D + 1) * (D + 2) / 2; }
 
-void launch_preint_push(PreInt* slot, int n, const double* d_samples, double acc_n, double gyr_n, double acc_w, double gyr_w,
-                        cudaStream_t s) {
-    if (n <= 0) return;
-    preint_push_kernel<<<1, 256, 0, s>>>(slot, n, d_samples, acc_n, gyr_n, acc_w, gyr_w);
-}
+namespace {
 
-void launch_preint_init(PreInt* slot, const double* acc0, const double* gyr0, const double* ba, const double* bg, cudaStream_t s) {
-    PreIntInit v;
-    for (int i = 0; i < 3; i++) {
-        v.acc0[i] = acc0[i];
-        v.gyr0[i] = gyr0[i];
-        v.ba[i] = ba[i];
-        v.bg[i] = bg[i];
-    }
-    preint_init_kernel<<<1, 256, 0, s>>>(slot, v);
-}
+// Per-device launch configuration: function attributes (the opt-in to > 48 KB dynamic shared memory) belong to the
+// device the calling thread has current, and handles may live on different GPUs of one process.
+struct DeviceCfg {
+    bool init = false;
+    int smem_limit = 0, step_static = 0, marg_static = 0;
+    int step_configured = 0, marg_configured = 0;
+};
+std::mutex g_cfg_mutex;
+DeviceCfg g_cfg[64];
 
-void launch_sqrt_info(PreInt* slots, const int* d_which, int count, cudaStream_t s) {
-    if (count <= 0) return;
-    sqrt_info_kernel<<<count, 32, 0, s>>>(slots, d_which, count);
-}
-
-void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int* launches, KernelProfile* prof) {
-    KernelProfile none;
-    if (!prof) prof = &none;
-    const BaDims& d = p.dims;
-    const int lin_grid = ba_linearize_grid(d);
-    const int zero_grid = 64;
-    const int tiles = (d.D + ST - 1) / ST;
-    const size_t panel_bytes = sizeof(double) * CHOL_NB * CHOL_PS;
-    const size_t chol_bytes = sizeof(double) * (size_t)(d.D + 1) * (d.D + 2) / 2 + panel_bytes;
-    static std::mutex cfg_mutex;  // handles on different host threads share the per-function attributes
-    std::unique_lock<std::mutex> cfg_lock(cfg_mutex);
-    static int smem_limit = -1, smem_static = 0, smem_configured = 0;
-    if (smem_limit < 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+DeviceCfg& device_cfg_locked() {  // caller holds g_cfg_mutex
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DeviceCfg& c = g_cfg[dev & 63];
+    if (!c.init) {
+        cudaDeviceGetAttribute(&c.smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         cudaFuncAttributes fa{};
         cudaFuncGetAttributes(&fa, ba_step_kernel);
-        smem_static = (int)fa.sharedSizeBytes;
+        c.step_static = (int)fa.sharedSizeBytes;
+        cudaFuncGetAttributes(&fa, marg_solve_kernel);
+        c.marg_static = (int)fa.sharedSizeBytes;
+        c.init = true;
     }
-    const int use_smem = chol_bytes + (size_t)smem_static + 256 <= (size_t)smem_limit ? 1 : 0;
-    const size_t step_dyn = use_smem ? chol_bytes : panel_bytes;
-    if ((int)step_dyn > smem_configured) {
-        cudaFuncSetAttribute(ba_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dyn);
-        smem_configured = (int)step_dyn;
+    return c;
+}
+
+}  // namespace
+
+int marg_w_in_global(int m_dense, int n) {
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
+    DeviceCfg& c = device_cfg_locked();
+    return marg_solve_smem_bytes(m_dense, n, false) + (size_t)c.marg_static + 256 > (size_t)c.smem_limit ? 1 : 0;
+}
+
+void launch_preint_jobs(BaSeq* seqs, const BatchShape& sh, cudaStream_t s, int* launches, KernelProfile* prof) {
+    KernelProfile none;
+    if (!prof) prof = &none;
+    if (!sh.any_jobs) return;
+    prof->begin(s);
+    preint_jobs_kernel<<<dim3(sh.W + 1, sh.S), 256, 0, s>>>(seqs);
+    prof->end(6, s);
+    if (launches) *launches += 1;
+}
+
+void launch_ba_solve(BaSeq* seqs, const BatchShape& sh, cudaStream_t s, int* launches, KernelProfile* prof) {
+    KernelProfile none;
+    if (!prof) prof = &none;
+    if (!sh.any_active) return;
+    BaDims dmax{};
+    dmax.L = sh.max_L;
+    dmax.W = sh.W;
+    const int lin_grid = ba_linearize_grid(dmax);
+    const int zero_grid = 32;
+    const int tiles = (sh.D + ST - 1) / ST;
+    const size_t panel_bytes = sizeof(double) * CHOL_NB * CHOL_PS;
+    const size_t chol_bytes = sizeof(double) * (size_t)(sh.D + 1) * (sh.D + 2) / 2 + panel_bytes;
+    int use_smem;
+    size_t step_dyn;
+    {
+        std::lock_guard<std::mutex> lock(g_cfg_mutex);
+        DeviceCfg& c = device_cfg_locked();
+        use_smem = chol_bytes + (size_t)c.step_static + 256 <= (size_t)c.smem_limit ? 1 : 0;
+        step_dyn = use_smem ? chol_bytes : panel_bytes;
+        if ((int)step_dyn > c.step_configured) {
+            cudaFuncSetAttribute(ba_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_dyn);
+            c.step_configured = (int)step_dyn;
+        }
     }
-    cfg_lock.unlock();
     int n = 0;
     prof->begin(s);
-    ba_zero_kernel<<<zero_grid, 256, 0, s>>>(p, 1);
+    ba_zero_kernel<<<dim3(zero_grid, sh.S), 256, 0, s>>>(seqs, 1);
     prof->end(3, s);
     prof->begin(s);
-    ba_linearize_kernel<<<lin_grid, 32 * LIN_WARPS, 0, s>>>(p, 1);
+    ba_linearize_kernel<<<dim3(lin_grid, sh.S), 32 * LIN_WARPS, 0, s>>>(seqs, 1);
     prof->end(0, s);
     n += 2;
-    for (int it = 0; it < max_iterations; it++) {
+    for (int it = 0; it < sh.max_iterations; it++) {
         prof->begin(s);
-        ba_schur_kernel<<<dim3(tiles, tiles), dim3(ST, ST), 0, s>>>(p);
+        ba_schur_kernel<<<dim3(tiles, tiles, sh.S), dim3(ST, ST), 0, s>>>(seqs);
         prof->end(1, s);
         prof->begin(s);
-        ba_step_kernel<<<1, 512, step_dyn, s>>>(p, use_smem);
+        ba_step_kernel<<<sh.S, 512, step_dyn, s>>>(seqs, use_smem);
         prof->end(2, s);
         if (tiles < 2) {  // no lower-triangle CTA to do the clearing (never at the supported window sizes)
             prof->begin(s);
-            ba_zero_kernel<<<zero_grid, 256, 0, s>>>(p, 0);
+            ba_zero_kernel<<<dim3(zero_grid, sh.S), 256, 0, s>>>(seqs, 0);
             prof->end(3, s);
             n += 1;
         }
         prof->begin(s);
-        ba_linearize_kernel<<<lin_grid, 32 * LIN_WARPS, 0, s>>>(p, 0);
+        ba_linearize_kernel<<<dim3(lin_grid, sh.S), 32 * LIN_WARPS, 0, s>>>(seqs, 0);
         prof->end(0, s);
         n += 3;
     }
+    prof->begin(s);
+    ba_finish_kernel<<<sh.S, 128, 0, s>>>(seqs);
+    prof->end(7, s);
+    n += 1;
     if (launches) *launches += n;
 }
 
-void launch_marginalize(const BaProblem& p, const MargPlan& mp_in, cudaStream_t s, int* launches, KernelProfile* prof) {
+void launch_marginalize(BaSeq* seqs, const BatchShape& sh, cudaStream_t s, int* launches, KernelProfile* prof) {
     KernelProfile none;
     if (!prof) prof = &none;
-    MargPlan mp = mp_in;
+    if (!sh.any_marg) return;
+    const size_t smem = marg_solve_smem_bytes(sh.max_md, sh.max_n, sh.w_in_global != 0);
     {
-        static int smem_limit = -1, smem_static = 0;
-        static std::mutex m;
-        std::lock_guard<std::mutex> lock(m);
-        if (smem_limit < 0) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-            cudaFuncAttributes fa{};
-            cudaFuncGetAttributes(&fa, marg_solve_kernel);
-            smem_static = (int)fa.sharedSizeBytes;
-        }
-        mp.w_in_global = marg_solve_smem_bytes(mp.m_dense, mp.n, false) + (size_t)smem_static + 256 > (size_t)smem_limit ? 1 : 0;
-    }
-    cudaMemsetAsync(mp.Am, 0, sizeof(double) * (size_t)mp.P * mp.P, s);
-    cudaMemsetAsync(mp.bm, 0, sizeof(double) * (size_t)mp.P, s);
-    const int grid = (mp.n_lm + 3) / 4 + 2;
-    prof->begin(s);
-    marg_build_kernel<<<grid, 128, 0, s>>>(p, mp);
-    prof->end(4, s);
-    const size_t smem = marg_solve_smem_bytes(mp.m_dense, mp.n, mp.w_in_global != 0);
-    {
-        static std::mutex cfg_mutex;
-        static size_t configured = 0;
-        std::lock_guard<std::mutex> lock(cfg_mutex);
-        if (smem > configured) {
+        std::lock_guard<std::mutex> lock(g_cfg_mutex);
+        DeviceCfg& c = device_cfg_locked();
+        if ((int)smem > c.marg_configured) {
             cudaFuncSetAttribute(marg_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = smem;
+            c.marg_configured = (int)smem;
         }
     }
+    const int zgrid = std::max(1, std::min(64, (int)(((size_t)sh.max_P * sh.max_P + 256 * 8 - 1) / (256 * 8))));
+    const int grid = (sh.max_n_lm + 3) / 4 + 2;
     prof->begin(s);
-    marg_solve_kernel<<<1, MARG_THREADS, smem, s>>>(mp, 1e-8);
+    marg_zero_kernel<<<dim3(zgrid, sh.S), 256, 0, s>>>(seqs);
+    marg_build_kernel<<<dim3(grid, sh.S), 128, 0, s>>>(seqs);
+    prof->end(4, s, 2);
+    prof->begin(s);
+    marg_solve_kernel<<<sh.S, MARG_THREADS, smem, s>>>(seqs, 1e-8);
     prof->end(5, s);
-    if (launches) *launches += 2;
+    if (launches) *launches += 3;
+}
+
+void launch_debug_visual(const BaDims& d, const double* d_params23, const double* d_data16, int robust, double* d_out, cudaStream_t s) {
+    debug_visual_kernel<<<1, 32, 0, s>>>(d, d_params23, d_data16, robust, d_out);
+}
+void launch_debug_imu(const BaDims& d, const PreInt* d_pre, const double* d_params32, double* d_out, cudaStream_t s) {
+    debug_imu_kernel<<<1, 32, 0, s>>>(d, d_pre, d_params32, d_out);
 }
 
 }  // namespace vb

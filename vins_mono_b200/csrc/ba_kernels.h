@@ -1,4 +1,5 @@
-// Launch interface of the BA kernels (ba_kernels.cu).
+// Launch interface of the BA kernels (ba_kernels.cu).  Every launch serves a whole batch: `seqs` is a device array of
+// S per-member descriptors (ba_types.h), the member index is a grid dimension.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -7,34 +8,33 @@
 
 namespace vb {
 
-constexpr int BA_MAX_FRAMES = 32;
-
-struct MargPlan {  // dense marginalisation system layout: [m_dense | n_lm landmark columns | n kept]
-    int P, m_dense, n_lm, n;
-    const int* lms;     // device: indices (into the problem's landmark table) of the marginalised landmarks
-    const int* col_lm;  // device: their columns
-    int col_pose[BA_MAX_FRAMES], col_sb[BA_MAX_FRAMES];  // -1 when the block does not take part
-    int col_ex, col_td;
-    int use_imu;        // include IMU factor (frames 0,1)
-    double* Am;         // P x P (upper triangle accumulated)
-    double* bm;         // P
-    double* Aout;       // n x n   new prior A  (after the eps floor)
-    double* gout;       // n       new prior g0
-    double* cout;       // 1       new prior c0
-    double* Araw;       // n x n   Schur complement before the eps floor (tests), may be null
-    double* graw;       // n
-    double* Wglobal;    // q x q scratch (q = m_dense + n) used when the reduced system does not fit shared memory
-    int w_in_global;    // set by launch_marginalize
+struct BatchShape {  // host-side maxima over the members of this frame: grid and shared-memory sizing
+    int S;               // members
+    int W;               // window size (uniform over the batch)
+    int D;               // reduced dimension (uniform)
+    int max_L;           // landmarks
+    int max_n_lm;        // marginalised landmarks
+    int max_md, max_n;   // marginalisation: dense marginalised columns, kept columns
+    int max_P;           // marginalisation system size
+    int any_jobs, any_active, any_marg;
+    int max_iterations;
+    int w_in_global;     // marginalisation reduced system in global memory (decided once per batch: marg_w_in_global)
 };
 
-void launch_preint_push(PreInt* slot, int n, const double* d_samples, double acc_n, double gyr_n, double acc_w, double gyr_w,
-                        cudaStream_t s);
-void launch_preint_init(PreInt* slot, const double* acc0, const double* gyr0, const double* ba, const double* bg, cudaStream_t s);
-void launch_sqrt_info(PreInt* slots, const int* d_which, int count, cudaStream_t s);
-// full trust-region solve: linearise x[st->cur], then max_iterations x {schur, step, zero, linearise+decide}
-// profile slots: 0 linearize, 1 schur, 2 step, 3 zero, 4 marg_build, 5 marg_solve, 6 preint, 7 sqrt_info
-void launch_ba_solve(const BaProblem& p, int max_iterations, cudaStream_t s, int* launches, KernelProfile* prof = nullptr);
-void launch_marginalize(const BaProblem& p, const MargPlan& mp, cudaStream_t s, int* launches, KernelProfile* prof = nullptr);
+// profile slots: 0 linearize, 1 schur, 2 step, 3 zero, 4 marg_build, 5 marg_solve, 6 preint, 7 finish
+// Pre-integration jobs (new slots, pushed samples, refreshed sqrt_info) of all members.
+void launch_preint_jobs(BaSeq* seqs, const BatchShape& sh, cudaStream_t s, int* launches, KernelProfile* prof = nullptr);
+// Full trust-region solve of every active member: linearise x[st.cur], then max_iterations x {schur, step,
+// linearise + decide}; then the device-side double2vector / vector2double (results into the members' output blocks).
+void launch_ba_solve(BaSeq* seqs, const BatchShape& sh, cudaStream_t s, int* launches, KernelProfile* prof = nullptr);
+void launch_marginalize(BaSeq* seqs, const BatchShape& sh, cudaStream_t s, int* launches, KernelProfile* prof = nullptr);
 size_t ba_work_doubles(int D, int L);
+// Whether marg_solve_kernel keeps its reduced system in global memory for these sizes on the current device.
+int marg_w_in_global(int m_dense, int n);
+
+// Test access (ve_debug_*): residual / Jacobian of single factors evaluated by the same device code as the solve.
+// visual: out = r[2] | J[2][20]; imu: out = r_whitened[15] | Jw[15][30]
+void launch_debug_visual(const BaDims& d, const double* d_params23, const double* d_data16, int robust, double* d_out, cudaStream_t s);
+void launch_debug_imu(const BaDims& d, const PreInt* d_pre, const double* d_params32, double* d_out, cudaStream_t s);
 
 }  // namespace vb

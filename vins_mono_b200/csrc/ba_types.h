@@ -1,9 +1,11 @@
 // Device-side data layout of the sliding-window BA path (all float64, structure-of-arrays in HBM).
 //
-// One "BaProblem" = one sequence's window at one frame: states (current + candidate), the observation
-// table grouped by landmark, the pre-integration slots, the marginalization prior in information form,
-// the accumulation buffers of the normal equations and the trust-region state.  Kernels take a BaProblem
-// by value (a bundle of device pointers) so a batch of sequences is just an array of these.
+// One "BaSeq" = one sequence's window at one frame: the problem (states current + candidate, the observation table
+// grouped by landmark, the pre-integration slots, the marginalisation prior in information form, the accumulation
+// buffers of the normal equations, the trust-region state), the pre-integration jobs of the frame, the gauge
+// re-anchoring inputs of double2vector and the marginalisation plan.  A batch of S sequences is an array of S of
+// these in device memory; every kernel takes the array and picks its member with a grid dimension, so one launch
+// per stage serves the whole batch (S = 1 is the single-sequence path, the same code).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -11,6 +13,8 @@
 namespace vb {
 
 constexpr int BA_MAX_OBS_PER_LM = 32;  // lanes of the landmark warp (window size + 1 <= 32)
+constexpr int BA_MAX_FRAMES = 32;
+constexpr int BA_MAX_PRIOR_BLOCKS = 64;
 
 struct PreInt {  // IntegrationBase (integration_base.h:189-209) + cached sqrt_info (imu_factor.h:64)
     double sum_dt;
@@ -29,6 +33,7 @@ struct BaDims {
     int col_sb;   // first speed-bias column = 6(W+1)
     int col_ex;   // -1 when the extrinsic is constant
     int col_td;   // -1 when td is not estimated
+    int pad;
     double sqrt_info_vis;  // FOCAL_LENGTH / 1.5
     double tr_over_row;    // TR / ROW
     double half_row;       // ROW / 2 (projection_td_factor.cpp:18-19)
@@ -76,6 +81,8 @@ struct SolverState {  // trust-region / dogleg state, lives in device memory
     double initial_cost;
     long long clk[10];  // per-phase cycle counters of the last ba_step_kernel (profiling aid)
 };
+constexpr int BA_OUT_ST_DOUBLES = 32;  // room reserved for a SolverState at the head of a member's output block
+static_assert(sizeof(SolverState) <= BA_OUT_ST_DOUBLES * sizeof(double), "output block header too small");
 
 struct BaProblem {
     BaDims dims;
@@ -94,7 +101,7 @@ struct BaProblem {
     const double* ob_td;      // M
     const double* ob_row;     // M
     // IMU factors: factor k links frames k and k+1 through pre-integration slot imu_slot[k] (-1: skipped)
-    const PreInt* preint;     // slot array
+    PreInt* preint;           // slot array
     const int* imu_slot;      // W
     BaPrior prior;
     // solver workspace
@@ -107,7 +114,58 @@ struct BaProblem {
     double* grad;    // D + L
     double* gn;      // D + L
     double* work;    // 4 x (D + L) scratch
-    SolverState* st;
+    SolverState* st; // points at BaSeq::st of the same member
+};
+
+struct MargPlan {  // dense marginalisation system layout: [m_dense | n_lm landmark columns | n kept]
+    int P, m_dense, n_lm, n;
+    const int* lms;     // device: indices (into the problem's landmark table) of the marginalised landmarks
+    const int* col_lm;  // device: their columns
+    int col_pose[BA_MAX_FRAMES], col_sb[BA_MAX_FRAMES];  // -1 when the block does not take part
+    int col_ex, col_td;
+    int use_imu;        // include IMU factor (frames 0,1)
+    int w_in_global;    // the reduced system does not fit shared memory (set by the launcher, uniform per batch)
+    double* Am;         // P x P (upper triangle accumulated)
+    double* bm;         // P
+    double* Aout;       // n x n   new prior A  (after the eps floor)
+    double* gout;       // n       new prior g0
+    double* cout;       // 1       new prior c0
+    double* Araw;       // n x n   Schur complement before the eps floor (tests), may be null
+    double* graw;       // n (+ 7 diagnostics)
+    double* Wglobal;    // q x q scratch (q = m_dense + n) used when the reduced system does not fit shared memory
+};
+
+struct PreintJob {  // work of one frame on the pre-integration slots, executed in list order per slot
+    int type;        // 0: new IntegrationBase{acc0, gyr0, ba, bg}; 1: push_back of n samples
+    int slot, n, sample_off;  // sample_off in 7-double records (dt, acc[3], gyr[3]) from BaSeq::samples
+    double acc0[3], gyr0[3], ba[3], bg[3];
+};
+
+// Inputs and outputs of the device-side double2vector + vector2double (estimator.cpp:530-619, :486-528) that runs
+// between the solve and the marginalisation, so a frame needs no host round trip inside its kernel chain.
+struct FinishPlan {
+    double origin_ypr[3];  // R2ypr(Rs[0]) before the solve (degrees), or of last_R0 after a detected failure
+    double origin_P0[3];
+    double Rs0[9];         // Rs[0] before the solve (Euler-singularity fallback)
+    double* out;           // member's output block: SolverState | (W+1) x 21 (P, R row-major, V, Ba, Bg) | tic 3 | ric 9 | td | L depths
+    int n_kept;            // kept blocks of the new prior (0: nothing is marginalised this frame)
+    int kept_type[BA_MAX_PRIOR_BLOCKS], kept_index[BA_MAX_PRIOR_BLOCKS];  // pre-shift identities
+    double* x0_out;        // new prior's linearisation point, 9 doubles per kept block
+};
+
+struct BaSeq {
+    int active;            // this member runs a solve this frame
+    int do_marg;           // ... and a marginalisation
+    int n_jobs;
+    unsigned sqrt_mask;    // slots whose sqrt_info is refreshed after the jobs
+    const PreintJob* jobs;
+    const double* samples;
+    double noise[4];       // acc_n, gyr_n, acc_w, gyr_w
+    int prior_type[BA_MAX_PRIOR_BLOCKS], prior_index[BA_MAX_PRIOR_BLOCKS], prior_off[BA_MAX_PRIOR_BLOCKS];
+    SolverState st;
+    BaProblem p;
+    MargPlan mp;
+    FinishPlan fin;
 };
 
 }  // namespace vb

@@ -1,16 +1,26 @@
 // ve_* C ABI: host shim of the reference's Estimator / FeatureManager (vins_estimator/src/estimator.cpp,
 // feature_manager.cpp) around the CUDA BA path.  Bookkeeping that the reference does on the host stays on the
-// host (window arrays, feature tracks, slide/re-anchor logic, gauge re-anchoring in double2vector); IMU
-// pre-integration, factor linearisation, the trust-region solve and the marginalisation run on the GPU with all
-// problem data resident in HBM.  Per frame the PCIe traffic is the packed observation table + states down and
-// the states back.
+// host (window arrays, feature tracks, slide/re-anchor logic); IMU pre-integration, factor linearisation, the
+// trust-region solve, the gauge re-anchoring of double2vector and the marginalisation run on the GPU with all problem
+// data resident in HBM.
+//
+// Execution model: estimators are members of a batch (ve_batch; a stand-alone handle is a batch of one).  A frame of
+// the batch is   prepare (host, per member, parallel)  ->  ONE host-to-device copy of the packed inputs  ->  one launch
+// chain for all members (pre-integration jobs, 8-iteration solve, re-anchoring, marginalisation)  ->  ONE device-to-host
+// copy of the results  ->  finish (host, per member, parallel).  The host waits once per frame (for the results); the
+// marginalisation keeps running behind that point and is only awaited by the next frame's kernels on the same stream.
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ba_kernels.h"
@@ -60,14 +70,78 @@ struct DeviceBuf {
     }
 };
 
+// Minimal fork-join pool for the per-member host phases of a batch (prepare / finish are independent per member).
+class Pool {
+  public:
+    explicit Pool(int workers) {
+        for (int i = 0; i < workers; i++) th_.emplace_back([this] { loop(); });
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    void run(int n, const std::function<void(int)>& fn) {
+        if (th_.empty() || n <= 1) {
+            for (int i = 0; i < n; i++) fn(i);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &fn;
+            n_ = n;
+            next_.store(0);
+            pending_ = (int)th_.size();
+            gen_++;
+        }
+        cv_.notify_all();
+        for (int i; (i = next_.fetch_add(1)) < n;) fn(i);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+  private:
+    void loop() {
+        unsigned long long seen = 0;
+        for (;;) {
+            const std::function<void(int)>* fn;
+            int n;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+                fn = fn_;
+                n = n_;
+            }
+            for (int i; (i = next_.fetch_add(1)) < n;) (*fn)(i);
+            std::lock_guard<std::mutex> lk(m_);
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int n_ = 0, pending_ = 0;
+    std::atomic<int> next_{0};
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+};
+
+enum FrameStage { STAGE_DONE = 0, STAGE_INIT_SOLVE = 1, STAGE_RUN_SOLVE = 2 };
+
 }  // namespace
 
 struct ve_estimator {
     ve_config cfg{};
     std::string err;
     int W = 10;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {};  // 0-2 solve phases, 3 marginalisation done, 5 marginalisation start, 6 state upload of marginalize()
+    ve_batch* batch = nullptr;
+    int member = 0;
     // ---- Estimator state (estimator.h:65-115)
     int solver_flag = 0;           // INITIAL = 0, NON_LINEAR = 1
     int marginalization_flag = 0;  // MARGIN_OLD = 0, MARGIN_SECOND_NEW = 1
@@ -92,10 +166,13 @@ struct ve_estimator {
     // pre-integration slots: frame -> slot, per-slot host mirror of what the device slot was created with
     std::vector<int> slot_of;
     std::vector<bool> slot_valid;
-    std::vector<size_t> flushed;    // samples of dt_buf[frame] already integrated on the device
+    std::vector<size_t> flushed;    // samples of dt_buf[frame] already handed to the device
     std::vector<double> sum_dt;     // per frame
     std::vector<Vec3> lin_acc, lin_gyr;  // linearized_acc / linearized_gyr per frame
     std::vector<bool> sqrt_dirty;   // per slot
+    // device work queued since the last launch (executed in order at the head of the next frame's kernel chain)
+    std::vector<vb::PreintJob> jobs;
+    std::vector<double> job_samples;  // 7 doubles per record
     // prior (MarginalizationInfo) bookkeeping
     bool has_prior = false;
     int prior_n = 0, prior_buf = 0;
@@ -103,43 +180,52 @@ struct ve_estimator {
     // summary
     int n_solves = 0, n_reboots = 0, last_landmarks = 0, last_visual = 0;
     vb::SolverState last_state{};
-    float last_ms[4] = {0, 0, 0, 0};
-    int last_launches = 0;
-    vb::KernelProfile prof;
     size_t h2d_bytes = 0, d2h_bytes = 0;  // of the last process_image
-    // ---- device memory
+    // ---- per-frame plan (prepare -> launch -> finish)
+    int stage = STAGE_DONE;
+    int status = VE_OK;      // of the current frame
+    bool fr_marg = false;
+    int fr_L = 0;
+    size_t out_off = 0;      // doubles, into the batch output arena
+    const double* marg_Araw = nullptr;  // device: Schur complement of the last marginalisation before the eps floor
+    const double* marg_graw = nullptr;
+    int marg_n = 0;
+    // ---- persistent device memory of this member
     int Lmax = 0, Mmax = 0, D = 0, nmax = 0;
     DeviceBuf<vb::PreInt> d_preint;
-    DeviceBuf<double> d_samples;
-    DeviceBuf<int> d_which;
-    DeviceBuf<double> d_states[2];   // pose | sb | ex | td | lam
+    DeviceBuf<double> d_states1;     // x[1] (x[0] lives in the frame's input block)
     DeviceBuf<double> d_acc[2];      // Hpp | gp | Hpl | Hll | gl | cost
-    DeviceBuf<int> d_ints;           // lm_anchor | lm_start | ob_frame | imu_slot
-    DeviceBuf<double> d_obs;         // lm_pts | lm_vel | lm_td | lm_row | ob_pts | ob_vel | ob_td | ob_row
     DeviceBuf<double> d_S, d_Spk, d_Hfull, d_gred, d_vec, d_work;
-    DeviceBuf<vb::SolverState> d_st;
     DeviceBuf<double> d_prior[2];    // A | g0 | c0 | x0
-    DeviceBuf<int> d_prior_i[2];     // type | index | off
-    DeviceBuf<double> d_marg;        // Am | bm | Araw | graw
-    DeviceBuf<int> d_marg_i;         // lms | col_lm
-    // pinned staging
-    double* h_states = nullptr;
-    double* h_obs = nullptr;
-    int* h_ints = nullptr;
-    double* h_samples = nullptr;
-    vb::PreInt* h_preint = nullptr;
-    vb::SolverState* h_st = nullptr;
-    double* h_prior = nullptr;
-    int* h_prior_i = nullptr;
-    int* h_marg_i = nullptr;
-    int* h_which = nullptr;          // pinned staging of refresh_sqrt_info (h_marg_i may still be in flight)
-    double* h_marg_out = nullptr;
-    std::vector<double> prior_raw_A, prior_raw_b;  // last Schur complement before the eps floor
-    double marg_sweeps[7] = {0, 0, 0, 0, 0, 0, 0};
-    int sample_seg = 0, flushes_in_flight = 0;
-    bool marg_pending = false;  // marginalisation kernels enqueued, results not yet read back
-    int marg_n = 0;
-    bool states_upload_pending = false;
+    DeviceBuf<double> d_marg;        // Am | bm | Araw | graw | Wglobal
+};
+
+struct ve_batch {
+    ve_config cfg{};
+    int S = 0;
+    bool standalone = false;  // created by ve_create: destroyed with its only member
+    std::vector<ve_estimator*> members;
+    std::string err;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev[8] = {};  // 0 frame start, 1 after pre-integration, 2 after the solve + re-anchoring, 3 marginalisation done,
+                             // 4 results on the host, 5 marginalisation start
+    vb::BaSeq* h_seq = nullptr;  // pinned mirror of d_seq
+    vb::BaSeq* d_seq = nullptr;
+    unsigned char* h_in = nullptr;  // pinned: packed per-member input blocks of the frame
+    unsigned char* d_in = nullptr;
+    size_t in_cap = 0;
+    std::atomic<size_t> in_used{0};
+    double* h_out = nullptr;        // pinned: per-member output blocks
+    double* d_out = nullptr;
+    size_t out_cap = 0;             // doubles
+    std::atomic<size_t> out_used{0};
+    vb::KernelProfile prof;
+    Pool* pool = nullptr;
+    float last_ms[4] = {0, 0, 0, 0};
+    int last_launches = 0;
+    bool marg_timing_valid = false;
+    int w_in_global = 0;            // marg_solve keeps its reduced system in global memory (large windows)
+    std::vector<int> active;        // scratch: members taking part in the current frame
 };
 
 namespace {
@@ -153,12 +239,11 @@ namespace {
         }                                                                    \
     } while (0)
 
-size_t states_doubles(const ve_estimator* e) { return (size_t)(e->W + 1) * 16 + 8 + e->Lmax; }
+size_t states_doubles(const ve_estimator* e, int L) { return (size_t)(e->W + 1) * 16 + 8 + L; }
 size_t acc_doubles(const ve_estimator* e) { return (size_t)e->D * e->D + e->D + (size_t)e->Lmax * e->D + 2 * (size_t)e->Lmax + 1; }
+size_t align16(size_t bytes) { return (bytes + 15) & ~(size_t)15; }
 
-vb::BaStates states_view(const ve_estimator* e, int b) {
-    double* p = e->d_states[b].p;
-    const int F = e->W + 1;
+vb::BaStates states_view(double* p, int F) {
     vb::BaStates s;
     s.pose = p;
     s.sb = p + 7 * F;
@@ -172,75 +257,58 @@ bool usable(const ve_estimator* e, FeaturePerId& it) {  // the filter repeated a
     return it.used_num >= 2 && it.start_frame < e->W - 2;
 }
 
-// ---- pre-integration slots ---------------------------------------------------------------------
-int init_slot(ve_estimator* e, int frame, const Vec3& a0, const Vec3& g0, const Vec3& ba, const Vec3& bg) {
-    const double A0[3] = {a0.x, a0.y, a0.z}, G0[3] = {g0.x, g0.y, g0.z}, BA[3] = {ba.x, ba.y, ba.z}, BG[3] = {bg.x, bg.y, bg.z};
+// ---- pre-integration slots: the device work is queued and runs at the head of the next frame's kernel chain -------
+void init_slot(ve_estimator* e, int frame, const Vec3& a0, const Vec3& g0, const Vec3& ba, const Vec3& bg) {
     const int slot = e->slot_of[frame];
-    vb::launch_preint_init(e->d_preint.p + slot, A0, G0, BA, BG, e->stream);  // values travel as kernel arguments
-    e->last_launches++;
+    // a new IntegrationBase supersedes whatever was queued for the slot
+    e->jobs.erase(std::remove_if(e->jobs.begin(), e->jobs.end(), [&](const vb::PreintJob& j) { return j.slot == slot; }), e->jobs.end());
+    if (e->jobs.empty()) e->job_samples.clear();
+    vb::PreintJob j{};
+    j.type = 0;
+    j.slot = slot;
+    j.acc0[0] = a0.x; j.acc0[1] = a0.y; j.acc0[2] = a0.z;
+    j.gyr0[0] = g0.x; j.gyr0[1] = g0.y; j.gyr0[2] = g0.z;
+    j.ba[0] = ba.x; j.ba[1] = ba.y; j.ba[2] = ba.z;
+    j.bg[0] = bg.x; j.bg[1] = bg.y; j.bg[2] = bg.z;
+    e->jobs.push_back(j);
     e->slot_valid[frame] = true;
     e->flushed[frame] = 0;
     e->sum_dt[frame] = 0;
     e->lin_acc[frame] = a0;
     e->lin_gyr[frame] = g0;
     e->sqrt_dirty[slot] = true;
-    return VE_OK;
 }
 
-// Integrates the not-yet-integrated samples of `frame`'s buffers into its device slot.
-int flush_frame(ve_estimator* e, int frame) {
+// Queues the not-yet-integrated samples of `frame`'s buffers for its device slot.
+void flush_frame(ve_estimator* e, int frame) {
     const size_t n = e->dt_buf[frame].size();
-    if (!e->slot_valid[frame] || e->flushed[frame] >= n) return VE_OK;
+    if (!e->slot_valid[frame] || e->flushed[frame] >= n) return;
     const size_t k0 = e->flushed[frame], cnt = n - k0;
-    if (cnt > 512) {
-        e->err = "too many IMU samples in one interval";
-        return VE_ERR_CAPACITY;
-    }
-    // ring of 8 staging segments: no host wait here; a segment is reused 8 flushes later, by which time at least one
-    // per-frame synchronisation (the solve's state read-back) has drained the stream
-    if (++e->flushes_in_flight > 8) {  // every staging segment may still be waiting for its copy
-        VE_CUDA(cudaStreamSynchronize(e->stream));
-        e->flushes_in_flight = 1;
-    }
-    const int seg = e->sample_seg;
-    e->sample_seg = (e->sample_seg + 1) & 7;
-    double* hs = e->h_samples + (size_t)seg * 7 * 512;
-    double* ds = e->d_samples.p + (size_t)seg * 7 * 512;
+    vb::PreintJob j{};
+    j.type = 1;
+    j.slot = e->slot_of[frame];
+    j.n = (int)cnt;
+    j.sample_off = (int)(e->job_samples.size() / 7);
     for (size_t k = 0; k < cnt; k++) {
-        double* s = hs + 7 * k;
-        s[0] = e->dt_buf[frame][k0 + k];
         const Vec3 &a = e->acc_buf[frame][k0 + k], &w = e->gyr_buf[frame][k0 + k];
-        s[1] = a.x; s[2] = a.y; s[3] = a.z; s[4] = w.x; s[5] = w.y; s[6] = w.z;
+        const double rec[7] = {e->dt_buf[frame][k0 + k], a.x, a.y, a.z, w.x, w.y, w.z};
+        e->job_samples.insert(e->job_samples.end(), rec, rec + 7);
     }
-    VE_CUDA(cudaMemcpyAsync(ds, hs, sizeof(double) * 7 * cnt, cudaMemcpyHostToDevice, e->stream));
-    e->prof.begin(e->stream);
-    vb::launch_preint_push(e->d_preint.p + e->slot_of[frame], (int)cnt, ds, e->cfg.acc_n, e->cfg.gyr_n, e->cfg.acc_w,
-                           e->cfg.gyr_w, e->stream);
-    e->prof.end(6, e->stream);
-    e->h2d_bytes += sizeof(double) * 7 * cnt;
-    e->last_launches++;
+    e->jobs.push_back(j);
     e->flushed[frame] = n;
     e->sqrt_dirty[e->slot_of[frame]] = true;
-    return VE_OK;
 }
 
-int refresh_sqrt_info(ve_estimator* e) {
-    int cnt = 0;
+unsigned refresh_sqrt_mask(ve_estimator* e) {
+    unsigned mask = 0;
     for (int f = 1; f <= e->W; f++) {
         const int s = e->slot_of[f];
         if (e->slot_valid[f] && e->sqrt_dirty[s] && e->dt_buf[f].size() > 0) {
-            e->h_which[cnt++] = s;
+            mask |= 1u << s;
             e->sqrt_dirty[s] = false;
         }
     }
-    if (!cnt) return VE_OK;
-    // no host wait: h_which is rewritten only after the next solve's read-back has drained the stream
-    VE_CUDA(cudaMemcpyAsync(e->d_which.p, e->h_which, sizeof(int) * cnt, cudaMemcpyHostToDevice, e->stream));
-    e->prof.begin(e->stream);
-    vb::launch_sqrt_info(e->d_preint.p, e->d_which.p, cnt, e->stream);
-    e->prof.end(7, e->stream);
-    e->last_launches++;
-    return VE_OK;
+    return mask;
 }
 
 // ---- FeatureManager (feature_manager.cpp) ------------------------------------------------------
@@ -377,10 +445,10 @@ void set_parameter(ve_estimator* e) {
 }
 
 void clear_state(ve_estimator* e) {
-    if (e->stream) cudaStreamSynchronize(e->stream);  // nothing of the old state may still be in flight
-    e->marg_pending = false;
-    e->states_upload_pending = false;
-    e->flushes_in_flight = 0;
+    // Device-side leftovers need no wait: the slots are re-created by queued jobs, the prior is dropped (has_prior), and
+    // anything still running on the batch stream is ordered before the next frame's kernels.
+    e->jobs.clear();
+    e->job_samples.clear();
     for (int i = 0; i <= e->W; i++) {
         e->Rs[i] = Mat3();
         e->Ps[i] = e->Vs[i] = e->Bas[i] = e->Bgs[i] = Vec3();
@@ -405,17 +473,14 @@ void clear_state(ve_estimator* e) {
     e->failure_occur = false;
 }
 
-int process_imu(ve_estimator* e, double dt, const Vec3& acc, const Vec3& gyr) {
+void process_imu(ve_estimator* e, double dt, const Vec3& acc, const Vec3& gyr) {
     if (!e->first_imu) {
         e->first_imu = true;
         e->acc_0 = acc;
         e->gyr_0 = gyr;
     }
     const int j = e->frame_count;
-    if (!e->slot_valid[j]) {
-        const int rc = init_slot(e, j, e->acc_0, e->gyr_0, e->Bas[j], e->Bgs[j]);
-        if (rc) return rc;
-    }
+    if (!e->slot_valid[j]) init_slot(e, j, e->acc_0, e->gyr_0, e->Bas[j], e->Bgs[j]);
     if (j != 0) {
         e->dt_buf[j].push_back(dt);
         e->acc_buf[j].push_back(acc);
@@ -431,32 +496,32 @@ int process_imu(ve_estimator* e, double dt, const Vec3& acc, const Vec3& gyr) {
     }
     e->acc_0 = acc;
     e->gyr_0 = gyr;
-    return VE_OK;
 }
 
-int initial_from_seed(ve_estimator* e, bool* ok) {
-    *ok = false;
+bool initial_from_seed(ve_estimator* e) {
     for (int i = 0; i <= e->W; i++) {
         const SeedRow* s = nullptr;
         for (auto& c : e->seeds)
             if (std::fabs(c.t - e->Headers[i]) < 1e-6) s = &c;
-        if (!s) return VE_OK;
+        if (!s) return false;
+    }
+    for (int i = 0; i <= e->W; i++) {
+        const SeedRow* s = nullptr;
+        for (auto& c : e->seeds)
+            if (std::fabs(c.t - e->Headers[i]) < 1e-6) s = &c;
         e->Ps[i] = s->P; e->Rs[i] = s->R; e->Vs[i] = s->V; e->Bas[i] = e->seed_ba; e->Bgs[i] = e->seed_bg;
     }
     for (int i = 0; i <= e->W; i++) {  // IntegrationBase::repropagate(Bas[i], Bgs[i])
         if (!e->slot_valid[i]) continue;
         const Vec3 la = e->lin_acc[i], lg = e->lin_gyr[i];
-        int rc = init_slot(e, i, la, lg, e->Bas[i], e->Bgs[i]);
-        if (rc) return rc;
+        init_slot(e, i, la, lg, e->Bas[i], e->Bgs[i]);
         e->sum_dt[i] = 0;
         for (double v : e->dt_buf[i]) e->sum_dt[i] += v;
-        rc = flush_frame(e, i);
-        if (rc) return rc;
+        flush_frame(e, i);
     }
     for (auto& it : e->feature) it.estimated_depth = -1;
     triangulate(e);
-    *ok = true;
-    return VE_OK;
+    return true;
 }
 
 bool failure_detection(ve_estimator* e) {
@@ -470,7 +535,7 @@ bool failure_detection(ve_estimator* e) {
 }
 
 // vector2double (estimator.cpp:486-528): packs the window into the staging layout pose|sb|ex|td|lam
-void pack_states(ve_estimator* e, double* out, int* n_lam) {
+void pack_states(ve_estimator* e, double* out) {
     const int F = e->W + 1;
     for (int i = 0; i < F; i++) {
         const Quat q = Quat::FromR(e->Rs[i]);
@@ -488,195 +553,43 @@ void pack_states(ve_estimator* e, double* out, int* n_lam) {
     int k = 0;
     for (auto& it : e->feature)
         if (usable(e, it)) out[16 * F + 8 + k++] = 1. / it.estimated_depth;
-    *n_lam = k;
 }
 
-// double2vector (estimator.cpp:530-619)
-void unpack_states(ve_estimator* e, const double* in) {
+// Results of the device-side double2vector (ba_finish_kernel) -> Estimator members.
+void unpack_results(ve_estimator* e, const double* out) {
     const int F = e->W + 1;
-    Vec3 origin_R0 = hm::R2ypr(e->Rs[0]);
-    Vec3 origin_P0 = e->Ps[0];
-    if (e->failure_occur) {
-        origin_R0 = hm::R2ypr(e->last_R0);
-        origin_P0 = e->last_P0;
-        e->failure_occur = false;
-    }
-    auto Qp = [&](const double* p) { return Quat(p[6], p[3], p[4], p[5]); };
-    const Mat3 R00 = Qp(in).R();
-    const Vec3 origin_R00 = hm::R2ypr(R00);
-    const double y_diff = origin_R0.x - origin_R00.x;
-    Mat3 rot_diff = hm::ypr2R(Vec3(y_diff, 0, 0));
-    if (std::fabs(std::fabs(origin_R0.y) - 90) < 1.0 || std::fabs(std::fabs(origin_R00.y) - 90) < 1.0) rot_diff = e->Rs[0] * R00.T();
+    std::memcpy(&e->last_state, out, sizeof(vb::SolverState));
+    const double* of = out + vb::BA_OUT_ST_DOUBLES;
     for (int i = 0; i < F; i++) {
-        const double* p = in + 7 * i;
-        const double* s = in + 7 * F + 9 * i;
-        e->Rs[i] = rot_diff * Qp(p).normalized().R();
-        e->Ps[i] = rot_diff * Vec3(p[0] - in[0], p[1] - in[1], p[2] - in[2]) + origin_P0;
-        e->Vs[i] = rot_diff * Vec3(s[0], s[1], s[2]);
-        e->Bas[i] = Vec3(s[3], s[4], s[5]);
-        e->Bgs[i] = Vec3(s[6], s[7], s[8]);
+        const double* o = of + 21 * i;
+        e->Ps[i] = Vec3(o[0], o[1], o[2]);
+        std::memcpy(e->Rs[i].m, o + 3, 9 * sizeof(double));
+        e->Vs[i] = Vec3(o[12], o[13], o[14]);
+        e->Bas[i] = Vec3(o[15], o[16], o[17]);
+        e->Bgs[i] = Vec3(o[18], o[19], o[20]);
     }
-    const double* x = in + 16 * F;
+    const double* x = of + 21 * F;
     e->tic = Vec3(x[0], x[1], x[2]);
-    e->ric = Qp(x).R();
+    std::memcpy(e->ric.m, x + 3, 9 * sizeof(double));
+    if (e->cfg.estimate_td) e->td = x[12];
+    const double* od = x + 13;
     int k = 0;
     for (auto& it : e->feature) {  // FeatureManager::setDepth
         if (!usable(e, it)) continue;
-        it.estimated_depth = 1.0 / in[16 * F + 8 + k++];
+        it.estimated_depth = od[k++];
         it.solve_flag = it.estimated_depth < 0 ? 2 : 1;
     }
-    if (e->cfg.estimate_td) e->td = in[16 * F + 7];
 }
 
-int upload_prior_meta(ve_estimator* e, int buf) {
-    const int nb = (int)e->prior_blocks.size();
-    for (int b = 0; b < nb; b++) {
-        e->h_prior_i[b] = e->prior_blocks[b].type;
-        e->h_prior_i[64 + b] = e->prior_blocks[b].index;
-        e->h_prior_i[128 + b] = e->prior_blocks[b].off;
-    }
-    VE_CUDA(cudaMemcpyAsync(e->d_prior_i[buf].p, e->h_prior_i, sizeof(int) * 192, cudaMemcpyHostToDevice, e->stream));
-    return VE_OK;
-}
+struct MargHost {  // host side of one marginalisation plan
+    bool run = false;
+    std::vector<int> lms, col_lm;
+    std::vector<PriorBlock> kept, shifted;
+};
 
-vb::BaPrior prior_view(const ve_estimator* e) {
-    vb::BaPrior pr{};
-    if (!e->has_prior) return pr;
-    const int buf = e->prior_buf;
-    const int nm = e->nmax;
-    pr.n = e->prior_n;
-    pr.nblocks = (int)e->prior_blocks.size();
-    pr.type = e->d_prior_i[buf].p;
-    pr.index = pr.type + 64;
-    pr.off = pr.type + 128;
-    pr.A = e->d_prior[buf].p;
-    pr.g0 = pr.A + (size_t)nm * nm;
-    pr.c0 = pr.g0 + nm;
-    pr.x0 = pr.c0 + 1;
-    return pr;
-}
-
-// Fills a BaProblem for the current window; uploads the observation table and the states to x[0].
-int build_problem(ve_estimator* e, vb::BaProblem& p, bool upload_tables) {
-    const int W = e->W, F = W + 1;
-    int L = 0, M = 0;
-    int* lm_anchor = e->h_ints;
-    int* lm_start = lm_anchor + e->Lmax;
-    int* ob_frame = lm_start + e->Lmax + 1;
-    int* imu_slot = ob_frame + e->Mmax;
-    double* lm_pts = e->h_obs;
-    double* lm_vel = lm_pts + 2 * e->Lmax;
-    double* lm_td = lm_vel + 2 * e->Lmax;
-    double* lm_row = lm_td + e->Lmax;
-    double* ob_pts = lm_row + e->Lmax;
-    double* ob_vel = ob_pts + 2 * e->Mmax;
-    double* ob_td = ob_vel + 2 * e->Mmax;
-    double* ob_row = ob_td + e->Mmax;
-    for (auto& it : e->feature) {
-        if (!usable(e, it)) continue;
-        if (L >= e->Lmax || M + (int)it.feature_per_frame.size() > e->Mmax) {
-            e->err = "feature capacity (max_features) exceeded";  // NUM_OF_F overflow is silent in the reference (estimator.h:111)
-            return VE_ERR_CAPACITY;
-        }
-        const FeaturePerFrame& f0 = it.feature_per_frame[0];
-        lm_anchor[L] = it.start_frame;
-        lm_start[L] = M;
-        lm_pts[2 * L] = f0.point.x; lm_pts[2 * L + 1] = f0.point.y;
-        lm_vel[2 * L] = f0.vx; lm_vel[2 * L + 1] = f0.vy;
-        lm_td[L] = f0.cur_td;
-        lm_row[L] = f0.v;
-        for (size_t k = 1; k < it.feature_per_frame.size(); k++) {
-            const FeaturePerFrame& fj = it.feature_per_frame[k];
-            ob_frame[M] = it.start_frame + (int)k;
-            ob_pts[2 * M] = fj.point.x; ob_pts[2 * M + 1] = fj.point.y;
-            ob_vel[2 * M] = fj.vx; ob_vel[2 * M + 1] = fj.vy;
-            ob_td[M] = fj.cur_td;
-            ob_row[M] = fj.v;
-            M++;
-        }
-        L++;
-    }
-    lm_start[L] = M;
-    for (int k = 0; k < W; k++) imu_slot[k] = (e->sum_dt[k + 1] > 10.0 || !e->slot_valid[k + 1]) ? -1 : e->slot_of[k + 1];
-    if (upload_tables) {
-        const size_t nints = (size_t)e->Lmax + (e->Lmax + 1) + e->Mmax + W;
-        const size_t nobs = 6 * (size_t)e->Lmax + 6 * (size_t)e->Mmax;
-        VE_CUDA(cudaMemcpyAsync(e->d_ints.p, e->h_ints, sizeof(int) * nints, cudaMemcpyHostToDevice, e->stream));
-        VE_CUDA(cudaMemcpyAsync(e->d_obs.p, e->h_obs, sizeof(double) * nobs, cudaMemcpyHostToDevice, e->stream));
-        e->h2d_bytes += sizeof(int) * nints + sizeof(double) * nobs;
-    }
-    vb::BaDims& d = p.dims;
-    d.W = W;
-    d.L = L;
-    d.M = M;
-    d.est_ex = e->cfg.estimate_extrinsic ? 1 : 0;
-    d.est_td = e->cfg.estimate_td ? 1 : 0;
-    d.col_sb = 6 * F;
-    d.col_ex = d.est_ex ? 15 * F : -1;
-    d.col_td = d.est_td ? 15 * F + 6 * d.est_ex : -1;
-    d.D = 15 * F + 6 * d.est_ex + d.est_td;
-    d.sqrt_info_vis = e->cfg.focal_length / 1.5;
-    d.tr_over_row = e->cfg.tr / e->cfg.row;
-    d.half_row = e->cfg.row / 2;
-    d.G[0] = 0; d.G[1] = 0; d.G[2] = e->cfg.g_norm;
-    // the accumulation buffers were sized for the maximum D; the kernels index with dims.D
-    for (int b = 0; b < 2; b++) {
-        p.x[b] = states_view(e, b);
-        double* a = e->d_acc[b].p;
-        p.acc[b].Hpp = a;
-        p.acc[b].gp = a + (size_t)d.D * d.D;
-        p.acc[b].Hpl = p.acc[b].gp + d.D;
-        p.acc[b].Hll = p.acc[b].Hpl + (size_t)e->Lmax * d.D;
-        p.acc[b].gl = p.acc[b].Hll + e->Lmax;
-        p.acc[b].cost = p.acc[b].gl + e->Lmax;
-    }
-    const int* di = e->d_ints.p;
-    p.lm_anchor = di;
-    p.lm_start = di + e->Lmax;
-    p.ob_frame = di + 2 * e->Lmax + 1;
-    p.imu_slot = p.ob_frame + e->Mmax;
-    const double* dobs = e->d_obs.p;
-    p.lm_pts = dobs;
-    p.lm_vel = dobs + 2 * e->Lmax;
-    p.lm_td = dobs + 4 * e->Lmax;
-    p.lm_row = dobs + 5 * e->Lmax;
-    p.ob_pts = dobs + 6 * e->Lmax;
-    p.ob_vel = p.ob_pts + 2 * e->Mmax;
-    p.ob_td = p.ob_vel + 2 * e->Mmax;
-    p.ob_row = p.ob_td + e->Mmax;
-    p.preint = e->d_preint.p;
-    p.prior = prior_view(e);
-    p.S = e->d_S.p;
-    p.Spk = e->d_Spk.p;
-    p.Hfull = e->d_Hfull.p;
-    p.gred = e->d_gred.p;
-    const size_t N = (size_t)e->D + e->Lmax;
-    p.scale = e->d_vec.p;
-    p.diag = p.scale + N;
-    p.grad = p.diag + N;
-    p.gn = p.grad + N;
-    p.work = e->d_work.p;
-    p.st = e->d_st.p;
-    e->last_landmarks = L;
-    e->last_visual = M;
-    return VE_OK;
-}
-
-int upload_states(ve_estimator* e, int* n_lam) {
-    if (e->states_upload_pending) {  // marginalize() of the previous frame staged its linearisation point here
-        VE_CUDA(cudaEventSynchronize(e->ev[6]));
-        e->states_upload_pending = false;
-    }
-    pack_states(e, e->h_states, n_lam);
-    VE_CUDA(cudaMemcpyAsync(e->d_states[0].p, e->h_states, sizeof(double) * states_doubles(e), cudaMemcpyHostToDevice, e->stream));
-    e->h2d_bytes += sizeof(double) * states_doubles(e);
-    return VE_OK;
-}
-
-int finish_marg(ve_estimator* e);
-
-// The marginalisation branches of Estimator::optimization (estimator.cpp:826-999)
-int marginalize(ve_estimator* e, vb::BaProblem& p) {
+// The marginalisation branches of Estimator::optimization (estimator.cpp:826-999): everything but the arithmetic is
+// known before the solve (which blocks are dropped, the column layout, the identities of the kept blocks).
+int plan_marginalization(ve_estimator* e, vb::MargPlan& mp, MargHost& mh) {
     const int W = e->W, F = W + 1;
     const bool old = e->marginalization_flag == 0;
     auto prior_has = [&](int type, int index) {
@@ -684,19 +597,8 @@ int marginalize(ve_estimator* e, vb::BaProblem& p) {
             if (b.type == type && (type >= 2 || b.index == index)) return true;
         return false;
     };
+    mh.run = false;
     if (!old && !(e->has_prior && prior_has(0, W - 1))) return VE_OK;
-    // the previous marginalisation's diagnostics are collected before its staging area is reused (the stream has just
-    // been drained by the solve's read-back: no wait)
-    int rc = finish_marg(e);
-    if (rc) return rc;
-    // vector2double() after double2vector(): the linearisation point is the re-anchored state
-    int n_lam = 0;
-    rc = upload_states(e, &n_lam);
-    if (rc) return rc;
-    VE_CUDA(cudaEventRecord(e->ev[6], e->stream));
-    e->states_upload_pending = true;
-    VE_CUDA(cudaEventRecord(e->ev[5], e->stream));
-    // which parameter blocks take part
     std::vector<bool> t_pose(F, false), t_sb(F, false);
     bool t_ex = false, t_td = false;
     if (e->has_prior)
@@ -706,8 +608,6 @@ int marginalize(ve_estimator* e, vb::BaProblem& p) {
             else if (b.type == 2) t_ex = true;
             else t_td = true;
         }
-    vb::MargPlan mp{};
-    std::vector<int> lms, col_lm;
     mp.use_imu = 0;
     if (old) {
         if (e->slot_valid[1] && e->sum_dt[1] < 10.0) {
@@ -719,7 +619,7 @@ int marginalize(ve_estimator* e, vb::BaProblem& p) {
             if (!usable(e, it)) continue;
             ++li;
             if (it.start_frame != 0) continue;
-            lms.push_back(li);
+            mh.lms.push_back(li);
             t_pose[0] = true;
             for (size_t k = 1; k < it.feature_per_frame.size(); k++) t_pose[k] = true;
             t_ex = true;
@@ -734,146 +634,283 @@ int marginalize(ve_estimator* e, vb::BaProblem& p) {
     if (t_pose[drop_pose]) { mp.col_pose[drop_pose] = pos; pos += 6; }
     if (old && t_sb[0]) { mp.col_sb[0] = pos; pos += 9; }
     mp.m_dense = pos;
-    for (size_t k = 0; k < lms.size(); k++) col_lm.push_back(pos++);
-    mp.n_lm = (int)lms.size();
+    for (size_t k = 0; k < mh.lms.size(); k++) mh.col_lm.push_back(pos++);
+    mp.n_lm = (int)mh.lms.size();
     const int m = pos;
-    std::vector<PriorBlock> kept;
     for (int f = 0; f < F; f++)
-        if (t_pose[f] && mp.col_pose[f] < 0) { mp.col_pose[f] = pos; kept.push_back({0, f, pos - m, 6}); pos += 6; }
+        if (t_pose[f] && mp.col_pose[f] < 0) { mp.col_pose[f] = pos; mh.kept.push_back({0, f, pos - m, 6}); pos += 6; }
     for (int f = 0; f < F; f++)
-        if (t_sb[f] && mp.col_sb[f] < 0) { mp.col_sb[f] = pos; kept.push_back({1, f, pos - m, 9}); pos += 9; }
-    if (t_ex) { mp.col_ex = pos; kept.push_back({2, 0, pos - m, 6}); pos += 6; }
-    if (t_td) { mp.col_td = pos; kept.push_back({3, 0, pos - m, 1}); pos += 1; }
+        if (t_sb[f] && mp.col_sb[f] < 0) { mp.col_sb[f] = pos; mh.kept.push_back({1, f, pos - m, 9}); pos += 9; }
+    if (t_ex) { mp.col_ex = pos; mh.kept.push_back({2, 0, pos - m, 6}); pos += 6; }
+    if (t_td) { mp.col_td = pos; mh.kept.push_back({3, 0, pos - m, 1}); pos += 1; }
     mp.P = pos;
     mp.n = pos - m;
-    if (mp.n > e->nmax || mp.P > e->nmax + 15 + e->Lmax || mp.m_dense == 0) {
+    if (mp.n > e->nmax || mp.P > e->nmax + 15 + e->Lmax || mp.m_dense == 0 || (int)mh.kept.size() > vb::BA_MAX_PRIOR_BLOCKS) {
         e->err = "marginalisation system larger than the configured capacity";
         return VE_ERR_CAPACITY;
     }
-    for (size_t k = 0; k < lms.size(); k++) {
-        e->h_marg_i[k] = lms[k];
-        e->h_marg_i[e->Lmax + k] = col_lm[k];
-    }
-    VE_CUDA(cudaMemcpyAsync(e->d_marg_i.p, e->h_marg_i, sizeof(int) * 2 * e->Lmax, cudaMemcpyHostToDevice, e->stream));
-    mp.lms = e->d_marg_i.p;
-    mp.col_lm = e->d_marg_i.p + e->Lmax;
-    const size_t Pm = (size_t)e->nmax + 15 + e->Lmax;
-    mp.Am = e->d_marg.p;
-    mp.bm = mp.Am + Pm * Pm;
-    mp.Araw = mp.bm + Pm;
-    mp.graw = mp.Araw + (size_t)e->nmax * e->nmax;
-    mp.Wglobal = mp.graw + e->nmax;  // (nmax + 15)^2 doubles
-    mp.w_in_global = 0;
-    const int nb = e->prior_buf ^ 1;
-    mp.Aout = e->d_prior[nb].p;
-    mp.gout = mp.Aout + (size_t)e->nmax * e->nmax;
-    mp.cout = mp.gout + e->nmax;
-    // NOTE: Aout is written with leading dimension n (dense n x n at the front of the buffer)
-    vb::launch_marginalize(p, mp, e->stream, &e->last_launches, &e->prof);
-    VE_CUDA(cudaGetLastError());
-    // new prior: linearisation point = current parameter values of the kept blocks, identities shifted
-    // (addr_shift, estimator.cpp:913-925 / :969-990)
-    double* x0 = e->h_prior;
-    std::vector<PriorBlock> shifted;
-    for (size_t b = 0; b < kept.size(); b++) {
-        PriorBlock nbk = kept[b];
-        double* dst = x0 + 9 * b;
-        std::memset(dst, 0, 9 * sizeof(double));
-        const double* src = nullptr;
-        int gsz = 0;
-        if (nbk.type == 0) { src = e->h_states + 7 * nbk.index; gsz = 7; }
-        else if (nbk.type == 1) { src = e->h_states + 7 * F + 9 * nbk.index; gsz = 9; }
-        else if (nbk.type == 2) { src = e->h_states + 16 * F; gsz = 7; }
-        else { src = e->h_states + 16 * F + 7; gsz = 1; }
-        std::memcpy(dst, src, gsz * sizeof(double));
+    // identities of the kept blocks after the slide (addr_shift, estimator.cpp:913-925 / :969-990)
+    for (auto nbk : mh.kept) {
         if (nbk.type <= 1) {
             if (old) nbk.index -= 1;
             else if (nbk.index == W) nbk.index = W - 1;
         }
-        shifted.push_back(nbk);
+        mh.shifted.push_back(nbk);
     }
-    double* d_x0 = e->d_prior[nb].p + (size_t)e->nmax * e->nmax + e->nmax + 1;
-    VE_CUDA(cudaMemcpyAsync(d_x0, x0, sizeof(double) * 9 * kept.size(), cudaMemcpyHostToDevice, e->stream));
-    // un-thresholded Schur complement for tests
-    VE_CUDA(cudaMemcpyAsync(e->h_marg_out, mp.Araw, sizeof(double) * ((size_t)e->nmax * e->nmax + e->nmax), cudaMemcpyDeviceToHost, e->stream));
-    e->prior_blocks = shifted;
-    e->prior_n = mp.n;
-    e->prior_buf = nb;
-    e->has_prior = true;
-    rc = upload_prior_meta(e, nb);
-    if (rc) return rc;
-    // No host wait: the new prior is consumed by the next solve on the same (in-order) stream, so the marginalisation
-    // overlaps whatever the caller does next (the reference's tracker node runs in another process anyway).
-    e->marg_pending = true;
-    e->marg_n = mp.n;
+    mh.run = true;
     return VE_OK;
 }
 
-// Waits for a pending marginalisation and collects its diagnostics (Schur complement before the eps floor).
-int finish_marg(ve_estimator* e) {
-    if (!e->marg_pending) return VE_OK;
-    VE_CUDA(cudaEventSynchronize(e->ev[3]));
-    e->marg_pending = false;
-    const int n = e->marg_n;
-    e->prior_raw_A.assign(e->h_marg_out, e->h_marg_out + (size_t)n * n);
-    e->prior_raw_b.assign(e->h_marg_out + (size_t)e->nmax * e->nmax, e->h_marg_out + (size_t)e->nmax * e->nmax + n);
-    if (n + 7 <= e->nmax)
-        for (int k = 0; k < 7; k++) e->marg_sweeps[k] = e->h_marg_out[(size_t)e->nmax * e->nmax + n + k];
-    cudaEventElapsedTime(&e->last_ms[2], e->ev[5], e->ev[3]);
-    return VE_OK;
-}
+// Builds this member's part of the frame: the input block (jobs, samples, observation table, states, marginalisation
+// lists) in the pinned arena and its descriptor.  `solve` = the window is optimised this frame.
+int stage_frame(ve_estimator* e, bool solve) {
+    ve_batch* b = e->batch;
+    vb::BaSeq& q = b->h_seq[e->member];
+    const int W = e->W, F = W + 1;
+    q.active = 0;
+    q.do_marg = 0;
+    q.n_jobs = 0;
+    q.sqrt_mask = 0;
+    e->fr_marg = false;
+    int L = 0, M = 0;
+    vb::MargPlan mp{};
+    MargHost mh;
+    if (solve) {
+        for (int f = 0; f <= W; f++) flush_frame(e, f);
+        q.sqrt_mask = refresh_sqrt_mask(e);
+        for (auto& it : e->feature) {
+            if (!usable(e, it)) continue;
+            if (L >= e->Lmax || M + (int)it.feature_per_frame.size() > e->Mmax) {
+                e->err = "feature capacity (max_features) exceeded";  // NUM_OF_F overflow is silent in the reference (estimator.h:111)
+                return VE_ERR_CAPACITY;
+            }
+            M += (int)it.feature_per_frame.size() - 1;
+            L++;
+        }
+        const int rc = plan_marginalization(e, mp, mh);
+        if (rc) return rc;
+    }
+    const size_t n_jobs = e->jobs.size(), n_rec = e->job_samples.size() / 7;
+    if (!solve && n_jobs == 0) return VE_OK;
+    const size_t n_lm = mh.lms.size();
+    // layout of the input block (byte offsets, every array 16-byte aligned)
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t o = off;
+        off += align16(bytes);
+        return o;
+    };
+    const size_t o_jobs = take(n_jobs * sizeof(vb::PreintJob)), o_samples = take(n_rec * 7 * sizeof(double));
+    size_t o_int = 0, o_dbl = 0, o_states = 0, o_marg = 0;
+    if (solve) {
+        o_int = take(sizeof(int) * ((size_t)2 * L + 1 + M + W));
+        o_dbl = take(sizeof(double) * (6 * (size_t)L + 6 * (size_t)M));
+        o_states = take(sizeof(double) * states_doubles(e, L));
+        o_marg = take(sizeof(int) * 2 * n_lm);
+    }
+    const size_t base = b->in_used.fetch_add(off);
+    if (base + off > b->in_cap) {
+        e->err = "batch input arena exhausted";
+        return VE_ERR_CAPACITY;
+    }
+    unsigned char* hb = b->h_in + base;
+    unsigned char* db = b->d_in + base;
+    e->h2d_bytes = off + sizeof(vb::BaSeq);
+    // pre-integration jobs
+    if (n_jobs) std::memcpy(hb + o_jobs, e->jobs.data(), n_jobs * sizeof(vb::PreintJob));
+    if (n_rec) std::memcpy(hb + o_samples, e->job_samples.data(), n_rec * 7 * sizeof(double));
+    q.n_jobs = (int)n_jobs;
+    q.jobs = reinterpret_cast<const vb::PreintJob*>(db + o_jobs);
+    q.samples = reinterpret_cast<const double*>(db + o_samples);
+    q.noise[0] = e->cfg.acc_n; q.noise[1] = e->cfg.gyr_n; q.noise[2] = e->cfg.acc_w; q.noise[3] = e->cfg.gyr_w;
+    q.p.preint = e->d_preint.p;
+    e->jobs.clear();
+    e->job_samples.clear();
+    if (!solve) return VE_OK;
 
-int optimization(ve_estimator* e) {
-    int rc;
-    // No wait for the previous frame's marginalisation here: everything below is enqueued behind it on the same stream
-    // while it is still running, so the host side of a frame (bookkeeping, problem tables, uploads, 26 launches) is
-    // hidden instead of sitting between two kernels.
-    VE_CUDA(cudaEventRecord(e->ev[0], e->stream));
-    for (int f = 0; f <= e->W; f++)
-        if ((rc = flush_frame(e, f))) return rc;
-    if ((rc = refresh_sqrt_info(e))) return rc;
-    VE_CUDA(cudaEventRecord(e->ev[1], e->stream));
-    vb::BaProblem p{};
-    if ((rc = build_problem(e, p, true))) return rc;
-    int n_lam = 0;
-    if ((rc = upload_states(e, &n_lam))) return rc;
-    vb::SolverState& st = *e->h_st;
+    // ---- observation table grouped by landmark (Estimator::optimization's problem assembly, estimator.cpp:670-801)
+    int* lm_anchor = reinterpret_cast<int*>(hb + o_int);
+    int* lm_start = lm_anchor + L;
+    int* ob_frame = lm_start + L + 1;
+    int* imu_slot = ob_frame + M;
+    double* lm_pts = reinterpret_cast<double*>(hb + o_dbl);
+    double* lm_vel = lm_pts + 2 * L;
+    double* lm_td = lm_vel + 2 * L;
+    double* lm_row = lm_td + L;
+    double* ob_pts = lm_row + L;
+    double* ob_vel = ob_pts + 2 * M;
+    double* ob_td = ob_vel + 2 * M;
+    double* ob_row = ob_td + M;
+    int l = 0, m = 0;
+    for (auto& it : e->feature) {
+        if (!usable(e, it)) continue;
+        const FeaturePerFrame& f0 = it.feature_per_frame[0];
+        lm_anchor[l] = it.start_frame;
+        lm_start[l] = m;
+        lm_pts[2 * l] = f0.point.x; lm_pts[2 * l + 1] = f0.point.y;
+        lm_vel[2 * l] = f0.vx; lm_vel[2 * l + 1] = f0.vy;
+        lm_td[l] = f0.cur_td;
+        lm_row[l] = f0.v;
+        for (size_t k = 1; k < it.feature_per_frame.size(); k++) {
+            const FeaturePerFrame& fj = it.feature_per_frame[k];
+            ob_frame[m] = it.start_frame + (int)k;
+            ob_pts[2 * m] = fj.point.x; ob_pts[2 * m + 1] = fj.point.y;
+            ob_vel[2 * m] = fj.vx; ob_vel[2 * m + 1] = fj.vy;
+            ob_td[m] = fj.cur_td;
+            ob_row[m] = fj.v;
+            m++;
+        }
+        l++;
+    }
+    lm_start[L] = M;
+    for (int k = 0; k < W; k++) imu_slot[k] = (e->sum_dt[k + 1] > 10.0 || !e->slot_valid[k + 1]) ? -1 : e->slot_of[k + 1];
+    double* h_states = reinterpret_cast<double*>(hb + o_states);
+    pack_states(e, h_states);
+
+    vb::BaProblem& p = q.p;
+    vb::BaDims& d = p.dims;
+    d.W = W;
+    d.L = L;
+    d.M = M;
+    d.est_ex = e->cfg.estimate_extrinsic ? 1 : 0;
+    d.est_td = e->cfg.estimate_td ? 1 : 0;
+    d.col_sb = 6 * F;
+    d.col_ex = d.est_ex ? 15 * F : -1;
+    d.col_td = d.est_td ? 15 * F + 6 * d.est_ex : -1;
+    d.D = 15 * F + 6 * d.est_ex + d.est_td;
+    d.pad = 0;
+    d.sqrt_info_vis = e->cfg.focal_length / 1.5;
+    d.tr_over_row = e->cfg.tr / e->cfg.row;
+    d.half_row = e->cfg.row / 2;
+    d.G[0] = 0; d.G[1] = 0; d.G[2] = e->cfg.g_norm;
+    p.x[0] = states_view(reinterpret_cast<double*>(db + o_states), F);
+    p.x[1] = states_view(e->d_states1.p, F);
+    for (int k = 0; k < 2; k++) {  // the accumulation buffers were sized for the maximum D; the kernels index with dims.D
+        double* a = e->d_acc[k].p;
+        p.acc[k].Hpp = a;
+        p.acc[k].gp = a + (size_t)d.D * d.D;
+        p.acc[k].Hpl = p.acc[k].gp + d.D;
+        p.acc[k].Hll = p.acc[k].Hpl + (size_t)e->Lmax * d.D;
+        p.acc[k].gl = p.acc[k].Hll + e->Lmax;
+        p.acc[k].cost = p.acc[k].gl + e->Lmax;
+    }
+    const int* di = reinterpret_cast<const int*>(db + o_int);
+    p.lm_anchor = di;
+    p.lm_start = di + L;
+    p.ob_frame = di + 2 * L + 1;
+    p.imu_slot = p.ob_frame + M;
+    const double* dobs = reinterpret_cast<const double*>(db + o_dbl);
+    p.lm_pts = dobs;
+    p.lm_vel = dobs + 2 * L;
+    p.lm_td = dobs + 4 * L;
+    p.lm_row = dobs + 5 * L;
+    p.ob_pts = dobs + 6 * L;
+    p.ob_vel = p.ob_pts + 2 * M;
+    p.ob_td = p.ob_vel + 2 * M;
+    p.ob_row = p.ob_td + M;
+    // current prior
+    vb::BaPrior& pr = p.prior;
+    pr = vb::BaPrior{};
+    vb::BaSeq* dq = b->d_seq + e->member;
+    if (e->has_prior) {
+        const int nm = e->nmax;
+        pr.n = e->prior_n;
+        pr.nblocks = (int)e->prior_blocks.size();
+        for (int k = 0; k < pr.nblocks; k++) {
+            q.prior_type[k] = e->prior_blocks[k].type;
+            q.prior_index[k] = e->prior_blocks[k].index;
+            q.prior_off[k] = e->prior_blocks[k].off;
+        }
+        pr.type = dq->prior_type;  // addresses inside the device copy of this descriptor
+        pr.index = dq->prior_index;
+        pr.off = dq->prior_off;
+        pr.A = e->d_prior[e->prior_buf].p;
+        pr.g0 = pr.A + (size_t)nm * nm;
+        pr.c0 = pr.g0 + nm;
+        pr.x0 = pr.c0 + 1;
+    }
+    p.S = e->d_S.p;
+    p.Spk = e->d_Spk.p;
+    p.Hfull = e->d_Hfull.p;
+    p.gred = e->d_gred.p;
+    const size_t N = (size_t)e->D + e->Lmax;
+    p.scale = e->d_vec.p;
+    p.diag = p.scale + N;
+    p.grad = p.diag + N;
+    p.gn = p.grad + N;
+    p.work = e->d_work.p;
+    p.st = &dq->st;
+    vb::SolverState& st = q.st;
     std::memset(&st, 0, sizeof(st));
     st.max_iterations = e->cfg.num_iterations;
     st.first = 1;
     st.radius = 1e4;
     st.mu = 1e-8;
-    VE_CUDA(cudaMemcpyAsync(e->d_st.p, &st, sizeof(st), cudaMemcpyHostToDevice, e->stream));
-    vb::launch_ba_solve(p, e->cfg.num_iterations, e->stream, &e->last_launches, &e->prof);
-    VE_CUDA(cudaGetLastError());
-    VE_CUDA(cudaMemcpyAsync(&st, e->d_st.p, sizeof(st), cudaMemcpyDeviceToHost, e->stream));
-    const size_t ns = states_doubles(e);
-    double* h2 = e->h_states + ns;  // second half of the staging area holds both device buffers
-    VE_CUDA(cudaMemcpyAsync(h2, e->d_states[0].p, sizeof(double) * ns, cudaMemcpyDeviceToHost, e->stream));
-    VE_CUDA(cudaMemcpyAsync(h2 + ns, e->d_states[1].p, sizeof(double) * ns, cudaMemcpyDeviceToHost, e->stream));
-    e->d2h_bytes += 2 * sizeof(double) * ns + sizeof(st);
-    VE_CUDA(cudaEventRecord(e->ev[2], e->stream));
-    VE_CUDA(cudaStreamSynchronize(e->stream));
-    e->flushes_in_flight = 0;
-    e->last_state = st;
-    e->n_solves++;
-    unpack_states(e, h2 + (size_t)st.cur * ns);
-    cudaEventElapsedTime(&e->last_ms[0], e->ev[0], e->ev[1]);
-    cudaEventElapsedTime(&e->last_ms[1], e->ev[1], e->ev[2]);
-    cudaEventElapsedTime(&e->last_ms[3], e->ev[0], e->ev[2]);
-    rc = marginalize(e, p);
-    if (rc) return rc;
-    VE_CUDA(cudaEventRecord(e->ev[3], e->stream));
-    if (e->prof.on && (rc = finish_marg(e))) return rc;  // profiling runs are serialised anyway
-    return VE_OK;
-}
-
-int solve_odometry(ve_estimator* e) {
-    if (e->frame_count < e->W) return VE_OK;
-    if (e->solver_flag == 1) {
-        triangulate(e);
-        return optimization(e);
+    // ---- double2vector inputs and the output block
+    vb::FinishPlan& fp = q.fin;
+    Vec3 origin_R0 = hm::R2ypr(e->Rs[0]);
+    Vec3 origin_P0 = e->Ps[0];
+    if (e->failure_occur) {
+        origin_R0 = hm::R2ypr(e->last_R0);
+        origin_P0 = e->last_P0;
+        e->failure_occur = false;
     }
+    fp.origin_ypr[0] = origin_R0.x; fp.origin_ypr[1] = origin_R0.y; fp.origin_ypr[2] = origin_R0.z;
+    fp.origin_P0[0] = origin_P0.x; fp.origin_P0[1] = origin_P0.y; fp.origin_P0[2] = origin_P0.z;
+    std::memcpy(fp.Rs0, e->Rs[0].m, sizeof(fp.Rs0));
+    const size_t out_doubles = vb::BA_OUT_ST_DOUBLES + 21 * (size_t)F + 13 + L;
+    const size_t obase = b->out_used.fetch_add((out_doubles + 1) & ~(size_t)1);
+    if (obase + out_doubles > b->out_cap) {
+        e->err = "batch output arena exhausted";
+        return VE_ERR_CAPACITY;
+    }
+    e->out_off = obase;
+    e->d2h_bytes = out_doubles * sizeof(double);
+    fp.out = b->d_out + obase;
+    fp.n_kept = 0;
+    fp.x0_out = nullptr;
+    // ---- marginalisation
+    if (mh.run) {
+        int* h_lms = reinterpret_cast<int*>(hb + o_marg);
+        for (size_t k = 0; k < n_lm; k++) {
+            h_lms[k] = mh.lms[k];
+            h_lms[n_lm + k] = mh.col_lm[k];
+        }
+        mp.lms = reinterpret_cast<const int*>(db + o_marg);
+        mp.col_lm = mp.lms + n_lm;
+        const size_t Pm = (size_t)e->nmax + 15 + e->Lmax;
+        mp.Am = e->d_marg.p;
+        mp.bm = mp.Am + Pm * Pm;
+        mp.Araw = mp.bm + Pm;
+        mp.graw = mp.Araw + (size_t)e->nmax * e->nmax;
+        mp.Wglobal = mp.graw + e->nmax + 8;  // (nmax + 15)^2 doubles
+        mp.w_in_global = b->w_in_global;  // fixed at batch creation
+        const int nb = e->prior_buf ^ 1;
+        mp.Aout = e->d_prior[nb].p;  // written with leading dimension n (dense n x n at the front of the buffer)
+        mp.gout = mp.Aout + (size_t)e->nmax * e->nmax;
+        mp.cout = mp.gout + e->nmax;
+        fp.n_kept = (int)mh.kept.size();
+        for (int k = 0; k < fp.n_kept; k++) {
+            fp.kept_type[k] = mh.kept[k].type;
+            fp.kept_index[k] = mh.kept[k].index;
+        }
+        fp.x0_out = mp.cout + 1;
+        q.mp = mp;
+        q.do_marg = 1;
+        e->fr_marg = true;
+        e->marg_Araw = mp.Araw;
+        e->marg_graw = mp.graw;
+        e->marg_n = mp.n;
+        // the new prior replaces the old one for every later frame
+        e->prior_blocks = mh.shifted;
+        e->prior_n = mp.n;
+        e->prior_buf = nb;
+        e->has_prior = true;
+    }
+    q.active = 1;
+    e->fr_L = L;
+    e->last_landmarks = L;
+    e->last_visual = M;
     return VE_OK;
 }
 
@@ -886,7 +923,7 @@ void slide_window_old(ve_estimator* e) {
         remove_back(e);
 }
 
-int slide_window(ve_estimator* e) {
+void slide_window(ve_estimator* e) {
     const int W = e->W;
     if (e->marginalization_flag == 0) {
         e->back_R0 = e->Rs[0];
@@ -914,8 +951,7 @@ int slide_window(ve_estimator* e) {
             e->Headers[W] = e->Headers[W - 1];
             e->Ps[W] = e->Ps[W - 1]; e->Vs[W] = e->Vs[W - 1]; e->Rs[W] = e->Rs[W - 1];
             e->Bas[W] = e->Bas[W - 1]; e->Bgs[W] = e->Bgs[W - 1];
-            const int rc = init_slot(e, W, e->acc_0, e->gyr_0, e->Bas[W], e->Bgs[W]);
-            if (rc) return rc;
+            init_slot(e, W, e->acc_0, e->gyr_0, e->Bas[W], e->Bgs[W]);
             e->dt_buf[W].clear(); e->acc_buf[W].clear(); e->gyr_buf[W].clear();
             slide_window_old(e);
         }
@@ -927,17 +963,14 @@ int slide_window(ve_estimator* e) {
             e->gyr_buf[fc - 1].push_back(e->gyr_buf[fc][i]);
             e->sum_dt[fc - 1] += e->dt_buf[fc][i];
         }
-        int rc = flush_frame(e, fc - 1);  // pre_integrations[frame_count - 1]->push_back(...)
-        if (rc) return rc;
+        flush_frame(e, fc - 1);  // pre_integrations[frame_count - 1]->push_back(...)
         e->Headers[fc - 1] = e->Headers[fc];
         e->Ps[fc - 1] = e->Ps[fc]; e->Vs[fc - 1] = e->Vs[fc]; e->Rs[fc - 1] = e->Rs[fc];
         e->Bas[fc - 1] = e->Bas[fc]; e->Bgs[fc - 1] = e->Bgs[fc];
-        rc = init_slot(e, W, e->acc_0, e->gyr_0, e->Bas[W], e->Bgs[W]);
-        if (rc) return rc;
+        init_slot(e, W, e->acc_0, e->gyr_0, e->Bas[W], e->Bgs[W]);
         e->dt_buf[W].clear(); e->acc_buf[W].clear(); e->gyr_buf[W].clear();
         remove_front(e, fc);
     }
-    return VE_OK;
 }
 
 void remove_failures(ve_estimator* e) {
@@ -945,39 +978,228 @@ void remove_failures(ve_estimator* e) {
                      e->feature.end());
 }
 
-}  // namespace
+// Estimator::processImage up to the point where the window is handed to the solver (estimator.cpp:120-217).
+int prepare_frame(ve_estimator* e, int n, const int* ids, const double* xyz_uv_vel, double stamp) {
+    e->h2d_bytes = e->d2h_bytes = 0;
+    e->stage = STAGE_DONE;
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ids[a] < ids[b]; });
+    e->marginalization_flag = add_feature_check_parallax(e, n, order.data(), ids, xyz_uv_vel, e->td) ? 0 : 1;
+    e->Headers[e->frame_count] = stamp;
+    const int W = e->W;
+    bool solve = false;
+    if (e->solver_flag == 0) {
+        if (e->frame_count == W) {
+            if (initial_from_seed(e)) {
+                e->solver_flag = 1;
+                e->stage = STAGE_INIT_SOLVE;
+                solve = true;
+            } else
+                slide_window(e);
+        } else
+            e->frame_count++;
+    } else {
+        e->stage = STAGE_RUN_SOLVE;
+        solve = true;
+    }
+    if (solve) triangulate(e);  // solveOdometry (estimator.cpp:473-484)
+    const int rc = stage_frame(e, solve);
+    if (rc) e->stage = STAGE_DONE;
+    return rc;
+}
 
-extern "C" {
+// The rest of processImage once the solve's results are on the host.
+void finish_frame(ve_estimator* e) {
+    if (e->stage == STAGE_DONE) return;
+    const int W = e->W;
+    unpack_results(e, e->batch->h_out + e->out_off);
+    e->n_solves++;
+    if (e->stage == STAGE_RUN_SOLVE && failure_detection(e)) {
+        e->failure_occur = true;
+        clear_state(e);
+        set_parameter(e);
+        e->n_reboots++;
+        e->stage = STAGE_DONE;
+        return;
+    }
+    slide_window(e);
+    remove_failures(e);
+    e->last_R = e->Rs[W]; e->last_P = e->Ps[W]; e->last_R0 = e->Rs[0]; e->last_P0 = e->Ps[0];
+    e->stage = STAGE_DONE;
+}
 
-int ve_create(const ve_config* cfg, ve_estimator** out) {
-    if (!cfg || !out) return VE_ERR_INVALID;
-    *out = nullptr;
+struct FrameMsg {
+    int active, n;
+    const int* ids;
+    const double* obs;
+    double stamp;
+};
+
+#define VB_CUDA(call)                                                        \
+    do {                                                                     \
+        cudaError_t e_ = (call);                                             \
+        if (e_ != cudaSuccess) {                                             \
+            b->err = std::string(#call) + ": " + cudaGetErrorString(e_);     \
+            return VE_ERR_CUDA;                                              \
+        }                                                                    \
+    } while (0)
+
+// One frame of the batch: members with a message take part, the others idle.
+int batch_process(ve_batch* b, const FrameMsg* msgs, int* status_out) {
+    VB_CUDA(cudaSetDevice(b->cfg.device));
+    const int S = b->S;
+    b->in_used.store(0);
+    b->out_used.store(0);
+    b->last_launches = 0;
+    b->pool->run(S, [&](int k) {
+        ve_estimator* e = b->members[k];
+        vb::BaSeq& q = b->h_seq[k];
+        q.active = q.do_marg = q.n_jobs = 0;
+        q.sqrt_mask = 0;
+        e->status = VE_OK;
+        e->stage = STAGE_DONE;
+        if (msgs[k].active) {
+            e->status = prepare_frame(e, msgs[k].n, msgs[k].ids, msgs[k].obs, msgs[k].stamp);
+            if (e->status != VE_OK) q.active = q.do_marg = 0;
+        }
+    });
+    vb::BatchShape sh{};
+    sh.S = S;
+    sh.W = b->cfg.window_size;
+    sh.D = b->members[0]->D - (b->cfg.estimate_extrinsic ? 0 : 6) - (b->cfg.estimate_td ? 0 : 1);
+    sh.max_iterations = b->cfg.num_iterations;
+    sh.w_in_global = b->w_in_global;
+    for (int k = 0; k < S; k++) {
+        const vb::BaSeq& q = b->h_seq[k];
+        if (q.n_jobs) sh.any_jobs = 1;
+        if (!q.active) continue;
+        sh.any_active = 1;
+        sh.max_L = std::max(sh.max_L, q.p.dims.L);
+        if (q.do_marg) {
+            sh.any_marg = 1;
+            sh.max_n_lm = std::max(sh.max_n_lm, q.mp.n_lm);
+            sh.max_md = std::max(sh.max_md, q.mp.m_dense);
+            sh.max_n = std::max(sh.max_n, q.mp.n);
+            sh.max_P = std::max(sh.max_P, q.mp.P);
+        }
+    }
+    int rc = VE_OK;
+    if (sh.any_jobs || sh.any_active) {
+        VB_CUDA(cudaMemcpyAsync(b->d_seq, b->h_seq, sizeof(vb::BaSeq) * S, cudaMemcpyHostToDevice, b->stream));
+        const size_t in_bytes = std::min(b->in_used.load(), b->in_cap);
+        if (in_bytes) VB_CUDA(cudaMemcpyAsync(b->d_in, b->h_in, in_bytes, cudaMemcpyHostToDevice, b->stream));
+        VB_CUDA(cudaEventRecord(b->ev[0], b->stream));
+        vb::launch_preint_jobs(b->d_seq, sh, b->stream, &b->last_launches, &b->prof);
+        VB_CUDA(cudaEventRecord(b->ev[1], b->stream));
+        vb::launch_ba_solve(b->d_seq, sh, b->stream, &b->last_launches, &b->prof);
+        VB_CUDA(cudaEventRecord(b->ev[2], b->stream));
+        if (sh.any_active) {  // results travel on the copy stream while the marginalisation already runs
+            VB_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev[2], 0));
+            const size_t out_doubles = std::min(b->out_used.load(), b->out_cap);
+            VB_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(double) * out_doubles, cudaMemcpyDeviceToHost, b->copy_stream));
+            VB_CUDA(cudaEventRecord(b->ev[4], b->copy_stream));
+        }
+        VB_CUDA(cudaEventRecord(b->ev[5], b->stream));
+        vb::launch_marginalize(b->d_seq, sh, b->stream, &b->last_launches, &b->prof);
+        VB_CUDA(cudaEventRecord(b->ev[3], b->stream));
+        VB_CUDA(cudaGetLastError());
+        b->marg_timing_valid = sh.any_marg != 0;
+        if (sh.any_active) {
+            VB_CUDA(cudaEventSynchronize(b->ev[4]));
+            cudaEventElapsedTime(&b->last_ms[0], b->ev[0], b->ev[1]);
+            cudaEventElapsedTime(&b->last_ms[1], b->ev[1], b->ev[2]);
+            cudaEventElapsedTime(&b->last_ms[3], b->ev[0], b->ev[2]);
+        } else {
+            // jobs only: the input arena must not be rewritten before the copy has been consumed
+            VB_CUDA(cudaEventSynchronize(b->ev[0]));
+            b->last_ms[0] = b->last_ms[1] = b->last_ms[3] = 0;
+        }
+        b->last_ms[2] = 0;
+    } else {
+        b->last_ms[0] = b->last_ms[1] = b->last_ms[2] = b->last_ms[3] = 0;
+        b->marg_timing_valid = false;
+    }
+    b->pool->run(S, [&](int k) { finish_frame(b->members[k]); });
+    for (int k = 0; k < S; k++) {
+        if (status_out) status_out[k] = b->members[k]->status;
+        if (b->members[k]->status != VE_OK && rc == VE_OK) {
+            rc = b->members[k]->status;
+            b->err = "member " + std::to_string(k) + ": " + b->members[k]->err;
+        }
+    }
+    return rc;
+}
+
+void destroy_member(ve_estimator* e) {
+    if (!e) return;
+    e->d_preint.release(); e->d_states1.release();
+    for (int k = 0; k < 2; k++) { e->d_acc[k].release(); e->d_prior[k].release(); }
+    e->d_S.release(); e->d_Spk.release(); e->d_Hfull.release(); e->d_gred.release(); e->d_vec.release();
+    e->d_work.release(); e->d_marg.release();
+    delete e;
+}
+
+int config_valid(const ve_config* cfg) {
     if (cfg->window_size < 3 || cfg->window_size + 1 > vb::BA_MAX_FRAMES || cfg->window_size + 1 > vb::BA_MAX_OBS_PER_LM ||
-        cfg->max_features < 8 || cfg->num_iterations < 1 || cfg->estimate_extrinsic > 1)
-        return VE_ERR_INVALID;
+        cfg->max_features < 8 || cfg->num_iterations < 1 || cfg->estimate_extrinsic > 1 || cfg->estimate_extrinsic < 0)
+        return 0;
     // work arrays of the single-CTA solvers: prior of 6 W + 9 + 6 + 1 <= 160 parameters, reduced system of
     // 15 (W + 1) + 7 <= 352 columns, i.e. WINDOW_SIZE <= 22 (the reference ships 10; above 13 the reduced systems
     // move from shared to global memory)
-    if (6 * cfg->window_size + 16 > 160 || 15 * (cfg->window_size + 1) + 7 > 352) return VE_ERR_INVALID;
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) return VE_ERR_NO_DEVICE;
+    if (6 * cfg->window_size + 16 > 160 || 15 * (cfg->window_size + 1) + 7 > 352) return 0;
+    return 1;
+}
+
+ve_estimator* create_member(ve_batch* b, int k) {
     ve_estimator* e = new ve_estimator();
-    e->cfg = *cfg;
-    e->W = cfg->window_size;
+    e->cfg = b->cfg;
+    e->batch = b;
+    e->member = k;
+    e->W = b->cfg.window_size;
     const int W = e->W, F = W + 1;
     e->Ps.resize(F); e->Vs.resize(F); e->Bas.resize(F); e->Bgs.resize(F); e->Rs.resize(F);
     e->Headers.assign(F, 0.0);
     e->dt_buf.resize(F); e->acc_buf.resize(F); e->gyr_buf.resize(F);
     e->slot_of.resize(F); e->slot_valid.assign(F, false); e->flushed.assign(F, 0); e->sum_dt.assign(F, 0.0);
     e->lin_acc.resize(F); e->lin_gyr.resize(F); e->sqrt_dirty.assign(F, true);
-    e->Lmax = cfg->max_features;
-    e->Mmax = cfg->max_features * W;
+    e->Lmax = b->cfg.max_features;
+    e->Mmax = b->cfg.max_features * W;
     e->D = 15 * F + 6 + 1;
     e->nmax = 6 * F + 9 * 2 + 6 + 1;
     clear_state(e);
     set_parameter(e);
+    const size_t Pm = (size_t)e->nmax + 15 + e->Lmax;
+    bool ok = e->d_preint.alloc(F) == cudaSuccess && e->d_states1.alloc(states_doubles(e, e->Lmax)) == cudaSuccess;
+    for (int k2 = 0; k2 < 2 && ok; k2++)
+        ok = e->d_acc[k2].alloc(acc_doubles(e)) == cudaSuccess &&
+             e->d_prior[k2].alloc((size_t)e->nmax * e->nmax + e->nmax + 1 + 9 * vb::BA_MAX_PRIOR_BLOCKS) == cudaSuccess;
+    ok = ok && e->d_S.alloc((size_t)e->D * e->D) == cudaSuccess && e->d_Spk.alloc((size_t)e->D * (e->D + 1) / 2) == cudaSuccess &&
+         e->d_Hfull.alloc((size_t)e->D * e->D) == cudaSuccess && e->d_gred.alloc(e->D) == cudaSuccess &&
+         e->d_vec.alloc(4 * ((size_t)e->D + e->Lmax)) == cudaSuccess && e->d_work.alloc(vb::ba_work_doubles(e->D, e->Lmax)) == cudaSuccess &&
+         e->d_marg.alloc(Pm * Pm + Pm + (size_t)e->nmax * e->nmax + e->nmax + 8 + ((size_t)e->nmax + 15) * (e->nmax + 15)) == cudaSuccess;
+    if (!ok) {
+        destroy_member(e);
+        return nullptr;
+    }
+    return e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ve_batch_create(const ve_config* cfg, int n, ve_batch** out) {
+    if (!cfg || !out || n < 1 || n > 4096) return VE_ERR_INVALID;
+    *out = nullptr;
+    if (!config_valid(cfg)) return VE_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) return VE_ERR_NO_DEVICE;
+    ve_batch* b = new ve_batch();
+    b->cfg = *cfg;
+    b->S = n;
     auto fail = [&](int code) {
-        ve_destroy(e);
+        ve_batch_destroy(b);
         return code;
     };
 #define VE_TRY(call)                                          \
@@ -985,62 +1207,137 @@ int ve_create(const ve_config* cfg, ve_estimator** out) {
         if ((call) != cudaSuccess) return fail(VE_ERR_CUDA);  \
     } while (0)
     VE_TRY(cudaSetDevice(cfg->device));
-    VE_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    for (auto& ev : e->ev) VE_TRY(cudaEventCreate(&ev));
-    VE_TRY(e->d_preint.alloc(F));
-    VE_TRY(e->d_samples.alloc(8 * 7 * 512));
-    VE_TRY(e->d_which.alloc(F));
-    const size_t Pm = (size_t)e->nmax + 15 + e->Lmax;
-    for (int b = 0; b < 2; b++) {
-        VE_TRY(e->d_states[b].alloc(states_doubles(e)));
-        VE_TRY(e->d_acc[b].alloc(acc_doubles(e)));
-        VE_TRY(e->d_prior[b].alloc((size_t)e->nmax * e->nmax + e->nmax + 1 + 9 * 64));
-        VE_TRY(e->d_prior_i[b].alloc(192));
+    VE_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    VE_TRY(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+    for (auto& ev : b->ev) VE_TRY(cudaEventCreate(&ev));
+    for (int k = 0; k < n; k++) {
+        ve_estimator* e = create_member(b, k);
+        if (!e) return fail(VE_ERR_CUDA);
+        b->members.push_back(e);
     }
-    VE_TRY(e->d_ints.alloc((size_t)2 * e->Lmax + 1 + e->Mmax + W));
-    VE_TRY(e->d_obs.alloc(6 * (size_t)e->Lmax + 6 * (size_t)e->Mmax));
-    VE_TRY(e->d_S.alloc((size_t)e->D * e->D));
-    VE_TRY(e->d_Spk.alloc((size_t)e->D * (e->D + 1) / 2));
-    VE_TRY(e->d_Hfull.alloc((size_t)e->D * e->D));
-    VE_TRY(e->d_gred.alloc(e->D));
-    VE_TRY(e->d_vec.alloc(4 * ((size_t)e->D + e->Lmax)));
-    VE_TRY(e->d_work.alloc(vb::ba_work_doubles(e->D, e->Lmax)));
-    VE_TRY(e->d_st.alloc(1));
-    VE_TRY(e->d_marg.alloc(Pm * Pm + Pm + (size_t)e->nmax * e->nmax + e->nmax + ((size_t)e->nmax + 15) * (e->nmax + 15)));
-    VE_TRY(e->d_marg_i.alloc(2 * (size_t)e->Lmax));
-    VE_TRY(cudaHostAlloc(&e->h_states, sizeof(double) * 3 * states_doubles(e), cudaHostAllocDefault));
-    VE_TRY(cudaHostAlloc(&e->h_obs, sizeof(double) * (6 * (size_t)e->Lmax + 6 * (size_t)e->Mmax), cudaHostAllocDefault));
-    VE_TRY(cudaHostAlloc(&e->h_ints, sizeof(int) * ((size_t)2 * e->Lmax + 1 + e->Mmax + W), cudaHostAllocDefault));
-    VE_TRY(cudaHostAlloc(&e->h_samples, sizeof(double) * 8 * 7 * 512, cudaHostAllocDefault));
-    VE_TRY(cudaHostAlloc(&e->h_preint, sizeof(vb::PreInt), cudaHostAllocDefault));
-    VE_TRY(cudaHostAlloc(&e->h_st, sizeof(vb::SolverState), cudaHostAllocDefault));
-    VE_TRY(cudaHostAlloc(&e->h_prior, sizeof(double) * 9 * 64, cudaHostAllocDefault));
-    VE_TRY(cudaHostAlloc(&e->h_prior_i, sizeof(int) * 192, cudaHostAllocDefault));
-    VE_TRY(cudaHostAlloc(&e->h_marg_i, sizeof(int) * std::max<size_t>(2 * (size_t)e->Lmax, 64), cudaHostAllocDefault));
-    VE_TRY(cudaHostAlloc(&e->h_which, sizeof(int) * 64, cudaHostAllocDefault));
-    VE_TRY(cudaHostAlloc(&e->h_marg_out, sizeof(double) * ((size_t)e->nmax * e->nmax + e->nmax), cudaHostAllocDefault));
+    const ve_estimator* e0 = b->members[0];
+    const int W = cfg->window_size, F = W + 1;
+    // input block of one member at full capacity: jobs + samples + tables + states + marginalisation lists
+    const size_t per_in = align16(sizeof(vb::PreintJob) * 4 * F) + align16(sizeof(double) * 7 * 4096) +
+                          align16(sizeof(int) * ((size_t)2 * e0->Lmax + 1 + e0->Mmax + W)) +
+                          align16(sizeof(double) * (6 * (size_t)e0->Lmax + 6 * (size_t)e0->Mmax)) +
+                          align16(sizeof(double) * states_doubles(e0, e0->Lmax)) + align16(sizeof(int) * 2 * (size_t)e0->Lmax);
+    // a batch rarely has every member at capacity: size the arenas for the full capacity of 8 members or a quarter of
+    // the batch, whichever is larger (exhaustion is reported as VE_ERR_CAPACITY, never overrun)
+    const size_t members_at_cap = std::max<size_t>(std::min<size_t>(n, 8), (size_t)(n + 3) / 4);
+    b->in_cap = per_in * members_at_cap;
+    b->out_cap = ((size_t)vb::BA_OUT_ST_DOUBLES + 21 * F + 13 + e0->Lmax + 1) * members_at_cap +
+                 ((size_t)vb::BA_OUT_ST_DOUBLES + 21 * F + 13 + 256) * (size_t)n;
+    VE_TRY(cudaMalloc(&b->d_seq, sizeof(vb::BaSeq) * n));
+    VE_TRY(cudaHostAlloc(&b->h_seq, sizeof(vb::BaSeq) * n, cudaHostAllocDefault));
+    std::memset(b->h_seq, 0, sizeof(vb::BaSeq) * n);
+    VE_TRY(cudaMalloc(&b->d_in, b->in_cap));
+    VE_TRY(cudaHostAlloc(&b->h_in, b->in_cap, cudaHostAllocDefault));
+    VE_TRY(cudaMalloc(&b->d_out, sizeof(double) * b->out_cap));
+    VE_TRY(cudaHostAlloc(&b->h_out, sizeof(double) * b->out_cap, cudaHostAllocDefault));
 #undef VE_TRY
-    *out = e;
+    b->w_in_global = vb::marg_w_in_global(15, e0->nmax);
+    const int hw = (int)std::thread::hardware_concurrency();
+    const int workers = std::max(0, std::min(std::min(n - 1, hw - 2), 23));
+    b->pool = new Pool(workers);
+    *out = b;
+    return VE_OK;
+}
+
+void ve_batch_destroy(ve_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->cfg.device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
+    delete b->pool;
+    for (auto* e : b->members) destroy_member(e);
+    cudaFree(b->d_seq); cudaFree(b->d_in); cudaFree(b->d_out);
+    cudaFreeHost(b->h_seq); cudaFreeHost(b->h_in); cudaFreeHost(b->h_out);
+    for (auto& ev : b->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+    delete b;
+}
+
+int ve_batch_size(const ve_batch* b) { return b ? b->S : VE_ERR_INVALID; }
+
+ve_estimator* ve_batch_member(ve_batch* b, int k) { return (b && k >= 0 && k < b->S) ? b->members[k] : nullptr; }
+
+const char* ve_batch_last_error(const ve_batch* b) { return b ? b->err.c_str() : "null batch"; }
+
+int ve_batch_process_image(ve_batch* b, const int* active, const int* n, const int* const* ids, const double* const* xyz_uv_vel,
+                           const double* stamps, int* status) {
+    if (!b || !n || !ids || !xyz_uv_vel || !stamps) return VE_ERR_INVALID;
+    std::vector<FrameMsg> msgs(b->S);
+    for (int k = 0; k < b->S; k++) {
+        msgs[k].active = active ? (active[k] != 0) : 1;
+        msgs[k].n = n[k];
+        msgs[k].ids = ids[k];
+        msgs[k].obs = xyz_uv_vel[k];
+        msgs[k].stamp = stamps[k];
+        if (msgs[k].active && (n[k] < 0 || (n[k] && (!ids[k] || !xyz_uv_vel[k])))) return VE_ERR_INVALID;
+    }
+    return batch_process(b, msgs.data(), status);
+}
+
+int ve_batch_last_timing(const ve_batch* cb, float* ms4, int* launches) {
+    if (!cb) return VE_ERR_INVALID;
+    ve_batch* b = const_cast<ve_batch*>(cb);
+    if (ms4) {
+        if (b->marg_timing_valid) {
+            cudaSetDevice(b->cfg.device);
+            if (cudaEventSynchronize(b->ev[3]) != cudaSuccess) return VE_ERR_CUDA;
+            cudaEventElapsedTime(&b->last_ms[2], b->ev[5], b->ev[3]);
+        }
+        std::memcpy(ms4, b->last_ms, sizeof(b->last_ms));
+    }
+    if (launches) *launches = b->last_launches;
+    return VE_OK;
+}
+
+int ve_batch_set_profile(ve_batch* b, int on) {
+    if (!b) return VE_ERR_INVALID;
+    b->prof.enable(on != 0);
+    return VE_OK;
+}
+
+int ve_batch_kernel_times(const ve_batch* b, double* ms8, int* count8) {
+    if (!b) return VE_ERR_INVALID;
+    for (int k = 0; k < 8; k++) {
+        if (ms8) ms8[k] = b->prof.ms[k];
+        if (count8) count8[k] = b->prof.count[k];
+    }
+    return VE_OK;
+}
+
+int ve_batch_sync(ve_batch* b) {
+    if (!b) return VE_ERR_INVALID;
+    VB_CUDA(cudaSetDevice(b->cfg.device));
+    VB_CUDA(cudaStreamSynchronize(b->stream));
+    return VE_OK;
+}
+
+int ve_create(const ve_config* cfg, ve_estimator** out) {
+    if (!cfg || !out) return VE_ERR_INVALID;
+    *out = nullptr;
+    ve_batch* b = nullptr;
+    const int rc = ve_batch_create(cfg, 1, &b);
+    if (rc) return rc;
+    b->standalone = true;
+    *out = b->members[0];
     return VE_OK;
 }
 
 void ve_destroy(ve_estimator* e) {
     if (!e) return;
-    cudaSetDevice(e->cfg.device);
-    if (e->stream) cudaStreamSynchronize(e->stream);
-    e->d_preint.release(); e->d_samples.release(); e->d_which.release();
-    for (int b = 0; b < 2; b++) { e->d_states[b].release(); e->d_acc[b].release(); e->d_prior[b].release(); e->d_prior_i[b].release(); }
-    e->d_ints.release(); e->d_obs.release(); e->d_S.release(); e->d_Spk.release(); e->d_Hfull.release(); e->d_gred.release(); e->d_vec.release();
-    e->d_work.release(); e->d_st.release(); e->d_marg.release(); e->d_marg_i.release();
-    cudaFreeHost(e->h_states); cudaFreeHost(e->h_obs); cudaFreeHost(e->h_ints); cudaFreeHost(e->h_samples); cudaFreeHost(e->h_preint);
-    cudaFreeHost(e->h_st); cudaFreeHost(e->h_prior); cudaFreeHost(e->h_prior_i); cudaFreeHost(e->h_marg_i); cudaFreeHost(e->h_which); cudaFreeHost(e->h_marg_out);
-    for (auto& ev : e->ev)
-        if (ev) cudaEventDestroy(ev);
-    if (e->stream) cudaStreamDestroy(e->stream);
-    delete e;
+    if (e->batch && e->batch->standalone) ve_batch_destroy(e->batch);  // members of an explicit batch die with the batch
 }
 
-const char* ve_last_error(const ve_estimator* e) { return e ? e->err.c_str() : "null handle"; }
+const char* ve_last_error(const ve_estimator* e) {
+    if (!e) return "null handle";
+    return e->err.empty() && e->batch ? e->batch->err.c_str() : e->err.c_str();
+}
 
 int ve_clear_state(ve_estimator* e) {
     if (!e) return VE_ERR_INVALID;
@@ -1068,51 +1365,27 @@ int ve_set_seed(ve_estimator* e, int n, const double* rows, const double* ba, co
 
 int ve_process_imu(ve_estimator* e, double dt, const double* acc, const double* gyr) {
     if (!e || !acc || !gyr) return VE_ERR_INVALID;
-    VE_CUDA(cudaSetDevice(e->cfg.device));
-    return process_imu(e, dt, Vec3(acc[0], acc[1], acc[2]), Vec3(gyr[0], gyr[1], gyr[2]));
+    process_imu(e, dt, Vec3(acc[0], acc[1], acc[2]), Vec3(gyr[0], gyr[1], gyr[2]));
+    return VE_OK;
+}
+
+int ve_process_imu_batch(ve_estimator* e, int n, const double* dt, const double* acc, const double* gyr) {
+    if (!e || n < 0 || (n && (!dt || !acc || !gyr))) return VE_ERR_INVALID;
+    for (int i = 0; i < n; i++)
+        process_imu(e, dt[i], Vec3(acc[3 * i], acc[3 * i + 1], acc[3 * i + 2]), Vec3(gyr[3 * i], gyr[3 * i + 1], gyr[3 * i + 2]));
+    return VE_OK;
 }
 
 int ve_process_image(ve_estimator* e, int n, const int* ids, const double* xyz_uv_vel, double stamp) {
     if (!e || n < 0 || (n && (!ids || !xyz_uv_vel))) return VE_ERR_INVALID;
-    VE_CUDA(cudaSetDevice(e->cfg.device));
-    e->last_launches = 0;
-    e->h2d_bytes = e->d2h_bytes = 0;
-    e->last_ms[0] = e->last_ms[1] = e->last_ms[2] = e->last_ms[3] = 0;
-    std::vector<int> order(n);
-    for (int i = 0; i < n; i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ids[a] < ids[b]; });
-    e->marginalization_flag = add_feature_check_parallax(e, n, order.data(), ids, xyz_uv_vel, e->td) ? 0 : 1;
-    e->Headers[e->frame_count] = stamp;
-    int rc = VE_OK;
-    const int W = e->W;
-    if (e->solver_flag == 0) {
-        if (e->frame_count == W) {
-            bool ok = false;
-            if ((rc = initial_from_seed(e, &ok))) return rc;
-            if (ok) {
-                e->solver_flag = 1;
-                if ((rc = solve_odometry(e))) return rc;
-                if ((rc = slide_window(e))) return rc;
-                remove_failures(e);
-                e->last_R = e->Rs[W]; e->last_P = e->Ps[W]; e->last_R0 = e->Rs[0]; e->last_P0 = e->Ps[0];
-            } else if ((rc = slide_window(e)))
-                return rc;
-        } else
-            e->frame_count++;
-    } else {
-        if ((rc = solve_odometry(e))) return rc;
-        if (failure_detection(e)) {
-            e->failure_occur = true;
-            clear_state(e);
-            set_parameter(e);
-            e->n_reboots++;
-            return VE_OK;
-        }
-        if ((rc = slide_window(e))) return rc;
-        remove_failures(e);
-        e->last_R = e->Rs[W]; e->last_P = e->Ps[W]; e->last_R0 = e->Rs[0]; e->last_P0 = e->Ps[0];
+    ve_batch* b = e->batch;
+    if (!b->standalone) {
+        e->err = "ve_process_image on a member of a batch: use ve_batch_process_image";
+        return VE_ERR_INVALID;
     }
-    return VE_OK;
+    e->err.clear();
+    FrameMsg m{1, n, ids, xyz_uv_vel, stamp};
+    return batch_process(b, &m, nullptr);
 }
 
 int ve_get_states(const ve_estimator* e, double* out, double* td) {
@@ -1126,6 +1399,13 @@ int ve_get_states(const ve_estimator* e, double* out, double* td) {
         o[13] = e->Bgs[i].x; o[14] = e->Bgs[i].y; o[15] = e->Bgs[i].z;
     }
     if (td) *td = e->td;
+    return VE_OK;
+}
+
+int ve_get_extrinsic(const ve_estimator* e, double* tic3, double* ric9) {
+    if (!e) return VE_ERR_INVALID;
+    if (tic3) { tic3[0] = e->tic.x; tic3[1] = e->tic.y; tic3[2] = e->tic.z; }
+    if (ric9) std::memcpy(ric9, e->ric.m, 9 * sizeof(double));
     return VE_OK;
 }
 
@@ -1145,12 +1425,15 @@ int ve_info(const ve_estimator* e, int* o, double* costs2) {
 int ve_get_prior(const ve_estimator* ce, int cap, double* A, double* b, int* nblocks, int* blocks4) {
     if (!ce) return VE_ERR_INVALID;
     ve_estimator* e = const_cast<ve_estimator*>(ce);
-    if (!e->has_prior) return 0;
-    if (finish_marg(e)) return VE_ERR_CUDA;
+    if (!e->has_prior || !e->marg_Araw) return 0;
     const int n = e->prior_n;
     if (n > cap) return -n;
-    std::memcpy(A, e->prior_raw_A.data(), sizeof(double) * (size_t)n * n);
-    std::memcpy(b, e->prior_raw_b.data(), sizeof(double) * n);
+    // the marginalisation that produced the prior may still be running: wait for the batch stream, then read the
+    // un-floored Schur complement straight from device memory
+    VE_CUDA(cudaSetDevice(e->cfg.device));
+    VE_CUDA(cudaStreamSynchronize(e->batch->stream));
+    VE_CUDA(cudaMemcpy(A, e->marg_Araw, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost));
+    VE_CUDA(cudaMemcpy(b, e->marg_graw, sizeof(double) * n, cudaMemcpyDeviceToHost));
     if (nblocks) *nblocks = (int)e->prior_blocks.size();
     if (blocks4)
         for (size_t k = 0; k < e->prior_blocks.size(); k++) {
@@ -1162,30 +1445,9 @@ int ve_get_prior(const ve_estimator* ce, int cap, double* A, double* b, int* nbl
     return n;
 }
 
-int ve_process_imu_batch(ve_estimator* e, int n, const double* dt, const double* acc, const double* gyr) {
-    if (!e || n < 0 || (n && (!dt || !acc || !gyr))) return VE_ERR_INVALID;
-    VE_CUDA(cudaSetDevice(e->cfg.device));
-    for (int i = 0; i < n; i++) {
-        const int rc = process_imu(e, dt[i], Vec3(acc[3 * i], acc[3 * i + 1], acc[3 * i + 2]), Vec3(gyr[3 * i], gyr[3 * i + 1], gyr[3 * i + 2]));
-        if (rc) return rc;
-    }
-    return VE_OK;
-}
+int ve_set_profile(ve_estimator* e, int on) { return e ? ve_batch_set_profile(e->batch, on) : VE_ERR_INVALID; }
 
-int ve_set_profile(ve_estimator* e, int on) {
-    if (!e) return VE_ERR_INVALID;
-    e->prof.enable(on != 0);
-    return VE_OK;
-}
-
-int ve_kernel_times(const ve_estimator* e, double* ms8, int* count8) {
-    if (!e) return VE_ERR_INVALID;
-    for (int k = 0; k < 8; k++) {
-        if (ms8) ms8[k] = e->prof.ms[k];
-        if (count8) count8[k] = e->prof.count[k];
-    }
-    return VE_OK;
-}
+int ve_kernel_times(const ve_estimator* e, double* ms8, int* count8) { return e ? ve_batch_kernel_times(e->batch, ms8, count8) : VE_ERR_INVALID; }
 
 int ve_last_traffic(const ve_estimator* e, double* h2d_bytes, double* d2h_bytes) {
     if (!e) return VE_ERR_INVALID;
@@ -1194,27 +1456,124 @@ int ve_last_traffic(const ve_estimator* e, double* h2d_bytes, double* d2h_bytes)
     return VE_OK;
 }
 
-int ve_solver_debug(const ve_estimator* ce, double* out13) {  // 18 doubles
-    if (!ce || !out13) return VE_ERR_INVALID;
+int ve_solver_debug(const ve_estimator* ce, double* out18) {
+    if (!ce || !out18) return VE_ERR_INVALID;
     ve_estimator* e = const_cast<ve_estimator*>(ce);
-    if (finish_marg(e)) return VE_ERR_CUDA;
-    out13[0] = e->last_state.retries;
-    out13[1] = e->last_state.mu;
-    out13[2] = e->last_state.radius;
-    for (int k = 0; k < 8; k++) out13[3 + k] = (double)e->last_state.clk[k];
-    out13[11] = e->marg_sweeps[0];
-    out13[12] = e->marg_sweeps[1];
-    for (int k = 0; k < 5; k++) out13[13 + k] = e->marg_sweeps[2 + k];
+    out18[0] = e->last_state.retries;
+    out18[1] = e->last_state.mu;
+    out18[2] = e->last_state.radius;
+    for (int k = 0; k < 8; k++) out18[3 + k] = (double)e->last_state.clk[k];
+    double sweeps[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (e->has_prior && e->marg_graw) {
+        VE_CUDA(cudaSetDevice(e->cfg.device));
+        VE_CUDA(cudaStreamSynchronize(e->batch->stream));
+        VE_CUDA(cudaMemcpy(sweeps, e->marg_graw + e->marg_n, sizeof(sweeps), cudaMemcpyDeviceToHost));
+    }
+    out18[11] = sweeps[0];
+    out18[12] = sweeps[1];
+    for (int k = 0; k < 5; k++) out18[13 + k] = sweeps[2 + k];
     return VE_OK;
 }
 
-int ve_last_timing(const ve_estimator* ce, float* ms4, int* launches) {
-    if (!ce) return VE_ERR_INVALID;
-    ve_estimator* e = const_cast<ve_estimator*>(ce);
-    if (ms4 && finish_marg(e)) return VE_ERR_CUDA;
-    if (ms4) std::memcpy(ms4, e->last_ms, sizeof(e->last_ms));
-    if (launches) *launches = e->last_launches;
-    return VE_OK;
+int ve_last_timing(const ve_estimator* e, float* ms4, int* launches) { return e ? ve_batch_last_timing(e->batch, ms4, launches) : VE_ERR_INVALID; }
+
+// ---- single-factor test entries: the device code of the solve evaluated on caller-supplied blocks -------------------
+int ve_debug_projection_factor(const double* params23, const double* data12, int use_td, double focal_length, double tr, double row,
+                               int robust, double* out43) {
+    if (!params23 || !data12 || !out43) return VE_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return VE_ERR_NO_DEVICE;
+    double* d = nullptr;
+    if (cudaMalloc(&d, sizeof(double) * (23 + 12 + 43)) != cudaSuccess) return VE_ERR_CUDA;
+    vb::BaDims dm{};
+    dm.est_td = use_td ? 1 : 0;
+    dm.sqrt_info_vis = focal_length / 1.5;
+    dm.tr_over_row = tr / row;
+    dm.half_row = row / 2;
+    int rc = VE_OK;
+    if (cudaMemcpy(d, params23, sizeof(double) * 23, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d + 23, data12, sizeof(double) * 12, cudaMemcpyHostToDevice) != cudaSuccess)
+        rc = VE_ERR_CUDA;
+    if (rc == VE_OK) {
+        vb::launch_debug_visual(dm, d, d + 23, robust, d + 35, nullptr);
+        if (cudaMemcpy(out43, d + 35, sizeof(double) * 43, cudaMemcpyDeviceToHost) != cudaSuccess) rc = VE_ERR_CUDA;
+    }
+    cudaFree(d);
+    return rc;
+}
+
+int ve_debug_imu_factor(const double* noise4, double g_norm, const double* ba, const double* bg, int n, const double* dt,
+                        const double* acc, const double* gyr, const double* params32, double* out_preint, double* out_factor) {
+    if (!noise4 || !ba || !bg || n < 1 || !dt || !acc || !gyr) return VE_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return VE_ERR_NO_DEVICE;
+    // sample 0 seeds the IntegrationBase (acc_0 / gyr_0), samples 1..n-1 are pushed with dt[k]
+    vb::BaSeq q{};
+    vb::PreintJob jobs[2]{};
+    jobs[0].type = 0;
+    for (int c = 0; c < 3; c++) {
+        jobs[0].acc0[c] = acc[c];
+        jobs[0].gyr0[c] = gyr[c];
+        jobs[0].ba[c] = ba[c];
+        jobs[0].bg[c] = bg[c];
+    }
+    jobs[1].type = 1;
+    jobs[1].n = n - 1;
+    std::vector<double> rec(7 * (size_t)std::max(n - 1, 1));
+    for (int k = 1; k < n; k++) {
+        double* r = &rec[7 * (size_t)(k - 1)];
+        r[0] = dt[k];
+        for (int c = 0; c < 3; c++) {
+            r[1 + c] = acc[3 * k + c];
+            r[4 + c] = gyr[3 * k + c];
+        }
+    }
+    unsigned char* d = nullptr;
+    const size_t o_seq = 0, o_jobs = align16(sizeof(vb::BaSeq)), o_rec = o_jobs + align16(sizeof(jobs)),
+                 o_pre = o_rec + align16(rec.size() * sizeof(double)), o_prm = o_pre + align16(sizeof(vb::PreInt)),
+                 o_out = o_prm + align16(32 * sizeof(double)), total = o_out + align16(465 * sizeof(double));
+    if (cudaMalloc(&d, total) != cudaSuccess) return VE_ERR_CUDA;
+    q.n_jobs = 2;
+    q.sqrt_mask = 1u;
+    q.jobs = reinterpret_cast<const vb::PreintJob*>(d + o_jobs);
+    q.samples = reinterpret_cast<const double*>(d + o_rec);
+    for (int c = 0; c < 4; c++) q.noise[c] = noise4[c];
+    q.p.preint = reinterpret_cast<vb::PreInt*>(d + o_pre);
+    vb::BaDims dm{};
+    dm.G[2] = g_norm;
+    int rc = VE_OK;
+    bool ok = cudaMemcpy(d + o_seq, &q, sizeof(q), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(d + o_jobs, jobs, sizeof(jobs), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(d + o_rec, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok && params32) ok = cudaMemcpy(d + o_prm, params32, 32 * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok) {
+        vb::BatchShape sh{};
+        sh.S = 1;
+        sh.W = 0;
+        sh.any_jobs = 1;
+        vb::launch_preint_jobs(reinterpret_cast<vb::BaSeq*>(d + o_seq), sh, nullptr, nullptr, nullptr);
+        if (params32 && out_factor) {
+            vb::launch_debug_imu(dm, reinterpret_cast<const vb::PreInt*>(d + o_pre), reinterpret_cast<const double*>(d + o_prm),
+                                 reinterpret_cast<double*>(d + o_out), nullptr);
+            ok = cudaMemcpy(out_factor, d + o_out, 465 * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+        }
+        if (ok && out_preint) {
+            vb::PreInt pre;
+            ok = cudaMemcpy(&pre, d + o_pre, sizeof(pre), cudaMemcpyDeviceToHost) == cudaSuccess;
+            if (ok) {  // sum_dt | dp 3 | dq 4 (wxyz) | dv 3 | jac 225 | cov 225 | sqrt_info 225
+                out_preint[0] = pre.sum_dt;
+                std::memcpy(out_preint + 1, pre.dp, 3 * sizeof(double));
+                std::memcpy(out_preint + 4, pre.dq, 4 * sizeof(double));
+                std::memcpy(out_preint + 8, pre.dv, 3 * sizeof(double));
+                std::memcpy(out_preint + 11, pre.jac, 225 * sizeof(double));
+                std::memcpy(out_preint + 236, pre.cov, 225 * sizeof(double));
+                std::memcpy(out_preint + 461, pre.sqrt_info, 225 * sizeof(double));
+            }
+        }
+    }
+    if (!ok || cudaGetLastError() != cudaSuccess) rc = VE_ERR_CUDA;
+    cudaFree(d);
+    return rc;
 }
 
 }  // extern "C"

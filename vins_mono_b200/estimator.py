@@ -50,33 +50,63 @@ def _bind(lib):
     lib.ve_set_profile.argtypes = [C.c_void_p, C.c_int]
     lib.ve_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ve_last_traffic.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.ve_get_extrinsic.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ve_batch_create.argtypes = [C.POINTER(EstimatorConfig), C.c_int, C.POINTER(C.c_void_p)]
+    lib.ve_batch_destroy.argtypes = [C.c_void_p]
+    lib.ve_batch_size.argtypes = [C.c_void_p]
+    lib.ve_batch_member.argtypes = [C.c_void_p, C.c_int]
+    lib.ve_batch_member.restype = C.c_void_p
+    lib.ve_batch_last_error.argtypes = [C.c_void_p]
+    lib.ve_batch_last_error.restype = C.c_char_p
+    lib.ve_batch_process_image.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ve_batch_last_timing.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    lib.ve_batch_set_profile.argtypes = [C.c_void_p, C.c_int]
+    lib.ve_batch_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ve_batch_sync.argtypes = [C.c_void_p]
+    lib.ve_debug_projection_factor.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
+    lib.ve_debug_imu_factor.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
     _bound = True
+
+
+def _make_config(window_size=10, max_features=1000, num_iterations=8, estimate_extrinsic=0, estimate_td=0,
+                 focal_length=460.0, keyframe_parallax=10.0, acc_n=0.08, gyr_n=0.004, acc_w=0.00004, gyr_w=2.0e-6,
+                 g_norm=9.81007, init_depth=5.0, td=0.0, tr=0.0, row=480.0, tic=(0, 0, 0), ric=np.eye(3), device=0):
+    cfg = EstimatorConfig(window_size=window_size, max_features=max_features, num_iterations=num_iterations,
+                          estimate_extrinsic=estimate_extrinsic, estimate_td=estimate_td, focal_length=focal_length,
+                          keyframe_parallax=keyframe_parallax, acc_n=acc_n, gyr_n=gyr_n, acc_w=acc_w, gyr_w=gyr_w,
+                          g_norm=g_norm, init_depth=init_depth, td=td, tr=tr, row=row, device=device)
+    cfg.tic[:] = list(np.asarray(tic, float))
+    cfg.ric[:] = list(np.asarray(ric, float).ravel())
+    return cfg
 
 
 class Estimator:
     """Drop-in for the reference Estimator: processIMU / processImage, then read Ps, Rs, Vs, Bas, Bgs."""
 
-    def __init__(self, window_size=10, max_features=1000, num_iterations=8, estimate_extrinsic=0, estimate_td=0,
-                 focal_length=460.0, keyframe_parallax=10.0, acc_n=0.08, gyr_n=0.004, acc_w=0.00004, gyr_w=2.0e-6,
-                 g_norm=9.81007, init_depth=5.0, td=0.0, tr=0.0, row=480.0, tic=(0, 0, 0), ric=np.eye(3), device=0):
+    def __init__(self, **kw):
         self.lib = load_library()
         _bind(self.lib)
-        cfg = EstimatorConfig(window_size=window_size, max_features=max_features, num_iterations=num_iterations,
-                              estimate_extrinsic=estimate_extrinsic, estimate_td=estimate_td, focal_length=focal_length,
-                              keyframe_parallax=keyframe_parallax, acc_n=acc_n, gyr_n=gyr_n, acc_w=acc_w, gyr_w=gyr_w,
-                              g_norm=g_norm, init_depth=init_depth, td=td, tr=tr, row=row, device=device)
-        cfg.tic[:] = list(np.asarray(tic, float))
-        cfg.ric[:] = list(np.asarray(ric, float).ravel())
-        self.cfg, self.W = cfg, window_size
+        cfg = _make_config(**kw)
+        self.cfg, self.W = cfg, cfg.window_size
         h = C.c_void_p()
         rc = self.lib.ve_create(C.byref(cfg), C.byref(h))
         if rc != 0:
             raise RuntimeError(f"ve_create failed with status {rc} (-2 = no CUDA device; this library has no CPU path)")
         self.h = h
+        self._borrowed = False
+
+    @classmethod
+    def _member(cls, lib, handle, cfg):
+        """Borrowed handle of a batch member (driven and destroyed through its EstimatorBatch)."""
+        self = cls.__new__(cls)
+        self.lib, self.cfg, self.W, self.h, self._borrowed = lib, cfg, cfg.window_size, C.c_void_p(handle), True
+        return self
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.ve_destroy(self.h)
+            if not self._borrowed:
+                self.lib.ve_destroy(self.h)
             self.h = None
 
     __del__ = close
@@ -122,7 +152,7 @@ class Estimator:
         n = self._check(self.lib.ve_get_prior(self.h, cap, _p(A), _p(b), C.byref(nb), _p(blk)))
         return A[: n * n].reshape(n, n).copy(), b[:n].copy(), [tuple(int(v) for v in blk[4 * k:4 * k + 4]) for k in range(nb.value)]
 
-    KERNELS = ["ba_linearize", "ba_schur", "ba_step", "ba_zero", "marg_build", "marg_solve", "preint_push", "sqrt_info"]
+    KERNELS = ["ba_linearize", "ba_schur", "ba_step", "ba_zero", "marg_build", "marg_solve", "preint_jobs", "ba_finish"]
 
     def processIMU_batch(self, dt, acc, gyr):
         dt, acc, gyr = _d(dt), _d(acc), _d(gyr)
@@ -156,3 +186,106 @@ class Estimator:
         ms, k = np.zeros(4, np.float32), C.c_int(0)
         self.lib.ve_last_timing(self.h, _p(ms), C.byref(k))
         return dict(preint_ms=float(ms[0]), solve_ms=float(ms[1]), marg_ms=float(ms[2]), total_ms=float(ms[3]), launches=k.value)
+
+    def extrinsic(self):
+        t, r = np.zeros(3), np.zeros(9)
+        self._check(self.lib.ve_get_extrinsic(self.h, _p(t), _p(r)))
+        return t, r.reshape(3, 3)
+
+
+class EstimatorBatch:
+    """n independent estimators advancing together (include/vinsb200/estimator.h, ve_batch_*): one launch chain per frame
+    for the whole batch.  members[k] is an Estimator mirror for the per-sequence calls (set_seed, processIMU, states ...)."""
+
+    def __init__(self, n, **kw):
+        self.lib = load_library()
+        _bind(self.lib)
+        self.cfg, self.n = _make_config(**kw), n
+        h = C.c_void_p()
+        rc = self.lib.ve_batch_create(C.byref(self.cfg), n, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"ve_batch_create failed with status {rc} (-2 = no CUDA device; this library has no CPU path)")
+        self.h = h
+        self.members = [Estimator._member(self.lib, self.lib.ve_batch_member(h, k), self.cfg) for k in range(n)]
+
+    def close(self):
+        if getattr(self, "h", None):
+            for m in self.members:
+                m.h = None
+            self.lib.ve_batch_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def processImage(self, msgs):
+        """msgs[k] = (ids, xyz_uv_vel, stamp) or None (member k idles this frame).  Returns the per-member status list."""
+        n = self.n
+        active = np.zeros(n, np.int32)
+        cnt = np.zeros(n, np.int32)
+        stamps = np.zeros(n)
+        idp, obp, keep = (C.c_void_p * n)(), (C.c_void_p * n)(), []
+        for k, m in enumerate(msgs):
+            if m is None:
+                continue
+            ids, d = np.ascontiguousarray(m[0], np.int32), _d(m[1])
+            keep += [ids, d]
+            active[k], cnt[k], stamps[k] = 1, len(ids), float(m[2])
+            idp[k], obp[k] = ids.ctypes.data, d.ctypes.data
+        status = np.zeros(n, np.int32)
+        rc = self.lib.ve_batch_process_image(self.h, _p(active), _p(cnt), idp, obp, _p(stamps), _p(status))
+        if rc < 0:
+            raise RuntimeError(f"vinsb200 batch error {rc}: {self.lib.ve_batch_last_error(self.h).decode()}")
+        return status
+
+    def timing(self):
+        ms, k = np.zeros(4, np.float32), C.c_int(0)
+        self.lib.ve_batch_last_timing(self.h, _p(ms), C.byref(k))
+        return dict(preint_ms=float(ms[0]), solve_ms=float(ms[1]), marg_ms=float(ms[2]), total_ms=float(ms[3]), launches=k.value)
+
+    def launch_count(self):
+        k = C.c_int(0)
+        self.lib.ve_batch_last_timing(self.h, None, C.byref(k))
+        return k.value
+
+    def set_profile(self, on):
+        self.lib.ve_batch_set_profile(self.h, int(on))
+
+    def kernel_times(self):
+        ms, cnt = np.zeros(8), np.zeros(8, np.int32)
+        self.lib.ve_batch_kernel_times(self.h, _p(ms), _p(cnt))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(Estimator.KERNELS)}
+
+    def sync(self):
+        self.lib.ve_batch_sync(self.h)
+
+
+def debug_projection_factor(params23, data12, use_td=False, focal_length=460.0, tr=0.0, row=480.0, robust=False):
+    """Residual (2), Jacobian (2 x 20: pose_i 6, pose_j 6, ex 6, depth, td) and rho/2 of one visual factor, evaluated by the
+    device code of the solve."""
+    lib = load_library()
+    _bind(lib)
+    prm, dat, out = _d(params23), _d(data12), np.zeros(43)
+    assert prm.size == 23 and dat.size == 12
+    rc = lib.ve_debug_projection_factor(_p(prm), _p(dat), int(use_td), float(focal_length), float(tr), float(row), int(robust), _p(out))
+    if rc != 0:
+        raise RuntimeError(f"ve_debug_projection_factor: {rc}")
+    return out[0:2].copy(), out[2:42].reshape(2, 20).copy(), float(out[42])
+
+
+def debug_imu_factor(ba, bg, dt, acc, gyr, params32=None, noise=(0.08, 0.004, 0.00004, 2.0e-6), g_norm=9.81007):
+    """Device pre-integration of the samples (sample 0 seeds acc_0 / gyr_0) and, with params32, the whitened IMU factor."""
+    lib = load_library()
+    _bind(lib)
+    dt, acc, gyr = _d(dt), _d(acc), _d(gyr)
+    pre, fac = np.zeros(686), np.zeros(465)
+    prm = _d(params32) if params32 is not None else None
+    noise = _d(noise)
+    rc = lib.ve_debug_imu_factor(_p(noise), float(g_norm), _p(_d(ba)), _p(_d(bg)), len(dt), _p(dt), _p(acc), _p(gyr), _p(prm), _p(pre),
+                                 _p(fac) if prm is not None else None)
+    if rc != 0:
+        raise RuntimeError(f"ve_debug_imu_factor: {rc}")
+    out = dict(sum_dt=pre[0], dp=pre[1:4].copy(), dq=pre[4:8].copy(), dv=pre[8:11].copy(), jacobian=pre[11:236].reshape(15, 15).copy(),
+               covariance=pre[236:461].reshape(15, 15).copy(), sqrt_info=pre[461:686].reshape(15, 15).copy())
+    if prm is not None:
+        out["residual"], out["jacobian_w"] = fac[:15].copy(), fac[15:].reshape(15, 30).copy()
+    return out
