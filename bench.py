@@ -51,9 +51,9 @@ def sequence_inputs(seed, n_pub):
 class BatchedImu(pipeline.ImuFeeder):
     """Same sample selection / interpolation as estimator_node.cpp:98-136, 225-265, delivered in one call."""
 
-    def feed(self, estimator, img_t):
+    def feed(self, estimator, stamp, td=None):
         rec = _Recorder()
-        super().feed(rec, img_t)
+        super().feed(rec, stamp, estimator.states()[1] if td is None else td)
         if rec.dt:
             estimator.processIMU_batch(np.array(rec.dt), np.array(rec.acc), np.array(rec.gyr))
 

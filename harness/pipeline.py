@@ -58,11 +58,14 @@ class ImuFeeder:
         self.k = 0
         self.current_time = -1.0
 
-    def feed(self, estimator, img_t):
+    def feed(self, estimator, stamp, td=None):
+        """img_t = stamp + estimator.td, both for the sample selection and for the interpolation at the image
+        (estimator_node.cpp:106-126, 232-265); td defaults to the estimator's current estimate."""
+        if td is None:
+            td = estimator.states()[1] if hasattr(estimator, "states") else 0.0
+        img_t = stamp + td
         n = len(self.t)
-        last = None
         while self.k < n and self.t[self.k] < img_t:
-            last = self.k
             self._one(estimator, self.k, img_t)
             self.k += 1
         if self.k < n:  # the first sample at/after the image stamp is used but stays in the buffer

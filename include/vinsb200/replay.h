@@ -43,6 +43,11 @@ typedef struct vr_session vr_session;
 /* The session borrows the handles and the sequence memory: they must outlive it.  Seed / configure the estimators
  * before the first vr_advance. */
 int vr_open(int n_seq, vt_tracker* const* trackers, ve_estimator* const* estimators, const vr_sequence* seqs, vr_session** out);
+/* Batch mode: the sequences are the members of one tracker batch and one estimator batch (same count, same order; all
+ * sequences with the same row_stride and images_on_device).  The session then runs ONE tracker loop and ONE estimator loop:
+ * every image step is a vt_batch_node_image call, every published step a ve_batch_process_image call (one launch chain for all
+ * sequences); vr_stats reports the batch's kernel launches on sequence 0. */
+int vr_open_batch(vt_batch* trackers, ve_batch* estimators, const vr_sequence* seqs, vr_session** out);
 void vr_close(vr_session* s);
 const char* vr_last_error(const vr_session* s);
 

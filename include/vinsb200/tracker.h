@@ -56,6 +56,7 @@ typedef struct vt_config {
 } vt_config;
 
 typedef struct vt_tracker vt_tracker;
+typedef struct vt_batch vt_batch;
 
 int vt_create(const vt_config* cfg, vt_tracker** out);
 void vt_destroy(vt_tracker* t);
@@ -81,6 +82,32 @@ int vt_node_image_device(vt_tracker* t, const uint8_t* d_img, size_t row_stride,
  * channel values id*NUM_OF_CAM+cam (NUM_OF_CAM = 1), u, v, velocity_x, velocity_y.  Returns the point count. */
 int vt_node_pack(const vt_tracker* t, int capacity, float* xy_un, float* id_of_point, float* u_of_point,
                  float* v_of_point, float* velocity_x, float* velocity_y);
+
+/* ---- Batched sequences (SURVEY.md 8b "Threading", BASELINE configs[2] / [4]) --------------------------------------
+ * n trackers with one configuration that advance image by image TOGETHER: per image step one host-to-device copy, one
+ * launch per kernel stage (CLAHE, pyramid, LK, mask, Shi-Tomasi, candidate sort, selection; the member index is the last grid
+ * dimension) and one device-to-host copy for the whole batch; the members' host bookkeeping (culls, F-RANSAC, setMask,
+ * undistortion, ids) runs on a thread pool.  Within a member the serial chain prev/cur/forw of the reference
+ * (feature_tracker.cpp:160-164) is kept.  A stand-alone handle from vt_create is a batch of one running the same code.
+ *
+ *   vt_batch_member       borrowed handle of member k for vt_count / vt_get / vt_node_pack / vt_last_traffic (image calls and
+ *                         vt_destroy go through the batch)
+ *   vt_batch_read_image   FeatureTracker::readImage for every member k with active[k] != 0 (NULL = all); imgs[k] host or device
+ *                         pointers (images_on_device), all with the same row_stride
+ *   vt_batch_node_image   img_callback for every active member; results[k] = 0 / 1 / 2 as vt_node_image, restarts[k] may be NULL
+ */
+int vt_batch_create(const vt_config* cfg, int n, vt_batch** out);
+void vt_batch_destroy(vt_batch* b);
+int vt_batch_size(const vt_batch* b);
+vt_tracker* vt_batch_member(vt_batch* b, int k);
+const char* vt_batch_last_error(const vt_batch* b);
+int vt_batch_read_image(vt_batch* b, const int* active, const uint8_t* const* imgs, size_t row_stride, const double* cur_times,
+                        const int* pub_this_frame, int images_on_device);
+int vt_batch_node_image(vt_batch* b, const int* active, const uint8_t* const* imgs, size_t row_stride, const double* stamps,
+                        int images_on_device, int* results, int* restarts);
+int vt_batch_last_timing(const vt_batch* b, float* device_ms, int* kernel_launches);
+int vt_batch_set_profile(vt_batch* b, int on);
+int vt_batch_kernel_times(const vt_batch* b, double* ms6, int* count6);
 
 /* Device time (ms, CUDA events on the handle's stream) and launch count of the last read_image. */
 int vt_last_timing(const vt_tracker* t, float* device_ms, int* kernel_launches);

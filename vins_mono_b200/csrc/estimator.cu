@@ -25,6 +25,7 @@
 
 #include "ba_kernels.h"
 #include "host_math.h"
+#include "hostpool.h"
 #include "vinsb200/estimator.h"
 
 using hm::Mat3;
@@ -68,68 +69,6 @@ struct DeviceBuf {
         if (p) cudaFree(p);
         p = nullptr;
     }
-};
-
-// Minimal fork-join pool for the per-member host phases of a batch (prepare / finish are independent per member).
-class Pool {
-  public:
-    explicit Pool(int workers) {
-        for (int i = 0; i < workers; i++) th_.emplace_back([this] { loop(); });
-    }
-    ~Pool() {
-        {
-            std::lock_guard<std::mutex> lk(m_);
-            stop_ = true;
-        }
-        cv_.notify_all();
-        for (auto& t : th_) t.join();
-    }
-    void run(int n, const std::function<void(int)>& fn) {
-        if (th_.empty() || n <= 1) {
-            for (int i = 0; i < n; i++) fn(i);
-            return;
-        }
-        {
-            std::lock_guard<std::mutex> lk(m_);
-            fn_ = &fn;
-            n_ = n;
-            next_.store(0);
-            pending_ = (int)th_.size();
-            gen_++;
-        }
-        cv_.notify_all();
-        for (int i; (i = next_.fetch_add(1)) < n;) fn(i);
-        std::unique_lock<std::mutex> lk(m_);
-        done_.wait(lk, [this] { return pending_ == 0; });
-    }
-
-  private:
-    void loop() {
-        unsigned long long seen = 0;
-        for (;;) {
-            const std::function<void(int)>* fn;
-            int n;
-            {
-                std::unique_lock<std::mutex> lk(m_);
-                cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
-                if (stop_) return;
-                seen = gen_;
-                fn = fn_;
-                n = n_;
-            }
-            for (int i; (i = next_.fetch_add(1)) < n;) (*fn)(i);
-            std::lock_guard<std::mutex> lk(m_);
-            if (--pending_ == 0) done_.notify_one();
-        }
-    }
-    std::vector<std::thread> th_;
-    std::mutex m_;
-    std::condition_variable cv_, done_;
-    const std::function<void(int)>* fn_ = nullptr;
-    int n_ = 0, pending_ = 0;
-    std::atomic<int> next_{0};
-    unsigned long long gen_ = 0;
-    bool stop_ = false;
 };
 
 enum FrameStage { STAGE_DONE = 0, STAGE_INIT_SOLVE = 1, STAGE_RUN_SOLVE = 2 };
@@ -220,7 +159,7 @@ struct ve_batch {
     size_t out_cap = 0;             // doubles
     std::atomic<size_t> out_used{0};
     vb::KernelProfile prof;
-    Pool* pool = nullptr;
+    vb::HostPool* pool = nullptr;
     float last_ms[4] = {0, 0, 0, 0};
     int last_launches = 0;
     bool marg_timing_valid = false;
@@ -1237,9 +1176,7 @@ int ve_batch_create(const ve_config* cfg, int n, ve_batch** out) {
     VE_TRY(cudaHostAlloc(&b->h_out, sizeof(double) * b->out_cap, cudaHostAllocDefault));
 #undef VE_TRY
     b->w_in_global = vb::marg_w_in_global(15, e0->nmax);
-    const int hw = (int)std::thread::hardware_concurrency();
-    const int workers = std::max(0, std::min(std::min(n - 1, hw - 2), 23));
-    b->pool = new Pool(workers);
+    b->pool = new vb::HostPool(vb::HostPool::default_workers(n));
     *out = b;
     return VE_OK;
 }

@@ -29,9 +29,13 @@ __device__ __forceinline__ uint8_t sat_u8(float v) {
 // ---------------------------------------------------------------------------------------------
 // CLAHE step 1: one CTA per tile -> 256-entry LUT (histogram, clip, redistribute, cumulative sum).
 // Image reads are coalesced along rows; per-warp shared histograms keep atomics off a single bank set.
-__global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restrict__ src, int rows, int cols, int pitch,
-                                                        int tiles_x, int tw, int th, int clip, float lut_scale,
-                                                        uint8_t* __restrict__ lut) {
+__global__ void __launch_bounds__(256) clahe_lut_kernel(const FeSeq* __restrict__ seqs, int rows, int cols,
+                                                        int tiles_x, int tw, int th, int clip, float lut_scale) {
+    const FeSeq& q = seqs[blockIdx.y];
+    if (!q.track || !q.equalize) return;
+    const uint8_t* __restrict__ src = q.raw;
+    const int pitch = q.raw_pitch;
+    uint8_t* __restrict__ lut = q.lut;
     __shared__ int wh[8][256];
     __shared__ int red[8];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -91,13 +95,23 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
 }
 
 // CLAHE step 2: bilinear blend of the four neighbouring tile LUTs, 4 pixels per thread.
-__global__ void __launch_bounds__(256) clahe_apply_kernel(const uint8_t* __restrict__ src, int rows, int cols, int spitch,
-                                                          const uint8_t* __restrict__ lut, int tiles_x, int tiles_y,
-                                                          float inv_tw, float inv_th, uint8_t* __restrict__ dst,
-                                                          int dpitch) {
+__global__ void __launch_bounds__(256) clahe_apply_kernel(const FeSeq* __restrict__ seqs, int rows, int cols, int tiles_x,
+                                                          int tiles_y, float inv_tw, float inv_th) {
+    const FeSeq& q = seqs[blockIdx.z];
+    if (!q.track) return;
+    const uint8_t* __restrict__ src = q.raw;
+    const int spitch = q.raw_pitch;
+    const uint8_t* __restrict__ lut = q.lut;
+    uint8_t* __restrict__ dst = const_cast<uint8_t*>(q.forw.img[0]);
+    const int dpitch = q.forw.pitch[0];
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y;
     if (x0 >= cols) return;
+    if (!q.equalize) {  // EQUALIZE = 0: forw_img = img (feature_tracker.cpp:94-95)
+        for (int k = 0; k < 4; k++)
+            if (x0 + k < cols) dst[(size_t)y * dpitch + x0 + k] = src[(size_t)y * spitch + x0 + k];
+        return;
+    }
     const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
     int ty1 = (int)floorf(tyf);
     const float ya = __fsub_rn(tyf, (float)ty1), ya1 = __fsub_rn(1.0f, ya);
@@ -136,8 +150,15 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(const uint8_t* __restr
 // ---------------------------------------------------------------------------------------------
 // pyrDown: [1 4 6 4 1]^2, reflect-101, (sum + 128) >> 8.  One thread per output pixel; the 5x5
 // footprint is served by L1 (source level <= 361 KB, read once from HBM).
-__global__ void __launch_bounds__(256) pyrdown_kernel(const uint8_t* __restrict__ src, int rows, int cols, int spitch,
-                                                      uint8_t* __restrict__ dst, int drows, int dcols, int dpitch) {
+__global__ void __launch_bounds__(256) pyrdown_kernel(const FeSeq* __restrict__ seqs, int level, int use_cur) {
+    const FeSeq& q = seqs[blockIdx.z];
+    if (!q.track) return;
+    const PyramidView& pv = use_cur ? q.cur : q.forw;  // use_cur: the debug entry builds both pyramids
+    if (level > pv.nlev) return;
+    const uint8_t* __restrict__ src = pv.img[level - 1];
+    const int rows = pv.rows[level - 1], cols = pv.cols[level - 1], spitch = pv.pitch[level - 1];
+    uint8_t* __restrict__ dst = const_cast<uint8_t*>(pv.img[level]);
+    const int drows = pv.rows[level], dcols = pv.cols[level], dpitch = pv.pitch[level];
     const int dx = blockIdx.x * blockDim.x + threadIdx.x;
     const int dy = blockIdx.y * blockDim.y + threadIdx.y;
     if (dx >= dcols || dy >= drows) return;
@@ -182,18 +203,21 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
     return v;
 }
 
-__global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(PyramidView prev, PyramidView next,
-                                                                 const float* __restrict__ prev_pts, int n,
-                                                                 int max_iter, double eps2, float min_eig_thr,
-                                                                 int img_rows, int img_cols,
-                                                                 float* __restrict__ next_pts,
-                                                                 uint8_t* __restrict__ status) {
+__global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(const FeSeq* __restrict__ seqs, int max_iter, double eps2,
+                                                                 float min_eig_thr) {
     __shared__ LkSmem sm;
     constexpr int NT = 32 * LK_WARPS;
+    const FeSeq& q = seqs[blockIdx.y];
     const int lane = threadIdx.x;  // index within the CTA that owns point p
     const int wl = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int p = blockIdx.x;
-    if (p >= n) return;
+    if (!q.track || p >= q.n_pts) return;
+    const PyramidView& prev = q.cur;
+    const PyramidView& next = q.forw;
+    const float* __restrict__ prev_pts = q.pts_in;
+    float* __restrict__ next_pts = q.pts_out;
+    uint8_t* __restrict__ status = q.status;
+    const int img_rows = prev.rows[0], img_cols = prev.cols[0];
     int rpar = 0;
     const int W = 21;
     const float half = 10.f;
@@ -382,11 +406,31 @@ __global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(PyramidView pre
 // ---------------------------------------------------------------------------------------------
 // Mask: 255 (or the fisheye mask) with a filled cv::circle of radius r at every kept track.
 // halfw[d] = half width of the rasterised disc at row offset |d| (midpoint algorithm, host-computed).
-__global__ void __launch_bounds__(128) mask_discs_kernel(uint8_t* __restrict__ mask, int rows, int cols, int pitch,
-                                                         const int* __restrict__ centres, int n, int radius,
+// Mask start: 255 everywhere, or the fisheye mask (feature_tracker.cpp:38-41); also clears the detection counters.
+__global__ void __launch_bounds__(256) mask_init_kernel(const FeSeq* __restrict__ seqs, int rows, int cols) {
+    const FeSeq& q = seqs[blockIdx.y];
+    if (!q.detect) return;
+    const size_t n16 = (size_t)rows * cols / 16, total = (size_t)rows * cols;
+    uint4* m16 = reinterpret_cast<uint4*>(q.mask);
+    const uint4* s16 = reinterpret_cast<const uint4*>(q.mask_init);
+    const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = i0; i < n16; i += stride) m16[i] = s16 ? s16[i] : make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (size_t i = n16 * 16 + i0; i < total; i += stride) q.mask[i] = q.mask_init ? q.mask_init[i] : (uint8_t)255;
+    if (i0 == 0) {
+        q.count[0] = 0;
+        q.count[1] = 0;
+        *q.maxv = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(128) mask_discs_kernel(const FeSeq* __restrict__ seqs, int rows, int cols, int radius,
                                                          const int* __restrict__ halfw) {
+    const FeSeq& q = seqs[blockIdx.y];
     const int c = blockIdx.x;
-    if (c >= n) return;
+    if (!q.detect || c >= q.n_centres) return;
+    uint8_t* __restrict__ mask = q.mask;
+    const int pitch = cols;
+    const int* __restrict__ centres = q.centres;
     const int cx = centres[2 * c], cy = centres[2 * c + 1];
     const int side = 2 * radius + 1;
     for (int i = threadIdx.x; i < side * side; i += blockDim.x) {
@@ -410,11 +454,15 @@ __device__ __forceinline__ unsigned f32_sortable(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-__global__ void __launch_bounds__(ME_TW* ME_TH) min_eig_kernel(const uint8_t* __restrict__ img, int rows, int cols,
-                                                                int pitch, const uint8_t* __restrict__ mask,
-                                                                int mpitch, float k1, float k2,
-                                                                float* __restrict__ eig, int epitch,
-                                                                unsigned* __restrict__ max_sortable) {
+__global__ void __launch_bounds__(ME_TW* ME_TH) min_eig_kernel(const FeSeq* __restrict__ seqs, int rows, int cols, float k1, float k2) {
+    const FeSeq& q = seqs[blockIdx.z];
+    if (!q.detect) return;
+    const uint8_t* __restrict__ img = q.det_img;
+    const int pitch = q.det_pitch;
+    const uint8_t* __restrict__ mask = q.use_mask ? q.mask : nullptr;
+    const int mpitch = cols, epitch = cols;
+    float* __restrict__ eig = q.eig;
+    unsigned* __restrict__ max_sortable = q.maxv;
     __shared__ uint8_t tile[(ME_TH + 4) * (ME_TW + 4)];
     __shared__ float sxx[(ME_TH + 2) * (ME_TW + 2)], sxy[(ME_TH + 2) * (ME_TW + 2)], syy[(ME_TH + 2) * (ME_TW + 2)];
     __shared__ unsigned wmax[ME_TW * ME_TH / 32];
@@ -488,11 +536,16 @@ __global__ void __launch_bounds__(ME_TW* ME_TH) min_eig_kernel(const uint8_t* __
 // Candidate collection: interior pixels with thresholded eig != 0, equal to the 3x3 max of the
 // thresholded map, and mask != 0.  Key = (eig bits << 32) | linear offset: eig > thr >= 0 so the float
 // bit pattern orders like the value; ties resolve on the larger offset first (greaterThanPtr).
-__global__ void __launch_bounds__(256) gftt_candidates_kernel(const float* __restrict__ eig, int rows, int cols,
-                                                              int epitch, const uint8_t* __restrict__ mask, int mpitch,
-                                                              const unsigned* __restrict__ max_sortable, double quality,
-                                                              unsigned long long* __restrict__ keys, int capacity,
-                                                              int* __restrict__ count) {
+__global__ void __launch_bounds__(256) gftt_candidates_kernel(const FeSeq* __restrict__ seqs, int rows, int cols, double quality,
+                                                              int capacity) {
+    const FeSeq& q = seqs[blockIdx.z];
+    if (!q.detect) return;
+    const float* __restrict__ eig = q.eig;
+    const int epitch = cols, mpitch = cols;
+    const uint8_t* __restrict__ mask = q.use_mask ? q.mask : nullptr;
+    const unsigned* __restrict__ max_sortable = q.maxv;
+    unsigned long long* __restrict__ keys = q.keys;
+    int* __restrict__ count = q.count;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x < 1 || y < 1 || x >= cols - 1 || y >= rows - 1) return;
@@ -519,9 +572,12 @@ __global__ void __launch_bounds__(256) gftt_candidates_kernel(const float* __res
 }
 
 // Descending bitonic sort of the candidate keys by one CTA; keys live in shared memory when they fit.
-__global__ void __launch_bounds__(1024) sort_keys_desc_kernel(unsigned long long* __restrict__ keys,
-                                                              const int* __restrict__ count, int capacity) {
+__global__ void __launch_bounds__(1024) sort_keys_desc_kernel(const FeSeq* __restrict__ seqs, int capacity) {
     extern __shared__ unsigned long long sk[];
+    const FeSeq& q = seqs[blockIdx.x];
+    if (!q.detect) return;
+    unsigned long long* __restrict__ keys = q.keys;
+    const int* __restrict__ count = q.count;
     int n = min(*count, capacity);
     int npad = 1;
     while (npad < n) npad <<= 1;
@@ -558,12 +614,17 @@ __global__ void __launch_bounds__(1024) sort_keys_desc_kernel(unsigned long long
 // of a cell_size grid), then the batch is resolved in priority order with shuffles, so the result is
 // exactly the sequential greedy scan.
 #define SEL_CELL_CAP 8
-__global__ void __launch_bounds__(32) gftt_select_kernel(const unsigned long long* __restrict__ keys,
-                                                         const int* __restrict__ count, int capacity, int cols,
-                                                         int rows, int max_corners, float min_dist, int cell,
-                                                         int gw, int gh, int* __restrict__ cell_cnt,
-                                                         short2* __restrict__ cell_pts, float* __restrict__ out_pts,
-                                                         int* __restrict__ out_n) {
+__global__ void __launch_bounds__(32) gftt_select_kernel(const FeSeq* __restrict__ seqs, int capacity, int cols, int rows,
+                                                         float min_dist, int cell, int gw, int gh) {
+    const FeSeq& q = seqs[blockIdx.x];
+    if (!q.detect) return;
+    const unsigned long long* __restrict__ keys = q.keys;
+    const int* __restrict__ count = q.count;
+    const int max_corners = q.max_corners;
+    int* __restrict__ cell_cnt = q.cell_cnt;
+    short2* __restrict__ cell_pts = q.cell_pts;
+    float* __restrict__ out_pts = q.new_pts;
+    int* __restrict__ out_n = q.count + 1;
     const int lane = threadIdx.x;
     const int n = min(*count, capacity);
     for (int i = lane; i < gw * gh; i += 32) cell_cnt[i] = 0;
@@ -621,72 +682,111 @@ __global__ void __launch_bounds__(32) gftt_select_kernel(const unsigned long lon
 }
 
 // ---------------------------------------------------------------------------------------------
-// launch wrappers
-void launch_clahe(const uint8_t* src, int rows, int cols, int spitch, uint8_t* lut, uint8_t* dst, int dpitch,
-                  cudaStream_t s) {
-    const int tiles_x = 8, tiles_y = 8;
-    int ext_rows = rows, ext_cols = cols;
-    if (cols % tiles_x != 0 || rows % tiles_y != 0) {
-        ext_rows = rows + (tiles_y - rows % tiles_y);
-        ext_cols = cols + (tiles_x - cols % tiles_x);
+// launch wrappers: one launch per stage for the whole batch (member = last grid dimension)
+namespace {
+std::mutex g_sort_mutex;
+bool g_sort_configured[64] = {};
+}  // namespace
+
+void launch_track(const FeSeq* seqs, const FeShape& sh, cudaStream_t s, int* launches, KernelProfile* prof) {
+    KernelProfile none;
+    if (!prof) prof = &none;
+    if (!sh.any_track) return;
+    const int rows = sh.rows, cols = sh.cols;
+    int n = 0;
+    prof->begin(s);
+    if (sh.any_equalize) {
+        const int tiles_x = 8, tiles_y = 8;
+        int ext_rows = rows, ext_cols = cols;
+        if (cols % tiles_x != 0 || rows % tiles_y != 0) {
+            ext_rows = rows + (tiles_y - rows % tiles_y);
+            ext_cols = cols + (tiles_x - cols % tiles_x);
+        }
+        const int tw = ext_cols / tiles_x, th = ext_rows / tiles_y, area = tw * th;
+        const float lut_scale = 255.f / (float)area;
+        int clip = (int)(3.0 * area / 256);
+        clip = clip < 1 ? 1 : clip;
+        clahe_lut_kernel<<<dim3(tiles_x * tiles_y, sh.S), 256, 0, s>>>(seqs, rows, cols, tiles_x, tw, th, clip, lut_scale);
+        clahe_apply_kernel<<<dim3((cols + 4 * 256 - 1) / (4 * 256), rows, sh.S), 256, 0, s>>>(seqs, rows, cols, tiles_x, tiles_y,
+                                                                                               1.0f / tw, 1.0f / th);
+        n += 2;
+    } else {
+        clahe_apply_kernel<<<dim3((cols + 4 * 256 - 1) / (4 * 256), rows, sh.S), 256, 0, s>>>(seqs, rows, cols, 8, 8, 1.f, 1.f);
+        n += 1;
     }
-    const int tw = ext_cols / tiles_x, th = ext_rows / tiles_y, area = tw * th;
-    const float lut_scale = 255.f / (float)area;
-    int clip = (int)(3.0 * area / 256);
-    clip = clip < 1 ? 1 : clip;
-    clahe_lut_kernel<<<tiles_x * tiles_y, 256, 0, s>>>(src, rows, cols, spitch, tiles_x, tw, th, clip, lut_scale, lut);
-    dim3 grid((cols + 4 * 256 - 1) / (4 * 256), rows);
-    clahe_apply_kernel<<<grid, 256, 0, s>>>(src, rows, cols, spitch, lut, tiles_x, tiles_y, 1.0f / tw, 1.0f / th, dst,
-                                            dpitch);
+    prof->end(0, s, n);
+    prof->begin(s);
+    int r = rows, c = cols;
+    for (int l = 1; l <= sh.nlev; l++) {
+        r = (r + 1) / 2;
+        c = (c + 1) / 2;
+        pyrdown_kernel<<<dim3((c + 31) / 32, (r + 7) / 8, sh.S), dim3(32, 8), 0, s>>>(seqs, l, 0);
+        n++;
+    }
+    prof->end(1, s, sh.nlev);
+    if (sh.max_pts > 0) {
+        const double eps = 0.01;
+        prof->begin(s);
+        lk_track_kernel<<<dim3(sh.max_pts, sh.S), 32 * LK_WARPS, 0, s>>>(seqs, 30, eps * eps, 1e-4f);
+        prof->end(2, s);
+        n++;
+    }
+    if (launches) *launches += n;
 }
 
-void launch_pyrdown(const uint8_t* src, int rows, int cols, int spitch, uint8_t* dst, int dpitch, cudaStream_t s) {
-    const int drows = (rows + 1) / 2, dcols = (cols + 1) / 2;
-    dim3 block(32, 8), grid((dcols + 31) / 32, (drows + 7) / 8);
-    pyrdown_kernel<<<grid, block, 0, s>>>(src, rows, cols, spitch, dst, drows, dcols, dpitch);
+void launch_pyramid_only(const FeSeq* seqs, const FeShape& sh, int use_cur, cudaStream_t s) {
+    int r = sh.rows, c = sh.cols;
+    for (int l = 1; l <= sh.nlev; l++) {
+        r = (r + 1) / 2;
+        c = (c + 1) / 2;
+        pyrdown_kernel<<<dim3((c + 31) / 32, (r + 7) / 8, sh.S), dim3(32, 8), 0, s>>>(seqs, l, use_cur);
+    }
 }
 
-void launch_lk(const PyramidView& prev, const PyramidView& next, const float* prev_pts, int n, float* next_pts,
-               uint8_t* status, cudaStream_t s) {
-    if (n <= 0) return;
+void launch_lk_only(const FeSeq* seqs, const FeShape& sh, cudaStream_t s) {
+    if (sh.max_pts <= 0) return;
     const double eps = 0.01;
-    lk_track_kernel<<<n, 32 * LK_WARPS, 0, s>>>(prev, next, prev_pts, n, 30, eps * eps, 1e-4f,
-                                                                          prev.rows[0], prev.cols[0], next_pts, status);
+    lk_track_kernel<<<dim3(sh.max_pts, sh.S), 32 * LK_WARPS, 0, s>>>(seqs, 30, eps * eps, 1e-4f);
 }
 
-void launch_mask_discs(uint8_t* mask, int rows, int cols, int pitch, const int* centres, int n, int radius,
-                       const int* halfw, cudaStream_t s) {
-    if (n <= 0) return;
-    mask_discs_kernel<<<n, 128, 0, s>>>(mask, rows, cols, pitch, centres, n, radius, halfw);
-}
-
-void launch_min_eig(const uint8_t* img, int rows, int cols, int pitch, const uint8_t* mask, int mpitch, float* eig,
-                    int epitch, unsigned* max_sortable, cudaStream_t s) {
+void launch_detect(const FeSeq* seqs, const FeShape& sh, const int* halfw, cudaStream_t s, int* launches, KernelProfile* prof) {
+    KernelProfile none;
+    if (!prof) prof = &none;
+    if (!sh.any_detect) return;
+    const int rows = sh.rows, cols = sh.cols;
+    int n = 0;
+    prof->begin(s);
+    mask_init_kernel<<<dim3(32, sh.S), 256, 0, s>>>(seqs, rows, cols);
+    n++;
+    if (sh.max_centres > 0) {
+        mask_discs_kernel<<<dim3(sh.max_centres, sh.S), 128, 0, s>>>(seqs, rows, cols, sh.min_dist, halfw);
+        n++;
+    }
+    prof->end(3, s, n);
     const double scale = 1.0 / ((double)(1 << 2) * 3 * 255.0);
-    dim3 block(ME_TW, ME_TH), grid((cols + ME_TW - 1) / ME_TW, (rows + ME_TH - 1) / ME_TH);
-    min_eig_kernel<<<grid, block, 0, s>>>(img, rows, cols, pitch, mask, mpitch, (float)scale, (float)(2.0 * scale), eig,
-                                          epitch, max_sortable);
-}
-
-void launch_gftt_tail(const float* eig, int rows, int cols, int epitch, const uint8_t* mask, int mpitch,
-                      const unsigned* max_sortable, double quality, unsigned long long* keys, int capacity, int* count,
-                      int max_corners, float min_dist, int* cell_cnt, short2* cell_pts, float* out_pts, int* out_n,
-                      cudaStream_t s) {
-    dim3 block(32, 8), grid((cols + 31) / 32, (rows + 7) / 8);
-    gftt_candidates_kernel<<<grid, block, 0, s>>>(eig, rows, cols, epitch, mask, mpitch, max_sortable, quality, keys,
-                                                  capacity, count);
+    prof->begin(s);
+    min_eig_kernel<<<dim3((cols + ME_TW - 1) / ME_TW, (rows + ME_TH - 1) / ME_TH, sh.S), dim3(ME_TW, ME_TH), 0, s>>>(
+        seqs, rows, cols, (float)scale, (float)(2.0 * scale));
+    prof->end(4, s);
+    prof->begin(s);
+    gftt_candidates_kernel<<<dim3((cols + 31) / 32, (rows + 7) / 8, sh.S), dim3(32, 8), 0, s>>>(seqs, rows, cols, 0.01, sh.key_capacity);
     {
-        static std::once_flag attr_once;  // trackers on different host threads share the function attribute
-        std::call_once(attr_once, [] {
+        std::lock_guard<std::mutex> lock(g_sort_mutex);  // the attribute belongs to the current device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!g_sort_configured[dev & 63]) {
             cudaFuncSetAttribute(sort_keys_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  SORT_SMEM_KEYS * (int)sizeof(unsigned long long));
-        });
+            g_sort_configured[dev & 63] = true;
+        }
     }
-    sort_keys_desc_kernel<<<1, 1024, SORT_SMEM_KEYS * sizeof(unsigned long long), s>>>(keys, count, capacity);
-    const int cell = (int)lrint((double)min_dist);
+    sort_keys_desc_kernel<<<sh.S, 1024, SORT_SMEM_KEYS * sizeof(unsigned long long), s>>>(seqs, sh.key_capacity);
+    const int cell = (int)lrint((double)sh.min_dist);
     const int gw = (cols + cell - 1) / cell, gh = (rows + cell - 1) / cell;
-    gftt_select_kernel<<<1, 32, 0, s>>>(keys, count, capacity, cols, rows, max_corners, min_dist, cell, gw, gh, cell_cnt,
-                                        cell_pts, out_pts, out_n);
+    gftt_select_kernel<<<sh.S, 32, 0, s>>>(seqs, sh.key_capacity, cols, rows, (float)sh.min_dist, cell, gw, gh);
+    prof->end(5, s, 3);
+    n += 4;
+    if (launches) *launches += n;
 }
 
 }  // namespace vb

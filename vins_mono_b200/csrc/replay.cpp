@@ -62,9 +62,40 @@ struct SeqState {
     std::vector<double> dt, acc, gyr, states;
 };
 
+struct BatchStep {  // what one image step of a tracker batch produced: at most one feature message per member
+    std::vector<FeatureMsg> msgs;
+    std::vector<char> has;
+    bool end = false;
+};
+
+struct BatchChannel {
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<BatchStep> q;
+    size_t depth = 2;
+    void put(BatchStep&& v) {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return q.size() < depth; });
+        q.push_back(std::move(v));
+        cv.notify_all();
+    }
+    BatchStep get() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return !q.empty(); });
+        BatchStep v = std::move(q.front());
+        q.pop_front();
+        cv.notify_all();
+        return v;
+    }
+};
+
 }  // namespace
 
 struct vr_session {
+    vt_batch* tb = nullptr;  // batch mode (vr_open_batch): one tracker loop and one estimator loop for all sequences
+    ve_batch* eb = nullptr;
+    BatchChannel bch;
+    long long batch_launches = 0;
     std::vector<SeqState> seqs;
     std::string error;
     std::mutex err_m;
@@ -193,7 +224,9 @@ void estimator_loop(vr_session* s, SeqState* q) {
         if (q->first_msg) {
             q->first_msg = false;
         } else {
-            collect_imu(q, msg.stamp);
+            double td = 0;  // img_t = stamp + estimator.td in getMeasurements and process() (estimator_node.cpp:106-126, 232-265)
+            ve_get_states(q->est, q->states.data(), &td);
+            collect_imu(q, msg.stamp + td);
             int rc = q->dt.empty() ? 0 : ve_process_imu_batch(q->est, (int)q->dt.size(), q->dt.data(), q->acc.data(), q->gyr.data());
             if (rc == 0) rc = ve_process_image(q->est, (int)msg.ids.size(), msg.ids.data(), msg.obs.data(), msg.stamp);
             if (rc < 0) {
@@ -223,9 +256,205 @@ void estimator_loop(vr_session* s, SeqState* q) {
     }
 }
 
+// Packs the feature message of tracker handle trk (estimator_node.cpp:283-302: v = id_of_point + 0.5, feature_id = v / NUM_OF_CAM).
+int pack_message(SeqState* q, vt_tracker* trk, double stamp, FeatureMsg& msg) {
+    const int cap = vt_count(trk);
+    q->f_xy.resize(2 * (size_t)cap + 2);
+    q->f_id.resize(cap + 1);
+    q->f_u.resize(cap + 1);
+    q->f_v.resize(cap + 1);
+    q->f_vx.resize(cap + 1);
+    q->f_vy.resize(cap + 1);
+    const int n = vt_node_pack(trk, cap, q->f_xy.data(), q->f_id.data(), q->f_u.data(), q->f_v.data(), q->f_vx.data(), q->f_vy.data());
+    if (n < 0) return n;
+    msg.stamp = stamp;
+    msg.ids.resize(n);
+    msg.obs.resize(7 * (size_t)n);
+    for (int k = 0; k < n; k++) {
+        msg.ids[k] = (int)(q->f_id[k] + 0.5f);
+        double* o = &msg.obs[7 * (size_t)k];
+        o[0] = q->f_xy[2 * k];
+        o[1] = q->f_xy[2 * k + 1];
+        o[2] = 1.0;
+        o[3] = q->f_u[k];
+        o[4] = q->f_v[k];
+        o[5] = q->f_vx[k];
+        o[6] = q->f_vy[k];
+    }
+    return 0;
+}
+
+// Batch mode, tracker side: every sequence that still owes published frames consumes its next image in the same
+// vt_batch_node_image call; the members that published hand their messages to the estimator loop as one BatchStep.
+void tracker_batch_loop(vr_session* s, int n_pub) {
+    const int S = (int)s->seqs.size();
+    std::vector<int> produced(S, 0), active(S), results(S), restarts(S);
+    std::vector<const uint8_t*> imgs(S);
+    std::vector<double> stamps(S);
+    std::vector<double> acc_h2d(S, 0.0), acc_d2h(S, 0.0);
+    long long acc_launches = 0;
+    while (s->status.load() == 0) {
+        bool any = false;
+        for (int k = 0; k < S; k++) {
+            SeqState& q = s->seqs[k];
+            active[k] = produced[k] < n_pub && q.cursor < q.in.n_images;
+            imgs[k] = nullptr;
+            stamps[k] = 0;
+            if (!active[k]) continue;
+            any = true;
+            imgs[k] = q.in.images + (size_t)q.cursor * q.in.frame_stride;
+            stamps[k] = q.in.stamps[q.cursor];
+        }
+        if (!any) break;
+        const vr_sequence& in0 = s->seqs[0].in;
+        const int rc = vt_batch_node_image(s->tb, active.data(), imgs.data(), in0.row_stride, stamps.data(), in0.images_on_device,
+                                           results.data(), restarts.data());
+        if (rc < 0) {
+            s->fail(rc, std::string("tracker batch: ") + vt_batch_last_error(s->tb));
+            break;
+        }
+        int l = 0;
+        vt_batch_last_timing(s->tb, nullptr, &l);
+        acc_launches += l;
+        BatchStep step;
+        step.msgs.resize(S);
+        step.has.assign(S, 0);
+        bool any_msg = false;
+        for (int k = 0; k < S; k++) {
+            if (!active[k]) continue;
+            SeqState& q = s->seqs[k];
+            q.cursor++;
+            if (results[k] > 0) {
+                double a = 0, b = 0;
+                vt_last_traffic(q.trk, &a, &b);
+                acc_h2d[k] += a;
+                acc_d2h[k] += b;
+            }
+            if (results[k] != 2) continue;
+            FeatureMsg& msg = step.msgs[k];
+            const int prc = pack_message(&q, q.trk, stamps[k], msg);
+            if (prc < 0) {
+                s->fail(prc, "tracker batch: vt_node_pack");
+                break;
+            }
+            msg.h2d = acc_h2d[k];
+            msg.d2h = acc_d2h[k];
+            acc_h2d[k] = acc_d2h[k] = 0;
+            step.has[k] = 1;
+            produced[k]++;
+            any_msg = true;
+        }
+        if (any_msg) {
+            step.msgs[0].launches += acc_launches;  // batch launches are not attributable to a member: carried on member 0's slot
+            acc_launches = 0;
+            s->bch.put(std::move(step));
+        }
+    }
+    BatchStep fin;
+    fin.end = true;
+    s->bch.put(std::move(fin));
+}
+
+// Batch mode, estimator side: IMU selection per member, then ONE ve_batch_process_image for all members with a message.
+void estimator_batch_loop(vr_session* s) {
+    const int S = (int)s->seqs.size();
+    std::vector<int> active(S), n(S), status(S);
+    std::vector<const int*> ids(S);
+    std::vector<const double*> obs(S);
+    std::vector<double> stamps(S);
+    for (;;) {
+        BatchStep step = s->bch.get();
+        if (step.end) break;
+        if (s->status.load() != 0) continue;  // keep draining so that the producer can finish
+        bool any = false;
+        s->batch_launches += step.msgs[0].launches;
+        for (int k = 0; k < S; k++) {
+            SeqState& q = s->seqs[k];
+            active[k] = 0;
+            n[k] = 0;
+            ids[k] = nullptr;
+            obs[k] = nullptr;
+            stamps[k] = 0;
+            if (!step.has[k]) continue;
+            FeatureMsg& msg = step.msgs[k];
+            q.h2d += msg.h2d;
+            q.d2h += msg.d2h;
+            if (q.first_msg) {  // estimator_node.cpp:167-172
+                q.first_msg = false;
+                q.frames++;
+                continue;
+            }
+            double td = 0;
+            ve_get_states(q.est, q.states.data(), &td);
+            collect_imu(&q, msg.stamp + td);
+            const int rc = q.dt.empty() ? 0 : ve_process_imu_batch(q.est, (int)q.dt.size(), q.dt.data(), q.acc.data(), q.gyr.data());
+            if (rc < 0) {
+                s->fail(rc, std::string("estimator: ") + ve_last_error(q.est));
+                break;
+            }
+            active[k] = 1;
+            n[k] = (int)msg.ids.size();
+            ids[k] = msg.ids.data();
+            obs[k] = msg.obs.data();
+            stamps[k] = msg.stamp;
+            any = true;
+        }
+        if (s->status.load() != 0 || !any) continue;
+        const int rc = ve_batch_process_image(s->eb, active.data(), n.data(), ids.data(), obs.data(), stamps.data(), status.data());
+        if (rc < 0) {
+            s->fail(rc, std::string("estimator batch: ") + ve_batch_last_error(s->eb));
+            continue;
+        }
+        int l = 0;
+        ve_batch_last_timing(s->eb, nullptr, &l);
+        s->batch_launches += l;
+        for (int k = 0; k < S; k++) {
+            if (!active[k]) continue;
+            SeqState& q = s->seqs[k];
+            double a = 0, b = 0;
+            ve_last_traffic(q.est, &a, &b);
+            q.h2d += a;
+            q.d2h += b;
+            q.frames++;
+            int info[10];
+            double costs[2];
+            if (ve_info(q.est, info, costs) == 0 && info[0] == 1) {
+                ve_get_states(q.est, q.states.data(), nullptr);
+                const double* newest = &q.states[16 * (size_t)info[1]];
+                q.traj_t.push_back(stamps[k]);
+                q.traj_p.insert(q.traj_p.end(), newest, newest + 3);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int vr_open_batch(vt_batch* trackers, ve_batch* estimators, const vr_sequence* seqs, vr_session** out) {
+    if (!trackers || !estimators || !seqs || !out) return -1;
+    const int n_seq = vt_batch_size(trackers);
+    if (n_seq <= 0 || n_seq != ve_batch_size(estimators)) return -1;
+    auto* s = new vr_session;
+    s->tb = trackers;
+    s->eb = estimators;
+    s->seqs = std::vector<SeqState>(n_seq);
+    for (int k = 0; k < n_seq; k++) {
+        SeqState& q = s->seqs[k];
+        if (!seqs[k].images || !seqs[k].stamps || (seqs[k].n_imu > 0 && !seqs[k].imu_t) || seqs[k].row_stride != seqs[0].row_stride ||
+            seqs[k].images_on_device != seqs[0].images_on_device) {
+            delete s;
+            return -1;
+        }
+        q.trk = vt_batch_member(trackers, k);
+        q.est = ve_batch_member(estimators, k);
+        q.in = seqs[k];
+        q.states.assign(16 * 65, 0.0);
+    }
+    *out = s;
+    return 0;
+}
 
 int vr_open(int n_seq, vt_tracker* const* trackers, ve_estimator* const* estimators, const vr_sequence* seqs, vr_session** out) {
     if (n_seq <= 0 || !trackers || !estimators || !seqs || !out) return -1;
@@ -255,11 +484,15 @@ int vr_advance(vr_session* s, int n_pub) {
     if (s->status.load() != 0) return s->status.load();
     std::vector<int> before(s->seqs.size());
     std::vector<std::thread> threads;
-    for (size_t k = 0; k < s->seqs.size(); k++) {
-        before[k] = s->seqs[k].frames;
-        threads.emplace_back(tracker_loop, s, &s->seqs[k], n_pub);
-        threads.emplace_back(estimator_loop, s, &s->seqs[k]);
-    }
+    for (size_t k = 0; k < s->seqs.size(); k++) before[k] = s->seqs[k].frames;
+    if (s->tb) {
+        threads.emplace_back(tracker_batch_loop, s, n_pub);
+        threads.emplace_back(estimator_batch_loop, s);
+    } else
+        for (size_t k = 0; k < s->seqs.size(); k++) {
+            threads.emplace_back(tracker_loop, s, &s->seqs[k], n_pub);
+            threads.emplace_back(estimator_loop, s, &s->seqs[k]);
+        }
     for (auto& t : threads) t.join();
     if (s->status.load() != 0) return s->status.load();
     int total = 0;
@@ -295,7 +528,7 @@ int vr_stats(const vr_session* s, int seq, int* frames, long long* launches, dou
     if (!s || seq < 0 || seq >= (int)s->seqs.size()) return -1;
     const SeqState& q = s->seqs[seq];
     if (frames) *frames = q.frames;
-    if (launches) *launches = q.launches;
+    if (launches) *launches = s->tb ? (seq == 0 ? s->batch_launches : 0) : q.launches;
     if (h2d_bytes) *h2d_bytes = q.h2d;
     if (d2h_bytes) *d2h_bytes = q.d2h;
     return 0;

@@ -21,8 +21,12 @@ class ReplaySession:
     stamps, imu_t, acc, gyr).  trackers / estimators: the Python mirrors (their .h handles are borrowed)."""
 
     def __init__(self, trackers, estimators, sequences):
+        """trackers / estimators: lists of FeatureTracker / Estimator mirrors (one thread pair per sequence), or a TrackerBatch
+        and an EstimatorBatch (batch mode: one tracker loop and one estimator loop, one launch chain per step for all)."""
         self.lib = load_library()
         L = self.lib
+        batch_mode = not isinstance(trackers, (list, tuple))
+        L.vr_open_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.vr_open.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.vr_advance.argtypes = [C.c_void_p, C.c_int]
         L.vr_close.argtypes = [C.c_void_p]
@@ -31,7 +35,7 @@ class ReplaySession:
         L.vr_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.vr_trajectory.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         n = len(sequences)
-        assert len(trackers) == n and len(estimators) == n
+        assert (trackers.n == n and estimators.n == n) if batch_mode else (len(trackers) == n and len(estimators) == n)
         self._keep = []  # arrays the session borrows
         arr = (_Seq * n)()
         for k, sq in enumerate(sequences):
@@ -51,11 +55,15 @@ class ReplaySession:
                 setattr(arr[k], name, a.ctypes.data)
             arr[k].n_imu = len(sq["imu_t"])
         self._arr, self.n = arr, n
-        th = (C.c_void_p * n)(*[t.h for t in trackers])
-        eh = (C.c_void_p * n)(*[e.h for e in estimators])
         self.h = C.c_void_p()
-        if L.vr_open(n, th, eh, arr, C.byref(self.h)) != 0:
-            raise RuntimeError("vr_open failed")
+        if batch_mode:
+            if L.vr_open_batch(trackers.h, estimators.h, arr, C.byref(self.h)) != 0:
+                raise RuntimeError("vr_open_batch failed")
+        else:
+            th = (C.c_void_p * n)(*[t.h for t in trackers])
+            eh = (C.c_void_p * n)(*[e.h for e in estimators])
+            if L.vr_open(n, th, eh, arr, C.byref(self.h)) != 0:
+                raise RuntimeError("vr_open failed")
 
     def advance(self, n_pub: int) -> int:
         r = self.lib.vr_advance(self.h, n_pub)

@@ -47,8 +47,31 @@ def load_library():
                                       C.POINTER(C.c_int), C.c_void_p]
         lib.vt_debug_lk.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
                                     C.c_void_p]
+        lib.vt_batch_create.argtypes = [C.POINTER(TrackerConfig), C.c_int, C.POINTER(C.c_void_p)]
+        lib.vt_batch_destroy.argtypes = [C.c_void_p]
+        lib.vt_batch_member.argtypes = [C.c_void_p, C.c_int]
+        lib.vt_batch_member.restype = C.c_void_p
+        lib.vt_batch_last_error.argtypes = [C.c_void_p]
+        lib.vt_batch_last_error.restype = C.c_char_p
+        lib.vt_batch_read_image.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+        lib.vt_batch_node_image.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.vt_batch_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        lib.vt_batch_set_profile.argtypes = [C.c_void_p, C.c_int]
+        lib.vt_batch_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
+
+
+def _make_tracker_config(rows=480, cols=752, max_cnt=150, min_dist=30, freq=10, equalize=1, focal_length=460,
+                         f_threshold=1.0, fx=461.6, fy=460.3, cx=363.0, cy=248.1, k1=-0.2917, k2=0.08228, p1=5.333e-05,
+                         p2=-1.578e-04, fisheye=0, fisheye_mask=None, device=0, **_ignored):
+    cfg = TrackerConfig(rows=rows, cols=cols, max_cnt=max_cnt, min_dist=min_dist, freq=freq, equalize=equalize,
+                        fisheye=fisheye, focal_length=focal_length, f_threshold=f_threshold, camera_model=0,
+                        device=device)
+    cfg.intrinsics[:] = [fx, fy, cx, cy, k1, k2, p1, p2]
+    mask = np.ascontiguousarray(fisheye_mask, np.uint8) if fisheye_mask is not None else None
+    cfg.fisheye_mask = mask.ctypes.data if mask is not None else None
+    return cfg, mask
 
 
 def _ptr(a):
@@ -58,27 +81,29 @@ def _ptr(a):
 class FeatureTracker:
     """Drop-in for the reference FeatureTracker: readImage(img, t) then read the public result arrays."""
 
-    def __init__(self, rows=480, cols=752, max_cnt=150, min_dist=30, freq=10, equalize=1, focal_length=460,
-                 f_threshold=1.0, fx=461.6, fy=460.3, cx=363.0, cy=248.1, k1=-0.2917, k2=0.08228, p1=5.333e-05,
-                 p2=-1.578e-04, fisheye=0, fisheye_mask=None, device=0, **_ignored):
+    def __init__(self, **kw):
         self.lib = load_library()
-        cfg = TrackerConfig(rows=rows, cols=cols, max_cnt=max_cnt, min_dist=min_dist, freq=freq, equalize=equalize,
-                            fisheye=fisheye, focal_length=focal_length, f_threshold=f_threshold, camera_model=0,
-                            device=device)
-        cfg.intrinsics[:] = [fx, fy, cx, cy, k1, k2, p1, p2]
-        self._mask = np.ascontiguousarray(fisheye_mask, np.uint8) if fisheye_mask is not None else None
-        cfg.fisheye_mask = self._mask.ctypes.data if self._mask is not None else None
-        self.cfg, self.rows, self.cols, self.max_cnt = cfg, rows, cols, max_cnt
+        cfg, self._mask = _make_tracker_config(**kw)
+        self.cfg, self.rows, self.cols, self.max_cnt = cfg, cfg.rows, cfg.cols, cfg.max_cnt
         h = C.c_void_p()
         rc = self.lib.vt_create(C.byref(cfg), C.byref(h))
         if rc != 0:
             raise RuntimeError(f"vt_create failed with status {rc} (-2 = no CUDA device; this library has no CPU path)")
         self.h = h
+        self._borrowed = False
         self.PUB_THIS_FRAME = False
+
+    @classmethod
+    def _member(cls, lib, handle, cfg):
+        self = cls.__new__(cls)
+        self.lib, self.cfg, self.rows, self.cols, self.max_cnt = lib, cfg, cfg.rows, cfg.cols, cfg.max_cnt
+        self.h, self._borrowed, self.PUB_THIS_FRAME, self._mask = C.c_void_p(handle), True, False, None
+        return self
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.vt_destroy(self.h)
+            if not self._borrowed:
+                self.lib.vt_destroy(self.h)
             self.h = None
 
     __del__ = close
@@ -171,3 +196,77 @@ class FeatureTracker:
         out, st = np.zeros((n, 2), np.float32), np.zeros(n, np.uint8)
         self._check(self.lib.vt_debug_lk(self.h, _ptr(prev), _ptr(nxt), prev.strides[0], _ptr(pts), n, _ptr(out), _ptr(st)))
         return out, st
+
+
+class TrackerBatch:
+    """n trackers advancing image by image together (include/vinsb200/tracker.h, vt_batch_*): one launch per kernel stage
+    for the whole batch.  members[k] is a FeatureTracker mirror for result() / feature_message()."""
+
+    def __init__(self, n, **kw):
+        self.lib = load_library()
+        self.cfg, self._mask = _make_tracker_config(**kw)
+        self.n, self.rows, self.cols = n, self.cfg.rows, self.cfg.cols
+        h = C.c_void_p()
+        rc = self.lib.vt_batch_create(C.byref(self.cfg), n, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"vt_batch_create failed with status {rc} (-2 = no CUDA device; this library has no CPU path)")
+        self.h = h
+        self.members = [FeatureTracker._member(self.lib, self.lib.vt_batch_member(h, k), self.cfg) for k in range(n)]
+
+    def close(self):
+        if getattr(self, "h", None):
+            for m in self.members:
+                m.h = None
+            self.lib.vt_batch_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _pointers(self, imgs):
+        n = self.n
+        active = np.zeros(n, np.int32)
+        ptrs, keep, stride, dev = (C.c_void_p * n)(), [], self.cols, 0
+        for k, im in enumerate(imgs):
+            if im is None:
+                continue
+            active[k] = 1
+            if isinstance(im, np.ndarray):
+                im = np.ascontiguousarray(im, np.uint8)
+                assert im.shape == (self.rows, self.cols)
+                keep.append(im)
+                ptrs[k] = im.ctypes.data
+            else:  # device pointer (int), rows x cols contiguous
+                ptrs[k], dev = int(im), 1
+        return active, ptrs, keep, stride, dev
+
+    def _check(self, rc):
+        if rc < 0:
+            raise RuntimeError(f"vinsb200 batch error {rc}: {self.lib.vt_batch_last_error(self.h).decode()}")
+
+    def readImage(self, imgs, cur_times, pubs):
+        """imgs[k]: numpy frame, device pointer or None (member idles)."""
+        active, ptrs, keep, stride, dev = self._pointers(imgs)
+        t = np.ascontiguousarray(cur_times, np.float64)
+        p = np.ascontiguousarray(pubs, np.int32)
+        self._check(self.lib.vt_batch_read_image(self.h, _ptr(active), ptrs, stride, _ptr(t), _ptr(p), dev))
+
+    def node_image(self, imgs, stamps):
+        """img_callback for every member with a frame; returns (results, restarts) arrays (0 / 1 / 2 per member)."""
+        active, ptrs, keep, stride, dev = self._pointers(imgs)
+        t = np.ascontiguousarray(stamps, np.float64)
+        res, rst = np.zeros(self.n, np.int32), np.zeros(self.n, np.int32)
+        self._check(self.lib.vt_batch_node_image(self.h, _ptr(active), ptrs, stride, _ptr(t), dev, _ptr(res), _ptr(rst)))
+        return res, rst
+
+    def timing(self):
+        ms, k = C.c_float(0), C.c_int(0)
+        self.lib.vt_batch_last_timing(self.h, C.byref(ms), C.byref(k))
+        return ms.value, k.value
+
+    def set_profile(self, on):
+        self.lib.vt_batch_set_profile(self.h, int(on))
+
+    def kernel_times(self):
+        ms, cnt = np.zeros(6), np.zeros(6, np.int32)
+        self.lib.vt_batch_kernel_times(self.h, _ptr(ms), _ptr(cnt))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(FeatureTracker.KERNEL_GROUPS)}
