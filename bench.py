@@ -4,16 +4,22 @@
 A "step" is one published (10 Hz) frame of one sequence, fully processed: the two 752x480 camera images that
 arrive in that interval go through FeatureTracker::readImage (the second one publishes), the ~20 IMU samples
 through processIMU, the feature message through Estimator::processImage (triangulate, 8-iteration dogleg solve,
-marginalisation, slide).  Workload = BASELINE.json configs[1]: one synthetic EuRoC-shaped sequence per GPU
-(weak scaling: rank r runs sequence seed r).  Inputs are synthetic (harness/synth.py), no dataset is read.
+marginalisation, slide).  Inputs are synthetic (harness/synth.py), no dataset is read.
+
+Workloads (BASELINE.json configs):
+  N = 1 (default)   configs[1]: one sequence on the GPU (the headline line); the same line carries a "c3" object =
+                    configs[2], 64 independent sequences on the same GPU through the batched path
+  N > 1 (torchrun)  configs[4]'s share per GPU: 64 sequences per rank (512 on 8 GPUs), no data-path collective
+  --config c3       emit the configs[2] line as the main line on one GPU
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
-  python bench.py --impl reference ...                            the CPU oracle port of the reference path
-Under torchrun (N > 1) every rank runs one sequence; rank 0 prints ONE JSON line.
+  python bench.py --impl reference ...                            the CPU path: cv2 (OpenCV) tracker twin + oracle estimator
+Under torchrun (N > 1) rank 0 prints ONE JSON line.
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import sys
@@ -21,10 +27,6 @@ import threading
 import time
 
 import numpy as np
-
-# Concurrent sequences use two CUDA streams each; the default of 8 hardware work queues would alias them onto each other
-# (false serialisation).  Must be set before the CUDA context exists.
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
@@ -34,9 +36,12 @@ from harness import synth, pipeline  # noqa: E402
 METRIC = "frames/sec (tracker+BA) at 752x480, 10-KF window, 150 feats; ATE vs ref"
 WORKLOAD = ("configs[1]: single 752x480 synthetic sequence per GPU, 10-keyframe window, 150 features, 200 Hz IMU, "
             "fp64 Jacobians")
+WORKLOAD_BATCH = ("configs[2]/[4]: {s} independent 752x480 synthetic sequences per GPU ({d} distinct trajectories/scenes, "
+                  "replicated), 10-keyframe window, 150 features, 200 Hz IMU, fp64 Jacobians, batched launches")
 INIT_PUBS = 12           # published frames consumed before the window is full and seeded (estimator goes NON_LINEAR)
 ALGO_BYTES_IMAGE = 1_319_760   # compulsory front-end traffic per input image
 ALGO_BYTES_SOLVE = 233_000     # back-end inputs+outputs per solve at C1
+SEQS_PER_GPU = 64
 
 
 def sequence_inputs(seed, n_pub):
@@ -291,27 +296,38 @@ def run_ours_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, host_images
     return out
 
 
-def run_replay_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, n_seq, host_images=False, flush=None, sync_cb=None):
-    """n_seq replicas of the sequence driven by the native replay driver (include/vinsb200/replay.h: the reference's two
-    node loops in C++, one thread pair per sequence), all concurrently on one GPU.  The timed region is ONE vr_advance
-    call of `steps` published frames per sequence, bracketed like the single-sequence pass.  n_seq = 1 is the plain
-    single-sequence pipeline without any Python in the loop."""
+def distinct_inputs(first_seed, n_distinct, n_pub):
+    """Rendered frames + IMU of n_distinct sequences (seeds first_seed ...), enough for n_pub published frames each."""
+    return [sequence_inputs(first_seed + d, n_pub) for d in range(n_distinct)]
+
+
+def run_batch_pass(inputs, n_seq, n_init, warmup, steps, device, host_images=False, flush=None, sync_cb=None, profile=False,
+                   clocks=None):
+    """n_seq sequences on one GPU through the batched path (vt_batch / ve_batch / vr_open_batch): member k runs the
+    distinct sequence k % len(inputs).  One tracker loop and one estimator loop for all members, one launch chain per
+    step.  The timed region is ONE vr_advance call of `steps` published frames per member."""
     import torch
-    from vins_mono_b200 import ReplaySession
-    t_imu, acc, gyr = imu
-    pairs = [make_gpu_pair(device) for _ in range(n_seq)]
-    seed = pipeline.gt_seed_rows(seq, ts)
-    for _, est in pairs:
-        est.set_seed(seed, seq.ba, seq.bg)
-    d_imgs = None
-    if host_images:
-        images = dict(images=imgs)
-    else:
-        d_imgs = torch.from_numpy(np.array(imgs, copy=True)).to(f"cuda:{device}")
-        images = dict(images=d_imgs.data_ptr(), shape=imgs.shape)
-    seqs = [dict(stamps=ts, imu_t=t_imu, acc=acc, gyr=gyr, **images) for _ in range(n_seq)]
-    ses = ReplaySession([p[0] for p in pairs], [p[1] for p in pairs], seqs)
-    gate = SoloGate(device, flush, sync_cb)
+    from vins_mono_b200 import TrackerBatch, EstimatorBatch, ReplaySession
+    tb = TrackerBatch(n_seq, device=device, **synth.tracker_config_dict())
+    eb = EstimatorBatch(n_seq, tic=synth.TIC, ric=synth.RIC, device=device)
+    if profile:
+        tb.set_profile(True)
+        eb.set_profile(True)
+    keep, seqs = [], []
+    dev_imgs = {}
+    for k in range(n_seq):
+        d = k % len(inputs)
+        seq, ts, imgs, (t_imu, acc, gyr) = inputs[d]
+        eb.members[k].set_seed(pipeline.gt_seed_rows(seq, ts), seq.ba, seq.bg)
+        if host_images:
+            images = dict(images=imgs)
+        else:
+            if d not in dev_imgs:
+                dev_imgs[d] = torch.from_numpy(np.array(imgs, copy=True)).to(f"cuda:{device}")
+            images = dict(images=dev_imgs[d].data_ptr(), shape=imgs.shape)
+        seqs.append(dict(stamps=ts, imu_t=t_imu, acc=acc, gyr=gyr, **images))
+    ses = ReplaySession(tb, eb, seqs)
+    gate = SoloGate(device, flush, sync_cb, clocks)
     ses.advance(n_init + warmup)
     before = [ses.stats(k) for k in range(n_seq)]
     gate.begin()
@@ -319,24 +335,50 @@ def run_replay_pass(seq, ts, imgs, imu, n_init, warmup, steps, device, n_seq, ho
     region_ms = gate.end()
     after = [ses.stats(k) for k in range(n_seq)]
     trajs = [ses.trajectory(k) for k in range(n_seq)]
-    infos = [p[1].info() for p in pairs]
+    infos = [m.info() for m in eb.members]
+    out = dict(frames=frames, region_ms=region_ms, fps=frames / (region_ms / 1e3) if region_ms else 0.0,
+               launches=sum(a_["launches"] - b_["launches"] for a_, b_ in zip(after, before)),
+               h2d=sum(a_["h2d"] - b_["h2d"] for a_, b_ in zip(after, before)),
+               d2h=sum(a_["d2h"] - b_["d2h"] for a_, b_ in zip(after, before)), trajs=trajs, infos=infos)
+    if profile:
+        out["trk_k"], out["est_k"] = tb.kernel_times(), eb.kernel_times()
     ses.close()
-    for trk, est in pairs:
-        trk.close()
-        est.close()
-    del d_imgs
-    return dict(frames=frames, region_ms=region_ms, fps=frames / (region_ms / 1e3) if region_ms else 0.0,
-                launches=sum(a["launches"] - b["launches"] for a, b in zip(after, before)),
-                h2d=sum(a["h2d"] - b["h2d"] for a, b in zip(after, before)), d2h=sum(a["d2h"] - b["d2h"] for a, b in zip(after, before)),
-                trajs=trajs, infos=infos, final_cost=[i["final_cost"] for i in infos])
+    tb.close()
+    eb.close()
+    del dev_imgs
+    return out
 
 
-def run_reference_pass(seq, ts, imgs, imu, n_init, warmup, steps):
-    """The CPU port of the reference path (oracle tracker + estimator twins) on two host threads, tracker and estimator
-    coupled by a queue like the reference's two nodes (each hot loop single-threaded: the tracker node is, and Ceres
-    runs with num_threads = 1)."""
+def _cv2_tracker_class():
+    """The cv2-backed twin of FeatureTracker::readImage + img_callback that generated tests/golden/frontend_track.npz
+    (the reference's front end = OpenCV's own kernels); None when cv2 is not importable."""
+    try:
+        spec = importlib.util.spec_from_file_location("make_frontend_golden", os.path.join(ROOT, "tests", "golden", "make_frontend_golden.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        import cv2
+        cv2.setNumThreads(1)        # the reference's tracker node is single threaded
+        cv2.setUseOptimized(True)   # the library at its real speed (the golden vectors use the baseline mode for bit-reproducibility)
+        return mod.Cv2Tracker
+    except Exception:
+        return None
+
+
+def run_reference_pass(seq, ts, imgs, imu, n_init, warmup, steps, front="cv2"):
+    """The reference's CPU path on two host threads coupled by a queue like its two nodes (each hot loop single-threaded:
+    the tracker node is, and Ceres runs with num_threads = 1).  front = "cv2": OpenCV's own CLAHE / LK / goodFeaturesToTrack /
+    findFundamentalMat behind the Python twin of readImage; "port": the oracle's scalar C++ restatement.  Back end: the oracle
+    estimator (oracle/, CPU restatement of Estimator + the Ceres dogleg/DENSE_SCHUR loop, tridiagonal-QL eigen-solver)."""
     import orc
-    trk = orc.OracleTracker(synth.tracker_config_dict())
+    cv2_cls = _cv2_tracker_class() if front == "cv2" else None
+    if cv2_cls is not None:
+        trk = cv2_cls(synth.tracker_config_dict())
+        node_image = lambda img, t: trk.node_image(np.ascontiguousarray(img), t)  # noqa: E731
+        used = "cv2"
+    else:
+        trk = orc.OracleTracker(synth.tracker_config_dict())
+        node_image = lambda img, t: trk.node_image(img, t)[0]  # noqa: E731
+        used = "port"
     est = orc.OracleEstimator(orc.be_config())
     est.set_fast_eigen(True)  # tridiagonal QL (the reference's Eigen solver class) instead of the parity tests' Jacobi
     feeder = pipeline.ImuFeeder(*imu)
@@ -344,12 +386,15 @@ def run_reference_pass(seq, ts, imgs, imu, n_init, warmup, steps):
     n_pub = n_init + warmup + steps
     traj_t, traj_p = [], []
     cursor = [0]
+    t_front = [0.0]
 
     def produce():
         r = 0
+        t0 = time.perf_counter()
         while r != 2 and cursor[0] < len(ts):
-            r, _ = trk.node_image(imgs[cursor[0]], float(ts[cursor[0]]))
+            r = node_image(imgs[cursor[0]], float(ts[cursor[0]]))
             cursor[0] += 1
+        t_front[0] += time.perf_counter() - t0
         if r != 2:
             return None
         ids, d = pipeline.oracle_feature_message(trk.result())
@@ -357,14 +402,17 @@ def run_reference_pass(seq, ts, imgs, imu, n_init, warmup, steps):
 
     stage = TwoStage(produce, n_init + warmup, n_pub)
     pubs, first_msg, n_timed, t0 = 0, True, 0, None
+    t_back = 0.0
     while pubs < n_pub:
         if pubs == n_init + warmup:
             t0 = time.perf_counter()
+            t_front[0] = 0.0
             stage.go()
         msg = stage.get()
         if msg is None:
             break
         stamp, ids, d = msg
+        tb0 = time.perf_counter()
         if first_msg:
             first_msg = False
         else:
@@ -372,6 +420,7 @@ def run_reference_pass(seq, ts, imgs, imu, n_init, warmup, steps):
             est.processImage(ids, d, stamp)
         if t0 is not None:
             n_timed += 1
+            t_back += time.perf_counter() - tb0
         if est.info()["solver_flag"] == 1:
             st, _ = est.states()
             traj_t.append(stamp)
@@ -379,7 +428,40 @@ def run_reference_pass(seq, ts, imgs, imu, n_init, warmup, steps):
         pubs += 1
     total_ms = (time.perf_counter() - t0) * 1e3 if t0 is not None else 0.0
     stage.go()
-    return dict(times=[total_ms / max(n_timed, 1)] * n_timed, traj_t=traj_t, traj_p=traj_p)
+    return dict(times=[total_ms / max(n_timed, 1)] * n_timed, traj_t=traj_t, traj_p=traj_p, front=used,
+                front_ms_per_frame=1e3 * t_front[0] / max(n_timed, 1), back_ms_per_frame=1e3 * t_back / max(n_timed, 1))
+
+
+def _reference_worker(args):
+    seed, n_init, warmup, steps, front = args
+    seq, ts, imgs, imu = sequence_inputs(seed, n_init + warmup + steps)
+    r = run_reference_pass(seq, ts, imgs, imu, n_init, warmup, steps, front)
+    return dict(n=len(r["times"]), total_s=sum(r["times"]) / 1e3, front=r["front"], front_ms=r["front_ms_per_frame"],
+                back_ms=r["back_ms_per_frame"], ate=pipeline.ate_rmse(seq, r["traj_t"], r["traj_p"]) if len(r["traj_t"]) > 3 else None)
+
+
+def run_reference_parallel(seeds, n_init, warmup, steps, front):
+    """One CPU pipeline (2 threads) per sequence, as many at a time as the host has core pairs; frames/s = all frames over the
+    wall time of the whole pool."""
+    import multiprocessing as mp
+    procs = max(1, min(len(seeds), (os.cpu_count() or 2) // 2))
+    for sd in seeds:  # render (or load from the cache) before forking the workers
+        sequence_inputs(sd, n_init + warmup + steps)
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(procs) as pool:
+        res = pool.map(_reference_worker, [(sd, n_init, warmup, steps, front) for sd in seeds], chunksize=1)
+    wall = time.perf_counter() - t0
+    return res, wall, procs
+
+
+def _oracle_traj_worker(args):
+    """Full CPU oracle pipeline (tracker + estimator twins, Jacobi eigen-solver: the parity configuration) on one sequence."""
+    seed, n_pub = args
+    import orc
+    seq, ts, imgs, imu = sequence_inputs(seed, n_pub)
+    trk, est = orc.OracleTracker(synth.tracker_config_dict()), orc.OracleEstimator(orc.be_config())
+    r = pipeline.run_vio(seq, trk, est, len(ts), messages=list(pipeline.feature_messages(trk, ts, imgs))[:n_pub])
+    return np.asarray(r["t"]), np.asarray(r["P"])
 
 
 def cpu_model():
@@ -392,47 +474,136 @@ def cpu_model():
     return "unknown"
 
 
+def kernel_table(trk_k, est_k):
+    kt = {}
+    for name, (ms, cnt) in list(trk_k.items()) + list(est_k.items()):
+        if cnt:
+            kt[name] = {"total_ms": ms, "launches": cnt, "avg_us": 1e3 * ms / cnt}
+    return kt
+
+
+def roofline_object(kt, n_solves, n_images, units_per_launch, peak, peaks_found, note):
+    """Dominant kernel by accumulated device time of a profile pass.  Algorithmic bytes per launch = SURVEY 8(d)'s per-unit
+    figure (per image for front-end kernels, per solve for BA kernels) x units one launch serves / launches per unit."""
+    fe = ("clahe", "pyrdown", "lk_track", "mask_discs", "min_eig", "gftt_tail")
+    per_kernel = {}
+    for k, v in kt.items():
+        if k in fe:
+            algo = ALGO_BYTES_IMAGE * n_images * units_per_launch / v["launches"]
+        else:
+            algo = ALGO_BYTES_SOLVE * n_solves * units_per_launch / v["launches"]
+        per_kernel[k] = dict(v, algorithmic_bytes_per_launch=algo, achieved_gbs=algo / (v["avg_us"] * 1e-6) / 1e9,
+                             frac=algo / (v["avg_us"] * 1e-6) / 1e9 / peak)
+    dominant = max(kt, key=lambda k: kt[k]["total_ms"])
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(dominant, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    dk = per_kernel[dominant]
+    return {"bound": "hbm", "kernel": dominant, "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dk["frac"],
+            "traffic": traffic if units_per_launch == 1 else None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks_found else "fallback 6650 GB/s",
+            "algorithmic_bytes_per_launch": dk["algorithmic_bytes_per_launch"], "avg_launch_us": dk["avg_us"],
+            "profiled_solves": n_solves, "profiled_images": n_images, "sequences_per_launch": units_per_launch,
+            "note": note, "kernels": per_kernel}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="auto", choices=["auto", "c2", "c3"],
+                    help="auto: configs[1] on one GPU (with a c3 object), configs[4]'s share (64 sequences per GPU) under torchrun")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-frames", type=int, default=200,
+    ap.add_argument("--cpu-frames", type=int, default=150,
                     help="published frames of the CPU-baseline sample inside the b200 arm (~10 s of CPU work)")
-    ap.add_argument("--batch", type=int, default=16,
-                    help="supplementary pass: this many concurrent replicas of the sequence per GPU (0 = skip)")
+    ap.add_argument("--seqs-per-gpu", type=int, default=SEQS_PER_GPU, help="members of the batched workload (configs[2]/[4])")
+    ap.add_argument("--distinct", type=int, default=16, help="distinct rendered sequences behind the batch members")
+    ap.add_argument("--no-c3", action="store_true", help="skip the configs[2] object of the single-GPU line")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
-    n_pub = INIT_PUBS + warmup + a.steps
+    batched = a.config == "c3" or (a.config == "auto" and world > 1)
+    S = a.seqs_per_gpu
+    n_distinct = max(1, min(a.distinct, S))
 
     if a.impl == "reference":
         if rank != 0:
             return
-        seq, ts, imgs, imu = sequence_inputs(0, n_pub)
-        r = run_reference_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, a.steps)
-        total_s = sum(r["times"]) / 1e3
-        fps = len(r["times"]) / total_s
-        sample = f"{len(r['times'])} published frames (2 images + 1 window solve each) of sequence seed 0 after {INIT_PUBS} init + {warmup} warm-up frames"
+        front = "cv2" if _cv2_tracker_class() is not None else "port"
+        if not batched:
+            seq, ts, imgs, imu = sequence_inputs(0, INIT_PUBS + warmup + a.steps)
+            r = run_reference_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, a.steps, front)
+            total_s, n = sum(r["times"]) / 1e3, len(r["times"])
+            fps, cores = n / total_s, 2
+            sample = (f"{n} published frames (2 images + 1 window solve each) of sequence seed 0 after {INIT_PUBS} init + {warmup} "
+                      f"warm-up frames")
+            extra = {"front_ms_per_frame": r["front_ms_per_frame"], "back_ms_per_frame": r["back_ms_per_frame"]}
+            workload, spg = WORKLOAD, 1
+            ate = pipeline.ate_rmse(seq, r["traj_t"], r["traj_p"]) if len(r["traj_t"]) > 3 else None
+        else:
+            # the batched workload on the host: as many sequences at a time as there are core pairs, each a bounded sample
+            n_seq_total = S * max(a.gpus, 1)
+            procs_cap = max(1, (os.cpu_count() or 2) // 2)
+            seeds = list(range(min(n_seq_total, procs_cap, n_distinct * max(a.gpus, 1))))
+            steps = min(a.steps, 20)
+            res, wall, procs = run_reference_parallel(seeds, INIT_PUBS, warmup, steps, front)
+            n = sum(x["n"] for x in res)
+            # the pool's wall time contains start-up and the untimed init frames: use the slowest worker's timed region
+            total_s = max(x["total_s"] for x in res)
+            fps, cores = n / total_s, 2 * procs
+            sample = (f"{len(seeds)} of the {n_seq_total} sequences concurrently ({procs} processes x 2 threads on {os.cpu_count()} "
+                      f"host cores), {steps} published frames each after {INIT_PUBS} init + {warmup} warm-up frames; aggregate = all "
+                      f"frames / slowest pipeline's timed region")
+            extra = {"front_ms_per_frame": float(np.mean([x["front_ms"] for x in res])),
+                     "back_ms_per_frame": float(np.mean([x["back_ms"] for x in res])), "pool_wall_s": wall}
+            workload, spg = WORKLOAD_BATCH.format(s=S, d=n_distinct), S
+            ates = [x["ate"] for x in res if x["ate"] is not None]
+            ate = float(np.mean(ates)) if ates else None
         print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": len(r["times"]),
-            "warmup": warmup, "ms_per_step": 1e3 * total_s / len(r["times"]), "higher_is_better": True, "scaling": "weak",
+            "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": warmup, "ms_per_step": 1e3 / fps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sequences_per_gpu": 1,
-                       "arm": "configs[0]: the same sequence on the host CPU, 1 stream (tracker thread + estimator thread)"},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 2, "kind": "port", "sample": sample, "cpu": cpu_model(),
-                             "note": "CPU restatement of the reference path (oracle/), not Ceres/OpenCV; no wall-clock solver cap"},
+            "config": {"workload": workload, "sequences_per_gpu": spg,
+                       "arm": "the same workload on the host CPU: per sequence one tracker thread + one estimator thread"},
+            "cpu_baseline": dict({"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample, "cpu": cpu_model(),
+                                  "front_end": "OpenCV " + __import__("cv2").__version__ + " (cv2 wheel) behind the Python twin of readImage, 1 thread"
+                                  if front == "cv2" else "oracle/ scalar C++ restatement of the OpenCV routines (cv2 not importable)",
+                                  "back_end": "oracle/ CPU restatement of Estimator + Ceres dogleg/DENSE_SCHUR (not Ceres itself), own "
+                                              "tridiagonal-QL eigen-solver, no wall-clock solver cap"}, **extra),
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "ate_rmse_m": pipeline.ate_rmse(seq, r["traj_t"], r["traj_p"]) if len(r["traj_t"]) > 3 else None,
+            "ate_rmse_m": ate,
         }))
         return
 
     from vins_mono_b200 import shard
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+
     # frames are rendered (fork pool) before this process touches CUDA; the CPU-baseline sample needs a longer sequence
-    cpu_frames = max(a.steps, a.cpu_frames) if (not a.no_cpu_baseline and world == 1) else a.steps
-    seq, ts, imgs, imu = sequence_inputs(shard.sequences_of_rank(rank, world, 1)[0], INIT_PUBS + warmup + cpu_frames)
+    cpu_frames = max(a.steps, a.cpu_frames) if (not a.no_cpu_baseline and world == 1 and not batched) else a.steps
+    want_c3 = (batched or not a.no_c3)
+    c3_steps = min(a.steps, 20)
+    batch_inputs = None
+    if want_c3:
+        first_seed = 100 + shard.sequences_of_rank(rank, world, S)[0]
+        batch_inputs = distinct_inputs(first_seed, n_distinct, INIT_PUBS + warmup + c3_steps)
+    if not batched:
+        seq, ts, imgs, imu = sequence_inputs(shard.sequences_of_rank(rank, world, 1)[0], INIT_PUBS + warmup + cpu_frames)
+    # the oracle trajectories of the distinct batch sequences (parity of every member), computed before CUDA exists
+    oracle_traj = None
+    if want_c3 and rank == 0 and not a.no_cpu_baseline:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(n_distinct, max(1, (os.cpu_count() or 2) - 2))) as pool:
+            oracle_traj = pool.map(_oracle_traj_worker, [(100 + shard.sequences_of_rank(rank, world, S)[0] + d, INIT_PUBS + warmup + c3_steps)
+                                                          for d in range(n_distinct)], chunksize=1)
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the vinsb200 library has no CPU path")
@@ -444,19 +615,92 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=f"cuda:{local}")  # 256 MB > 126 MB L2
 
-    # untimed shake-out pass (first CUDA context / module load, pinned allocations)
-    run_ours_pass(seq, ts, imgs, imu, INIT_PUBS, 0, 2, local, host_images=True)
-
     def barrier():
         torch.cuda.synchronize(local)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(local)
 
+    rank_barrier = (lambda: dist.barrier()) if world > 1 else None
+
+    def batch_object(with_profile):
+        """configs[2] on this GPU: device-resident pass (value), host-image pass (e2e), optional profile pass + parity."""
+        run_batch_pass(batch_inputs, min(S, 4), INIT_PUBS, 0, 2, local)  # shake-out
+        barrier()
+        clk_b = ClockSampler(local)
+        clk_b.start()
+        rb = run_batch_pass(batch_inputs, S, INIT_PUBS, warmup, c3_steps, local, host_images=False, flush=flush, sync_cb=rank_barrier,
+                            clocks=clk_b)
+        barrier()
+        clocks_b = clk_b.stop()
+        barrier()
+        re_ = run_batch_pass(batch_inputs, S, INIT_PUBS, warmup, c3_steps, local, host_images=True, flush=flush, sync_cb=rank_barrier)
+        barrier()
+        obj = {"sequences_per_gpu": S, "distinct_sequences": n_distinct, "frames": rb["frames"], "ms_region": rb["region_ms"],
+               "h2d_bytes_per_step": re_["h2d"] / max(re_["frames"], 1), "d2h_bytes_per_step": re_["d2h"] / max(re_["frames"], 1),
+               "gpu_launches": rb["launches"], "clocks": clocks_b}
+        if with_profile:
+            pr = run_batch_pass(batch_inputs, S, INIT_PUBS, 2, 6, local, profile=True)
+            kt = kernel_table(pr["trk_k"], pr["est_k"])
+            n_solves = kt.get("ba_finish", {}).get("launches", 1)
+            n_images = kt.get("pyrdown", {}).get("launches", 3) // 3
+            obj["roofline"] = roofline_object(kt, n_solves, n_images, S, peak, bool(peaks),
+                                              "batched launches: one launch serves every member, algorithmic bytes scale with the batch")
+        # parity: every member against the CPU oracle's trajectory of its sequence, and the replicas among themselves
+        if oracle_traj is not None:
+            worst, worst_rep, n_cmp = 0.0, 0.0, 0
+            for k, (tt, pp) in enumerate(rb["trajs"]):
+                ot, op = oracle_traj[k % n_distinct]
+                m = min(len(tt), len(ot))
+                if m and np.array_equal(tt[:m], ot[:m]):
+                    worst = max(worst, float(np.abs(pp[:m] - op[:m]).max()))
+                    n_cmp += 1
+                base = rb["trajs"][k % n_distinct][1]
+                mm = min(len(pp), len(base))
+                if mm:
+                    worst_rep = max(worst_rep, float(np.abs(pp[:mm] - base[:mm]).max()))
+            obj["parity"] = {"members_compared": n_cmp, "max_position_dev_vs_oracle_m": worst, "tolerance_m": 3e-4,
+                             "ok": bool(n_cmp == len(rb["trajs"]) and worst <= 3e-4), "max_replica_spread_m": worst_rep}
+        ates = []
+        for k, (tt, pp) in enumerate(rb["trajs"]):
+            if len(tt) > 3:
+                ates.append(pipeline.ate_rmse(batch_inputs[k % n_distinct][0], tt, pp))
+        obj["ate_rmse_m_mean"] = float(np.mean(ates)) if ates else None
+        return rb, re_, obj
+
+    if batched:
+        rb, re_, obj = batch_object(with_profile=(rank == 0))
+        fps_dev, t_dev, n_frames = shard.aggregate_rate(rb["region_ms"], rb["frames"], device=f"cuda:{local}")
+        fps_e2e, t_e2e, _ = shard.aggregate_rate(re_["region_ms"], re_["frames"], device=f"cuda:{local}")
+        launches = torch.tensor([float(rb["launches"])], device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(launches)
+        if rank == 0:
+            print(json.dumps({
+                "impl": "b200", "metric": METRIC, "value": fps_dev, "unit": "frames/s", "n_gpus": world, "steps": c3_steps, "warmup": warmup,
+                "ms_per_step": 1e3 * t_dev / c3_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD_BATCH.format(s=S, d=n_distinct), "sequences_per_gpu": S, "sequences_total": S * world,
+                           "step": f"one step = one published frame of every sequence ({S * world} frames); ms_per_step is the time of such a step",
+                           "pipelining": "one tracker-batch host thread and one estimator-batch host thread coupled by a depth-2 queue",
+                           "l2": "L2 flushed (256 MB write) at the start of the timed region; a step reads 2 x 64 frames (46 MB) that were never touched since upload",
+                           "timing": "one CUDA-event pair around the K steps, device synchronised (and ranks barriered) on both sides; max over ranks",
+                           "seeded_from_ground_truth": True},
+                "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": 1e3 * t_e2e / c3_steps,
+                        "h2d_bytes_per_step": obj["h2d_bytes_per_step"] * S * world, "d2h_bytes_per_step": obj["d2h_bytes_per_step"] * S * world},
+                "gpu_launches": int(launches.item()), "roofline": obj.get("roofline"), "cpu_baseline": None, "clocks": obj["clocks"],
+                "parity": obj.get("parity"), "ate_rmse_m": obj["ate_rmse_m_mean"],
+            }))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- configs[1]: one sequence ------------------------------------------------------------------------------------
+    # untimed shake-out pass (first CUDA context / module load, pinned allocations)
+    run_ours_pass(seq, ts, imgs, imu, INIT_PUBS, 0, 2, local, host_images=True)
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
-    rank_barrier = (lambda: dist.barrier()) if world > 1 else None
     res_dev = run_ours_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, a.steps, local, host_images=False, flush=flush, sync_cb=rank_barrier,
                             clocks=clocks)
     barrier()
@@ -471,75 +715,46 @@ def main():
 
     fps_dev, t_dev = agg(res_dev)
     fps_e2e, t_e2e = agg(res_e2e)
-    launches = torch.tensor([float(res_dev["launches"])], device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(launches)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
 
     # ---- roofline of the dominant kernel, measured live with CUDA events in a profile pass
     prof = run_ours_pass(seq, ts, imgs, imu, INIT_PUBS, 2, 10, local, host_images=False, profile=True)
-    kt = {}
-    for name, (ms, cnt) in list(prof["trk_k"].items()) + list(prof["est_k"].items()):
-        if cnt:
-            kt[name] = {"total_ms": ms, "launches": cnt, "avg_us": 1e3 * ms / cnt}
-    n_prof_frames = 12
-    dominant = max(kt, key=lambda k: kt[k]["total_ms"])
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    per_frame = {k: v["launches"] / n_prof_frames for k, v in kt.items()}
-    # algorithmic bytes per launch of the dominant kernel: the per-unit figure of SURVEY §8(d)
-    # divided by the launches that unit needs
-    if dominant in ("clahe", "pyrdown", "lk_track", "mask_discs", "min_eig", "gftt_tail"):
-        algo = 2 * ALGO_BYTES_IMAGE / max(per_frame[dominant], 1e-9)
-    else:
-        algo = ALGO_BYTES_SOLVE / max(per_frame[dominant], 1e-9)
-    avg_s = kt[dominant]["avg_us"] * 1e-6
-    achieved = algo / avg_s / 1e9
-    traffic = None
-    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(dominant, {}).get("dram_bytes_per_launch")
-    except (OSError, ValueError):
-        pass
-    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": algo, "avg_launch_us": kt[dominant]["avg_us"],
-                "note": "single-sequence step: every kernel is latency/launch bound, not HBM bound (see DESIGN.md)",
-                "kernels": kt}
+    kt = kernel_table(prof["trk_k"], prof["est_k"])
+    n_solves = kt.get("ba_finish", {}).get("launches", 1)       # one double2vector launch per solve
+    n_images = kt.get("pyrdown", {}).get("launches", 3) // 3      # three pyramid levels per image
+    roofline = roofline_object(kt, n_solves, n_images, 1, peak, bool(peaks),
+                               "single-sequence step: every kernel is latency/launch bound, not HBM bound (see DESIGN.md)")
 
-    # ---- supplementary: concurrent sequences on the same GPU (BASELINE.json configs[2] direction; not the headline)
-    batch = None
-    if a.batch > 1 and world == 1:
-        rb = run_replay_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, min(a.steps, 30), local, a.batch, flush=flush)
-        spread = max(abs(c - rb["final_cost"][0]) for c in rb["final_cost"]) / max(1.0, abs(rb["final_cost"][0]))
-        r1 = run_replay_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, min(a.steps, 30), local, 1, flush=flush)
-        batch = {"sequences_per_gpu": a.batch, "value": rb["fps"], "unit": "frames/s", "frames": rb["frames"],
-                 "ms_region": rb["region_ms"], "gpu_launches": rb["launches"], "replica_final_cost_rel_spread": spread,
-                 "single_sequence_same_driver": {"value": r1["fps"], "unit": "frames/s", "frames": r1["frames"]},
-                 "spread_note": "replicas see identical inputs; they differ only through the order of the fp64 atomic adds "
-                                "of the Hessian assembly (not bit-reproducible run to run, same as a single sequence)",
-                 "note": "replicas of sequence 0 (device-resident frames) driven by the native replay driver "
-                         "(vinsb200/replay.h: one tracker thread + one estimator thread per sequence); aggregate frames/s "
-                         "over one shared timed region"}
+    # ---- configs[2]: 64 sequences on this GPU through the batched path
+    c3 = None
+    if want_c3:
+        rb, re_, c3 = batch_object(with_profile=True)
+        c3.update({"value": rb["fps"], "unit": "frames/s", "e2e_value": re_["fps"], "steps": c3_steps,
+                   "vs_single_sequence": rb["fps"] / fps_dev if fps_dev else None,
+                   "note": "BASELINE configs[2]: device-resident frames for value, host frames for e2e_value; one tracker-batch and one "
+                           "estimator-batch host thread; same timing bracket as the headline"})
 
     # ---- CPU baseline on this box's host cores (bounded sample of the same workload)
     cpu_b = None
     ate_ref = ate_same = None
-    if not a.no_cpu_baseline and world == 1:
-        rr = run_reference_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, cpu_frames)
+    if not a.no_cpu_baseline:
+        rr = run_reference_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, cpu_frames, "cv2")
         tot = sum(rr["times"]) / 1e3
         cpu_b = {"value": len(rr["times"]) / tot, "unit": "frames/s", "cores": 2, "kind": "port", "cpu": cpu_model(),
+                 "front_end": rr["front"], "front_ms_per_frame": rr["front_ms_per_frame"], "back_ms_per_frame": rr["back_ms_per_frame"],
                  "sample": f"{len(rr['times'])} published frames of the same sequence after the same {INIT_PUBS} init + {warmup} "
-                           f"warm-up frames (oracle tracker + estimator twins on two threads, {tot:.1f} s)"}
-        nn = min(len(rr["traj_t"]), len(res_dev["traj_t"]))
+                           f"warm-up frames (front end: {'OpenCV (cv2) twin of readImage' if rr['front'] == 'cv2' else 'oracle scalar port'}, "
+                           f"back end: oracle estimator; two threads, {tot:.1f} s)"}
+        if rr["front"] == "cv2":  # the all-port figure beside it (scalar C++ tracker), shorter sample
+            rp = run_reference_pass(seq, ts, imgs, imu, INIT_PUBS, warmup, min(cpu_frames, 60), "port")
+            cpu_b["port_front_end_value"] = len(rp["times"]) / (sum(rp["times"]) / 1e3)
+            cpu_b["port_front_ms_per_frame"] = rp["front_ms_per_frame"]
+            # trajectories are compared against the port: its tracker is bit-identical to the GPU tracker
+            rr_cmp = rp
+        else:
+            rr_cmp = rr
+        nn = min(len(rr_cmp["traj_t"]), len(res_dev["traj_t"]))
         if nn > 3:  # the same frames of both trajectories, so that the two ATE figures are comparable
-            ate_ref = pipeline.ate_rmse(seq, rr["traj_t"][:nn], rr["traj_p"][:nn])
+            ate_ref = pipeline.ate_rmse(seq, rr_cmp["traj_t"][:nn], rr_cmp["traj_p"][:nn])
             ate_same = pipeline.ate_rmse(seq, res_dev["traj_t"][:nn], res_dev["traj_p"][:nn])
     ate = pipeline.ate_rmse(seq, res_dev["traj_t"], res_dev["traj_p"]) if len(res_dev["traj_t"]) > 3 else None
 
@@ -552,17 +767,16 @@ def main():
                    "pipelining": "tracker and estimator handles driven from two host threads coupled by a depth-2 queue (the "
                                  "reference's two nodes); the timed region starts with both idle and ends with both drained",
                    "l2": "L2 flushed (256 MB write) at the start of the timed region; every step reads two images that were never touched since upload",
-                   "timing": "one CUDA-event pair around the K steps, device synchronised (and ranks barriered) on both sides; max over ranks"},
+                   "timing": "one CUDA-event pair around the K steps, device synchronised (and ranks barriered) on both sides; max over ranks",
+                   "seeded_from_ground_truth": True},
         "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": 1e3 * t_e2e / k,
                 "h2d_bytes_per_step": res_e2e["h2d"] / k, "d2h_bytes_per_step": res_e2e["d2h"] / k},
-        "gpu_launches": int(launches.item()),
-        "roofline": roofline, "cpu_baseline": cpu_b, "clocks": clk, "batch": batch,
+        "gpu_launches": int(res_dev["launches"]),
+        "roofline": roofline, "cpu_baseline": cpu_b, "clocks": clk, "c3": c3,
         "ate_rmse_m": ate, "ate_rmse_m_same_frames": ate_same, "ate_rmse_m_cpu_port": ate_ref,
         "ate_rel_diff": (abs(ate_same - ate_ref) / ate_ref) if ate_ref else None,
         "solver": res_dev["info"],
     }))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

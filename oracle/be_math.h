@@ -1,7 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  Small dense linear algebra used by the back-end restatement
 // (stands in for the Eigen calls of the reference; Eigen is not available offline).
 #pragma once
-#include "../vins_mono_b200/csrc/sym_eig.h"
 #include <algorithm>
 #include <cassert>
 #include <cmath>
@@ -281,28 +280,157 @@ inline void sym_eigen(const Mat& A, std::vector<double>& w, Mat& V) {
     V = Vs;
 }
 
-// Cross-check of the solver above: the tridiagonal-QL template that the CUDA marginalisation kernel instantiates
-// (vins_mono_b200/csrc/sym_eig.h; tred2 + tql2, the algorithm family of Eigen's SelfAdjointEigenSolver which the
-// reference calls at marginalization_factor.cpp:268, :283), run on one host thread.  The oracle itself keeps the
-// Jacobi solver: it is independent of the product code and resolves small eigenvalues of these graded matrices to
+// Second solver, used for the TIMED CPU baseline only (bench.py cpu_baseline / --impl reference): Householder
+// tridiagonalisation + implicit-shift QL (EISPACK tred2 / tql2 as published in Wilkinson & Reinsch, Handbook for Automatic
+// Computation II; the algorithm family of Eigen's SelfAdjointEigenSolver which the reference calls at
+// marginalization_factor.cpp:268, :283), written here from the published algorithm: independent of the product's kernel
+// template.  The parity tests keep the Jacobi solver above: it resolves small eigenvalues of these graded matrices to
 // relative accuracy, whereas QL/QR (the reference included) delivers them to eps*|A| only — which of the round-off
 // eigenvalues of the rank-deficient prior pass the reference's 1e-8 floor is therefore implementation noise, and it
 // bounds the achievable state parity at ~1e-5.
 inline void sym_eigen_ql(const Mat& A, std::vector<double>& w, Mat& V) {
-    const int n = A.r, ld = n | 1;
-    std::vector<double> v((size_t)n * ld, 0.0), d(n), e(n), cs(4 * (size_t)n), scal(16);
+    const int n = A.r;
+    V = Mat(n, n);
     for (int i = 0; i < n; i++)
-        for (int j = 0; j < n; j++) v[(size_t)i * ld + j] = 0.5 * (A(i, j) + A(j, i));
-    vb::sym_eig(vb::HostCtx(), v.data(), n, ld, d.data(), e.data(), cs.data(), scal.data());
+        for (int j = 0; j < n; j++) V(i, j) = 0.5 * (A(i, j) + A(j, i));
+    std::vector<double> d(n), e(n, 0.0);
+    // ---- tred2: reduce to tridiagonal form, accumulating the orthogonal transformation in V
+    for (int j = 0; j < n; j++) d[j] = V(n - 1, j);
+    for (int i = n - 1; i > 0; i--) {
+        double scale = 0.0, h = 0.0;
+        for (int k = 0; k < i; k++) scale += std::fabs(d[k]);
+        if (scale == 0.0) {
+            e[i] = d[i - 1];
+            for (int j = 0; j < i; j++) {
+                d[j] = V(i - 1, j);
+                V(i, j) = 0.0;
+                V(j, i) = 0.0;
+            }
+        } else {
+            for (int k = 0; k < i; k++) {
+                d[k] /= scale;
+                h += d[k] * d[k];
+            }
+            double f = d[i - 1];
+            double g = std::sqrt(h);
+            if (f > 0) g = -g;
+            e[i] = scale * g;
+            h -= f * g;
+            d[i - 1] = f - g;
+            for (int j = 0; j < i; j++) e[j] = 0.0;
+            for (int j = 0; j < i; j++) {
+                f = d[j];
+                V(j, i) = f;
+                g = e[j] + V(j, j) * f;
+                for (int k = j + 1; k <= i - 1; k++) {
+                    g += V(k, j) * d[k];
+                    e[k] += V(k, j) * f;
+                }
+                e[j] = g;
+            }
+            f = 0.0;
+            for (int j = 0; j < i; j++) {
+                e[j] /= h;
+                f += e[j] * d[j];
+            }
+            const double hh = f / (h + h);
+            for (int j = 0; j < i; j++) e[j] -= hh * d[j];
+            for (int j = 0; j < i; j++) {
+                f = d[j];
+                g = e[j];
+                for (int k = j; k <= i - 1; k++) V(k, j) -= (f * e[k] + g * d[k]);
+                d[j] = V(i - 1, j);
+                V(i, j) = 0.0;
+            }
+        }
+        d[i] = h;
+    }
+    for (int i = 0; i < n - 1; i++) {
+        V(n - 1, i) = V(i, i);
+        V(i, i) = 1.0;
+        const double h = d[i + 1];
+        if (h != 0.0) {
+            for (int k = 0; k <= i; k++) d[k] = V(k, i + 1) / h;
+            for (int j = 0; j <= i; j++) {
+                double g = 0.0;
+                for (int k = 0; k <= i; k++) g += V(k, i + 1) * V(k, j);
+                for (int k = 0; k <= i; k++) V(k, j) -= g * d[k];
+            }
+        }
+        for (int k = 0; k <= i; k++) V(k, i + 1) = 0.0;
+    }
+    for (int j = 0; j < n; j++) {
+        d[j] = V(n - 1, j);
+        V(n - 1, j) = 0.0;
+    }
+    if (n > 0) V(n - 1, n - 1) = 1.0;
+    e[0] = 0.0;
+    // ---- tql2: implicit-shift QL on the tridiagonal matrix
+    for (int i = 1; i < n; i++) e[i - 1] = e[i];
+    if (n > 0) e[n - 1] = 0.0;
+    double f = 0.0, tst1 = 0.0;
+    const double eps = std::pow(2.0, -52.0);
+    for (int l = 0; l < n; l++) {
+        tst1 = std::max(tst1, std::fabs(d[l]) + std::fabs(e[l]));
+        int m = l;
+        while (m < n) {
+            if (std::fabs(e[m]) <= eps * tst1) break;
+            m++;
+        }
+        if (m > l) {
+            int iter = 0;
+            do {
+                iter++;
+                double g = d[l];
+                double p = (d[l + 1] - g) / (2.0 * e[l]);
+                double r = std::hypot(p, 1.0);
+                if (p < 0) r = -r;
+                d[l] = e[l] / (p + r);
+                d[l + 1] = e[l] * (p + r);
+                const double dl1 = d[l + 1];
+                double h = g - d[l];
+                for (int i = l + 2; i < n; i++) d[i] -= h;
+                f += h;
+                p = d[m];
+                double c = 1.0, c2 = c, c3 = c;
+                const double el1 = e[l + 1];
+                double s = 0.0, s2 = 0.0;
+                for (int i = m - 1; i >= l; i--) {
+                    c3 = c2;
+                    c2 = c;
+                    s2 = s;
+                    g = c * e[i];
+                    h = c * p;
+                    r = std::hypot(p, e[i]);
+                    e[i + 1] = s * r;
+                    s = e[i] / r;
+                    c = p / r;
+                    p = c * d[i] - s * g;
+                    d[i + 1] = h + s * (c * g + s * d[i]);
+                    for (int k = 0; k < n; k++) {
+                        h = V(k, i + 1);
+                        V(k, i + 1) = s * V(k, i) + c * h;
+                        V(k, i) = c * V(k, i) - s * h;
+                    }
+                }
+                p = -s * s2 * c3 * el1 * e[l] / dl1;
+                e[l] = s * p;
+                d[l] = c * p;
+            } while (std::fabs(e[l]) > eps * tst1 && iter < 200);
+        }
+        d[l] = d[l] + f;
+        e[l] = 0.0;
+    }
     std::vector<int> idx(n);
     for (int i = 0; i < n; i++) idx[i] = i;
     std::sort(idx.begin(), idx.end(), [&](int i, int j) { return d[i] < d[j]; });
     w.resize(n);
-    V = Mat(n, n);
+    Mat Vs(n, n);
     for (int k = 0; k < n; k++) {
         w[k] = d[idx[k]];
-        for (int i = 0; i < n; i++) V(i, k) = v[(size_t)i * ld + idx[k]];
+        for (int i = 0; i < n; i++) Vs(i, k) = V(i, idx[k]);
     }
+    V = Vs;
 }
 
 // Right singular vector of the smallest singular value of A (rows x 4): one-sided Jacobi on the columns

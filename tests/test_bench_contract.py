@@ -36,6 +36,6 @@ def test_our_arm_needs_a_gpu():
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present")
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--no-cpu-baseline", "--batch", "0"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--no-cpu-baseline", "--no-c3"],
                          capture_output=True, text=True, timeout=580, cwd=ROOT)
     assert out.returncode != 0 and "no CPU path" in (out.stderr + out.stdout)
