@@ -78,7 +78,7 @@ def test_batch_members_match_standalone_and_oracle():
     assert n_nl >= n * (n_pub - 12)
     print("batch vs stand-alone", worst_solo, "batch vs oracle", worst_cpu)
     for key in worst_solo:
-        assert worst_solo[key] <= 0.2 * TOL[key], (key, worst_solo)   # same code, different atomic orders only
+        assert worst_solo[key] == 0.0, (key, worst_solo)   # same code, fixed summation orders: bit-identical
         assert worst_cpu[key] <= TOL[key], (key, worst_cpu)
     batch.close()
 
@@ -121,7 +121,7 @@ def test_batch_of_64_sequences_runs():
     for k in check:
         w = _worst(batch.members[k].states()[0], solo[k].states()[0])
         for key in w:
-            assert w[key] <= 0.2 * TOL[key], (k, w)
+            assert w[key] == 0.0, (k, w)   # the batch only changes which grid dimension a sequence lives on
     # one launch chain per frame regardless of the batch size: zero + linearize + 8 x 3 + finish + 3 marginalisation + jobs
     assert max(launches) <= 2 + 8 * 3 + 1 + 3 + 1, launches
     batch.close()

@@ -137,6 +137,9 @@ struct VisualEval {
     double half_rho;
 };
 
+// EX / TD select at compile time whether the Jacobians with respect to the camera extrinsic (columns 12..17) and the
+// time offset (column 19) are produced (constant parameter blocks get no Jacobian: ceres hands jacobians[k] == NULL).
+template <bool EX, bool TD>
 __device__ __forceinline__ void eval_visual(const BaDims& d, const double* pose_i, const double* pose_j, const double* ex,
                                             double inv_dep_i, double td, double pix, double piy, double pjx, double pjy,
                                             double vix, double viy, double vjx, double vjy, double td_i, double td_j,
@@ -174,9 +177,12 @@ __device__ __forceinline__ void eval_visual(const BaDims& d, const double* pose_
         const M3d Cm = mscale(A, -1.0);                      // d pcj / d Pj
         const M3d Dm = mmul(ricT, skew(pts_imu_j));
         const M3d tmp_r = mmul(mmul(A, Ri), ric);
-        const M3d Eex = mmul(ricT, msub(mmul(RjT, Ri), mident()));
-        const V3d inner = mv(RjT, mv(Ri, tic) + Pi - Pj) - tic;
-        const M3d Fex = madd(madd(mscale(mmul(tmp_r, skew(pci)), -1.0), skew(mv(tmp_r, pci))), skew(mv(ricT, inner)));
+        M3d Eex, Fex;
+        if (EX) {
+            Eex = mmul(ricT, msub(mmul(RjT, Ri), mident()));
+            const V3d inner = mv(RjT, mv(Ri, tic) + Pi - Pj) - tic;
+            Fex = madd(madd(mscale(mmul(tmp_r, skew(pci)), -1.0), skew(mv(tmp_r, pci))), skew(mv(ricT, inner)));
+        }
         const V3d dl = mv(tmp_r, pts_i) * (-1.0 / (inv_dep_i * inv_dep_i));
 #pragma unroll
         for (int rr = 0; rr < 2; rr++) {
@@ -186,13 +192,18 @@ __device__ __forceinline__ void eval_visual(const BaDims& d, const double* pose_
                 e.J[rr][3 + cc] = red[rr][0] * B.m[cc] + red[rr][1] * B.m[3 + cc] + red[rr][2] * B.m[6 + cc];
                 e.J[rr][6 + cc] = red[rr][0] * Cm.m[cc] + red[rr][1] * Cm.m[3 + cc] + red[rr][2] * Cm.m[6 + cc];
                 e.J[rr][9 + cc] = red[rr][0] * Dm.m[cc] + red[rr][1] * Dm.m[3 + cc] + red[rr][2] * Dm.m[6 + cc];
-                e.J[rr][12 + cc] = red[rr][0] * Eex.m[cc] + red[rr][1] * Eex.m[3 + cc] + red[rr][2] * Eex.m[6 + cc];
-                e.J[rr][15 + cc] = red[rr][0] * Fex.m[cc] + red[rr][1] * Fex.m[3 + cc] + red[rr][2] * Fex.m[6 + cc];
+                if (EX) {
+                    e.J[rr][12 + cc] = red[rr][0] * Eex.m[cc] + red[rr][1] * Eex.m[3 + cc] + red[rr][2] * Eex.m[6 + cc];
+                    e.J[rr][15 + cc] = red[rr][0] * Fex.m[cc] + red[rr][1] * Fex.m[3 + cc] + red[rr][2] * Fex.m[6 + cc];
+                } else {
+                    e.J[rr][12 + cc] = 0.0;
+                    e.J[rr][15 + cc] = 0.0;
+                }
             }
             e.J[rr][18] = red[rr][0] * dl.x + red[rr][1] * dl.y + red[rr][2] * dl.z;
             e.J[rr][19] = 0.0;
         }
-        if (d.est_td) {
+        if (TD && d.est_td) {
             const V3d vi = mk(vix, viy, 0.0);
             const V3d dtd = mv(tmp_r, vi) * (-1.0 / inv_dep_i);
             e.J[0][19] = red[0][0] * dtd.x + red[0][1] * dtd.y + red[0][2] * dtd.z + s * vjx;

@@ -2,14 +2,13 @@
 //
 //   preint_push_kernel    IntegrationBase::propagate / midPointIntegration     integration_base.h:54-158
 //   sqrt_info_kernel      LLT(covariance^-1).matrixL().transpose()            imu_factor.h:64
-//   ba_linearize_kernel   factor Evaluate() + Cauchy corrector + J^T J / J^T r accumulation; one warp per
-//                         landmark (lanes = its observations), one CTA per IMU factor, one CTA for the prior;
-//                         the last CTA to finish runs the trust-region accept/reject logic
-//   ba_schur_kernel       landmark elimination S = Hpp - Hpl^T (Hll + mu E)^-1 Hpl as a dense tiled SYRK
-//                         (deterministic summation order), plus the reduced gradient
+//   ba_eval_kernel        factor Evaluate() + Cauchy corrector into per-factor records (ba_assemble.cuh); the last CTA to
+//                         finish runs the trust-region accept/reject logic
+//   ba_reduce_kernel      landmark elimination S = Hpp - Hpl^T (Hll + mu E)^-1 Hpl gathered block by block in a fixed
+//                         order (no atomics, only co-visible landmarks), plus the reduced gradient
 //   ba_step_kernel        Jacobi scaling, dogleg (Cauchy point, regularised Gauss-Newton via in-shared-memory
 //                         Cholesky), model cost change, candidate point x (+) delta
-//   marg_build_kernel / marg_solve_kernel   MarginalizationInfo::preMarginalize + marginalize
+//   marg_eval / marg_gather / marg_solve_kernel   MarginalizationInfo::preMarginalize + marginalize
 //                         (marginalization_factor.cpp:110-297) producing the new prior in information form
 // The solve replaces ceres::Solve(DENSE_SCHUR, DOGLEG) at estimator.cpp:803-818; no wall-clock cap.
 // Everything here is small dense float64 algebra: latency bound for one sequence, HBM bound in batches;
@@ -261,441 +260,11 @@ __device__ __forceinline__ void load_desc(T* dst, const T* src) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) ba_zero_kernel(const BaSeq* __restrict__ seqs, int initial) {
-    const BaSeq& q = seqs[blockIdx.y];
-    if (!q.active) return;
-    const BaProblem& p = q.p;
-    const SolverState* st = p.st;
-    if (!initial && (st->done || !st->cand_valid)) return;
-    const int b = initial ? st->cur : 1 - st->cur;
-    const BaAccum a = p.acc[b];
-    const int D = p.dims.D, L = p.dims.L;
-    const size_t n1 = (size_t)D * D, n2 = (size_t)L * D;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + D + 2 * (size_t)L + 1; i += stride) {
-        if (i < n1) a.Hpp[i] = 0.0;
-        else if (i < n1 + n2) a.Hpl[i - n1] = 0.0;
-        else if (i < n1 + n2 + D) a.gp[i - n1 - n2] = 0.0;
-        else if (i < n1 + n2 + D + L) a.Hll[i - n1 - n2 - D] = 0.0;
-        else if (i < n1 + n2 + D + 2 * (size_t)L) a.gl[i - n1 - n2 - D - L] = 0.0;
-        else a.cost[0] = 0.0;
-    }
-}
+}  // namespace vb
 
-namespace {
+#include "ba_assemble.cuh"
 
-// Trust-region bookkeeping after a point has been evaluated (Ceres TrustRegionMinimizer: iteration zero,
-// ParameterToleranceReached, FunctionToleranceReached, IsStepSuccessful, Handle(Un)SuccessfulStep and
-// DoglegStrategy::StepAccepted / StepRejected).
-__device__ void decide(const BaProblem& p, int initial) {
-    SolverState* st = p.st;
-    if (initial) {
-        const double c = *(volatile double*)p.acc[st->cur].cost;
-        st->x_cost = c;
-        st->initial_cost = c;
-        return;
-    }
-    const double cand = *(volatile double*)p.acc[1 - st->cur].cost;
-    st->cand_cost = cand;
-    if (st->step_norm <= 1e-8 * (st->x_norm + 1e-8)) {
-        st->done = 2;
-        return;
-    }
-    const double cost_change = st->x_cost - cand;
-    if (fabs(cost_change) <= 1e-6 * st->x_cost) {
-        st->done = 3;
-        return;
-    }
-    const double rho = cost_change / st->model_cost_change;
-    if (rho > 1e-3) {
-        st->cur = 1 - st->cur;
-        st->x_cost = cand;
-        st->successful++;
-        if (rho < 0.25) st->radius *= 0.5;
-        if (rho > 0.75) st->radius = fmax(st->radius, 3.0 * st->dogleg_step_norm);
-        st->mu = fmax(1e-8, 2.0 * st->mu / 10.0);
-        st->reuse = 0;
-    } else {
-        st->radius *= 0.5;
-        st->reuse = 1;
-    }
-    if (st->iteration >= st->max_iterations) st->done = 1;
-}
-
-__device__ __forceinline__ void lin_visual(const BaProblem& p, const BaStates& x, const BaAccum& a, int l, int lane) {
-    const BaDims& d = p.dims;
-    const int D = d.D;
-    const int s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0;
-    const int fi = p.lm_anchor[l];
-    const bool has = lane < nobs;
-    VisualEval e;
-    int fj = fi;
-    if (has) {
-        const int o = s0 + lane;
-        fj = p.ob_frame[o];
-        eval_visual(d, x.pose + 7 * fi, x.pose + 7 * fj, x.ex, x.lam[l], d.est_td ? x.td[0] : 0.0, p.lm_pts[2 * l], p.lm_pts[2 * l + 1],
-                    p.ob_pts[2 * o], p.ob_pts[2 * o + 1], p.lm_vel[2 * l], p.lm_vel[2 * l + 1], p.ob_vel[2 * o], p.ob_vel[2 * o + 1],
-                    p.lm_td[l], p.ob_td[o], p.lm_row[l], p.ob_row[o], true, true, e);
-    } else {
-        e.r[0] = e.r[1] = 0;
-        e.half_rho = 0;
-#pragma unroll
-        for (int k = 0; k < 20; k++) e.J[0][k] = e.J[1][k] = 0;
-    }
-    const int ci = 6 * fi, cj = 6 * fj;
-    double v = warp_sum_d(e.half_rho);
-    if (lane == 0) atomicAdd(a.cost, v);
-    v = warp_sum_d(e.J[0][18] * e.J[0][18] + e.J[1][18] * e.J[1][18]);
-    if (lane == 0) a.Hll[l] = v;
-    v = warp_sum_d(e.J[0][18] * e.r[0] + e.J[1][18] * e.r[1]);
-    if (lane == 0) a.gl[l] = v;
-    auto dotJ = [&](int aa, int bb) { return e.J[0][aa] * e.J[0][bb] + e.J[1][aa] * e.J[1][bb]; };
-    auto dotr = [&](int aa) { return e.J[0][aa] * e.r[0] + e.J[1][aa] * e.r[1]; };
-    // anchor pose block (shared by all observations of the landmark): warp-reduce, one lane commits
-#pragma unroll
-    for (int aa = 0; aa < 6; aa++) {
-#pragma unroll
-        for (int bb = aa; bb < 6; bb++) {
-            v = warp_sum_d(dotJ(aa, bb));
-            if (lane == 0) atomicAdd(&a.Hpp[(size_t)(ci + aa) * D + ci + bb], v);
-        }
-        v = warp_sum_d(dotr(aa));
-        if (lane == 0) atomicAdd(&a.gp[ci + aa], v);
-        v = warp_sum_d(dotJ(aa, 18));
-        if (lane == 0) a.Hpl[(size_t)l * D + ci + aa] = v;
-    }
-    if (has) {  // blocks involving this observation's own frame j
-#pragma unroll
-        for (int aa = 0; aa < 6; aa++) {
-#pragma unroll
-            for (int bb = 0; bb < 6; bb++) atomicAdd(&a.Hpp[(size_t)(ci + aa) * D + cj + bb], dotJ(aa, 6 + bb));
-#pragma unroll
-            for (int bb = aa; bb < 6; bb++) atomicAdd(&a.Hpp[(size_t)(cj + aa) * D + cj + bb], dotJ(6 + aa, 6 + bb));
-            atomicAdd(&a.gp[cj + aa], dotr(6 + aa));
-            a.Hpl[(size_t)l * D + cj + aa] = dotJ(6 + aa, 18);
-        }
-    }
-    if (d.col_ex >= 0) {
-        const int ce = d.col_ex;
-#pragma unroll
-        for (int aa = 0; aa < 6; aa++) {
-#pragma unroll
-            for (int bb = 0; bb < 6; bb++) {
-                v = warp_sum_d(dotJ(aa, 12 + bb));
-                if (lane == 0) atomicAdd(&a.Hpp[(size_t)(ci + aa) * D + ce + bb], v);
-                if (has) atomicAdd(&a.Hpp[(size_t)(cj + aa) * D + ce + bb], dotJ(6 + aa, 12 + bb));
-            }
-#pragma unroll
-            for (int bb = aa; bb < 6; bb++) {
-                v = warp_sum_d(dotJ(12 + aa, 12 + bb));
-                if (lane == 0) atomicAdd(&a.Hpp[(size_t)(ce + aa) * D + ce + bb], v);
-            }
-            v = warp_sum_d(dotr(12 + aa));
-            if (lane == 0) atomicAdd(&a.gp[ce + aa], v);
-            v = warp_sum_d(dotJ(12 + aa, 18));
-            if (lane == 0) a.Hpl[(size_t)l * D + ce + aa] = v;
-        }
-    }
-    if (d.col_td >= 0) {
-        const int ct = d.col_td;
-#pragma unroll
-        for (int aa = 0; aa < 6; aa++) {
-            v = warp_sum_d(dotJ(aa, 19));
-            if (lane == 0) atomicAdd(&a.Hpp[(size_t)(ci + aa) * D + ct], v);
-            if (has) atomicAdd(&a.Hpp[(size_t)(cj + aa) * D + ct], dotJ(6 + aa, 19));
-            if (d.col_ex >= 0) {
-                v = warp_sum_d(dotJ(12 + aa, 19));
-                if (lane == 0) atomicAdd(&a.Hpp[(size_t)(d.col_ex + aa) * D + ct], v);
-            }
-        }
-        v = warp_sum_d(dotJ(19, 19));
-        if (lane == 0) atomicAdd(&a.Hpp[(size_t)ct * D + ct], v);
-        v = warp_sum_d(dotr(19));
-        if (lane == 0) atomicAdd(&a.gp[ct], v);
-        v = warp_sum_d(dotJ(19, 18));
-        if (lane == 0) a.Hpl[(size_t)l * D + ct] = v;
-    }
-}
-
-__device__ __forceinline__ int imu_col(const BaDims& d, int k, int aa) {
-    if (aa < 6) return 6 * k + aa;
-    if (aa < 15) return d.col_sb + 9 * k + (aa - 6);
-    if (aa < 21) return 6 * (k + 1) + (aa - 15);
-    return d.col_sb + 9 * (k + 1) + (aa - 21);
-}
-
-// Whitened IMU residual and Jacobian of factor k in shared memory (Jw 15x30, rw 15).  Returns false if skipped.
-__device__ __forceinline__ bool imu_whitened(const BaProblem& p, const BaStates& x, int k, int lane, double* Jraw, double* Jw,
-                                             double* rr, double* rw) {
-    const int slot = p.imu_slot[k];
-    if (slot < 0) return false;
-    const PreInt& pre = p.preint[slot];
-    for (int i = lane; i < 450; i += 32) Jraw[i] = 0.0;
-    __syncwarp();
-    if (lane == 0) eval_imu_raw(p.dims, pre, x.pose + 7 * k, x.sb + 9 * k, x.pose + 7 * (k + 1), x.sb + 9 * (k + 1), rr, Jraw);
-    __syncwarp();
-    for (int idx = lane; idx < 450; idx += 32) {
-        const int i = idx / 30, c = idx % 30;
-        double s = 0;
-        for (int q = 0; q < 15; q++) s += pre.sqrt_info[i * 15 + q] * Jraw[q * 30 + c];
-        Jw[idx] = s;
-    }
-    if (lane < 15) {
-        double s = 0;
-        for (int q = 0; q < 15; q++) s += pre.sqrt_info[lane * 15 + q] * rr[q];
-        rw[lane] = s;
-    }
-    __syncwarp();
-    return true;
-}
-
-// One CTA per IMU factor: warp 0 evaluates and whitens the 15x30 Jacobian (shared memory), then every warp of the
-// CTA adds its share of the 30x30 product into the Hessian (the product was 29 serial passes for a single warp and,
-// with the prior, the critical path of the kernel).
-__device__ __forceinline__ void lin_imu(const BaProblem& p, const BaStates& x, const BaAccum& a, int k, double* Jraw, double* Jw,
-                                        double* rr, double* rw, int* valid) {
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-    if (tid < 32) {
-        const bool ok = imu_whitened(p, x, k, lane, Jraw, Jw, rr, rw);
-        if (lane == 0) *valid = ok ? 1 : 0;
-    }
-    __syncthreads();
-    if (!*valid) return;
-    const BaDims& d = p.dims;
-    const int D = d.D;
-    if (tid == 0) {
-        double c = 0;
-        for (int q = 0; q < 15; q++) c += rw[q] * rw[q];
-        atomicAdd(a.cost, 0.5 * c);
-    }
-    for (int idx = tid; idx < 900; idx += nt) {
-        const int aa = idx / 30, bb = idx - aa * 30;
-        const int ga = imu_col(d, k, aa), gb = imu_col(d, k, bb);
-        if (ga > gb) continue;
-        double s = 0;
-#pragma unroll
-        for (int q = 0; q < 15; q++) s += Jw[q * 30 + aa] * Jw[q * 30 + bb];
-        if (s != 0.0) atomicAdd(&a.Hpp[(size_t)ga * D + gb], s);
-    }
-    if (tid >= nt - 32 && lane < 30) {  // the last warp: gradient
-        double s = 0;
-        for (int q = 0; q < 15; q++) s += Jw[q * 30 + lane] * rw[q];
-        atomicAdd(&a.gp[imu_col(d, k, lane)], s);
-    }
-}
-
-#define PRIOR_MAX_N 160
-
-// dx of the prior's kept blocks (MarginalizationFactor::Evaluate, marginalization_factor.cpp:343-364)
-__device__ __forceinline__ void prior_dx(const BaProblem& p, const BaStates& x, double* dx, int tid, int nthreads) {
-    const BaPrior& pr = p.prior;
-    for (int b = tid; b < pr.nblocks; b += nthreads) {
-        const int type = pr.type[b], idx = pr.index[b], off = pr.off[b];
-        const double* x0 = pr.x0 + 9 * b;
-        if (type == 0 || type == 2) {
-            const double* xv = type == 0 ? x.pose + 7 * idx : x.ex;
-            for (int q = 0; q < 3; q++) dx[off + q] = xv[q] - x0[q];
-            const Q4 dq = qmul(qinv(q_from_param(x0)), q_from_param(xv));
-            const double sg = (dq.w >= 0) ? 2.0 : -2.0;
-            dx[off + 3] = sg * dq.x;
-            dx[off + 4] = sg * dq.y;
-            dx[off + 5] = sg * dq.z;
-        } else if (type == 1) {
-            for (int q = 0; q < 9; q++) dx[off + q] = x.sb[9 * idx + q] - x0[q];
-        } else {
-            dx[off] = x.td[0] - x0[0];
-        }
-    }
-}
-
-__device__ __forceinline__ void prior_cols(const BaProblem& p, int* col, int tid, int nthreads) {
-    const BaPrior& pr = p.prior;
-    const BaDims& d = p.dims;
-    for (int b = tid; b < pr.nblocks; b += nthreads) {
-        const int type = pr.type[b], idx = pr.index[b], off = pr.off[b];
-        if (type == 0) for (int q = 0; q < 6; q++) col[off + q] = 6 * idx + q;
-        else if (type == 1) for (int q = 0; q < 9; q++) col[off + q] = d.col_sb + 9 * idx + q;
-        else if (type == 2) for (int q = 0; q < 6; q++) col[off + q] = d.col_ex >= 0 ? d.col_ex + q : -1;
-        else col[off] = d.col_td;
-    }
-}
-
-__device__ void lin_prior(const BaProblem& p, const BaStates& x, const BaAccum& a) {
-    __shared__ double dx[PRIOR_MAX_N], gpr[PRIOR_MAX_N];
-    __shared__ int col[PRIOR_MAX_N];
-    __shared__ double red[4];
-    const BaPrior& pr = p.prior;
-    const int n = pr.n, tid = threadIdx.x, nt = blockDim.x, D = p.dims.D;
-    if (n <= 0) return;
-    prior_dx(p, x, dx, tid, nt);
-    prior_cols(p, col, tid, nt);
-    __syncthreads();
-    double part = 0;
-    for (int aa = tid >> 5; aa < n; aa += nt >> 5) {  // a warp per row of A: coalesced reads, shuffle reduction
-        double s = 0;
-        for (int bb = tid & 31; bb < n; bb += 32) s += pr.A[(size_t)aa * n + bb] * dx[bb];
-        s = warp_sum_d(s);
-        if ((tid & 31) == 0) {
-            s += pr.g0[aa];
-            gpr[aa] = s;
-            part += dx[aa] * (pr.g0[aa] + s);
-        }
-    }
-    part = warp_sum_d(part);
-    if ((tid & 31) == 0) red[tid >> 5] = part;
-    __syncthreads();
-    if (tid == 0) {
-        double c = pr.c0[0];
-        for (int w = 0; w < nt / 32; w++) c += red[w];
-        atomicAdd(a.cost, 0.5 * c);
-    }
-    for (int idx = tid; idx < n * n; idx += nt) {
-        const int aa = idx / n, bb = idx % n;
-        const int ga = col[aa], gb = col[bb];
-        if (ga < 0 || gb < 0 || ga > gb || (ga == gb && aa != bb)) continue;
-        const double v = pr.A[idx];
-        if (v != 0.0) atomicAdd(&a.Hpp[(size_t)ga * D + gb], v);
-    }
-    for (int aa = tid; aa < n; aa += nt)
-        if (col[aa] >= 0) atomicAdd(&a.gp[col[aa]], gpr[aa]);
-}
-
-}  // namespace
-
-#define LIN_WARPS 4
-__host__ __device__ inline int ba_linearize_grid(const BaDims& d) { return (d.L + LIN_WARPS - 1) / LIN_WARPS + d.W + 1; }
-__global__ void __launch_bounds__(32 * LIN_WARPS) ba_linearize_kernel(const BaSeq* __restrict__ seqs, int initial) {
-    __shared__ double sJraw[450], sJw[450], srr[15], srw[15];
-    __shared__ int imu_valid;
-    __shared__ BaProblem sp;
-    const BaSeq& q = seqs[blockIdx.y];
-    if (!q.active) return;
-    {
-        const SolverState* st0 = &q.st;
-        if (!initial && (st0->done || !st0->cand_valid)) return;
-    }
-    load_desc(&sp, &q.p);
-    const BaProblem& p = sp;
-    SolverState* st = p.st;
-    if ((int)blockIdx.x >= ba_linearize_grid(p.dims)) return;  // the grid is sized for the largest member of the batch
-    const int b = initial ? st->cur : 1 - st->cur;
-    const BaStates x = p.x[b];
-    const BaAccum a = p.acc[b];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int nb_vis = (p.dims.L + LIN_WARPS - 1) / LIN_WARPS, nb_imu = p.dims.W;
-    const int blk = blockIdx.x;
-    if (blk < nb_imu) {  // the long CTAs first
-        lin_imu(p, x, a, blk, sJraw, sJw, srr, srw, &imu_valid);
-    } else if (blk < nb_imu + nb_vis) {
-        const int l = (blk - nb_imu) * LIN_WARPS + wid;
-        if (l < p.dims.L) lin_visual(p, x, a, l, lane);
-    } else {
-        lin_prior(p, x, a);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned t = atomicAdd(&st->lin_ticket, 1u);
-        if (t == (unsigned)ba_linearize_grid(p.dims) - 1u) {
-            st->lin_ticket = 0;
-            __threadfence();
-            decide(p, initial);
-        }
-    }
-}
-
-
-// ------------------------------------------------------------------------------------------------
-// Landmark elimination as a dense, deterministic tiled product:
-//   S = sym(Hpp) - sum_l w_l w_l^T / (Hll_l + mu E_l),   gred = gp - sum_l w_l gl_l / (Hll_l + mu E_l)
-// E_l = clamp(Hll_l s_l^2, 1e-6, 1e32) / s_l^2 is the dogleg/LM diagonal expressed in unscaled variables.
-#define ST 16
-__device__ __forceinline__ double lm_inv_lambda(const BaProblem& p, const BaAccum& a, int l, double mu, int first) {
-    const double h = a.Hll[l];
-    const double s = first ? 1.0 / (1.0 + sqrt(h)) : p.scale[p.dims.D + l];
-    const double d2 = fmin(fmax(h * s * s, 1e-6), 1e32);
-    return 1.0 / (h + mu * d2 / (s * s));
-}
-
-__global__ void __launch_bounds__(ST* ST) ba_schur_kernel(const BaSeq* __restrict__ seqs) {
-    __shared__ BaProblem sp;
-    const BaSeq& q = seqs[blockIdx.z];
-    if (!q.active || q.st.done) return;
-    load_desc(&sp, &q.p);
-    const BaProblem& p = sp;
-    const SolverState* st = p.st;
-    if (blockIdx.y > blockIdx.x) {
-        // The product needs the upper tiles only; the CTAs of the lower triangle clear the accumulators the next
-        // linearisation (of the candidate point) adds into, which saves a launch per iteration.
-        const BaAccum z = p.acc[1 - st->cur];
-        const int D = p.dims.D, L = p.dims.L;
-        const int nlow = gridDim.x * (gridDim.x - 1) / 2;
-        const int lin = blockIdx.y * (blockIdx.y - 1) / 2 + blockIdx.x;  // 0 .. nlow-1
-        const size_t n1 = (size_t)D * D, n2 = (size_t)L * D, total = n1 + n2 + D + 2 * (size_t)L + 1;
-        const size_t stride = (size_t)nlow * ST * ST;
-        for (size_t i = (size_t)lin * ST * ST + threadIdx.y * ST + threadIdx.x; i < total; i += stride) {
-            if (i < n1) z.Hpp[i] = 0.0;
-            else if (i < n1 + n2) z.Hpl[i - n1] = 0.0;
-            else if (i < n1 + n2 + D) z.gp[i - n1 - n2] = 0.0;
-            else if (i < n1 + n2 + D + L) z.Hll[i - n1 - n2 - D] = 0.0;
-            else if (i < n1 + n2 + D + 2 * (size_t)L) z.gl[i - n1 - n2 - D - L] = 0.0;
-            else z.cost[0] = 0.0;
-        }
-        return;
-    }
-    if (st->reuse) return;
-    __shared__ double As[ST][ST + 1], Bs[ST][ST + 1], inv[ST], gls[ST];
-    const BaAccum a = p.acc[st->cur];
-    const int D = p.dims.D, L = p.dims.L;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int r0 = blockIdx.y * ST, c0 = blockIdx.x * ST;
-    const double mu = st->mu;
-    const int first = st->first;
-    double acc = 0, gacc = 0;
-    // software pipelined: the global loads of chunk k+1 are in flight while chunk k is multiplied out of shared memory
-    // (a chunk is only 16 landmark rows; unpipelined, every chunk paid a full L2 round trip behind a barrier)
-    auto fetch = [&](int l0, double& va, double& vb, double& vi, double& vg) {
-        const int l = l0 + ty;
-        va = (l < L && r0 + tx < D) ? a.Hpl[(size_t)l * D + r0 + tx] : 0.0;
-        vb = (l < L && c0 + tx < D) ? a.Hpl[(size_t)l * D + c0 + tx] : 0.0;
-        vi = 0.0;
-        vg = 0.0;
-        if (tx == 0 && l < L) {
-            vi = lm_inv_lambda(p, a, l, mu, first);
-            vg = a.gl[l];
-        }
-    };
-    double va, vb, vi, vg;
-    fetch(0, va, vb, vi, vg);
-    for (int l0 = 0; l0 < L; l0 += ST) {
-        As[ty][tx] = va;
-        Bs[ty][tx] = vb;
-        if (tx == 0) {
-            inv[ty] = vi;
-            gls[ty] = vg;
-        }
-        __syncthreads();
-        if (l0 + ST < L) fetch(l0 + ST, va, vb, vi, vg);
-#pragma unroll
-        for (int q = 0; q < ST; q++) {
-            acc += As[q][ty] * inv[q] * Bs[q][tx];
-            if (blockIdx.x == blockIdx.y && ty == 0) gacc += Bs[q][tx] * inv[q] * gls[q];
-        }
-        __syncthreads();
-    }
-    const int r = r0 + ty, c = c0 + tx;
-    if (r < D && c < D) {
-        const double h = r <= c ? a.Hpp[(size_t)r * D + c] : a.Hpp[(size_t)c * D + r];
-        p.Hfull[(size_t)r * D + c] = h;
-        p.S[(size_t)r * D + c] = h - acc;
-        if (r <= c) p.Spk[(size_t)c * (c + 1) / 2 + r] = h - acc;
-        if (blockIdx.x != blockIdx.y) {
-            p.Hfull[(size_t)c * D + r] = h;
-            p.S[(size_t)c * D + r] = h - acc;
-        }
-    }
-    if (blockIdx.x == blockIdx.y && ty == 0 && c < D) p.gred[c] = a.gp[c] - gacc;
-}
+namespace vb {
 
 // ------------------------------------------------------------------------------------------------
 namespace {
@@ -710,7 +279,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return s;
 }
 
-// q = v^T H v over all parameters (H = [[Hfull, Hpl^T], [Hpl, diag(Hll)]]), also returns v^T g if g given
+// q = v^T H v over all parameters (H = [[Hfull, Hpl^T], [Hpl, diag(Hll)]], the landmark rows of Hpl in their sparse form)
 __device__ double quad_form(const BaProblem& p, const BaAccum& a, const double* v, double* tmp, double* red) {
     const int D = p.dims.D, L = p.dims.L;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x / 32;
@@ -722,10 +291,8 @@ __device__ double quad_form(const BaProblem& p, const BaAccum& a, const double* 
         if (lane == 0) part += v[r] * s;
     }
     for (int l = wid; l < L; l += nw) {
-        double s = 0;
-        for (int c = lane; c < D; c += 32) s += a.Hpl[(size_t)l * D + c] * v[c];
-        s = warp_sum_d(s);
-        if (lane == 0) part += v[D + l] * (2.0 * s + a.Hll[l] * v[D + l]);
+        const double s = lm_row_dot(p, a, l, v, lane);
+        if (lane == 0) part += v[D + l] * (2.0 * s + a.lmW[(size_t)l * p.dims.lw + LW_HLL] * v[D + l]);
     }
     (void)tmp;
     return block_sum(part, red);
@@ -992,27 +559,45 @@ __device__ void chol_solve_packed(const double* Lp, const double* linv, int n, d
     }
 }
 
-// Slow path: recompute S for a new mu inside the single step CTA (only after a failed factorisation).
+// Slow path: recompute S for a new mu inside the single step CTA (only after a failed factorisation): every entry of a
+// pose-type block pair walks all landmarks in order.
 __device__ void reduce_single_cta(const BaProblem& p, const BaAccum& a, double mu, int first) {
-    const int D = p.dims.D, L = p.dims.L;
-    for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {
+    const BaDims& d = p.dims;
+    const int D = d.D, L = d.L, NV = num_vblocks(d);
+    for (int idx = threadIdx.x; idx < D * D; idx += blockDim.x) {  // S = Hfull everywhere first
         const int r = idx / D, c = idx % D;
         if (r > c) continue;
-        double acc = 0;
-        for (int l = 0; l < L; l++) {
-            const double wr = a.Hpl[(size_t)l * D + r];
-            if (wr == 0.0) continue;
-            acc += wr * lm_inv_lambda(p, a, l, mu, first) * a.Hpl[(size_t)l * D + c];
-        }
         const double h = p.Hfull[idx];
-        p.S[idx] = h - acc;
-        p.S[(size_t)c * D + r] = h - acc;
-        p.Spk[(size_t)c * (c + 1) / 2 + r] = h - acc;
+        p.S[idx] = h;
+        p.S[(size_t)c * D + r] = h;
+        p.Spk[(size_t)c * (c + 1) / 2 + r] = h;
     }
-    for (int c = threadIdx.x; c < D; c += blockDim.x) {
-        double acc = 0;
-        for (int l = 0; l < L; l++) acc += a.Hpl[(size_t)l * D + c] * lm_inv_lambda(p, a, l, mu, first) * a.gl[l];
-        p.gred[c] = a.gp[c] - acc;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) p.gred[c] = a.gp[c];
+    __syncthreads();
+    // entries of the pose-type block pairs: 36 slots per pair
+    for (int e = threadIdx.x; e < NV * NV * 36; e += blockDim.x) {
+        const int pair = e / 36, t = e - 36 * pair;
+        const int TA = pair / NV, TB = pair - TA * NV;
+        if (TA > TB) continue;
+        const VBlock A = vblock(d, TA), B = vblock(d, TB);
+        const int i = t / B.dim, j = t - i * B.dim;
+        if (t >= A.dim * B.dim || (TA == TB && i > j)) continue;
+        double E = 0.0, gE = 0.0;
+        for (int l = 0; l < L; l++) {
+            const int an = p.lm_anchor[l], s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0;
+            if (!lm_covers(A, an, nobs) || !lm_covers(B, an, nobs)) continue;
+            const double* rec = a.lmW + (size_t)l * d.lw;
+            const double inv = lm_inv_lambda(p, a, l, mu, first);
+            const double wa = lm_w(a, d.oj, rec, A, i, an, s0);
+            E += wa * inv * lm_w(a, d.oj, rec, B, j, an, s0);
+            if (TA == TB && i == j) gE += wa * inv * rec[LW_GL];
+        }
+        const int r = A.col + i, c = B.col + j;
+        const double sv = p.Hfull[(size_t)r * D + c] - E;
+        p.S[(size_t)r * D + c] = sv;
+        p.S[(size_t)c * D + r] = sv;
+        p.Spk[(size_t)c * (c + 1) / 2 + r] = sv;
+        if (TA == TB && i == j) p.gred[r] = a.gp[r] - gE;
     }
     __syncthreads();
 }
@@ -1093,8 +678,8 @@ __global__ void __launch_bounds__(512) ba_step_kernel(const BaSeq* __restrict__ 
     }
     if (!st->reuse) {
         for (int j = tid; j < N; j += nt) {
-            const double hjj = j < D ? p.Hfull[(size_t)j * D + j] : a.Hll[j - D];
-            const double gj = j < D ? a.gp[j] : a.gl[j - D];
+            const double hjj = j < D ? p.Hfull[(size_t)j * D + j] : a.lmW[(size_t)(j - D) * d.lw + LW_HLL];
+            const double gj = j < D ? a.gp[j] : a.lmW[(size_t)(j - D) * d.lw + LW_GL];
             if (first) p.scale[j] = 1.0 / (1.0 + sqrt(hjj));
             const double s = p.scale[j];
             const double d2 = fmin(fmax(hjj * s * s, 1e-6), 1e32);
@@ -1152,10 +737,8 @@ __global__ void __launch_bounds__(512) ba_step_kernel(const BaSeq* __restrict__ 
             STAMP(4);
             for (int j = tid; j < D; j += nt) y[j] = ysm[j];
             for (int l = wid; l < L; l += nw) {
-                double s = 0;
-                for (int c = lane; c < D; c += 32) s += a.Hpl[(size_t)l * D + c] * ysm[c];
-                s = warp_sum_d(s);
-                if (lane == 0) y[D + l] = (a.gl[l] - s) * lm_inv_lambda(p, a, l, mu, first);
+                const double s = lm_row_dot(p, a, l, ysm, lane);
+                if (lane == 0) y[D + l] = (a.lmW[(size_t)l * d.lw + LW_GL] - s) * lm_inv_lambda(p, a, l, mu, first);
             }
             __syncthreads();
             for (int j = tid; j < N; j += nt) p.gn[j] = -p.diag[j] * y[j] / p.scale[j];
@@ -1223,7 +806,7 @@ __global__ void __launch_bounds__(512) ba_step_kernel(const BaSeq* __restrict__ 
             const double s_ = p.scale[j];
             const double dl = sd / p.diag[j] * s_;  // undo trust-region diagonal and Jacobi scaling
             delta[j] = dl;
-            pg += dl * (j < D ? a.gp[j] : a.gl[j - D]);
+            pg += dl * (j < D ? a.gp[j] : a.lmW[(size_t)(j - D) * d.lw + LW_GL]);
             pe += dl * dl * (p.diag[j] * p.diag[j]) / (s_ * s_);
         }
         const double sn = block_sum(pn, red), dg = block_sum(pg, red), dEd = block_sum(pe, red);
@@ -1314,32 +897,12 @@ __global__ void __launch_bounds__(512) ba_step_kernel(const BaSeq* __restrict__ 
 
 // ------------------------------------------------------------------------------------------------
 // Marginalisation.  Column layout of the dense system: [m_dense | m_landmarks (diagonal block) | kept n].
-namespace {
-
-struct LocalCols {
-    int c[30];
-};
-
-__device__ __forceinline__ void marg_scatter(double* Am, double* bm, int P, const double* J, int ld, int nrows, const double* r,
-                                             const int* gc, int ncols, int lane, int nlanes) {
-    for (int idx = lane; idx < ncols * ncols; idx += nlanes) {
-        const int aa = idx / ncols, bb = idx % ncols;
-        const int ga = gc[aa], gb = gc[bb];
-        if (ga < 0 || gb < 0 || ga > gb || (ga == gb && aa > bb)) continue;
-        double s = 0;
-        for (int q = 0; q < nrows; q++) s += J[q * ld + aa] * J[q * ld + bb];
-        if (ga == gb && aa != bb) s *= 2.0;  // two local columns mapping to one global column never happens; kept for safety
-        if (s != 0.0) atomicAdd(&Am[(size_t)ga * P + gb], s);
-    }
-    for (int aa = lane; aa < ncols; aa += nlanes) {
-        if (gc[aa] < 0) continue;
-        double s = 0;
-        for (int q = 0; q < nrows; q++) s += J[q * ld + aa] * r[q];
-        atomicAdd(&bm[gc[aa]], s);
-    }
-}
-
-}  // namespace
+// MarginalizationInfo::preMarginalize + the assembly part of marginalize (marginalization_factor.cpp:110-172): the factors
+// that touch the dropped blocks are evaluated at the re-anchored point x[0] into their records (marg_eval_kernel, the
+// same device code as the solve's linearisation, with the extrinsic block always live: it is a parameter of the prior even
+// when the solve keeps it constant), then the dense system is gathered entry by entry in a fixed order (marg_gather_kernel).
+constexpr int MARG_OJ = OJ_FULL, MARG_LW = LW_FULL;
+constexpr int MARG_QMAX = 160 + 16;  // non-landmark columns: m_dense (<= 15) + kept (<= 160)
 
 // Clears the members' marginalisation systems (Am P x P, bm P).
 __global__ void __launch_bounds__(256) marg_zero_kernel(const BaSeq* __restrict__ seqs) {
@@ -1354,91 +917,157 @@ __global__ void __launch_bounds__(256) marg_zero_kernel(const BaSeq* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(128) marg_build_kernel(const BaSeq* __restrict__ seqs) {
-    __shared__ double sJraw[1][450], sJw[1][450], srr[1][15], srw[1][15];
-    __shared__ double dx[PRIOR_MAX_N], gpr[PRIOR_MAX_N];
-    __shared__ int pcol[PRIOR_MAX_N];
+template <bool TD>
+__global__ void __launch_bounds__(32 * LIN_WARPS) marg_eval_kernel(const BaSeq* __restrict__ seqs) {
+    __shared__ double sJraw[450], srr[16];
+    __shared__ double sdx[PRIOR_MAX_N], sred[PRIOR_MAX_N];
     __shared__ BaProblem sp;
-    __shared__ MargPlan smp;
     const BaSeq& q = seqs[blockIdx.y];
     if (!q.active || !q.do_marg) return;
-    if ((int)blockIdx.x >= (q.mp.n_lm + 3) / 4 + 2) return;
+    const int n_lm = q.mp.n_lm, nb_vis = (n_lm + LIN_WARPS - 1) / LIN_WARPS;
+    if ((int)blockIdx.x >= nb_vis + 2) return;
+    load_desc(&sp, &q.p);
+    const BaProblem& p = sp;
+    const BaStates x = p.x[0];
+    const BaAccum a = p.acc[0];  // the solve is over: its records are free
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int blk = blockIdx.x;
+    if (blk < nb_vis) {
+        const int li = blk * LIN_WARPS + wid;
+        if (li < n_lm) lin_visual<true, TD>(p, x, a, MARG_OJ, MARG_LW, q.mp.lms[li], lane);
+    } else if (blk == nb_vis) {
+        if (q.mp.use_imu) lin_imu(p, x, a, 0, sJraw, srr);
+    } else {
+        lin_prior(p, x, a, sdx, sred);
+    }
+}
+
+struct MargCol {  // a non-landmark column of the marginalisation system
+    short type, frame, i;  // 0 pose, 1 speed-bias, 2 ex, 3 td
+};
+
+__global__ void __launch_bounds__(128) marg_gather_kernel(const BaSeq* __restrict__ seqs, int dense_ctas) {
+    __shared__ BaProblem sp;
+    __shared__ MargPlan smp;
+    __shared__ MargCol mcol[MARG_QMAX];
+    __shared__ short mfull[MARG_QMAX];  // reduced index -> column in Am
+    __shared__ short pinv_m[MARG_QMAX]; // reduced index -> row of the previous prior, or -1
+    const BaSeq& q = seqs[blockIdx.y];
+    if (!q.active || !q.do_marg) return;
     load_desc(&sp, &q.p);
     load_desc(&smp, &q.mp);
     const BaProblem& p = sp;
     const MargPlan& mp = smp;
-    const BaStates x = p.x[0];
     const BaDims& d = p.dims;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int P = mp.P;
-    const int nb_vis = (mp.n_lm + 3) / 4;
+    const BaAccum a = p.acc[0];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int md = mp.m_dense, nl = mp.n_lm, n = mp.n, P = mp.P, Q = md + n;
+    const int F = d.W + 1;
+    // reduced (non-landmark) columns: decode through the plan's column tables
+    for (int k = tid; k < Q; k += nt) {
+        mfull[k] = (short)(k < md ? k : k + nl);
+        pinv_m[k] = -1;
+    }
+    __syncthreads();
+    auto reduced = [&](int col) { return col < md ? col : col - nl; };
+    for (int f = tid; f < F; f += nt) {
+        if (mp.col_pose[f] >= 0)
+            for (int i = 0; i < 6; i++) mcol[reduced(mp.col_pose[f] + i)] = MargCol{0, (short)f, (short)i};
+        if (mp.col_sb[f] >= 0)
+            for (int i = 0; i < 9; i++) mcol[reduced(mp.col_sb[f] + i)] = MargCol{1, (short)f, (short)i};
+    }
+    if (tid == 0) {
+        if (mp.col_ex >= 0)
+            for (int i = 0; i < 6; i++) mcol[reduced(mp.col_ex + i)] = MargCol{2, 0, (short)i};
+        if (mp.col_td >= 0) mcol[reduced(mp.col_td)] = MargCol{3, 0, 0};
+    }
+    for (int b = tid; b < p.prior.nblocks; b += nt) {
+        const int type = p.prior.type[b], idx = p.prior.index[b], off = p.prior.off[b];
+        const int base = type == 0 ? mp.col_pose[idx] : type == 1 ? mp.col_sb[idx] : type == 2 ? mp.col_ex : mp.col_td;
+        const int sz = type == 0 || type == 2 ? 6 : type == 1 ? 9 : 1;
+        for (int i = 0; i < sz; i++) pinv_m[reduced(base + i)] = (short)(off + i);
+    }
+    __syncthreads();
     const int blk = blockIdx.x;
-    if (blk < nb_vis) {
-        const int li = blk * 4 + wid;
-        if (li >= mp.n_lm) return;
-        const int l = mp.lms[li];
-        const int s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0, fi = p.lm_anchor[l];
-        // one observation at a time per lane group would waste lanes; instead every lane evaluates one
-        // observation and commits its own 2 x 20 block with atomics
-        if (lane < nobs) {
-            const int o = s0 + lane, fj = p.ob_frame[o];
-            VisualEval e;
-            eval_visual(d, x.pose + 7 * fi, x.pose + 7 * fj, x.ex, x.lam[l], d.est_td ? x.td[0] : 0.0, p.lm_pts[2 * l], p.lm_pts[2 * l + 1],
-                        p.ob_pts[2 * o], p.ob_pts[2 * o + 1], p.lm_vel[2 * l], p.lm_vel[2 * l + 1], p.ob_vel[2 * o], p.ob_vel[2 * o + 1],
-                        p.lm_td[l], p.ob_td[o], p.lm_row[l], p.ob_row[o], true, true, e);
-            int gc[20];
-            for (int q = 0; q < 6; q++) {
-                gc[q] = mp.col_pose[fi] + q;
-                gc[6 + q] = mp.col_pose[fj] + q;
-                gc[12 + q] = mp.col_ex + q;
-            }
-            gc[18] = mp.col_lm[li];
-            gc[19] = d.est_td ? mp.col_td : -1;
-            marg_scatter(mp.Am, mp.bm, P, &e.J[0][0], 20, 2, e.r, gc, 20, 0, 1);
+    if (blk >= dense_ctas) {
+        // landmark columns: one warp per marginalised landmark writes its column, diagonal and right-hand side
+        const int li = (blk - dense_ctas) * (nt / 32) + (tid >> 5), lane = tid & 31;
+        if (li >= nl) return;
+        const int l = mp.lms[li], cl = mp.col_lm[li];
+        const int an = p.lm_anchor[l], s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0;
+        const double* rec = a.lmW + (size_t)l * MARG_LW;
+        for (int idx = lane; idx < 6 * (nobs + 1); idx += 32) {
+            const int t = idx / 6, i = idx - 6 * t;
+            const double w = t == 0 ? rec[LW_WI + i] : a.obsJ[(size_t)(s0 + t - 1) * MARG_OJ + OJ_WJ + i];
+            const int col = mp.col_pose[an + t] + i;
+            if (col < cl) mp.Am[(size_t)col * P + cl] = w;
+            else mp.Am[(size_t)cl * P + col] = w;
         }
-    } else if (blk == nb_vis) {
-        if (wid == 0 && mp.use_imu) {
-            if (imu_whitened(p, x, 0, lane, sJraw[0], sJw[0], srr[0], srw[0])) {
-                __shared__ int gci[30];
-                if (lane < 30) {
-                    int c;
-                    if (lane < 6) c = mp.col_pose[0] + lane;
-                    else if (lane < 15) c = mp.col_sb[0] + lane - 6;
-                    else if (lane < 21) c = mp.col_pose[1] + lane - 15;
-                    else c = mp.col_sb[1] + lane - 21;
-                    gci[lane] = c;
+        if (lane < 6) {
+            const int col = mp.col_ex + lane;
+            mp.Am[(size_t)cl * P + col] = rec[LW_WE + lane];  // kept columns come after the landmark columns
+        }
+        if (lane == 6 && d.est_td && mp.col_td >= 0) mp.Am[(size_t)cl * P + mp.col_td] = rec[LW_WT];
+        if (lane == 7) {
+            mp.Am[(size_t)cl * P + cl] = rec[LW_HLL];
+            mp.bm[cl] = rec[LW_GL];
+        }
+        return;
+    }
+    // dense part: upper-triangle entries between non-landmark columns
+    const int total = Q * (Q + 1) / 2;
+    for (int idx = blk * nt + tid; idx < total; idx += dense_ctas * nt) {
+        int cb = (int)((sqrtf(8.f * (float)idx + 1.f) - 1.f) * 0.5f);
+        while (cb * (cb + 1) / 2 > idx) cb--;
+        while ((cb + 1) * (cb + 2) / 2 <= idx) cb++;
+        const int ra = idx - cb * (cb + 1) / 2;  // ra <= cb, reduced indices
+        const MargCol A = mcol[ra], B = mcol[cb];
+        // previous prior (J^T J = A), in the order the prior rows map to the columns
+        double h = 0.0;
+        if (p.prior.n > 0 && pinv_m[ra] >= 0 && pinv_m[cb] >= 0) h = p.prior.A[(size_t)pinv_m[ra] * p.prior.n + pinv_m[cb]];
+        // IMU factor between frames 0 and 1
+        auto loc0 = [](const MargCol& c) { return c.type > 1 || c.frame > 1 ? -1 : (c.frame == 0 ? (c.type == 0 ? c.i : 6 + c.i) : (c.type == 0 ? 15 + c.i : 21 + c.i)); };
+        const double* irec = a.imuJ;
+        if (mp.use_imu && irec[IMUJ_VALID] != 0.0) {
+            const int la = loc0(A), lb = loc0(B);
+            if (la >= 0 && lb >= 0) {
+                double s = 0;
+                for (int k = 0; k < 15; k++) s += irec[IMUJ_JW + k * 30 + la] * irec[IMUJ_JW + k * 30 + lb];
+                h += s;
+            }
+        }
+        // visual factors of the marginalised landmarks (all anchored in the dropped frame)
+        const bool va = A.type != 1, vb_ = B.type != 1;
+        double g = 0.0;
+        if (va && vb_) {
+            VBlock VA{A.type, A.frame, 0, A.type == 3 ? 1 : 6}, VB{B.type, B.frame, 0, B.type == 3 ? 1 : 6};
+            // block order pose < ex < td with poses by frame: (ra <= cb) does not imply it, so order the pair explicitly
+            const bool swap = (VA.type > VB.type) || (VA.type == 0 && VB.type == 0 && VA.frame > VB.frame);
+            for (int li = 0; li < nl; li++) {
+                const int l = mp.lms[li];
+                const int an = p.lm_anchor[l], s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0;
+                if (!lm_covers(VA, an, nobs) || !lm_covers(VB, an, nobs)) continue;
+                const double* rec = a.lmW + (size_t)l * MARG_LW;
+                h += swap ? vis_entry(a, MARG_OJ, rec, VB, VA, B.i, A.i, an, s0) : vis_entry(a, MARG_OJ, rec, VA, VB, A.i, B.i, an, s0);
+                if (ra == cb) g += vis_grad(a, MARG_OJ, rec, VA, A.i, an, s0);
+            }
+        }
+        const int fa = mfull[ra], fb = mfull[cb];
+        if (fa <= fb) mp.Am[(size_t)fa * P + fb] = h;
+        else mp.Am[(size_t)fb * P + fa] = h;
+        if (ra == cb) {
+            double gb = g;
+            if (p.prior.n > 0 && pinv_m[ra] >= 0) gb += a.gpr[pinv_m[ra]];
+            if (mp.use_imu && irec[IMUJ_VALID] != 0.0) {
+                const int la = loc0(A);
+                if (la >= 0) {
+                    double s = 0;
+                    for (int k = 0; k < 15; k++) s += irec[IMUJ_JW + k * 30 + la] * irec[IMUJ_RW + k];
+                    gb += s;
                 }
-                __syncwarp();
-                marg_scatter(mp.Am, mp.bm, P, sJw[0], 30, 15, srw[0], gci, 30, lane, 32);
             }
+            mp.bm[fa] = gb;
         }
-    } else {
-        // previous prior: J^T J = A, J^T r = g0 + A dx, columns through the kept-block -> marg column map
-        const BaPrior& pr = p.prior;
-        const int n = pr.n, tid = threadIdx.x, nt = blockDim.x;
-        if (n <= 0) return;
-        prior_dx(p, x, dx, tid, nt);
-        for (int b = tid; b < pr.nblocks; b += nt) {
-            const int type = pr.type[b], idx = pr.index[b], off = pr.off[b];
-            const int base = type == 0 ? mp.col_pose[idx] : type == 1 ? mp.col_sb[idx] : type == 2 ? mp.col_ex : mp.col_td;
-            const int sz = type == 0 || type == 2 ? 6 : type == 1 ? 9 : 1;
-            for (int q = 0; q < sz; q++) pcol[off + q] = base + q;
-        }
-        __syncthreads();
-        for (int aa = tid; aa < n; aa += nt) {
-            double s = pr.g0[aa];
-            for (int bb = 0; bb < n; bb++) s += pr.A[(size_t)aa * n + bb] * dx[bb];
-            gpr[aa] = s;
-        }
-        __syncthreads();
-        for (int idx = tid; idx < n * n; idx += nt) {
-            const int aa = idx / n, bb = idx % n;
-            const int ga = pcol[aa], gb = pcol[bb];
-            if (ga > gb || (ga == gb && aa != bb)) continue;
-            const double v = pr.A[idx];
-            if (v != 0.0) atomicAdd(&mp.Am[(size_t)ga * P + gb], v);
-        }
-        for (int aa = tid; aa < n; aa += nt) atomicAdd(&mp.bm[pcol[aa]], gpr[aa]);
     }
 }
 
@@ -1792,7 +1421,7 @@ __global__ void debug_visual_kernel(BaDims d, const double* __restrict__ prm, co
     if (threadIdx.x != 0) return;
     VisualEval e;
     // prm: pose_i 7 | pose_j 7 | ex 7 | inv_dep | td     dat: pts_i 2, pts_j 2, vel_i 2, vel_j 2, td_i, td_j, row_i, row_j
-    eval_visual(d, prm, prm + 7, prm + 14, prm[21], prm[22], dat[0], dat[1], dat[2], dat[3], dat[4], dat[5], dat[6], dat[7], dat[8],
+    eval_visual<true, true>(d, prm, prm + 7, prm + 14, prm[21], prm[22], dat[0], dat[1], dat[2], dat[3], dat[4], dat[5], dat[6], dat[7], dat[8],
                 dat[9], dat[10], dat[11], true, robust != 0, e);
     out[0] = e.r[0];
     out[1] = e.r[1];
@@ -1882,6 +1511,18 @@ void launch_preint_jobs(BaSeq* seqs, const BatchShape& sh, cudaStream_t s, int* 
     if (launches) *launches += 1;
 }
 
+namespace {
+
+void launch_eval(const BaSeq* seqs, const BatchShape& sh, int grid, int initial, cudaStream_t s) {
+    const dim3 g(grid, sh.S);
+    if (sh.est_ex && sh.est_td) ba_eval_kernel<true, true><<<g, 32 * LIN_WARPS, 0, s>>>(seqs, initial);
+    else if (sh.est_ex) ba_eval_kernel<true, false><<<g, 32 * LIN_WARPS, 0, s>>>(seqs, initial);
+    else if (sh.est_td) ba_eval_kernel<false, true><<<g, 32 * LIN_WARPS, 0, s>>>(seqs, initial);
+    else ba_eval_kernel<false, false><<<g, 32 * LIN_WARPS, 0, s>>>(seqs, initial);
+}
+
+}  // namespace
+
 void launch_ba_solve(BaSeq* seqs, const BatchShape& sh, cudaStream_t s, int* launches, KernelProfile* prof) {
     KernelProfile none;
     if (!prof) prof = &none;
@@ -1889,9 +1530,9 @@ void launch_ba_solve(BaSeq* seqs, const BatchShape& sh, cudaStream_t s, int* lau
     BaDims dmax{};
     dmax.L = sh.max_L;
     dmax.W = sh.W;
-    const int lin_grid = ba_linearize_grid(dmax);
-    const int zero_grid = 32;
-    const int tiles = (sh.D + ST - 1) / ST;
+    const int eval_grid = ba_eval_grid(dmax);
+    const int NV = sh.W + 1 + (sh.est_ex ? 1 : 0) + (sh.est_td ? 1 : 0), n_pairs = NV * (NV + 1) / 2;
+    const int generic = (sh.D * (sh.D + 1) / 2 + 4 * RED_THREADS - 1) / (4 * RED_THREADS);
     const size_t panel_bytes = sizeof(double) * CHOL_NB * CHOL_PS;
     const size_t chol_bytes = sizeof(double) * (size_t)(sh.D + 1) * (sh.D + 2) / 2 + panel_bytes;
     int use_smem;
@@ -1908,27 +1549,18 @@ void launch_ba_solve(BaSeq* seqs, const BatchShape& sh, cudaStream_t s, int* lau
     }
     int n = 0;
     prof->begin(s);
-    ba_zero_kernel<<<dim3(zero_grid, sh.S), 256, 0, s>>>(seqs, 1);
-    prof->end(3, s);
-    prof->begin(s);
-    ba_linearize_kernel<<<dim3(lin_grid, sh.S), 32 * LIN_WARPS, 0, s>>>(seqs, 1);
+    launch_eval(seqs, sh, eval_grid, 1, s);
     prof->end(0, s);
-    n += 2;
+    n += 1;
     for (int it = 0; it < sh.max_iterations; it++) {
         prof->begin(s);
-        ba_schur_kernel<<<dim3(tiles, tiles, sh.S), dim3(ST, ST), 0, s>>>(seqs);
+        ba_reduce_kernel<<<dim3(n_pairs + generic, sh.S), RED_THREADS, 0, s>>>(seqs, n_pairs);
         prof->end(1, s);
         prof->begin(s);
         ba_step_kernel<<<sh.S, 512, step_dyn, s>>>(seqs, use_smem);
         prof->end(2, s);
-        if (tiles < 2) {  // no lower-triangle CTA to do the clearing (never at the supported window sizes)
-            prof->begin(s);
-            ba_zero_kernel<<<dim3(zero_grid, sh.S), 256, 0, s>>>(seqs, 0);
-            prof->end(3, s);
-            n += 1;
-        }
         prof->begin(s);
-        ba_linearize_kernel<<<dim3(lin_grid, sh.S), 32 * LIN_WARPS, 0, s>>>(seqs, 0);
+        launch_eval(seqs, sh, eval_grid, 0, s);
         prof->end(0, s);
         n += 3;
     }
@@ -1953,15 +1585,18 @@ void launch_marginalize(BaSeq* seqs, const BatchShape& sh, cudaStream_t s, int* 
         }
     }
     const int zgrid = std::max(1, std::min(64, (int)(((size_t)sh.max_P * sh.max_P + 256 * 8 - 1) / (256 * 8))));
-    const int grid = (sh.max_n_lm + 3) / 4 + 2;
+    const int egrid = (sh.max_n_lm + LIN_WARPS - 1) / LIN_WARPS + 2;
+    const int dense_ctas = 16, lm_ctas = (sh.max_n_lm + 3) / 4;
     prof->begin(s);
     marg_zero_kernel<<<dim3(zgrid, sh.S), 256, 0, s>>>(seqs);
-    marg_build_kernel<<<dim3(grid, sh.S), 128, 0, s>>>(seqs);
-    prof->end(4, s, 2);
+    if (sh.est_td) marg_eval_kernel<true><<<dim3(egrid, sh.S), 32 * LIN_WARPS, 0, s>>>(seqs);
+    else marg_eval_kernel<false><<<dim3(egrid, sh.S), 32 * LIN_WARPS, 0, s>>>(seqs);
+    marg_gather_kernel<<<dim3(dense_ctas + lm_ctas, sh.S), 128, 0, s>>>(seqs, dense_ctas);
+    prof->end(4, s, 3);
     prof->begin(s);
     marg_solve_kernel<<<sh.S, MARG_THREADS, smem, s>>>(seqs, 1e-8);
     prof->end(5, s);
-    if (launches) *launches += 3;
+    if (launches) *launches += 4;
 }
 
 void launch_debug_visual(const BaDims& d, const double* d_params23, const double* d_data16, int robust, double* d_out, cudaStream_t s) {

@@ -17,11 +17,12 @@ struct BatchShape {  // host-side maxima over the members of this frame: grid an
     int max_md, max_n;   // marginalisation: dense marginalised columns, kept columns
     int max_P;           // marginalisation system size
     int any_jobs, any_active, any_marg;
+    int est_ex, est_td;  // which optional parameter blocks are live (uniform over the batch: selects the kernel variants)
     int max_iterations;
     int w_in_global;     // marginalisation reduced system in global memory (decided once per batch: marg_w_in_global)
 };
 
-// profile slots: 0 linearize, 1 schur, 2 step, 3 zero, 4 marg_build, 5 marg_solve, 6 preint, 7 finish
+// profile slots: 0 eval (linearise), 1 reduce (Schur gather), 2 step, 3 unused, 4 marg zero + eval + gather, 5 marg_solve, 6 preint, 7 finish
 // Pre-integration jobs (new slots, pushed samples, refreshed sqrt_info) of all members.
 void launch_preint_jobs(BaSeq* seqs, const BatchShape& sh, cudaStream_t s, int* launches, KernelProfile* prof = nullptr);
 // Full trust-region solve of every active member: linearise x[st.cur], then max_iterations x {schur, step,

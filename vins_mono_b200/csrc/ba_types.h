@@ -34,6 +34,7 @@ struct BaDims {
     int col_ex;   // -1 when the extrinsic is constant
     int col_td;   // -1 when td is not estimated
     int pad;
+    int oj, lw;   // strides (doubles) of the per-observation / per-landmark linearisation records (BaAccum)
     double sqrt_info_vis;  // FOCAL_LENGTH / 1.5
     double tr_over_row;    // TR / ROW
     double half_row;       // ROW / 2 (projection_td_factor.cpp:18-19)
@@ -48,13 +49,28 @@ struct BaStates {  // one point x: Ceres parameter layouts
     double* lam;   // L inverse depths
 };
 
-struct BaAccum {  // normal equations of one linearization point (unscaled)
-    double* Hpp;  // D x D, upper triangle (row <= col) accumulated, rest zero
-    double* gp;   // D
-    double* Hpl;  // L x D dense rows (J_l^T J_p)
-    double* Hll;  // L
-    double* gl;   // L
-    double* cost; // 1
+// One linearisation point, factor by factor (nothing is accumulated with atomics: the normal equations are gathered
+// from these records in a fixed order by ba_reduce_kernel, so a solve is bit-reproducible).  Record layouts:
+//   obsJ  per visual residual block o (stride dims.oj):  Ji 2x6 | Jj 2x6 | r 2 | Jl 2 | wj = Jj^T Jl 6 | [Jex 2x6] [Jtd 2]
+//   lmW   per landmark l (stride dims.lw), sums over its observations:
+//         Hii = sum Ji^T Ji (21, packed upper) | gi = sum Ji^T r 6 | wi = sum Ji^T Jl 6 | Hll | gl | cost |
+//         [Hie 6x6 | Hee 21 | ge 6 | we 6] [Hit 6 | Het 6 | Htt | gt | wt]
+//   imuJ  per IMU factor k (stride 480): whitened Jacobian 15x30 | whitened residual 15 | cost | valid
+//   gpr   prior gradient g0 + A dx (n), cost of the prior at gpr[BA_PRIOR_COST]
+enum : int {
+    OJ_JI = 0, OJ_JJ = 12, OJ_R = 24, OJ_JL = 26, OJ_WJ = 28, OJ_BASE = 34, OJ_JEX = 34, OJ_JTD = 46, OJ_FULL = 48,
+    LW_HII = 0, LW_GI = 21, LW_WI = 27, LW_HLL = 33, LW_GL = 34, LW_COST = 35, LW_BASE = 36,
+    LW_HIE = 36, LW_HEE = 72, LW_GE = 93, LW_WE = 99, LW_HIT = 105, LW_HET = 111, LW_HTT = 117, LW_GT = 118, LW_WT = 119, LW_FULL = 120,
+    IMUJ_JW = 0, IMUJ_RW = 450, IMUJ_COST = 465, IMUJ_VALID = 466, IMUJ_STRIDE = 480,
+    BA_PRIOR_COST = 160
+};
+struct BaAccum {
+    double* obsJ;  // M x oj
+    double* lmW;   // L x lw
+    double* imuJ;  // W x IMUJ_STRIDE
+    double* gpr;   // BA_PRIOR_COST + 1
+    double* gp;    // D: gradient of the camera-side parameters (written by ba_reduce_kernel)
+    double* cost;  // 1: total cost, summed in a fixed order by the last CTA of ba_eval_kernel
 };
 
 struct BaPrior {  // MarginalizationInfo in information form: A = J0^T J0, g0 = J0^T r0, c0 = |r0|^2

@@ -179,7 +179,10 @@ namespace {
     } while (0)
 
 size_t states_doubles(const ve_estimator* e, int L) { return (size_t)(e->W + 1) * 16 + 8 + L; }
-size_t acc_doubles(const ve_estimator* e) { return (size_t)e->D * e->D + e->D + (size_t)e->Lmax * e->D + 2 * (size_t)e->Lmax + 1; }
+// per-factor linearisation records of one point (BaAccum): obsJ | lmW | imuJ | gpr | gp | cost, at the widest strides
+size_t acc_doubles(const ve_estimator* e) {
+    return (size_t)e->Mmax * vb::OJ_FULL + (size_t)e->Lmax * vb::LW_FULL + (size_t)e->W * vb::IMUJ_STRIDE + (vb::BA_PRIOR_COST + 8) + e->D + 8;
+}
 size_t align16(size_t bytes) { return (bytes + 15) & ~(size_t)15; }
 
 vb::BaStates states_view(double* p, int F) {
@@ -724,14 +727,17 @@ int stage_frame(ve_estimator* e, bool solve) {
     d.G[0] = 0; d.G[1] = 0; d.G[2] = e->cfg.g_norm;
     p.x[0] = states_view(reinterpret_cast<double*>(db + o_states), F);
     p.x[1] = states_view(e->d_states1.p, F);
-    for (int k = 0; k < 2; k++) {  // the accumulation buffers were sized for the maximum D; the kernels index with dims.D
+    const bool wide = d.est_ex || d.est_td;
+    d.oj = wide ? vb::OJ_FULL : vb::OJ_BASE;
+    d.lw = wide ? vb::LW_FULL : vb::LW_BASE;
+    for (int k = 0; k < 2; k++) {  // sized for the widest records; the kernels index with dims.oj / dims.lw
         double* a = e->d_acc[k].p;
-        p.acc[k].Hpp = a;
-        p.acc[k].gp = a + (size_t)d.D * d.D;
-        p.acc[k].Hpl = p.acc[k].gp + d.D;
-        p.acc[k].Hll = p.acc[k].Hpl + (size_t)e->Lmax * d.D;
-        p.acc[k].gl = p.acc[k].Hll + e->Lmax;
-        p.acc[k].cost = p.acc[k].gl + e->Lmax;
+        p.acc[k].obsJ = a;
+        p.acc[k].lmW = a + (size_t)e->Mmax * vb::OJ_FULL;
+        p.acc[k].imuJ = p.acc[k].lmW + (size_t)e->Lmax * vb::LW_FULL;
+        p.acc[k].gpr = p.acc[k].imuJ + (size_t)e->W * vb::IMUJ_STRIDE;
+        p.acc[k].gp = p.acc[k].gpr + vb::BA_PRIOR_COST + 8;
+        p.acc[k].cost = p.acc[k].gp + e->D;
     }
     const int* di = reinterpret_cast<const int*>(db + o_int);
     p.lm_anchor = di;
@@ -1008,6 +1014,8 @@ int batch_process(ve_batch* b, const FrameMsg* msgs, int* status_out) {
     sh.W = b->cfg.window_size;
     sh.D = b->members[0]->D - (b->cfg.estimate_extrinsic ? 0 : 6) - (b->cfg.estimate_td ? 0 : 1);
     sh.max_iterations = b->cfg.num_iterations;
+    sh.est_ex = b->cfg.estimate_extrinsic ? 1 : 0;
+    sh.est_td = b->cfg.estimate_td ? 1 : 0;
     sh.w_in_global = b->w_in_global;
     for (int k = 0; k < S; k++) {
         const vb::BaSeq& q = b->h_seq[k];
