@@ -228,11 +228,16 @@ extern "C" {
 // ---------------------------------------------------------------------------
 // Pyramidal LK exactly as OpenCV's LKTrackerInvoker (video/lkpyramid.cpp), flags = 0,
 // criteria = COUNT+EPS (30, 0.01), minEigThreshold 1e-4.  The window sums A11/A12/A22/b1/b2 are sums
-// of integer products; they are accumulated EXACTLY in int64 (OpenCV's own `acctype` on its CV_NEON
-// build) and converted to float once, which makes the result independent of summation order.  OpenCV's
-// x86 build accumulates the same terms in 4 float SIMD lanes, whose lane order is not part of the
-// algorithm: against cv2 4.13 x86 this restatement agrees to <= ~1e-4 px with identical status flags
-// (checked in tests/test_oracle_frontend.py).
+// of integer products accumulated in float exactly the way OpenCV's x86 (CV_SIMD128) build does it: 16 pixels
+// of every window row through four float lanes, the remaining 5 through a scalar float, lanes combined as
+// (l0 + l2) + (l1 + l3) at the end.  Against cv2 4.13 this restatement is bit-exact (coordinates and status;
+// tests/test_oracle_frontend.py).  orc_lk_set_simd_sums(0) switches to exact int64 sums (the accumulator type of
+// OpenCV's NEON build), which differ from the x86 results by <= ~1e-4 px.
+// 1 (default): window sums accumulated like OpenCV's x86 SIMD path (bit-exact against cv2 4.13, verified in
+// tests/test_oracle_frontend.py); 0: exact int64 sums (OpenCV's NEON accumulator type), kept for comparison.
+static int simd_sums = 1;
+void orc_lk_set_simd_sums(int on) { simd_sums = on != 0; }
+
 void orc_lk(const uint8_t* prev, const uint8_t* next, int rows, int cols, int stride, const float* prev_pts, int n,
             int win, int max_level, int max_iter, double eps, double min_eig_thr, float* next_pts,
             uint8_t* status) {
@@ -275,6 +280,11 @@ void orc_lk(const uint8_t* prev, const uint8_t* next, int rows, int cols, int st
             int iw01 = cv_round_f(a * (1.f - b) * (1 << W_BITS));
             int iw10 = cv_round_f((1.f - a) * b * (1 << W_BITS));
             int iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+            // Window sums in OpenCV's own accumulation structure (video/lkpyramid.cpp, CV_SIMD128 path of the x86 builds):
+            // per row the first 16 pixels go through four float lanes (lane j takes pixels j, 4+j, 8+j, 12+j), the last
+            // five through a scalar float accumulator; at the end total = scalar + ((l0 + l2) + (l1 + l3)).
+            float qA11[4] = {0, 0, 0, 0}, qA12[4] = {0, 0, 0, 0}, qA22[4] = {0, 0, 0, 0}, sA11 = 0, sA12 = 0, sA22 = 0;
+            const int nsimd = simd_sums ? (win / 8) * 8 : 0;
             int64_t iA11 = 0, iA12 = 0, iA22 = 0;
             for (int y = 0; y < win; y++)
                 for (int x = 0; x < win; x++) {
@@ -294,8 +304,23 @@ void orc_lk(const uint8_t* prev, const uint8_t* next, int rows, int cols, int st
                     iA11 += (int64_t)ixval * ixval;
                     iA12 += (int64_t)ixval * iyval;
                     iA22 += (int64_t)iyval * iyval;
+                    if (x < nsimd) {
+                        const float fx = (float)ixval, fy = (float)iyval;
+                        qA22[x & 3] += fy * fy;
+                        qA12[x & 3] += fx * fy;
+                        qA11[x & 3] += fx * fx;
+                    } else {
+                        sA11 += (float)(ixval * ixval);
+                        sA12 += (float)(ixval * iyval);
+                        sA22 += (float)(iyval * iyval);
+                    }
                 }
             float A11 = (float)iA11 * FLT_SCALE, A12 = (float)iA12 * FLT_SCALE, A22 = (float)iA22 * FLT_SCALE;
+            if (simd_sums) {
+                A11 = (sA11 + ((qA11[0] + qA11[2]) + (qA11[1] + qA11[3]))) * FLT_SCALE;
+                A12 = (sA12 + ((qA12[0] + qA12[2]) + (qA12[1] + qA12[3]))) * FLT_SCALE;
+                A22 = (sA22 + ((qA22[0] + qA22[2]) + (qA22[1] + qA22[3]))) * FLT_SCALE;
+            }
             float D = A11 * A22 - A12 * A12;
             float minEig = (A22 + A11 - std::sqrt((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (2 * win * win);
             if (minEig < (float)min_eig_thr || D < FLT_EPSILON) {
@@ -319,6 +344,10 @@ void orc_lk(const uint8_t* prev, const uint8_t* next, int rows, int cols, int st
                 iw10 = cv_round_f((1.f - a) * b * (1 << W_BITS));
                 iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
                 int64_t ib1 = 0, ib2 = 0;
+                // mismatch vector: per row and block of 8 pixels, lane pairs (k, k+4) are summed as integers
+                // (v_dotprod), converted to float and added to the float lanes qb0 (k = 0, 1) / qb1 (k = 2, 3)
+                float qb0[4] = {0, 0, 0, 0}, qb1[4] = {0, 0, 0, 0}, sb1 = 0, sb2 = 0;
+                int dbuf[8], xbuf[8], ybuf[8];
                 for (int y = 0; y < win; y++)
                     for (int x = 0; x < win; x++) {
                         int yy = y + iny, xx = x + inx;
@@ -326,10 +355,34 @@ void orc_lk(const uint8_t* prev, const uint8_t* next, int rows, int cols, int st
                                                J.px(yy + 1, xx + 1) * iw11,
                                            W_BITS - 5) -
                                    Iw[y * win + x];
-                        ib1 += (int64_t)diff * dIw[(y * win + x) * 2];
-                        ib2 += (int64_t)diff * dIw[(y * win + x) * 2 + 1];
+                        const int ixv = dIw[(y * win + x) * 2], iyv = dIw[(y * win + x) * 2 + 1];
+                        ib1 += (int64_t)diff * ixv;
+                        ib2 += (int64_t)diff * iyv;
+                        if (x < nsimd) {
+                            dbuf[x & 7] = diff;
+                            xbuf[x & 7] = ixv;
+                            ybuf[x & 7] = iyv;
+                            if ((x & 7) == 7) {
+                                qb0[0] += (float)(dbuf[0] * xbuf[0] + dbuf[4] * xbuf[4]);
+                                qb0[1] += (float)(dbuf[0] * ybuf[0] + dbuf[4] * ybuf[4]);
+                                qb0[2] += (float)(dbuf[1] * xbuf[1] + dbuf[5] * xbuf[5]);
+                                qb0[3] += (float)(dbuf[1] * ybuf[1] + dbuf[5] * ybuf[5]);
+                                qb1[0] += (float)(dbuf[2] * xbuf[2] + dbuf[6] * xbuf[6]);
+                                qb1[1] += (float)(dbuf[2] * ybuf[2] + dbuf[6] * ybuf[6]);
+                                qb1[2] += (float)(dbuf[3] * xbuf[3] + dbuf[7] * xbuf[7]);
+                                qb1[3] += (float)(dbuf[3] * ybuf[3] + dbuf[7] * ybuf[7]);
+                            }
+                        } else {
+                            sb1 += (float)(diff * ixv);
+                            sb2 += (float)(diff * iyv);
+                        }
                     }
                 float b1 = (float)ib1 * FLT_SCALE, b2 = (float)ib2 * FLT_SCALE;
+                if (simd_sums) {
+                    const float q0 = qb0[0] + qb1[0], q1 = qb0[1] + qb1[1], q2 = qb0[2] + qb1[2], q3 = qb0[3] + qb1[3];
+                    b1 = (sb1 + (q0 + q2)) * FLT_SCALE;
+                    b2 = (sb2 + (q1 + q3)) * FLT_SCALE;
+                }
                 float dx = (float)((A12 * b2 - A22 * b1) * D);
                 float dy = (float)((A12 * b1 - A11 * b2) * D);
                 nx += dx;

@@ -136,7 +136,8 @@ class Cv2Tracker:
             for i in range(len(un)):
                 if self.ids[i] != -1 and int(self.ids[i]) in self.prev_un_map:
                     pu = self.prev_un_map[int(self.ids[i])]
-                    vel[i] = ((float(un[i, 0]) - float(pu[0])) / dt, (float(un[i, 1]) - float(pu[1])) / dt)
+                    # double v_x = (cur_un_pts[i].x - it->second.x) / dt: the difference of two floats is a float
+                    vel[i] = (float(np.float32(un[i, 0]) - np.float32(pu[0])) / dt, float(np.float32(un[i, 1]) - np.float32(pu[1])) / dt)
         self.prev_un_map = cur_map
         self.prev_time = t
         self.un_pts, self.velocity = un, vel
@@ -196,7 +197,15 @@ def image_hash(imgs):
     return hashlib.sha256(np.ascontiguousarray(imgs).tobytes()).hexdigest()
 
 
-TRACK_SEED, TRACK_FRAMES = 7, 25
+TRACK_SEED, TRACK_FRAMES, TRACK_FULL = 0, 240, 30   # bench.py's sequence (seed 0); full arrays for the first frames, digests for all
+
+
+def result_digest(res):
+    """Bit-level digest of one frame's public result vectors."""
+    h = hashlib.sha256()
+    for k in ("ids", "track_cnt", "cur_pts", "un_pts", "velocity"):
+        h.update(np.ascontiguousarray(res[k]).tobytes())
+    return h.hexdigest()[:24]
 
 
 def main():
@@ -235,17 +244,24 @@ def main():
     ops["fm_count"] = np.array(len(fm))
     np.savez_compressed(os.path.join(HERE, "frontend_ops.npz"), **ops)
 
-    seq = synth.Sequence(seed=TRACK_SEED, duration=2.0)
+    seq = synth.Sequence(seed=TRACK_SEED, duration=TRACK_FRAMES / 20.0 + 0.5)
     ts, imgs = seq.images(TRACK_FRAMES)
     cfg = synth.tracker_config_dict()
     tr = Cv2Tracker(cfg)
-    out = dict(opencv_version=cv2.__version__, images_sha=image_hash(imgs), seed=np.array(TRACK_SEED), n_frames=np.array(TRACK_FRAMES))
+    out = dict(opencv_version=cv2.__version__, images_sha=image_hash(imgs), seed=np.array(TRACK_SEED), n_frames=np.array(TRACK_FRAMES),
+               n_full=np.array(TRACK_FULL))
+    rets, digests, counts = [], [], []
     for i in range(TRACK_FRAMES):
-        r = tr.node_image(imgs[i], float(ts[i]))
-        out[f"f{i}_ret"] = np.array(r)
-        if r:
-            for k, v in tr.result().items():
-                out[f"f{i}_{k}"] = v
+        r = tr.node_image(np.ascontiguousarray(imgs[i]), float(ts[i]))
+        rets.append(r)
+        digests.append(result_digest(tr.result()) if r else "")
+        counts.append(len(tr.ids) if r else 0)
+        if i < TRACK_FULL:
+            out[f"f{i}_ret"] = np.array(r)
+            if r:
+                for k, v in tr.result().items():
+                    out[f"f{i}_{k}"] = v
+    out["rets"], out["digests"], out["counts"], out["final_n_id"] = np.array(rets), np.array(digests), np.array(counts), np.array(tr.n_id)
     np.savez_compressed(os.path.join(HERE, "frontend_track.npz"), **out)
     print("wrote golden; last frame tracks:", len(tr.ids), "n_id:", tr.n_id)
 

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import orc
-from harness import synth
+from harness import synth, pipeline
 
 pytestmark = pytest.mark.gpu
 
@@ -230,3 +230,27 @@ def test_tracker_config_variants_match_oracle(FT, variant):
                 assert (mask[p[new, 1], p[new, 0]] == 255).all()      # detections only inside the fisheye mask
         n_pub += rc == 2
     assert n_pub >= 5 and n_feat >= 40
+
+
+def test_tracker_bit_identical_to_cv2_twin_over_bench_sequence(FT):
+    """The CUDA tracker against the golden digests of the cv2-backed (real OpenCV) twin of readImage + img_callback over the
+    whole bench sequence (240 frames of seed 0, 119 publishes, > 1000 ids): ids, track counts, pixel / undistorted coordinates
+    and velocities bit-identical in every frame (tests/golden/make_frontend_golden.py generated the digests with cv2 4.13)."""
+    import hashlib
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frontend_track.npz"))
+    n = int(g["n_frames"])
+    seq = synth.Sequence(seed=int(g["seed"]), duration=n / 20.0 + 0.5)
+    ts, imgs = pipeline.cached_images(seq, n)
+    assert hashlib.sha256(np.ascontiguousarray(imgs).tobytes()).hexdigest() == str(g["images_sha"])
+    tr = FT(**synth.tracker_config_dict())
+    for i in range(n):
+        r, restart = tr.node_image(imgs[i], float(ts[i]))
+        assert r == int(g["rets"][i]) and restart == 0
+        if not r:
+            continue
+        res = tr.result()
+        h = hashlib.sha256()
+        for k in ("ids", "track_cnt", "cur_pts", "un_pts", "velocity"):
+            h.update(np.ascontiguousarray(res[k]).tobytes())
+        assert len(res["ids"]) == int(g["counts"][i]) and h.hexdigest()[:24] == str(g["digests"][i]), f"diverged from the cv2 twin at frame {i}"

@@ -178,7 +178,10 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(const FeSeq* __restrict__ 
 
 // ---------------------------------------------------------------------------------------------
 // Pyramidal Lucas-Kanade, one 128-thread CTA per point, all levels inside one launch.
-// Mirrors OpenCV's LKTrackerInvoker with exact (int64) window sums.  Per level the CTA stages the
+// Mirrors OpenCV's LKTrackerInvoker including the float accumulation structure of its x86 (CV_SIMD128) build: per window
+// row 16 pixels go through four float lanes and 5 through a scalar float, lanes are combined as (l0 + l2) + (l1 + l3); the
+// per-pixel terms are produced by all threads, the (inherently sequential) float chains run on 15 / 10 threads.  Results
+// are bit-identical to cv2 4.13 (tests: oracle vs cv2 golden vectors on the CPU, kernel vs oracle on the GPU).  Per level the CTA stages the
 // 24x24 previous-image neighbourhood in shared memory, derives the Scharr gradient there (zero outside
 // the image, reflect-101 inside), builds the 21x21 int16 patch + gradient patch, then iterates on a cached
 // 40x40 region of the next image.  The 441-pixel window is spread over 4 warps (the track count of a frame, 150,
@@ -191,17 +194,13 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(const FeSeq* __restrict__ 
 struct LkSmem {
     uint8_t tile[24 * 24];       // previous-level neighbourhood
     uint8_t region[LK_RS * LK_RS];  // next-level search region (reflect-101 padded coordinates)
-    long long red[2][LK_WARPS][3];  // cross-warp exchange, double buffered (one barrier per reduction)
     int16_t deriv[22 * 22 * 2];  // Scharr dx,dy at the 22x22 bilinear source positions
     int16_t iwin[441];
     int16_t dwin[441 * 2];
+    float tx[21 * 8], ty[21 * 8];  // mismatch terms of the 16 SIMD pixels of a row: [row][block 0..1][pair k 0..3]
+    float ux[21 * 5], uy[21 * 5];  // the 5 scalar-tail pixels of a row
+    float chain[16];
 };
-
-__device__ __forceinline__ long long warp_sum_ll(long long v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 __global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(const FeSeq* __restrict__ seqs, int max_iter, double eps2,
                                                                  float min_eig_thr) {
@@ -218,7 +217,6 @@ __global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(const FeSeq* __
     float* __restrict__ next_pts = q.pts_out;
     uint8_t* __restrict__ status = q.status;
     const int img_rows = prev.rows[0], img_cols = prev.cols[0];
-    int rpar = 0;
     const int W = 21;
     const float half = 10.f;
     const float FLT_SCALE = 1.f / (1 << 20);
@@ -277,7 +275,6 @@ __global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(const FeSeq* __
             sm.deriv[2 * i + 1] = (int16_t)ddy;
         }
         __syncthreads();
-        long long a11 = 0, a12 = 0, a22 = 0;
         for (int i = lane; i < 441; i += NT) {
             const int y = i / 21, x = i - y * 21;
             const uint8_t* t = &sm.tile[(y + 1) * 24 + (x + 1)];
@@ -288,30 +285,42 @@ __global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(const FeSeq* __
             sm.iwin[i] = (int16_t)ival;
             sm.dwin[2 * i] = (int16_t)ixval;
             sm.dwin[2 * i + 1] = (int16_t)iyval;
-            a11 += (long long)(ixval * ixval);
-            a12 += (long long)(ixval * iyval);
-            a22 += (long long)(iyval * iyval);
-        }
-        a11 = warp_sum_ll(a11);
-        a12 = warp_sum_ll(a12);
-        a22 = warp_sum_ll(a22);
-        if (wl == 0) {
-            sm.red[rpar][wid][0] = a11;
-            sm.red[rpar][wid][1] = a12;
-            sm.red[rpar][wid][2] = a22;
         }
         __syncthreads();
-        a11 = a12 = a22 = 0;
+        // window sums A11, A12, A22: 12 lane chains (quantity q, lane j: pixels j, 4+j, 8+j, 12+j of every row, float product
+        // then float add) and 3 scalar-tail chains (pixels 16..20, integer product converted to float)
+        if (lane < 15) {
+            const int qi = lane < 12 ? lane >> 2 : lane - 12, j = lane & 3;
+            float acc = 0.f;
+            if (lane < 12) {
+                for (int y = 0; y < 21; y++)
 #pragma unroll
-        for (int w = 0; w < LK_WARPS; w++) {
-            a11 += sm.red[rpar][w][0];
-            a12 += sm.red[rpar][w][1];
-            a22 += sm.red[rpar][w][2];
+                    for (int g = 0; g < 4; g++) {
+                        const int i = y * 21 + 4 * g + j;
+                        const float fx = (float)sm.dwin[2 * i], fy = (float)sm.dwin[2 * i + 1];
+                        const float term = qi == 0 ? __fmul_rn(fx, fx) : qi == 1 ? __fmul_rn(fx, fy) : __fmul_rn(fy, fy);
+                        acc = __fadd_rn(acc, term);
+                    }
+            } else {
+                for (int y = 0; y < 21; y++)
+#pragma unroll
+                    for (int x = 16; x < 21; x++) {
+                        const int i = y * 21 + x;
+                        const int ix = sm.dwin[2 * i], iy = sm.dwin[2 * i + 1];
+                        const int prod = qi == 0 ? ix * ix : qi == 1 ? ix * iy : iy * iy;
+                        acc = __fadd_rn(acc, __int2float_rn(prod));
+                    }
+            }
+            sm.chain[lane] = acc;
         }
-        rpar ^= 1;
-        const float A11 = __fmul_rn(__ll2float_rn(a11), FLT_SCALE);
-        const float A12 = __fmul_rn(__ll2float_rn(a12), FLT_SCALE);
-        const float A22 = __fmul_rn(__ll2float_rn(a22), FLT_SCALE);
+        __syncthreads();
+        float A11, A12, A22;
+        {
+            const float* c = sm.chain;
+            A11 = __fmul_rn(__fadd_rn(c[12], __fadd_rn(__fadd_rn(c[0], c[2]), __fadd_rn(c[1], c[3]))), FLT_SCALE);
+            A12 = __fmul_rn(__fadd_rn(c[13], __fadd_rn(__fadd_rn(c[4], c[6]), __fadd_rn(c[5], c[7]))), FLT_SCALE);
+            A22 = __fmul_rn(__fadd_rn(c[14], __fadd_rn(__fadd_rn(c[8], c[10]), __fadd_rn(c[9], c[11]))), FLT_SCALE);
+        }
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
         const float dif = __fsub_rn(A11, A22);
         const float disc = __fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12));
@@ -352,29 +361,53 @@ __global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(const FeSeq* __
                 have_region = true;
             }
             const uint8_t* rbase = &sm.region[(iny - ry0) * LK_RS + (inx - rx0)];
-            long long b1 = 0, b2 = 0;
-            for (int i = lane; i < 441; i += NT) {
-                const int y = i / 21, x = i - y * 21;
+            auto mismatch = [&](int y, int x, int& px, int& py) {  // (J - I) * (Ix, Iy) of one window pixel, exact integers
+                const int i = y * 21 + x;
                 const uint8_t* t = rbase + y * LK_RS + x;
                 const int diff = ((t[0] * iw00 + t[1] * iw01 + t[LK_RS] * iw10 + t[LK_RS + 1] * iw11 + (1 << 8)) >> 9) - sm.iwin[i];
-                b1 += (long long)(diff * sm.dwin[2 * i]);
-                b2 += (long long)(diff * sm.dwin[2 * i + 1]);
-            }
-            b1 = warp_sum_ll(b1);
-            b2 = warp_sum_ll(b2);
-            if (wl == 0) {
-                sm.red[rpar][wid][0] = b1;
-                sm.red[rpar][wid][1] = b2;
+                px = diff * sm.dwin[2 * i];
+                py = diff * sm.dwin[2 * i + 1];
+            };
+            // work items: 168 pixel pairs (k, k + 4) of the SIMD part (integer pair sum -> float, like v_dotprod + v_cvt_f32)
+            // and 105 single pixels of the scalar tail
+            for (int w = lane; w < 168 + 105; w += NT) {
+                if (w < 168) {
+                    const int y = w >> 3, bk = w & 7, b = bk >> 2, k = bk & 3;
+                    int ax, ay, bx, by;
+                    mismatch(y, 8 * b + k, ax, ay);
+                    mismatch(y, 8 * b + k + 4, bx, by);
+                    sm.tx[w] = __int2float_rn(ax + bx);
+                    sm.ty[w] = __int2float_rn(ay + by);
+                } else {
+                    const int u = w - 168, y = u / 5, x = 16 + (u - 5 * y);
+                    int ax, ay;
+                    mismatch(y, x, ax, ay);
+                    sm.ux[u] = __int2float_rn(ax);
+                    sm.uy[u] = __int2float_rn(ay);
+                }
             }
             __syncthreads();
-            b1 = b2 = 0;
-#pragma unroll
-            for (int w = 0; w < LK_WARPS; w++) {
-                b1 += sm.red[rpar][w][0];
-                b2 += sm.red[rpar][w][1];
+            if (lane < 10) {
+                float acc = 0.f;
+                if (lane < 8) {  // lane chains: X / Y of pair k, rows in order, block 0 then block 1
+                    const float* src = (lane & 1) ? sm.ty : sm.tx;
+                    const int k = lane >> 1;
+                    for (int y = 0; y < 21; y++) {
+                        acc = __fadd_rn(acc, src[y * 8 + k]);
+                        acc = __fadd_rn(acc, src[y * 8 + 4 + k]);
+                    }
+                } else {
+                    const float* src = lane == 8 ? sm.ux : sm.uy;
+                    for (int u = 0; u < 105; u++) acc = __fadd_rn(acc, src[u]);
+                }
+                sm.chain[lane] = acc;
             }
-            rpar ^= 1;
-            const float fb1 = __fmul_rn(__ll2float_rn(b1), FLT_SCALE), fb2 = __fmul_rn(__ll2float_rn(b2), FLT_SCALE);
+            __syncthreads();
+            // qb0 = {X0, Y0, X1, Y1}, qb1 = {X2, Y2, X3, Y3}; q = qb0 + qb1; b1 = tail + (q0 + q2), b2 = tail + (q1 + q3)
+            const float* c = sm.chain;
+            const float q0 = __fadd_rn(c[0], c[4]), q1 = __fadd_rn(c[1], c[5]), q2 = __fadd_rn(c[2], c[6]), q3 = __fadd_rn(c[3], c[7]);
+            const float fb1 = __fmul_rn(__fadd_rn(c[8], __fadd_rn(q0, q2)), FLT_SCALE);
+            const float fb2 = __fmul_rn(__fadd_rn(c[9], __fadd_rn(q1, q3)), FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb2), __fmul_rn(A22, fb1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb1), __fmul_rn(A11, fb2)), D);
             nx = __fadd_rn(nx, dx);
