@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(const FeSeq* __restrict__ 
 // Mirrors OpenCV's LKTrackerInvoker including the float accumulation structure of its x86 (CV_SIMD128) build: per window
 // row 16 pixels go through four float lanes and 5 through a scalar float, lanes are combined as (l0 + l2) + (l1 + l3); the
 // per-pixel terms are produced by all threads, the (inherently sequential) float chains run on 15 / 10 threads.  Results
-// are bit-identical to cv2 4.13 (tests: oracle vs cv2 golden vectors on the CPU, kernel vs oracle on the GPU).  Per level the CTA stages the
+// are bit-identical to cv2 4.13 (tests/test_frontend_gpu.py checks the golden digests of the cv2-backed twin).  Per level the CTA stages the
 // 24x24 previous-image neighbourhood in shared memory, derives the Scharr gradient there (zero outside
 // the image, reflect-101 inside), builds the 21x21 int16 patch + gradient patch, then iterates on a cached
 // 40x40 region of the next image.  The 441-pixel window is spread over 4 warps (the track count of a frame, 150,
