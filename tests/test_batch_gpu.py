@@ -39,7 +39,6 @@ def test_batch_members_match_standalone_and_oracle():
     # member 3 starts two frames late, member 1 skips nothing but idles on frame 7 of the schedule (its message is delivered
     # one step later): the batch must cope with members in different phases
     cursor = [0] * n
-    worst_solo = dict(p=0, q=0, v=0, ba=0, bg=0)
     worst_cpu = dict(p=0, q=0, v=0, ba=0, bg=0)
     n_nl = 0
     for step in range(n_pub + 3):
@@ -71,14 +70,12 @@ def test_batch_members_match_standalone_and_oracle():
                 continue
             n_nl += 1
             sa, sb, sc = batch.members[k].states()[0], solo[k].states()[0], cpu[k].states()[0]
-            for key, val in _worst(sa, sb).items():
-                worst_solo[key] = max(worst_solo[key], val)
+            assert np.array_equal(sa, sb), (step, k)   # same code, fixed summation orders: bit-identical to the stand-alone handle
             for key, val in _worst(sa, sc).items():
                 worst_cpu[key] = max(worst_cpu[key], val)
     assert n_nl >= n * (n_pub - 12)
-    print("batch vs stand-alone", worst_solo, "batch vs oracle", worst_cpu)
-    for key in worst_solo:
-        assert worst_solo[key] == 0.0, (key, worst_solo)   # same code, fixed summation orders: bit-identical
+    print("batch vs oracle", worst_cpu)
+    for key in worst_cpu:
         assert worst_cpu[key] <= TOL[key], (key, worst_cpu)
     batch.close()
 
@@ -118,10 +115,8 @@ def test_batch_of_64_sequences_runs():
     for k in range(n):
         info = batch.members[k].info()
         assert info["solver_flag"] == 1 and info["n_solves"] == batch.members[k % 4].info()["n_solves"] >= 3
-    for k in check:
-        w = _worst(batch.members[k].states()[0], solo[k].states()[0])
-        for key in w:
-            assert w[key] == 0.0, (k, w)   # the batch only changes which grid dimension a sequence lives on
+    for k in check:   # the batch only changes which grid dimension a sequence lives on
+        assert np.array_equal(batch.members[k].states()[0], solo[k].states()[0]), k
     # one launch chain per frame regardless of the batch size: zero + linearize + 8 x 3 + finish + 3 marginalisation + jobs
     assert max(launches) <= 2 + 8 * 3 + 1 + 3 + 1, launches
     batch.close()

@@ -16,7 +16,7 @@
 namespace vb {
 
 constexpr int RED_MAXD = 352;       // 15 (W + 1) + 7 for W <= 22
-constexpr int RED_THREADS = 64;
+constexpr int RED_THREADS = 256;
 
 #define LIN_WARPS 4
 __host__ __device__ inline int ba_eval_grid(const BaDims& d) { return (d.L + LIN_WARPS - 1) / LIN_WARPS + d.W + 1; }
@@ -490,14 +490,20 @@ __device__ __forceinline__ void store_sym(const BaProblem& p, int r, int c, doub
     }
 }
 
-// grid.x: first the NV (NV + 1) / 2 pose-type block pairs (one CTA each), then CTAs of 256 generic entries (4 per thread).
+// grid.x: first the NV (NV + 1) / 2 pose-type block pairs (one CTA each), then CTAs of generic entries (4 per thread).
+// A pair CTA first stages anchor / track length / record offset / 1/(Hll + mu E) of every landmark in shared memory (coalesced),
+// so that the per-landmark terms need no dependent global loads: seven slices of 36 entry threads then walk the landmarks
+// (slice s takes l = s, s + 7, ...) with predicated, unrolled loads from the factor records, and the slice sums are combined in a
+// fixed order.
+constexpr int RED_SLICES = 7;
+constexpr int RED_SLAB = 1024;
 __global__ void __launch_bounds__(RED_THREADS) ba_reduce_kernel(const BaSeq* __restrict__ seqs, int n_pairs_max) {
     __shared__ BaProblem sp;
     __shared__ int pinv[RED_MAXD];
-    __shared__ int cov[1024];  // compacted list of the landmarks seen from both blocks (chunked when L > 1024)
-    __shared__ int c_an[1024], c_s0[1024];
-    __shared__ double c_inv[1024];
-    __shared__ int wcnt[RED_THREADS / 32];
+    __shared__ short s_an[RED_SLAB], s_nobs[RED_SLAB];
+    __shared__ int s_s0[RED_SLAB];
+    __shared__ double s_inv[RED_SLAB];
+    __shared__ double part[4][RED_SLICES][36];
     const BaSeq& q = seqs[blockIdx.y];
     if (!q.active || q.st.done || q.st.reuse) return;
     load_desc(&sp, &q.p);
@@ -521,70 +527,123 @@ __global__ void __launch_bounds__(RED_THREADS) ba_reduce_kernel(const BaSeq* __r
         }
         const int TB = TA + rem;
         const VBlock A = vblock(d, TA), B = vblock(d, TB);
-        const int i = tid / B.dim, j = tid - i * B.dim;
-        const bool entry = tid < A.dim * B.dim && !(TA == TB && i > j);
-        const bool gradt = TA == TB && tid < A.dim;  // thread tid also owns gradient component tid of block A
-        const int r = A.col + i, c = B.col + j;
+        const int slice = tid / 36, e = tid - 36 * slice;  // threads 252..255 only help with the staging
+        const int i = e / B.dim, j = e - i * B.dim;
+        const bool worker = slice < RED_SLICES && e < A.dim * B.dim && !(TA == TB && i > j);
+        const bool gworker = slice < RED_SLICES && TA == TB && e < A.dim;  // gradient component e of block A
         double h = 0.0, E = 0.0, gvis = 0.0, gE = 0.0;
-        if (entry) h = prior_entry(p.prior, pinv, r, c) + imu_entry(d, a, col_info(d, r), col_info(d, c));
-        double gbase = 0.0;
-        if (gradt) {
-            const int rg = A.col + tid;
-            gbase = (p.prior.n > 0 && pinv[rg] >= 0 ? a.gpr[pinv[rg]] : 0.0) + imu_grad(d, a, col_info(d, rg));
-        }
-        for (int l0 = 0; l0 < L; l0 += 1024) {
-            // ordered compaction of the covering landmarks of this chunk
-            int n_cov = 0;
-            const int lend = min(L, l0 + 1024);
-            for (int base = l0; base < lend; base += RED_THREADS) {
-                const int l = base + tid;
-                bool ok = false;
-                if (l < lend) {
-                    const int an = p.lm_anchor[l], nobs = p.lm_start[l + 1] - p.lm_start[l];
-                    ok = lm_covers(A, an, nobs) && lm_covers(B, an, nobs);
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if ((tid & 31) == 0) wcnt[tid >> 5] = __popc(m);
-                __syncthreads();
-                int off = n_cov;
-                for (int w = 0; w < (tid >> 5); w++) off += wcnt[w];
-                if (ok) cov[off + __popc(m & ((1u << (tid & 31)) - 1u))] = l;
-                int tot = 0;
-                for (int w = 0; w < RED_THREADS / 32; w++) tot += wcnt[w];
-                n_cov += tot;
-                __syncthreads();
-            }
-            for (int k = tid; k < n_cov; k += RED_THREADS) {
-                const int l = cov[k];
-                c_an[k] = p.lm_anchor[l];
-                c_s0[k] = p.lm_start[l];
-                c_inv[k] = lm_inv_lambda(p, a, l, mu, first);
+        for (int l0 = 0; l0 < L; l0 += RED_SLAB) {
+            const int nl = min(RED_SLAB, L - l0);
+            __syncthreads();
+            for (int k = tid; k < nl; k += RED_THREADS) {
+                const int l = l0 + k, s0 = p.lm_start[l];
+                s_an[k] = (short)p.lm_anchor[l];
+                s_nobs[k] = (short)(p.lm_start[l + 1] - s0);
+                s_s0[k] = s0;
+                s_inv[k] = lm_inv_lambda(p, a, l, mu, first);
             }
             __syncthreads();
-            if (entry || gradt) {
-                for (int k = 0; k < n_cov; k++) {
-                    const int l = cov[k];
-                    const int an = c_an[k], s0 = c_s0[k];
-                    const double* rec = a.lmW + (size_t)l * lw;
-                    const double inv = c_inv[k];
-                    if (entry) {
+            if ((worker || gworker) && A.type == 0 && B.type == 0) {
+                // (pose a, pose b): the common case, written so that the loads of four landmarks are in flight together
+                // (no early exits: uncovered landmarks contribute exact zeros through predicated loads)
+                const int fa = A.frame, fb = B.frame;
+                const bool diag = fa == fb;
+                for (int k = slice; k < nl; k += 4 * RED_SLICES) {
+                    double wa[4], wb[4], inv[4], x0[4], x1[4], y0[4], y1[4], gl[4], gv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int kk = k + u * RED_SLICES;
+                        const bool in = kk < nl;
+                        const int ks = in ? kk : 0;
+                        const int an = s_an[ks], nobs = s_nobs[ks], s0 = s_s0[ks];
+                        const bool cv = in && an <= fa && fb <= an + nobs;
+                        const bool anchored = an == fa;
+                        const double* rec = a.lmW + (size_t)(l0 + ks) * lw;
+                        const double* oa = a.obsJ + (size_t)(s0 + max(fa - an - 1, 0)) * oj;  // observation in frame a (when not the anchor)
+                        const double* ob = a.obsJ + (size_t)(s0 + max(fb - an - 1, 0)) * oj;  // observation in frame b
+                        inv[u] = s_inv[ks];
+                        wa[u] = cv ? (anchored ? rec[LW_WI + i] : oa[OJ_WJ + i]) : 0.0;
+                        wb[u] = cv ? ((an == fb) ? rec[LW_WI + j] : ob[OJ_WJ + j]) : 0.0;
+                        gl[u] = cv ? rec[LW_GL] : 0.0;
+                        if (diag) {
+                            // anchored: Hii(i, j); otherwise Jj^T Jj of the observation in this frame
+                            const int hij = i <= j ? hii_index(i, j) : hii_index(j, i);
+                            x0[u] = cv ? (anchored ? rec[LW_HII + hij] : oa[OJ_JJ + i]) : 0.0;
+                            y0[u] = cv && !anchored ? oa[OJ_JJ + j] : (anchored ? 1.0 : 0.0);
+                            x1[u] = cv && !anchored ? oa[OJ_JJ + 6 + i] : 0.0;
+                            y1[u] = cv && !anchored ? oa[OJ_JJ + 6 + j] : 0.0;
+                            // gradient threads are the entries (0, e): their component index is j
+                            gv[u] = cv ? (anchored ? rec[LW_GI + j] : oa[OJ_JJ + j] * oa[OJ_R] + oa[OJ_JJ + 6 + j] * oa[OJ_R + 1]) : 0.0;
+                        } else {
+                            const bool on = cv && anchored;  // only the factor anchored in a links a and b
+                            x0[u] = on ? ob[OJ_JI + i] : 0.0;
+                            y0[u] = on ? ob[OJ_JJ + j] : 0.0;
+                            x1[u] = on ? ob[OJ_JI + 6 + i] : 0.0;
+                            y1[u] = on ? ob[OJ_JJ + 6 + j] : 0.0;
+                            gv[u] = 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (worker) {
+                            h += x0[u] * y0[u] + x1[u] * y1[u];
+                            E += wa[u] * inv[u] * wb[u];
+                        }
+                        if (gworker) {  // diagonal pair: block B is block A, so wb is component j = e of w_A
+                            gvis += gv[u];
+                            gE += wb[u] * inv[u] * gl[u];
+                        }
+                    }
+                }
+            } else if (worker || gworker) {
+#pragma unroll 4
+                for (int k = slice; k < nl; k += RED_SLICES) {
+                    const int an = s_an[k], nobs = s_nobs[k], s0 = s_s0[k];
+                    if (!lm_covers(A, an, nobs) || !lm_covers(B, an, nobs)) continue;
+                    const double* rec = a.lmW + (size_t)(l0 + k) * lw;
+                    const double inv = s_inv[k];
+                    if (worker) {
                         h += vis_entry(a, oj, rec, A, B, i, j, an, s0);
                         E += lm_w(a, oj, rec, A, i, an, s0) * inv * lm_w(a, oj, rec, B, j, an, s0);
                     }
-                    if (gradt) {
-                        gvis += vis_grad(a, oj, rec, A, tid, an, s0);
-                        gE += lm_w(a, oj, rec, A, tid, an, s0) * inv * rec[LW_GL];
+                    if (gworker) {
+                        gvis += vis_grad(a, oj, rec, A, e, an, s0);
+                        gE += lm_w(a, oj, rec, A, e, an, s0) * inv * rec[LW_GL];
                     }
                 }
             }
-            __syncthreads();
         }
-        if (entry) store_sym(p, r, c, h, h - E);
-        if (gradt) {
-            const int rg = A.col + tid;
-            const double g = gbase + gvis;
+        if (slice < RED_SLICES) {
+            part[0][slice][e] = h;
+            part[1][slice][e] = E;
+            part[2][slice][e] = gvis;
+            part[3][slice][e] = gE;
+        }
+        __syncthreads();
+        if (slice == 0 && worker) {
+            const int r = A.col + i, c = B.col + j;
+            const double base = prior_entry(p.prior, pinv, r, c) + imu_entry(d, a, col_info(d, r), col_info(d, c));
+            double hs = part[0][0][e], Ev = part[1][0][e];
+#pragma unroll
+            for (int sl = 1; sl < RED_SLICES; sl++) {  // slices in order
+                hs += part[0][sl][e];
+                Ev += part[1][sl][e];
+            }
+            const double hv = base + hs;
+            store_sym(p, r, c, hv, hv - Ev);
+        }
+        if (slice == 0 && gworker) {
+            const int rg = A.col + e;
+            const double gbase = (p.prior.n > 0 && pinv[rg] >= 0 ? a.gpr[pinv[rg]] : 0.0) + imu_grad(d, a, col_info(d, rg));
+            double gs = part[2][0][e], gEs = part[3][0][e];
+#pragma unroll
+            for (int sl = 1; sl < RED_SLICES; sl++) {
+                gs += part[2][sl][e];
+                gEs += part[3][sl][e];
+            }
+            const double g = gbase + gs;
             a.gp[rg] = g;
-            p.gred[rg] = g - gE;
+            p.gred[rg] = g - gEs;
         }
         return;
     }

@@ -197,8 +197,7 @@ struct LkSmem {
     int16_t deriv[22 * 22 * 2];  // Scharr dx,dy at the 22x22 bilinear source positions
     int16_t iwin[441];
     int16_t dwin[441 * 2];
-    float tx[21 * 8], ty[21 * 8];  // mismatch terms of the 16 SIMD pixels of a row: [row][block 0..1][pair k 0..3]
-    float ux[21 * 5], uy[21 * 5];  // the 5 scalar-tail pixels of a row
+    int px[441], py[441];        // (J - I) Ix and (J - I) Iy of every window pixel (exact integers)
     float chain[16];
 };
 
@@ -292,24 +291,33 @@ __global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(const FeSeq* __
         if (lane < 15) {
             const int qi = lane < 12 ? lane >> 2 : lane - 12, j = lane & 3;
             float acc = 0.f;
+            // the terms of a batch of rows are formed first (independent loads and products), then added in order: only the
+            // additions sit on the dependent chain
             if (lane < 12) {
-                for (int y = 0; y < 21; y++)
+                for (int y0 = 0; y0 < 21; y0 += 3) {
+                    float term[12];
 #pragma unroll
-                    for (int g = 0; g < 4; g++) {
-                        const int i = y * 21 + 4 * g + j;
-                        const float fx = (float)sm.dwin[2 * i], fy = (float)sm.dwin[2 * i + 1];
-                        const float term = qi == 0 ? __fmul_rn(fx, fx) : qi == 1 ? __fmul_rn(fx, fy) : __fmul_rn(fy, fy);
-                        acc = __fadd_rn(acc, term);
+                    for (int u = 0; u < 12; u++) {
+                        const int i = (y0 + (u >> 2)) * 21 + 4 * (u & 3) + j;
+                        // A11: Ix Ix, A12: Ix Iy, A22: Iy Iy, as index selects (no divergent paths inside the chain warp)
+                        const float fa = (float)sm.dwin[2 * i + (qi == 2)], fb = (float)sm.dwin[2 * i + (qi != 0)];
+                        term[u] = __fmul_rn(fa, fb);
                     }
+#pragma unroll
+                    for (int u = 0; u < 12; u++) acc = __fadd_rn(acc, term[u]);
+                }
             } else {
-                for (int y = 0; y < 21; y++)
+                for (int y0 = 0; y0 < 21; y0 += 3) {
+                    float term[15];
 #pragma unroll
-                    for (int x = 16; x < 21; x++) {
-                        const int i = y * 21 + x;
-                        const int ix = sm.dwin[2 * i], iy = sm.dwin[2 * i + 1];
-                        const int prod = qi == 0 ? ix * ix : qi == 1 ? ix * iy : iy * iy;
-                        acc = __fadd_rn(acc, __int2float_rn(prod));
+                    for (int u = 0; u < 15; u++) {
+                        const int i = (y0 + u / 5) * 21 + 16 + u % 5;
+                        const int ia = sm.dwin[2 * i + (qi == 2)], ib = sm.dwin[2 * i + (qi != 0)];
+                        term[u] = __int2float_rn(ia * ib);
                     }
+#pragma unroll
+                    for (int u = 0; u < 15; u++) acc = __fadd_rn(acc, term[u]);
+                }
             }
             sm.chain[lane] = acc;
         }
@@ -368,37 +376,38 @@ __global__ void __launch_bounds__(32 * LK_WARPS) lk_track_kernel(const FeSeq* __
                 px = diff * sm.dwin[2 * i];
                 py = diff * sm.dwin[2 * i + 1];
             };
-            // work items: 168 pixel pairs (k, k + 4) of the SIMD part (integer pair sum -> float, like v_dotprod + v_cvt_f32)
-            // and 105 single pixels of the scalar tail
-            for (int w = lane; w < 168 + 105; w += NT) {
-                if (w < 168) {
-                    const int y = w >> 3, bk = w & 7, b = bk >> 2, k = bk & 3;
-                    int ax, ay, bx, by;
-                    mismatch(y, 8 * b + k, ax, ay);
-                    mismatch(y, 8 * b + k + 4, bx, by);
-                    sm.tx[w] = __int2float_rn(ax + bx);
-                    sm.ty[w] = __int2float_rn(ay + by);
-                } else {
-                    const int u = w - 168, y = u / 5, x = 16 + (u - 5 * y);
-                    int ax, ay;
-                    mismatch(y, x, ax, ay);
-                    sm.ux[u] = __int2float_rn(ax);
-                    sm.uy[u] = __int2float_rn(ay);
-                }
+            // every thread forms the integer products of its window pixels; the chain threads pair them up
+            for (int w = lane; w < 441; w += NT) {
+                const int y = w / 21, x = w - 21 * y;
+                int ax, ay;
+                mismatch(y, x, ax, ay);
+                sm.px[w] = ax;
+                sm.py[w] = ay;
             }
             __syncthreads();
             if (lane < 10) {
                 float acc = 0.f;
-                if (lane < 8) {  // lane chains: X / Y of pair k, rows in order, block 0 then block 1
-                    const float* src = (lane & 1) ? sm.ty : sm.tx;
-                    const int k = lane >> 1;
-                    for (int y = 0; y < 21; y++) {
-                        acc = __fadd_rn(acc, src[y * 8 + k]);
-                        acc = __fadd_rn(acc, src[y * 8 + 4 + k]);
+                if (lane < 8) {  // lane chains: X / Y of pixel pair (k, k + 4), rows in order, block 0 then block 1
+                    const int* src = ((lane & 1) ? sm.py : sm.px) + (lane >> 1);
+                    for (int y0 = 0; y0 < 21; y0 += 7) {
+                        float term[14];
+#pragma unroll
+                        for (int u = 0; u < 14; u++) {  // integer pair sum -> float, like v_dotprod + v_cvt_f32
+                            const int* q2 = src + (y0 + (u >> 1)) * 21 + 8 * (u & 1);
+                            term[u] = __int2float_rn(q2[0] + q2[4]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 14; u++) acc = __fadd_rn(acc, term[u]);
                     }
                 } else {
-                    const float* src = lane == 8 ? sm.ux : sm.uy;
-                    for (int u = 0; u < 105; u++) acc = __fadd_rn(acc, src[u]);
+                    const int* src = lane == 8 ? sm.px : sm.py;
+                    for (int y0 = 0; y0 < 21; y0 += 3) {
+                        float term[15];
+#pragma unroll
+                        for (int u = 0; u < 15; u++) term[u] = __int2float_rn(src[(y0 + u / 5) * 21 + 16 + u % 5]);
+#pragma unroll
+                        for (int u = 0; u < 15; u++) acc = __fadd_rn(acc, term[u]);
+                    }
                 }
                 sm.chain[lane] = acc;
             }
@@ -497,7 +506,9 @@ __global__ void __launch_bounds__(ME_TW* ME_TH) min_eig_kernel(const FeSeq* __re
     float* __restrict__ eig = q.eig;
     unsigned* __restrict__ max_sortable = q.maxv;
     __shared__ uint8_t tile[(ME_TH + 4) * (ME_TW + 4)];
-    __shared__ float sxx[(ME_TH + 2) * (ME_TW + 2)], sxy[(ME_TH + 2) * (ME_TW + 2)], syy[(ME_TH + 2) * (ME_TW + 2)];
+    // the derivative products are staged already widened to double (the box filter sums them in double like OpenCV's CV_64F
+    // sum type): one conversion per staged element instead of nine per output pixel
+    __shared__ double sxx[(ME_TH + 2) * (ME_TW + 2)], sxy[(ME_TH + 2) * (ME_TW + 2)], syy[(ME_TH + 2) * (ME_TW + 2)];
     __shared__ unsigned wmax[ME_TW * ME_TH / 32];
     const int tx0 = blockIdx.x * ME_TW, ty0 = blockIdx.y * ME_TH;
     const int tid = threadIdx.y * ME_TW + threadIdx.x;
@@ -513,7 +524,7 @@ __global__ void __launch_bounds__(ME_TW* ME_TH) min_eig_kernel(const FeSeq* __re
         const int j = i / DW, ii = i - j * DW;
         // derivative position p = (ty0-1+j, tx0-1+ii); evaluate Sobel at q = reflect101(p)
         if (ty0 - 1 + j > rows || tx0 - 1 + ii > cols) {  // beyond the 1-pixel ring of the image: unused
-            sxx[i] = sxy[i] = syy[i] = 0.f;
+            sxx[i] = sxy[i] = syy[i] = 0.0;
             continue;
         }
         const int qy = reflect101(ty0 - 1 + j, rows), qx = reflect101(tx0 - 1 + ii, cols);
@@ -530,9 +541,9 @@ __global__ void __launch_bounds__(ME_TW* ME_TH) min_eig_kernel(const FeSeq* __re
         const float sm_ = __fadd_rn(__fadd_rn(__fmul_rn(k1, pmm), __fmul_rn(k2, pm0)), __fmul_rn(k1, pmp));
         const float sp_ = __fadd_rn(__fadd_rn(__fmul_rn(k1, ppm), __fmul_rn(k2, pp0)), __fmul_rn(k1, ppp));
         const float gy = __fsub_rn(sp_, sm_);
-        sxx[i] = __fmul_rn(gx, gx);
-        sxy[i] = __fmul_rn(gx, gy);
-        syy[i] = __fmul_rn(gy, gy);
+        sxx[i] = (double)__fmul_rn(gx, gx);
+        sxy[i] = (double)__fmul_rn(gx, gy);
+        syy[i] = (double)__fmul_rn(gy, gy);
     }
     __syncthreads();
     const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y;
@@ -542,9 +553,9 @@ __global__ void __launch_bounds__(ME_TW* ME_TH) min_eig_kernel(const FeSeq* __re
 #pragma unroll
         for (int j = 0; j < 3; j++) {
             const int o = (threadIdx.y + j) * DW + threadIdx.x;
-            const double ra = __dadd_rn(__dadd_rn((double)sxx[o], (double)sxx[o + 1]), (double)sxx[o + 2]);
-            const double rb = __dadd_rn(__dadd_rn((double)sxy[o], (double)sxy[o + 1]), (double)sxy[o + 2]);
-            const double rc = __dadd_rn(__dadd_rn((double)syy[o], (double)syy[o + 1]), (double)syy[o + 2]);
+            const double ra = __dadd_rn(__dadd_rn(sxx[o], sxx[o + 1]), sxx[o + 2]);
+            const double rb = __dadd_rn(__dadd_rn(sxy[o], sxy[o + 1]), sxy[o + 2]);
+            const double rc = __dadd_rn(__dadd_rn(syy[o], syy[o + 1]), syy[o + 2]);
             sa = __dadd_rn(sa, ra);
             sb = __dadd_rn(sb, rb);
             sc = __dadd_rn(sc, rc);
