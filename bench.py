@@ -42,6 +42,12 @@ INIT_PUBS = 12           # published frames consumed before the window is full a
 ALGO_BYTES_IMAGE = 1_319_760   # compulsory front-end traffic per input image
 ALGO_BYTES_SOLVE = 233_000     # back-end inputs+outputs per solve at C1
 SEQS_PER_GPU = 64
+# estimator / tracker parameters of the workload (configs[3] swaps them: see main)
+TRK_KW = {}
+EST_KW = {}
+ORC_KW = {}
+WORKLOAD_C4 = ("configs[3]: single 752x480 synthetic sequence, 20-keyframe window, 300 features (min_dist 20), ProjectionTdFactor with "
+               "estimate_td and rolling-shutter row term (TR 0.033 s), 200 Hz IMU, fp64 Jacobians")
 
 
 def sequence_inputs(seed, n_pub):
@@ -129,8 +135,8 @@ class ClockSampler:
 
 def make_gpu_pair(device):
     from vins_mono_b200 import FeatureTracker, Estimator
-    trk = FeatureTracker(device=device, **synth.tracker_config_dict())
-    est = Estimator(tic=synth.TIC, ric=synth.RIC, device=device)
+    trk = FeatureTracker(device=device, **synth.tracker_config_dict(**TRK_KW))
+    est = Estimator(tic=synth.TIC, ric=synth.RIC, device=device, **EST_KW)
     return trk, est
 
 
@@ -308,8 +314,8 @@ def run_batch_pass(inputs, n_seq, n_init, warmup, steps, device, host_images=Fal
     step.  The timed region is ONE vr_advance call of `steps` published frames per member."""
     import torch
     from vins_mono_b200 import TrackerBatch, EstimatorBatch, ReplaySession
-    tb = TrackerBatch(n_seq, device=device, **synth.tracker_config_dict())
-    eb = EstimatorBatch(n_seq, tic=synth.TIC, ric=synth.RIC, device=device)
+    tb = TrackerBatch(n_seq, device=device, **synth.tracker_config_dict(**TRK_KW))
+    eb = EstimatorBatch(n_seq, tic=synth.TIC, ric=synth.RIC, device=device, **EST_KW)
     if profile:
         tb.set_profile(True)
         eb.set_profile(True)
@@ -372,14 +378,14 @@ def run_reference_pass(seq, ts, imgs, imu, n_init, warmup, steps, front="cv2"):
     import orc
     cv2_cls = _cv2_tracker_class() if front == "cv2" else None
     if cv2_cls is not None:
-        trk = cv2_cls(synth.tracker_config_dict())
+        trk = cv2_cls(synth.tracker_config_dict(**TRK_KW))
         node_image = lambda img, t: trk.node_image(np.ascontiguousarray(img), t)  # noqa: E731
         used = "cv2"
     else:
-        trk = orc.OracleTracker(synth.tracker_config_dict())
+        trk = orc.OracleTracker(synth.tracker_config_dict(**TRK_KW))
         node_image = lambda img, t: trk.node_image(img, t)[0]  # noqa: E731
         used = "port"
-    est = orc.OracleEstimator(orc.be_config())
+    est = orc.OracleEstimator(orc.be_config(**ORC_KW))
     est.set_fast_eigen(True)  # tridiagonal QL (the reference's Eigen solver class) instead of the parity tests' Jacobi
     feeder = pipeline.ImuFeeder(*imu)
     est.set_seed(pipeline.gt_seed_rows(seq, ts), seq.ba, seq.bg)
@@ -459,7 +465,7 @@ def _oracle_traj_worker(args):
     seed, n_pub = args
     import orc
     seq, ts, imgs, imu = sequence_inputs(seed, n_pub)
-    trk, est = orc.OracleTracker(synth.tracker_config_dict()), orc.OracleEstimator(orc.be_config())
+    trk, est = orc.OracleTracker(synth.tracker_config_dict(**TRK_KW)), orc.OracleEstimator(orc.be_config(**ORC_KW))
     r = pipeline.run_vio(seq, trk, est, len(ts), messages=list(pipeline.feature_messages(trk, ts, imgs))[:n_pub])
     return np.asarray(r["t"]), np.asarray(r["P"])
 
@@ -515,7 +521,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="auto", choices=["auto", "c2", "c3"],
+    ap.add_argument("--config", default="auto", choices=["auto", "c2", "c3", "c4"],
                     help="auto: configs[1] on one GPU (with a c3 object), configs[4]'s share (64 sequences per GPU) under torchrun")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=150,
@@ -526,6 +532,13 @@ def main():
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    global INIT_PUBS, WORKLOAD
+    if a.config == "c4":  # BASELINE configs[3]
+        TRK_KW.update(max_cnt=300, min_dist=20)
+        EST_KW.update(window_size=20, estimate_td=1, tr=0.033, row=480.0, max_features=2000)
+        ORC_KW.update(window_size=20, estimate_td=1, tr=0.033, row=480.0)
+        INIT_PUBS, WORKLOAD = 22, WORKLOAD_C4
+        a.no_c3 = True
     batched = a.config == "c3" or (a.config == "auto" and world > 1)
     S = a.seqs_per_gpu
     n_distinct = max(1, min(a.distinct, S))

@@ -702,6 +702,12 @@ int orc_est_prior(void* h, int cap, double* A, double* b) {
     std::memcpy(b, e->last_marginalization_info->b_debug.data(), n * sizeof(double));
     return n;
 }
+// Estimator::clearState + setParameter, as the node does on a restart message (estimator_node.cpp:186-203)
+void orc_est_clear_state(void* h) {
+    Estimator* e = (Estimator*)h;
+    e->clearState();
+    e->setParameter();
+}
 int orc_est_feature_count(void* h) { return (int)((Estimator*)h)->f_manager.feature.size(); }
 
 // ---- single-factor known-answer access -------------------------------------------------------------

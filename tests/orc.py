@@ -284,6 +284,9 @@ class OracleEstimator:
         rows = _d(rows)
         lib().orc_est_set_seed(self.h, len(rows), P(rows, f64p), P(_d(ba), f64p), P(_d(bg), f64p))
 
+    def clearState(self):
+        lib().orc_est_clear_state(self.h)
+
     def processIMU(self, dt, acc, gyr):
         lib().orc_est_process_imu(self.h, C.c_double(dt), P(_d(acc), f64p), P(_d(gyr), f64p))
 

@@ -168,3 +168,67 @@ def test_estimator_window20_300_features_rolling_shutter():
     for k, tol in TOL.items():
         assert worst[k] <= 2 * tol, (k, worst)
     assert abs(cpu.states()[1] - gpu.states()[1]) < 1e-5
+
+
+def _compare_run(seq, msgs, acc, gyr, t_imu, on_message=None, tol_mult=1.0):
+    cpu, gpu = orc.OracleEstimator(orc.be_config()), make_gpu()
+    seeds = pipeline.gt_seed_rows(seq, [m[0] for m in msgs])
+    cpu.set_seed(seeds, seq.ba, seq.bg)
+    gpu.set_seed(seeds, seq.ba, seq.bg)
+    fa, fb = pipeline.ImuFeeder(t_imu, acc, gyr), pipeline.ImuFeeder(t_imu, acc, gyr)
+    trace, worst = [], dict(p=0.0, q=0.0, v=0.0, ba=0.0, bg=0.0)
+    for k, (stamp, ids, d) in enumerate(msgs):
+        if on_message:
+            on_message(k, cpu, gpu)
+        fa.feed(cpu, stamp)
+        fb.feed(gpu, stamp)
+        cpu.processImage(ids, d, stamp)
+        gpu.processImage(ids, d, stamp)
+        ia, ib = cpu.info(), gpu.info()
+        for key in ("solver_flag", "frame_count", "marginalization_flag", "n_reboots", "n_solves"):
+            assert ia[key] == ib[key], (k, key, ia, ib)
+        trace.append((ia["solver_flag"], ia["frame_count"], ia["n_reboots"]))
+        if ia["solver_flag"] == 1:
+            sa, sb = cpu.states()[0], gpu.states()[0]
+            worst["p"] = max(worst["p"], np.abs(sa[:, 0:3] - sb[:, 0:3]).max())
+            worst["q"] = max(worst["q"], quat_angle(sa[:, 3:7], sb[:, 3:7]).max())
+            worst["v"] = max(worst["v"], np.abs(sa[:, 7:10] - sb[:, 7:10]).max())
+            worst["ba"] = max(worst["ba"], np.abs(sa[:, 10:13] - sb[:, 10:13]).max())
+            worst["bg"] = max(worst["bg"], np.abs(sa[:, 13:16] - sb[:, 13:16]).max())
+    for key in worst:
+        assert worst[key] <= tol_mult * TOL[key], (key, worst)
+    return trace
+
+
+def test_failure_detection_reboots_like_the_reference():
+    """Estimator::failureDetection (estimator.cpp:621-667) -> clearState + setParameter (:193-201): a burst of corrupted
+    accelerometer samples (+300 m/s^2 for one frame interval) drives the newest position past the 5 m / 1 m limits, both
+    estimators reboot at the same message, refill the window, re-initialise and agree again."""
+    seq = synth.Sequence(seed=4, duration=5.5)
+    msgs = synth.track_messages(seq, 44, max_feats=90)
+    t_imu, acc, gyr = seq.imu()
+    acc = acc.copy()
+    t0 = msgs[20][0]
+    # the first sample after the stamp is left clean: it also enters message 20 through the interpolation at the image time
+    acc[(t_imu > t0 + 0.0051) & (t_imu <= t0 + 0.1), 0] += 300.0
+    trace = _compare_run(seq, msgs, acc, gyr, t_imu)
+    flags = [t[0] for t in trace]
+    reboots = [t[2] for t in trace]
+    assert reboots[20] == 0 and reboots[21] == 1 and reboots[-1] == 1
+    assert flags[20] == 1 and flags[21] == 0 and flags[-1] == 1          # rebooted, then NON_LINEAR again
+    assert [t[1] for t in trace[21:32]] == list(range(0, 11))             # frame_count restarts at 0 and refills the window
+
+
+def test_clear_state_mid_run():
+    """Estimator::clearState + setParameter called by the node on a restart message (estimator_node.cpp:186-203)."""
+    seq = synth.Sequence(seed=6, duration=4.5)
+    msgs = synth.track_messages(seq, 34, max_feats=90)
+    t_imu, acc, gyr = seq.imu()
+
+    def restart(k, cpu, gpu):
+        if k == 17:
+            cpu.clearState()
+            gpu.clearState()
+
+    trace = _compare_run(seq, msgs, acc, gyr, t_imu, on_message=restart)
+    assert trace[16][0] == 1 and trace[17][0] == 0 and trace[17][1] == 1 and trace[-1][0] == 1

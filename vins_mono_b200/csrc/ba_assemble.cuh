@@ -255,7 +255,7 @@ __device__ inline void lin_prior(const BaProblem& p, const BaStates& x, const Ba
 }
 
 template <bool EX, bool TD>
-__global__ void __launch_bounds__(32 * LIN_WARPS) ba_eval_kernel(const BaSeq* __restrict__ seqs, int initial) {
+__global__ void __launch_bounds__(32 * LIN_WARPS, 3) ba_eval_kernel(const BaSeq* __restrict__ seqs, int initial) {
     __shared__ double sJraw[450], srr[16];
     __shared__ double sdx[PRIOR_MAX_N], sred[PRIOR_MAX_N];
     __shared__ BaProblem sp;
@@ -497,7 +497,7 @@ __device__ __forceinline__ void store_sym(const BaProblem& p, int r, int c, doub
 // fixed order.
 constexpr int RED_SLICES = 7;
 constexpr int RED_SLAB = 1024;
-__global__ void __launch_bounds__(RED_THREADS) ba_reduce_kernel(const BaSeq* __restrict__ seqs, int n_pairs_max) {
+__global__ void __launch_bounds__(RED_THREADS, 3) ba_reduce_kernel(const BaSeq* __restrict__ seqs, int n_pairs_max) {
     __shared__ BaProblem sp;
     __shared__ int pinv[RED_MAXD];
     __shared__ short s_an[RED_SLAB], s_nobs[RED_SLAB];
