@@ -84,6 +84,10 @@ int ve_kernel_times(const ve_estimator* e, double* ms8, int* count8);
 /* Host<->device bytes moved by the last ve_process_image. */
 int ve_last_traffic(const ve_estimator* e, double* h2d_bytes, double* d2h_bytes);
 
+/* WINDOW_SIZE of the handle; acc_0 / gyr_0 (the last IMU sample handed to processIMU, estimator.h:84) and g (estimator.h:69),
+ * read by the node's update() (estimator_node.cpp:80-96); any pointer may be NULL. */
+int ve_window_size(const ve_estimator* e);
+int ve_get_latest_imu(const ve_estimator* e, double* acc0, double* gyr0, double* g3);
 /* tic (3) and ric (9, row-major) as currently estimated (estimator.h:75-76); either may be NULL. */
 int ve_get_extrinsic(const ve_estimator* e, double* tic3, double* ric9);
 

@@ -69,6 +69,34 @@ int vr_trajectory(const vr_session* s, int seq, int cap, double* stamps, double*
 int vr_debug_imu_batches(int n_imu, const double* imu_t, const double* acc, const double* gyr, int n_stamps, const double* stamps,
                          int cap, int* counts, double* dt, double* acc_out, double* gyr_out);
 
+/* ---- The rest of the node shells, host only -----------------------------------------------------
+ * High-rate pose prediction between two optimisations: estimator_node.cpp:42-78 predict() and :80-96 update().
+ *   vr_prop_predict   one IMU message: the first one only latches its stamp (init_imu), later ones propagate tmp_P / tmp_Q /
+ *                     tmp_V with the mid-point rule; out10 (may be NULL) receives P 3 | Q wxyz | V 3 (what pubLatestOdometry sends)
+ *   vr_prop_update    update(): restart from the estimator's newest window state at `current_time` and re-apply the n queued
+ *                     IMU messages (the node's imu_buf)
+ *   vr_prop_update_from_estimator   the same, reading Ps/Rs/Vs/Bas/Bgs[WINDOW_SIZE], acc_0, gyr_0 and g from a handle */
+typedef struct vr_propagator vr_propagator;
+vr_propagator* vr_prop_create(void);
+void vr_prop_destroy(vr_propagator* p);
+int vr_prop_predict(vr_propagator* p, double t, const double* acc, const double* gyr, double* out10);
+int vr_prop_update(vr_propagator* p, double current_time, const double* P3, const double* Qwxyz, const double* V3, const double* Ba3,
+                   const double* Bg3, const double* acc0, const double* gyr0, const double* g3, int n, const double* t, const double* acc,
+                   const double* gyr);
+int vr_prop_update_from_estimator(vr_propagator* p, const ve_estimator* e, double current_time, int n, const double* t, const double* acc,
+                                  const double* gyr);
+
+/* One row of vins_result_no_loop.csv exactly as pubOdometry writes it (utility/visualization.cpp:156-172): the stamp in ns with
+ * precision 0, then P, Q (w x y z), V with precision 5, every field followed by a comma, then a newline.  Returns the length
+ * written (excluding the terminator) or < 0 when cap is too small. */
+int vr_format_result_row(double stamp, const double* P3, const double* Qwxyz, const double* V3, char* buf, int cap);
+
+/* Decoding of the tracker node's sensor_msgs/PointCloud into processImage's map (estimator_node.cpp:275-302): per point
+ * v = id_of_point + 0.5, feature_id = v / NUM_OF_CAM, camera_id = v % NUM_OF_CAM (NUM_OF_CAM = 1), observation =
+ * (x, y, z, u, v, velocity_x, velocity_y) widened to double; z must be 1 (ROS_ASSERT).  xyz: n x 3 float32.  Returns n or -1. */
+int vr_decode_pointcloud(int n, const float* xyz, const float* id_of_point, const float* u_of_point, const float* v_of_point,
+                         const float* velocity_x, const float* velocity_y, int* feature_ids, int* camera_ids, double* obs7);
+
 #ifdef __cplusplus
 }
 #endif

@@ -176,7 +176,7 @@ def _compare_run(seq, msgs, acc, gyr, t_imu, on_message=None, tol_mult=1.0):
     cpu.set_seed(seeds, seq.ba, seq.bg)
     gpu.set_seed(seeds, seq.ba, seq.bg)
     fa, fb = pipeline.ImuFeeder(t_imu, acc, gyr), pipeline.ImuFeeder(t_imu, acc, gyr)
-    trace, worst = [], dict(p=0.0, q=0.0, v=0.0, ba=0.0, bg=0.0)
+    trace, worst, per_frame = [], dict(p=0.0, q=0.0, v=0.0, ba=0.0, bg=0.0), []
     for k, (stamp, ids, d) in enumerate(msgs):
         if on_message:
             on_message(k, cpu, gpu)
@@ -190,13 +190,14 @@ def _compare_run(seq, msgs, acc, gyr, t_imu, on_message=None, tol_mult=1.0):
         trace.append((ia["solver_flag"], ia["frame_count"], ia["n_reboots"]))
         if ia["solver_flag"] == 1:
             sa, sb = cpu.states()[0], gpu.states()[0]
+            per_frame.append((k, float(np.abs(sa[:, 0:3] - sb[:, 0:3]).max())))
             worst["p"] = max(worst["p"], np.abs(sa[:, 0:3] - sb[:, 0:3]).max())
             worst["q"] = max(worst["q"], quat_angle(sa[:, 3:7], sb[:, 3:7]).max())
             worst["v"] = max(worst["v"], np.abs(sa[:, 7:10] - sb[:, 7:10]).max())
             worst["ba"] = max(worst["ba"], np.abs(sa[:, 10:13] - sb[:, 10:13]).max())
             worst["bg"] = max(worst["bg"], np.abs(sa[:, 13:16] - sb[:, 13:16]).max())
     for key in worst:
-        assert worst[key] <= tol_mult * TOL[key], (key, worst)
+        assert worst[key] <= tol_mult * TOL[key], (key, worst, [(k, "%.1e" % v) for k, v in per_frame])
     return trace
 
 

@@ -1354,6 +1354,16 @@ int ve_get_extrinsic(const ve_estimator* e, double* tic3, double* ric9) {
     return VE_OK;
 }
 
+int ve_window_size(const ve_estimator* e) { return e ? e->W : VE_ERR_INVALID; }
+
+int ve_get_latest_imu(const ve_estimator* e, double* acc0, double* gyr0, double* g3) {
+    if (!e) return VE_ERR_INVALID;
+    if (acc0) { acc0[0] = e->acc_0.x; acc0[1] = e->acc_0.y; acc0[2] = e->acc_0.z; }
+    if (gyr0) { gyr0[0] = e->gyr_0.x; gyr0[1] = e->gyr_0.y; gyr0[2] = e->gyr_0.z; }
+    if (g3) { g3[0] = e->g.x; g3[1] = e->g.y; g3[2] = e->g.z; }
+    return VE_OK;
+}
+
 int ve_info(const ve_estimator* e, int* o, double* costs2) {
     if (!e || !o) return VE_ERR_INVALID;
     o[0] = e->solver_flag; o[1] = e->frame_count; o[2] = e->marginalization_flag; o[3] = e->n_solves; o[4] = e->n_reboots;

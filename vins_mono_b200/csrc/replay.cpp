@@ -3,6 +3,10 @@
 // to feature_tracker_node.cpp / estimator_node.cpp.  Pure host code on top of the two C ABIs.
 #include "vinsb200/replay.h"
 
+#include <cstdio>
+
+#include "host_math.h"
+
 #include <atomic>
 #include <condition_variable>
 #include <deque>
@@ -522,6 +526,126 @@ int vr_debug_imu_batches(int n_imu, const double* imu_t, const double* acc, cons
         }
     }
     return total;
+}
+
+// ---- node shells, remainder ------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct vr_propagator {  // the globals of estimator_node.cpp:21-40
+    double latest_time = 0;
+    hm::Vec3 tmp_P, tmp_V, tmp_Ba, tmp_Bg, acc_0, gyr_0, g;
+    hm::Quat tmp_Q;
+    bool init_imu = true;
+};
+
+namespace {
+hm::Quat qmul(const hm::Quat& a, const hm::Quat& b) {
+    return hm::Quat(a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+                    a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z, a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x);
+}
+hm::Vec3 qrot(const hm::Quat& q, const hm::Vec3& v) {  // Eigen's quaternion * vector
+    const hm::Vec3 u(q.x, q.y, q.z);
+    auto cross = [](const hm::Vec3& a, const hm::Vec3& b) { return hm::Vec3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); };
+    hm::Vec3 uv = cross(u, v);
+    uv = uv + uv;
+    return v + uv * q.w + cross(u, uv);
+}
+void prop_one(vr_propagator* p, double t, const double* a, const double* w) {
+    if (p->init_imu) {
+        p->latest_time = t;
+        p->init_imu = false;
+        return;
+    }
+    const double dt = t - p->latest_time;
+    p->latest_time = t;
+    const hm::Vec3 acc(a[0], a[1], a[2]), gyr(w[0], w[1], w[2]);
+    const hm::Vec3 un_acc_0 = qrot(p->tmp_Q, p->acc_0 - p->tmp_Ba) - p->g;
+    const hm::Vec3 un_gyr = 0.5 * (p->gyr_0 + gyr) - p->tmp_Bg;
+    p->tmp_Q = qmul(p->tmp_Q, hm::Quat(1.0, un_gyr.x * dt / 2.0, un_gyr.y * dt / 2.0, un_gyr.z * dt / 2.0));  // Utility::deltaQ, not normalised
+    const hm::Vec3 un_acc_1 = qrot(p->tmp_Q, acc - p->tmp_Ba) - p->g;
+    const hm::Vec3 un_acc = 0.5 * (un_acc_0 + un_acc_1);
+    p->tmp_P = p->tmp_P + dt * p->tmp_V + 0.5 * dt * dt * un_acc;
+    p->tmp_V = p->tmp_V + dt * un_acc;
+    p->acc_0 = acc;
+    p->gyr_0 = gyr;
+}
+void prop_out(const vr_propagator* p, double* o) {
+    if (!o) return;
+    o[0] = p->tmp_P.x; o[1] = p->tmp_P.y; o[2] = p->tmp_P.z;
+    o[3] = p->tmp_Q.w; o[4] = p->tmp_Q.x; o[5] = p->tmp_Q.y; o[6] = p->tmp_Q.z;
+    o[7] = p->tmp_V.x; o[8] = p->tmp_V.y; o[9] = p->tmp_V.z;
+}
+}  // namespace
+
+extern "C" {
+
+vr_propagator* vr_prop_create(void) { return new vr_propagator; }
+void vr_prop_destroy(vr_propagator* p) { delete p; }
+
+int vr_prop_predict(vr_propagator* p, double t, const double* acc, const double* gyr, double* out10) {
+    if (!p || !acc || !gyr) return -1;
+    prop_one(p, t, acc, gyr);
+    prop_out(p, out10);
+    return 0;
+}
+
+int vr_prop_update(vr_propagator* p, double current_time, const double* P3, const double* Q, const double* V3, const double* Ba3,
+                   const double* Bg3, const double* acc0, const double* gyr0, const double* g3, int n, const double* t, const double* acc,
+                   const double* gyr) {
+    if (!p || !P3 || !Q || !V3 || !Ba3 || !Bg3 || !acc0 || !gyr0 || !g3 || n < 0 || (n && (!t || !acc || !gyr))) return -1;
+    p->latest_time = current_time;
+    p->tmp_P = hm::Vec3(P3[0], P3[1], P3[2]);
+    p->tmp_Q = hm::Quat(Q[0], Q[1], Q[2], Q[3]);
+    p->tmp_V = hm::Vec3(V3[0], V3[1], V3[2]);
+    p->tmp_Ba = hm::Vec3(Ba3[0], Ba3[1], Ba3[2]);
+    p->tmp_Bg = hm::Vec3(Bg3[0], Bg3[1], Bg3[2]);
+    p->acc_0 = hm::Vec3(acc0[0], acc0[1], acc0[2]);
+    p->gyr_0 = hm::Vec3(gyr0[0], gyr0[1], gyr0[2]);
+    p->g = hm::Vec3(g3[0], g3[1], g3[2]);
+    for (int k = 0; k < n; k++) prop_one(p, t[k], acc + 3 * k, gyr + 3 * k);
+    return 0;
+}
+
+int vr_prop_update_from_estimator(vr_propagator* p, const ve_estimator* e, double current_time, int n, const double* t, const double* acc,
+                                  const double* gyr) {
+    if (!p || !e) return -1;
+    int info[10];
+    if (ve_info(e, info, nullptr) != 0) return -1;
+    std::vector<double> st(16 * 65, 0.0);
+    double imu0[9];
+    if (ve_get_states(e, st.data(), nullptr) != 0 || ve_get_latest_imu(e, imu0, imu0 + 3, imu0 + 6) != 0) return -1;
+    const int W = ve_window_size(e);
+    const double* s = &st[16 * (size_t)W];
+    return vr_prop_update(p, current_time, s, s + 3, s + 7, s + 10, s + 13, imu0, imu0 + 3, imu0 + 6, n, t, acc, gyr);
+}
+
+int vr_format_result_row(double stamp, const double* P3, const double* Q, const double* V3, char* buf, int cap) {
+    if (!P3 || !Q || !V3 || !buf || cap <= 0) return -1;
+    // ofstream with ios::fixed: precision 0 for the nanosecond stamp, 5 for the rest, a comma after every field
+    const int n = std::snprintf(buf, (size_t)cap, "%.0f,%.5f,%.5f,%.5f,%.5f,%.5f,%.5f,%.5f,%.5f,%.5f,%.5f,\n", stamp * 1e9, P3[0], P3[1], P3[2],
+                                Q[0], Q[1], Q[2], Q[3], V3[0], V3[1], V3[2]);
+    return n < cap ? n : -1;
+}
+
+int vr_decode_pointcloud(int n, const float* xyz, const float* id_of_point, const float* u_of_point, const float* v_of_point,
+                         const float* velocity_x, const float* velocity_y, int* feature_ids, int* camera_ids, double* obs7) {
+    if (n < 0 || (n && (!xyz || !id_of_point || !u_of_point || !v_of_point || !velocity_x || !velocity_y || !feature_ids || !obs7))) return -1;
+    const int NUM_OF_CAM = 1;
+    for (int i = 0; i < n; i++) {
+        const int v = (int)(id_of_point[i] + 0.5f);
+        feature_ids[i] = v / NUM_OF_CAM;
+        if (camera_ids) camera_ids[i] = v % NUM_OF_CAM;
+        if (xyz[3 * i + 2] != 1.0f) return -1;  // ROS_ASSERT(z == 1)
+        double* o = obs7 + 7 * (size_t)i;
+        o[0] = xyz[3 * i];
+        o[1] = xyz[3 * i + 1];
+        o[2] = xyz[3 * i + 2];
+        o[3] = u_of_point[i];
+        o[4] = v_of_point[i];
+        o[5] = velocity_x[i];
+        o[6] = velocity_y[i];
+    }
+    return n;
 }
 
 int vr_stats(const vr_session* s, int seq, int* frames, long long* launches, double* h2d_bytes, double* d2h_bytes) {
