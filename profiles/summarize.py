@@ -75,7 +75,7 @@ def launches(round_):
         a[3] = max(a[3], us)
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(OUT, f"{round_}_launches.csv"), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 5 --warmup 3 --no-cpu-baseline\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-c3\n")
         f.write("kernel,launches,total_us,mean_us,min_us,max_us,share_of_gpu_time\n")
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k},{a[0]},{a[1]:.1f},{a[1] / a[0]:.2f},{a[2]:.2f},{a[3]:.2f},{a[1] / tot:.4f}\n")
@@ -107,6 +107,8 @@ def full_captures(round_):
                         v *= UNITS.get(units[i], 1.0)
                     rec[name] = v
             out_rows.append(rec)
+            if "_batch_" in rec["capture"]:   # one launch serves 64 sequences: kept apart from the per-sequence traffic table
+                rec["kernel"] += "@64"
             if "dram_read_B" in rec:
                 t = traffic.setdefault(rec["kernel"], {"samples": 0, "dram_bytes_per_launch": 0.0, "round": round_})
                 if t.get("round") != round_:
