@@ -16,7 +16,7 @@ $FULL -k "regex:ba_eval|ba_reduce|marg_eval|marg_gather|preint_jobs|ba_finish" -
 $FULL -k regex:lk_track -s 12 -c 1 -o gpurun_out/${R}_lk_track python harness/run_tracker.py --frames 24 > gpurun_out/${R}_ncu_lk.log 2>&1
 $FULL -k "regex:clahe|pyrdown|min_eig|gftt|sort_keys|mask_" -s 60 -c 10 -o gpurun_out/${R}_fe_small python harness/run_tracker.py --frames 24 > gpurun_out/${R}_ncu_fe.log 2>&1
 # 3. the same kernels serving a batch of 64 sequences (BASELINE configs[2]): one launch per stage for all members
-$FULL -k "regex:lk_track|min_eig|clahe_apply|pyrdown" -s 1400 -c 6 -o gpurun_out/${R}_batch_fe python harness/run_batch.py --seqs 64 --steps 3 > gpurun_out/${R}_ncu_batch_fe.log 2>&1
+$FULL -k "regex:lk_track|min_eig|clahe_apply|pyrdown" -s 150 -c 6 -o gpurun_out/${R}_batch_fe python harness/run_batch.py --seqs 64 --steps 3 > gpurun_out/${R}_ncu_batch_fe.log 2>&1
 $FULL -k "regex:ba_eval|ba_reduce|ba_step|marg_solve" -s 60 -c 6 -o gpurun_out/${R}_batch_ba python harness/run_batch.py --seqs 64 --steps 3 > gpurun_out/${R}_ncu_batch_ba.log 2>&1
 # 4. microbenchmarks that sized the single-CTA solvers (cycle counters, not wall clock)
 for b in lat chol_bench eig_bench; do [ -x harness/micro/$b ] && harness/micro/$b > gpurun_out/${R}_micro_$b.txt 2>&1; done
