@@ -83,13 +83,13 @@ def launches(round_):
 
 
 def full_captures(round_):
-    reps = sorted(glob.glob(os.path.join(SCRATCH, f"{round_}_*.ncu-rep")))
+    reps = sorted(glob.glob(os.path.join(SCRATCH, f"{round_}_*.raw.csv")) or glob.glob(os.path.join(SCRATCH, f"{round_}_*.ncu-rep")))
     out_rows, traffic = [], {}
     tpath = os.path.join(OUT, "dram_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
     for rep in reps:
-        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        txt = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(txt)))
         if len(rows) < 3:
             continue

@@ -1,7 +1,12 @@
 // Host shim with the reference's class surface: drop-in for vins_estimator/src/estimator.h:25-139 as far as
-// estimator_node.cpp and utility/visualization.cpp use it (processIMU, processImage, clearState, setParameter and
-// the public window arrays).  Vector/matrix types are plain structs so that Eigen is not required; with Eigen
-// available, Eigen::Map<Eigen::Vector3d>(Ps[i].v) etc. view them without copies.
+// estimator_node.cpp and utility/visualization.cpp use it: processIMU, processImage(image, header), setReloFrame,
+// clearState, setParameter and the public members Ps, Vs, Rs, Bas, Bgs, tic, ric, td, acc_0, gyr_0, g, Headers,
+// solver_flag, marginalization_flag, frame_count.
+//
+// Types: with Eigen on the include path (the reference's build) the members ARE Eigen::Vector3d / Matrix3d /
+// Matrix<double, 7, 1>, so the node's expressions (`tmp_Q = estimator.Rs[WINDOW_SIZE]`, `estimator.Ps[i].x()`,
+// `estimator.ric[0] * p + estimator.tic[0]`) compile unchanged; without Eigen, small stand-ins with the same accessors
+// (v[k], v.x(), m(r, c)) are used so that this header and its compile test need no third-party dependency.
 #pragma once
 #include <map>
 #include <stdexcept>
@@ -11,62 +16,137 @@
 
 #include "vinsb200/estimator.h"
 
+#if defined(__has_include)
+#if __has_include(<Eigen/Dense>) && !defined(VINSB200_NO_EIGEN)
+#define VINSB200_HAVE_EIGEN 1
+#include <Eigen/Dense>
+#endif
+#endif
+
 namespace vinsb200 {
 
-struct Vector3d { double v[3]; };
-struct Quaterniond { double w, x, y, z; };
-using FeatureObservation = std::pair<int, std::vector<double>>;  // camera id, (x, y, z, u, v, vx, vy)
+#ifdef VINSB200_HAVE_EIGEN
+using Vector3d = Eigen::Vector3d;
+using Matrix3d = Eigen::Matrix3d;
+using Vector7d = Eigen::Matrix<double, 7, 1>;
+#else
+struct Vector3d {
+    double v[3] = {0, 0, 0};
+    Vector3d() {}
+    Vector3d(double a, double b, double c) { v[0] = a; v[1] = b; v[2] = c; }
+    double& operator[](int i) { return v[i]; }
+    double operator[](int i) const { return v[i]; }
+    double x() const { return v[0]; }
+    double y() const { return v[1]; }
+    double z() const { return v[2]; }
+};
+struct Matrix3d {
+    double m[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double& operator()(int r, int c) { return m[3 * r + c]; }
+    double operator()(int r, int c) const { return m[3 * r + c]; }
+    Vector3d operator*(const Vector3d& p) const {
+        return Vector3d(m[0] * p[0] + m[1] * p[1] + m[2] * p[2], m[3] * p[0] + m[4] * p[1] + m[5] * p[2], m[6] * p[0] + m[7] * p[1] + m[8] * p[2]);
+    }
+};
+struct Vector7d {
+    double v[7] = {0, 0, 0, 0, 0, 0, 0};
+    double& operator[](int i) { return v[i]; }
+    double operator[](int i) const { return v[i]; }
+    double& operator()(int i) { return v[i]; }
+    double operator()(int i) const { return v[i]; }
+};
+#endif
 
 class Estimator {
   public:
     enum SolverFlag { INITIAL, NON_LINEAR };
     enum MarginalizationFlag { MARGIN_OLD = 0, MARGIN_SECOND_NEW = 1 };
+    // the feature message of estimator_node.cpp:296-313: feature_id -> [(camera_id, x y z u v vx vy)]
+    using ImageMap = std::map<int, std::vector<std::pair<int, Vector7d>>>;
 
     explicit Estimator(const ve_config& cfg) : cfg_(cfg) {
         if (ve_create(&cfg, &h_) != VE_OK) throw std::runtime_error("ve_create failed (no CUDA device?)");
         const int n = cfg.window_size + 1;
-        Ps.resize(n); Vs.resize(n); Bas.resize(n); Bgs.resize(n); Rs.resize(n);
+        Ps.resize(n); Vs.resize(n); Bas.resize(n); Bgs.resize(n); Rs.resize(n); Headers.resize(n, 0.0);
+        refresh();
     }
     ~Estimator() { ve_destroy(h_); }
     Estimator(const Estimator&) = delete;
     Estimator& operator=(const Estimator&) = delete;
 
-    void setParameter() {}                       // parameters travel in ve_config
+    void setParameter() {}  // parameters travel in ve_config (parameters.cpp:42-137); clearState re-applies them
     void clearState() { check(ve_clear_state(h_)); refresh(); }
     void processIMU(double dt, const Vector3d& linear_acceleration, const Vector3d& angular_velocity) {
-        check(ve_process_imu(h_, dt, linear_acceleration.v, angular_velocity.v));
+        const double a[3] = {linear_acceleration[0], linear_acceleration[1], linear_acceleration[2]};
+        const double w[3] = {angular_velocity[0], angular_velocity[1], angular_velocity[2]};
+        check(ve_process_imu(h_, dt, a, w));
+        refresh_imu();
     }
-    // image: feature_id -> [(camera_id, xyz_uv_velocity)] exactly as estimator_node.cpp:296-313 builds it
-    void processImage(const std::map<int, std::vector<FeatureObservation>>& image, double header_stamp) {
+    // Estimator::processImage(image, header): Header is std_msgs::Header (header.stamp.toSec()) or any type with that shape
+    template <class Header>
+    void processImage(const ImageMap& image, const Header& header) { processImageAt(image, header.stamp.toSec()); }
+    void processImageAt(const ImageMap& image, double stamp) {
         std::vector<int> ids;
         std::vector<double> d;
-        for (const auto& kv : image) {
+        for (const auto& kv : image) {  // NUM_OF_CAM = 1: the first (only) camera's observation
             ids.push_back(kv.first);
-            d.insert(d.end(), kv.second[0].second.begin(), kv.second[0].second.begin() + 7);
+            for (int k = 0; k < 7; k++) d.push_back(kv.second[0].second[k]);
         }
-        check(ve_process_image(h_, (int)ids.size(), ids.data(), d.data(), header_stamp));
+        check(ve_process_image(h_, (int)ids.size(), ids.data(), d.data(), stamp));
+        const int i = frame_count < (int)Headers.size() ? frame_count : (int)Headers.size() - 1;
+        Headers[i] = stamp;
         refresh();
+    }
+    // Relocalisation is the pose-graph coupling (estimator.cpp:769-801, 1128-1146), outside this library's hot path
+    // (SURVEY 8f next-4): the call is accepted and ignored, relocalization_info stays false.
+    template <class Points>
+    void setReloFrame(double /*frame_stamp*/, int /*frame_index*/, Points& /*match_points*/, const Vector3d& /*relo_t*/, const Matrix3d& /*relo_r*/) {
+        relocalization_info = false;
     }
 
     SolverFlag solver_flag = INITIAL;
     MarginalizationFlag marginalization_flag = MARGIN_OLD;
     int frame_count = 0;
+    Vector3d g;
     std::vector<Vector3d> Ps, Vs, Bas, Bgs;
-    std::vector<Quaterniond> Rs;  // rotations as quaternions (w, x, y, z)
+    std::vector<Matrix3d> Rs;
+    Matrix3d ric[1];
+    Vector3d tic[1];
+    Vector3d acc_0, gyr_0;
+    std::vector<double> Headers;  // stamps (the reference keeps std_msgs::Header objects)
     double td = 0;
+    bool relocalization_info = false;
+    ve_estimator* handle() { return h_; }
 
   private:
     void check(int rc) {
         if (rc < 0) throw std::runtime_error(std::string("vinsb200: ") + ve_last_error(h_));
+    }
+    static void q_to_R(const double* q /* w x y z */, Matrix3d& R) {
+        const double w = q[0], x = q[1], y = q[2], z = q[3];
+        R(0, 0) = 1 - 2 * (y * y + z * z); R(0, 1) = 2 * (x * y - z * w); R(0, 2) = 2 * (x * z + y * w);
+        R(1, 0) = 2 * (x * y + z * w); R(1, 1) = 1 - 2 * (x * x + z * z); R(1, 2) = 2 * (y * z - x * w);
+        R(2, 0) = 2 * (x * z - y * w); R(2, 1) = 2 * (y * z + x * w); R(2, 2) = 1 - 2 * (x * x + y * y);
+    }
+    void refresh_imu() {
+        double a[3], w[3], gg[3];
+        ve_get_latest_imu(h_, a, w, gg);
+        for (int k = 0; k < 3; k++) { acc_0[k] = a[k]; gyr_0[k] = w[k]; g[k] = gg[k]; }
     }
     void refresh() {
         std::vector<double> s(16 * Ps.size());
         ve_get_states(h_, s.data(), &td);
         for (size_t i = 0; i < Ps.size(); i++) {
             const double* o = &s[16 * i];
-            for (int k = 0; k < 3; k++) { Ps[i].v[k] = o[k]; Vs[i].v[k] = o[7 + k]; Bas[i].v[k] = o[10 + k]; Bgs[i].v[k] = o[13 + k]; }
-            Rs[i] = Quaterniond{o[3], o[4], o[5], o[6]};
+            for (int k = 0; k < 3; k++) { Ps[i][k] = o[k]; Vs[i][k] = o[7 + k]; Bas[i][k] = o[10 + k]; Bgs[i][k] = o[13 + k]; }
+            q_to_R(o + 3, Rs[i]);
         }
+        double t3[3], r9[9];
+        ve_get_extrinsic(h_, t3, r9);
+        for (int k = 0; k < 3; k++) tic[0][k] = t3[k];
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) ric[0](r, c) = r9[3 * r + c];
+        refresh_imu();
         int info[10];
         double c[2];
         ve_info(h_, info, c);

@@ -30,9 +30,32 @@ int main() {
         ec.window_size = 10; ec.max_features = 1000; ec.num_iterations = 8; ec.focal_length = 460; ec.keyframe_parallax = 10;
         ec.acc_n = 0.08; ec.gyr_n = 0.004; ec.acc_w = 4e-5; ec.gyr_w = 2e-6; ec.g_norm = 9.81007; ec.init_depth = 5; ec.row = 480;
         ec.ric[0] = ec.ric[4] = ec.ric[8] = 1;
-        vinsb200::Estimator est(ec);
-        est.processIMU(0.005, vinsb200::Vector3d{{0, 0, 9.8}}, vinsb200::Vector3d{{0, 0, 0}});
-        std::printf("frame_count %d\n", est.frame_count);
+        vinsb200::Estimator estimator(ec);
+        // the expressions estimator_node.cpp and utility/visualization.cpp apply to the Estimator (update() :84-90, process() :242-316,
+        // restart_callback :190-193, pubOdometry): written out here so that a signature drift breaks the build
+        using vinsb200::Vector3d;
+        using vinsb200::Matrix3d;
+        const int WINDOW_SIZE = ec.window_size;
+        estimator.processIMU(0.005, Vector3d(0, 0, 9.8), Vector3d(0, 0, 0));
+        vinsb200::Estimator::ImageMap image;
+        vinsb200::Vector7d xyz_uv_velocity;
+        xyz_uv_velocity[0] = 0.1; xyz_uv_velocity[1] = -0.2; xyz_uv_velocity[2] = 1.0;
+        image[7].emplace_back(0, xyz_uv_velocity);
+        struct Stamp { double t; double toSec() const { return t; } };
+        struct Header { Stamp stamp; } header{{0.05}};
+        estimator.processImage(image, header);
+        Vector3d tmp_P = estimator.Ps[WINDOW_SIZE], tmp_V = estimator.Vs[WINDOW_SIZE], tmp_Ba = estimator.Bas[WINDOW_SIZE], tmp_Bg = estimator.Bgs[WINDOW_SIZE];
+        Matrix3d tmp_R = estimator.Rs[WINDOW_SIZE];
+        Vector3d acc_0 = estimator.acc_0, gyr_0 = estimator.gyr_0, g = estimator.g;
+        Vector3d cam = estimator.ric[0] * Vector3d(0, 0, 1);
+        const double camx = cam[0] + estimator.tic[0][0];
+        std::vector<Vector3d> match_points;
+        estimator.setReloFrame(0.05, 3, match_points, Vector3d(0, 0, 0), tmp_R);
+        const bool nonlinear = estimator.solver_flag == vinsb200::Estimator::SolverFlag::NON_LINEAR;
+        estimator.clearState();
+        estimator.setParameter();
+        std::printf("frame_count %d td %.3f nonlinear %d %.3f %.3f %.3f\n", estimator.frame_count, estimator.td, (int)nonlinear,
+                    tmp_P.x() + tmp_V.y() + tmp_Ba.z() + tmp_Bg[0] + tmp_R(0, 0), acc_0[2] + gyr_0[0] + g[2], camx + estimator.Headers[0]);
     } catch (const std::exception& e) {
         std::printf("no device: %s\n", e.what());
     }
