@@ -346,6 +346,7 @@ def run_batch_pass(inputs, n_seq, n_init, warmup, steps, device, host_images=Fal
                launches=sum(a_["launches"] - b_["launches"] for a_, b_ in zip(after, before)),
                h2d=sum(a_["h2d"] - b_["h2d"] for a_, b_ in zip(after, before)),
                d2h=sum(a_["d2h"] - b_["d2h"] for a_, b_ in zip(after, before)), trajs=trajs, infos=infos)
+    out["est_groups"] = eb.groups()
     if profile:
         out["trk_k"], out["est_k"] = tb.kernel_times(), eb.kernel_times()
     ses.close()
@@ -488,7 +489,7 @@ def kernel_table(trk_k, est_k):
     return kt
 
 
-def roofline_object(kt, n_solves, n_images, units_per_launch, peak, peaks_found, note):
+def roofline_object(kt, n_solves, n_images, units_per_launch, peak, peaks_found, note, ba_units_per_launch=None):
     """Dominant kernel by accumulated device time of a profile pass.  Algorithmic bytes per launch = SURVEY 8(d)'s per-unit
     figure (per image for front-end kernels, per solve for BA kernels) x units one launch serves / launches per unit."""
     fe = ("clahe", "pyrdown", "lk_track", "mask_discs", "min_eig", "gftt_tail")
@@ -497,7 +498,7 @@ def roofline_object(kt, n_solves, n_images, units_per_launch, peak, peaks_found,
         if k in fe:
             algo = ALGO_BYTES_IMAGE * n_images * units_per_launch / v["launches"]
         else:
-            algo = ALGO_BYTES_SOLVE * n_solves * units_per_launch / v["launches"]
+            algo = ALGO_BYTES_SOLVE * n_solves * (ba_units_per_launch or units_per_launch) / v["launches"]
         per_kernel[k] = dict(v, algorithmic_bytes_per_launch=algo, achieved_gbs=algo / (v["avg_us"] * 1e-6) / 1e9,
                              frac=algo / (v["avg_us"] * 1e-6) / 1e9 / peak)
     dominant = max(kt, key=lambda k: kt[k]["total_ms"])
@@ -669,7 +670,10 @@ def main():
             n_solves = kt.get("ba_finish", {}).get("launches", 1)
             n_images = kt.get("pyrdown", {}).get("launches", 3) // 3
             obj["roofline"] = roofline_object(kt, n_solves, n_images, S, peak, bool(peaks),
-                                              "batched launches: one launch serves every member, algorithmic bytes scale with the batch")
+                                              "batched launches: a front-end launch serves all members, a BA launch the members of its launch group "
+                                              f"({pr['est_groups']} groups whose chains overlap); algorithmic bytes scale with the members served",
+                                              ba_units_per_launch=S / pr["est_groups"])
+            obj["estimator_launch_groups"] = pr["est_groups"]
         # parity: every member against the CPU oracle's trajectory of its sequence, and the replicas among themselves
         if oracle_traj is not None:
             worst, worst_rep, n_cmp = 0.0, 0.0, 0

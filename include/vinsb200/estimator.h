@@ -109,6 +109,9 @@ int ve_get_extrinsic(const ve_estimator* e, double* tic3, double* ric9);
 int ve_batch_create(const ve_config* cfg, int n, ve_batch** out);
 void ve_batch_destroy(ve_batch* b);
 int ve_batch_size(const ve_batch* b);
+/* Launch groups: the members are split into this many contiguous groups, each with its own stream and launch chain, so that the
+ * chains overlap on the GPU (default: groups of 16 members for batches of 32 and more; VINSB200_BATCH_GROUPS overrides). */
+int ve_batch_groups(const ve_batch* b);
 ve_estimator* ve_batch_member(ve_batch* b, int k);
 const char* ve_batch_last_error(const ve_batch* b);
 int ve_batch_process_image(ve_batch* b, const int* active, const int* n, const int* const* ids, const double* const* xyz_uv_vel,

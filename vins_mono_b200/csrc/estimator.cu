@@ -16,6 +16,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -145,19 +146,28 @@ struct ve_batch {
     bool standalone = false;  // created by ve_create: destroyed with its only member
     std::vector<ve_estimator*> members;
     std::string err;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev[8] = {};  // 0 frame start, 1 after pre-integration, 2 after the solve + re-anchoring, 3 marginalisation done,
-                             // 4 results on the host, 5 marginalisation start
+    // Launch groups: the members are split into G contiguous groups, each with its own streams, events and arena slices.
+    // Every group runs the same launch chain over its members; the chains of different groups overlap on the GPU (the
+    // single-CTA-per-member solvers of one group leave most SMs to the wide kernels of another).
+    struct Group {
+        int first = 0, count = 0;
+        cudaStream_t stream = nullptr, copy_stream = nullptr;
+        cudaEvent_t ev[8] = {};  // 0 frame start, 1 after pre-integration, 2 after the solve + re-anchoring, 3 marginalisation done,
+                                 // 4 results on the host, 5 marginalisation start
+        size_t in_base = 0, in_cap = 0;    // bytes, slice of the input arena
+        size_t out_base = 0, out_cap = 0;  // doubles, slice of the output arena
+        std::atomic<size_t> in_used{0}, out_used{0};
+        bool waits_results = false, has_marg = false;
+    };
+    int G = 1;
+    Group* groups = nullptr;
+    int members_per_group = 1;
     vb::BaSeq* h_seq = nullptr;  // pinned mirror of d_seq
     vb::BaSeq* d_seq = nullptr;
     unsigned char* h_in = nullptr;  // pinned: packed per-member input blocks of the frame
     unsigned char* d_in = nullptr;
-    size_t in_cap = 0;
-    std::atomic<size_t> in_used{0};
     double* h_out = nullptr;        // pinned: per-member output blocks
     double* d_out = nullptr;
-    size_t out_cap = 0;             // doubles
-    std::atomic<size_t> out_used{0};
     vb::KernelProfile prof;
     vb::HostPool* pool = nullptr;
     float last_ms[4] = {0, 0, 0, 0};
@@ -650,8 +660,10 @@ int stage_frame(ve_estimator* e, bool solve) {
         o_states = take(sizeof(double) * states_doubles(e, L));
         o_marg = take(sizeof(int) * 2 * n_lm);
     }
-    const size_t base = b->in_used.fetch_add(off);
-    if (base + off > b->in_cap) {
+    ve_batch::Group& grp = b->groups[e->member / b->members_per_group];
+    const size_t rel = grp.in_used.fetch_add(off);
+    const size_t base = grp.in_base + rel;
+    if (rel + off > grp.in_cap) {
         e->err = "batch input arena exhausted";
         return VE_ERR_CAPACITY;
     }
@@ -804,8 +816,9 @@ int stage_frame(ve_estimator* e, bool solve) {
     fp.origin_P0[0] = origin_P0.x; fp.origin_P0[1] = origin_P0.y; fp.origin_P0[2] = origin_P0.z;
     std::memcpy(fp.Rs0, e->Rs[0].m, sizeof(fp.Rs0));
     const size_t out_doubles = vb::BA_OUT_ST_DOUBLES + 21 * (size_t)F + 13 + L;
-    const size_t obase = b->out_used.fetch_add((out_doubles + 1) & ~(size_t)1);
-    if (obase + out_doubles > b->out_cap) {
+    const size_t orel = grp.out_used.fetch_add((out_doubles + 1) & ~(size_t)1);
+    const size_t obase = grp.out_base + orel;
+    if (orel + out_doubles > grp.out_cap) {
         e->err = "batch output arena exhausted";
         return VE_ERR_CAPACITY;
     }
@@ -994,8 +1007,10 @@ struct FrameMsg {
 int batch_process(ve_batch* b, const FrameMsg* msgs, int* status_out) {
     VB_CUDA(cudaSetDevice(b->cfg.device));
     const int S = b->S;
-    b->in_used.store(0);
-    b->out_used.store(0);
+    for (int g = 0; g < b->G; g++) {
+        b->groups[g].in_used.store(0);
+        b->groups[g].out_used.store(0);
+    }
     b->last_launches = 0;
     b->pool->run(S, [&](int k) {
         ve_estimator* e = b->members[k];
@@ -1009,63 +1024,73 @@ int batch_process(ve_batch* b, const FrameMsg* msgs, int* status_out) {
             if (e->status != VE_OK) q.active = q.do_marg = 0;
         }
     });
-    vb::BatchShape sh{};
-    sh.S = S;
-    sh.W = b->cfg.window_size;
-    sh.D = b->members[0]->D - (b->cfg.estimate_extrinsic ? 0 : 6) - (b->cfg.estimate_td ? 0 : 1);
-    sh.max_iterations = b->cfg.num_iterations;
-    sh.est_ex = b->cfg.estimate_extrinsic ? 1 : 0;
-    sh.est_td = b->cfg.estimate_td ? 1 : 0;
-    sh.w_in_global = b->w_in_global;
-    for (int k = 0; k < S; k++) {
-        const vb::BaSeq& q = b->h_seq[k];
-        if (q.n_jobs) sh.any_jobs = 1;
-        if (!q.active) continue;
-        sh.any_active = 1;
-        sh.max_L = std::max(sh.max_L, q.p.dims.L);
-        if (q.do_marg) {
-            sh.any_marg = 1;
-            sh.max_n_lm = std::max(sh.max_n_lm, q.mp.n_lm);
-            sh.max_md = std::max(sh.max_md, q.mp.m_dense);
-            sh.max_n = std::max(sh.max_n, q.mp.n);
-            sh.max_P = std::max(sh.max_P, q.mp.P);
-        }
-    }
     int rc = VE_OK;
-    if (sh.any_jobs || sh.any_active) {
-        VB_CUDA(cudaMemcpyAsync(b->d_seq, b->h_seq, sizeof(vb::BaSeq) * S, cudaMemcpyHostToDevice, b->stream));
-        const size_t in_bytes = std::min(b->in_used.load(), b->in_cap);
-        if (in_bytes) VB_CUDA(cudaMemcpyAsync(b->d_in, b->h_in, in_bytes, cudaMemcpyHostToDevice, b->stream));
-        VB_CUDA(cudaEventRecord(b->ev[0], b->stream));
-        vb::launch_preint_jobs(b->d_seq, sh, b->stream, &b->last_launches, &b->prof);
-        VB_CUDA(cudaEventRecord(b->ev[1], b->stream));
-        vb::launch_ba_solve(b->d_seq, sh, b->stream, &b->last_launches, &b->prof);
-        VB_CUDA(cudaEventRecord(b->ev[2], b->stream));
-        if (sh.any_active) {  // results travel on the copy stream while the marginalisation already runs
-            VB_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev[2], 0));
-            const size_t out_doubles = std::min(b->out_used.load(), b->out_cap);
-            VB_CUDA(cudaMemcpyAsync(b->h_out, b->d_out, sizeof(double) * out_doubles, cudaMemcpyDeviceToHost, b->copy_stream));
-            VB_CUDA(cudaEventRecord(b->ev[4], b->copy_stream));
+    b->marg_timing_valid = false;
+    b->last_ms[0] = b->last_ms[1] = b->last_ms[2] = b->last_ms[3] = 0;
+    for (int g = 0; g < b->G; g++) {  // enqueue every group's chain; nothing is waited for inside this loop
+        ve_batch::Group& grp = b->groups[g];
+        grp.waits_results = grp.has_marg = false;
+        vb::BatchShape sh{};
+        sh.S = grp.count;
+        sh.W = b->cfg.window_size;
+        sh.D = b->members[0]->D - (b->cfg.estimate_extrinsic ? 0 : 6) - (b->cfg.estimate_td ? 0 : 1);
+        sh.max_iterations = b->cfg.num_iterations;
+        sh.est_ex = b->cfg.estimate_extrinsic ? 1 : 0;
+        sh.est_td = b->cfg.estimate_td ? 1 : 0;
+        sh.w_in_global = b->w_in_global;
+        for (int k = grp.first; k < grp.first + grp.count; k++) {
+            const vb::BaSeq& q = b->h_seq[k];
+            if (q.n_jobs) sh.any_jobs = 1;
+            if (!q.active) continue;
+            sh.any_active = 1;
+            sh.max_L = std::max(sh.max_L, q.p.dims.L);
+            if (q.do_marg) {
+                sh.any_marg = 1;
+                sh.max_n_lm = std::max(sh.max_n_lm, q.mp.n_lm);
+                sh.max_md = std::max(sh.max_md, q.mp.m_dense);
+                sh.max_n = std::max(sh.max_n, q.mp.n);
+                sh.max_P = std::max(sh.max_P, q.mp.P);
+            }
         }
-        VB_CUDA(cudaEventRecord(b->ev[5], b->stream));
-        vb::launch_marginalize(b->d_seq, sh, b->stream, &b->last_launches, &b->prof);
-        VB_CUDA(cudaEventRecord(b->ev[3], b->stream));
-        VB_CUDA(cudaGetLastError());
-        b->marg_timing_valid = sh.any_marg != 0;
-        if (sh.any_active) {
-            VB_CUDA(cudaEventSynchronize(b->ev[4]));
-            cudaEventElapsedTime(&b->last_ms[0], b->ev[0], b->ev[1]);
-            cudaEventElapsedTime(&b->last_ms[1], b->ev[1], b->ev[2]);
-            cudaEventElapsedTime(&b->last_ms[3], b->ev[0], b->ev[2]);
+        if (!sh.any_jobs && !sh.any_active) continue;
+        vb::BaSeq* dq = b->d_seq + grp.first;
+        VB_CUDA(cudaMemcpyAsync(dq, b->h_seq + grp.first, sizeof(vb::BaSeq) * grp.count, cudaMemcpyHostToDevice, grp.stream));
+        const size_t in_bytes = std::min(grp.in_used.load(), grp.in_cap);
+        if (in_bytes) VB_CUDA(cudaMemcpyAsync(b->d_in + grp.in_base, b->h_in + grp.in_base, in_bytes, cudaMemcpyHostToDevice, grp.stream));
+        VB_CUDA(cudaEventRecord(grp.ev[0], grp.stream));
+        vb::launch_preint_jobs(dq, sh, grp.stream, &b->last_launches, &b->prof);
+        VB_CUDA(cudaEventRecord(grp.ev[1], grp.stream));
+        vb::launch_ba_solve(dq, sh, grp.stream, &b->last_launches, &b->prof);
+        VB_CUDA(cudaEventRecord(grp.ev[2], grp.stream));
+        if (sh.any_active) {  // results travel on the copy stream while the marginalisation already runs
+            VB_CUDA(cudaStreamWaitEvent(grp.copy_stream, grp.ev[2], 0));
+            const size_t out_doubles = std::min(grp.out_used.load(), grp.out_cap);
+            VB_CUDA(cudaMemcpyAsync(b->h_out + grp.out_base, b->d_out + grp.out_base, sizeof(double) * out_doubles, cudaMemcpyDeviceToHost,
+                                    grp.copy_stream));
+            VB_CUDA(cudaEventRecord(grp.ev[4], grp.copy_stream));
+            grp.waits_results = true;
         } else {
             // jobs only: the input arena must not be rewritten before the copy has been consumed
-            VB_CUDA(cudaEventSynchronize(b->ev[0]));
-            b->last_ms[0] = b->last_ms[1] = b->last_ms[3] = 0;
+            VB_CUDA(cudaEventRecord(grp.ev[4], grp.stream));
+            grp.waits_results = true;
         }
-        b->last_ms[2] = 0;
-    } else {
-        b->last_ms[0] = b->last_ms[1] = b->last_ms[2] = b->last_ms[3] = 0;
-        b->marg_timing_valid = false;
+        VB_CUDA(cudaEventRecord(grp.ev[5], grp.stream));
+        vb::launch_marginalize(dq, sh, grp.stream, &b->last_launches, &b->prof);
+        VB_CUDA(cudaEventRecord(grp.ev[3], grp.stream));
+        VB_CUDA(cudaGetLastError());
+        grp.has_marg = sh.any_marg != 0;
+    }
+    for (int g = 0; g < b->G; g++) {
+        ve_batch::Group& grp = b->groups[g];
+        if (!grp.waits_results) continue;
+        VB_CUDA(cudaEventSynchronize(grp.ev[4]));
+        if (g == 0) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, grp.ev[0], grp.ev[1]) == cudaSuccess) b->last_ms[0] = t;
+            if (cudaEventElapsedTime(&t, grp.ev[1], grp.ev[2]) == cudaSuccess) b->last_ms[1] = t;
+            if (cudaEventElapsedTime(&t, grp.ev[0], grp.ev[2]) == cudaSuccess) b->last_ms[3] = t;
+            b->marg_timing_valid = grp.has_marg;
+        }
     }
     b->pool->run(S, [&](int k) { finish_frame(b->members[k]); });
     for (int k = 0; k < S; k++) {
@@ -1154,9 +1179,22 @@ int ve_batch_create(const ve_config* cfg, int n, ve_batch** out) {
         if ((call) != cudaSuccess) return fail(VE_ERR_CUDA);  \
     } while (0)
     VE_TRY(cudaSetDevice(cfg->device));
-    VE_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-    VE_TRY(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
-    for (auto& ev : b->ev) VE_TRY(cudaEventCreate(&ev));
+    // launch groups: VINSB200_BATCH_GROUPS overrides the default (groups of 16 members, at most 8 groups)
+    int G = n >= 32 ? std::min(8, n / 16) : 1;
+    if (const char* env = std::getenv("VINSB200_BATCH_GROUPS")) G = std::atoi(env);
+    G = std::max(1, std::min(G, n));
+    b->G = G;
+    b->members_per_group = (n + G - 1) / G;
+    b->G = G = (n + b->members_per_group - 1) / b->members_per_group;
+    b->groups = new ve_batch::Group[G];
+    for (int g = 0; g < G; g++) {
+        ve_batch::Group& grp = b->groups[g];
+        grp.first = g * b->members_per_group;
+        grp.count = std::min(b->members_per_group, n - grp.first);
+        VE_TRY(cudaStreamCreateWithFlags(&grp.stream, cudaStreamNonBlocking));
+        VE_TRY(cudaStreamCreateWithFlags(&grp.copy_stream, cudaStreamNonBlocking));
+        for (auto& ev : grp.ev) VE_TRY(cudaEventCreate(&ev));
+    }
     for (int k = 0; k < n; k++) {
         ve_estimator* e = create_member(b, k);
         if (!e) return fail(VE_ERR_CUDA);
@@ -1171,17 +1209,27 @@ int ve_batch_create(const ve_config* cfg, int n, ve_batch** out) {
                           align16(sizeof(double) * states_doubles(e0, e0->Lmax)) + align16(sizeof(int) * 2 * (size_t)e0->Lmax);
     // a batch rarely has every member at capacity: size the arenas for the full capacity of 8 members or a quarter of
     // the batch, whichever is larger (exhaustion is reported as VE_ERR_CAPACITY, never overrun)
-    const size_t members_at_cap = std::max<size_t>(std::min<size_t>(n, 8), (size_t)(n + 3) / 4);
-    b->in_cap = per_in * members_at_cap;
-    b->out_cap = ((size_t)vb::BA_OUT_ST_DOUBLES + 21 * F + 13 + e0->Lmax + 1) * members_at_cap +
-                 ((size_t)vb::BA_OUT_ST_DOUBLES + 21 * F + 13 + 256) * (size_t)n;
+    // per group: full capacity of 4 members or a quarter of the group, whichever is larger, plus a typical share for the rest
+    size_t in_total = 0, out_total = 0;
+    for (int g = 0; g < b->G; g++) {
+        ve_batch::Group& grp = b->groups[g];
+        const size_t at_cap = std::max<size_t>(std::min<size_t>(grp.count, 4), (size_t)(grp.count + 3) / 4);
+        grp.in_base = in_total;
+        grp.in_cap = per_in * at_cap;
+        in_total += grp.in_cap;
+        grp.out_base = out_total;
+        grp.out_cap = ((size_t)vb::BA_OUT_ST_DOUBLES + 21 * F + 13 + e0->Lmax + 1) * at_cap +
+                      ((size_t)vb::BA_OUT_ST_DOUBLES + 21 * F + 13 + 256) * (size_t)grp.count;
+        grp.out_cap = (grp.out_cap + 1) & ~(size_t)1;
+        out_total += grp.out_cap;
+    }
     VE_TRY(cudaMalloc(&b->d_seq, sizeof(vb::BaSeq) * n));
     VE_TRY(cudaHostAlloc(&b->h_seq, sizeof(vb::BaSeq) * n, cudaHostAllocDefault));
     std::memset(b->h_seq, 0, sizeof(vb::BaSeq) * n);
-    VE_TRY(cudaMalloc(&b->d_in, b->in_cap));
-    VE_TRY(cudaHostAlloc(&b->h_in, b->in_cap, cudaHostAllocDefault));
-    VE_TRY(cudaMalloc(&b->d_out, sizeof(double) * b->out_cap));
-    VE_TRY(cudaHostAlloc(&b->h_out, sizeof(double) * b->out_cap, cudaHostAllocDefault));
+    VE_TRY(cudaMalloc(&b->d_in, in_total));
+    VE_TRY(cudaHostAlloc(&b->h_in, in_total, cudaHostAllocDefault));
+    VE_TRY(cudaMalloc(&b->d_out, sizeof(double) * out_total));
+    VE_TRY(cudaHostAlloc(&b->h_out, sizeof(double) * out_total, cudaHostAllocDefault));
 #undef VE_TRY
     b->w_in_global = vb::marg_w_in_global(15, e0->nmax);
     b->pool = new vb::HostPool(vb::HostPool::default_workers(n));
@@ -1192,20 +1240,26 @@ int ve_batch_create(const ve_config* cfg, int n, ve_batch** out) {
 void ve_batch_destroy(ve_batch* b) {
     if (!b) return;
     cudaSetDevice(b->cfg.device);
-    if (b->stream) cudaStreamSynchronize(b->stream);
-    if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
+    for (int g = 0; b->groups && g < b->G; g++) {
+        if (b->groups[g].stream) cudaStreamSynchronize(b->groups[g].stream);
+        if (b->groups[g].copy_stream) cudaStreamSynchronize(b->groups[g].copy_stream);
+    }
     delete b->pool;
     for (auto* e : b->members) destroy_member(e);
     cudaFree(b->d_seq); cudaFree(b->d_in); cudaFree(b->d_out);
     cudaFreeHost(b->h_seq); cudaFreeHost(b->h_in); cudaFreeHost(b->h_out);
-    for (auto& ev : b->ev)
-        if (ev) cudaEventDestroy(ev);
-    if (b->stream) cudaStreamDestroy(b->stream);
-    if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+    for (int g = 0; b->groups && g < b->G; g++) {
+        for (auto& ev : b->groups[g].ev)
+            if (ev) cudaEventDestroy(ev);
+        if (b->groups[g].stream) cudaStreamDestroy(b->groups[g].stream);
+        if (b->groups[g].copy_stream) cudaStreamDestroy(b->groups[g].copy_stream);
+    }
+    delete[] b->groups;
     delete b;
 }
 
 int ve_batch_size(const ve_batch* b) { return b ? b->S : VE_ERR_INVALID; }
+int ve_batch_groups(const ve_batch* b) { return b ? b->G : VE_ERR_INVALID; }
 
 ve_estimator* ve_batch_member(ve_batch* b, int k) { return (b && k >= 0 && k < b->S) ? b->members[k] : nullptr; }
 
@@ -1232,8 +1286,8 @@ int ve_batch_last_timing(const ve_batch* cb, float* ms4, int* launches) {
     if (ms4) {
         if (b->marg_timing_valid) {
             cudaSetDevice(b->cfg.device);
-            if (cudaEventSynchronize(b->ev[3]) != cudaSuccess) return VE_ERR_CUDA;
-            cudaEventElapsedTime(&b->last_ms[2], b->ev[5], b->ev[3]);
+            if (cudaEventSynchronize(b->groups[0].ev[3]) != cudaSuccess) return VE_ERR_CUDA;
+            cudaEventElapsedTime(&b->last_ms[2], b->groups[0].ev[5], b->groups[0].ev[3]);
         }
         std::memcpy(ms4, b->last_ms, sizeof(b->last_ms));
     }
@@ -1259,7 +1313,7 @@ int ve_batch_kernel_times(const ve_batch* b, double* ms8, int* count8) {
 int ve_batch_sync(ve_batch* b) {
     if (!b) return VE_ERR_INVALID;
     VB_CUDA(cudaSetDevice(b->cfg.device));
-    VB_CUDA(cudaStreamSynchronize(b->stream));
+    for (int g = 0; g < b->G; g++) VB_CUDA(cudaStreamSynchronize(b->groups[g].stream));
     return VE_OK;
 }
 
@@ -1386,7 +1440,7 @@ int ve_get_prior(const ve_estimator* ce, int cap, double* A, double* b, int* nbl
     // the marginalisation that produced the prior may still be running: wait for the batch stream, then read the
     // un-floored Schur complement straight from device memory
     VE_CUDA(cudaSetDevice(e->cfg.device));
-    VE_CUDA(cudaStreamSynchronize(e->batch->stream));
+    VE_CUDA(cudaStreamSynchronize(e->batch->groups[e->member / e->batch->members_per_group].stream));
     VE_CUDA(cudaMemcpy(A, e->marg_Araw, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost));
     VE_CUDA(cudaMemcpy(b, e->marg_graw, sizeof(double) * n, cudaMemcpyDeviceToHost));
     if (nblocks) *nblocks = (int)e->prior_blocks.size();
@@ -1421,7 +1475,7 @@ int ve_solver_debug(const ve_estimator* ce, double* out18) {
     double sweeps[7] = {0, 0, 0, 0, 0, 0, 0};
     if (e->has_prior && e->marg_graw) {
         VE_CUDA(cudaSetDevice(e->cfg.device));
-        VE_CUDA(cudaStreamSynchronize(e->batch->stream));
+        VE_CUDA(cudaStreamSynchronize(e->batch->groups[e->member / e->batch->members_per_group].stream));
         VE_CUDA(cudaMemcpy(sweeps, e->marg_graw + e->marg_n, sizeof(sweeps), cudaMemcpyDeviceToHost));
     }
     out18[11] = sweeps[0];

@@ -54,6 +54,7 @@ def _bind(lib):
     lib.ve_batch_create.argtypes = [C.POINTER(EstimatorConfig), C.c_int, C.POINTER(C.c_void_p)]
     lib.ve_batch_destroy.argtypes = [C.c_void_p]
     lib.ve_batch_size.argtypes = [C.c_void_p]
+    lib.ve_batch_groups.argtypes = [C.c_void_p]
     lib.ve_batch_member.argtypes = [C.c_void_p, C.c_int]
     lib.ve_batch_member.restype = C.c_void_p
     lib.ve_batch_last_error.argtypes = [C.c_void_p]
@@ -246,6 +247,9 @@ class EstimatorBatch:
         k = C.c_int(0)
         self.lib.ve_batch_last_timing(self.h, None, C.byref(k))
         return k.value
+
+    def groups(self):
+        return int(self.lib.ve_batch_groups(self.h))
 
     def set_profile(self, on):
         self.lib.ve_batch_set_profile(self.h, int(on))
