@@ -535,25 +535,41 @@ __global__ void __launch_bounds__(RED_THREADS, 3) ba_reduce_kernel(const BaSeq* 
         for (int l0 = 0; l0 < L; l0 += RED_SLAB) {
             const int nl = min(RED_SLAB, L - l0);
             __syncthreads();
+            int unsorted = 0;
             for (int k = tid; k < nl; k += RED_THREADS) {
                 const int l = l0 + k, s0 = p.lm_start[l];
-                s_an[k] = (short)p.lm_anchor[l];
+                const int an = p.lm_anchor[l];
+                s_an[k] = (short)an;
                 s_nobs[k] = (short)(p.lm_start[l + 1] - s0);
                 s_s0[k] = s0;
                 s_inv[k] = lm_inv_lambda(p, a, l, mu, first);
+                if (k > 0 && p.lm_anchor[l - 1] > an) unsorted = 1;
             }
-            __syncthreads();
+            const int sorted_by_anchor = __syncthreads_or(unsorted) == 0;
             if ((worker || gworker) && A.type == 0 && B.type == 0) {
                 // (pose a, pose b): the common case, written so that the loads of four landmarks are in flight together
                 // (no early exits: uncovered landmarks contribute exact zeros through predicated loads)
                 const int fa = A.frame, fb = B.frame;
                 const bool diag = fa == fb;
-                for (int k = slice; k < nl; k += 4 * RED_SLICES) {
+                // The landmark table is ordered by anchor frame (FeatureManager appends new tracks at the end and the slides
+                // keep the order), so the landmarks that can see frame a are a prefix [0, hi) of it.  hi is found from the
+                // staged anchors; an unsorted table (never produced by the host) only costs the shortcut, not correctness.
+                int hi = nl;
+                if (sorted_by_anchor) {
+                    int lo_ = 0, hi_ = nl;  // first k with anchor > fa
+                    while (lo_ < hi_) {
+                        const int mid = (lo_ + hi_) >> 1;
+                        if (s_an[mid] <= fa) lo_ = mid + 1;
+                        else hi_ = mid;
+                    }
+                    hi = lo_;
+                }
+                for (int k = slice; k < hi; k += 4 * RED_SLICES) {
                     double wa[4], wb[4], inv[4], x0[4], x1[4], y0[4], y1[4], gl[4], gv[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         const int kk = k + u * RED_SLICES;
-                        const bool in = kk < nl;
+                        const bool in = kk < hi;
                         const int ks = in ? kk : 0;
                         const int an = s_an[ks], nobs = s_nobs[ks], s0 = s_s0[ks];
                         const bool cv = in && an <= fa && fb <= an + nobs;

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -447,6 +448,10 @@ vb::FeShape base_shape(const vt_batch* b) {
 int batch_read_image(vt_batch* b, const ImageMsg* msgs, size_t stride, bool on_device) {
     VTB_CUDA(cudaSetDevice(b->cfg.device));
     const int S = b->S;
+    static const bool trace = std::getenv("VINSB200_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b2) { return std::chrono::duration<double, std::milli>(b2 - a).count(); };
+    const auto t0 = now();
     b->last_launches = 0;
     b->pool->run(S, [&](int k) {
         vt_tracker* t = b->members[k];
@@ -469,6 +474,7 @@ int batch_read_image(vt_batch* b, const ImageMsg* msgs, size_t stride, bool on_d
         sh.max_pts = std::max(sh.max_pts, q.n_pts);
     }
     if (!sh.any_track) return VT_OK;
+    const auto t1 = now();
     VTB_CUDA(cudaEventRecord(b->ev0, b->stream));
     if (!on_device) {  // the frames of members first_active..last_active travel in one copy
         const int rows = b->cfg.rows, cols = b->cfg.cols;
@@ -481,9 +487,11 @@ int batch_read_image(vt_batch* b, const ImageMsg* msgs, size_t stride, bool on_d
     vb::launch_track(b->d_seq, sh, b->stream, &b->last_launches, &b->prof);
     if (sh.max_pts > 0) VTB_CUDA(cudaMemcpyAsync(b->h_dn, b->d_dn, b->dn_track_bytes, cudaMemcpyDeviceToHost, b->stream));
     VTB_CUDA(cudaStreamSynchronize(b->stream));
+    const auto t2 = now();
     b->pool->run(S, [&](int k) {
         if (b->members[k]->step_active) step_after_track(b->members[k]);
     });
+    const auto t3 = now();
     for (int k = 0; k < S; k++) {
         const vb::FeSeq& q = b->h_seq[k];
         if (!q.detect) continue;
@@ -503,9 +511,13 @@ int batch_read_image(vt_batch* b, const ImageMsg* msgs, size_t stride, bool on_d
     VTB_CUDA(cudaEventSynchronize(b->ev1));
     VTB_CUDA(cudaGetLastError());
     VTB_CUDA(cudaEventElapsedTime(&b->last_ms, b->ev0, b->ev1));
+    const auto t4 = now();
     b->pool->run(S, [&](int k) {
         if (b->members[k]->step_active) step_finish(b->members[k]);
     });
+    if (trace)
+        std::fprintf(stderr, "[vt_batch] prepare %.3f track(gpu) %.3f host %.3f detect(gpu) %.3f finish %.3f ms (S=%d detect=%d)\n", ms(t0, t1), ms(t1, t2),
+                     ms(t2, t3), ms(t3, t4), ms(t4, now()), S, sh.any_detect);
     int rc = VT_OK;
     for (int k = 0; k < S; k++)
         if (b->members[k]->status != VT_OK && rc == VT_OK) {
