@@ -140,8 +140,9 @@ int ve_debug_imu_factor(const double* noise4, double g_norm, const double* ba, c
                         const double* acc, const double* gyr, const double* params32, double* out_preint, double* out_factor);
 
 /* Solver internals of the last solve (profiling/tests): out[0] linear-solver retries, [1] mu, [2] radius,
- * [3..10] per-phase cycle counters of the step kernel summed over the iterations, [11..12] cycles of the
- * tridiagonalisation / QL phases of the last marginalisation's prior eigen-decomposition, [13..17] its phase cycle counters. */
+ * [3..10] per-phase cycle counters of the step kernel summed over the iterations, [11] cycles of the tridiagonalisation of
+ * the last marginalisation's A', [12] eigenpairs its eps floor separated explicitly (-1: the full decomposition ran),
+ * [13..17] phase cycle counters of the marginalisation solve. */
 int ve_solver_debug(const ve_estimator* e, double* out18);
 
 #ifdef __cplusplus

@@ -20,7 +20,7 @@
 #include <cfloat>
 
 #include "ba_device.cuh"
-#include "sym_eig.h"
+#include "prior_floor.h"
 
 namespace vb {
 
@@ -1082,6 +1082,10 @@ __host__ __device__ inline int marg_scratch_doubles(int md, int n, bool w_in_glo
     const int b = n * (ldm + md), c = w_in_global ? 0 : n * (n | 1);
     a = a > b ? a : b;
     a = a > c ? a : c;
+    if (!w_in_global) {  // Wk | Ev together hold the work arrays of the prior's eps floor (prior_floor.h) once both are dead
+        const int f = prior_floor_work(n, MARG_THREADS, 32) - ((q * q + 1) & ~1);
+        a = a > f ? a : f;
+    }
     return (a + 1) & ~1;
 }
 
@@ -1248,70 +1252,27 @@ __global__ void __launch_bounds__(MARG_THREADS) marg_solve_kernel(const BaSeq* _
         for (int idx = tid; idx < n * n; idx += nt) mp.Araw[idx] = 0.5 * (Ap[idx] + Ap[(idx % n) * n + idx / n]);
     if (mp.graw)
         for (int i = tid; i < n; i += nt) mp.graw[i] = mp.gout[i];
-    // 4. eigen-decomposition of A' with the eps floor: A+ = V S+ V^T, g0 = V 1+ V^T b', c0 = b'^T V S+^-1 V^T b'
-    __syncthreads();
-    for (int idx = tid; idx < n * n; idx += nt) {
-        const int i = idx / n, j = idx - i * n;
-        Vv[i * ldvn + j] = 0.5 * (Ap[i * n + j] + Ap[j * n + i]);
-    }
+    // 4. the eps floor of A' (prior_floor.h): A+ = V S+ V^T, g0 = V 1+ V^T b', c0 = b'^T V S+^-1 V^T b'.  Only the eigenpairs at the
+    //    noise floor are separated explicitly when the scratch behind Wk | Ev (both dead by now) holds the work arrays;
+    //    otherwise (reduced system in global memory: the large windows) the full decomposition runs.
     __syncthreads();
     MSTAMP(2);
-    if (n <= 96)
-        sym_eig<CtaCtx, 3>(CtaCtx(), Vv, n, ldvn, dval, ework, cs, scal);
-    else
-        sym_eig<CtaCtx, SE_PER_LANE_MAX>(CtaCtx(), Vv, n, ldvn, dval, ework, cs, scal);
+    __shared__ int fstats[2];
+    {
+        const int avail = (int)(Vv - sm);  // doubles in front of Vv
+        double* fwork = (!mp.w_in_global && prior_floor_work(n, nt, 32) <= avail) ? sm : nullptr;
+        double* fev = mp.w_in_global ? nullptr : Ev;
+        if (n <= 96)
+            prior_floor<CtaCtx, 3>(CtaCtx(), Ap, mp.gout, mp.cout, n, eps, Vv, ldvn, dval, ework, cs, scal, tv, fwork, fev, fstats);
+        else
+            prior_floor<CtaCtx, SE_PER_LANE_MAX>(CtaCtx(), Ap, mp.gout, mp.cout, n, eps, Vv, ldvn, dval, ework, cs, scal, tv, fwork, fev, fstats);
+    }
     MSTAMP(3);
-    for (int k = tid; k < n; k += nt) {
-        double s = 0;
-        for (int i = 0; i < n; i++) s += Vv[i * ldvn + k] * mp.gout[i];
-        tv[k] = s;  // V_k^T b'
-    }
-    __syncthreads();
-    double cpart = 0;
-    for (int k = tid; k < n; k += nt) {
-        const double w = dval[k];
-        if (w > eps) cpart += tv[k] * tv[k] / w;
-    }
-    const double c0 = block_sum(cpart, red);
-    // A+ = V diag(w+) V^T with the floored eigenvalues w+ (ework is free after the decomposition)
-    for (int k = tid; k < n; k += nt) ework[k] = dval[k] > eps ? dval[k] : 0.0;
-    __syncthreads();
-    if (!mp.w_in_global) {  // room for a scaled copy of V: one multiply less in the n^3 product
-        for (int idx = tid; idx < n * n; idx += nt) {
-            const int i = idx / n, k = idx - i * n;
-            Ev[i * ldvn + k] = Vv[i * ldvn + k] * ework[k];
-        }
-        __syncthreads();
-        for (int idx = tid; idx < n * n; idx += nt) {
-            const int i = idx / n, j = idx - i * n;
-            double s = 0;
-            for (int k = 0; k < n; k++) s += Ev[i * ldvn + k] * Vv[j * ldvn + k];
-            Ap[idx] = s;
-        }
-    } else {
-        for (int idx = tid; idx < n * n; idx += nt) {
-            const int i = idx / n, j = idx - i * n;
-            double s = 0;
-            for (int k = 0; k < n; k++) s += Vv[i * ldvn + k] * ework[k] * Vv[j * ldvn + k];
-            Ap[idx] = s;
-        }
-    }
-    for (int i = tid; i < n; i += nt) {
-        double s = 0;
-        for (int k = 0; k < n; k++)
-            if (dval[k] > eps) s += Vv[i * ldvn + k] * tv[k];
-        bw[i] = s;
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += nt) mp.gout[i] = bw[i];
-    if (tid == 0) {
-        mp.cout[0] = c0;
-        if (mp.graw) {  // diagnostics behind the n used entries
-            mp.graw[n] = scal[4];      // A' decomposition: tridiagonalisation cycles
-            mp.graw[n + 1] = scal[5];  // QL cycles
-            MSTAMP(4);
-            for (int k = 0; k < 5; k++) mp.graw[n + 2 + k] = (double)mclk[k];
-        }
+    if (tid == 0 && mp.graw) {  // diagnostics behind the n used entries
+        mp.graw[n] = scal[4];              // A' decomposition: tridiagonalisation cycles
+        mp.graw[n + 1] = (double)fstats[0];  // eigenpairs separated explicitly (-1: full decomposition)
+        MSTAMP(4);
+        for (int k = 0; k < 5; k++) mp.graw[n + 2 + k] = (double)mclk[k];
     }
 }
 

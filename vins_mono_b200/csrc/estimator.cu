@@ -1059,6 +1059,10 @@ int batch_process(ve_batch* b, const FrameMsg* msgs, int* status_out) {
             }
         }
         if (!sh.any_jobs && !sh.any_active) continue;
+        if (sh.any_marg) {  // reduced system of the marginalisation in shared memory whenever this frame's sizes fit
+            sh.w_in_global = vb::marg_w_in_global(sh.max_md, sh.max_n);
+            for (int k = grp.first; k < grp.first + grp.count; k++) b->h_seq[k].mp.w_in_global = sh.w_in_global;
+        }
         vb::BaSeq* dq = b->d_seq + grp.first;
         VB_CUDA(cudaMemcpyAsync(dq, b->h_seq + grp.first, sizeof(vb::BaSeq) * grp.count, cudaMemcpyHostToDevice, grp.stream));
         const size_t in_bytes = std::min(grp.in_used.load(), grp.in_cap);

@@ -66,6 +66,7 @@ struct HostCtx {
     int lane() const { return 0; }
     int ws() const { return 1; }
     void warp_sync() const {}
+    double wsum(double x) const { return x; }
     bool is_aux() const { return true; }
     int aux_lane() const { return 0; }
     int aux_size() const { return 1; }
@@ -102,6 +103,7 @@ struct CtaCtx {  // blockDim.x a multiple of 32 and >= 128; named barriers 1..4 
     __device__ int lane() const { return threadIdx.x & 31; }
     __device__ int ws() const { return 32; }
     __device__ void warp_sync() const { __syncwarp(); }
+    __device__ double wsum(double x) const { return lead_sum(x); }  // any full warp
     // aux group: the last warp (idle in the row-group loops when there are more groups than rows)
     __device__ bool is_aux() const { return (threadIdx.x >> 5) == (blockDim.x >> 5) - 1; }
     __device__ int aux_lane() const { return threadIdx.x & 31; }
@@ -298,21 +300,16 @@ __device__ inline void ql_pipelined(double* V, int n, int ld, double* d, double*
 
 // SE_PER_LANE: columns per lane of the warp-wide phases on the device (n <= 32 * SE_PER_LANE); callers pick the smallest
 // instantiation that covers their n (the unrolled per-lane loops cost instructions even when predicated off).
+#define VV(i, j) V[(i) * ld + (j)]
+// Stage 1 (n >= 2): Householder tridiagonalisation.  Leaves the diagonal of T in VV(i, i), the sub-diagonal T(i, i-1) in
+// cs[n + i], the reflector scalars h_i in cs[2n + i] and reflector i (components 0 .. i-1) in column i of V; d, e and
+// cs[0, n) are scratch afterwards.  se_finish or se_small_eigs continue from this state.
 template <class Ctx, int SE_PER_LANE = 3>
-SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, double* cs, double* scal) {
+SE_HD void se_tridiag(Ctx ctx, double* V, int n, int ld, double* d, double* e, double* cs, double* scal) {
     const int tid = ctx.tid(), nt = ctx.nt();
     const int LD = ctx.lead(), G = ctx.grp();
     const int wid = ctx.wid(), nw = ctx.nw(), lane = ctx.lane(), ws = ctx.ws();
     const int gi = tid / G, gl = tid - gi * G, ng = nt / G;  // row-group coordinates
-#define VV(i, j) V[(i) * ld + (j)]
-    if (n == 1) {
-        if (tid == 0) {
-            d[0] = V[0];
-            V[0] = 1.0;
-        }
-        ctx.sync();
-        return;
-    }
 #if defined(__CUDA_ARCH__)
     const long long clk0 = clock64();
 #endif
@@ -491,6 +488,23 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
         u = un;
         un = t;
     }
+#if defined(__CUDA_ARCH__)
+    if (tid == 0) scal[4] = (double)(clock64() - clk0);
+#endif
+}
+
+// Stage 2: accumulation of the reflectors into V (tred2 part 2) and implicit-shift QL with the rotations applied to V.
+template <class Ctx, int SE_PER_LANE = 3>
+SE_HD void se_finish(Ctx ctx, double* V, int n, int ld, double* d, double* e, double* cs, double* scal) {
+    const int tid = ctx.tid(), nt = ctx.nt();
+    const int LD = ctx.lead(), G = ctx.grp();
+    const int wid = ctx.wid(), nw = ctx.nw(), lane = ctx.lane(), ws = ctx.ws();
+    const int gi = tid / G, gl = tid - gi * G, ng = nt / G;  // row-group coordinates
+    double* sub = cs + n;
+    double* hv = cs + 2 * n;
+    double* rhv = cs + 3 * n;
+    (void)LD;
+    SE_T0();
     // ---- tred2 part 2: accumulate the transformations (2 barrier phases per step)
     for (int i = tid; i < n; i += nt) rhv[i] = hv[i] != 0.0 ? 1.0 / hv[i] : 0.0;
     if (tid == 0) {
@@ -572,7 +586,6 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
     if constexpr (Ctx::kPipelinedQL) {
         ql_pipelined<(SE_PER_LANE > 3)>(V, n, ld, d, e, cs, scal);
         if (tid == 0) {
-            scal[4] = (double)(clk1 - clk0);
             scal[5] = (double)(clock64() - clk1);
         }
         ctx.sync();
@@ -630,13 +643,306 @@ SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, doub
         ctx.sync();
     }
 #if defined(__CUDA_ARCH__)
-    if (tid == 0) {  // phase cycle counters for profiling: tridiagonalisation, QL
-        scal[4] = (double)(clk1 - clk0);
-        scal[5] = (double)(clock64() - clk1);
-    }
+    if (tid == 0) scal[5] = (double)(clock64() - clk1);  // phase cycle counter for profiling
     ctx.sync();
 #endif
-#undef VV
 }
+
+// ------------------------------------------------------------------------------------------------
+// The eigenpairs below a threshold only (the marginalisation prior needs nothing else of its decomposition: the kept part
+// of the spectrum never has to be separated from the matrix, see prior_floor.h).  LAPACK's dstebz / dstein scheme on the
+// tridiagonal form: Sturm-sequence counts + multisection for the eigenvalues (every thread evaluates one abscissa per
+// round), inverse iteration with partial-pivoting LU of T - lambda I for the vectors, joint modified Gram-Schmidt (the
+// eigenvalues at the noise floor eps |T| form one cluster), Rayleigh quotients, back-transformation through the stored
+// reflectors.  None of it has the O(n^2)-step serial rotation chain of QL.
+constexpr int SE_KMAX = 16;
+
+// Eigenvalues of the tridiagonal (td, te2 = squared sub-diagonal) below x: negative pivots of the LDL^T of T - x I.
+SE_HD inline int se_sturm(const double* td, const double* te2, int n, double x, double pivmin) {
+    double q = td[0] - x;
+    if (fabs(q) <= pivmin) q = -pivmin;
+    int c = q < 0.0 ? 1 : 0;
+    for (int i = 1; i < n; i++) {
+        q = (td[i] - x) - te2[i - 1] * (1.0 / q);
+        if (fabs(q) <= pivmin) q = -pivmin;
+        c += q < 0.0 ? 1 : 0;
+    }
+    return c;
+}
+
+// doubles of scratch se_small_eigs needs in `work` for n, kmax and nt threads (ws = threads per warp of the context)
+SE_HD inline int se_small_work(int n, int kmax, int nt, int ws) {
+    const int c = nt > kmax * ws ? nt : kmax * ws;
+    return 16 + 3 * kmax + c + kmax * 5 * n;
+}
+
+// Continues from se_tridiag.  tau = max(tau_rel * |T|, tau_min).  Returns k >= 0: lam[j] (Rayleigh quotients, ascending
+// up to noise) and X[j * n .. +n) = orthonormal eigenvectors of the ORIGINAL matrix for all eigenvalues below tau; or -1 when
+// there are more than kmax (<= SE_KMAX) of them or a vector failed its residual check.  V and cs[n, 3n) are left intact
+// either way (se_finish can still run).  d, e hold T afterwards; work[0] = |T| (max row sum), work[1] = tau.
+template <class Ctx>
+SE_HD int se_small_eigs(Ctx ctx, const double* V, int n, int ld, double* d, double* e, double* cs, double tau_rel,
+                        double tau_min, int kmax, double* lam, double* X, double* work) {
+    const int tid = ctx.tid(), nt = ctx.nt();
+    const int LD = ctx.lead();
+    const int wid = ctx.wid(), nw = ctx.nw(), lane = ctx.lane(), ws = ctx.ws();
+    const double ulp = 2.220446049250313e-16;
+    const double* sub = cs + n;
+    const double* hv = cs + 2 * n;
+    double* te2 = cs;
+    double* S = work;
+    double* lohi = work + 16;
+    double* lhat = lohi + 2 * kmax;
+    double* cnt = lhat + kmax;
+    double* fac = cnt + (nt > kmax * ws ? nt : kmax * ws);
+    for (int i = tid; i < n; i += nt) {
+        d[i] = V[i * ld + i];
+        const double ei = i + 1 < n ? sub[i + 1] : 0.0;
+        e[i] = ei;
+        te2[i] = ei * ei;
+    }
+    ctx.sync();
+    if (tid == 0) {
+        double tn = 0.0, gl = d[0], emax = 0.0;
+        for (int i = 0; i < n; i++) {
+            const double r = fabs(e[i]) + (i > 0 ? fabs(e[i - 1]) : 0.0);
+            tn = fmax(tn, fabs(d[i]) + r);
+            gl = fmin(gl, d[i] - r);
+            emax = fmax(emax, te2[i]);
+        }
+        S[0] = tn;
+        S[1] = fmax(tau_rel * tn, tau_min);
+        S[2] = gl - 2.0 * ulp * tn * n - 1e-300;
+        S[6] = 2.2250738585072014e-308 * fmax(1.0, emax);
+        S[5] = 0.0;  // failure flag
+    }
+    ctx.sync();
+    const double tnorm = S[0], tau = S[1], pivmin = S[6];
+    const double atol = 2.0 * ulp * tnorm;
+    SE_T0();
+    const int k = se_sturm(d, te2, n, tau, pivmin);  // every thread: the same arithmetic, the same answer
+    if (k == 0) return 0;
+    if (k > kmax) return -1;
+    // ---- hull of the k wanted eigenvalues in ONE round: every thread evaluates one abscissa of a geometric ladder (ratio
+    // 2^c per rung) from -|T| up to -atol/4 and from +atol/4 up to tau, so the hull comes out within one rung of the
+    // extreme wanted eigenvalues whatever their magnitude (skipped by narrow contexts: bisection below does it all)
+    double lo = S[2], hi = tau;
+    if (nt >= 64) {
+        const int half = nt / 2;
+        const double xmin = 0.25 * atol;
+        double x;
+        if (tid < half) {
+            const double c = log2(tnorm / xmin) / (double)(half - 1);
+            x = -tnorm * exp2(-c * (double)tid);
+        } else {
+            const double c = tau > xmin ? log2(tau / xmin) / (double)(nt - half - 1) : 0.0;
+            x = tau * exp2(-c * (double)(nt - 1 - tid));
+        }
+        const int c = se_sturm(d, te2, n, x, pivmin);
+        cnt[tid] = (double)c;
+        if (tid == 0) {
+            S[3] = lo;
+            S[4] = hi;
+        }
+        ctx.sync();
+        if (c <= 0 && (tid == nt - 1 || cnt[tid + 1] > 0.0)) S[3] = x;
+        if (c >= k && (tid == 0 || cnt[tid - 1] < (double)k)) S[4] = x;
+        ctx.sync();
+        lo = S[3];
+        hi = S[4];
+        ctx.sync();
+    }
+    // ---- eigenvalue j (0-based from below): (ws + 1)-section by warp j
+    for (int j = wid; j < k; j += nw) {
+        double lj = lo, hj = hi;
+        double* wc = cnt + (j % nw) * ws;
+        for (int round = 0; round < 128 && hj - lj > atol; round++) {
+            const double x = lj + (hj - lj) * ((double)(lane + 1) / (double)(ws + 1));
+            const int c = se_sturm(d, te2, n, x, pivmin);
+            wc[lane] = (double)c;
+            if (lane == 0) {
+                lohi[2 * j] = lj;
+                lohi[2 * j + 1] = hj;
+            }
+            ctx.warp_sync();
+            if (c <= j && (lane == ws - 1 || wc[lane + 1] > (double)j)) lohi[2 * j] = x;
+            if (c > j && (lane == 0 || wc[lane - 1] <= (double)j)) lohi[2 * j + 1] = x;
+            ctx.warp_sync();
+            lj = lohi[2 * j];
+            hj = lohi[2 * j + 1];
+            ctx.warp_sync();
+        }
+        if (lane == 0) lhat[j] = 0.5 * (lj + hj);
+    }
+    ctx.sync();
+    SE_STAMP(11);  // bisection
+    if (tid == 0) {  // keep the shifts of a cluster apart (dstein's perturbation)
+        const double sep = 4.0 * ulp * tnorm;
+        for (int j = 1; j < k; j++)
+            if (lhat[j] - lhat[j - 1] < sep) lhat[j] = lhat[j - 1] + sep;
+    }
+    ctx.sync();
+    // ---- inverse iteration: P L U = T - lhat[j] I (dlagtf), then U^-1 L^-1 P applied four times (dlagts with perturbed pivots)
+    const double tiny = ulp * tnorm;
+    for (int j = wid; j < k; j += nw) {
+        if (lane != 0) continue;
+        double* fa = fac + (size_t)j * 5 * n;  // U diagonal
+        double* fb = fa + n;                    // U first super-diagonal
+        double* fd = fb + n;                    // U second super-diagonal
+        double* fl = fd + n;                    // multipliers
+        double* fi = fl + n;                    // 1: rows k, k+1 were interchanged
+        const double sh = lhat[j];
+        for (int i = 0; i < n; i++) {
+            fa[i] = d[i] - sh;
+            fb[i] = e[i];
+            fd[i] = 0.0;
+        }
+        for (int i = 0; i + 1 < n; i++) {
+            const double ci = e[i];  // sub-diagonal entry of row i + 1
+            if (fabs(fa[i]) >= fabs(ci)) {
+                const double m = fa[i] != 0.0 ? ci / fa[i] : 0.0;
+                fl[i] = m;
+                fi[i] = 0.0;
+                fa[i + 1] -= m * fb[i];
+            } else {
+                const double m = fa[i] / ci;
+                fl[i] = m;
+                fi[i] = 1.0;
+                fa[i] = ci;
+                const double t = fa[i + 1];
+                fa[i + 1] = fb[i] - m * t;
+                if (i + 2 < n) {
+                    fd[i] = fb[i + 1];
+                    fb[i + 1] = -m * fd[i];
+                }
+                fb[i] = t;
+            }
+        }
+        // reciprocal pivots for the back substitutions; a vanishing pivot (the shift IS an eigenvalue) is replaced by eps |T|
+        for (int i = 0; i < n; i++) {
+            double ak = fa[i];
+            if (fabs(ak) < tiny) ak = ak < 0.0 ? -tiny : tiny;
+            fa[i] = 1.0 / ak;
+        }
+    }
+    ctx.sync();
+    for (int it = 0; it < 4; it++) {
+        for (int j = wid; j < k; j += nw) {
+            if (lane != 0) continue;
+            const double* fa = fac + (size_t)j * 5 * n;
+            const double *fb = fa + n, *fd = fb + n, *fl = fd + n, *fi = fl + n;
+            double* y = X + (size_t)j * n;
+            if (it == 0) {  // start vector: fixed pseudo-random numbers in (-1, 1)
+                unsigned sd = 12345u + 7919u * (unsigned)j;
+                for (int i = 0; i < n; i++) {
+                    sd = sd * 1664525u + 1013904223u;
+                    y[i] = (double)(sd >> 8) * (2.0 / 16777216.0) - 1.0;
+                }
+            }
+            // forward: y <- L^-1 P y, the running entry in a register (one multiply-add per row on the dependent chain)
+            double cur = y[0];
+            for (int i = 0; i + 1 < n; i++) {
+                const double nxt = y[i + 1], m = fl[i];
+                if (fi[i] == 0.0) {
+                    y[i] = cur;
+                    cur = nxt - m * cur;
+                } else {
+                    y[i] = nxt;
+                    cur = cur - m * nxt;
+                }
+            }
+            // backward: y <- U^-1 y with the reciprocal pivots
+            double y1 = cur * fa[n - 1], y2 = 0.0;
+            y[n - 1] = y1;
+            for (int i = n - 2; i >= 0; i--) {
+                const double t = (y[i] - fb[i] * y1 - fd[i] * y2) * fa[i];
+                y[i] = t;
+                y2 = y1;
+                y1 = t;
+            }
+        }
+        ctx.sync();
+        if (tid < LD) {  // joint modified Gram-Schmidt, one group of threads
+            for (int j = 0; j < k; j++) {
+                double* y = X + (size_t)j * n;
+                double nb = 0.0;
+                for (int i = tid; i < n; i += LD) nb += y[i] * y[i];
+                nb = ctx.lead_sum(nb);
+                for (int jp = 0; jp < j; jp++) {
+                    const double* z = X + (size_t)jp * n;
+                    double s = 0.0;
+                    for (int i = tid; i < n; i += LD) s += z[i] * y[i];
+                    s = ctx.lead_sum(s);
+                    for (int i = tid; i < n; i += LD) y[i] -= s * z[i];
+                    ctx.lead_sync();
+                }
+                double nn = 0.0;
+                for (int i = tid; i < n; i += LD) nn += y[i] * y[i];
+                nn = ctx.lead_sum(nn);
+                if (it == 3 && !(nn > 1e-12 * nb) && tid == 0) S[5] = 1.0;  // no direction of its own left
+                const double sc = nn > 0.0 ? 1.0 / sqrt(nn) : 0.0;
+                for (int i = tid; i < n; i += LD) y[i] *= sc;
+                ctx.lead_sync();
+            }
+        }
+        ctx.sync();
+    }
+    SE_STAMP(12);  // inverse iteration
+    double* rh = cs + 3 * n;  // free until se_finish recomputes it
+    for (int i = tid; i < n; i += nt) rh[i] = hv[i] != 0.0 ? 1.0 / hv[i] : 0.0;
+    ctx.sync();
+    // ---- Rayleigh quotients, residual check, back-transformation x = H_(n-1) .. H_1 u
+    for (int j = wid; j < k; j += nw) {
+        double* y = X + (size_t)j * n;
+        double rq = 0.0;
+        for (int i = lane; i < n; i += ws) {
+            double t = d[i] * y[i];
+            if (i > 0) t += e[i - 1] * y[i - 1];
+            if (i + 1 < n) t += e[i] * y[i + 1];
+            rq += y[i] * t;
+        }
+        rq = ctx.wsum(rq);
+        double rs = 0.0;
+        for (int i = lane; i < n; i += ws) {
+            double t = (d[i] - rq) * y[i];
+            if (i > 0) t += e[i - 1] * y[i - 1];
+            if (i + 1 < n) t += e[i] * y[i + 1];
+            rs += t * t;
+        }
+        rs = ctx.wsum(rs);
+        if (lane == 0) {
+            lam[j] = rq;
+            const double lim = 1e3 * ulp * tnorm;
+            if (!(rs <= lim * lim)) S[5] = 1.0;
+        }
+        ctx.warp_sync();
+        for (int i = 1; i < n; i++) {
+            const double r = rh[i];
+            if (r == 0.0) continue;
+            double s = 0.0;
+            for (int t = lane; t < i; t += ws) s += V[t * ld + i] * y[t];
+            s = ctx.wsum(s) * r;
+            for (int t = lane; t < i; t += ws) y[t] -= s * V[t * ld + i];
+        }
+    }
+    ctx.sync();
+    SE_STAMP(13);  // Rayleigh quotients + back-transformation
+    return S[5] != 0.0 ? -1 : k;
+}
+
+template <class Ctx, int SE_PER_LANE = 3>
+SE_HD void sym_eig(Ctx ctx, double* V, int n, int ld, double* d, double* e, double* cs, double* scal) {
+    if (n == 1) {
+        if (ctx.tid() == 0) {
+            d[0] = V[0];
+            V[0] = 1.0;
+        }
+        ctx.sync();
+        return;
+    }
+    se_tridiag<Ctx, SE_PER_LANE>(ctx, V, n, ld, d, e, cs, scal);
+    se_finish<Ctx, SE_PER_LANE>(ctx, V, n, ld, d, e, cs, scal);
+}
+#undef VV
 
 }  // namespace vb

@@ -175,7 +175,7 @@ class Estimator:
     def solver_debug(self):
         out = np.zeros(18)
         self.lib.ve_solver_debug(self.h, _p(out))
-        return dict(retries=int(out[0]), mu=out[1], radius=out[2], clk=out[3:].astype(np.int64).tolist())
+        return dict(retries=int(out[0]), mu=out[1], radius=out[2], clk=out[3:].astype(np.int64).tolist(), floor_pairs=int(out[12]))
 
     def launch_count(self):
         """Kernel launches of the last processImage (does not wait for a pending marginalisation)."""
