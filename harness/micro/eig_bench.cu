@@ -114,9 +114,9 @@ int main(int argc, char** argv) {
             printf("prior floor, %s: %s  explicit pairs %d dropped %d  c0 %.12g  total %lld cycles\n", partial ? "partial route" : "full decomposition",
                    cudaGetErrorString(cudaGetLastError()), st[partial][0], st[partial][1], c0[partial], clk[16]);
             if (partial) {
-                const char* nm[] = {"bisection", "inverse iteration + MGS", "Rayleigh q. + back-transformation", "M + LDL^T", "A+, g0"};
+                const char* nm[] = {"bisection", "inverse iteration + MGS", "Rayleigh q. + back-transformation", "A+, g0, M, LDL^T"};
                 printf("    tridiagonalisation A/B/C           %9lld\n", clk[0] + clk[1] + clk[2]);
-                for (int k = 0; k < 5; k++) printf("    %-34s %9lld\n", nm[k], clk[11 + k]);
+                for (int k = 0; k < 4; k++) printf("    %-34s %9lld\n", nm[k], clk[11 + k]);
             }
         }
         double dAm = 0, am = 0, dgm = 0, gm = 0;

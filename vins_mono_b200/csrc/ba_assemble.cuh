@@ -702,4 +702,25 @@ __device__ __forceinline__ double lm_row_dot(const BaProblem& p, const BaAccum& 
     return warp_sum_d(s);
 }
 
+// The same sum by a group of 8 adjacent lanes (gl = lane within the group); every lane of the warp must call it (l >= L: 0).
+__device__ __forceinline__ double lm_row_dot8(const BaProblem& p, const BaAccum& a, int l, int L, const double* v, int gl) {
+    const BaDims& d = p.dims;
+    double s = 0;
+    if (l < L) {
+        const int an = p.lm_anchor[l], s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0;
+        const double* rec = a.lmW + (size_t)l * d.lw;
+        for (int idx = gl; idx < 6 * (nobs + 1); idx += 8) {
+            const int t = idx / 6, i = idx - 6 * t;
+            const double w = t == 0 ? rec[LW_WI + i] : a.obsJ[(size_t)(s0 + t - 1) * d.oj + OJ_WJ + i];
+            s += w * v[6 * (an + t) + i];
+        }
+        if (d.col_ex >= 0 && gl < 6) s += rec[LW_WE + gl] * v[d.col_ex + gl];
+        if (d.col_td >= 0 && gl == 6) s += rec[LW_WT] * v[d.col_td];
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    return s;
+}
+
 }  // namespace vb

@@ -619,6 +619,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// The same transfer as `chunk`-byte pieces issued back to back by one thread: several bulk requests in flight drain a 119 KB
+// matrix from L2 faster than one request walking it alone (17 k cycles measured for the single copy, harness/debug_backend.py).
+__device__ __forceinline__ void bulk_g2s_chunked(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned chunk, unsigned long long* bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    for (unsigned off = 0; off < bytes; off += chunk) {
+        const unsigned nb = bytes - off < chunk ? bytes - off : chunk;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem) + off),
+                     "l"((const char*)src_gmem + off), "r"(nb), "r"(smem_u32(bar))
+                     : "memory");
+    }
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     asm volatile(
         "{\n"
@@ -669,11 +681,14 @@ __global__ void __launch_bounds__(512) ba_step_kernel(const BaSeq* __restrict__ 
     long long c0 = clock64();
 #define STAMP(k) do { if (tid == 0) { const long long c1_ = clock64(); st->clk[k] += c1_ - c0; c0 = c1_; } } while (0)
     const int npk0 = D * (D + 1) / 2;
-    const bool bulk_ok = use_smem_chol && (npk0 & 1) == 0;  // 16-byte granularity of cp.async.bulk
+    // cp.async.bulk moves multiples of 16 bytes: an odd count is rounded up, the extra double lands on Lp[npk0] (the first
+    // entry of the right-hand-side row, written after the transfer has completed; Spk is allocated for the largest D)
+    const unsigned copy_bytes = (unsigned)(((npk0 + 1) & ~1) * sizeof(double));
+    const bool bulk_ok = use_smem_chol != 0;
     bool copy_in_flight = false;
     if (!st->reuse && bulk_ok) {
         // start the transfer of the packed Schur complement now: it overlaps the scaling / gradient phase below
-        if (tid == 0) bulk_g2s(Lp, p.Spk, (unsigned)(npk0 * sizeof(double)), &copy_bar);
+        if (tid == 0) bulk_g2s_chunked(Lp, p.Spk, copy_bytes, 8192u, &copy_bar);
         copy_in_flight = true;
     }
     if (!st->reuse) {
@@ -696,12 +711,17 @@ __global__ void __launch_bounds__(512) ba_step_kernel(const BaSeq* __restrict__ 
             if (bulk_ok) {
                 if (!copy_in_flight) {  // a retry with a larger mu: fetch the matrix again
                     __syncthreads();    // every thread is done with the previous contents of Lp
-                    if (tid == 0) bulk_g2s(Lp, p.Spk, (unsigned)(npk * sizeof(double)), &copy_bar);
+                    if (tid == 0) bulk_g2s_chunked(Lp, p.Spk, copy_bytes, 8192u, &copy_bar);
                 }
                 copy_in_flight = false;
-                for (int j = tid; j <= D; j += nt) Lp[npk + j] = j < D ? p.gred[j] : 0.0;  // row D: the right-hand side
+                double rhs[2];  // row D: the right-hand side (D <= 2 nt), fetched while the transfer runs
+#pragma unroll
+                for (int u = 0; u < 2; u++) rhs[u] = tid + u * nt < D ? p.gred[tid + u * nt] : 0.0;
                 mbar_wait(&copy_bar, copy_phase);
                 copy_phase ^= 1;
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+                    if (tid + u * nt <= D) Lp[npk + tid + u * nt] = rhs[u];
             } else {
                 for (int idx = tid; idx < npk; idx += nt) Lp[idx] = p.Spk[idx];
                 for (int j = tid; j <= D; j += nt) Lp[npk + j] = j < D ? p.gred[j] : 0.0;  // row D: the right-hand side
@@ -736,9 +756,12 @@ __global__ void __launch_bounds__(512) ba_step_kernel(const BaSeq* __restrict__ 
             __syncthreads();
             STAMP(4);
             for (int j = tid; j < D; j += nt) y[j] = ysm[j];
-            for (int l = wid; l < L; l += nw) {
-                const double s = lm_row_dot(p, a, l, ysm, lane);
-                if (lane == 0) y[D + l] = (a.lmW[(size_t)l * d.lw + LW_GL] - s) * lm_inv_lambda(p, a, l, mu, first);
+            // landmark back-substitution, 8 lanes per landmark (4 landmarks per warp in flight: the loop is bound by the
+            // latency of the record reads, 25 k cycles per iteration with a warp per landmark)
+            for (int l0 = 4 * wid; l0 < L; l0 += 4 * nw) {
+                const int l = l0 + (lane >> 3);
+                const double s = lm_row_dot8(p, a, l, L, ysm, lane & 7);
+                if (l < L && (lane & 7) == 0) y[D + l] = (a.lmW[(size_t)l * d.lw + LW_GL] - s) * lm_inv_lambda(p, a, l, mu, first);
             }
             __syncthreads();
             for (int j = tid; j < N; j += nt) p.gn[j] = -p.diag[j] * y[j] / p.scale[j];
@@ -1206,35 +1229,113 @@ __global__ void __launch_bounds__(MARG_THREADS) marg_solve_kernel(const BaSeq* _
         }
     }
     __syncthreads();
-    // 2. pseudo-inverse of the dense marginalised block T (md x md) by eigen-decomposition
+    // 2. pseudo-inverse of the dense marginalised block T (md x md, md <= 15).  The reference takes V diag(1/w where w > eps) V^T
+    //    (marginalization_factor.cpp:268-275); whenever T - s I still has a Cholesky factor (s = max(2 eps, 64 ulp trace T):
+    //    every eigenvalue beyond doubt above the floor) that is the plain inverse, computed by warp 0 from the factor of T:
+    //    20 k cycles against 116 k for the decomposition.  Otherwise the decomposition decides pair by pair.
     const int ldvm = md | 1, ldvn = n | 1;
-    for (int idx = tid; idx < md * md; idx += nt) {
-        const int i = idx / md, j = idx - i * md;
-        Vv[i * ldvm + j] = Wk[i * q + j];
-    }
-    __syncthreads();
+    __shared__ double Tl[16][17], Tinv[16][17];
+    __shared__ int t_pd;
     MSTAMP(0);
-    sym_eig<CtaCtx, 3>(CtaCtx(), Vv, md, ldvm, dval, ework, cs, scal);  // md <= 15
-    MSTAMP(1);
-    for (int k = tid; k < md; k += nt) tv[k] = dval[k] > eps ? 1.0 / dval[k] : 0.0;
-    __syncthreads();
-    // 3. X = Wrm Tinv (n x md) computed directly from the eigen-factors: X = (Wrm V) diag(tv) V^T
-    //    Y = Wrm V diag(tv) -> Ev as n x md
-    for (int idx = tid; idx < n * md; idx += nt) {
-        const int i = idx / md, k = idx - i * md;
-        double s = 0;
-        for (int j = 0; j < md; j++) s += Wk[(md + i) * q + j] * Vv[j * ldvm + k];
-        Ev[idx] = s * tv[k];
+    if (tid < 32) {
+        const int lane = tid;
+        double tr = 0.0;
+        if (lane < md) tr = Wk[lane * q + lane];
+        tr = warp_sum_d(tr);
+        const double shift = fmax(2.0 * eps, 64.0 * 2.220446049250313e-16 * tr);
+        bool ok = true;
+        for (int pass = 0; pass < 2 && ok; pass++) {  // pass 0: T - shift I (the test), pass 1: T
+            for (int idx = lane; idx < md * md; idx += 32) {
+                const int i = idx / md, j = idx - i * md;
+                Tl[i][j] = Wk[i * q + j] - ((i == j && pass == 0) ? shift : 0.0);
+            }
+            __syncwarp();
+            for (int j = 0; j < md; j++) {  // lane i owns row i
+                const double piv = Tl[j][j];
+                if (!(piv > 0.0) || !(piv < 1e300)) {
+                    ok = false;
+                    break;
+                }
+                const double r = rsqrt(piv);
+                double lij = 0.0;
+                if (lane >= j && lane < md) {
+                    lij = lane == j ? piv * r : Tl[lane][j] * r;
+                    Tl[lane][j] = lij;
+                }
+                __syncwarp();
+                if (lane > j && lane < md)
+                    for (int c = j + 1; c <= lane; c++) Tl[lane][c] -= lij * Tl[c][j];
+                __syncwarp();
+            }
+        }
+        if (ok && lane < md) {  // column `lane` of T^-1: L z = e_lane, L^T x = z
+            double x[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                double v = i == lane ? 1.0 : 0.0;
+                if (i < md) {
+#pragma unroll
+                    for (int c = 0; c < 16; c++)
+                        if (c < i) v -= Tl[i][c] * x[c];
+                    v /= Tl[i][i];
+                }
+                x[i] = i < md ? v : 0.0;
+            }
+#pragma unroll
+            for (int i = 15; i >= 0; i--) {
+                if (i < md) {
+                    double v = x[i];
+#pragma unroll
+                    for (int c = 0; c < 16; c++)
+                        if (c > i && c < md) v -= Tl[c][i] * x[c];
+                    x[i] = v / Tl[i][i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                if (i < md) Tinv[i][lane] = x[i];
+        }
+        if (lane == 0) t_pd = ok ? 1 : 0;
     }
     __syncthreads();
     double* X = Ev + (size_t)n * md;  // n x md
-    for (int idx = tid; idx < n * md; idx += nt) {
-        const int i = idx / md, j = idx - i * md;
-        double s = 0;
-        for (int k = 0; k < md; k++) s += Ev[i * md + k] * Vv[j * ldvm + k];
-        X[idx] = s;
+    if (t_pd) {
+        MSTAMP(1);
+        // 3. X = Wrm Tinv (n x md)
+        for (int idx = tid; idx < n * md; idx += nt) {
+            const int i = idx / md, j = idx - i * md;
+            double s = 0;
+            for (int k = 0; k < md; k++) s += Wk[(md + i) * q + k] * Tinv[k][j];
+            X[idx] = s;
+        }
+        __syncthreads();
+    } else {
+        for (int idx = tid; idx < md * md; idx += nt) {
+            const int i = idx / md, j = idx - i * md;
+            Vv[i * ldvm + j] = Wk[i * q + j];
+        }
+        __syncthreads();
+        sym_eig<CtaCtx, 3>(CtaCtx(), Vv, md, ldvm, dval, ework, cs, scal);  // md <= 15
+        MSTAMP(1);
+        for (int k = tid; k < md; k += nt) tv[k] = dval[k] > eps ? 1.0 / dval[k] : 0.0;
+        __syncthreads();
+        // 3. X = Wrm Tinv (n x md) computed directly from the eigen-factors: X = (Wrm V) diag(tv) V^T
+        //    Y = Wrm V diag(tv) -> Ev as n x md
+        for (int idx = tid; idx < n * md; idx += nt) {
+            const int i = idx / md, k = idx - i * md;
+            double s = 0;
+            for (int j = 0; j < md; j++) s += Wk[(md + i) * q + j] * Vv[j * ldvm + k];
+            Ev[idx] = s * tv[k];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < n * md; idx += nt) {
+            const int i = idx / md, j = idx - i * md;
+            double s = 0;
+            for (int k = 0; k < md; k++) s += Ev[i * md + k] * Vv[j * ldvm + k];
+            X[idx] = s;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     double* Ap = mp.Aout;  // n x n (global, becomes the prior's A after thresholding)
     for (int idx = tid; idx < n * n; idx += nt) {
         const int i = idx / n, j = idx % n;

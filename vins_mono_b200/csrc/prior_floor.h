@@ -17,9 +17,10 @@
 
 namespace vb {
 
-// Doubles of scratch behind `work` (partial route): the LDL^T copy M (n x (n|1)), X (SE_KMAX x n), se_small_eigs' work.
+// Doubles of scratch behind `work` (partial route): the LDL^T copy M (n x (n|1)), X (SE_KMAX x n), se_small_eigs' work,
+// projections / eigenvalues / flags, the LDL^T entry table (one int per entry of the lower triangle).
 SE_HD inline int prior_floor_work(int n, int nt, int ws) {
-    return n * (n | 1) + SE_KMAX * n + se_small_work(n, SE_KMAX, nt, ws) + 4 * SE_KMAX + 8;
+    return n * (n | 1) + SE_KMAX * n + se_small_work(n, SE_KMAX, nt, ws) + 2 * SE_KMAX + 8 + (n * (n + 1) / 2 + 1) / 2;
 }
 
 // In:  Ap (n x n, row-major) = A' as assembled (not exactly symmetric), g (n) = b'.
@@ -31,21 +32,23 @@ SE_HD void prior_floor(Ctx ctx, double* Ap, double* g, double* c0, int n, double
                        double* e, double* cs, double* scal, double* tv, double* work, double* Ev, int* stats) {
     const int tid = ctx.tid(), nt = ctx.nt(), LD = ctx.lead();
     const int wid = ctx.wid(), nw = ctx.nw(), lane = ctx.lane(), ws = ctx.ws();
-    for (int idx = tid; idx < n * n; idx += nt) {
-        const int i = idx / n, j = idx - i * n;
-        V[i * ld + j] = 0.5 * (Ap[i * n + j] + Ap[j * n + i]);
-    }
-    ctx.sync();
     int k = -1;
     const int ldm = n | 1;
     double* M = work;
+    for (int idx = tid; idx < n * n; idx += nt) {  // the symmetrised A': V for the decomposition, M for the partial route
+        const int i = idx / n, j = idx - i * n;
+        const double v = 0.5 * (Ap[i * n + j] + Ap[j * n + i]);
+        V[i * ld + j] = v;
+        if (M) M[i * ldm + j] = v;
+    }
+    ctx.sync();
     double* X = work ? M + (size_t)n * ldm : nullptr;
     double* sw = work ? X + (size_t)SE_KMAX * n : nullptr;
     double* xb = work ? sw + se_small_work(n, SE_KMAX, nt, ws) : nullptr;  // x_k . b'
     double* lam = work ? xb + SE_KMAX : nullptr;
     double* fl = work ? lam + SE_KMAX : nullptr;  // [0] pivot failure, [1] corner, [2] sigma, [3..6] pivot | 1/pivot, double buffered
     if (n >= 2) se_tridiag<Ctx, SE_PER_LANE>(ctx, V, n, ld, d, e, cs, scal);
-    if (work && n >= 2) k = se_small_eigs(ctx, V, n, ld, d, e, cs, 1e-12, 4.0 * eps, SE_KMAX, lam, X, sw);
+    if (work && n >= 2) k = se_small_eigs<Ctx, SE_PER_LANE>(ctx, V, n, ld, d, e, cs, 1e-12, 4.0 * eps, SE_KMAX, lam, X, sw);
     SE_T0();
     if (k >= 0) {
         // projections of b' on the explicit vectors; sigma
@@ -64,28 +67,53 @@ SE_HD void prior_floor(Ctx ctx, double* Ap, double* g, double* c0, int n, double
         }
         ctx.sync();
         const double sigma = fl[2];
-        // M = sym(A') + sum_explicit (sigma - w_k) x_k x_k^T;  tv = g_hi
+        // A+ = sym(A') - sum_dropped w_k x_k x_k^T (final);  M = sym(A') + sum_explicit (sigma - w_k) x_k x_k^T;
+        // g <- g0, tv = g_hi, b' kept in cs[0, n) for the fall-back
         for (int idx = tid; idx < n * n; idx += nt) {
             const int i = idx / n, j = idx - i * n;
-            double v = 0.5 * (Ap[i * n + j] + Ap[j * n + i]);
-            for (int t = 0; t < k; t++) v += (sigma - lam[t]) * X[(size_t)t * n + i] * X[(size_t)t * n + j];
-            M[i * ldm + j] = v;
+            const double v = M[i * ldm + j];
+            double ap = v, mm = v;
+            for (int t = 0; t < k; t++) {
+                const double xx = X[(size_t)t * n + i] * X[(size_t)t * n + j];
+                mm += (sigma - lam[t]) * xx;
+                if (!(lam[t] > eps)) ap -= lam[t] * xx;
+            }
+            Ap[idx] = ap;
+            M[i * ldm + j] = mm;
         }
         for (int i = tid; i < n; i += nt) {
-            double v = g[i];
-            for (int t = 0; t < k; t++) v -= X[(size_t)t * n + i] * xb[t];
-            tv[i] = v;
+            const double b = g[i];
+            double hi = b, g0 = b;
+            for (int t = 0; t < k; t++) {
+                const double c = X[(size_t)t * n + i] * xb[t];
+                hi -= c;
+                if (!(lam[t] > eps)) g0 -= c;
+            }
+            cs[i] = b;
+            tv[i] = hi;
+            g[i] = g0;
         }
         ctx.sync();
         // LDL^T of [M g_hi; g_hi^T 0] without pivoting: the corner ends as -g_hi^T M^-1 g_hi.  One barrier per column; the
         // thread that finishes the next pivot publishes it and its reciprocal (double buffered) so that the division is off
-        // the other threads' path; a warp owns a row of the trailing triangle and issues all its loads before the first store.
+        // the other threads' path.
         if (tid == 0) {
             fl[3] = M[0];
             fl[4] = 1.0 / M[0];
         }
         ctx.sync();
-        constexpr int NCH = 5;  // row chunks per lane (n <= 160 on the device)
+        // Entries of the trailing triangle are dealt to the threads once, enumerated from the fixed corner (n-1, n-1)
+        // outwards (reversed row/column r' <= c', index c'(c'+1)/2 + r'): entry idx is live at column j exactly when
+        // idx < m(m+1)/2, so a thread's entries and their (row, column) never change and the last live one is the next pivot.
+        const int E = n * (n + 1) / 2;
+        int* tab = reinterpret_cast<int*>(fl + 8);  // packed row << 16 | column, one int per entry
+        for (int idx = tid; idx < E; idx += nt) {
+            int cp = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+            while (cp * (cp + 1) / 2 > idx) cp--;
+            while ((cp + 1) * (cp + 2) / 2 <= idx) cp++;
+            const int rp = idx - cp * (cp + 1) / 2;
+            tab[idx] = ((n - 1 - rp) << 16) | (n - 1 - cp);
+        }
         for (int j = 0; j < n; j++) {
             const int pb = 3 + 2 * (j & 1), nb = 3 + 2 * ((j + 1) & 1);
             const double p = fl[pb];
@@ -94,68 +122,39 @@ SE_HD void prior_floor(Ctx ctx, double* Ap, double* g, double* c0, int n, double
                 break;  // every thread reads the same p
             }
             const double ip = fl[pb + 1];
-            const int m = n - 1 - j;
+            const int m = n - 1 - j, live = m * (m + 1) / 2;
             const double zj = tv[j];
-            for (int r = wid; r < m; r += nw) {
-                double* row = M + (size_t)(j + 1 + r) * ldm;
-                const double f = row[j] * ip;
-                if (ws == 1) {
-                    for (int c = 0; c <= r; c++) row[j + 1 + c] -= f * M[(j + 1 + c) * ldm + j];
-                } else {
-                    double cv[NCH], rv[NCH];
-#pragma unroll
-                    for (int u = 0; u < NCH; u++) {
-                        const int c = lane + u * ws;
-                        const bool ok = c <= r;
-                        cv[u] = ok ? M[(j + 1 + c) * ldm + j] : 0.0;
-                        rv[u] = ok ? row[j + 1 + c] : 0.0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < NCH; u++) {
-                        const int c = lane + u * ws;
-                        if (c <= r) row[j + 1 + c] = rv[u] - f * cv[u];
-                    }
-                }
-                if (r == 0 && lane == 0) {  // the next pivot is final
-                    const double pn = row[j + 1];
-                    fl[nb] = pn;
-                    fl[nb + 1] = 1.0 / pn;
+            for (int idx = tid; idx < live; idx += nt) {
+                const int rc = tab[idx], row = rc >> 16, col = rc & 0xffff;
+                const double v = M[row * ldm + col] - M[row * ldm + j] * ip * M[col * ldm + j];
+                M[row * ldm + col] = v;
+                if (idx == live - 1) {  // (j+1, j+1): the next pivot is final
+                    fl[nb] = v;
+                    fl[nb + 1] = 1.0 / v;
                 }
             }
-            for (int r = tid; r < m; r += nt) tv[j + 1 + r] -= M[(j + 1 + r) * ldm + j] * zj * ip;
+            for (int r = tid; r < m; r += nt) tv[j + 1 + r] -= M[(j + 1 + r) * ldm + j] * ip * zj;
             if (tid == 0) fl[1] += zj * zj * ip;
             ctx.sync();
         }
         ctx.sync();
-        SE_STAMP(14);  // M, LDL^T
-        if (fl[0] != 0.0) k = -1;
+        SE_STAMP(14);  // A+, g0, M, LDL^T
+        if (fl[0] != 0.0) {  // a pivot of M was not positive: restore b', the full decomposition rewrites A+ entirely
+            for (int i = tid; i < n; i += nt) g[i] = cs[i];
+            ctx.sync();
+            k = -1;
+        }
     }
     if (k >= 0) {
-        int dropped = 0;
-        double cex = 0.0;
-        for (int t = 0; t < k; t++) {
-            if (lam[t] > eps)
-                cex += xb[t] * xb[t] / lam[t];
-            else
-                dropped++;
-        }
-        // A+ (pairs (i, j), i <= j: both mirror entries read before either is written), g0, c0
-        for (int idx = tid; idx < n * n; idx += nt) {
-            const int i = idx / n, j = idx - i * n;
-            if (i > j) continue;
-            double v = 0.5 * (Ap[i * n + j] + Ap[j * n + i]);
-            for (int t = 0; t < k; t++)
-                if (!(lam[t] > eps)) v -= lam[t] * X[(size_t)t * n + i] * X[(size_t)t * n + j];
-            Ap[i * n + j] = v;
-            Ap[j * n + i] = v;
-        }
-        for (int i = tid; i < n; i += nt) {
-            double v = g[i];
-            for (int t = 0; t < k; t++)
-                if (!(lam[t] > eps)) v -= X[(size_t)t * n + i] * xb[t];
-            g[i] = v;
-        }
         if (tid == 0) {
+            int dropped = 0;
+            double cex = 0.0;
+            for (int t = 0; t < k; t++) {
+                if (lam[t] > eps)
+                    cex += xb[t] * xb[t] / lam[t];
+                else
+                    dropped++;
+            }
             c0[0] = cex + fl[1];
             if (stats) {
                 stats[0] = k;
@@ -163,7 +162,6 @@ SE_HD void prior_floor(Ctx ctx, double* Ap, double* g, double* c0, int n, double
             }
         }
         ctx.sync();
-        SE_STAMP(15);  // A+, g0
         return;
     }
     // ---- full decomposition: A+ = V diag(w+) V^T, g0 = V 1+ V^T b', c0 = sum_kept (v_k^T b')^2 / w_k

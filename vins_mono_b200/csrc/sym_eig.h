@@ -680,7 +680,7 @@ SE_HD inline int se_small_work(int n, int kmax, int nt, int ws) {
 // up to noise) and X[j * n .. +n) = orthonormal eigenvectors of the ORIGINAL matrix for all eigenvalues below tau; or -1 when
 // there are more than kmax (<= SE_KMAX) of them or a vector failed its residual check.  V and cs[n, 3n) are left intact
 // either way (se_finish can still run).  d, e hold T afterwards; work[0] = |T| (max row sum), work[1] = tau.
-template <class Ctx>
+template <class Ctx, int SE_PER_LANE = 3>
 SE_HD int se_small_eigs(Ctx ctx, const double* V, int n, int ld, double* d, double* e, double* cs, double tau_rel,
                         double tau_min, int kmax, double* lam, double* X, double* work) {
     const int tid = ctx.tid(), nt = ctx.nt();
@@ -782,56 +782,63 @@ SE_HD int se_small_eigs(Ctx ctx, const double* V, int n, int ld, double* d, doub
             if (lhat[j] - lhat[j - 1] < sep) lhat[j] = lhat[j - 1] + sep;
     }
     ctx.sync();
-    // ---- inverse iteration: P L U = T - lhat[j] I (dlagtf), then U^-1 L^-1 P applied four times (dlagts with perturbed pivots)
+    // ---- inverse iteration: P L U = T - lhat[j] I (dlagtf), then U^-1 L^-1 P applied three times (dlagts with perturbed pivots)
     const double tiny = ulp * tnorm;
     for (int j = wid; j < k; j += nw) {
         if (lane != 0) continue;
-        double* fa = fac + (size_t)j * 5 * n;  // U diagonal
-        double* fb = fa + n;                    // U first super-diagonal
-        double* fd = fb + n;                    // U second super-diagonal
-        double* fl = fd + n;                    // multipliers
-        double* fi = fl + n;                    // 1: rows k, k+1 were interchanged
+        double* __restrict__ fa = fac + (size_t)j * 5 * n;  // reciprocal of the U diagonal
+        double* __restrict__ fb = fa + n;                    // U first super-diagonal
+        double* __restrict__ fd = fb + n;                    // U second super-diagonal
+        double* __restrict__ fl = fd + n;                    // multipliers
+        double* __restrict__ fi = fl + n;                    // 1: rows i, i+1 were interchanged
         const double sh = lhat[j];
-        for (int i = 0; i < n; i++) {
-            fa[i] = d[i] - sh;
-            fb[i] = e[i];
-            fd[i] = 0.0;
-        }
+        // row i of the partly eliminated matrix is (a, b) in columns (i, i+1), carried in registers; one reciprocal per row
+        // serves the multiplier and the back substitutions; a vanishing pivot (the shift IS an eigenvalue) becomes eps |T|
+        double a = d[0] - sh, b = e[0];
         for (int i = 0; i + 1 < n; i++) {
-            const double ci = e[i];  // sub-diagonal entry of row i + 1
-            if (fabs(fa[i]) >= fabs(ci)) {
-                const double m = fa[i] != 0.0 ? ci / fa[i] : 0.0;
+            const double ci = e[i];                  // sub-diagonal entry of row i + 1
+            const double an = d[i + 1] - sh, bn = e[i + 1];  // row i + 1: (ci, an, bn) in columns (i, i+1, i+2)
+            if (fabs(a) >= fabs(ci)) {
+                const double piv = fabs(a) < tiny ? (a < 0.0 ? -tiny : tiny) : a;
+                const double r = 1.0 / piv;
+                const double m = a != 0.0 ? ci * r : 0.0;
+                fa[i] = r;
+                fb[i] = b;
+                fd[i] = 0.0;
                 fl[i] = m;
                 fi[i] = 0.0;
-                fa[i + 1] -= m * fb[i];
+                a = an - m * b;
+                b = bn;
             } else {
-                const double m = fa[i] / ci;
+                const double r = 1.0 / ci;
+                const double m = a * r;
+                fa[i] = r;
+                fb[i] = an;
+                fd[i] = bn;
                 fl[i] = m;
                 fi[i] = 1.0;
-                fa[i] = ci;
-                const double t = fa[i + 1];
-                fa[i + 1] = fb[i] - m * t;
-                if (i + 2 < n) {
-                    fd[i] = fb[i + 1];
-                    fb[i + 1] = -m * fd[i];
-                }
-                fb[i] = t;
+                a = b - m * an;
+                b = -m * bn;
             }
         }
-        // reciprocal pivots for the back substitutions; a vanishing pivot (the shift IS an eigenvalue) is replaced by eps |T|
-        for (int i = 0; i < n; i++) {
-            double ak = fa[i];
-            if (fabs(ak) < tiny) ak = ak < 0.0 ? -tiny : tiny;
-            fa[i] = 1.0 / ak;
+        {
+            const double piv = fabs(a) < tiny ? (a < 0.0 ? -tiny : tiny) : a;
+            fa[n - 1] = 1.0 / piv;
+            fb[n - 1] = 0.0;
+            fd[n - 1] = 0.0;
         }
     }
     ctx.sync();
-    for (int it = 0; it < 4; it++) {
+    constexpr int INV_ITERS = 3;
+    for (int it = 0; it < INV_ITERS; it++) {
         for (int j = wid; j < k; j += nw) {
             if (lane != 0) continue;
-            const double* fa = fac + (size_t)j * 5 * n;
-            const double *fb = fa + n, *fd = fb + n, *fl = fd + n, *fi = fl + n;
-            double* y = X + (size_t)j * n;
+            const double* __restrict__ fa = fac + (size_t)j * 5 * n;
+            const double* __restrict__ fb = fa + n;
+            const double* __restrict__ fd = fb + n;
+            const double* __restrict__ fl = fd + n;
+            const double* __restrict__ fi = fl + n;
+            double* __restrict__ y = X + (size_t)j * n;
             if (it == 0) {  // start vector: fixed pseudo-random numbers in (-1, 1)
                 unsigned sd = 12345u + 7919u * (unsigned)j;
                 for (int i = 0; i < n; i++) {
@@ -879,7 +886,7 @@ SE_HD int se_small_eigs(Ctx ctx, const double* V, int n, int ld, double* d, doub
                 double nn = 0.0;
                 for (int i = tid; i < n; i += LD) nn += y[i] * y[i];
                 nn = ctx.lead_sum(nn);
-                if (it == 3 && !(nn > 1e-12 * nb) && tid == 0) S[5] = 1.0;  // no direction of its own left
+                if (it == INV_ITERS - 1 && !(nn > 1e-12 * nb) && tid == 0) S[5] = 1.0;  // no direction of its own left
                 const double sc = nn > 0.0 ? 1.0 / sqrt(nn) : 0.0;
                 for (int i = tid; i < n; i += LD) y[i] *= sc;
                 ctx.lead_sync();
@@ -916,13 +923,37 @@ SE_HD int se_small_eigs(Ctx ctx, const double* V, int n, int ld, double* d, doub
             if (!(rs <= lim * lim)) S[5] = 1.0;
         }
         ctx.warp_sync();
-        for (int i = 1; i < n; i++) {
-            const double r = rh[i];
-            if (r == 0.0) continue;
-            double s = 0.0;
-            for (int t = lane; t < i; t += ws) s += V[t * ld + i] * y[t];
-            s = ctx.wsum(s) * r;
-            for (int t = lane; t < i; t += ws) y[t] -= s * V[t * ld + i];
+        if (ws == 1) {
+            for (int i = 1; i < n; i++) {
+                const double r = rh[i];
+                if (r == 0.0) continue;
+                double s = 0.0;
+                for (int t = 0; t < i; t++) s += V[t * ld + i] * y[t];
+                s *= r;
+                for (int t = 0; t < i; t++) y[t] -= s * V[t * ld + i];
+            }
+        } else {  // the lane's components stay in registers: the chain per reflector is multiply-adds + one warp sum
+            double yy[SE_PER_LANE];
+#pragma unroll
+            for (int u = 0; u < SE_PER_LANE; u++) yy[u] = lane + u * ws < n ? y[lane + u * ws] : 0.0;
+            for (int i = 1; i < n; i++) {
+                const double r = rh[i];
+                if (r == 0.0) continue;
+                double vv[SE_PER_LANE];
+                double s = 0.0;
+#pragma unroll
+                for (int u = 0; u < SE_PER_LANE; u++) {
+                    const int t = lane + u * ws;
+                    vv[u] = t < i ? V[t * ld + i] : 0.0;
+                    s += vv[u] * yy[u];
+                }
+                s = ctx.wsum(s) * r;
+#pragma unroll
+                for (int u = 0; u < SE_PER_LANE; u++) yy[u] -= s * vv[u];
+            }
+#pragma unroll
+            for (int u = 0; u < SE_PER_LANE; u++)
+                if (lane + u * ws < n) y[lane + u * ws] = yy[u];
         }
     }
     ctx.sync();
