@@ -504,12 +504,13 @@ def roofline_object(kt, n_solves, n_images, units_per_launch, peak, peaks_found,
     dominant = max(kt, key=lambda k: kt[k]["total_ms"])
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(dominant, {}).get("dram_bytes_per_launch")
+        key = dominant if units_per_launch == 1 else f"{dominant}@{units_per_launch}"  # batch captures are stored as name@members
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(key, {}).get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
     dk = per_kernel[dominant]
     return {"bound": "hbm", "kernel": dominant, "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dk["frac"],
-            "traffic": traffic if units_per_launch == 1 else None,
+            "traffic": traffic,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks_found else "fallback 6650 GB/s",
             "algorithmic_bytes_per_launch": dk["algorithmic_bytes_per_launch"], "avg_launch_us": dk["avg_us"],
             "profiled_solves": n_solves, "profiled_images": n_images, "sequences_per_launch": units_per_launch,

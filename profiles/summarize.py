@@ -52,6 +52,8 @@ KEEP = [  # (column prefix in the raw page, short name)
 
 
 def short(name):
+    name = re.sub(r"^void\s+", "", name)
+    name = re.sub(r"<[^()]*>(?=\()", "", name)  # template arguments of the kernel itself
     m = re.search(r"(?:vb::)?(\w+?)(?:_kernel)?\(", name)
     return m.group(1) if m else name
 

@@ -153,7 +153,7 @@ class Estimator:
         n = self._check(self.lib.ve_get_prior(self.h, cap, _p(A), _p(b), C.byref(nb), _p(blk)))
         return A[: n * n].reshape(n, n).copy(), b[:n].copy(), [tuple(int(v) for v in blk[4 * k:4 * k + 4]) for k in range(nb.value)]
 
-    KERNELS = ["ba_linearize", "ba_schur", "ba_step", "ba_zero", "marg_build", "marg_solve", "preint_jobs", "ba_finish"]
+    KERNELS = ["ba_eval", "ba_reduce", "ba_step", "unused", "marg_build", "marg_solve", "preint_jobs", "ba_finish"]
 
     def processIMU_batch(self, dt, acc, gyr):
         dt, acc, gyr = _d(dt), _d(acc), _d(gyr)
