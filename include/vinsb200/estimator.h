@@ -139,6 +139,43 @@ int ve_debug_projection_factor(const double* params23, const double* data12, int
 int ve_debug_imu_factor(const double* noise4, double g_norm, const double* ba, const double* bg, int n, const double* dt,
                         const double* acc, const double* gyr, const double* params32, double* out_preint, double* out_factor);
 
+/* ---- Initialisation (Estimator::initialStructure, vins_estimator/src/estimator.cpp:218-471) ----------
+ * The estimator bootstraps itself from the first full window (relative pose -> global SfM -> PnP of every image ->
+ * visual-inertial alignment) unless a seed trajectory covering the window was supplied with ve_set_seed.  The stages are
+ * host code in the reference as well; the entries below run them on caller-supplied arrays WITHOUT a handle or a GPU so
+ * that they can be pinned against OpenCV / numpy twins (tests/test_host_initial.py).
+ *   ve_debug_relative_rt        solve_5pts.cpp:193-227: corres4 = n x (x0 y0 x1 y1) normalised coordinates; R9 / T3 = the
+ *                               reference's Rotation / Translation; returns 1 when inlier_cnt > 12, inliers = inlier_cnt.
+ *   ve_debug_solve_pnp          cv::solvePnP(obj, img, I, none, rvec, t, useExtrinsicGuess = 1): R9 / t3 in-out
+ *                               (world -> camera); returns 1 on success.
+ *   ve_debug_sfm_construct      GlobalSFM::construct (initial_sfm.cpp:117-312): tracks = per feature id, first window
+ *                               frame, number of consecutive observations, xy per observation; q_wxyz (4 per frame) / T
+ *                               (3 per frame) = camera-to-world poses; pt_ids / pts = sfm_tracked_points (capacity
+ *                               n_tracks); function_tolerance <= 0 selects Ceres' default 1e-6 (the bundle's stopping
+ *                               rule; tests tighten it to reach the minimum); returns 1 on success.
+ *   ve_debug_initial_structure  the whole of initialStructure up to VisualIMUAlignment.  Window headers[F]; all image
+ *                               frames (n_all stamps; per frame its feature ids ascending + xy through pts_off, and the IMU
+ *                               samples dt acc gyr (7 doubles) pre-integrated INTO that frame through imu_off, function_tolerance as above, lin6 =
+ *                               the acc / gyr sample its integration starts from); tracks as above.  Outputs: frame_R
+ *                               (9 per frame, already x RIC^T) / frame_T, x (3 per frame velocities | 2 | scale), g3 (before the
+ *                               yaw alignment), delta_bg3, info4 = l, bundle iterations, is-keyframe count, reserved;
+ *                               bundle_cost.  Returns 0 or the failing stage (1 relative pose, 2 SfM, 3 PnP, 4 alignment). */
+int ve_debug_relative_rt(const double* corres4, int n, double* R9, double* T3, int* inliers);
+int ve_debug_solve_pnp(const double* pts3, const double* pts2, int n, double* R9, double* t3);
+int ve_debug_sfm_construct(int frame_num, int l, const double* relative_R9, const double* relative_T3, int n_tracks,
+                           const int* track_ids, const int* track_start, const int* track_nobs, const double* track_xy,
+                           double function_tolerance, double* q_wxyz, double* T, int* n_pts, int* pt_ids, double* pts,
+                           int* iterations, double* final_cost);
+int ve_debug_initial_structure(int F, const double* headers, int n_all, const double* stamps, const int* pts_off,
+                               const int* pt_ids, const double* pt_xy, const int* imu_off, const double* imu7,
+                               const double* lin6, int n_tracks, const int* track_ids, const int* track_start,
+                               const int* track_nobs, const double* track_xy, const double* ric9, const double* tic3,
+                               double g_norm, double function_tolerance, double* frame_R, double* frame_T, double* x, double* g3,
+                               double* delta_bg3, int* info4, double* bundle_cost);
+/* 1 when the handle's last transition to NON_LINEAR came from its own initialisation (0: from a seed); result8 (may be
+ * NULL) = l, scale, g (3, after the yaw alignment), bundle iterations, bundle cost, failed attempts so far. */
+int ve_init_info(const ve_estimator* e, double* result8);
+
 /* Solver internals of the last solve (profiling/tests): out[0] linear-solver retries, [1] mu, [2] radius,
  * [3..10] per-phase cycle counters of the step kernel summed over the iterations, [11] cycles of the tridiagonalisation of
  * the last marginalisation's A', [12] eigenpairs its eps floor separated explicitly (-1: the full decomposition ran),

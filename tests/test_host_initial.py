@@ -1,0 +1,152 @@
+"""The product's host C++ of the one-shot initialisation (vins_mono_b200/csrc/initial.cpp) through the handle-free
+ve_debug_* entries against the OpenCV / numpy / scipy twin in oracle/initial.py, which computes every stage the way the reference
+does (cv::findFundamentalMat + cv::recoverPose, cv::solvePnP, SVD triangulation, the visual-inertial alignment).  CPU only.
+
+Stated tolerances: two-view pose 1e-9, PnP 1e-6 (OpenCV stops at FLT_EPSILON parameter change).  The vision-only bundle stops by
+Ceres' rule (relative cost decrease below function_tolerance = 1e-6), i.e. a hair before the minimum; Ceres is not available, so
+the twin solves the same problem to its minimum with scipy and the comparison is made twice: with the product's tolerance
+tightened to 1e-14 (same minimum: equal cost to 1e-9 relative, poses 2e-4 -- the valley along the weakly constrained depths is
+flat --, gyroscope bias 2e-5, scale / velocities 3e-3) and with the default (poses 1e-3 .. 2e-3, scale 2 %).  Measured: poses 3e-7 .. 6e-5,
+scale 7e-6 .. 6e-4."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+from harness import init_inputs, synth  # noqa: E402
+from vins_mono_b200 import estimator as ve  # noqa: E402
+
+cv2 = pytest.importorskip("cv2")
+import initial as oi  # noqa: E402
+
+
+def corres_between(tracks, a, b):
+    out = []
+    for _i, s, xy in tracks:
+        if s <= a and s + len(xy) - 1 >= b:
+            out.append(np.r_[xy[a - s], xy[b - s]])
+    return np.array(out)
+
+
+@pytest.mark.parametrize("seed,a", [(0, 0), (1, 2), (3, 5), (5, 0)])
+def test_relative_rt_matches_opencv(seed, a):
+    seq = synth.Sequence(seed=seed, duration=3.0)
+    _, _, tracks = init_inputs.first_window(seq)
+    c = corres_between(tracks, a, 10)
+    ok_c, R_c, T_c, cnt_c = oi.solve_relative_rt(c)
+    ok, R, T, cnt = ve.debug_relative_rt(c)
+    assert ok == ok_c and cnt == cnt_c and cnt > 12
+    assert np.abs(R - R_c).max() < 1e-9 and np.abs(T - T_c).max() < 1e-9
+    assert abs(np.linalg.det(R) - 1) < 1e-12 and abs(np.linalg.norm(T) - 1) < 1e-12
+
+
+def test_relative_rt_rejects_degenerate_input():
+    rng = np.random.default_rng(0)
+    few = rng.uniform(-0.3, 0.3, (14, 4))
+    assert ve.debug_relative_rt(few)[0] is False and oi.solve_relative_rt(few)[0] is False
+    # no motion at all (every point at the same place in both views): OpenCV 4.13 raises inside findFundamentalMat, i.e. the
+    # reference would abort; the product reports failure
+    same = np.tile(rng.uniform(-0.3, 0.3, (40, 2)), (1, 2))
+    with pytest.raises(cv2.error):
+        oi.solve_relative_rt(same)
+    assert ve.debug_relative_rt(same)[0] is False
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_solve_pnp_matches_opencv(seed):
+    rng = np.random.default_rng(seed)
+    from scipy.spatial.transform import Rotation
+    R_true = Rotation.from_rotvec(rng.normal(0, 0.3, 3)).as_matrix()
+    t_true = rng.normal(0, 0.5, 3)
+    n = 40 if seed else 12
+    Xc = np.c_[rng.uniform(-1, 1, n), rng.uniform(-0.7, 0.7, n), rng.uniform(2, 8, n)]
+    Xw = (Xc - t_true) @ R_true  # R_true^T (Xc - t)
+    uv = Xc[:, :2] / Xc[:, 2:3] + rng.normal(0, 0.3 / 460, (n, 2))
+    R0 = Rotation.from_rotvec(rng.normal(0, 0.05, 3)).as_matrix() @ R_true
+    t0 = t_true + rng.normal(0, 0.1, 3)
+    ok_c, R_c, t_c = oi.solve_pnp(Xw, uv, R0, t0)
+    ok, R, t = ve.debug_solve_pnp(Xw, uv, R0, t0)
+    assert ok and ok_c
+    assert np.abs(R - R_c).max() < 1e-6 and np.abs(t - t_c).max() < 1e-6
+    assert np.abs(R @ R.T - np.eye(3)).max() < 1e-12
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_sfm_construct_matches_twin(seed):
+    seq = synth.Sequence(seed=seed, duration=3.0)
+    _, _, tracks = init_inputs.first_window(seq)
+    ok, rel_R, rel_T, l = oi.relative_pose(tracks, 10)
+    assert ok
+    ok_c, q_c, T_c, pts_c, cost_c = oi.sfm_construct(11, l, rel_R, rel_T, tracks)
+    assert ok_c
+    for tol, pose_tol, pt_tol in ((1e-14, 2e-4, 2e-2), (0.0, 1e-3, 5e-2)):
+        out = ve.debug_sfm_construct(11, l, rel_R, rel_T, tracks, function_tolerance=tol)
+        assert out["ok"] and 1 <= out["iterations"] <= 50
+        assert set(out["points"]) == set(pts_c)
+        for i in range(11):
+            dq = min(np.abs(out["q"][i] - q_c[i]).max(), np.abs(out["q"][i] + q_c[i]).max())
+            assert dq < pose_tol and np.abs(out["T"][i] - T_c[i]).max() < pose_tol, (tol, i)
+        # the gauge: frame l at the origin, |T_last| = |relative_T| = 1
+        assert np.abs(out["T"][l]).max() == 0 and abs(np.linalg.norm(out["T"][10]) - 1) < 1e-12
+        worst = max(np.abs(out["points"][i] - pts_c[i]).max() / max(1.0, np.abs(pts_c[i]).max()) for i in pts_c)
+        assert worst < pt_tol, (tol, worst)  # poorly constrained depths move most; the poses are what the alignment consumes
+        assert out["cost"] <= cost_c * (1 + (1e-9 if tol else 1e-3)) + 1e-15
+
+
+@pytest.mark.parametrize("seed,drop", [(0, ()), (3, ()), (0, (9,)), (3, (4, 8))])
+def test_initial_structure_matches_twin(seed, drop):
+    """Whole initialStructure (up to VisualIMUAlignment) incl. frames that left the window as non-keyframes but stay in
+    all_image_frame (PnP branch, estimator.cpp:306-356)."""
+    seq = synth.Sequence(seed=seed, duration=3.0)
+    headers, frames, tracks = init_inputs.first_window(seq, drop=drop)
+    oframes = init_inputs.oracle_frames(frames)
+    ref = oi.initial_structure(oframes, headers, tracks, synth.RIC, synth.TIC, synth.G_NORM)
+    assert ref["code"] == 0 and sum(f.is_key_frame for f in oframes) == 11
+    s_c = ref["x"][-1]
+    for tol, pose_tol, bg_tol, g_tol, rel in ((1e-14, 2e-4, 2e-5, 1e-3, 3e-3), (0.0, 2e-3, 2e-5, 5e-2, 2e-2)):
+        res = ve.debug_initial_structure(headers, frames, tracks, synth.RIC, synth.TIC, synth.G_NORM, function_tolerance=tol)
+        assert res["code"] == 0 and res["l"] == ref["l"] and res["key_frames"] == 11
+        for k, f in enumerate(oframes):
+            assert np.abs(res["R"][k] - f.R).max() < pose_tol and np.abs(res["T"][k] - f.T).max() < pose_tol, (tol, k)
+        assert np.abs(res["delta_bg"] - ref["delta_bg"]).max() < bg_tol
+        assert np.abs(res["g"] - ref["g"]).max() < g_tol and abs(np.linalg.norm(res["g"]) - synth.G_NORM) < 1e-9
+        s = res["x"][-1]
+        assert s > 0 and abs(s - s_c) < rel * s_c, (tol, s, s_c)
+        assert np.abs(res["x"][:-3] - ref["x"][:-3]).max() < rel * max(1.0, np.abs(ref["x"][:-3]).max())  # body-frame velocities
+
+
+def test_initialisation_recovers_truth_without_noise():
+    """Noise-free measurements: gyroscope bias, gravity direction and metric scale come out at their true values (the scale up to
+    the accelerometer bias the linear alignment does not model)."""
+    seq = synth.Sequence(seed=0, duration=3.0, imu_noise=False)
+    headers, frames, tracks = init_inputs.first_window(seq, pixel_sigma=0.0)
+    res = ve.debug_initial_structure(headers, frames, tracks, synth.RIC, synth.TIC, synth.G_NORM)
+    assert res["code"] == 0
+    assert np.abs(res["delta_bg"] - seq.bg).max() < 2e-5
+    l = res["l"]
+    pose = [seq.pose(t) for t in headers]
+    cam = [p[0] + p[1] @ synth.TIC for p in pose]
+    true_scale = np.linalg.norm(cam[10] - cam[l])
+    assert abs(res["x"][-1] / true_scale - 1) < 0.08
+    # gravity is expressed in the camera frame of window frame l: g_c = (R_wb R_ic)^T g_w
+    g_true = (pose[l][1] @ synth.RIC).T @ np.array([0, 0, synth.G_NORM])
+    cosang = res["g"] @ g_true / (np.linalg.norm(res["g"]) * synth.G_NORM)
+    assert np.degrees(np.arccos(min(1.0, cosang))) < 1.0
+    # rotations of the window frames against ground truth (relative to frame l): exact up to the pixel quantisation of float
+    for k in range(11):
+        R_rel_true = (pose[l][1] @ synth.RIC).T @ pose[k][1]
+        assert np.abs(res["R"][k] - R_rel_true).max() < 1e-5
+
+
+def test_initial_structure_reports_missing_parallax():
+    """A hovering camera: relativePose finds no frame pair with 30 px of parallax (estimator.cpp:442-471)."""
+    seq = synth.Sequence(seed=0, duration=3.0)
+    headers, frames, tracks = init_inputs.first_window(seq)
+    still = [(i, s, np.repeat(xy[:1], len(xy), axis=0)) for i, s, xy in tracks]
+    res = ve.debug_initial_structure(headers, frames, still, synth.RIC, synth.TIC, synth.G_NORM)
+    assert res["code"] == 1

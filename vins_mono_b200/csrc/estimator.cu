@@ -28,6 +28,7 @@
 #include "ba_kernels.h"
 #include "host_math.h"
 #include "hostpool.h"
+#include "initial.h"
 #include "vinsb200/estimator.h"
 
 using hm::Mat3;
@@ -104,6 +105,13 @@ struct ve_estimator {
     int last_track_num = 0;
     std::vector<SeedRow> seeds;
     Vec3 seed_ba, seed_bg;
+    // initialisation bookkeeping while solver_flag == INITIAL (estimator.h:117-119: all_image_frame, tmp_pre_integration)
+    std::vector<vb::init::ImageFrame> all_image_frame;  // ascending stamps (std::map<double, ImageFrame> in the reference)
+    vb::init::Preint tmp_pre;
+    double initial_timestamp = 0;
+    bool self_initialised = false;
+    int init_failures = 0, init_l = -1, init_iterations = 0;
+    double init_scale = 0, init_cost = 0;
     // pre-integration slots: frame -> slot, per-slot host mirror of what the device slot was created with
     std::vector<int> slot_of;
     std::vector<bool> slot_valid;
@@ -424,6 +432,9 @@ void clear_state(ve_estimator* e) {
     e->prior_blocks.clear();
     e->feature.clear();
     e->failure_occur = false;
+    e->all_image_frame.clear();
+    e->tmp_pre.valid = false;
+    e->initial_timestamp = 0;
 }
 
 void process_imu(ve_estimator* e, double dt, const Vec3& acc, const Vec3& gyr) {
@@ -439,6 +450,7 @@ void process_imu(ve_estimator* e, double dt, const Vec3& acc, const Vec3& gyr) {
         e->acc_buf[j].push_back(acc);
         e->gyr_buf[j].push_back(gyr);
         e->sum_dt[j] += dt;
+        if (e->solver_flag == 0 && e->tmp_pre.valid) e->tmp_pre.push_back(dt, acc, gyr);  // tmp_pre_integration->push_back
         const Vec3 un_acc_0 = e->Rs[j] * (e->acc_0 - e->Bas[j]) - e->g;
         const Vec3 un_gyr = 0.5 * (e->gyr_0 + gyr) - e->Bgs[j];
         e->Rs[j] = e->Rs[j] * hm::deltaQ_R(un_gyr * dt);
@@ -474,6 +486,102 @@ bool initial_from_seed(ve_estimator* e) {
     }
     for (auto& it : e->feature) it.estimated_depth = -1;
     triangulate(e);
+    return true;
+}
+
+bool seeds_cover_window(const ve_estimator* e) {
+    for (int i = 0; i <= e->W; i++) {
+        bool found = false;
+        for (auto& c : e->seeds)
+            if (std::fabs(c.t - e->Headers[i]) < 1e-6) found = true;
+        if (!found) return false;
+    }
+    return !e->seeds.empty();
+}
+
+// Estimator::initialStructure + visualInitialAlign (estimator.cpp:218-440).  The stages up to VisualIMUAlignment live in
+// initial.cpp; this is the "change state" tail that writes the window.
+bool initial_structure(ve_estimator* e) {
+    namespace vi = vb::init;
+    const int W = e->W;
+    std::vector<vi::Track> tracks;
+    tracks.reserve(e->feature.size());
+    for (auto& it : e->feature) {
+        vi::Track t;
+        t.id = it.feature_id;
+        t.start_frame = it.start_frame;
+        for (auto& f : it.feature_per_frame) {
+            t.xy.push_back(f.point.x);
+            t.xy.push_back(f.point.y);
+        }
+        tracks.push_back(std::move(t));
+    }
+    Mat3 RIC;
+    std::memcpy(RIC.m, e->cfg.ric, sizeof(RIC.m));
+    const Vec3 TIC(e->cfg.tic[0], e->cfg.tic[1], e->cfg.tic[2]);
+    std::vector<double> headers(e->Headers.begin(), e->Headers.begin() + W + 1), x;
+    std::vector<Vec3> Bgs(e->Bgs.begin(), e->Bgs.begin() + W + 1);
+    const vi::Result res = vi::initial_structure(e->all_image_frame, headers, tracks, RIC, TIC, e->cfg.g_norm, Bgs, x);
+    e->init_l = res.l;
+    e->init_iterations = res.sfm_iterations;
+    e->init_cost = res.sfm_cost;
+    if (res.code == vi::INIT_FAIL_SFM) e->marginalization_flag = 0;  // estimator.cpp:284
+    if (res.code != vi::INIT_OK) {
+        e->init_failures++;
+        return false;
+    }
+    for (int i = 0; i <= W; i++) e->Bgs[i] = Bgs[i];
+    // visualInitialAlign: change state
+    auto frame_at = [&](double t) -> vi::ImageFrame& {
+        for (auto& f : e->all_image_frame)
+            if (f.t == t) return f;
+        return e->all_image_frame.back();
+    };
+    for (int i = 0; i <= e->frame_count; i++) {
+        vi::ImageFrame& f = frame_at(e->Headers[i]);
+        e->Ps[i] = f.T;
+        e->Rs[i] = f.R;
+        f.is_key_frame = true;
+    }
+    for (auto& it : e->feature) it.estimated_depth = -1;
+    // triangulate on the camera poses, no tic
+    const Vec3 tic_keep = e->tic;
+    e->tic = Vec3();
+    e->ric = RIC;
+    triangulate(e);
+    e->tic = tic_keep;
+    const double s = x.back();
+    for (int i = 0; i <= W; i++) {  // pre_integrations[i]->repropagate(0, Bgs[i])
+        if (!e->slot_valid[i]) continue;
+        const Vec3 la = e->lin_acc[i], lg = e->lin_gyr[i];
+        init_slot(e, i, la, lg, Vec3(), e->Bgs[i]);
+        e->sum_dt[i] = 0;
+        for (double v : e->dt_buf[i]) e->sum_dt[i] += v;
+        flush_frame(e, i);
+    }
+    for (int i = e->frame_count; i >= 0; i--) e->Ps[i] = s * e->Ps[i] - e->Rs[i] * TIC - (s * e->Ps[0] - e->Rs[0] * TIC);
+    int kv = -1;
+    for (auto& f : e->all_image_frame)
+        if (f.is_key_frame) {
+            kv++;
+            // the reference indexes the alignment vector with the key-frame counter (estimator.cpp:400-408)
+            e->Vs[kv] = f.R * Vec3(x[3 * kv], x[3 * kv + 1], x[3 * kv + 2]);
+        }
+    for (auto& it : e->feature) {
+        if (!usable(e, it)) continue;
+        it.estimated_depth *= s;
+    }
+    Mat3 R0 = vi::g2R(res.g);
+    const double yaw = hm::R2ypr(R0 * e->Rs[0]).x;
+    R0 = hm::ypr2R(Vec3(-yaw, 0, 0)) * R0;
+    e->g = R0 * res.g;
+    for (int i = 0; i <= e->frame_count; i++) {
+        e->Ps[i] = R0 * e->Ps[i];
+        e->Rs[i] = R0 * e->Rs[i];
+        e->Vs[i] = R0 * e->Vs[i];
+    }
+    e->init_scale = s;
+    e->self_initialised = true;
     return true;
 }
 
@@ -885,9 +993,14 @@ void slide_window_old(ve_estimator* e) {
 void slide_window(ve_estimator* e) {
     const int W = e->W;
     if (e->marginalization_flag == 0) {
+        const double t_0 = e->Headers[0];
         e->back_R0 = e->Rs[0];
         e->back_P0 = e->Ps[0];
         if (e->frame_count == W) {
+            // all_image_frame.erase(begin, t_0] (estimator.cpp:1034-1051)
+            e->all_image_frame.erase(std::remove_if(e->all_image_frame.begin(), e->all_image_frame.end(),
+                                                    [&](const vb::init::ImageFrame& f) { return f.t <= t_0; }),
+                                     e->all_image_frame.end());
             const int slot0 = e->slot_of[0];
             for (int i = 0; i < W; i++) {
                 std::swap(e->Rs[i], e->Rs[i + 1]);
@@ -949,11 +1062,34 @@ int prepare_frame(ve_estimator* e, int n, const int* ids, const double* xyz_uv_v
     const int W = e->W;
     bool solve = false;
     if (e->solver_flag == 0) {
+        // ImageFrame imageframe(image, stamp); imageframe.pre_integration = tmp_pre_integration; new tmp_pre_integration
+        vb::init::ImageFrame fr;
+        fr.t = stamp;
+        fr.ids.resize(n);
+        fr.xy.resize(2 * (size_t)n);
+        for (int k = 0; k < n; k++) {
+            fr.ids[k] = ids[order[k]];
+            fr.xy[2 * k] = xyz_uv_vel[7 * order[k]];
+            fr.xy[2 * k + 1] = xyz_uv_vel[7 * order[k] + 1];
+        }
+        fr.pre = e->tmp_pre;
+        e->all_image_frame.push_back(std::move(fr));
+        e->tmp_pre.start(e->acc_0, e->gyr_0, e->Bas[e->frame_count], e->Bgs[e->frame_count]);
         if (e->frame_count == W) {
-            if (initial_from_seed(e)) {
+            bool result = false;
+            if (seeds_cover_window(e)) {
+                result = initial_from_seed(e);
+                e->self_initialised = false;
+            } else if (stamp - e->initial_timestamp > 0.1) {
+                result = initial_structure(e);
+                e->initial_timestamp = stamp;
+            }
+            if (result) {
                 e->solver_flag = 1;
                 e->stage = STAGE_INIT_SOLVE;
                 solve = true;
+                e->all_image_frame.clear();  // only read while INITIAL
+                e->tmp_pre.valid = false;
             } else
                 slide_window(e);
         } else
@@ -1414,6 +1550,15 @@ int ve_get_states(const ve_estimator* e, double* out, double* td) {
     }
     if (td) *td = e->td;
     return VE_OK;
+}
+
+int ve_init_info(const ve_estimator* e, double* r) {
+    if (!e) return VE_ERR_INVALID;
+    if (r) {
+        r[0] = e->init_l; r[1] = e->init_scale; r[2] = e->g.x; r[3] = e->g.y; r[4] = e->g.z;
+        r[5] = e->init_iterations; r[6] = e->init_cost; r[7] = e->init_failures;
+    }
+    return e->self_initialised ? 1 : 0;
 }
 
 int ve_get_extrinsic(const ve_estimator* e, double* tic3, double* ric9) {

@@ -281,6 +281,11 @@ int mark_inliers(const std::vector<float>& err, double thresh, uint8_t* mask) {
 
 bool fundamental_ransac_mask(const float* m1, const float* m2, int count, double threshold, double confidence,
                              uint8_t* status) {
+    return fundamental_ransac(m1, m2, count, threshold, confidence, status, nullptr);
+}
+
+bool fundamental_ransac(const float* m1, const float* m2, int count, double threshold, double confidence, uint8_t* status,
+                        double* F) {
     std::memset(status, 0, count);
     if (count < 7) return false;
     if (threshold <= 0) threshold = 3;
@@ -289,6 +294,7 @@ bool fundamental_ransac_mask(const float* m1, const float* m2, int count, double
     if (count == 7) {
         if (seven_point(m1, m2, models) <= 0) return false;
         std::memset(status, 1, count);
+        if (F) std::memcpy(F, models, sizeof(best));
         return true;
     }
     std::vector<float> err(count);
@@ -308,12 +314,16 @@ bool fundamental_ransac_mask(const float* m1, const float* m2, int count, double
                 const int good = mark_inliers(err, threshold, mask.data());
                 if (good > std::max(best_good, 6)) {
                     std::memcpy(status, mask.data(), count);
+                    std::memcpy(best, models + 9 * k, sizeof(best));
                     best_good = good;
                     niters = updated_iterations(confidence, (double)(count - good) / count, niters);
                 }
             }
         }
-        if (best_good > 0) return true;
+        if (best_good > 0) {
+            if (F) std::memcpy(F, best, sizeof(best));
+            return true;
+        }
         std::memset(status, 0, count);
         return false;
     }
@@ -341,6 +351,7 @@ bool fundamental_ransac_mask(const float* m1, const float* m2, int count, double
     const double sigma = std::max(2.5 * 1.4826 * (1 + 5. / (count - 7)) * std::sqrt(min_median), 0.001);
     epipolar_errors(m1, m2, count, best, err.data());
     mark_inliers(err, sigma, status);
+    if (F) std::memcpy(F, best, sizeof(best));
     return true;
 }
 

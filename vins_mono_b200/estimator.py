@@ -67,6 +67,14 @@ def _bind(lib):
     lib.ve_debug_projection_factor.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
     lib.ve_debug_imu_factor.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ve_init_info.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ve_debug_relative_rt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    lib.ve_debug_solve_pnp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.ve_debug_sfm_construct.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_double] + \
+        [C.c_void_p] * 2 + \
+        [C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    lib.ve_debug_initial_structure.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_int] + [C.c_void_p] * 6 + \
+        [C.c_double, C.c_double] + [C.c_void_p] * 6 + [C.POINTER(C.c_double)]
     _bound = True
 
 
@@ -116,6 +124,13 @@ class Estimator:
         if rc < 0:
             raise RuntimeError(f"vinsb200 error {rc}: {self.lib.ve_last_error(self.h).decode()}")
         return rc
+
+    def init_info(self):
+        """How the window was initialised: own initialStructure (self_initialised) or a caller-supplied seed."""
+        r = np.zeros(8)
+        rc = self._check(self.lib.ve_init_info(self.h, _p(r)))
+        return dict(self_initialised=bool(rc), l=int(r[0]), scale=float(r[1]), g=r[2:5].copy(), bundle_iterations=int(r[5]),
+                    bundle_cost=float(r[6]), failed_attempts=int(r[7]))
 
     def clearState(self):
         self._check(self.lib.ve_clear_state(self.h))
@@ -293,3 +308,86 @@ def debug_imu_factor(ba, bg, dt, acc, gyr, params32=None, noise=(0.08, 0.004, 0.
     if prm is not None:
         out["residual"], out["jacobian_w"] = fac[:15].copy(), fac[15:].reshape(15, 30).copy()
     return out
+
+
+# ---- initialisation stages (host code, no device needed; include/vinsb200/estimator.h "Initialisation") -------------------
+def _tracks_flat(tracks):
+    ids = np.array([t[0] for t in tracks], np.int32)
+    start = np.array([t[1] for t in tracks], np.int32)
+    nobs = np.array([len(np.asarray(t[2]).reshape(-1, 2)) for t in tracks], np.int32)
+    xy = _d(np.concatenate([np.asarray(t[2], float).reshape(-1, 2) for t in tracks])) if len(tracks) else np.zeros((0, 2))
+    return ids, start, nobs, xy
+
+
+def debug_relative_rt(corres):
+    """MotionEstimator::solveRelativeRT on n x (x0 y0 x1 y1): (ok, Rotation, Translation, inlier_cnt)."""
+    lib = load_library()
+    _bind(lib)
+    c = _d(corres).reshape(-1, 4)
+    R, T, cnt = np.zeros(9), np.zeros(3), C.c_int()
+    rc = lib.ve_debug_relative_rt(_p(c), len(c), _p(R), _p(T), C.byref(cnt))
+    if rc < 0:
+        raise RuntimeError(f"ve_debug_relative_rt: {rc}")
+    return bool(rc), R.reshape(3, 3), T, cnt.value
+
+
+def debug_solve_pnp(pts3, pts2, R_initial, P_initial):
+    """cv::solvePnP(..., useExtrinsicGuess=true) from (R_initial, P_initial) (world -> camera): (ok, R, t)."""
+    lib = load_library()
+    _bind(lib)
+    p3, p2 = _d(pts3).reshape(-1, 3), _d(pts2).reshape(-1, 2)
+    R, t = _d(R_initial).reshape(9).copy(), _d(P_initial).reshape(3).copy()
+    rc = lib.ve_debug_solve_pnp(_p(p3), _p(p2), len(p2), _p(R), _p(t))
+    if rc < 0:
+        raise RuntimeError(f"ve_debug_solve_pnp: {rc}")
+    return bool(rc), R.reshape(3, 3), t
+
+
+def debug_sfm_construct(frame_num, l, relative_R, relative_T, tracks, function_tolerance=0.0):
+    """GlobalSFM::construct; tracks = [(id, start_frame, xy[nobs, 2])].  Returns dict(ok, q[F,4] wxyz, T[F,3], points{id: xyz},
+    iterations, cost)."""
+    lib = load_library()
+    _bind(lib)
+    ids, start, nobs, xy = _tracks_flat(tracks)
+    q, T = np.zeros((frame_num, 4)), np.zeros((frame_num, 3))
+    n_pts, it, cost = C.c_int(), C.c_int(), C.c_double()
+    pid, pts = np.zeros(max(len(ids), 1), np.int32), np.zeros((max(len(ids), 1), 3))
+    rR, rT = _d(relative_R).reshape(9), _d(relative_T).reshape(3)
+    rc = lib.ve_debug_sfm_construct(frame_num, l, _p(rR), _p(rT), len(ids), _p(ids), _p(start), _p(nobs), _p(xy),
+                                    float(function_tolerance), _p(q), _p(T), C.byref(n_pts), _p(pid), _p(pts), C.byref(it),
+                                    C.byref(cost))
+    if rc < 0:
+        raise RuntimeError(f"ve_debug_sfm_construct: {rc}")
+    return dict(ok=bool(rc), q=q, T=T, points={int(pid[k]): pts[k].copy() for k in range(n_pts.value)}, iterations=it.value,
+                cost=cost.value)
+
+
+def debug_initial_structure(headers, frames, tracks, ric, tic, g_norm=9.81007, function_tolerance=0.0):
+    """Estimator::initialStructure up to VisualIMUAlignment.  frames = [dict(t, ids, xy[n,2], imu[m,7] (dt acc gyr), lin[6])] for every
+    image (imu / lin of frame 0 unused); tracks = [(id, start_frame, xy[nobs,2])].  Returns dict(code, l, R[n,3,3], T[n,3], x, g,
+    delta_bg, bundle_iterations, bundle_cost, key_frames)."""
+    lib = load_library()
+    _bind(lib)
+    hd = _d(headers)
+    na = len(frames)
+    stamps = _d([f["t"] for f in frames])
+    pts_off = np.zeros(na + 1, np.int32)
+    pts_off[1:] = np.cumsum([len(f["ids"]) for f in frames])
+    pt_ids = np.ascontiguousarray(np.concatenate([np.asarray(f["ids"], np.int32) for f in frames]), np.int32)
+    pt_xy = _d(np.concatenate([np.asarray(f["xy"], float).reshape(-1, 2) for f in frames]))
+    imu_off = np.zeros(na + 1, np.int32)
+    imu_off[1:] = np.cumsum([0 if k == 0 else len(f["imu"]) for k, f in enumerate(frames)])
+    rows = [np.asarray(f["imu"], float).reshape(-1, 7) for k, f in enumerate(frames) if k > 0]
+    imu7 = _d(np.concatenate(rows)) if rows else np.zeros((0, 7))
+    lin6 = _d([np.zeros(6) if k == 0 else np.asarray(f["lin"], float) for k, f in enumerate(frames)])
+    ids, start, nobs, xy = _tracks_flat(tracks)
+    fR, fT, x = np.zeros((na, 9)), np.zeros((na, 3)), np.zeros(3 * na + 3)
+    g3, dbg, info, cost = np.zeros(3), np.zeros(3), np.zeros(4, np.int32), C.c_double()
+    rc = lib.ve_debug_initial_structure(len(hd), _p(hd), na, _p(stamps), _p(pts_off), _p(pt_ids), _p(pt_xy), _p(imu_off), _p(imu7),
+                                        _p(lin6), len(ids), _p(ids), _p(start), _p(nobs), _p(xy), _p(_d(ric).reshape(9)),
+                                        _p(_d(tic).reshape(3)), float(g_norm), float(function_tolerance), _p(fR), _p(fT), _p(x), _p(g3), _p(dbg), _p(info),
+                                        C.byref(cost))
+    if rc < 0:
+        raise RuntimeError(f"ve_debug_initial_structure: {rc}")
+    return dict(code=rc, l=int(info[0]), R=fR.reshape(na, 3, 3), T=fT, x=x, g=g3, delta_bg=dbg, bundle_iterations=int(info[1]),
+                bundle_cost=cost.value, key_frames=int(info[2]))
