@@ -38,7 +38,8 @@ typedef enum vt_status {
     VT_ERR_CAPACITY = -4    /* more features than the handle was created for */
 } vt_status;
 
-typedef enum vt_camera_model { VT_CAMERA_PINHOLE = 0 } vt_camera_model;
+/* camera_model/src/camera_models/{PinholeCamera,CataCamera,EquidistantCamera}.cc: model_type PINHOLE, MEI, KANNALA_BRANDT */
+typedef enum vt_camera_model { VT_CAMERA_PINHOLE = 0, VT_CAMERA_MEI = 1, VT_CAMERA_KANNALA_BRANDT = 2 } vt_camera_model;
 
 typedef struct vt_config {
     int rows, cols;        /* image_height, image_width */
@@ -50,9 +51,11 @@ typedef struct vt_config {
     int focal_length;      /* FOCAL_LENGTH = 460 (parameters.cpp:65) */
     double f_threshold;    /* F_threshold (:48) */
     int camera_model;      /* vt_camera_model */
-    double intrinsics[8];  /* PINHOLE: fx fy cx cy k1 k2 p1 p2 */
+    double intrinsics[8];  /* PINHOLE: fx fy cx cy k1 k2 p1 p2; MEI: gamma1 gamma2 u0 v0 k1 k2 p1 p2 (+ xi below);
+                              KANNALA_BRANDT: mu mv u0 v0 k2 k3 k4 k5 */
     const uint8_t* fisheye_mask; /* rows*cols bytes, only read when fisheye != 0 */
     int device;            /* CUDA device ordinal */
+    double xi;             /* MEI mirror parameter (mirror_parameters.xi); ignored by the other models */
 } vt_config;
 
 typedef struct vt_tracker vt_tracker;
@@ -132,6 +135,8 @@ int vt_debug_fundamental_ransac(const float* pts1, const float* pts2, int n, dou
 /* PinholeCamera::liftProjective (PinholeCamera.cc:450-510) as undistortedPoints() applies it: n pixel pairs -> n normalised
  * (x, y) pairs; intrinsics8 = fx fy cx cy k1 k2 p1 p2.  Host only. */
 int vt_debug_lift_projective(const double* intrinsics8, const double* px, int n, double* out_xy);
+/* The same for any vt_camera_model: liftProjective followed by the division by z (what undistortedPoints / rejectWithF use). */
+int vt_debug_lift_projective_model(int camera_model, const double* intrinsics8, double xi, const double* px, int n, double* out_xy);
 /* Half widths per row offset |dy| = 0..radius of the filled cv::circle that setMask() draws (feature_tracker.cpp:66): the
  * table the mask kernel rasterises discs from.  out has radius + 1 entries.  Host only. */
 int vt_debug_disc_half_widths(int radius, int* out);

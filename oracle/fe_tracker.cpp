@@ -36,6 +36,10 @@ struct orc_tracker_config {
     int fisheye;       // use fisheye_mask as the initial mask
     double f_threshold;
     double fx, fy, cx, cy, k1, k2, p1, p2;  // PINHOLE (config/euroc/euroc_config.yaml:13-22)
+    // model_type: 0 PINHOLE, 1 MEI (fx fy cx cy hold gamma1 gamma2 u0 v0; xi below), 2 KANNALA_BRANDT (fx fy cx cy hold mu mv u0 v0,
+    // k1 k2 p1 p2 hold k2 k3 k4 k5)
+    int camera_model;
+    double xi;
 };
 }
 
@@ -65,12 +69,75 @@ struct Tracker {
     // diagnostics of the last readImage
     int last_lk_in = 0, last_lk_ok = 0, last_ransac_in = 0, last_ransac_ok = 0, last_new = 0;
 
-    // PinholeCamera::liftProjective (recursive distortion model, n = 8)
+    // CameraPtr::liftProjective, returned as (x / z, y / z) like every caller uses it (feature_tracker.cpp:179-186, 268-272).
+    //   PinholeCamera.cc:450-510, CataCamera.cc:556-625 (recursive distortion model, n = 8), EquidistantCamera.cc:428-442
     void lift(double px, double py, double& X, double& Y) const {
         const double inv_K11 = 1.0 / cfg.fx, inv_K13 = -cfg.cx / cfg.fx;
         const double inv_K22 = 1.0 / cfg.fy, inv_K23 = -cfg.cy / cfg.fy;
         double mx_d = inv_K11 * px + inv_K13;
         double my_d = inv_K22 * py + inv_K23;
+        if (cfg.camera_model == 2) {
+            // backprojectSymmetric (EquidistantCamera.cc:716-818): smallest non-negative real root of
+            // theta + k2 theta^3 + k3 theta^5 + k4 theta^7 + k5 theta^9 = |p_u|.  The reference reads it off the companion
+            // matrix; this oracle brackets the first sign change and runs the Illinois false-position iteration
+            // (tests/test_host_frontend.py pins it against numpy.roots, i.e. against the companion-matrix eigenvalues).
+            const double r = std::sqrt(mx_d * mx_d + my_d * my_d);
+            const double phi = r < 1e-10 ? 0.0 : std::atan2(my_d, mx_d);
+            double kk[4] = {cfg.k1, cfg.k2, cfg.p1, cfg.p2};
+            int npow = 9;  // lowered by 2 per zero coefficient; higher terms are dropped (EquidistantCamera.cc:733-770)
+            for (double kv : kk)
+                if (kv == 0.0) npow -= 2;
+            for (int i = 0; i < 4; i++)
+                if (2 * i + 3 > npow) kk[i] = 0.0;
+            auto poly = [&](double t) {
+                double acc = 0, tp = t;
+                const double t2 = t * t;
+                acc = tp;
+                for (int i = 0; i < 4; i++) {
+                    tp *= t2;
+                    acc += kk[i] * tp;
+                }
+                return acc - r;
+            };
+            double theta = r;
+            if (r <= 1e-10)
+                theta = 0.0;
+            else if (kk[0] != 0.0 || kk[1] != 0.0 || kk[2] != 0.0 || kk[3] != 0.0) {
+                double a = 0.0, fa = -r;
+                bool found = false;
+                for (int i = 1; i <= 2400 && !found; i++) {
+                    double b = i / 300.0, fb = poly(b);
+                    if (fb >= 0.0) {
+                        found = true;
+                        int side = 0;
+                        for (int it = 0; it < 200 && fb != 0.0; it++) {
+                            const double c = (a * fb - b * fa) / (fb - fa), fc = poly(c);
+                            if (std::fabs(b - a) <= 4e-16 * std::fabs(b)) break;
+                            if (fc * fb > 0) {
+                                b = c; fb = fc;
+                                if (side == -1) fa *= 0.5;
+                                side = -1;
+                            } else if (fc * fa > 0) {
+                                a = c; fa = fc;
+                                if (side == 1) fb *= 0.5;
+                                side = 1;
+                            } else {
+                                a = b = c;
+                                break;
+                            }
+                        }
+                        theta = std::fabs(poly(a)) < std::fabs(poly(b)) ? a : b;
+                    } else {
+                        a = b;
+                        fa = fb;
+                    }
+                }
+            }
+            const double Px = std::sin(theta) * std::cos(phi), Py = std::sin(theta) * std::sin(phi), Pz = std::cos(theta);
+            X = Px / Pz;
+            Y = Py / Pz;
+            return;
+        }
         double mx_u, my_u;
         if (cfg.k1 == 0.0 && cfg.k2 == 0.0 && cfg.p1 == 0.0 && cfg.p2 == 0.0) {
             mx_u = mx_d;
@@ -92,6 +159,19 @@ struct Tracker {
                 mx_u = mx_d - dx;
                 my_u = my_d - dy;
             }
+        }
+        if (cfg.camera_model == 1) {
+            const double xi = cfg.xi;
+            double z;
+            if (xi == 1.0)
+                z = (1.0 - mx_u * mx_u - my_u * my_u) / 2.0;
+            else {
+                const double rho2_d = mx_u * mx_u + my_u * my_u;
+                z = 1.0 - xi * (rho2_d + 1.0) / (xi + std::sqrt(1.0 + (1.0 - xi * xi) * rho2_d));
+            }
+            X = mx_u / z;
+            Y = my_u / z;
+            return;
         }
         X = mx_u;
         Y = my_u;  // Z = 1

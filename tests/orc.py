@@ -22,7 +22,8 @@ class TrackerConfig(C.Structure):
     _fields_ = [("rows", C.c_int), ("cols", C.c_int), ("max_cnt", C.c_int), ("min_dist", C.c_int),
                 ("equalize", C.c_int), ("freq", C.c_int), ("focal_length", C.c_int), ("fisheye", C.c_int),
                 ("f_threshold", C.c_double), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double),
-                ("cy", C.c_double), ("k1", C.c_double), ("k2", C.c_double), ("p1", C.c_double), ("p2", C.c_double)]
+                ("cy", C.c_double), ("k1", C.c_double), ("k2", C.c_double), ("p1", C.c_double), ("p2", C.c_double),
+                ("camera_model", C.c_int), ("xi", C.c_double)]
 
 
 def lib():

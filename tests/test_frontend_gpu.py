@@ -191,11 +191,12 @@ def test_tracker_edge_cases_match_oracle(FT):
     assert seen_restart == 2 and max_id > 150
 
 
-@pytest.mark.parametrize("variant", ["fisheye_mask", "no_equalize", "small_dense", "qvga_rate20"])
+@pytest.mark.parametrize("variant", ["fisheye_mask", "no_equalize", "small_dense", "qvga_rate20", "mei_camera", "kannala_brandt_camera"])
 def test_tracker_config_variants_match_oracle(FT, variant):
     """Configurations beyond the EuRoC default (euroc_config.yaml:45-51 / parameters.cpp:37-74): FISHEYE with a circular
     mask as the initial setMask image (feature_tracker.cpp:38-41), EQUALIZE off (:87-95), other MAX_CNT / MIN_DIST, other
-    image sizes and FREQ.  20 frames each, bit-identical to the CPU oracle."""
+    image sizes and FREQ, the MEI (config/3dm) and KANNALA_BRANDT (config/cla) camera models in undistortedPoints / rejectWithF
+    (CataCamera.cc:556-625, EquidistantCamera.cc:428-442).  20 frames each, bit-identical to the CPU oracle."""
     rows, cols = 480, 752
     kw, mask = {}, None
     if variant == "fisheye_mask":
@@ -211,6 +212,12 @@ def test_tracker_config_variants_match_oracle(FT, variant):
         kw = dict(max_cnt=80, min_dist=15, freq=20)
     cfg = synth.tracker_config_dict(rows=rows, cols=cols, **{k: v for k, v in kw.items() if k in ("max_cnt", "min_dist", "freq", "equalize")})
     cfg.update({k: v for k, v in kw.items() if k == "fisheye"})
+    if variant == "mei_camera":
+        cfg.update(camera_model=1, xi=2.057, k1=7.145e-02, k2=5.059e-01, p1=4.727e-05, p2=-5.492e-04, fx=1.115e+03, fy=1.114e+03,
+                   cx=3.672e+02, cy=2.385e+02)
+    elif variant == "kannala_brandt_camera":
+        cfg.update(camera_model=2, xi=0.0, k1=-0.005740195474458931, k2=0.02878252863739417, p1=-0.04010621197185408,
+                   p2=0.02008469575876223, fx=472.2863830700696, fy=470.83759684346785, cx=368.8316828103749, cy=232.23688706965652)
     gpu = FT(fisheye_mask=mask, **cfg) if mask is not None else FT(**cfg)
     cpu = orc.OracleTracker(cfg, fisheye_mask=mask)
     tex = synth.value_noise_image(rows + 40, cols + 60, seed=31)

@@ -183,17 +183,10 @@ std::vector<int> disc_half_widths(int radius) {
     return hw;
 }
 
-// PinholeCamera::liftProjective (camera_model/src/camera_models/PinholeCamera.cc:450-510)
-void lift_projective(const vt_config& c, double px, double py, double& X, double& Y) {
-    const double fx = c.intrinsics[0], fy = c.intrinsics[1], cx = c.intrinsics[2], cy = c.intrinsics[3];
-    const double k1 = c.intrinsics[4], k2 = c.intrinsics[5], p1 = c.intrinsics[6], p2 = c.intrinsics[7];
-    const double mx_d = (1.0 / fx) * px + (-cx / fx), my_d = (1.0 / fy) * py + (-cy / fy);
-    if (k1 == 0.0 && k2 == 0.0 && p1 == 0.0 && p2 == 0.0) {
-        X = mx_d;
-        Y = my_d;
-        return;
-    }
-    double ux = mx_d, uy = my_d;
+// Recursive inverse of the radial-tangential distortion, n = 8 (PinholeCamera.cc:487-503, CataCamera.cc:596-611).
+inline void undistort_radtan(double k1, double k2, double p1, double p2, double mx_d, double my_d, double& ux, double& uy) {
+    ux = mx_d;
+    uy = my_d;
     for (int i = 0; i < 8; ++i) {
         const double x2 = ux * ux, y2 = uy * uy, xy = ux * uy, rho2 = x2 + y2;
         const double rad = k1 * rho2 + k2 * rho2 * rho2;
@@ -201,6 +194,86 @@ void lift_projective(const vt_config& c, double px, double py, double& X, double
         const double ddy = uy * rad + 2.0 * p2 * xy + p1 * (rho2 + 2.0 * y2);
         ux = mx_d - ddx;
         uy = my_d - ddy;
+    }
+}
+
+// EquidistantCamera::backprojectSymmetric (EquidistantCamera.cc:716-818): the smallest non-negative real root of
+// k5 t^9 + k4 t^7 + k3 t^5 + k2 t^3 + t - r = 0, r itself when there is none.  The reference takes it from the eigenvalues of
+// the companion matrix; here the first sign change of the polynomial on a fine grid is bracketed and polished by
+// bisection + Newton (the same root to rounding).
+double kb_theta(const double kin[4], double r) {
+    // the reference lowers the polynomial degree by 2 for EVERY zero coefficient, whichever it is, and drops the terms above
+    // the resulting degree (EquidistantCamera.cc:733-770)
+    int npow = 9;
+    for (int i = 0; i < 4; i++) npow -= kin[i] == 0.0 ? 2 : 0;
+    if (npow == 1) return r;
+    double k[4];
+    for (int i = 0; i < 4; i++) k[i] = 2 * i + 3 <= npow ? kin[i] : 0.0;
+    auto f = [&](double t) {
+        const double t2 = t * t;
+        return t * (1.0 + t2 * (k[0] + t2 * (k[1] + t2 * (k[2] + t2 * k[3])))) - r;
+    };
+    auto df = [&](double t) {
+        const double t2 = t * t;
+        return 1.0 + t2 * (3.0 * k[0] + t2 * (5.0 * k[1] + t2 * (7.0 * k[2] + t2 * 9.0 * k[3])));
+    };
+    if (r <= 1e-10) return 0.0;  // f(0) = -r: the root is within the reference's tolerance of zero
+    const double step = 1.0 / 512.0;
+    double lo = 0.0;
+    for (int i = 1; i <= 4096; i++) {  // up to theta = 8 rad, far beyond any lens
+        double hi = i * step;
+        if (f(hi) >= 0.0) {
+            for (int it = 0; it < 24; it++) {  // bisection narrows the bracket, Newton finishes
+                const double mid = 0.5 * (lo + hi);
+                if (f(mid) < 0.0) lo = mid; else hi = mid;
+            }
+            double t = 0.5 * (lo + hi);
+            for (int it = 0; it < 20; it++) {
+                const double d = df(t);
+                if (d == 0.0) break;
+                const double tn = t - f(t) / d;
+                if (!(tn >= lo && tn <= hi)) break;
+                if (tn == t) break;
+                t = tn;
+            }
+            return t;
+        }
+        lo = hi;
+    }
+    return r;
+}
+
+// CameraPtr::liftProjective followed by the division by z that every caller applies (feature_tracker.cpp:179-186, 268-272):
+//   PINHOLE  PinholeCamera.cc:450-510      intrinsics = fx fy cx cy k1 k2 p1 p2
+//   MEI      CataCamera.cc:556-625         intrinsics = gamma1 gamma2 u0 v0 k1 k2 p1 p2, cfg.xi
+//   KANNALA_BRANDT  EquidistantCamera.cc:428-442   intrinsics = mu mv u0 v0 k2 k3 k4 k5
+void lift_projective(const vt_config& c, double px, double py, double& X, double& Y) {
+    const double fx = c.intrinsics[0], fy = c.intrinsics[1], cx = c.intrinsics[2], cy = c.intrinsics[3];
+    const double k1 = c.intrinsics[4], k2 = c.intrinsics[5], p1 = c.intrinsics[6], p2 = c.intrinsics[7];
+    const double mx_d = (1.0 / fx) * px + (-cx / fx), my_d = (1.0 / fy) * py + (-cy / fy);
+    if (c.camera_model == VT_CAMERA_KANNALA_BRANDT) {
+        const double r = std::sqrt(mx_d * mx_d + my_d * my_d);
+        const double phi = r < 1e-10 ? 0.0 : std::atan2(my_d, mx_d);
+        const double theta = kb_theta(&c.intrinsics[4], r);
+        const double Px = std::sin(theta) * std::cos(phi), Py = std::sin(theta) * std::sin(phi), Pz = std::cos(theta);
+        X = Px / Pz;
+        Y = Py / Pz;
+        return;
+    }
+    double ux = mx_d, uy = my_d;
+    if (!(k1 == 0.0 && k2 == 0.0 && p1 == 0.0 && p2 == 0.0)) undistort_radtan(k1, k2, p1, p2, mx_d, my_d, ux, uy);
+    if (c.camera_model == VT_CAMERA_MEI) {
+        const double xi = c.xi;
+        double Pz;
+        if (xi == 1.0)
+            Pz = (1.0 - ux * ux - uy * uy) / 2.0;
+        else {
+            const double rho2 = ux * ux + uy * uy;
+            Pz = 1.0 - xi * (rho2 + 1.0) / (xi + std::sqrt(1.0 + (1.0 - xi * xi) * rho2));
+        }
+        X = ux / Pz;
+        Y = uy / Pz;
+        return;
     }
     X = ux;
     Y = uy;
@@ -635,7 +708,7 @@ int vt_batch_create(const vt_config* cfg, int n, vt_batch** out) {
     if (!cfg || !out || n < 1 || n > 4096) return VT_ERR_INVALID;
     *out = nullptr;
     if (cfg->rows < 32 || cfg->cols < 32 || cfg->max_cnt <= 0 || cfg->min_dist < 1 ||
-        cfg->camera_model != VT_CAMERA_PINHOLE || (cfg->fisheye && !cfg->fisheye_mask))
+        cfg->camera_model < VT_CAMERA_PINHOLE || cfg->camera_model > VT_CAMERA_KANNALA_BRANDT || (cfg->fisheye && !cfg->fisheye_mask))
         return VT_ERR_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev)
@@ -864,6 +937,17 @@ int vt_debug_fundamental_ransac(const float* pts1, const float* pts2, int n, dou
 int vt_debug_lift_projective(const double* intrinsics8, const double* px, int n, double* out_xy) {
     if (!intrinsics8 || !px || !out_xy || n < 0) return VT_ERR_INVALID;
     vt_config c{};
+    for (int i = 0; i < 8; i++) c.intrinsics[i] = intrinsics8[i];
+    for (int k = 0; k < n; k++) lift_projective(c, px[2 * k], px[2 * k + 1], out_xy[2 * k], out_xy[2 * k + 1]);
+    return VT_OK;
+}
+
+int vt_debug_lift_projective_model(int camera_model, const double* intrinsics8, double xi, const double* px, int n, double* out_xy) {
+    if (!intrinsics8 || !px || !out_xy || n < 0 || camera_model < VT_CAMERA_PINHOLE || camera_model > VT_CAMERA_KANNALA_BRANDT)
+        return VT_ERR_INVALID;
+    vt_config c{};
+    c.camera_model = camera_model;
+    c.xi = xi;
     for (int i = 0; i < 8; i++) c.intrinsics[i] = intrinsics8[i];
     for (int k = 0; k < n; k++) lift_projective(c, px[2 * k], px[2 * k + 1], out_xy[2 * k], out_xy[2 * k + 1]);
     return VT_OK;

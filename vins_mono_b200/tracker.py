@@ -17,7 +17,7 @@ class TrackerConfig(C.Structure):
     _fields_ = [("rows", C.c_int), ("cols", C.c_int), ("max_cnt", C.c_int), ("min_dist", C.c_int), ("freq", C.c_int),
                 ("equalize", C.c_int), ("fisheye", C.c_int), ("focal_length", C.c_int), ("f_threshold", C.c_double),
                 ("camera_model", C.c_int), ("intrinsics", C.c_double * 8), ("fisheye_mask", C.c_void_p),
-                ("device", C.c_int)]
+                ("device", C.c_int), ("xi", C.c_double)]
 
 
 def load_library():
@@ -64,10 +64,12 @@ def load_library():
 
 def _make_tracker_config(rows=480, cols=752, max_cnt=150, min_dist=30, freq=10, equalize=1, focal_length=460,
                          f_threshold=1.0, fx=461.6, fy=460.3, cx=363.0, cy=248.1, k1=-0.2917, k2=0.08228, p1=5.333e-05,
-                         p2=-1.578e-04, fisheye=0, fisheye_mask=None, device=0, **_ignored):
+                         p2=-1.578e-04, fisheye=0, fisheye_mask=None, device=0, camera_model=0, xi=0.0, **_ignored):
+    """camera_model 0 PINHOLE (fx fy cx cy k1 k2 p1 p2), 1 MEI (the same slots hold gamma1 gamma2 u0 v0 k1 k2 p1 p2, plus xi),
+    2 KANNALA_BRANDT (mu mv u0 v0 k2 k3 k4 k5)."""
     cfg = TrackerConfig(rows=rows, cols=cols, max_cnt=max_cnt, min_dist=min_dist, freq=freq, equalize=equalize,
-                        fisheye=fisheye, focal_length=focal_length, f_threshold=f_threshold, camera_model=0,
-                        device=device)
+                        fisheye=fisheye, focal_length=focal_length, f_threshold=f_threshold, camera_model=int(camera_model),
+                        device=device, xi=float(xi))
     cfg.intrinsics[:] = [fx, fy, cx, cy, k1, k2, p1, p2]
     mask = np.ascontiguousarray(fisheye_mask, np.uint8) if fisheye_mask is not None else None
     cfg.fisheye_mask = mask.ctypes.data if mask is not None else None
