@@ -11,8 +11,9 @@
  *                               estimator.h:47, estimator.cpp:670-1003)
  *   ve_get_states              the public state arrays Ps, Rs (as quaternions), Vs, Bas, Bgs, td   estimator.h:71-79
  *   ve_info                    solver_flag, frame_count, marginalization_flag (estimator.h:65-66) + solver summary
- *   ve_set_seed                stand-in for initialStructure() (estimator.cpp:218-362):
- *                              the first window is seeded from a caller-supplied trajectory
+ *   ve_set_seed                OPTIONAL external initialiser: a trajectory that covers the first full window replaces
+ *                              initialStructure() (estimator.cpp:218-362).  Without it the estimator initialises
+ *                              itself (section "Initialisation" below), also after a failureDetection reboot.
  *   ve_get_prior               last_marginalization_info in information form (tests)
  *
  * `image` is the feature message: n points with ids (feature_id) and 7 doubles each
