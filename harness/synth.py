@@ -259,12 +259,8 @@ def value_noise_image(rows, cols, seed):
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
 
 
-def track_messages(seq: Sequence, n_pub: int, n_points: int = 2500, max_feats: int = 150, pub_hz: float = 10.0, pixel_sigma: float = 0.3,
-                   start_id: int = 0):
-    """Feature messages (stamp, ids, xyz_uv_vel[n,7]) made directly from the scene geometry (no images), in the
-    spirit of the reference's data_generator (data_generator/src/data_generator.cpp:11-59): random landmarks on
-    the room walls, projected through the EuRoC pinhole+radtan model, at most `max_feats` per frame with stable
-    ids, pixel noise sigma `pixel_sigma`.  Back-end tests/benchmarks use this to avoid rendering."""
+def scene_landmarks(seq: Sequence, n_points: int = 2500):
+    """The random wall landmarks track_messages observes (feature id = index + start_id) and the generator state after drawing them."""
     rng = np.random.default_rng(5000 + seq.seed)
     lo, hi = seq.room_lo, seq.room_hi
     pts = []
@@ -273,7 +269,32 @@ def track_messages(seq: Sequence, n_pub: int, n_points: int = 2500, max_feats: i
         p = rng.uniform(lo, hi)
         p[ax] = lo[ax] if rng.random() < 0.5 else hi[ax]
         pts.append(p)
-    pts = np.array(pts)
+    return np.array(pts), rng
+
+
+def loop_frame_matches(seq: Sequence, t_loop: float, ids, n_points: int = 2500, pixel_sigma: float = 0.0, seed: int = 0):
+    """What pose_graph sends on /pose_graph/match_points for a loop between an old key frame at t_loop and a window frame whose
+    features are `ids`: the normalised coordinates of those landmarks in the OLD frame (those in front of it), as rows (x, y, id)
+    sorted by id (keyframe.cpp:485-520), plus the old frame's true pose (p_wb, R_wb)."""
+    pts, _ = scene_landmarks(seq, n_points)
+    p, R, *_ = seq.pose(t_loop)
+    rng = np.random.default_rng(7000 + seed)
+    rows = []
+    for i in sorted(int(k) for k in ids):
+        Pc = (R @ RIC).T @ (pts[i] - (p + R @ TIC))
+        if Pc[2] > 0.3 and abs(Pc[0] / Pc[2]) < 1.0 and abs(Pc[1] / Pc[2]) < 0.7:
+            e = rng.normal(0, pixel_sigma, 2) / 460.0 if pixel_sigma > 0 else np.zeros(2)
+            rows.append([Pc[0] / Pc[2] + e[0], Pc[1] / Pc[2] + e[1], float(i)])
+    return np.array(rows).reshape(-1, 3), p, R
+
+
+def track_messages(seq: Sequence, n_pub: int, n_points: int = 2500, max_feats: int = 150, pub_hz: float = 10.0, pixel_sigma: float = 0.3,
+                   start_id: int = 0):
+    """Feature messages (stamp, ids, xyz_uv_vel[n,7]) made directly from the scene geometry (no images), in the
+    spirit of the reference's data_generator (data_generator/src/data_generator.cpp:11-59): random landmarks on
+    the room walls, projected through the EuRoC pinhole+radtan model, at most `max_feats` per frame with stable
+    ids, pixel noise sigma `pixel_sigma`.  Back-end tests/benchmarks use this to avoid rendering."""
+    pts, rng = scene_landmarks(seq, n_points)
 
     def project(t):
         p, R, *_ = seq.pose(t)

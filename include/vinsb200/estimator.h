@@ -173,6 +173,19 @@ int ve_debug_initial_structure(int F, const double* headers, int n_all, const do
                                const int* track_nobs, const double* track_xy, const double* ric9, const double* tic3,
                                double g_norm, double function_tolerance, double* frame_R, double* frame_T, double* x, double* g3,
                                double* delta_bg3, int* info4, double* bundle_cost);
+/* ---- Relocalisation (the only coupling to pose_graph; estimator.h:36, estimator.cpp:769-801, 598-617, 1128-1146) -------------
+ *   ve_set_relo_frame       Estimator::setReloFrame(frame_stamp, frame_index, match_points, relo_t, relo_r): match_points = n x
+ *                           (x, y, feature id) as decoded from /pose_graph/match_points (estimator_node.cpp:275-290; ascending
+ *                           id), relo_r row-major.  When frame_stamp is the stamp of a window frame the NEXT solve carries
+ *                           relo_Pose as a 12th pose block with one ProjectionFactor per matched landmark anchored at or before
+ *                           that frame.  Returns 1 when the stamp was found (relocalization_info set), 0 otherwise.
+ *   ve_get_relocalization   out24 = drift_correct_r 9 (row-major) | drift_correct_t 3 | relo_relative_t 3 | relo_relative_q wxyz |
+ *                           relo_relative_yaw (degrees) | relocalization_info still pending | relo_frame_local_index |
+ *                           relocalisation factors of the last solve | solves that carried a relocalisation block. */
+int ve_set_relo_frame(ve_estimator* e, double frame_stamp, int frame_index, int n, const double* match_points, const double* relo_t,
+                      const double* relo_r);
+int ve_get_relocalization(const ve_estimator* e, double* out24);
+
 /* 1 when the handle's last transition to NON_LINEAR came from its own initialisation (0: from a seed); result8 (may be
  * NULL) = l, scale, g (3, after the yaw alignment), bundle iterations, bundle cost, failed attempts so far. */
 int ve_init_info(const ve_estimator* e, double* result8);

@@ -250,6 +250,17 @@ class Estimator {
     std::vector<SeedState> seeds;
     V3 seed_ba, seed_bg;
     CauchyLoss loss{1.0};
+    // relocalisation (estimator.h:125-138)
+    bool relocalization_info = false;
+    double relo_frame_stamp = 0;
+    int relo_frame_index = 0, relo_frame_local_index = 0;
+    std::vector<V3> match_points;  // x, y, feature id
+    std::array<double, 7> relo_Pose{};
+    M3 drift_correct_r = M3::Identity(), prev_relo_r = M3::Identity();
+    V3 drift_correct_t, prev_relo_t, relo_relative_t;
+    Quat relo_relative_q;
+    double relo_relative_yaw = 0;
+    int n_relo_factors = 0, n_relo_solves = 0;
     SolveSummary last_summary;
     int n_solves = 0, n_reboots = 0, last_landmarks = 0, last_visual = 0;
     // test hook: called with (columns, residuals) right before Solve of solve number probe_solve (-1: every solve)
@@ -297,6 +308,23 @@ class Estimator {
         last_marginalization_parameter_blocks.clear();
         f_manager.feature.clear();
         failure_occur = false;
+        relocalization_info = false;
+        drift_correct_r = M3::Identity();
+        drift_correct_t = V3();
+    }
+    // Estimator::setReloFrame (estimator.cpp:1128-1146)
+    void setReloFrame(double stamp, int index, const std::vector<V3>& pts, const V3& relo_t, const M3& relo_r) {
+        relo_frame_stamp = stamp;
+        relo_frame_index = index;
+        match_points = pts;
+        prev_relo_t = relo_t;
+        prev_relo_r = relo_r;
+        for (int i = 0; i < W; i++)
+            if (relo_frame_stamp == Headers[i]) {
+                relo_frame_local_index = i;
+                relocalization_info = true;
+                relo_Pose = para_Pose[i];
+            }
     }
     void processIMU(double dt, const V3& linear_acceleration, const V3& angular_velocity) {
         if (!first_imu) {
@@ -413,6 +441,21 @@ class Estimator {
         for (size_t i = 0; i < dep.size(); i++) dep[i] = para_Feature[i][0];
         f_manager.setDepth(dep);
         if (cfg.estimate_td) td = para_Td[0];
+        if (relocalization_info) {  // estimator.cpp:598-617
+            const M3 relo_r = rot_diff * Quat(relo_Pose[6], relo_Pose[3], relo_Pose[4], relo_Pose[5]).normalized().R();
+            const V3 relo_t = rot_diff * V3(relo_Pose[0] - para_Pose[0][0], relo_Pose[1] - para_Pose[0][1], relo_Pose[2] - para_Pose[0][2]) + origin_P0;
+            const double drift_correct_yaw = R2ypr(prev_relo_r).x - R2ypr(relo_r).x;
+            drift_correct_r = ypr2R(V3(drift_correct_yaw, 0, 0));
+            drift_correct_t = prev_relo_t - drift_correct_r * relo_t;
+            relo_relative_t = relo_r.T() * (Ps[relo_frame_local_index] - relo_t);
+            relo_relative_q = Quat::FromR(relo_r.T() * Rs[relo_frame_local_index]);
+            double a = R2ypr(Rs[relo_frame_local_index]).x - R2ypr(relo_r).x;  // Utility::normalizeAngle (degrees)
+            if (a > 180.0) a -= 360.0;
+            else if (a < -180.0) a += 360.0;
+            relo_relative_yaw = a;
+            relocalization_info = false;
+            n_relo_solves++;
+        }
     }
     bool failureDetection() {
         if (Bas[W].norm() > 2.5) return true;
@@ -465,6 +508,30 @@ class Estimator {
         }
         last_landmarks = feature_index + 1;
         last_visual = f_m_cnt;
+        n_relo_factors = 0;
+        if (relocalization_info) {  // estimator.cpp:769-801
+            problem.AddParameterBlock(relo_Pose.data(), 7, true);
+            size_t retrive_feature_index = 0;
+            int fi = -1;
+            for (auto& it : f_manager.feature) {
+                if (!f_manager.usable(it)) continue;
+                ++fi;
+                const int start = it.start_frame;
+                if (start <= relo_frame_local_index) {
+                    // (the reference walks match_points without a bound; past its end nothing can match)
+                    while (retrive_feature_index < match_points.size() && (int)match_points[retrive_feature_index].z < it.feature_id)
+                        retrive_feature_index++;
+                    if (retrive_feature_index < match_points.size() && (int)match_points[retrive_feature_index].z == it.feature_id) {
+                        const V3 pts_j(match_points[retrive_feature_index].x, match_points[retrive_feature_index].y, 1.0);
+                        const V3 pts_i = it.feature_per_frame[0].point;
+                        problem.AddResidualBlock(std::make_shared<ProjectionFactor>(pts_i, pts_j, sqrt_info_scale), &loss,
+                                                 {para_Pose[start].data(), relo_Pose.data(), para_Ex_Pose.data(), para_Feature[fi].data()});
+                        retrive_feature_index++;
+                        n_relo_factors++;
+                    }
+                }
+            }
+        }
         if (probe_cb && (probe_solve < 0 || probe_solve == n_solves)) {  // tests: hand the problem to an independent optimiser
             probe_problem = &problem;
             probe_cb(ProbeColumns(problem), ProbeResiduals(problem));
@@ -703,6 +770,32 @@ int orc_est_prior(void* h, int cap, double* A, double* b) {
     return n;
 }
 // Estimator::clearState + setParameter, as the node does on a restart message (estimator_node.cpp:186-203)
+// Estimator::setReloFrame: match_points = n x (x, y, feature id), relo_r row major
+void orc_est_set_relo_frame(void* h, double stamp, int index, int n, const double* match_points, const double* relo_t, const double* relo_r) {
+    Estimator* e = (Estimator*)h;
+    std::vector<V3> pts(n);
+    for (int i = 0; i < n; i++) pts[i] = V3(match_points[3 * i], match_points[3 * i + 1], match_points[3 * i + 2]);
+    M3 R;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) R(i, j) = relo_r[3 * i + j];
+    e->setReloFrame(stamp, index, pts, V3(relo_t[0], relo_t[1], relo_t[2]), R);
+}
+// out24: drift_correct_r 9 | drift_correct_t 3 | relo_relative_t 3 | relo_relative_q wxyz 4 | relo_relative_yaw | pending flag |
+// relo_frame_local_index | factors of the last solve | solves that carried relocalisation factors
+void orc_est_relo(void* h, double* out) {
+    Estimator* e = (Estimator*)h;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) out[3 * i + j] = e->drift_correct_r(i, j);
+    out[9] = e->drift_correct_t.x; out[10] = e->drift_correct_t.y; out[11] = e->drift_correct_t.z;
+    out[12] = e->relo_relative_t.x; out[13] = e->relo_relative_t.y; out[14] = e->relo_relative_t.z;
+    out[15] = e->relo_relative_q.w; out[16] = e->relo_relative_q.x; out[17] = e->relo_relative_q.y; out[18] = e->relo_relative_q.z;
+    out[19] = e->relo_relative_yaw;
+    out[20] = e->relocalization_info ? 1.0 : 0.0;
+    out[21] = e->relo_frame_local_index;
+    out[22] = e->n_relo_factors;
+    out[23] = e->n_relo_solves;
+}
+
 void orc_est_clear_state(void* h) {
     Estimator* e = (Estimator*)h;
     e->clearState();

@@ -288,6 +288,18 @@ class OracleEstimator:
     def clearState(self):
         lib().orc_est_clear_state(self.h)
 
+    def setReloFrame(self, stamp, index, match_points, relo_t, relo_r):
+        """Estimator::setReloFrame (estimator.cpp:1128-1146); match_points = n x (x, y, feature id)."""
+        mp = _d(match_points).reshape(-1, 3)
+        lib().orc_est_set_relo_frame(self.h, C.c_double(stamp), int(index), len(mp), P(mp, f64p), P(_d(relo_t), f64p), P(_d(relo_r).reshape(9), f64p))
+
+    def relo(self):
+        o = np.zeros(24)
+        lib().orc_est_relo(self.h, P(o, f64p))
+        return dict(drift_correct_r=o[0:9].reshape(3, 3).copy(), drift_correct_t=o[9:12].copy(), relo_relative_t=o[12:15].copy(),
+                    relo_relative_q=o[15:19].copy(), relo_relative_yaw=float(o[19]), pending=bool(o[20]), local_index=int(o[21]),
+                    factors=int(o[22]), solves=int(o[23]))
+
     def processIMU(self, dt, acc, gyr):
         lib().orc_est_process_imu(self.h, C.c_double(dt), P(_d(acc), f64p), P(_d(gyr), f64p))
 

@@ -63,19 +63,28 @@ __device__ __forceinline__ int hii_index(int i, int j) { return i * 6 - i * (i -
 
 // One landmark: lanes = its observations.  l_slot: record index of the landmark (== l for the solve; the marginalisation
 // evaluates a subset and keeps the same indices).
+// A relocalisation match (estimator.cpp:777-797) is the landmark's last observation row: a plain ProjectionFactor between the
+// anchor pose and relo_Pose (no velocity / time-offset terms), evaluated by the last lane; the anchor-side sums below take it in
+// like any other observation.  with_relo = false (the marginalisation, which never contains these factors) leaves the row out.
 template <bool EX, bool TD>
-__device__ __forceinline__ void lin_visual(const BaProblem& p, const BaStates& x, const BaAccum& a, int oj, int lw, int l, int lane) {
+__device__ __forceinline__ void lin_visual(const BaProblem& p, const BaStates& x, const BaAccum& a, int oj, int lw, int l, int lane,
+                                           bool with_relo = true) {
     const BaDims& d = p.dims;
-    const int s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0;
+    const int s0 = p.lm_start[l], nrows = p.lm_start[l + 1] - s0;
+    const int rl = d.col_relo >= 0 ? p.lm_relo[l] : 0;
+    const int nobs = nrows - (with_relo ? 0 : rl);
     const int fi = p.lm_anchor[l];
     const bool has = lane < nobs;
     VisualEval e;
     if (has) {
         const int o = s0 + lane;
-        const int fj = p.ob_frame[o];
-        eval_visual<EX, TD>(d, x.pose + 7 * fi, x.pose + 7 * fj, x.ex, x.lam[l], d.est_td ? x.td[0] : 0.0, p.lm_pts[2 * l], p.lm_pts[2 * l + 1],
-                            p.ob_pts[2 * o], p.ob_pts[2 * o + 1], p.lm_vel[2 * l], p.lm_vel[2 * l + 1], p.ob_vel[2 * o], p.ob_vel[2 * o + 1],
-                            p.lm_td[l], p.ob_td[o], p.lm_row[l], p.ob_row[o], true, true, e);
+        const bool is_relo = rl != 0 && lane == nrows - 1;
+        const double* pose_j = is_relo ? x.relo : x.pose + 7 * p.ob_frame[o];
+        const double vs = is_relo ? 0.0 : 1.0;  // zero velocities: ProjectionTdFactor degenerates to ProjectionFactor
+        eval_visual<EX, TD>(d, x.pose + 7 * fi, pose_j, x.ex, x.lam[l], d.est_td ? x.td[0] : 0.0, p.lm_pts[2 * l], p.lm_pts[2 * l + 1],
+                            p.ob_pts[2 * o], p.ob_pts[2 * o + 1], vs * p.lm_vel[2 * l], vs * p.lm_vel[2 * l + 1], vs * p.ob_vel[2 * o],
+                            vs * p.ob_vel[2 * o + 1], p.lm_td[l], p.ob_td[o], is_relo ? d.half_row : p.lm_row[l],
+                            is_relo ? d.half_row : p.ob_row[o], true, true, e);
         double* rec = a.obsJ + (size_t)o * oj;
 #pragma unroll
         for (int k = 0; k < 6; k++) {
@@ -324,7 +333,7 @@ __device__ __forceinline__ double lm_inv_lambda(const BaProblem& p, const BaAccu
 }
 
 struct ColInfo {  // a camera-side column: which parameter block it belongs to
-    int type;     // 0 pose, 1 speed-bias, 2 ex, 3 td
+    int type;     // 0 pose, 1 speed-bias, 2 ex, 3 td, 4 relocalisation pose
     int frame, i;
 };
 __device__ __forceinline__ ColInfo col_info(const BaDims& d, int c) {
@@ -337,6 +346,10 @@ __device__ __forceinline__ ColInfo col_info(const BaDims& d, int c) {
         ci.type = 1;
         ci.frame = (c - d.col_sb) / 9;
         ci.i = c - d.col_sb - 9 * ci.frame;
+    } else if (d.col_relo >= 0 && c >= d.col_relo) {
+        ci.type = 4;
+        ci.frame = 0;
+        ci.i = c - d.col_relo;
     } else if (d.col_ex >= 0 && c < d.col_ex + 6) {
         ci.type = 2;
         ci.frame = 0;
@@ -411,17 +424,21 @@ __device__ __forceinline__ double prior_entry(const BaPrior& pr, const int* pinv
     return (aa >= 0 && bb >= 0) ? pr.A[(size_t)aa * pr.n + bb] : 0.0;
 }
 
-// "Pose-type" blocks: the parameter blocks visual factors touch.  T < F: pose of frame T; then [ex] [td].
+// "Pose-type" blocks: the parameter blocks visual factors touch.  T < F: pose of frame T; then [ex] [td] [relo], in this order.
 struct VBlock {
-    int type;  // 0 pose, 2 ex, 3 td
+    int type;  // 0 pose, 2 ex, 3 td, 4 relocalisation pose
     int frame, col, dim;
 };
-__device__ __forceinline__ int num_vblocks(const BaDims& d) { return d.W + 1 + (d.col_ex >= 0 ? 1 : 0) + (d.col_td >= 0 ? 1 : 0); }
+__device__ __forceinline__ int num_vblocks(const BaDims& d) {
+    return d.W + 1 + (d.col_ex >= 0 ? 1 : 0) + (d.col_td >= 0 ? 1 : 0) + (d.col_relo >= 0 ? 1 : 0);
+}
 __device__ __forceinline__ VBlock vblock(const BaDims& d, int T) {
     const int F = d.W + 1;
     VBlock b;
     if (T < F) {
         b.type = 0; b.frame = T; b.col = 6 * T; b.dim = 6;
+    } else if (d.col_relo >= 0 && T == num_vblocks(d) - 1) {
+        b.type = 4; b.frame = 0; b.col = d.col_relo; b.dim = 6;
     } else if (d.col_ex >= 0 && T == F) {
         b.type = 2; b.frame = 0; b.col = d.col_ex; b.dim = 6;
     } else {
@@ -431,16 +448,25 @@ __device__ __forceinline__ VBlock vblock(const BaDims& d, int T) {
 }
 
 // w_l restricted to block B, component i: J_B^T J_lambda summed over the landmark's observations.
-__device__ __forceinline__ double lm_w(const BaAccum& a, int oj, const double* lw_rec, const VBlock& B, int i, int anchor, int s0) {
+// nobs = observations in window frames (the track); a relocalisation match, when the landmark has one, is row s0 + nobs.
+__device__ __forceinline__ double lm_w(const BaAccum& a, int oj, const double* lw_rec, const VBlock& B, int i, int anchor, int s0, int nobs) {
     if (B.type == 0) return B.frame == anchor ? lw_rec[LW_WI + i] : a.obsJ[(size_t)(s0 + B.frame - anchor - 1) * oj + OJ_WJ + i];
     if (B.type == 2) return lw_rec[LW_WE + i];
+    if (B.type == 4) return a.obsJ[(size_t)(s0 + nobs) * oj + OJ_WJ + i];
     return lw_rec[LW_WT];
 }
 
 // Visual J^T J entry (i, j) of block pair (A, B), A <= B in block order, contributed by landmark l (anchor, s0, nobs known to
 // cover both blocks).
 __device__ __forceinline__ double vis_entry(const BaAccum& a, int oj, const double* lw_rec, const VBlock& A, const VBlock& B, int i, int j,
-                                            int anchor, int s0) {
+                                            int anchor, int s0, int nobs) {
+    if (B.type == 4) {  // relocalisation pose (always the last block): only the match's own factor links it to anything
+        const double* o = a.obsJ + (size_t)(s0 + nobs) * oj;
+        if (A.type == 0) return A.frame == anchor ? o[OJ_JI + i] * o[OJ_JJ + j] + o[OJ_JI + 6 + i] * o[OJ_JJ + 6 + j] : 0.0;
+        if (A.type == 2) return o[OJ_JEX + i] * o[OJ_JJ + j] + o[OJ_JEX + 6 + i] * o[OJ_JJ + 6 + j];
+        if (A.type == 3) return 0.0;  // a plain ProjectionFactor has no time-offset Jacobian
+        return o[OJ_JJ + i] * o[OJ_JJ + j] + o[OJ_JJ + 6 + i] * o[OJ_JJ + 6 + j];
+    }
     if (A.type == 0 && B.type == 0) {
         if (A.frame == B.frame) {
             if (A.frame == anchor) return lw_rec[LW_HII + (i <= j ? hii_index(i, j) : hii_index(j, i))];
@@ -466,7 +492,11 @@ __device__ __forceinline__ double vis_entry(const BaAccum& a, int oj, const doub
     return lw_rec[LW_HTT];
 }
 // Visual gradient component i of block A from landmark l.
-__device__ __forceinline__ double vis_grad(const BaAccum& a, int oj, const double* lw_rec, const VBlock& A, int i, int anchor, int s0) {
+__device__ __forceinline__ double vis_grad(const BaAccum& a, int oj, const double* lw_rec, const VBlock& A, int i, int anchor, int s0, int nobs) {
+    if (A.type == 4) {
+        const double* o = a.obsJ + (size_t)(s0 + nobs) * oj;
+        return o[OJ_JJ + i] * o[OJ_R] + o[OJ_JJ + 6 + i] * o[OJ_R + 1];
+    }
     if (A.type == 0) {
         if (A.frame == anchor) return lw_rec[LW_GI + i];
         const double* o = a.obsJ + (size_t)(s0 + A.frame - anchor - 1) * oj;
@@ -475,7 +505,8 @@ __device__ __forceinline__ double vis_grad(const BaAccum& a, int oj, const doubl
     if (A.type == 2) return lw_rec[LW_GE + i];
     return lw_rec[LW_GT];
 }
-__device__ __forceinline__ bool lm_covers(const VBlock& B, int anchor, int nobs) {
+__device__ __forceinline__ bool lm_covers(const VBlock& B, int anchor, int nobs, int rl) {
+    if (B.type == 4) return rl != 0;
     return B.type != 0 || (anchor <= B.frame && B.frame <= anchor + nobs);
 }
 
@@ -501,6 +532,7 @@ __global__ void __launch_bounds__(RED_THREADS, 3) ba_reduce_kernel(const BaSeq* 
     __shared__ BaProblem sp;
     __shared__ int pinv[RED_MAXD];
     __shared__ short s_an[RED_SLAB], s_nobs[RED_SLAB];
+    __shared__ unsigned char s_rl[RED_SLAB];
     __shared__ int s_s0[RED_SLAB];
     __shared__ double s_inv[RED_SLAB];
     __shared__ double part[4][RED_SLICES][36];
@@ -539,8 +571,10 @@ __global__ void __launch_bounds__(RED_THREADS, 3) ba_reduce_kernel(const BaSeq* 
             for (int k = tid; k < nl; k += RED_THREADS) {
                 const int l = l0 + k, s0 = p.lm_start[l];
                 const int an = p.lm_anchor[l];
+                const int rl = d.col_relo >= 0 ? p.lm_relo[l] : 0;
                 s_an[k] = (short)an;
-                s_nobs[k] = (short)(p.lm_start[l + 1] - s0);
+                s_nobs[k] = (short)(p.lm_start[l + 1] - s0 - rl);  // the track; a relocalisation match is the row behind it
+                s_rl[k] = (unsigned char)rl;
                 s_s0[k] = s0;
                 s_inv[k] = lm_inv_lambda(p, a, l, mu, first);
                 if (k > 0 && p.lm_anchor[l - 1] > an) unsorted = 1;
@@ -614,17 +648,17 @@ __global__ void __launch_bounds__(RED_THREADS, 3) ba_reduce_kernel(const BaSeq* 
             } else if (worker || gworker) {
 #pragma unroll 4
                 for (int k = slice; k < nl; k += RED_SLICES) {
-                    const int an = s_an[k], nobs = s_nobs[k], s0 = s_s0[k];
-                    if (!lm_covers(A, an, nobs) || !lm_covers(B, an, nobs)) continue;
+                    const int an = s_an[k], nobs = s_nobs[k], s0 = s_s0[k], rl = s_rl[k];
+                    if (!lm_covers(A, an, nobs, rl) || !lm_covers(B, an, nobs, rl)) continue;
                     const double* rec = a.lmW + (size_t)(l0 + k) * lw;
                     const double inv = s_inv[k];
                     if (worker) {
-                        h += vis_entry(a, oj, rec, A, B, i, j, an, s0);
-                        E += lm_w(a, oj, rec, A, i, an, s0) * inv * lm_w(a, oj, rec, B, j, an, s0);
+                        h += vis_entry(a, oj, rec, A, B, i, j, an, s0, nobs);
+                        E += lm_w(a, oj, rec, A, i, an, s0, nobs) * inv * lm_w(a, oj, rec, B, j, an, s0, nobs);
                     }
                     if (gworker) {
-                        gvis += vis_grad(a, oj, rec, A, e, an, s0);
-                        gE += lm_w(a, oj, rec, A, e, an, s0) * inv * rec[LW_GL];
+                        gvis += vis_grad(a, oj, rec, A, e, an, s0, nobs);
+                        gE += lm_w(a, oj, rec, A, e, an, s0, nobs) * inv * rec[LW_GL];
                     }
                 }
             }
@@ -689,7 +723,8 @@ __global__ void __launch_bounds__(RED_THREADS, 3) ba_reduce_kernel(const BaSeq* 
 // sum over the camera-side columns a landmark touches of w_l[c] v[c], by one warp (fixed lane assignment + shuffle tree)
 __device__ __forceinline__ double lm_row_dot(const BaProblem& p, const BaAccum& a, int l, const double* v, int lane) {
     const BaDims& d = p.dims;
-    const int an = p.lm_anchor[l], s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0;
+    const int rl = d.col_relo >= 0 ? p.lm_relo[l] : 0;
+    const int an = p.lm_anchor[l], s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0 - rl;
     const double* rec = a.lmW + (size_t)l * d.lw;
     double s = 0;
     for (int idx = lane; idx < 6 * (nobs + 1); idx += 32) {
@@ -697,6 +732,7 @@ __device__ __forceinline__ double lm_row_dot(const BaProblem& p, const BaAccum& 
         const double w = t == 0 ? rec[LW_WI + i] : a.obsJ[(size_t)(s0 + t - 1) * d.oj + OJ_WJ + i];
         s += w * v[6 * (an + t) + i];
     }
+    if (rl && lane >= 8 && lane < 14) s += a.obsJ[(size_t)(s0 + nobs) * d.oj + OJ_WJ + lane - 8] * v[d.col_relo + lane - 8];
     if (d.col_ex >= 0 && lane < 6) s += rec[LW_WE + lane] * v[d.col_ex + lane];
     if (d.col_td >= 0 && lane == 6) s += rec[LW_WT] * v[d.col_td];
     return warp_sum_d(s);
@@ -707,13 +743,15 @@ __device__ __forceinline__ double lm_row_dot8(const BaProblem& p, const BaAccum&
     const BaDims& d = p.dims;
     double s = 0;
     if (l < L) {
-        const int an = p.lm_anchor[l], s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0;
+        const int rl = d.col_relo >= 0 ? p.lm_relo[l] : 0;
+        const int an = p.lm_anchor[l], s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0 - rl;
         const double* rec = a.lmW + (size_t)l * d.lw;
         for (int idx = gl; idx < 6 * (nobs + 1); idx += 8) {
             const int t = idx / 6, i = idx - 6 * t;
             const double w = t == 0 ? rec[LW_WI + i] : a.obsJ[(size_t)(s0 + t - 1) * d.oj + OJ_WJ + i];
             s += w * v[6 * (an + t) + i];
         }
+        if (rl && gl < 6) s += a.obsJ[(size_t)(s0 + nobs) * d.oj + OJ_WJ + gl] * v[d.col_relo + gl];
         if (d.col_ex >= 0 && gl < 6) s += rec[LW_WE + gl] * v[d.col_ex + gl];
         if (d.col_td >= 0 && gl == 6) s += rec[LW_WT] * v[d.col_td];
     }

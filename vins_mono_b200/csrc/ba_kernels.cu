@@ -584,12 +584,13 @@ __device__ void reduce_single_cta(const BaProblem& p, const BaAccum& a, double m
         if (t >= A.dim * B.dim || (TA == TB && i > j)) continue;
         double E = 0.0, gE = 0.0;
         for (int l = 0; l < L; l++) {
-            const int an = p.lm_anchor[l], s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0;
-            if (!lm_covers(A, an, nobs) || !lm_covers(B, an, nobs)) continue;
+            const int rl = d.col_relo >= 0 ? p.lm_relo[l] : 0;
+            const int an = p.lm_anchor[l], s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0 - rl;
+            if (!lm_covers(A, an, nobs, rl) || !lm_covers(B, an, nobs, rl)) continue;
             const double* rec = a.lmW + (size_t)l * d.lw;
             const double inv = lm_inv_lambda(p, a, l, mu, first);
-            const double wa = lm_w(a, d.oj, rec, A, i, an, s0);
-            E += wa * inv * lm_w(a, d.oj, rec, B, j, an, s0);
+            const double wa = lm_w(a, d.oj, rec, A, i, an, s0, nobs);
+            E += wa * inv * lm_w(a, d.oj, rec, B, j, an, s0, nobs);
             if (TA == TB && i == j) gE += wa * inv * rec[LW_GL];
         }
         const int r = A.col + i, c = B.col + j;
@@ -899,6 +900,16 @@ __global__ void __launch_bounds__(512) ba_step_kernel(const BaSeq* __restrict__ 
         } else
             xn.td[0] = xc.td[0];
     }
+    if (tid == 32 && d.col_relo >= 0) {  // relo_Pose: one more PoseLocalParameterization block
+        double out[7];
+        pose_plus(xc.relo, delta + d.col_relo, out);
+        for (int q = 0; q < 7; q++) {
+            const double o = xc.relo[q];
+            xn.relo[q] = out[q];
+            xs += o * o;
+            ss += (o - out[q]) * (o - out[q]);
+        }
+    }
     for (int l = tid; l < L; l += nt) {
         const double o = xc.lam[l], nv = o + delta[D + l];
         xn.lam[l] = nv;
@@ -957,7 +968,7 @@ __global__ void __launch_bounds__(32 * LIN_WARPS) marg_eval_kernel(const BaSeq* 
     const int blk = blockIdx.x;
     if (blk < nb_vis) {
         const int li = blk * LIN_WARPS + wid;
-        if (li < n_lm) lin_visual<true, TD>(p, x, a, MARG_OJ, MARG_LW, q.mp.lms[li], lane);
+        if (li < n_lm) lin_visual<true, TD>(p, x, a, MARG_OJ, MARG_LW, q.mp.lms[li], lane, false);
     } else if (blk == nb_vis) {
         if (q.mp.use_imu) lin_imu(p, x, a, 0, sJraw, srr);
     } else {
@@ -1017,7 +1028,8 @@ __global__ void __launch_bounds__(128) marg_gather_kernel(const BaSeq* __restric
         const int li = (blk - dense_ctas) * (nt / 32) + (tid >> 5), lane = tid & 31;
         if (li >= nl) return;
         const int l = mp.lms[li], cl = mp.col_lm[li];
-        const int an = p.lm_anchor[l], s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0;
+        // (a relocalisation match behind the track is not part of the marginalisation)
+        const int an = p.lm_anchor[l], s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0 - (d.col_relo >= 0 ? p.lm_relo[l] : 0);
         const double* rec = a.lmW + (size_t)l * MARG_LW;
         for (int idx = lane; idx < 6 * (nobs + 1); idx += 32) {
             const int t = idx / 6, i = idx - 6 * t;
@@ -1068,11 +1080,11 @@ __global__ void __launch_bounds__(128) marg_gather_kernel(const BaSeq* __restric
             const bool swap = (VA.type > VB.type) || (VA.type == 0 && VB.type == 0 && VA.frame > VB.frame);
             for (int li = 0; li < nl; li++) {
                 const int l = mp.lms[li];
-                const int an = p.lm_anchor[l], s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0;
-                if (!lm_covers(VA, an, nobs) || !lm_covers(VB, an, nobs)) continue;
+                const int an = p.lm_anchor[l], s0 = p.lm_start[l], nobs = p.lm_start[l + 1] - s0 - (d.col_relo >= 0 ? p.lm_relo[l] : 0);
+                if (!lm_covers(VA, an, nobs, 0) || !lm_covers(VB, an, nobs, 0)) continue;
                 const double* rec = a.lmW + (size_t)l * MARG_LW;
-                h += swap ? vis_entry(a, MARG_OJ, rec, VB, VA, B.i, A.i, an, s0) : vis_entry(a, MARG_OJ, rec, VA, VB, A.i, B.i, an, s0);
-                if (ra == cb) g += vis_grad(a, MARG_OJ, rec, VA, A.i, an, s0);
+                h += swap ? vis_entry(a, MARG_OJ, rec, VB, VA, B.i, A.i, an, s0, nobs) : vis_entry(a, MARG_OJ, rec, VA, VB, A.i, B.i, an, s0, nobs);
+                if (ra == cb) g += vis_grad(a, MARG_OJ, rec, VA, A.i, an, s0, nobs);
             }
         }
         const int fa = mfull[ra], fb = mfull[cb];
@@ -1458,6 +1470,14 @@ __global__ void __launch_bounds__(128) ba_finish_kernel(BaSeq* __restrict__ seqs
         xd.ex[3] = qq.x; xd.ex[4] = qq.y; xd.ex[5] = qq.z; xd.ex[6] = qq.w;
         xd.td[0] = xe[7];
     }
+    if (tid == nt - 2 && p.dims.col_relo >= 0) {  // relo_r / relo_t of double2vector (estimator.cpp:598-605)
+        const double* rp = xs.relo;
+        const M3d Rr = mmul(rd, qR(qnormalized(q_from_param(rp))));
+        const V3d Pr = mv(rd, mk(rp[0] - sin_[0], rp[1] - sin_[1], rp[2] - sin_[2])) + mk(fp.origin_P0[0], fp.origin_P0[1], fp.origin_P0[2]);
+        double* o = of + 21 * F + 13 + L;
+        for (int k = 0; k < 9; k++) o[k] = Rr.m[k];
+        o[9] = Pr.x; o[10] = Pr.y; o[11] = Pr.z;
+    }
     double* od = of + 21 * F + 13;
     for (int l = tid; l < L; l += nt) {  // FeatureManager::setDepth, then getDepthVector
         const double dep = 1.0 / xs.lam[l];
@@ -1593,7 +1613,8 @@ void launch_ba_solve(BaSeq* seqs, const BatchShape& sh, cudaStream_t s, int* lau
     dmax.L = sh.max_L;
     dmax.W = sh.W;
     const int eval_grid = ba_eval_grid(dmax);
-    const int NV = sh.W + 1 + (sh.est_ex ? 1 : 0) + (sh.est_td ? 1 : 0), n_pairs = NV * (NV + 1) / 2;
+    // pose-type blocks incl. the slot of a relocalisation pose (CTAs of pairs a member does not have return at once)
+    const int NV = sh.W + 1 + (sh.est_ex ? 1 : 0) + (sh.est_td ? 1 : 0) + 1, n_pairs = NV * (NV + 1) / 2;
     const int generic = (sh.D * (sh.D + 1) / 2 + 4 * RED_THREADS - 1) / (4 * RED_THREADS);
     const size_t panel_bytes = sizeof(double) * CHOL_NB * CHOL_PS;
     const size_t chol_bytes = sizeof(double) * (size_t)(sh.D + 1) * (sh.D + 2) / 2 + panel_bytes;

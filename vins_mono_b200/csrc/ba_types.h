@@ -26,14 +26,14 @@ struct PreInt {  // IntegrationBase (integration_base.h:189-209) + cached sqrt_i
 
 struct BaDims {
     int W;        // WINDOW_SIZE; frames 0..W
-    int D;        // reduced (camera-side) dimension: 6(W+1) + 9(W+1) [+6] [+1]
+    int D;        // reduced (camera-side) dimension: 6(W+1) + 9(W+1) [+6 ex] [+1 td] [+6 relo]
     int L;        // landmarks in this problem
     int M;        // non-anchor observations (= visual residual blocks)
     int est_ex, est_td;
     int col_sb;   // first speed-bias column = 6(W+1)
     int col_ex;   // -1 when the extrinsic is constant
     int col_td;   // -1 when td is not estimated
-    int pad;
+    int col_relo; // first column of the relocalisation pose block (relo_Pose, estimator.cpp:769-801), -1 without one
     int oj, lw;   // strides (doubles) of the per-observation / per-landmark linearisation records (BaAccum)
     double sqrt_info_vis;  // FOCAL_LENGTH / 1.5
     double tr_over_row;    // TR / ROW
@@ -47,6 +47,7 @@ struct BaStates {  // one point x: Ceres parameter layouts
     double* ex;    // 7
     double* td;    // 1
     double* lam;   // L inverse depths
+    double* relo;  // 7: relo_Pose (estimator.h:131), behind the inverse depths; only touched when dims.col_relo >= 0
 };
 
 // One linearisation point, factor by factor (nothing is accumulated with atomics: the normal equations are gathered
@@ -111,7 +112,8 @@ struct BaProblem {
     const double* lm_vel;     // L x 2
     const double* lm_td;      // L
     const double* lm_row;     // L: raw v pixel coordinate
-    const int* ob_frame;      // M
+    const int* ob_frame;      // M (-1 for a relocalisation match: its "frame j" is relo_Pose)
+    const int* lm_relo;       // L: 1 when the landmark's LAST observation row is its relocalisation match (read when col_relo >= 0)
     const double* ob_pts;     // M x 2
     const double* ob_vel;     // M x 2
     const double* ob_td;      // M
@@ -163,7 +165,8 @@ struct FinishPlan {
     double origin_ypr[3];  // R2ypr(Rs[0]) before the solve (degrees), or of last_R0 after a detected failure
     double origin_P0[3];
     double Rs0[9];         // Rs[0] before the solve (Euler-singularity fallback)
-    double* out;           // member's output block: SolverState | (W+1) x 21 (P, R row-major, V, Ba, Bg) | tic 3 | ric 9 | td | L depths
+    double* out;           // member's output block: SolverState | (W+1) x 21 (P, R row-major, V, Ba, Bg) | tic 3 | ric 9 | td | L depths |
+                           // with a relocalisation block: relo_r 9 (row-major) | relo_t 3 (estimator.cpp:598-605)
     int n_kept;            // kept blocks of the new prior (0: nothing is marginalised this frame)
     int kept_type[BA_MAX_PRIOR_BLOCKS], kept_index[BA_MAX_PRIOR_BLOCKS];  // pre-shift identities
     double* x0_out;        // new prior's linearisation point, 9 doubles per kept block

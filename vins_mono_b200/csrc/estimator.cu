@@ -27,6 +27,8 @@
 
 #include "ba_kernels.h"
 #include "host_math.h"
+#include <array>
+
 #include "hostpool.h"
 #include "initial.h"
 #include "vinsb200/estimator.h"
@@ -105,6 +107,18 @@ struct ve_estimator {
     int last_track_num = 0;
     std::vector<SeedRow> seeds;
     Vec3 seed_ba, seed_bg;
+    // relocalisation (estimator.h:125-138): set by ve_set_relo_frame, consumed by the next solve
+    bool relocalization_info = false, fr_relo = false;
+    double relo_frame_stamp = 0;
+    int relo_frame_index = 0, relo_frame_local_index = 0;
+    std::vector<double> match_points;  // x, y, feature id per match, ascending id
+    double relo_Pose[7] = {0, 0, 0, 0, 0, 0, 1};
+    std::vector<std::array<double, 7>> para_Pose;  // the window poses as last packed by vector2double (post-solve, pre-slide)
+    Mat3 drift_correct_r, prev_relo_r;
+    Vec3 drift_correct_t, prev_relo_t, relo_relative_t;
+    Quat relo_relative_q;
+    double relo_relative_yaw = 0;
+    int n_relo_factors = 0, n_relo_solves = 0;
     // initialisation bookkeeping while solver_flag == INITIAL (estimator.h:117-119: all_image_frame, tmp_pre_integration)
     std::vector<vb::init::ImageFrame> all_image_frame;  // ascending stamps (std::map<double, ImageFrame> in the reference)
     vb::init::Preint tmp_pre;
@@ -197,20 +211,21 @@ namespace {
         }                                                                    \
     } while (0)
 
-size_t states_doubles(const ve_estimator* e, int L) { return (size_t)(e->W + 1) * 16 + 8 + L; }
+size_t states_doubles(const ve_estimator* e, int L) { return (size_t)(e->W + 1) * 16 + 8 + L + 8; }  // ... | lam L | relo_Pose 7 (+1)
 // per-factor linearisation records of one point (BaAccum): obsJ | lmW | imuJ | gpr | gp | cost, at the widest strides
 size_t acc_doubles(const ve_estimator* e) {
     return (size_t)e->Mmax * vb::OJ_FULL + (size_t)e->Lmax * vb::LW_FULL + (size_t)e->W * vb::IMUJ_STRIDE + (vb::BA_PRIOR_COST + 8) + e->D + 8;
 }
 size_t align16(size_t bytes) { return (bytes + 15) & ~(size_t)15; }
 
-vb::BaStates states_view(double* p, int F) {
+vb::BaStates states_view(double* p, int F, int L) {
     vb::BaStates s;
     s.pose = p;
     s.sb = p + 7 * F;
     s.ex = p + 16 * F;
     s.td = p + 16 * F + 7;
     s.lam = p + 16 * F + 8;
+    s.relo = s.lam + L;
     return s;
 }
 bool usable(const ve_estimator* e, FeaturePerId& it) {  // the filter repeated all over feature_manager.cpp
@@ -435,6 +450,9 @@ void clear_state(ve_estimator* e) {
     e->all_image_frame.clear();
     e->tmp_pre.valid = false;
     e->initial_timestamp = 0;
+    e->relocalization_info = false;
+    e->drift_correct_r = Mat3();
+    e->drift_correct_t = Vec3();
 }
 
 void process_imu(ve_estimator* e, double dt, const Vec3& acc, const Vec3& gyr) {
@@ -614,6 +632,7 @@ void pack_states(ve_estimator* e, double* out) {
     int k = 0;
     for (auto& it : e->feature)
         if (usable(e, it)) out[16 * F + 8 + k++] = 1. / it.estimated_depth;
+    for (int q7 = 0; q7 < 7; q7++) out[16 * F + 8 + k + q7] = e->relo_Pose[q7];
 }
 
 // Results of the device-side double2vector (ba_finish_kernel) -> Estimator members.
@@ -639,6 +658,29 @@ void unpack_results(ve_estimator* e, const double* out) {
         if (!usable(e, it)) continue;
         it.estimated_depth = od[k++];
         it.solve_flag = it.estimated_depth < 0 ? 2 : 1;
+    }
+    for (int i = 0; i < F; i++) {  // what the closing vector2double leaves in para_Pose (setReloFrame copies from it)
+        const Quat q = Quat::FromR(e->Rs[i]);
+        e->para_Pose[i] = {e->Ps[i].x, e->Ps[i].y, e->Ps[i].z, q.x, q.y, q.z, q.w};
+    }
+    if (e->fr_relo) {  // drift bookkeeping of double2vector (estimator.cpp:598-617); relo_r / relo_t come from the device
+        const double* ro = od + k;
+        Mat3 relo_r;
+        std::memcpy(relo_r.m, ro, 9 * sizeof(double));
+        const Vec3 relo_t(ro[9], ro[10], ro[11]);
+        const double drift_correct_yaw = hm::R2ypr(e->prev_relo_r).x - hm::R2ypr(relo_r).x;
+        e->drift_correct_r = hm::ypr2R(Vec3(drift_correct_yaw, 0, 0));
+        e->drift_correct_t = e->prev_relo_t - e->drift_correct_r * relo_t;
+        const int li = e->relo_frame_local_index;
+        e->relo_relative_t = relo_r.T() * (e->Ps[li] - relo_t);
+        e->relo_relative_q = Quat::FromR(relo_r.T() * e->Rs[li]);
+        double a = hm::R2ypr(e->Rs[li]).x - hm::R2ypr(relo_r).x;  // Utility::normalizeAngle
+        if (a > 180.0) a -= 360.0;
+        else if (a < -180.0) a += 360.0;
+        e->relo_relative_yaw = a;
+        e->relocalization_info = false;
+        e->fr_relo = false;
+        e->n_relo_solves++;
     }
 }
 
@@ -736,18 +778,41 @@ int stage_frame(ve_estimator* e, bool solve) {
     int L = 0, M = 0;
     vb::MargPlan mp{};
     MargHost mh;
+    std::vector<int> relo_match;  // per landmark: index of its relocalisation match in match_points, or -1
+    e->fr_relo = false;
     if (solve) {
         for (int f = 0; f <= W; f++) flush_frame(e, f);
         q.sqrt_mask = refresh_sqrt_mask(e);
+        // the solver's column tables hold 352 entries (W = 22 with extrinsic and td): a relocalisation block that would not fit is
+        // left out (only possible at the largest window with both optional blocks live)
+        const bool relo = e->relocalization_info && 15 * F + 6 * (e->cfg.estimate_extrinsic ? 1 : 0) + (e->cfg.estimate_td ? 1 : 0) + 6 <= 352;
+        const size_t n_match = e->match_points.size() / 3;
+        size_t retrive_feature_index = 0;
+        int n_relo = 0;
         for (auto& it : e->feature) {
             if (!usable(e, it)) continue;
-            if (L >= e->Lmax || M + (int)it.feature_per_frame.size() > e->Mmax) {
+            if (L >= e->Lmax || M + (int)it.feature_per_frame.size() + 1 > e->Mmax) {
                 e->err = "feature capacity (max_features) exceeded";  // NUM_OF_F overflow is silent in the reference (estimator.h:111)
                 return VE_ERR_CAPACITY;
             }
             M += (int)it.feature_per_frame.size() - 1;
             L++;
+            if (relo) {  // the walk of estimator.cpp:777-797 (bounded: the reference runs off match_points' end)
+                int hit = -1;
+                if (it.start_frame <= e->relo_frame_local_index) {
+                    while (retrive_feature_index < n_match && (int)e->match_points[3 * retrive_feature_index + 2] < it.feature_id)
+                        retrive_feature_index++;
+                    if (retrive_feature_index < n_match && (int)e->match_points[3 * retrive_feature_index + 2] == it.feature_id) {
+                        hit = (int)retrive_feature_index++;
+                        n_relo++;
+                        M++;
+                    }
+                }
+                relo_match.push_back(hit);
+            }
         }
+        e->fr_relo = relo;
+        e->n_relo_factors = n_relo;
         const int rc = plan_marginalization(e, mp, mh);
         if (rc) return rc;
     }
@@ -764,7 +829,7 @@ int stage_frame(ve_estimator* e, bool solve) {
     const size_t o_jobs = take(n_jobs * sizeof(vb::PreintJob)), o_samples = take(n_rec * 7 * sizeof(double));
     size_t o_int = 0, o_dbl = 0, o_states = 0, o_marg = 0;
     if (solve) {
-        o_int = take(sizeof(int) * ((size_t)2 * L + 1 + M + W));
+        o_int = take(sizeof(int) * ((size_t)3 * L + 1 + M + W));
         o_dbl = take(sizeof(double) * (6 * (size_t)L + 6 * (size_t)M));
         o_states = take(sizeof(double) * states_doubles(e, L));
         o_marg = take(sizeof(int) * 2 * n_lm);
@@ -796,6 +861,7 @@ int stage_frame(ve_estimator* e, bool solve) {
     int* lm_start = lm_anchor + L;
     int* ob_frame = lm_start + L + 1;
     int* imu_slot = ob_frame + M;
+    int* lm_relo = imu_slot + W;
     double* lm_pts = reinterpret_cast<double*>(hb + o_dbl);
     double* lm_vel = lm_pts + 2 * L;
     double* lm_td = lm_vel + 2 * L;
@@ -823,6 +889,17 @@ int stage_frame(ve_estimator* e, bool solve) {
             ob_row[m] = fj.v;
             m++;
         }
+        lm_relo[l] = 0;
+        if (e->fr_relo && relo_match[l] >= 0) {  // ProjectionFactor(pts_i, pts_j = match) against relo_Pose: the row behind the track
+            const double* mpt = &e->match_points[3 * (size_t)relo_match[l]];
+            ob_frame[m] = -1;
+            ob_pts[2 * m] = mpt[0]; ob_pts[2 * m + 1] = mpt[1];
+            ob_vel[2 * m] = 0; ob_vel[2 * m + 1] = 0;
+            ob_td[m] = f0.cur_td;
+            ob_row[m] = 0;
+            lm_relo[l] = 1;
+            m++;
+        }
         l++;
     }
     lm_start[L] = M;
@@ -841,13 +918,17 @@ int stage_frame(ve_estimator* e, bool solve) {
     d.col_ex = d.est_ex ? 15 * F : -1;
     d.col_td = d.est_td ? 15 * F + 6 * d.est_ex : -1;
     d.D = 15 * F + 6 * d.est_ex + d.est_td;
-    d.pad = 0;
+    d.col_relo = -1;
+    if (e->fr_relo) {  // relo_Pose: one more pose block behind every other column
+        d.col_relo = d.D;
+        d.D += 6;
+    }
     d.sqrt_info_vis = e->cfg.focal_length / 1.5;
     d.tr_over_row = e->cfg.tr / e->cfg.row;
     d.half_row = e->cfg.row / 2;
     d.G[0] = 0; d.G[1] = 0; d.G[2] = e->cfg.g_norm;
-    p.x[0] = states_view(reinterpret_cast<double*>(db + o_states), F);
-    p.x[1] = states_view(e->d_states1.p, F);
+    p.x[0] = states_view(reinterpret_cast<double*>(db + o_states), F, L);
+    p.x[1] = states_view(e->d_states1.p, F, L);
     const bool wide = d.est_ex || d.est_td;
     d.oj = wide ? vb::OJ_FULL : vb::OJ_BASE;
     d.lw = wide ? vb::LW_FULL : vb::LW_BASE;
@@ -865,6 +946,7 @@ int stage_frame(ve_estimator* e, bool solve) {
     p.lm_start = di + L;
     p.ob_frame = di + 2 * L + 1;
     p.imu_slot = p.ob_frame + M;
+    p.lm_relo = p.imu_slot + W;
     const double* dobs = reinterpret_cast<const double*>(db + o_dbl);
     p.lm_pts = dobs;
     p.lm_vel = dobs + 2 * L;
@@ -924,7 +1006,7 @@ int stage_frame(ve_estimator* e, bool solve) {
     fp.origin_ypr[0] = origin_R0.x; fp.origin_ypr[1] = origin_R0.y; fp.origin_ypr[2] = origin_R0.z;
     fp.origin_P0[0] = origin_P0.x; fp.origin_P0[1] = origin_P0.y; fp.origin_P0[2] = origin_P0.z;
     std::memcpy(fp.Rs0, e->Rs[0].m, sizeof(fp.Rs0));
-    const size_t out_doubles = vb::BA_OUT_ST_DOUBLES + 21 * (size_t)F + 13 + L;
+    const size_t out_doubles = vb::BA_OUT_ST_DOUBLES + 21 * (size_t)F + 13 + L + (e->fr_relo ? 12 : 0);
     const size_t orel = grp.out_used.fetch_add((out_doubles + 1) & ~(size_t)1);
     const size_t obase = grp.out_base + orel;
     if (orel + out_doubles > grp.out_cap) {
@@ -1175,7 +1257,7 @@ int batch_process(ve_batch* b, const FrameMsg* msgs, int* status_out) {
         vb::BatchShape sh{};
         sh.S = grp.count;
         sh.W = b->cfg.window_size;
-        sh.D = b->members[0]->D - (b->cfg.estimate_extrinsic ? 0 : 6) - (b->cfg.estimate_td ? 0 : 1);
+        sh.D = 0;  // the largest reduced system of this frame (a relocalisation pose adds 6 columns to a member)
         sh.max_iterations = b->cfg.num_iterations;
         sh.est_ex = b->cfg.estimate_extrinsic ? 1 : 0;
         sh.est_td = b->cfg.estimate_td ? 1 : 0;
@@ -1186,6 +1268,7 @@ int batch_process(ve_batch* b, const FrameMsg* msgs, int* status_out) {
             if (!q.active) continue;
             sh.any_active = 1;
             sh.max_L = std::max(sh.max_L, q.p.dims.L);
+            sh.D = std::max(sh.D, q.p.dims.D);
             if (q.do_marg) {
                 sh.any_marg = 1;
                 sh.max_n_lm = std::max(sh.max_n_lm, q.mp.n_lm);
@@ -1283,12 +1366,13 @@ ve_estimator* create_member(ve_batch* b, int k) {
     const int W = e->W, F = W + 1;
     e->Ps.resize(F); e->Vs.resize(F); e->Bas.resize(F); e->Bgs.resize(F); e->Rs.resize(F);
     e->Headers.assign(F, 0.0);
+    e->para_Pose.assign(F, std::array<double, 7>{0, 0, 0, 0, 0, 0, 1});
     e->dt_buf.resize(F); e->acc_buf.resize(F); e->gyr_buf.resize(F);
     e->slot_of.resize(F); e->slot_valid.assign(F, false); e->flushed.assign(F, 0); e->sum_dt.assign(F, 0.0);
     e->lin_acc.resize(F); e->lin_gyr.resize(F); e->sqrt_dirty.assign(F, true);
     e->Lmax = b->cfg.max_features;
-    e->Mmax = b->cfg.max_features * W;
-    e->D = 15 * F + 6 + 1;
+    e->Mmax = b->cfg.max_features * (W + 1);  // + one relocalisation match per landmark
+    e->D = 15 * F + 6 + 1 + 6;               // ex, td and a relocalisation pose on top of the window
     e->nmax = 6 * F + 9 * 2 + 6 + 1;
     clear_state(e);
     set_parameter(e);
@@ -1355,7 +1439,7 @@ int ve_batch_create(const ve_config* cfg, int n, ve_batch** out) {
     const int W = cfg->window_size, F = W + 1;
     // input block of one member at full capacity: jobs + samples + tables + states + marginalisation lists
     const size_t per_in = align16(sizeof(vb::PreintJob) * 4 * F) + align16(sizeof(double) * 7 * 4096) +
-                          align16(sizeof(int) * ((size_t)2 * e0->Lmax + 1 + e0->Mmax + W)) +
+                          align16(sizeof(int) * ((size_t)3 * e0->Lmax + 1 + e0->Mmax + W)) +
                           align16(sizeof(double) * (6 * (size_t)e0->Lmax + 6 * (size_t)e0->Mmax)) +
                           align16(sizeof(double) * states_doubles(e0, e0->Lmax)) + align16(sizeof(int) * 2 * (size_t)e0->Lmax);
     // a batch rarely has every member at capacity: size the arenas for the full capacity of 8 members or a quarter of
@@ -1369,8 +1453,8 @@ int ve_batch_create(const ve_config* cfg, int n, ve_batch** out) {
         grp.in_cap = per_in * at_cap;
         in_total += grp.in_cap;
         grp.out_base = out_total;
-        grp.out_cap = ((size_t)vb::BA_OUT_ST_DOUBLES + 21 * F + 13 + e0->Lmax + 1) * at_cap +
-                      ((size_t)vb::BA_OUT_ST_DOUBLES + 21 * F + 13 + 256) * (size_t)grp.count;
+        grp.out_cap = ((size_t)vb::BA_OUT_ST_DOUBLES + 21 * F + 13 + e0->Lmax + 13) * at_cap +
+                      ((size_t)vb::BA_OUT_ST_DOUBLES + 21 * F + 13 + 256 + 12) * (size_t)grp.count;
         grp.out_cap = (grp.out_cap + 1) & ~(size_t)1;
         out_total += grp.out_cap;
     }
@@ -1549,6 +1633,39 @@ int ve_get_states(const ve_estimator* e, double* out, double* td) {
         o[13] = e->Bgs[i].x; o[14] = e->Bgs[i].y; o[15] = e->Bgs[i].z;
     }
     if (td) *td = e->td;
+    return VE_OK;
+}
+
+int ve_set_relo_frame(ve_estimator* e, double frame_stamp, int frame_index, int n, const double* match_points, const double* relo_t,
+                      const double* relo_r) {
+    if (!e || n < 0 || (n && !match_points) || !relo_t || !relo_r) return VE_ERR_INVALID;
+    e->relo_frame_stamp = frame_stamp;
+    e->relo_frame_index = frame_index;
+    e->match_points.assign(match_points, match_points + 3 * (size_t)n);
+    e->prev_relo_t = Vec3(relo_t[0], relo_t[1], relo_t[2]);
+    std::memcpy(e->prev_relo_r.m, relo_r, sizeof(e->prev_relo_r.m));
+    int found = 0;
+    for (int i = 0; i < e->W; i++)
+        if (e->relo_frame_stamp == e->Headers[i]) {
+            e->relo_frame_local_index = i;
+            e->relocalization_info = true;
+            for (int j = 0; j < 7; j++) e->relo_Pose[j] = e->para_Pose[i][j];
+            found = 1;
+        }
+    return found;
+}
+
+int ve_get_relocalization(const ve_estimator* e, double* o) {
+    if (!e || !o) return VE_ERR_INVALID;
+    std::memcpy(o, e->drift_correct_r.m, 9 * sizeof(double));
+    o[9] = e->drift_correct_t.x; o[10] = e->drift_correct_t.y; o[11] = e->drift_correct_t.z;
+    o[12] = e->relo_relative_t.x; o[13] = e->relo_relative_t.y; o[14] = e->relo_relative_t.z;
+    o[15] = e->relo_relative_q.w; o[16] = e->relo_relative_q.x; o[17] = e->relo_relative_q.y; o[18] = e->relo_relative_q.z;
+    o[19] = e->relo_relative_yaw;
+    o[20] = e->relocalization_info ? 1.0 : 0.0;
+    o[21] = e->relo_frame_local_index;
+    o[22] = e->n_relo_factors;
+    o[23] = e->n_relo_solves;
     return VE_OK;
 }
 

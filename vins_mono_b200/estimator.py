@@ -68,6 +68,8 @@ def _bind(lib):
     lib.ve_debug_imu_factor.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ve_init_info.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ve_set_relo_frame.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ve_get_relocalization.argtypes = [C.c_void_p, C.c_void_p]
     lib.ve_debug_relative_rt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
     lib.ve_debug_solve_pnp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.ve_debug_sfm_construct.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_double] + \
@@ -124,6 +126,19 @@ class Estimator:
         if rc < 0:
             raise RuntimeError(f"vinsb200 error {rc}: {self.lib.ve_last_error(self.h).decode()}")
         return rc
+
+    def setReloFrame(self, frame_stamp, frame_index, match_points, relo_t, relo_r):
+        """Estimator::setReloFrame (estimator.h:36): match_points = n x (x, y, feature id).  True when the stamp is in the window."""
+        mp = _d(match_points).reshape(-1, 3)
+        return bool(self._check(self.lib.ve_set_relo_frame(self.h, float(frame_stamp), int(frame_index), len(mp), _p(mp), _p(_d(relo_t)),
+                                                           _p(_d(relo_r).reshape(9)))))
+
+    def relo(self):
+        o = np.zeros(24)
+        self._check(self.lib.ve_get_relocalization(self.h, _p(o)))
+        return dict(drift_correct_r=o[0:9].reshape(3, 3).copy(), drift_correct_t=o[9:12].copy(), relo_relative_t=o[12:15].copy(),
+                    relo_relative_q=o[15:19].copy(), relo_relative_yaw=float(o[19]), pending=bool(o[20]), local_index=int(o[21]),
+                    factors=int(o[22]), solves=int(o[23]))
 
     def init_info(self):
         """How the window was initialised: own initialStructure (self_initialised) or a caller-supplied seed."""

@@ -97,11 +97,24 @@ class Estimator {
         Headers[i] = stamp;
         refresh();
     }
-    // Relocalisation is the pose-graph coupling (estimator.cpp:769-801, 1128-1146), outside this library's hot path
-    // (SURVEY 8f next-4): the call is accepted and ignored, relocalization_info stays false.
+    // Estimator::setReloFrame (estimator.cpp:1128-1146): match_points holds (x, y, feature id) triples (vector<Vector3d> in the node,
+    // estimator_node.cpp:275-290).  The next processImage optimises relo_Pose with the matched landmarks and refresh() publishes
+    // drift_correct_r / drift_correct_t / relo_relative_t / relo_relative_q / relo_relative_yaw / relo_frame_index as the
+    // reference does (estimator.cpp:598-617, read by visualization.cpp:326-350 and estimator_node.cpp:327-328).
     template <class Points>
-    void setReloFrame(double /*frame_stamp*/, int /*frame_index*/, Points& /*match_points*/, const Vector3d& /*relo_t*/, const Matrix3d& /*relo_r*/) {
-        relocalization_info = false;
+    void setReloFrame(double frame_stamp, int frame_index, Points& match_points, const Vector3d& relo_t, const Matrix3d& relo_r) {
+        std::vector<double> mp;
+        for (const auto& q : match_points)
+            for (int k = 0; k < 3; k++) mp.push_back(q[k]);
+        const double t[3] = {relo_t[0], relo_t[1], relo_t[2]};
+        double r[9];
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) r[3 * i + j] = relo_r(i, j);
+        relo_frame_stamp = frame_stamp;
+        relo_frame_index = frame_index;
+        const int rc = ve_set_relo_frame(h_, frame_stamp, frame_index, (int)(mp.size() / 3), mp.data(), t, r);
+        check(rc);
+        if (rc == 1) relocalization_info = true;
     }
 
     SolverFlag solver_flag = INITIAL;
@@ -116,6 +129,11 @@ class Estimator {
     std::vector<double> Headers;  // stamps (the reference keeps std_msgs::Header objects)
     double td = 0;
     bool relocalization_info = false;
+    double relo_frame_stamp = 0, relo_frame_index = 0, relo_relative_yaw = 0;  // (the reference declares relo_frame_index as double)
+    int relo_frame_local_index = 0;
+    Matrix3d drift_correct_r;
+    Vector3d drift_correct_t, relo_relative_t;
+    double relo_relative_q[4] = {1, 0, 0, 0};  // w x y z
     ve_estimator* handle() { return h_; }
 
   private:
@@ -150,6 +168,17 @@ class Estimator {
         int info[10];
         double c[2];
         ve_info(h_, info, c);
+        double ro[24];
+        ve_get_relocalization(h_, ro);
+        for (int r = 0; r < 3; r++) {
+            for (int cc = 0; cc < 3; cc++) drift_correct_r(r, cc) = ro[3 * r + cc];
+            drift_correct_t[r] = ro[9 + r];
+            relo_relative_t[r] = ro[12 + r];
+        }
+        for (int k = 0; k < 4; k++) relo_relative_q[k] = ro[15 + k];
+        relo_relative_yaw = ro[19];
+        relocalization_info = ro[20] != 0.0;
+        relo_frame_local_index = (int)ro[21];
         solver_flag = info[0] ? NON_LINEAR : INITIAL;
         frame_count = info[1];
         marginalization_flag = info[2] ? MARGIN_SECOND_NEW : MARGIN_OLD;
