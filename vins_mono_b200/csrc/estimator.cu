@@ -1059,7 +1059,7 @@ int stage_frame(ve_estimator* e, bool solve) {
     q.active = 1;
     e->fr_L = L;
     e->last_landmarks = L;
-    e->last_visual = M;
+    e->last_visual = M - (e->fr_relo ? e->n_relo_factors : 0);  // f_m_cnt counts the window's factors only (estimator.cpp:766)
     return VE_OK;
 }
 
