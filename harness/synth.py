@@ -80,7 +80,7 @@ class _Harmonics:
 
 class Sequence:
     def __init__(self, seed=0, duration=30.0, cam_hz=20.0, imu_hz=200.0, rows=ROWS, cols=COLS,
-                 pixel_noise=2.0, imu_noise=True, t0=0.0):
+                 pixel_noise=2.0, imu_noise=True, t0=0.0, rot_gain=1.0):
         self.seed, self.duration, self.cam_hz, self.imu_hz = seed, duration, cam_hz, imu_hz
         self.rows, self.cols, self.pixel_noise, self.imu_noise, self.t0 = rows, cols, pixel_noise, imu_noise, t0
         rng = np.random.default_rng(1000 + seed)
@@ -92,8 +92,11 @@ class Sequence:
 
         # extents ~ +-2.5 m horizontally, +-0.6 m vertically, peak speed ~1.5 m/s (EuRoC MH_01-like)
         self.px, self.py, self.pz = harm(2.2, 0.5, 0.05, 0.17), harm(1.8, 0.4, 0.07, 0.21), harm(0.5, 0.15, 0.09, 0.3)
-        self.yaw = harm(1.2, 0.3, 0.04, 0.13)
-        self.pitch, self.roll = harm(0.18, 0.05, 0.11, 0.37), harm(0.15, 0.05, 0.09, 0.41)
+        # rot_gain > 1 speeds the attitude harmonics up ("rotation movement is needed": the online extrinsic calibration,
+        # ESTIMATE_EXTRINSIC = 2, only converges under rotational excitation); 1.0 leaves every existing sequence unchanged
+        g_ = float(rot_gain)
+        self.yaw = harm(1.2, 0.3, 0.04 * g_, 0.13 * g_)
+        self.pitch, self.roll = harm(0.18, 0.05, 0.11 * g_, 0.37 * g_), harm(0.15, 0.05, 0.09 * g_, 0.41 * g_)
         self.ba = np.array([0.02, -0.015, 0.03]) + 0 * rng.normal(0, 1, 3)
         self.bg = np.array([0.003, -0.002, 0.001])
         ext = np.array([2.7, 2.2, 0.65])

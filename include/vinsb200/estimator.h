@@ -142,7 +142,9 @@ int ve_debug_imu_factor(const double* noise4, double g_norm, const double* ba, c
 
 /* ---- Initialisation (Estimator::initialStructure, vins_estimator/src/estimator.cpp:218-471) ----------
  * The estimator bootstraps itself from the first full window (relative pose -> global SfM -> PnP of every image ->
- * visual-inertial alignment) unless a seed trajectory covering the window was supplied with ve_set_seed.  The stages are
+ * visual-inertial alignment) unless a seed trajectory covering the window was supplied with ve_set_seed; with
+ * ve_config.estimate_extrinsic = 2 it first calibrates the camera-IMU rotation from the image / gyroscope rotation pairs
+ * (CalibrationExRotation, estimator.cpp:140-156) and then continues with estimate_extrinsic = 1.  The stages are
  * host code in the reference as well; the entries below run them on caller-supplied arrays WITHOUT a handle or a GPU so
  * that they can be pinned against OpenCV / numpy twins (tests/test_host_initial.py).
  *   ve_debug_relative_rt        solve_5pts.cpp:193-227: corres4 = n x (x0 y0 x1 y1) normalised coordinates; R9 / T3 = the
@@ -161,6 +163,15 @@ int ve_debug_imu_factor(const double* noise4, double g_norm, const double* ba, c
  *                               (9 per frame, already x RIC^T) / frame_T, x (3 per frame velocities | 2 | scale), g3 (before the
  *                               yaw alignment), delta_bg3, info4 = l, bundle iterations, is-keyframe count, reserved;
  *                               bundle_cost.  Returns 0 or the failing stage (1 relative pose, 2 SfM, 3 PnP, 4 alignment). */
+/*   ve_debug_ex_rotation        InitialEXRotation::CalibrationExRotation (initial_ex_rotation.cpp:11-67; ve_config.estimate_extrinsic
+ *                               = 2, with ric = I and tic = 0 as parameters.cpp:101-106 sets them) called n_steps times in a row:
+ *                               step k gets the correspondences corres4[corres_off[k] .. corres_off[k+1]) (x0 y0 x1 y1 between the
+ *                               two newest frames) and the gyroscope rotation dq_wxyz[4 k ..]; ric_out (9 per step) = the running
+ *                               estimate, ok_out = its return value, cov_out (may be NULL) = the singular value it thresholds, rc_out (may be NULL,
+ *                               9 per step) = the camera rotation solveRelativeR extracted from the step's correspondences; rc_in (may be
+ *                               NULL, 9 per step): use these camera rotations instead (pins the quaternion system by itself). */
+int ve_debug_ex_rotation(int n_steps, const int* corres_off, const double* corres4, const double* dq_wxyz, int window_size, double* ric_out,
+                         int* ok_out, double* cov_out, double* rc_out, const double* rc_in);
 int ve_debug_relative_rt(const double* corres4, int n, double* R9, double* T3, int* inliers);
 int ve_debug_solve_pnp(const double* pts3, const double* pts2, int n, double* R9, double* t3);
 int ve_debug_sfm_construct(int frame_num, int l, const double* relative_R9, const double* relative_T3, int n_tracks,

@@ -134,6 +134,10 @@ int vt_debug_lk(vt_tracker* t, const uint8_t* prev, const uint8_t* next, size_t 
 int vt_debug_fundamental_ransac(const float* pts1, const float* pts2, int n, double threshold, double confidence, uint8_t* status);
 /* PinholeCamera::liftProjective (PinholeCamera.cc:450-510) as undistortedPoints() applies it: n pixel pairs -> n normalised
  * (x, y) pairs; intrinsics8 = fx fy cx cy k1 k2 p1 p2.  Host only. */
+/* The same call returning the winning model as well (row-major 3x3; OpenCV does not refit it): what the estimator's
+ * initialisation hands to recoverPose / decomposeE (solve_5pts.cpp:205, initial_ex_rotation.cpp:79). */
+int vt_debug_fundamental_ransac_model(const float* pts1, const float* pts2, int n, double threshold, double confidence, uint8_t* status,
+                                      double* F9);
 int vt_debug_lift_projective(const double* intrinsics8, const double* px, int n, double* out_xy);
 /* The same for any vt_camera_model: liftProjective followed by the division by z (what undistortedPoints / rejectWithF use). */
 int vt_debug_lift_projective_model(int camera_model, const double* intrinsics8, double xi, const double* px, int n, double* out_xy);

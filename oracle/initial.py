@@ -427,3 +427,81 @@ def window_after_align(frames, headers, x, g, tic):
     yaw = R2ypr(R0 @ Rs[0])[0]
     R0 = Rotation.from_euler("z", -yaw, degrees=True).as_matrix() @ R0
     return [R0 @ p for p in Ps], [R0 @ r for r in Rs], [R0 @ v for v in Vs], R0 @ g
+
+
+# ---- InitialEXRotation (initial/initial_ex_rotation.cpp): ESTIMATE_EXTRINSIC == 2 ---------------------------------------------
+class ExRotation:
+    """Camera-IMU rotation from (essential-matrix rotation, gyroscope rotation) pairs; the two-view part through OpenCV as in the
+    reference (cv::findFundamentalMat with its defaults, cv::SVD, cv::triangulatePoints)."""
+
+    def __init__(self):
+        self.frame_count = 0
+        self.Rc, self.Rimu, self.Rc_g = [np.eye(3)], [np.eye(3)], [np.eye(3)]
+        self.ric = np.eye(3)
+        self.cov1 = 0.0
+
+    @staticmethod
+    def _test_triangulation(l, r, R, t):
+        import cv2
+        P = np.hstack([np.eye(3), np.zeros((3, 1))]).astype(np.float32)
+        P1 = np.hstack([R, t.reshape(3, 1)]).astype(np.float32)
+        X = cv2.triangulatePoints(P, P1, l.T.copy(), r.T.copy())
+        front = 0
+        for i in range(X.shape[1]):
+            x = X[:, i] / X[3, i]
+            if (P.astype(float) @ x)[2] > 0 and (P1.astype(float) @ x)[2] > 0:
+                front += 1
+        return front / X.shape[1]
+
+    def solve_relative_r(self, corres):
+        import cv2
+        corres = np.asarray(corres, float).reshape(-1, 4)
+        if len(corres) < 9:
+            return np.eye(3)
+        ll, rr = corres[:, :2].astype(np.float32), corres[:, 2:].astype(np.float32)
+        E, _ = cv2.findFundamentalMat(ll, rr)
+
+        def decompose(E):
+            _, u, vt = cv2.SVDecomp(E)
+            W = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1.0]])
+            return u @ W @ vt, u @ W.T @ vt, u[:, 2].copy(), -u[:, 2].copy()
+
+        R1, R2, t1, t2 = decompose(E)
+        if np.linalg.det(R1) + 1.0 < 1e-09:
+            R1, R2, t1, t2 = decompose(-E)
+        ratio1 = max(self._test_triangulation(ll, rr, R1, t1), self._test_triangulation(ll, rr, R1, t2))
+        ratio2 = max(self._test_triangulation(ll, rr, R2, t1), self._test_triangulation(ll, rr, R2, t2))
+        return (R1 if ratio1 > ratio2 else R2).T
+
+    def calibrate(self, corres, delta_q_imu, window_size=10, rc_given=None):
+        """delta_q_imu wxyz.  Returns (ok, ric)."""
+        self.frame_count += 1
+        self.Rc.append(self.solve_relative_r(corres) if rc_given is None else np.asarray(rc_given, float))
+        Rq = quat_to_R(np.asarray(delta_q_imu, float))
+        self.Rimu.append(Rq)
+        self.Rc_g.append(self.ric.T @ Rq @ self.ric)
+        A = np.zeros((4 * self.frame_count, 4))
+        for i in range(1, self.frame_count + 1):
+            r1, r2 = R_to_quat(self.Rc[i]), R_to_quat(self.Rc_g[i])
+            d = qmul(r1, r2 * np.array([1, -1, -1, -1]))
+            ang = np.degrees(2 * np.arctan2(np.linalg.norm(d[1:]), abs(d[0])))
+            huber = 5.0 / ang if ang > 5.0 else 1.0
+            w, q = r1[0], r1[1:]
+            L = np.zeros((4, 4))
+            L[:3, :3] = w * np.eye(3) + skew(q)
+            L[:3, 3] = q
+            L[3, :3] = -q
+            L[3, 3] = w
+            rij = R_to_quat(self.Rimu[i])
+            w, q = rij[0], rij[1:]
+            R = np.zeros((4, 4))
+            R[:3, :3] = w * np.eye(3) - skew(q)
+            R[:3, 3] = q
+            R[3, :3] = -q
+            R[3, 3] = w
+            A[4 * (i - 1): 4 * i] = huber * (L - R)
+        _, sv, vt = np.linalg.svd(A)
+        x = vt[3]  # Eigen quaternion coefficients (x, y, z, w)
+        self.ric = quat_to_R(np.array([x[3], x[0], x[1], x[2]]) / np.linalg.norm(x)).T
+        self.cov1 = sv[2] if len(sv) >= 3 else 0.0
+        return bool(self.frame_count >= window_size and self.cov1 > 0.25), self.ric

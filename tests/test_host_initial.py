@@ -150,3 +150,92 @@ def test_initial_structure_reports_missing_parallax():
     still = [(i, s, np.repeat(xy[:1], len(xy), axis=0)) for i, s, xy in tracks]
     res = ve.debug_initial_structure(headers, frames, still, synth.RIC, synth.TIC, synth.G_NORM)
     assert res["code"] == 1
+
+
+# ---- ESTIMATE_EXTRINSIC == 2: InitialEXRotation (initial/initial_ex_rotation.cpp) ----------------------------------------------
+def _ex_rotation_inputs(seq, n_frames, pixel_sigma=0.3):
+    _, frames, _ = init_inputs.first_window(seq, n_window=n_frames, pixel_sigma=pixel_sigma)
+    of = init_inputs.oracle_frames(frames)
+    corres, dqs = [], []
+    for k in range(1, len(frames)):
+        a = dict(zip(frames[k - 1]["ids"], frames[k - 1]["xy"]))
+        corres.append(np.array([np.r_[a[i], xy] for i, xy in zip(frames[k]["ids"], frames[k]["xy"]) if i in a]))
+        dqs.append(of[k].pre.dq)
+    return corres, dqs
+
+
+def _angle_deg(Ra, Rb):
+    return np.degrees(np.arccos(np.clip((np.trace(Ra.T @ Rb) - 1) / 2, -1, 1)))
+
+
+def test_ex_rotation_linear_system_matches_twin():
+    """The quaternion system of CalibrationExRotation (Huber weights against the running estimate, 4N x 4 stack of L(q_cam) - R(q_imu),
+    smallest right singular vector, the observability threshold) with the camera rotations handed in: exact pairs
+    q_imu (x) q_ic = q_ic (x) q_cam plus two outliers that the Huber weights must tame."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(3)
+    q_ic = Rotation.from_rotvec([0.3, -1.1, 0.5])
+    dqs, rcs = [], []
+    for k in range(14):
+        # the first pairs rotate by less than 2.5 degrees: their Huber weight is 1 whatever the (still ambiguous) running estimate
+        # is; later pairs are large, their weights depend on an estimate that has converged by then
+        rv = rng.normal(0, 0.15, 3) if k >= 4 else 0.04 * rng.normal(0, 1, 3) / 3
+        r_cam = Rotation.from_rotvec(rv)
+        r_imu = q_ic * r_cam * q_ic.inv()
+        if k in (5, 9):  # an outlier pair: 20 degrees off
+            r_cam = Rotation.from_rotvec([0.35, 0, 0]) * r_cam
+        x, y, z, w = r_imu.as_quat()
+        dqs.append([w, x, y, z] if w >= 0 else [-w, -x, -y, -z])
+        rcs.append(r_cam.as_matrix())
+    corres = [np.zeros((0, 4))] * 14
+    ric, ok, cov, rcam = ve.debug_ex_rotation(corres, dqs, 10, rc_given=rcs)
+    cal = oi.ExRotation()
+    for k in range(14):
+        ok_c, ric_c = cal.calibrate(corres[k], dqs[k], 10, rc_given=rcs[k])
+        assert np.array_equal(rcam[k], rcs[k])
+        assert ok[k] == ok_c and abs(cov[k] - cal.cov1) < 1e-10
+        if k >= 2:  # the null direction is unique once rotations about different axes are stacked
+            assert np.abs(ric[k] - ric_c).max() < 1e-9, k
+    assert ok[-1] and not ok[:9].any()
+    assert _angle_deg(ric[-1], q_ic.as_matrix()) < 1.0  # ric = R(q_ic): rotation from the camera frame to the IMU frame
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_ex_rotation_calibrates_under_rotation(seed):
+    """Camera rotations out of cv::findFundamentalMat's DEFAULT call (RANSAC threshold 3 on normalised coordinates: every hypothesis
+    explains every point, the first 7-point sample's first root wins).  Which root comes first depends on OpenCV's SVD null-space
+    basis, so the product's and the twin's per-step rotations differ in detail; the calibration converges to the true camera-IMU
+    rotation for both, at (nearly) the same step."""
+    seq = synth.Sequence(seed=seed, duration=5.0, rot_gain=5.0)
+    corres, dqs = _ex_rotation_inputs(seq, 32)
+    ric, ok, cov, rcam = ve.debug_ex_rotation(corres, dqs, 10)
+    cal, ok_c, ric_c = oi.ExRotation(), [], []
+    for c, dq in zip(corres, dqs):
+        o, r = cal.calibrate(c, dq, 10)
+        ok_c.append(o)
+        ric_c.append(r.copy())
+    assert ok.any() and any(ok_c)
+    first, first_c = int(np.argmax(ok)), ok_c.index(True)
+    assert first >= 9 and first_c >= 9 and abs(first - first_c) <= 2      # never before frame_count >= WINDOW_SIZE
+    assert not ok[:9].any()
+    assert _angle_deg(ric[first], synth.RIC) < 2.5 and _angle_deg(ric_c[first_c], synth.RIC) < 2.5
+    assert _angle_deg(ric[-1], synth.RIC) < 2.0 and cov[-1] > 0.25
+    for k in range(len(rcam)):  # every extracted camera rotation is a proper rotation
+        assert abs(np.linalg.det(rcam[k]) - 1) < 1e-9 and np.abs(rcam[k] @ rcam[k].T - np.eye(3)).max() < 1e-9
+
+
+def test_ransac_model_matches_opencv_at_the_initialisation_threshold():
+    """The F matrix behind solveRelativeRT (RANSAC winner at 0.3 / 460): identical inlier masks and the same model as OpenCV."""
+    import ctypes as C
+    from vins_mono_b200 import load_library
+    lib = load_library()
+    seq = synth.Sequence(seed=0, duration=3.0)
+    corres, _ = _ex_rotation_inputs(seq, 12)
+    for c in corres:
+        ll, rr = np.ascontiguousarray(c[:, :2], np.float32), np.ascontiguousarray(c[:, 2:], np.float32)
+        E, m = cv2.findFundamentalMat(ll, rr, cv2.FM_RANSAC, 0.3 / 460, 0.99)
+        F, st = np.zeros(9), np.zeros(len(ll), np.uint8)
+        assert lib.vt_debug_fundamental_ransac_model(ll.ctypes.data_as(C.c_void_p), rr.ctypes.data_as(C.c_void_p), len(ll), C.c_double(0.3 / 460),
+                                                     C.c_double(0.99), st.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p)) == 1
+        assert np.array_equal(m.ravel() != 0, st != 0)
+        assert np.abs(E - F.reshape(3, 3)).max() < 1e-6 * max(1.0, np.abs(E).max())

@@ -114,3 +114,46 @@ def test_reboot_reinitialises_without_seed():
     assert res["code"] == 0 and ii["l"] == res["l"] and abs(ii["scale"] - res["x"][-1]) < 2e-2 * res["x"][-1]
     T, P = np.array(T), np.array(P)
     assert len(T) >= 25 and pipeline.ate_rmse(seq, T, P, skip=10) < 0.03     # metric again (SE(3) alignment, no scale)
+
+
+def test_online_extrinsic_calibration():
+    """ESTIMATE_EXTRINSIC = 2 (estimator.cpp:140-156, initial_ex_rotation.cpp): no extrinsic is configured (ric = I, tic = 0 as
+    parameters.cpp:101-106 sets them); under rotational excitation the estimator calibrates the camera-IMU rotation from image /
+    gyroscope rotation pairs, only then initialises, and refines the extrinsic in the window solves (ESTIMATE_EXTRINSIC = 1)."""
+    from vins_mono_b200 import Estimator
+    seq = synth.Sequence(seed=0, duration=9.0, rot_gain=5.0)
+    msgs = synth.track_messages(seq, 80, max_feats=150)
+    gpu = Estimator(tic=(0, 0, 0), ric=np.eye(3), estimate_extrinsic=2)
+    feeder = pipeline.ImuFeeder(*seq.imu())
+    lib = gpu.lib
+    import ctypes as C
+
+    def ric_now():
+        r = np.zeros(9)
+        lib.ve_get_extrinsic(gpu.h, None, r.ctypes.data_as(C.c_void_p))
+        return r.reshape(3, 3)
+
+    def angle(R):
+        return np.degrees(np.arccos(np.clip((np.trace(R.T @ synth.RIC) - 1) / 2, -1, 1)))
+
+    calibrated_at, nonlinear_at, T, P = None, None, [], []
+    for k, (stamp, ids, d) in enumerate(msgs):
+        if k == 0:
+            continue
+        feeder.feed(gpu, stamp)
+        gpu.processImage(ids, d, stamp)
+        if calibrated_at is None and np.abs(ric_now() - np.eye(3)).max() > 1e-6:
+            calibrated_at = k
+            assert angle(ric_now()) < 3.0, angle(ric_now())
+        if gpu.info()["solver_flag"] == 1:
+            if nonlinear_at is None:
+                nonlinear_at = k
+            st, _ = gpu.states()
+            T.append(stamp)
+            P.append(st[-1, 0:3].copy())
+    print("calibrated at message", calibrated_at, "NON_LINEAR from", nonlinear_at, "final extrinsic angle", angle(ric_now()))
+    assert calibrated_at is not None and 10 <= calibrated_at <= 20       # needs frame_count >= WINDOW_SIZE rotation pairs
+    assert nonlinear_at is not None and nonlinear_at >= calibrated_at and gpu.init_info()["self_initialised"]
+    assert angle(ric_now()) < 2.0
+    T, P = np.array(T), np.array(P)
+    assert len(T) >= 30 and pipeline.ate_rmse(seq, T[-20:], P[-20:]) < 0.15

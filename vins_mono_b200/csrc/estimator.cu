@@ -119,6 +119,10 @@ struct ve_estimator {
     Quat relo_relative_q;
     double relo_relative_yaw = 0;
     int n_relo_factors = 0, n_relo_solves = 0;
+    // ESTIMATE_EXTRINSIC == 2 (estimator.cpp:140-156): the camera-IMU rotation is calibrated online before the initialisation
+    vb::init::ExRotation initial_ex_rotation;
+    bool ex_calib_pending = false;  // ESTIMATE_EXTRINSIC is still 2
+    Mat3 RIC;                       // RIC[0]: the configured rotation, replaced by the calibrated one
     // initialisation bookkeeping while solver_flag == INITIAL (estimator.h:117-119: all_image_frame, tmp_pre_integration)
     std::vector<vb::init::ImageFrame> all_image_frame;  // ascending stamps (std::map<double, ImageFrame> in the reference)
     vb::init::Preint tmp_pre;
@@ -415,7 +419,7 @@ void remove_front(ve_estimator* e, int frame_count) {
 // ---- Estimator ---------------------------------------------------------------------------------
 void set_parameter(ve_estimator* e) {
     e->tic = Vec3(e->cfg.tic[0], e->cfg.tic[1], e->cfg.tic[2]);
-    std::memcpy(e->ric.m, e->cfg.ric, sizeof(e->ric.m));
+    e->ric = e->RIC;
     e->td = e->cfg.td;
     e->g = Vec3(0, 0, e->cfg.g_norm);
 }
@@ -534,8 +538,7 @@ bool initial_structure(ve_estimator* e) {
         }
         tracks.push_back(std::move(t));
     }
-    Mat3 RIC;
-    std::memcpy(RIC.m, e->cfg.ric, sizeof(RIC.m));
+    const Mat3 RIC = e->RIC;
     const Vec3 TIC(e->cfg.tic[0], e->cfg.tic[1], e->cfg.tic[2]);
     std::vector<double> headers(e->Headers.begin(), e->Headers.begin() + W + 1), x;
     std::vector<Vec3> Bgs(e->Bgs.begin(), e->Bgs.begin() + W + 1);
@@ -1157,9 +1160,28 @@ int prepare_frame(ve_estimator* e, int n, const int* ids, const double* xyz_uv_v
         fr.pre = e->tmp_pre;
         e->all_image_frame.push_back(std::move(fr));
         e->tmp_pre.start(e->acc_0, e->gyr_0, e->Bas[e->frame_count], e->Bgs[e->frame_count]);
+        if (e->ex_calib_pending && e->frame_count != 0) {  // CalibrationExRotation (estimator.cpp:140-156)
+            const int fc = e->frame_count;
+            std::vector<double> corres;  // f_manager.getCorresponding(frame_count - 1, frame_count)
+            for (auto& it : e->feature)
+                if (it.start_frame <= fc - 1 && it.endFrame() >= fc) {
+                    const Vec3 &a = it.feature_per_frame[fc - 1 - it.start_frame].point, &b2 = it.feature_per_frame[fc - it.start_frame].point;
+                    corres.push_back(a.x); corres.push_back(a.y); corres.push_back(b2.x); corres.push_back(b2.y);
+                }
+            Mat3 calib_ric;
+            // pre_integrations[frame_count]->delta_q: the samples since the previous image, i.e. the pre-integration just stored
+            const vb::init::Preint& pre = e->all_image_frame.back().pre;
+            if (pre.valid && e->initial_ex_rotation.calibrate(corres, pre.dq, W, calib_ric)) {
+                e->ric = calib_ric;
+                e->RIC = calib_ric;
+                e->ex_calib_pending = false;  // ESTIMATE_EXTRINSIC = 1
+            }
+        }
         if (e->frame_count == W) {
             bool result = false;
-            if (seeds_cover_window(e)) {
+            if (e->ex_calib_pending) {
+                // no initialisation while the rotation is unknown (estimator.cpp:163)
+            } else if (seeds_cover_window(e)) {
                 result = initial_from_seed(e);
                 e->self_initialised = false;
             } else if (stamp - e->initial_timestamp > 0.1) {
@@ -1348,7 +1370,7 @@ void destroy_member(ve_estimator* e) {
 
 int config_valid(const ve_config* cfg) {
     if (cfg->window_size < 3 || cfg->window_size + 1 > vb::BA_MAX_FRAMES || cfg->window_size + 1 > vb::BA_MAX_OBS_PER_LM ||
-        cfg->max_features < 8 || cfg->num_iterations < 1 || cfg->estimate_extrinsic > 1 || cfg->estimate_extrinsic < 0)
+        cfg->max_features < 8 || cfg->num_iterations < 1 || cfg->estimate_extrinsic > 2 || cfg->estimate_extrinsic < 0)
         return 0;
     // work arrays of the single-CTA solvers: prior of 6 W + 9 + 6 + 1 <= 160 parameters, reduced system of
     // 15 (W + 1) + 7 <= 352 columns, i.e. WINDOW_SIZE <= 22 (the reference ships 10; above 13 the reduced systems
@@ -1367,6 +1389,8 @@ ve_estimator* create_member(ve_batch* b, int k) {
     e->Ps.resize(F); e->Vs.resize(F); e->Bas.resize(F); e->Bgs.resize(F); e->Rs.resize(F);
     e->Headers.assign(F, 0.0);
     e->para_Pose.assign(F, std::array<double, 7>{0, 0, 0, 0, 0, 0, 1});
+    std::memcpy(e->RIC.m, b->cfg.ric, sizeof(e->RIC.m));
+    e->ex_calib_pending = b->cfg.estimate_extrinsic == 2;
     e->dt_buf.resize(F); e->acc_buf.resize(F); e->gyr_buf.resize(F);
     e->slot_of.resize(F); e->slot_valid.assign(F, false); e->flushed.assign(F, 0); e->sum_dt.assign(F, 0.0);
     e->lin_acc.resize(F); e->lin_gyr.resize(F); e->sqrt_dirty.assign(F, true);
@@ -1666,6 +1690,24 @@ int ve_get_relocalization(const ve_estimator* e, double* o) {
     o[21] = e->relo_frame_local_index;
     o[22] = e->n_relo_factors;
     o[23] = e->n_relo_solves;
+    return VE_OK;
+}
+
+int ve_debug_ex_rotation(int n_steps, const int* corres_off, const double* corres4, const double* dq_wxyz, int window_size, double* ric_out,
+                         int* ok_out, double* cov_out, double* rc_out, const double* rc_in) {
+    if (n_steps < 0 || !corres_off || !dq_wxyz || !ric_out || !ok_out) return VE_ERR_INVALID;
+    vb::init::ExRotation cal;
+    for (int k = 0; k < n_steps; k++) {
+        std::vector<double> c(corres4 + 4 * (size_t)corres_off[k], corres4 + 4 * (size_t)corres_off[k + 1]);
+        Mat3 out;
+        const double* q = dq_wxyz + 4 * k;
+        Mat3 given;
+        if (rc_in) std::memcpy(given.m, rc_in + 9 * k, sizeof(given.m));
+        ok_out[k] = cal.calibrate(c, Quat(q[0], q[1], q[2], q[3]), window_size, out, rc_in ? &given : nullptr) ? 1 : 0;
+        std::memcpy(ric_out + 9 * k, cal.ric.m, 9 * sizeof(double));
+        if (cov_out) cov_out[k] = cal.last_cov1;
+        if (rc_out) std::memcpy(rc_out + 9 * k, cal.Rc.back().m, 9 * sizeof(double));
+    }
     return VE_OK;
 }
 

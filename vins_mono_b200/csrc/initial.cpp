@@ -1015,3 +1015,109 @@ Mat3 g2R(const Vec3& g) {
 
 }  // namespace init
 }  // namespace vb
+
+// ---- InitialEXRotation (initial/initial_ex_rotation.cpp): camera-IMU rotation from paired camera / gyroscope rotations -------------
+namespace vb {
+namespace init {
+
+namespace {
+
+// testTriangulation (:100-126): fraction of the correspondences in front of both cameras [I | 0] and [R | t]; the projection
+// matrices pass through float like the reference's cv::Matx34f.
+double test_triangulation(const std::vector<float>& l, const std::vector<float>& r, const Mat3& R, const Vec3& t) {
+    const int n = (int)(l.size() / 2);
+    double P0[12], P1[12];
+    pose34(Mat3(), Vec3(), P0);
+    Mat3 Rf;
+    for (int k = 0; k < 9; k++) Rf.m[k] = (double)(float)R.m[k];
+    pose34(Rf, Vec3((double)(float)t.x, (double)(float)t.y, (double)(float)t.z), P1);
+    int front = 0;
+    for (int i = 0; i < n; i++) {
+        const double x0[2] = {(double)l[2 * i], (double)l[2 * i + 1]}, x1[2] = {(double)r[2 * i], (double)r[2 * i + 1]};
+        const Vec3 X = triangulate_point(P0, P1, x0, x1);  // already divided by the homogeneous coordinate
+        const double zr = P1[8] * X.x + P1[9] * X.y + P1[10] * X.z + P1[11];
+        if (X.z > 0 && zr > 0) front++;
+    }
+    return n ? 1.0 * front / n : 0.0;
+}
+
+}  // namespace
+
+Mat3 ExRotation::solve_relative_r(const std::vector<double>& corres4) const {
+    const int n = (int)(corres4.size() / 4);
+    if (n < 9) return Mat3();
+    std::vector<float> ll(2 * n), rr(2 * n);
+    for (int i = 0; i < n; i++) {
+        ll[2 * i] = (float)corres4[4 * i]; ll[2 * i + 1] = (float)corres4[4 * i + 1];
+        rr[2 * i] = (float)corres4[4 * i + 2]; rr[2 * i + 1] = (float)corres4[4 * i + 3];
+    }
+    // cv::findFundamentalMat(ll, rr): FM_RANSAC with its default threshold 3 and confidence 0.99 (on normalised coordinates every
+    // hypothesis explains every point, so the first 7-point sample wins: the reference's behaviour, reproduced with the same RNG)
+    std::vector<unsigned char> mask(n);
+    double E[9];
+    if (!vb::fundamental_ransac(ll.data(), rr.data(), n, 3.0, 0.99, mask.data(), E)) return Mat3();
+    Mat3 Em, U, V;
+    std::memcpy(Em.m, E, sizeof(Em.m));
+    svd3_proper(Em, U, V);  // det U = det V = +1: the rotations below are proper, which is what the reference's E = -E retry achieves
+    Mat3 W = mscale(Mat3(), 0.0);
+    W(0, 1) = -1; W(1, 0) = 1; W(2, 2) = 1;
+    const Mat3 R1 = U * W * V.T(), R2 = U * W.T() * V.T();
+    const Vec3 t1 = U.col(2), t2 = U.col(2) * -1.0;
+    const double ratio1 = std::max(test_triangulation(ll, rr, R1, t1), test_triangulation(ll, rr, R1, t2));
+    const double ratio2 = std::max(test_triangulation(ll, rr, R2, t1), test_triangulation(ll, rr, R2, t2));
+    const Mat3 ans = ratio1 > ratio2 ? R1 : R2;
+    return ans.T();  // ans_R_eigen(j, i) = ans_R_cv(i, j)
+}
+
+bool ExRotation::calibrate(const std::vector<double>& corres4, const Quat& delta_q_imu, int window_size, Mat3& calib_ric_result,
+                           const Mat3* rc_given) {
+    frame_count++;
+    Rc.push_back(rc_given ? *rc_given : solve_relative_r(corres4));
+    Rimu.push_back(delta_q_imu.R());
+    Rc_g.push_back(ric.T() * delta_q_imu.R() * ric);
+    double AtA[16] = {0};
+    for (int i = 1; i <= frame_count; i++) {
+        const Quat r1 = Quat::FromR(Rc[i]), r2 = Quat::FromR(Rc_g[i]);
+        // Quaterniond::angularDistance: 2 atan2(|vec(d)|, |w(d)|) of d = r1 * r2^-1
+        const Quat dq = qmul(r1, qconj(r2));
+        const double angular_distance = 180 / M_PI * 2.0 * std::atan2(std::sqrt(dq.x * dq.x + dq.y * dq.y + dq.z * dq.z), std::fabs(dq.w));
+        const double huber = angular_distance > 5.0 ? 5.0 / angular_distance : 1.0;
+        double L[16], Rm[16];
+        auto fill = [](double* M, const Quat& q, double sgn) {  // [w I + sgn [q]x, q; -q^T, w]
+            const Mat3 S = skew(Vec3(q.x, q.y, q.z));
+            for (int a = 0; a < 3; a++) {
+                for (int b = 0; b < 3; b++) M[4 * a + b] = (a == b ? q.w : 0.0) + sgn * S(a, b);
+                M[4 * a + 3] = a == 0 ? q.x : a == 1 ? q.y : q.z;
+                M[12 + a] = -(a == 0 ? q.x : a == 1 ? q.y : q.z);
+            }
+            M[15] = q.w;
+        };
+        fill(L, r1, 1.0);
+        fill(Rm, Quat::FromR(Rimu[i]), -1.0);
+        double B[16];
+        for (int k = 0; k < 16; k++) B[k] = huber * (L[k] - Rm[k]);
+        for (int a = 0; a < 4; a++)
+            for (int b = 0; b < 4; b++) {
+                double s = 0;
+                for (int k = 0; k < 4; k++) s += B[4 * k + a] * B[4 * k + b];
+                AtA[4 * a + b] += s;
+            }
+    }
+    double d[4], Vv[16];
+    jacobi_eig(AtA, 4, d, Vv);
+    int o[4] = {0, 1, 2, 3};
+    std::sort(o, o + 4, [&](int a, int b) { return d[a] > d[b]; });
+    const int s = o[3];  // smallest singular value: svd.matrixV().col(3), quaternion coefficients in (x, y, z, w) order
+    const Quat est = Quat(Vv[12 + s], Vv[0 + s], Vv[4 + s], Vv[8 + s]).normalized();
+    ric = est.R().T();
+    const double ric_cov1 = std::sqrt(std::max(d[o[2]], 0.0));  // svd.singularValues().tail<3>()(1)
+    last_cov1 = ric_cov1;
+    if (frame_count >= window_size && ric_cov1 > 0.25) {
+        calib_ric_result = ric;
+        return true;
+    }
+    return false;
+}
+
+}  // namespace init
+}  // namespace vb

@@ -105,5 +105,20 @@ Result initial_structure(std::vector<ImageFrame>& frames, const std::vector<doub
 // Utility::g2R (utility/utility.cpp:3-13)
 Mat3 g2R(const Vec3& g);
 
+// InitialEXRotation (initial/initial_ex_rotation.{h,cpp}): ESTIMATE_EXTRINSIC == 2, the camera-IMU rotation from pairs of
+// (camera rotation out of the essential matrix of consecutive frames, gyroscope rotation delta_q of the same interval):
+// q_imu (x) q_ic = q_ic (x) q_cam stacked into a 4N x 4 system with Huber weights, smallest right singular vector.
+struct ExRotation {
+    int frame_count = 0;
+    std::vector<Mat3> Rc{Mat3()}, Rimu{Mat3()}, Rc_g{Mat3()};
+    Mat3 ric;
+    double last_cov1 = 0;  // second smallest singular value of the last system (the observability test: > 0.25)
+    // CalibrationExRotation(corres, delta_q_imu, calib_ric_result): corres4 = n x (x0 y0 x1 y1) between the two newest frames
+    // (rc_given: tests hand the camera rotation in instead of extracting it from the correspondences)
+    bool calibrate(const std::vector<double>& corres4, const Quat& delta_q_imu, int window_size, Mat3& calib_ric_result,
+                   const Mat3* rc_given = nullptr);
+    Mat3 solve_relative_r(const std::vector<double>& corres4) const;
+};
+
 }  // namespace init
 }  // namespace vb

@@ -934,6 +934,11 @@ int vt_debug_fundamental_ransac(const float* pts1, const float* pts2, int n, dou
     return vb::fundamental_ransac_mask(pts1, pts2, n, threshold, confidence, status) ? 1 : 0;
 }
 
+int vt_debug_fundamental_ransac_model(const float* pts1, const float* pts2, int n, double threshold, double confidence, uint8_t* status, double* F9) {
+    if (!pts1 || !pts2 || !status || !F9 || n < 0) return VT_ERR_INVALID;
+    return vb::fundamental_ransac(pts1, pts2, n, threshold, confidence, status, F9) ? 1 : 0;
+}
+
 int vt_debug_lift_projective(const double* intrinsics8, const double* px, int n, double* out_xy) {
     if (!intrinsics8 || !px || !out_xy || n < 0) return VT_ERR_INVALID;
     vt_config c{};

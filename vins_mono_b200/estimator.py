@@ -68,6 +68,7 @@ def _bind(lib):
     lib.ve_debug_imu_factor.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ve_init_info.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ve_debug_ex_rotation.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ve_set_relo_frame.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ve_get_relocalization.argtypes = [C.c_void_p, C.c_void_p]
     lib.ve_debug_relative_rt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
@@ -406,3 +407,20 @@ def debug_initial_structure(headers, frames, tracks, ric, tic, g_norm=9.81007, f
         raise RuntimeError(f"ve_debug_initial_structure: {rc}")
     return dict(code=rc, l=int(info[0]), R=fR.reshape(na, 3, 3), T=fT, x=x, g=g3, delta_bg=dbg, bundle_iterations=int(info[1]),
                 bundle_cost=cost.value, key_frames=int(info[2]))
+
+
+def debug_ex_rotation(corres_list, dq_list, window_size=10, rc_given=None):
+    """InitialEXRotation::CalibrationExRotation called once per (corres[n,4], delta_q wxyz) pair: (ric[k,3,3], ok[k], cov[k], Rc[k,3,3] = the camera rotations solveRelativeR found)."""
+    lib = load_library()
+    _bind(lib)
+    n = len(corres_list)
+    off = np.zeros(n + 1, np.int32)
+    off[1:] = np.cumsum([len(np.asarray(c).reshape(-1, 4)) for c in corres_list])
+    c4 = _d(np.concatenate([np.asarray(c, float).reshape(-1, 4) for c in corres_list])) if n else np.zeros((0, 4))
+    dq = _d(dq_list).reshape(-1, 4)
+    ric, ok, cov, rcam = np.zeros((n, 9)), np.zeros(n, np.int32), np.zeros(n), np.zeros((n, 9))
+    rc = lib.ve_debug_ex_rotation(n, _p(off), _p(c4), _p(dq), int(window_size), _p(ric), _p(ok), _p(cov), _p(rcam),
+                                  _p(_d(rc_given).reshape(-1, 9)) if rc_given is not None else None)
+    if rc < 0:
+        raise RuntimeError(f"ve_debug_ex_rotation: {rc}")
+    return ric.reshape(n, 3, 3), ok.astype(bool), cov, rcam.reshape(n, 3, 3)
