@@ -528,6 +528,8 @@ __device__ __forceinline__ void store_sym(const BaProblem& p, int r, int c, doub
 // fixed order.
 constexpr int RED_SLICES = 7;
 constexpr int RED_SLAB = 1024;
+// RELO = false is the kernel of frames without a relocalisation block (the usual case): no match-row bookkeeping at all.
+template <bool RELO>
 __global__ void __launch_bounds__(RED_THREADS, 3) ba_reduce_kernel(const BaSeq* __restrict__ seqs, int n_pairs_max) {
     __shared__ BaProblem sp;
     __shared__ int pinv[RED_MAXD];
@@ -571,10 +573,10 @@ __global__ void __launch_bounds__(RED_THREADS, 3) ba_reduce_kernel(const BaSeq* 
             for (int k = tid; k < nl; k += RED_THREADS) {
                 const int l = l0 + k, s0 = p.lm_start[l];
                 const int an = p.lm_anchor[l];
-                const int rl = d.col_relo >= 0 ? p.lm_relo[l] : 0;
+                const int rl = RELO && d.col_relo >= 0 ? p.lm_relo[l] : 0;
                 s_an[k] = (short)an;
                 s_nobs[k] = (short)(p.lm_start[l + 1] - s0 - rl);  // the track; a relocalisation match is the row behind it
-                s_rl[k] = (unsigned char)rl;
+                if (RELO) s_rl[k] = (unsigned char)rl;
                 s_s0[k] = s0;
                 s_inv[k] = lm_inv_lambda(p, a, l, mu, first);
                 if (k > 0 && p.lm_anchor[l - 1] > an) unsorted = 1;
@@ -648,7 +650,7 @@ __global__ void __launch_bounds__(RED_THREADS, 3) ba_reduce_kernel(const BaSeq* 
             } else if (worker || gworker) {
 #pragma unroll 4
                 for (int k = slice; k < nl; k += RED_SLICES) {
-                    const int an = s_an[k], nobs = s_nobs[k], s0 = s_s0[k], rl = s_rl[k];
+                    const int an = s_an[k], nobs = s_nobs[k], s0 = s_s0[k], rl = RELO ? s_rl[k] : 0;
                     if (!lm_covers(A, an, nobs, rl) || !lm_covers(B, an, nobs, rl)) continue;
                     const double* rec = a.lmW + (size_t)(l0 + k) * lw;
                     const double inv = s_inv[k];

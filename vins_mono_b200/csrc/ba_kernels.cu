@@ -1613,8 +1613,9 @@ void launch_ba_solve(BaSeq* seqs, const BatchShape& sh, cudaStream_t s, int* lau
     dmax.L = sh.max_L;
     dmax.W = sh.W;
     const int eval_grid = ba_eval_grid(dmax);
-    // pose-type blocks incl. the slot of a relocalisation pose (CTAs of pairs a member does not have return at once)
-    const int NV = sh.W + 1 + (sh.est_ex ? 1 : 0) + (sh.est_td ? 1 : 0) + 1, n_pairs = NV * (NV + 1) / 2;
+    // pose-type blocks, incl. the relocalisation pose when a member of this frame has one (CTAs of pairs a member does not
+    // have return at once)
+    const int NV = sh.W + 1 + (sh.est_ex ? 1 : 0) + (sh.est_td ? 1 : 0) + (sh.any_relo ? 1 : 0), n_pairs = NV * (NV + 1) / 2;
     const int generic = (sh.D * (sh.D + 1) / 2 + 4 * RED_THREADS - 1) / (4 * RED_THREADS);
     const size_t panel_bytes = sizeof(double) * CHOL_NB * CHOL_PS;
     const size_t chol_bytes = sizeof(double) * (size_t)(sh.D + 1) * (sh.D + 2) / 2 + panel_bytes;
@@ -1637,7 +1638,8 @@ void launch_ba_solve(BaSeq* seqs, const BatchShape& sh, cudaStream_t s, int* lau
     n += 1;
     for (int it = 0; it < sh.max_iterations; it++) {
         prof->begin(s);
-        ba_reduce_kernel<<<dim3(n_pairs + generic, sh.S), RED_THREADS, 0, s>>>(seqs, n_pairs);
+        if (sh.any_relo) ba_reduce_kernel<true><<<dim3(n_pairs + generic, sh.S), RED_THREADS, 0, s>>>(seqs, n_pairs);
+        else ba_reduce_kernel<false><<<dim3(n_pairs + generic, sh.S), RED_THREADS, 0, s>>>(seqs, n_pairs);
         prof->end(1, s);
         prof->begin(s);
         ba_step_kernel<<<sh.S, 512, step_dyn, s>>>(seqs, use_smem);

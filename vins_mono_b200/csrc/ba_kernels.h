@@ -17,6 +17,7 @@ struct BatchShape {  // host-side maxima over the members of this frame: grid an
     int max_md, max_n;   // marginalisation: dense marginalised columns, kept columns
     int max_P;           // marginalisation system size
     int any_jobs, any_active, any_marg;
+    int any_relo;        // some member carries a relocalisation pose block this frame (its block pairs get CTAs)
     int est_ex, est_td;  // which optional parameter blocks are live (uniform over the batch: selects the kernel variants)
     int max_iterations;
     int w_in_global;     // marginalisation reduced system in global memory (decided once per batch: marg_w_in_global)

@@ -1291,6 +1291,7 @@ int batch_process(ve_batch* b, const FrameMsg* msgs, int* status_out) {
             sh.any_active = 1;
             sh.max_L = std::max(sh.max_L, q.p.dims.L);
             sh.D = std::max(sh.D, q.p.dims.D);
+            if (q.p.dims.col_relo >= 0) sh.any_relo = 1;
             if (q.do_marg) {
                 sh.any_marg = 1;
                 sh.max_n_lm = std::max(sh.max_n_lm, q.mp.n_lm);
