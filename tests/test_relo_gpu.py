@@ -131,3 +131,51 @@ def test_relocalisation_stamp_outside_window_is_ignored():
         feeder.feed(ref, stamp)
         ref.processImage(ids, d, stamp)
     assert np.array_equal(ref.states()[0], gpu.states()[0])  # bit-identical: no trace of the ignored message
+
+
+def test_relocalisation_inside_a_batch():
+    """One member of a batch receives loop messages, its neighbours do not: the frame runs the relocalisation variant of the gather
+    for everybody.  Every member must come out bit-identical to a stand-alone estimator fed the same way."""
+    from vins_mono_b200 import Estimator, EstimatorBatch
+    seq = synth.Sequence(seed=0, duration=5.0)
+    msgs = synth.track_messages(seq, 36, max_feats=120)
+    seeds = pipeline.gt_seed_rows(seq, [m[0] for m in msgs])
+    t_imu, acc, gyr = seq.imu()
+    relo_at, D, td_ = (28, 29, 31), rz(np.radians(5.0)), np.array([0.2, 0.1, -0.1])
+
+    def loop_args(k):
+        j = k - 10 + 4
+        mp, p_old, R_old = synth.loop_frame_matches(seq, 1.2, msgs[j][1], pixel_sigma=0.3, seed=k)
+        return msgs[j][0], 9, mp, D @ p_old + td_, D @ R_old
+
+    solo = {}
+    for with_relo in (False, True):
+        e = Estimator(tic=synth.TIC, ric=synth.RIC)
+        e.set_seed(seeds, seq.ba, seq.bg)
+        f = pipeline.ImuFeeder(t_imu, acc, gyr)
+        for k, (stamp, ids, d) in enumerate(msgs):
+            f.feed(e, stamp)
+            if with_relo and k in relo_at:
+                assert e.setReloFrame(*loop_args(k))
+            e.processImage(ids, d, stamp)
+        solo[with_relo] = (e.states()[0].copy(), e.relo())
+        e.close()
+    assert solo[True][1]["solves"] == 3 and solo[False][1]["solves"] == 0
+    assert not np.array_equal(solo[True][0], solo[False][0])  # the loop factors do move the window
+
+    eb = EstimatorBatch(3, tic=synth.TIC, ric=synth.RIC)
+    feeders = [pipeline.ImuFeeder(t_imu, acc, gyr) for _ in range(3)]
+    for m in eb.members:
+        m.set_seed(seeds, seq.ba, seq.bg)
+    for k, (stamp, ids, d) in enumerate(msgs):
+        for m, f in zip(eb.members, feeders):
+            f.feed(m, stamp)
+        if k in relo_at:
+            assert eb.members[1].setReloFrame(*loop_args(k))
+        assert not eb.processImage([(ids, d, stamp)] * 3).any()
+    for j, with_relo in enumerate((False, True, False)):
+        assert np.array_equal(eb.members[j].states()[0], solo[with_relo][0]), j
+    r = eb.members[1].relo()
+    assert r["solves"] == 3 and np.array_equal(r["drift_correct_t"], solo[True][1]["drift_correct_t"])
+    assert eb.members[0].relo()["solves"] == 0
+    eb.close()

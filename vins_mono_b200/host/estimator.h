@@ -39,6 +39,8 @@ struct Vector3d {
     double x() const { return v[0]; }
     double y() const { return v[1]; }
     double z() const { return v[2]; }
+    Vector3d operator+(const Vector3d& o) const { return Vector3d(v[0] + o.v[0], v[1] + o.v[1], v[2] + o.v[2]); }
+    Vector3d operator-(const Vector3d& o) const { return Vector3d(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
 };
 struct Matrix3d {
     double m[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};

@@ -51,6 +51,11 @@ int main() {
         const double camx = cam[0] + estimator.tic[0][0];
         std::vector<Vector3d> match_points;
         estimator.setReloFrame(0.05, 3, match_points, Vector3d(0, 0, 0), tmp_R);
+        // what pubRelocalization / pubOdometry read after a loop message (utility/visualization.cpp:130-131, 326-350)
+        Vector3d correct_t = estimator.drift_correct_r * estimator.Ps[WINDOW_SIZE] + estimator.drift_correct_t;
+        const double relo_sum = correct_t[0] + estimator.relo_relative_t[1] + estimator.relo_relative_q[0] + estimator.relo_relative_yaw +
+                                estimator.relo_frame_index + estimator.relo_frame_stamp + (estimator.relocalization_info ? 1.0 : 0.0);
+        (void)relo_sum;
         const bool nonlinear = estimator.solver_flag == vinsb200::Estimator::SolverFlag::NON_LINEAR;
         estimator.clearState();
         estimator.setParameter();
