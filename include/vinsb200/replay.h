@@ -97,6 +97,19 @@ int vr_format_result_row(double stamp, const double* P3, const double* Qwxyz, co
 int vr_decode_pointcloud(int n, const float* xyz, const float* id_of_point, const float* u_of_point, const float* v_of_point,
                          const float* velocity_x, const float* velocity_y, int* feature_ids, int* camera_ids, double* obs7);
 
+/* Relocalisation messages (the pose_graph coupling; estimator_node.cpp:200-206, 266-291).
+ *   vr_decode_relo_message   a /pose_graph/match_points PointCloud -> the arguments of setReloFrame: points (x, y, z = feature id)
+ *                            -> match_points (n x 3 doubles); channels[0].values[0..2] = relo_t, [3..6] = relo_q (w x y z, turned
+ *                            into relo_r like Quaterniond::toRotationMatrix, i.e. without normalising), [7] = frame_index; the
+ *                            message's header stamp is the frame_stamp.  Returns n or -1.
+ *   vr_queue_relo            puts a message into sequence seq's relo_buf with an arrival time: before the first image whose stamp is
+ *                            >= arrival_stamp is processed, every message that has arrived is popped and the LAST one goes to
+ *                            ve_set_relo_frame, exactly as process() does.  Call between vr_advance calls (not concurrently). */
+int vr_decode_relo_message(int n, const float* xyz, const float* channel0_values8, double* match_points, double* relo_t3, double* relo_r9,
+                           int* frame_index);
+int vr_queue_relo(vr_session* s, int seq, double arrival_stamp, double frame_stamp, int frame_index, int n, const double* match_points,
+                  const double* relo_t3, const double* relo_r9);
+
 #ifdef __cplusplus
 }
 #endif

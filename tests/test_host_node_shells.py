@@ -100,3 +100,24 @@ def test_pointcloud_decoding():
     assert np.array_equal(obs[:, 0:3], xyz.astype(np.float64)) and np.array_equal(obs[:, 3], u) and np.array_equal(obs[:, 6], vy)
     xyz[2, 2] = 0.5   # the node asserts z == 1
     assert lib.vr_decode_pointcloud(n, _p(xyz), _p(idp), _p(u), _p(v), _p(vx), _p(vy), _p(ids), _p(cams), _p(obs)) == -1
+
+
+def test_relo_message_decoding():
+    """estimator_node.cpp:273-291: match_points PointCloud -> (match_points, relo_t, relo_r, frame_index)."""
+    lib = _lib()
+    lib.vr_decode_relo_message.argtypes = [C.c_int] + [C.c_void_p] * 6
+    rng = np.random.default_rng(2)
+    n = 17
+    xyz = np.c_[rng.uniform(-0.5, 0.5, (n, 2)), np.sort(rng.integers(0, 4000, n))].astype(np.float32)
+    q = rng.normal(0, 1, 4)
+    q /= np.linalg.norm(q)
+    ch = np.r_[rng.normal(0, 2, 3), q, 41.0].astype(np.float32)
+    mp, t3, r9, idx = np.zeros((n, 3)), np.zeros(3), np.zeros(9), C.c_int()
+    assert lib.vr_decode_relo_message(n, _p(xyz), _p(ch), _p(mp), _p(t3), _p(r9), C.byref(idx)) == n
+    assert np.array_equal(mp, xyz.astype(np.float64)) and np.array_equal(t3, ch[:3].astype(np.float64)) and idx.value == 41
+    w, x, y, z = ch[3:7].astype(np.float64)
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    assert np.abs(r9.reshape(3, 3) - R).max() < 1e-15
+    assert lib.vr_decode_relo_message(n, None, _p(ch), _p(mp), _p(t3), _p(r9), None) == -1

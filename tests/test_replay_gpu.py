@@ -53,3 +53,42 @@ def test_replay_matches_python_loop_and_replicas_agree():
     for t, e in pairs:
         t.close()
         e.close()
+
+
+def test_replay_delivers_queued_relocalisation_messages():
+    """vr_queue_relo: a loop message queued for a sequence reaches setReloFrame before the first image at or after its arrival time
+    (process() drains relo_buf and keeps the last message, estimator_node.cpp:266-291).  The matches are made for the ids the tracker
+    assigned in a first pass over the same images (the tracker is deterministic)."""
+    from harness import synth, pipeline
+    from vins_mono_b200 import FeatureTracker, Estimator, ReplaySession
+    n_pub = 22
+    n_img = 2 * (n_pub + 1) + 2
+    seq = synth.Sequence(seed=3, duration=n_img / 20.0 + 0.5)
+    ts, imgs = pipeline.cached_images(seq, n_img)
+    imgs = np.ascontiguousarray(imgs)
+    t_imu, acc, gyr = seq.imu()
+    seed = pipeline.gt_seed_rows(seq, ts)
+    trk = FeatureTracker(**synth.tracker_config_dict())
+    msgs = list(pipeline.feature_messages(trk, ts, imgs))[:n_pub]
+    trk.close()
+    # loop message for the frame of published message 15, arriving just before message 19: its own observations shifted by a
+    # small in-plane motion stand in for the old key frame's view (only the delivery is under test here)
+    stamp15, ids15, d15 = msgs[15]
+    mp = np.c_[d15[:, 0] + 0.01, d15[:, 1] - 0.005, np.asarray(ids15, float)]
+    mp = mp[np.argsort(mp[:, 2])]
+
+    t = FeatureTracker(**synth.tracker_config_dict())
+    e = Estimator(tic=synth.TIC, ric=synth.RIC)
+    e.set_seed(seed, seq.ba, seq.bg)
+    ses = ReplaySession([t], [e], [dict(images=imgs, stamps=ts, imu_t=t_imu, acc=acc, gyr=gyr)])
+    ses.queue_relo(0, msgs[18][0] + 1e-4, 0.0, 1, mp[:3], np.zeros(3), np.eye(3))        # superseded by the next one (same drain)
+    ses.queue_relo(0, msgs[18][0] + 2e-4, stamp15, 5, mp, np.array([0.1, 0.2, 0.3]), np.eye(3))
+    assert ses.advance(19) == 19
+    assert e.relo()["solves"] == 0 and not e.relo()["pending"]     # not yet delivered (arrival is after message 18's stamp)
+    assert ses.advance(1) == 1
+    r = e.relo()
+    assert r["solves"] == 1 and r["factors"] >= 10 and not r["pending"]
+    assert ses.advance(n_pub - 20) == n_pub - 20 and e.relo()["solves"] == 1
+    ses.close()
+    t.close()
+    e.close()

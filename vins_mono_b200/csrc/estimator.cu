@@ -814,7 +814,10 @@ int stage_frame(ve_estimator* e, bool solve) {
                 relo_match.push_back(hit);
             }
         }
-        e->fr_relo = relo;
+        // No matched landmark: Ceres drops a parameter block without residuals from the program, so the solve is the plain one;
+        // the message is consumed (relo_Pose, hence the drift outputs, stay as they are).
+        e->fr_relo = relo && n_relo > 0;
+        if (relo && n_relo == 0) e->relocalization_info = false;
         e->n_relo_factors = n_relo;
         const int rc = plan_marginalization(e, mp, mh);
         if (rc) return rc;

@@ -60,6 +60,13 @@ struct SeqState {
     long long launches = 0;
     double h2d = 0, d2h = 0;
     std::vector<double> traj_t, traj_p;
+    struct ReloMsg {  // a /pose_graph/match_points message waiting in relo_buf (estimator_node.cpp:22, 200-206)
+        double arrival, frame_stamp;
+        int frame_index;
+        std::vector<double> match_points;  // x, y, feature id
+        double relo_t[3], relo_r[9];
+    };
+    std::deque<ReloMsg> relo_buf;
     Channel ch;
     // scratch
     std::vector<float> f_xy, f_id, f_u, f_v, f_vx, f_vy;
@@ -218,6 +225,22 @@ void collect_imu(SeqState* q, double stamp) {
     if (q->imu_k < q->in.n_imu) imu_one(q, q->imu_k, stamp);  // used, but stays in the buffer
 }
 
+// process(): "set relocalization frame" (estimator_node.cpp:266-291): every message that has arrived by now is popped, the LAST
+// one is handed to setReloFrame.
+void apply_relo(SeqState* q, double now) {
+    const SeqState::ReloMsg* last = nullptr;
+    size_t n_pop = 0;
+    for (auto& m : q->relo_buf) {
+        if (m.arrival > now) break;
+        last = &m;
+        n_pop++;
+    }
+    if (last)
+        ve_set_relo_frame(q->est, last->frame_stamp, last->frame_index, (int)(last->match_points.size() / 3), last->match_points.data(),
+                          last->relo_t, last->relo_r);
+    for (size_t k = 0; k < n_pop; k++) q->relo_buf.pop_front();
+}
+
 void estimator_loop(vr_session* s, SeqState* q) {
     for (;;) {
         FeatureMsg msg = q->ch.get();
@@ -232,6 +255,7 @@ void estimator_loop(vr_session* s, SeqState* q) {
             ve_get_states(q->est, q->states.data(), &td);
             collect_imu(q, msg.stamp + td);
             int rc = q->dt.empty() ? 0 : ve_process_imu_batch(q->est, (int)q->dt.size(), q->dt.data(), q->acc.data(), q->gyr.data());
+            apply_relo(q, msg.stamp);
             if (rc == 0) rc = ve_process_image(q->est, (int)msg.ids.size(), msg.ids.data(), msg.obs.data(), msg.stamp);
             if (rc < 0) {
                 s->fail(rc, std::string("estimator: ") + ve_last_error(q->est));
@@ -396,6 +420,7 @@ void estimator_batch_loop(vr_session* s) {
                 s->fail(rc, std::string("estimator: ") + ve_last_error(q.est));
                 break;
             }
+            apply_relo(&q, msg.stamp);
             active[k] = 1;
             n[k] = (int)msg.ids.size();
             ids[k] = msg.ids.data();
@@ -646,6 +671,44 @@ int vr_decode_pointcloud(int n, const float* xyz, const float* id_of_point, cons
         o[6] = velocity_y[i];
     }
     return n;
+}
+
+int vr_decode_relo_message(int n, const float* xyz, const float* channel0_values8, double* match_points, double* relo_t3, double* relo_r9,
+                           int* frame_index) {
+    if (n < 0 || (n && (!xyz || !match_points)) || !channel0_values8 || !relo_t3 || !relo_r9) return -1;
+    for (int i = 0; i < n; i++) {  // u_v_id = (points[i].x, points[i].y, points[i].z)
+        match_points[3 * i] = xyz[3 * i];
+        match_points[3 * i + 1] = xyz[3 * i + 1];
+        match_points[3 * i + 2] = xyz[3 * i + 2];
+    }
+    const float* c = channel0_values8;
+    for (int k = 0; k < 3; k++) relo_t3[k] = c[k];
+    // Quaterniond relo_q(values[3], values[4], values[5], values[6]) = (w, x, y, z); toRotationMatrix() does not normalise
+    const double w = c[3], x = c[4], y = c[5], z = c[6];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z, twx = tx * w, twy = ty * w, twz = tz * w;
+    const double txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    relo_r9[0] = 1 - (tyy + tzz); relo_r9[1] = txy - twz; relo_r9[2] = txz + twy;
+    relo_r9[3] = txy + twz; relo_r9[4] = 1 - (txx + tzz); relo_r9[5] = tyz - twx;
+    relo_r9[6] = txz - twy; relo_r9[7] = tyz + twx; relo_r9[8] = 1 - (txx + tyy);
+    if (frame_index) *frame_index = (int)c[7];
+    return n;
+}
+
+int vr_queue_relo(vr_session* s, int seq, double arrival_stamp, double frame_stamp, int frame_index, int n, const double* match_points,
+                  const double* relo_t3, const double* relo_r9) {
+    if (!s || seq < 0 || seq >= (int)s->seqs.size() || n < 0 || (n && !match_points) || !relo_t3 || !relo_r9) return -1;
+    SeqState::ReloMsg m;
+    m.arrival = arrival_stamp;
+    m.frame_stamp = frame_stamp;
+    m.frame_index = frame_index;
+    m.match_points.assign(match_points, match_points + 3 * (size_t)n);
+    std::memcpy(m.relo_t, relo_t3, sizeof(m.relo_t));
+    std::memcpy(m.relo_r, relo_r9, sizeof(m.relo_r));
+    auto& buf = s->seqs[seq].relo_buf;  // kept in arrival order
+    auto it = buf.end();
+    while (it != buf.begin() && (it - 1)->arrival > arrival_stamp) --it;
+    buf.insert(it, std::move(m));
+    return 0;
 }
 
 int vr_stats(const vr_session* s, int seq, int* frames, long long* launches, double* h2d_bytes, double* d2h_bytes) {

@@ -71,6 +71,18 @@ class ReplaySession:
             raise RuntimeError(f"vr_advance: {self.lib.vr_last_error(self.h).decode()} ({r})")
         return r
 
+    def queue_relo(self, seq: int, arrival_stamp, frame_stamp, frame_index, match_points, relo_t, relo_r):
+        """A /pose_graph/match_points message for sequence seq (vr_queue_relo): applied before the first image at or after
+        arrival_stamp, like process() drains relo_buf (estimator_node.cpp:266-291).  Not concurrently with advance()."""
+        mp = np.ascontiguousarray(match_points, np.float64).reshape(-1, 3)
+        t3 = np.ascontiguousarray(relo_t, np.float64).reshape(3)
+        r9 = np.ascontiguousarray(relo_r, np.float64).reshape(9)
+        self.lib.vr_queue_relo.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = self.lib.vr_queue_relo(self.h, seq, float(arrival_stamp), float(frame_stamp), int(frame_index), len(mp),
+                                    mp.ctypes.data_as(C.c_void_p), t3.ctypes.data_as(C.c_void_p), r9.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RuntimeError(f"vr_queue_relo: {rc}")
+
     def stats(self, seq: int):
         f, l, a, b = C.c_int(0), C.c_longlong(0), C.c_double(0), C.c_double(0)
         self.lib.vr_stats(self.h, seq, C.byref(f), C.byref(l), C.byref(a), C.byref(b))
