@@ -193,6 +193,8 @@ int ve_debug_initial_structure(int F, const double* headers, int n_all, const do
  *   ve_get_relocalization   out24 = drift_correct_r 9 (row-major) | drift_correct_t 3 | relo_relative_t 3 | relo_relative_q wxyz |
  *                           relo_relative_yaw (degrees) | relocalization_info still pending | relo_frame_local_index |
  *                           relocalisation factors of the last solve | solves that carried a relocalisation block. */
+/* Headers[0 .. WINDOW_SIZE] as stamps in seconds (estimator.h:70): what setReloFrame compares frame_stamp with. */
+int ve_get_headers(const ve_estimator* e, double* stamps);
 int ve_set_relo_frame(ve_estimator* e, double frame_stamp, int frame_index, int n, const double* match_points, const double* relo_t,
                       const double* relo_r);
 int ve_get_relocalization(const ve_estimator* e, double* out24);

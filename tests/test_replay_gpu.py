@@ -71,9 +71,21 @@ def test_replay_delivers_queued_relocalisation_messages():
     trk = FeatureTracker(**synth.tracker_config_dict())
     msgs = list(pipeline.feature_messages(trk, ts, imgs))[:n_pub]
     trk.close()
-    # loop message for the frame of published message 15, arriving just before message 19: its own observations shifted by a
-    # small in-plane motion stand in for the old key frame's view (only the delivery is under test here)
-    stamp15, ids15, d15 = msgs[15]
+    # which frames are in the window when message 19 arrives: a Python-driven pass over messages 0 .. 18 (deterministic)
+    probe = Estimator(tic=synth.TIC, ric=synth.RIC)
+    probe.set_seed(seed, seq.ba, seq.bg)
+    feeder = pipeline.ImuFeeder(t_imu, acc, gyr)
+    for k, (stamp, ids, d) in enumerate(msgs[:19]):
+        if k == 0:
+            continue  # the node drops the first feature message
+        feeder.feed(probe, stamp)
+        probe.processImage(ids, d, stamp)
+    window = probe.headers()[:-1]
+    probe.close()
+    j = next(k for k in range(16, 8, -1) if np.any(window == msgs[k][0]))   # a frame a few places back in the window
+    # loop message for that frame, arriving just before message 19: its own observations shifted by a small in-plane motion stand
+    # in for the old key frame's view (only the delivery is under test here)
+    stamp15, ids15, d15 = msgs[j]
     mp = np.c_[d15[:, 0] + 0.01, d15[:, 1] - 0.005, np.asarray(ids15, float)]
     mp = mp[np.argsort(mp[:, 2])]
 

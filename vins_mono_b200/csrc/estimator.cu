@@ -1683,6 +1683,12 @@ int ve_set_relo_frame(ve_estimator* e, double frame_stamp, int frame_index, int 
     return found;
 }
 
+int ve_get_headers(const ve_estimator* e, double* stamps) {
+    if (!e || !stamps) return VE_ERR_INVALID;
+    for (int i = 0; i <= e->W; i++) stamps[i] = e->Headers[i];
+    return VE_OK;
+}
+
 int ve_get_relocalization(const ve_estimator* e, double* o) {
     if (!e || !o) return VE_ERR_INVALID;
     std::memcpy(o, e->drift_correct_r.m, 9 * sizeof(double));

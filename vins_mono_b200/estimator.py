@@ -71,6 +71,7 @@ def _bind(lib):
     lib.ve_debug_ex_rotation.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ve_set_relo_frame.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ve_get_relocalization.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ve_get_headers.argtypes = [C.c_void_p, C.c_void_p]
     lib.ve_debug_relative_rt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
     lib.ve_debug_solve_pnp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.ve_debug_sfm_construct.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_double] + \
@@ -133,6 +134,12 @@ class Estimator:
         mp = _d(match_points).reshape(-1, 3)
         return bool(self._check(self.lib.ve_set_relo_frame(self.h, float(frame_stamp), int(frame_index), len(mp), _p(mp), _p(_d(relo_t)),
                                                            _p(_d(relo_r).reshape(9)))))
+
+    def headers(self):
+        """Stamps of the window frames (Headers[0 .. WINDOW_SIZE])."""
+        h = np.zeros(self.W + 1)
+        self._check(self.lib.ve_get_headers(self.h, _p(h)))
+        return h
 
     def relo(self):
         o = np.zeros(24)
