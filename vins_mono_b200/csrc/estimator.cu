@@ -1409,7 +1409,7 @@ ve_estimator* create_member(ve_batch* b, int k) {
     for (int k2 = 0; k2 < 2 && ok; k2++)
         ok = e->d_acc[k2].alloc(acc_doubles(e)) == cudaSuccess &&
              e->d_prior[k2].alloc((size_t)e->nmax * e->nmax + e->nmax + 1 + 9 * vb::BA_MAX_PRIOR_BLOCKS) == cudaSuccess;
-    ok = ok && e->d_S.alloc((size_t)e->D * e->D) == cudaSuccess && e->d_Spk.alloc((size_t)e->D * (e->D + 1) / 2) == cudaSuccess &&
+    ok = ok && e->d_S.alloc((size_t)e->D * e->D) == cudaSuccess && e->d_Spk.alloc((size_t)e->D * (e->D + 1) / 2 + 2)  /* + slack: ba_step's bulk copy rounds an odd count up by one double */ == cudaSuccess &&
          e->d_Hfull.alloc((size_t)e->D * e->D) == cudaSuccess && e->d_gred.alloc(e->D) == cudaSuccess &&
          e->d_vec.alloc(4 * ((size_t)e->D + e->Lmax)) == cudaSuccess && e->d_work.alloc(vb::ba_work_doubles(e->D, e->Lmax)) == cudaSuccess &&
          e->d_marg.alloc(Pm * Pm + Pm + (size_t)e->nmax * e->nmax + e->nmax + 8 + ((size_t)e->nmax + 15) * (e->nmax + 15)) == cudaSuccess;
