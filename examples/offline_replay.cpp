@@ -8,8 +8,9 @@
 //   frames.u8    n_images * rows * cols bytes, row-major grayscale
 //   stamps.txt   n_images image time stamps [s], one per line
 //   imu.txt      t ax ay az gx gy gz per line (accelerometer m/s^2, gyroscope rad/s)
-//   seed.txt     t px py pz qw qx qy qz vx vy vz per line + last line "bias bax bay baz bgx bgy bgz"
-//                (stand-in for the reference's initialStructure(): see ve_set_seed in estimator.h)
+//   seed.txt     OPTIONAL: t px py pz qw qx qy qz vx vy vz per line + last line "bias bax bay baz bgx bgy bgz", an external
+//                initial window handed to ve_set_seed; without the file the estimator runs its own initialStructure()
+//                (relative pose, global SfM, visual-inertial alignment) like the reference
 // [copies] > 1 runs that many replicas concurrently on the GPU (throughput experiments).
 // Camera / noise parameters are the EuRoC ones of config/euroc/euroc_config.yaml.
 //
@@ -46,7 +47,7 @@ int main(int argc, char** argv) {
     const int copies = argc > 2 ? std::max(1, std::atoi(argv[2])) : 1;
     std::vector<double> meta, stamps, imu, seed;
     if (!read_numbers(dir + "/meta.txt", meta) || meta.size() < 3 || !read_numbers(dir + "/stamps.txt", stamps) ||
-        !read_numbers(dir + "/imu.txt", imu) || !read_numbers(dir + "/seed.txt", seed)) {
+        !read_numbers(dir + "/imu.txt", imu)) {
         std::fprintf(stderr, "cannot read the sequence files in %s\n", dir.c_str());
         return 2;
     }
@@ -68,8 +69,9 @@ int main(int argc, char** argv) {
             gyr[3 * k + c] = imu[7 * k + 4 + c];
         }
     }
-    const int n_seed = ((int)seed.size() - 6) / 11;
-    const double* bias = seed.data() + 11 * (size_t)n_seed;
+    const bool have_seed = read_numbers(dir + "/seed.txt", seed) && seed.size() >= 17;
+    const int n_seed = have_seed ? ((int)seed.size() - 6) / 11 : 0;
+    const double* bias = have_seed ? seed.data() + 11 * (size_t)n_seed : nullptr;
 
     vt_config tc{};
     tc.rows = rows; tc.cols = cols; tc.max_cnt = 150; tc.min_dist = 30; tc.freq = 10; tc.equalize = 1;
@@ -93,7 +95,7 @@ int main(int argc, char** argv) {
             std::fprintf(stderr, "no usable CUDA device (this library has no CPU path)\n");
             return 1;
         }
-        ve_set_seed(est[k], n_seed, seed.data(), bias, bias + 3);
+        if (have_seed) ve_set_seed(est[k], n_seed, seed.data(), bias, bias + 3);
         vr_sequence& s = seqs[k];
         s.images = frames.data();
         s.row_stride = (size_t)cols;
@@ -117,6 +119,12 @@ int main(int argc, char** argv) {
     }
     std::printf("# %d published frames over %d sequence(s) in %.3f s (%.1f frames/s, host images)\n", frames_done, copies, sec,
                 frames_done / sec);
+    {
+        double ii[8];
+        const int self = ve_init_info(est[0], ii);
+        std::printf("# initial window: %s (reference frame l = %d, scale %.4f, failed attempts %d)\n",
+                    self == 1 ? "own initialStructure" : "seed.txt", (int)ii[0], ii[1], (int)ii[7]);
+    }
     const int n = vr_trajectory(ses, 0, 0, nullptr, nullptr);
     std::vector<double> tt(n), pp(3 * (size_t)n);
     vr_trajectory(ses, 0, n, tt.data(), pp.data());

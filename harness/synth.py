@@ -5,7 +5,8 @@ body flying a smooth analytic trajectory inside a textured box room.  Calibratio
 imu-camera extrinsics, IMU noise densities, gravity) is the reference's EuRoC configuration
 (config/euroc/euroc_config.yaml:9-42,59-63).  The trajectory is analytic (sums of sinusoids with
 EuRoC-like extents/speeds) so position, velocity, acceleration and body rates are exact; SURVEY.md
-proposed replaying the EuRoC ground-truth CSVs, which do not travel to the GPU box.
+proposed replaying the EuRoC ground-truth CSVs, which do not travel to the GPU box (harness/euroc_format.py reads and writes the
+dataset's ASL directory layout, so a downloaded sequence or an exported synthetic one feeds the same replay driver).
 
 IMU model (the one Estimator::processIMU inverts, vins_estimator/src/estimator.cpp:107-114):
     acc = R_wb^T (a_w + g) + b_a + n_a,   gyr = w_b + b_g + n_g,   g = (0, 0, 9.81007).
