@@ -193,6 +193,13 @@ int ve_debug_initial_structure(int F, const double* headers, int n_all, const do
  *   ve_get_relocalization   out24 = drift_correct_r 9 (row-major) | drift_correct_t 3 | relo_relative_t 3 | relo_relative_q wxyz |
  *                           relo_relative_yaw (degrees) | relocalization_info still pending | relo_frame_local_index |
  *                           relocalisation factors of the last solve | solves that carried a relocalisation block. */
+/* f_manager.feature (feature_manager.h:48-72) as the publishers read it (visualization.cpp:228-296 pubPointCloud, :352-397
+ * pubKeyframe): per feature its id, start_frame, solve_flag, estimated_depth and the observations of its consecutive frames
+ * (obs5 = point x y z | uv) through obs_offset (cap_features + 1 entries).  Returns the number of features; call with both
+ * capacities 0 for that count alone; -(count) - 1 when a capacity is too small (an observation capacity of
+ * count x (WINDOW_SIZE + 1) always suffices). */
+int ve_get_features(const ve_estimator* e, int cap_features, int cap_obs, int* feature_id, int* start_frame, int* solve_flag,
+                    double* estimated_depth, int* obs_offset, double* obs5);
 /* Headers[0 .. WINDOW_SIZE] as stamps in seconds (estimator.h:70): what setReloFrame compares frame_stamp with. */
 int ve_get_headers(const ve_estimator* e, double* stamps);
 int ve_set_relo_frame(ve_estimator* e, double frame_stamp, int frame_index, int n, const double* match_points, const double* relo_t,

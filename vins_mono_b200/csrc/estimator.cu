@@ -1683,6 +1683,33 @@ int ve_set_relo_frame(ve_estimator* e, double frame_stamp, int frame_index, int 
     return found;
 }
 
+int ve_get_features(const ve_estimator* e, int cap_features, int cap_obs, int* feature_id, int* start_frame, int* solve_flag,
+                    double* estimated_depth, int* obs_offset, double* obs5) {
+    if (!e) return VE_ERR_INVALID;
+    int nf = (int)e->feature.size(), no = 0;
+    for (auto& it : e->feature) no += (int)it.feature_per_frame.size();
+    if (cap_features <= 0 && cap_obs <= 0) return nf;  // size query
+    if (nf > cap_features || no > cap_obs || !obs_offset) return -nf - 1;
+    int k = 0, o = 0;
+    for (auto& it : e->feature) {
+        if (feature_id) feature_id[k] = it.feature_id;
+        if (start_frame) start_frame[k] = it.start_frame;
+        if (solve_flag) solve_flag[k] = it.solve_flag;
+        if (estimated_depth) estimated_depth[k] = it.estimated_depth;
+        obs_offset[k] = o;
+        for (auto& f : it.feature_per_frame) {
+            if (obs5) {
+                double* d = obs5 + 5 * (size_t)o;
+                d[0] = f.point.x; d[1] = f.point.y; d[2] = f.point.z; d[3] = f.u; d[4] = f.v;
+            }
+            o++;
+        }
+        k++;
+    }
+    obs_offset[k] = o;
+    return nf;
+}
+
 int ve_get_headers(const ve_estimator* e, double* stamps) {
     if (!e || !stamps) return VE_ERR_INVALID;
     for (int i = 0; i <= e->W; i++) stamps[i] = e->Headers[i];

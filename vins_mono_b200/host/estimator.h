@@ -8,6 +8,7 @@
 // `estimator.ric[0] * p + estimator.tic[0]`) compile unchanged; without Eigen, small stand-ins with the same accessors
 // (v[k], v.x(), m(r, c)) are used so that this header and its compile test need no third-party dependency.
 #pragma once
+#include <list>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -29,6 +30,7 @@ namespace vinsb200 {
 using Vector3d = Eigen::Vector3d;
 using Matrix3d = Eigen::Matrix3d;
 using Vector7d = Eigen::Matrix<double, 7, 1>;
+using Vector2d = Eigen::Vector2d;
 #else
 struct Vector3d {
     double v[3] = {0, 0, 0};
@@ -41,6 +43,8 @@ struct Vector3d {
     double z() const { return v[2]; }
     Vector3d operator+(const Vector3d& o) const { return Vector3d(v[0] + o.v[0], v[1] + o.v[1], v[2] + o.v[2]); }
     Vector3d operator-(const Vector3d& o) const { return Vector3d(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
+    Vector3d operator*(double s) const { return Vector3d(v[0] * s, v[1] * s, v[2] * s); }
+    double operator()(int i) const { return v[i]; }
 };
 struct Matrix3d {
     double m[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -50,6 +54,13 @@ struct Matrix3d {
         return Vector3d(m[0] * p[0] + m[1] * p[1] + m[2] * p[2], m[3] * p[0] + m[4] * p[1] + m[5] * p[2], m[6] * p[0] + m[7] * p[1] + m[8] * p[2]);
     }
 };
+struct Vector2d {
+    double v[2] = {0, 0};
+    double x() const { return v[0]; }
+    double y() const { return v[1]; }
+    double& operator[](int i) { return v[i]; }
+    double operator[](int i) const { return v[i]; }
+};
 struct Vector7d {
     double v[7] = {0, 0, 0, 0, 0, 0, 0};
     double& operator[](int i) { return v[i]; }
@@ -58,6 +69,27 @@ struct Vector7d {
     double operator()(int i) const { return v[i]; }
 };
 #endif
+
+// FeatureManager as far as the publishers read it (feature_manager.h:19-72; visualization.cpp:228-296, :352-397)
+struct FeaturePerFrame {
+    Vector3d point;
+    Vector2d uv;
+};
+struct FeaturePerId {
+    int feature_id = 0, start_frame = 0, used_num = 0, solve_flag = 0;
+    double estimated_depth = -1;
+    std::vector<FeaturePerFrame> feature_per_frame;
+    int endFrame() const { return start_frame + (int)feature_per_frame.size() - 1; }
+};
+struct FeatureManager {
+    std::list<FeaturePerId> feature;
+    int getFeatureCount() const {
+        int cnt = 0;
+        for (const auto& it : feature) cnt += (int)it.feature_per_frame.size() >= 2 && it.start_frame < window_size - 2;
+        return cnt;
+    }
+    int window_size = 10;
+};
 
 class Estimator {
   public:
@@ -130,6 +162,8 @@ class Estimator {
     Vector3d acc_0, gyr_0;
     std::vector<double> Headers;  // stamps (the reference keeps std_msgs::Header objects)
     double td = 0;
+    std::vector<Vector3d> key_poses;  // Ps[0 .. WINDOW_SIZE] while NON_LINEAR (estimator.cpp:208-210)
+    FeatureManager f_manager;         // refreshed after every processImage
     bool relocalization_info = false;
     double relo_frame_stamp = 0, relo_frame_index = 0, relo_relative_yaw = 0;  // (the reference declares relo_frame_index as double)
     int relo_frame_local_index = 0;
@@ -170,6 +204,33 @@ class Estimator {
         int info[10];
         double c[2];
         ve_info(h_, info, c);
+        key_poses.clear();
+        if (info[0])
+            for (size_t i = 0; i < Ps.size(); i++) key_poses.push_back(Ps[i]);
+        {
+            f_manager.window_size = cfg_.window_size;
+            f_manager.feature.clear();
+            const int nf = ve_get_features(h_, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+            if (nf > 0) {
+                const int cap_obs = nf * (cfg_.window_size + 1);
+                std::vector<int> id(nf), st(nf), sf(nf), off(nf + 1);
+                std::vector<double> dep(nf), obs(5 * (size_t)cap_obs);
+                if (ve_get_features(h_, nf, cap_obs, id.data(), st.data(), sf.data(), dep.data(), off.data(), obs.data()) == nf)
+                    for (int k = 0; k < nf; k++) {
+                        FeaturePerId f;
+                        f.feature_id = id[k]; f.start_frame = st[k]; f.solve_flag = sf[k]; f.estimated_depth = dep[k];
+                        for (int o = off[k]; o < off[k + 1]; o++) {
+                            FeaturePerFrame pf;
+                            for (int c = 0; c < 3; c++) pf.point[c] = obs[5 * (size_t)o + c];
+                            pf.uv[0] = obs[5 * (size_t)o + 3];
+                            pf.uv[1] = obs[5 * (size_t)o + 4];
+                            f.feature_per_frame.push_back(pf);
+                        }
+                        f.used_num = (int)f.feature_per_frame.size();
+                        f_manager.feature.push_back(std::move(f));
+                    }
+            }
+        }
         double ro[24];
         ve_get_relocalization(h_, ro);
         for (int r = 0; r < 3; r++) {

@@ -56,6 +56,21 @@ int main() {
         const double relo_sum = correct_t[0] + estimator.relo_relative_t[1] + estimator.relo_relative_q[0] + estimator.relo_relative_yaw +
                                 estimator.relo_frame_index + estimator.relo_frame_stamp + (estimator.relocalization_info ? 1.0 : 0.0);
         (void)relo_sum;
+        // pubKeyPoses / pubPointCloud / pubKeyframe (utility/visualization.cpp:176-206, 228-296, 352-397)
+        double cloud = 0;
+        for (size_t i = 0; i < estimator.key_poses.size(); i++) cloud += estimator.key_poses[i].x();
+        for (auto& it_per_id : estimator.f_manager.feature) {
+            int used_num = it_per_id.feature_per_frame.size();
+            if (!(used_num >= 2 && it_per_id.start_frame < WINDOW_SIZE - 2)) continue;
+            if (it_per_id.start_frame > WINDOW_SIZE * 3.0 / 4.0 || it_per_id.solve_flag != 1) continue;
+            int imu_i = it_per_id.start_frame;
+            Vector3d pts_i = it_per_id.feature_per_frame[0].point * it_per_id.estimated_depth;
+            Vector3d w_pts_i = estimator.Rs[imu_i] * (estimator.ric[0] * pts_i + estimator.tic[0]) + estimator.Ps[imu_i];
+            int imu_j = WINDOW_SIZE - 2 - it_per_id.start_frame;
+            cloud += w_pts_i(0) + it_per_id.feature_per_frame[imu_j < used_num ? imu_j : 0].uv.x() + it_per_id.feature_id;
+        }
+        cloud += estimator.f_manager.getFeatureCount();
+        (void)cloud;
         const bool nonlinear = estimator.solver_flag == vinsb200::Estimator::SolverFlag::NON_LINEAR;
         estimator.clearState();
         estimator.setParameter();
