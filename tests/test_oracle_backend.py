@@ -191,3 +191,40 @@ def test_small_dense_kernels():
         assert np.allclose(w, np.linalg.eigvalsh(A), rtol=1e-10, atol=1e-9 * np.abs(A).max())
         assert np.allclose(V @ np.diag(w) @ V.T, A, rtol=1e-10, atol=1e-9 * np.abs(A).max())
         assert np.allclose(V.T @ V, np.eye(40), atol=1e-12)
+
+
+def test_oracle_relocalisation_recovers_injected_drift():
+    """The oracle's setReloFrame / relo_Pose block / drift bookkeeping (estimator.cpp:1128-1146, :769-801, :598-617) against physics: a
+    loop message whose old key frame is reported 7 degrees of yaw and (0.4, -0.3, 0.1) m away from where the odometry frame puts it
+    yields that drift (a single solve starts relo_Pose at the window frame's own pose, 2 m off, and gets most of the way)."""
+    from harness import pipeline, synth
+    seq = synth.Sequence(seed=0, duration=5.0)
+    msgs = synth.track_messages(seq, 34, max_feats=150)
+    est = orc.OracleEstimator(orc.be_config())
+    est.set_seed(pipeline.gt_seed_rows(seq, [m[0] for m in msgs]), seq.ba, seq.bg)
+    feeder = pipeline.ImuFeeder(*seq.imu())
+    a = np.radians(7.0)
+    D = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+    t_drift = np.array([0.4, -0.3, 0.1])
+    before = None
+    for k, (stamp, ids, d) in enumerate(msgs):
+        feeder.feed(est, stamp)
+        if k == 29:  # a stamp that is not in the window: nothing is armed
+            mp, p_old, R_old = synth.loop_frame_matches(seq, 1.0, msgs[24][1])
+            est.setReloFrame(msgs[24][0] + 0.0123, 3, mp, D @ p_old + t_drift, D @ R_old)
+            assert not est.relo()["pending"]
+        if k == 30:
+            mp, p_old, R_old = synth.loop_frame_matches(seq, 1.0, msgs[25][1], pixel_sigma=0.3)
+            est.setReloFrame(msgs[25][0], 3, mp, D @ p_old + t_drift, D @ R_old)
+            r = est.relo()
+            assert r["pending"] and 0 <= r["local_index"] < 10 and r["solves"] == 0
+            before = est.info()["visual"]
+        est.processImage(ids, d, stamp)
+        if k == 30:
+            r = est.relo()
+            assert not r["pending"] and r["solves"] == 1 and 20 <= r["factors"] <= len(mp)
+            assert abs(est.info()["visual"] - before) < 200     # f_m_cnt counts the window's own factors only
+            yaw = np.degrees(np.arctan2(r["drift_correct_r"][1, 0], r["drift_correct_r"][0, 0]))
+            assert abs(yaw - 7.0) < 1.5 and np.abs(r["drift_correct_t"] - t_drift).max() < 0.08
+            assert np.array_equal(r["drift_correct_r"][2], [0, 0, 1.0]) and abs(np.linalg.norm(r["relo_relative_q"]) - 1) < 1e-12
+    assert est.relo()["solves"] == 1 and est.info()["solver_flag"] == 1
