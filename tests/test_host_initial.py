@@ -239,3 +239,68 @@ def test_ransac_model_matches_opencv_at_the_initialisation_threshold():
                                                      C.c_double(0.99), st.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p)) == 1
         assert np.array_equal(m.ravel() != 0, st != 0)
         assert np.abs(E - F.reshape(3, 3)).max() < 1e-6 * max(1.0, np.abs(E).max())
+
+
+# ---- properties on exact data (general 3-D scenes, no noise): the stages recover the geometry they were given ----------------------
+def _random_scene(rng, n=80):
+    from scipy.spatial.transform import Rotation
+    X = np.c_[rng.uniform(-3, 3, n), rng.uniform(-2, 2, n), rng.uniform(3, 9, n)]     # a cloud with real depth variation
+    R = Rotation.from_rotvec(rng.normal(0, 0.12, 3)).as_matrix()                       # camera 1 expressed in camera 0
+    t = rng.normal(0, 0.4, 3) + np.array([0.5, 0, 0])
+    X1 = (X - t) @ R                                                                   # R^T (X - t)
+    return X, R, t, X[:, :2] / X[:, 2:3], X1[:, :2] / X1[:, 2:3]
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_relative_rt_recovers_exact_two_view_geometry(seed):
+    rng = np.random.default_rng(100 + seed)
+    X, R, t, x0, x1 = _random_scene(rng)
+    ok, Rot, Tr, cnt = ve.debug_relative_rt(np.c_[x0, x1])
+    ok_c, Rot_c, Tr_c, cnt_c = oi.solve_relative_rt(np.c_[x0, x1])
+    assert ok and ok_c and cnt == cnt_c == len(X)           # float32 rounding of the inputs stays far below the threshold
+    assert np.abs(Rot - Rot_c).max() < 1e-8 and np.abs(Tr - Tr_c).max() < 1e-8
+    # the reference's convention: Rotation = pose of camera 1 in camera 0, Translation its (unit) position
+    assert np.abs(Rot - R).max() < 1e-4 and np.abs(Tr - t / np.linalg.norm(t)).max() < 1e-3
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_solve_pnp_recovers_exact_pose(seed):
+    rng = np.random.default_rng(200 + seed)
+    X, R, t, _, x1 = _random_scene(rng, 30)
+    from scipy.spatial.transform import Rotation
+    R_wc, t_wc = R.T, -R.T @ t                               # world (= camera 0) -> camera 1
+    R0 = Rotation.from_rotvec(rng.normal(0, 0.08, 3)).as_matrix() @ R_wc
+    ok, Rp, tp = ve.debug_solve_pnp(X, x1, R0, t_wc + rng.normal(0, 0.2, 3))
+    assert ok and np.abs(Rp - R_wc).max() < 2e-6 and np.abs(tp - t_wc).max() < 2e-5   # inputs pass through float32
+    assert abs(np.linalg.det(Rp) - 1) < 1e-12
+
+
+def test_sfm_construct_recovers_a_known_structure():
+    """Five cameras on a curved path over a general point cloud, exact observations: poses and points come back in the frame of
+    camera l with |T_last| = 1 (the gauge GlobalSFM fixes)."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(7)
+    n_frames, n_pts = 5, 90
+    X = np.c_[rng.uniform(-3, 3, n_pts), rng.uniform(-2, 2, n_pts), rng.uniform(4, 10, n_pts)]
+    Rs = [Rotation.from_rotvec([0.02 * k, 0.05 * k, -0.01 * k]).as_matrix() for k in range(n_frames)]   # camera k in world
+    Ts = [np.array([0.25 * k, 0.05 * k * k, 0.03 * k]) for k in range(n_frames)]
+    tracks = []
+    for i, p in enumerate(X):
+        xy = []
+        for k in range(n_frames):
+            pc = Rs[k].T @ (p - Ts[k])
+            xy.append(pc[:2] / pc[2])
+        tracks.append((i, 0, np.array(xy)))
+    l = 0
+    rel_R = Rs[l].T @ Rs[-1]
+    rel_T = Rs[l].T @ (Ts[-1] - Ts[l])
+    scale = np.linalg.norm(rel_T)
+    out = ve.debug_sfm_construct(n_frames, l, rel_R, rel_T / scale, tracks, function_tolerance=1e-14)
+    assert out["ok"] and len(out["points"]) == n_pts and out["cost"] < 1e-12
+    for k in range(n_frames):
+        q = out["q"][k]
+        Rk = oi.quat_to_R(q)
+        assert np.abs(Rk - Rs[l].T @ Rs[k]).max() < 1e-5
+        assert np.abs(out["T"][k] - Rs[l].T @ (Ts[k] - Ts[l]) / scale).max() < 1e-5
+    worst = max(np.abs(out["points"][i] - Rs[l].T @ (X[i] - Ts[l]) / scale).max() for i in range(n_pts))
+    assert worst < 1e-4
