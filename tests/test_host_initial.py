@@ -304,3 +304,23 @@ def test_sfm_construct_recovers_a_known_structure():
         assert np.abs(out["T"][k] - Rs[l].T @ (Ts[k] - Ts[l]) / scale).max() < 1e-5
     worst = max(np.abs(out["points"][i] - Rs[l].T @ (X[i] - Ts[l]) / scale).max() for i in range(n_pts))
     assert worst < 1e-4
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_whole_initialisation_is_metric_on_exact_data(seed):
+    """No pixel noise, no IMU noise, no accelerometer bias (the one quantity the linear alignment does not model): scale, body-frame
+    velocities, gravity and the gyroscope bias come out at their true values up to the mid-point integration error."""
+    seq = synth.Sequence(seed=seed, duration=3.0, imu_noise=False)
+    seq.ba = np.zeros(3)
+    headers, frames, tracks = init_inputs.first_window(seq, pixel_sigma=0.0)
+    res = ve.debug_initial_structure(headers, frames, tracks, synth.RIC, synth.TIC, synth.G_NORM, function_tolerance=1e-14)
+    assert res["code"] == 0
+    pose = [seq.pose(t) for t in headers]
+    cam = [p[0] + p[1] @ synth.TIC for p in pose]
+    l = res["l"]
+    assert abs(res["x"][-1] / np.linalg.norm(cam[10] - cam[l]) - 1) < 1e-4
+    for k in range(11):
+        assert np.abs(res["x"][3 * k: 3 * k + 3] - pose[k][1].T @ pose[k][2]).max() < 1e-4      # R_wb^T v_w
+    assert np.abs(res["delta_bg"] - seq.bg).max() < 1e-5
+    g_true = (pose[l][1] @ synth.RIC).T @ np.array([0, 0, synth.G_NORM])
+    assert np.abs(res["g"] - g_true).max() < 1e-3
